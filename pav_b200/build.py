@@ -1,0 +1,58 @@
+"""Build libpavgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m pav_b200.build [--force]
+
+The shared library lands at pav_b200/libpavgpu.so (git-ignored, travels with gpurun snapshots).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libpavgpu.so')
+SOURCES = ['seqstore.cu', 'cigar.cu', 'density.cu', 'nccl_bcast.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
+         '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO, 'include', 'pavgpu.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    for s in srcs:
+        o = os.path.join(HERE, 'build', os.path.basename(s) + '.o')
+        objs.append(o)
+        cmd = [NVCC] + FLAGS + ['-I', os.path.join(REPO, 'include'), '-I', CSRC, '-c', s, '-o', o]
+        if verbose:
+            cmd.insert(1, '-Xptxas')
+            cmd.insert(2, '-v')
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out.decode())
+        if p.returncode:
+            raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
+    tmp = LIB + f'.{os.getpid()}.tmp'
+    cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static', '-ldl', '-lrt', '-lpthread']
+    subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,664 @@
+// cigar.cu -- Path A: the per-alignment-record CIGAR walk on the GPU.
+//
+// Reference semantics: pavlib/cigarcall.py:50-311 (walk), pavlib/call.py:542-647 (homology),
+// pavlib/align/align.py:286-322 (tokenizer, host side here). See SURVEY.md appendix A.1.
+//
+// Design (B200-first, not "one Python loop per record"):
+//   * all records' ops are flattened into one array of packed 4-bit-op words ((len << 4) | code);
+//     a warp owns a chunk of 128 consecutive ops (one 128-bit load per lane), chunks may span
+//     record boundaries, so a chromosome-scale record and ten thousand tiny records balance alike;
+//   * the walk's loop-carried state (pos_ref, pos_tig) is a *segmented* prefix sum over ops and the
+//     output slot of every row is a plain prefix sum of row counts, so rows land in the reference's
+//     emission order (record, op, base) without atomics or a sort:
+//       K1 cigar_reduce_kernel : per-chunk aggregates (warp shuffles only)
+//       K2 chunk_scan_kernel   : exclusive scan of the chunk aggregates (segmented for positions)
+//       K3 cigar_emit_kernel   : re-scan inside the warp and emit SNV rows + indel stubs
+//       K4 homology_kernel     : left-shift + four breakpoint-homology scans per indel on the packed
+//                                2-bit planes (data-dependent loops, kept out of K3 to avoid divergence)
+//   * SNV rows need no sequence access at all: REF/ALT characters (original case, IUPAC) are sliced on
+//     the host from the FASTA bytes with the coordinates computed here.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int OPS_PER_LANE = 4;
+constexpr int CHUNK = 32 * OPS_PER_LANE;  // ops per warp
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+constexpr uint32_t REF_ADV_MASK = (1u << PAVGPU_OP_D) | (1u << PAVGPU_OP_EQ) | (1u << PAVGPU_OP_X);
+constexpr uint32_t QRY_ADV_MASK = (1u << PAVGPU_OP_I) | (1u << PAVGPU_OP_S) | (1u << PAVGPU_OP_H) | (1u << PAVGPU_OP_EQ) | (1u << PAVGPU_OP_X);
+constexpr uint32_t LEGAL_MASK = REF_ADV_MASK | QRY_ADV_MASK;
+
+struct IndelStub {  // 32 B, written by K3, consumed by K4
+    int32_t rec, op_idx, svtype, n;
+    int32_t pos_ref, pos_qry, eq_before, pad;
+};
+
+struct RecView {
+    const int32_t *ref_id;
+    const int32_t *qry_id;
+    const int32_t *pos;
+    const uint8_t *rev;
+    const int64_t *op_off;  // n_rec + 1
+    int32_t n_rec;
+};
+
+// Largest r with op_off[r] <= g (records with zero ops are skipped naturally).
+__device__ __forceinline__ int32_t find_rec(const int64_t *__restrict__ op_off, int32_t n_rec, int64_t g)
+{
+    int32_t lo = 0, hi = n_rec;  // invariant: op_off[lo] <= g < op_off[hi]
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (__ldg(op_off + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct LaneOps {
+    uint32_t op[OPS_PER_LANE];
+    int nvalid;
+    int64_t g0;
+    int32_t rec0;
+};
+
+__device__ __forceinline__ LaneOps load_lane(const uint32_t *__restrict__ ops, int64_t n_ops, const RecView &rv, int64_t chunk, int lane)
+{
+    LaneOps L;
+    L.g0 = chunk * CHUNK + (int64_t)lane * OPS_PER_LANE;
+    int64_t rem = n_ops - L.g0;
+    L.nvalid = rem <= 0 ? 0 : (rem >= OPS_PER_LANE ? OPS_PER_LANE : (int)rem);
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (L.nvalid > 0) raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));  // buffer is padded to CHUNK
+    L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
+    L.rec0 = L.nvalid > 0 ? find_rec(rv.op_off, rv.n_rec, L.g0) : 0;
+    return L;
+}
+
+// Segmented inclusive warp scan of (flag, r, q): values accumulate until a lane whose own prefix
+// already contains a segment head.
+__device__ __forceinline__ void warp_seg_scan(int lane, int &f, int &r, int &q)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int f2 = __shfl_up_sync(FULL, f, d), r2 = __shfl_up_sync(FULL, r, d), q2 = __shfl_up_sync(FULL, q, d);
+        if (lane >= d) {
+            if (!f) { r += r2; q += q2; }
+            f |= f2;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_inc_scan(int lane, uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v2 = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += v2;
+    }
+    return v;
+}
+
+// Lane-local pass over up to 4 ops: position advances since the last record head, row counts.
+__device__ __forceinline__ void lane_aggregate(const LaneOps &L, const RecView &rv, int &f, int &r, int &q, uint32_t &ns, uint32_t &ni)
+{
+    f = 0; r = 0; q = 0; ns = 0; ni = 0;
+    int32_t rec = L.rec0;
+    int64_t next_off = L.nvalid > 0 ? __ldg(rv.op_off + rec + 1) : 0;
+    int64_t cur_off = L.nvalid > 0 ? __ldg(rv.op_off + rec) : 0;
+#pragma unroll
+    for (int j = 0; j < OPS_PER_LANE; j++) {
+        if (j < L.nvalid) {
+            int64_t g = L.g0 + j;
+            while (g >= next_off) { ++rec; cur_off = next_off; next_off = __ldg(rv.op_off + rec + 1); }
+            if (g == cur_off) { f = 1; r = 0; q = 0; }
+            uint32_t code = L.op[j] & 15u, len = L.op[j] >> 4;
+            uint32_t bit = 1u << code;
+            if (bit & REF_ADV_MASK) r += (int)len;
+            if (bit & QRY_ADV_MASK) q += (int)len;
+            if (code == PAVGPU_OP_X) ns += len;
+            if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) ni += 1;
+        }
+    }
+}
+
+// K1 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+cigar_reduce_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks,
+                    int4 *__restrict__ agg, uint2 *__restrict__ cnt)
+{
+    int lane = threadIdx.x & 31;
+    int64_t chunk = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (chunk >= n_chunks) return;
+    LaneOps L = load_lane(ops, n_ops, rv, chunk, lane);
+    int f, r, q; uint32_t ns, ni;
+    lane_aggregate(L, rv, f, r, q, ns, ni);
+    warp_seg_scan(lane, f, r, q);
+    ns = warp_inc_scan(lane, ns);
+    ni = warp_inc_scan(lane, ni);
+    if (lane == 31) {
+        agg[chunk] = make_int4(r, q, f, 0);
+        cnt[chunk] = make_uint2(ns, ni);
+    }
+}
+
+// K2 ---------------------------------------------------------------------------------------------
+// Exclusive scan over chunk aggregates in one CTA: each thread owns a contiguous slice (serial
+// reduce), the 1024 slice totals are combined through shared memory, then each thread rescans its
+// slice. n_chunks = n_ops / 128, so even a 60 M-op haplotype is < 0.5 M elements.
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+chunk_scan_kernel(const int4 *__restrict__ agg, const uint2 *__restrict__ cnt, int64_t n_chunks,
+                  int2 *__restrict__ pre_rq, longlong2 *__restrict__ pre_cnt, int64_t *__restrict__ totals)
+{
+    __shared__ int s_f[SCAN_THREADS], s_r[SCAN_THREADS], s_q[SCAN_THREADS];
+    __shared__ long long s_ns[SCAN_THREADS], s_ni[SCAN_THREADS];
+    int t = threadIdx.x;
+    int64_t per = (n_chunks + SCAN_THREADS - 1) / SCAN_THREADS;
+    int64_t lo = (int64_t)t * per, hi = min(lo + per, n_chunks);
+    int f = 0, r = 0, q = 0;
+    long long ns = 0, ni = 0;
+    for (int64_t c = lo; c < hi; c++) {
+        int4 a = agg[c];
+        uint2 k = cnt[c];
+        if (a.z) { f = 1; r = a.x; q = a.y; } else { r += a.x; q += a.y; }
+        ns += k.x; ni += k.y;
+    }
+    s_f[t] = f; s_r[t] = r; s_q[t] = q; s_ns[t] = ns; s_ni[t] = ni;
+    __syncthreads();
+    // inclusive scan over the 1024 slice totals: warp 0 does 32 serial steps per lane + warp scan
+    if (t < 32) {
+        int base = t * 32;
+        int lf = 0, lr = 0, lq = 0;
+        long long lns = 0, lni = 0;
+        for (int i = 0; i < 32; i++) {
+            int idx = base + i;
+            if (s_f[idx]) { lf = 1; lr = s_r[idx]; lq = s_q[idx]; } else { lr += s_r[idx]; lq += s_q[idx]; }
+            lns += s_ns[idx]; lni += s_ni[idx];
+            s_f[idx] = lf; s_r[idx] = lr; s_q[idx] = lq; s_ns[idx] = lns; s_ni[idx] = lni;  // inclusive within the group
+        }
+        int gf = lf, gr = lr, gq = lq;
+        warp_seg_scan(t, gf, gr, gq);
+        long long gns = lns, gni = lni;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            long long a2 = __shfl_up_sync(FULL, gns, d), b2 = __shfl_up_sync(FULL, gni, d);
+            if (t >= d) { gns += a2; gni += b2; }
+        }
+        // exclusive prefix of this group of 32 slices
+        int ef = __shfl_up_sync(FULL, gf, 1), er = __shfl_up_sync(FULL, gr, 1), eq = __shfl_up_sync(FULL, gq, 1);
+        long long ens = __shfl_up_sync(FULL, gns, 1), eni = __shfl_up_sync(FULL, gni, 1);
+        if (t == 0) { ef = 0; er = 0; eq = 0; ens = 0; eni = 0; }
+        for (int i = 0; i < 32; i++) {
+            int idx = base + i;
+            if (!s_f[idx]) { s_r[idx] += er; s_q[idx] += eq; }
+            s_f[idx] |= ef;
+            s_ns[idx] += ens; s_ni[idx] += eni;
+        }
+        if (t == 31) { totals[0] = gns; totals[1] = gni; }
+    }
+    __syncthreads();
+    // exclusive prefix for this thread's slice = inclusive value of slice t-1
+    if (t > 0) { r = s_r[t - 1]; q = s_q[t - 1]; ns = s_ns[t - 1]; ni = s_ni[t - 1]; }
+    else { r = 0; q = 0; ns = 0; ni = 0; }
+    for (int64_t c = lo; c < hi; c++) {
+        int4 a = agg[c];
+        uint2 k = cnt[c];
+        pre_rq[c] = make_int2(r, q);
+        pre_cnt[c] = make_longlong2(ns, ni);
+        if (a.z) { r = a.x; q = a.y; } else { r += a.x; q += a.y; }
+        ns += k.x; ni += k.y;
+    }
+}
+
+// K3 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks,
+                  const int2 *__restrict__ pre_rq, const longlong2 *__restrict__ pre_cnt,
+                  const int64_t *__restrict__ qry_len, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
+                  unsigned long long *__restrict__ first_illegal)
+{
+    int lane = threadIdx.x & 31;
+    int64_t chunk = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (chunk >= n_chunks) return;
+    LaneOps L = load_lane(ops, n_ops, rv, chunk, lane);
+    int f, r, q; uint32_t ns, ni;
+    lane_aggregate(L, rv, f, r, q, ns, ni);
+    int fi = f, ri = r, qi = q;
+    warp_seg_scan(lane, fi, ri, qi);
+    uint32_t nsi = warp_inc_scan(lane, ns), nii = warp_inc_scan(lane, ni);
+    // exclusive prefixes for this lane
+    int ef = __shfl_up_sync(FULL, fi, 1), er = __shfl_up_sync(FULL, ri, 1), eq = __shfl_up_sync(FULL, qi, 1);
+    if (lane == 0) { ef = 0; er = 0; eq = 0; }
+    int2 carry = pre_rq[chunk];
+    longlong2 cbase = pre_cnt[chunk];
+    int run_r = ef ? er : er + carry.x;
+    int run_q = ef ? eq : eq + carry.y;
+    long long snv_cur = cbase.x + (long long)(nsi - ns);
+    long long indel_cur = cbase.y + (long long)(nii - ni);
+    // previous op (for the "last op was '='" left-shift rule, cigarcall.py:149,225,310-311)
+    uint32_t prev_op = __shfl_up_sync(FULL, L.op[OPS_PER_LANE - 1], 1);
+    if (lane == 0) prev_op = (L.nvalid > 0 && L.g0 > 0) ? __ldg(ops + L.g0 - 1) : 0u;
+    if (L.nvalid == 0) return;
+
+    int32_t rec = L.rec0;
+    int64_t cur_off = __ldg(rv.op_off + rec), next_off = __ldg(rv.op_off + rec + 1);
+    int32_t rpos = __ldg(rv.pos + rec);
+    int rrev = __ldg(rv.rev + rec);
+    int32_t qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+#pragma unroll
+    for (int j = 0; j < OPS_PER_LANE; j++) {
+        if (j < L.nvalid) {
+            int64_t g = L.g0 + j;
+            bool moved = false;
+            while (g >= next_off) { ++rec; cur_off = next_off; next_off = __ldg(rv.op_off + rec + 1); moved = true; }
+            if (moved) {
+                rpos = __ldg(rv.pos + rec);
+                rrev = __ldg(rv.rev + rec);
+                qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+            }
+            bool head = (g == cur_off);
+            if (head) { run_r = 0; run_q = 0; }
+            uint32_t op = L.op[j], code = op & 15u, len = op >> 4;
+            int32_t op_idx = (int32_t)(g - cur_off);
+            int32_t pos_ref = rpos + run_r, pos_qry = run_q;
+            if (code == PAVGPU_OP_X) {
+                for (uint32_t i = 0; i < len; i++) {
+                    int32_t t = pos_qry + (int32_t)i;
+                    snv_rows[snv_cur + i] = make_int4(pos_ref + (int32_t)i, rrev ? qlen - 1 - t : t, rec, op_idx);
+                }
+                snv_cur += len;
+            } else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) {
+                IndelStub s;
+                s.rec = rec; s.op_idx = op_idx; s.svtype = (code == PAVGPU_OP_D); s.n = (int32_t)len;
+                s.pos_ref = pos_ref; s.pos_qry = pos_qry;
+                s.eq_before = (!head && (prev_op & 15u) == PAVGPU_OP_EQ) ? (int32_t)(prev_op >> 4) : 0;
+                s.pad = 0;
+                int4 *dst = reinterpret_cast<int4 *>(stubs + indel_cur);
+                dst[0] = make_int4(s.rec, s.op_idx, s.svtype, s.n);
+                dst[1] = make_int4(s.pos_ref, s.pos_qry, s.eq_before, 0);
+                ++indel_cur;
+            } else if (!((1u << code) & LEGAL_MASK)) {
+                atomicMin(first_illegal, (unsigned long long)g);
+            }
+            uint32_t bit = 1u << code;
+            if (bit & REF_ADV_MASK) run_r += (int)len;
+            if (bit & QRY_ADV_MASK) run_q += (int)len;
+            prev_op = op;
+        }
+    }
+}
+
+// K4 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, RecView rv, SeqPlanes ref, SeqPlanes qry,
+                pavgpu_indel_row *__restrict__ rows)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_indel) return;
+    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
+    int4 a = __ldg(sp4), b = __ldg(sp4 + 1);
+    int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
+    int32_t rid = __ldg(rv.ref_id + rec), qid = __ldg(rv.qry_id + rec);
+    OSeq R{ref.pack2, ref.nmask, __ldg(ref.off + rid), __ldg(ref.len + rid), 0};
+    OSeq Q{qry.pack2, qry.nmask, __ldg(qry.off + qid), __ldg(qry.len + qid), (int)__ldg(rv.rev + rec)};
+    int32_t L = (int32_t)Q.len;
+    pavgpu_indel_row o;
+    o.rec = rec; o.op_idx = op_idx; o.svtype = svtype; o.svlen = n; o.pad[0] = o.pad[1] = 0;
+    if (svtype == 0) {  // INS, cigarcall.py:141-213
+        int ls = 0;
+        if (eqb > 0) ls = min(eqb, dev_left_homology(R, (int64_t)pr - 1, Q, pq, n));
+        int32_t sp = pr - ls, sq = pq - ls;
+        o.left_shift = ls;
+        o.pos = sp; o.end = sp + 1;
+        if (Q.rev) { o.qry_end = L - sq; o.qry_pos = o.qry_end - n; } else { o.qry_pos = sq; o.qry_end = sq + n; }
+        o.hom_ref_l = dev_left_homology(R, (int64_t)sp - 1, Q, sq, n);
+        o.hom_ref_r = dev_right_homology(R, sp, Q, sq, n);
+        o.hom_tig_l = dev_left_homology(Q, (int64_t)sq - 1, Q, sq, n);
+        o.hom_tig_r = dev_right_homology(Q, (int64_t)sq + n, Q, sq, n);
+        o.seq_start = sq;
+    } else {  // DEL, cigarcall.py:217-282 (POS/END/SEQ stay unshifted)
+        int ls = 0;
+        if (eqb > 0) ls = min(eqb, dev_left_homology(R, (int64_t)pr - 1, R, pr, n));
+        int32_t sp = pr - ls, se = sp + n, sq = pq - ls;
+        o.left_shift = ls;
+        o.pos = pr; o.end = pr + n;
+        o.qry_pos = Q.rev ? L - sq : sq;
+        o.qry_end = o.qry_pos + 1;
+        o.hom_ref_l = dev_left_homology(R, (int64_t)sp - 1, R, pr, n);
+        o.hom_ref_r = dev_right_homology(R, se, R, pr, n);
+        o.hom_tig_l = dev_left_homology(Q, (int64_t)sq - 1, R, pr, n);
+        o.hom_tig_r = dev_right_homology(Q, sq, R, pr, n);
+        o.seq_start = pr;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(o.rec, o.op_idx, o.svtype, o.svlen);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.left_shift, o.hom_ref_l, o.hom_ref_r, o.hom_tig_l);
+    dst[3] = make_int4(o.hom_tig_r, o.seq_start, 0, 0);
+}
+
+__global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,
+                                      int32_t *__restrict__ left, int32_t *__restrict__ right)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OSeq T{st.pack2, st.nmask, st.off[0], st.len[0], 0};
+    OSeq V{st.pack2, st.nmask, st.off[1], st.len[1], 0};
+    int64_t p = pos[i];
+    left[i] = (p < T.len) ? dev_left_homology(T, p, V, 0, sv_len) : -1;
+    right[i] = (p >= 0) ? dev_right_homology(T, p, V, 0, sv_len) : -1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+struct pavgpu_cigar_batch {
+    pavgpu_ctx *ctx;
+    int32_t n_rec;
+    int64_t n_ops, n_chunks;
+    int32_t *d_ref_id, *d_qry_id, *d_pos;
+    uint8_t *d_rev;
+    int64_t *d_op_off;
+    uint32_t *d_ops;
+    int4 *d_agg;
+    uint2 *d_cnt;
+    int2 *d_pre_rq;
+    longlong2 *d_pre_cnt;
+    int64_t *d_totals;                   // [0] n_snv, [1] n_indel
+    unsigned long long *d_first_illegal;
+    int4 *d_snv; int64_t cap_snv;
+    IndelStub *d_stub; pavgpu_indel_row *d_indel; int64_t cap_indel;
+    int64_t n_snv, n_indel;
+    unsigned long long first_illegal;
+    bool ran;
+    float ms_h2d;
+    // host copies for error explanation
+    std::vector<uint32_t> h_ops;
+    std::vector<int64_t> h_op_off;
+    std::vector<int32_t> h_pos;
+};
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_parse(const char *text, const int64_t *text_off, int32_t n_rec, uint32_t **ops_out,
+                                  int64_t *op_off_out, pavgpu_parse_err *err)
+{
+    if (!ops_out || !op_off_out || (n_rec > 0 && (!text || !text_off))) { pav_set_error("cigar_parse: bad argument"); return PAVGPU_ERR_ARG; }
+    if (err) { err->code = 0; err->rec = -1; err->op_index = 0; err->text_pos = 0; err->ch = 0; }
+    // every op needs >= 2 characters
+    int64_t total_text = n_rec > 0 ? text_off[n_rec] - text_off[0] : 0;
+    size_t cap = (size_t)(total_text / 2 + 4);
+    uint32_t *ops = (uint32_t *)malloc(cap * sizeof(uint32_t));
+    if (!ops) { pav_set_error("cigar_parse: out of memory"); return PAVGPU_ERR_NOMEM; }
+    static const signed char code_of[128] = {
+        -1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, -1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,
+        -1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, -1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, 7,-1,-1,   // '=' = 61
+        -1,-1,-1,-1, 2,-1,-1,-1, 5, 1,-1,-1,-1, 0, 3,-1,  6,-1,-1, 4,-1,-1,-1,-1, 8,-1,-1,-1,-1,-1,-1,-1,   // D H I M N P S X
+        -1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1, -1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1,-1};
+    int64_t n = 0;
+    bool failed = false;
+    for (int32_t r = 0; r < n_rec; r++) {
+        op_off_out[r] = n;
+        if (failed) continue;  // records after a malformed one are never reached by the reference
+        const char *s = text + text_off[r];
+        int64_t len = text_off[r + 1] - text_off[r], p = 0;
+        int64_t first = n;
+        while (p < len) {
+            int64_t q = p;
+            uint64_t v = 0;
+            while (q < len && s[q] >= '0' && s[q] <= '9') { v = v * 10 + (uint64_t)(s[q] - '0'); q++; }
+            int ecode = 0;
+            if (q >= len) ecode = 4;
+            else if (q == p) ecode = 2;
+            else if ((unsigned char)s[q] >= 128 || code_of[(unsigned char)s[q]] < 0) ecode = 3;
+            if (ecode) {
+                if (err) { err->code = ecode; err->rec = r; err->op_index = n - first; err->text_pos = (ecode == 4) ? q : p; err->ch = (unsigned char)s[p]; }
+                failed = true;
+                break;
+            }
+            if (v >= (1ull << 28)) {
+                free(ops);
+                pav_set_error("cigar_parse: op length %llu in record %d exceeds 2^28-1", (unsigned long long)v, r);
+                return PAVGPU_ERR_ARG;
+            }
+            ops[n++] = (uint32_t)(v << 4) | (uint32_t)code_of[(unsigned char)s[q]];
+            p = q + 1;
+        }
+    }
+    op_off_out[n_rec] = n;
+    *ops_out = ops;
+    return PAVGPU_OK;
+}
+
+static void batch_release(pavgpu_cigar_batch *b)
+{
+    cudaFree(b->d_ref_id); cudaFree(b->d_qry_id); cudaFree(b->d_pos); cudaFree(b->d_rev); cudaFree(b->d_op_off);
+    cudaFree(b->d_ops); cudaFree(b->d_agg); cudaFree(b->d_cnt); cudaFree(b->d_pre_rq); cudaFree(b->d_pre_cnt);
+    cudaFree(b->d_totals); cudaFree(b->d_first_illegal); cudaFree(b->d_snv); cudaFree(b->d_stub); cudaFree(b->d_indel);
+}
+
+extern "C" __attribute__((visibility("default"))) void pavgpu_cigar_batch_free(pavgpu_cigar_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    batch_release(b);
+    delete b;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_id, const int32_t *qry_seq_id,
+                                         const int32_t *pos, const uint8_t *rev, const uint32_t *ops, const int64_t *op_off,
+                                         pavgpu_cigar_batch **out)
+{
+    if (!ctx || !out || n_rec < 0 || !op_off || (n_rec > 0 && (!ref_seq_id || !qry_seq_id || !pos || !rev))) {
+        pav_set_error("cigar_batch_create: bad argument");
+        return PAVGPU_ERR_ARG;
+    }
+    int64_t n_ops = op_off[n_rec] - op_off[0];
+    if (op_off[0] != 0 || n_ops < 0 || (n_ops > 0 && !ops)) { pav_set_error("cigar_batch_create: bad op offsets"); return PAVGPU_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    pavgpu_cigar_batch *b = new pavgpu_cigar_batch();
+    b->ctx = ctx; b->n_rec = n_rec; b->n_ops = n_ops;
+    b->n_chunks = (n_ops + CHUNK - 1) / CHUNK;
+    b->h_ops.assign(ops, ops + n_ops);
+    b->h_op_off.assign(op_off, op_off + n_rec + 1);
+    b->h_pos.assign(pos, pos + n_rec);
+    size_t ops_padded = (size_t)std::max<int64_t>(b->n_chunks, 1) * CHUNK;
+    size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1), nr = (size_t)std::max(n_rec, 1);
+    int rc = [&]() -> int {
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CUDA_TRY(cudaMalloc(&b->d_ref_id, nr * 4)); CUDA_TRY(cudaMalloc(&b->d_qry_id, nr * 4)); CUDA_TRY(cudaMalloc(&b->d_pos, nr * 4));
+        CUDA_TRY(cudaMalloc(&b->d_rev, nr)); CUDA_TRY(cudaMalloc(&b->d_op_off, (nr + 1) * 8));
+        CUDA_TRY(cudaMalloc(&b->d_ops, ops_padded * 4));
+        CUDA_TRY(cudaMalloc(&b->d_agg, nc * sizeof(int4))); CUDA_TRY(cudaMalloc(&b->d_cnt, nc * sizeof(uint2)));
+        CUDA_TRY(cudaMalloc(&b->d_pre_rq, nc * sizeof(int2))); CUDA_TRY(cudaMalloc(&b->d_pre_cnt, nc * sizeof(longlong2)));
+        CUDA_TRY(cudaMalloc(&b->d_totals, 2 * 8)); CUDA_TRY(cudaMalloc(&b->d_first_illegal, 8));
+        cudaStream_t st = ctx->stream;
+        CUDA_TRY(cudaMemsetAsync(b->d_ops, 0, ops_padded * 4, st));
+        if (n_rec) {
+            CUDA_TRY(cudaMemcpyAsync(b->d_ref_id, ref_seq_id, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(b->d_qry_id, qry_seq_id, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(b->d_pos, pos, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(b->d_rev, rev, (size_t)n_rec, cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(b->d_op_off, op_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n_ops) CUDA_TRY(cudaMemcpyAsync(b->d_ops, ops, (size_t)n_ops * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        b->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+        return PAVGPU_OK;
+    }();
+    if (rc) { batch_release(b); delete b; return rc; }
+    *out = b;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pavgpu_cigar_batch *b, const pavgpu_seqstore *ref_store, const pavgpu_seqstore *qry_store,
+                                      pavgpu_cigar_stats *stats)
+{
+    if (!b || !ref_store || !qry_store) { pav_set_error("cigar_batch_run: bad argument"); return PAVGPU_ERR_ARG; }
+    pavgpu_ctx *ctx = b->ctx;
+    if (ref_store->ctx->device != ctx->device || qry_store->ctx->device != ctx->device) {
+        pav_set_error("cigar_batch_run: stores live on another device");
+        return PAVGPU_ERR_ARG;
+    }
+    // ids must index the stores (checked on the host once; the kernels trust them)
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    RecView rv{b->d_ref_id, b->d_qry_id, b->d_pos, b->d_rev, b->d_op_off, b->n_rec};
+    unsigned long long init = ~0ull;
+    CUDA_TRY(cudaMemcpyAsync(b->d_first_illegal, &init, 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 16, st));
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+    b->n_snv = b->n_indel = 0;
+    if (b->n_chunks > 0) {
+        unsigned blocks = (unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        cigar_reduce_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_agg, b->d_cnt);
+        chunk_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(b->d_agg, b->d_cnt, b->n_chunks, b->d_pre_rq, b->d_pre_cnt, b->d_totals);
+        launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        int64_t tot[2];
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+        CUDA_TRY(cudaMemcpyAsync(tot, b->d_totals, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        b->n_snv = tot[0]; b->n_indel = tot[1];
+        if (b->n_snv > b->cap_snv) {
+            cudaFree(b->d_snv); b->d_snv = nullptr; b->cap_snv = 0;
+            CUDA_TRY(cudaMalloc(&b->d_snv, (size_t)b->n_snv * sizeof(int4)));
+            b->cap_snv = b->n_snv;
+        }
+        if (b->n_indel > b->cap_indel) {
+            cudaFree(b->d_stub); cudaFree(b->d_indel); b->d_stub = nullptr; b->d_indel = nullptr; b->cap_indel = 0;
+            CUDA_TRY(cudaMalloc(&b->d_stub, (size_t)b->n_indel * sizeof(IndelStub)));
+            CUDA_TRY(cudaMalloc(&b->d_indel, (size_t)b->n_indel * sizeof(pavgpu_indel_row)));
+            b->cap_indel = b->n_indel;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        cigar_emit_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_pre_rq, b->d_pre_cnt,
+                                                                   qry_store->d_len, b->d_snv, b->d_stub, b->d_first_illegal);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+        if (b->n_indel > 0) {
+            unsigned hb = (unsigned)((b->n_indel + 127) / 128);
+            homology_kernel<<<hb, 128, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel);
+            launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+        CUDA_TRY(cudaMemcpyAsync(&b->first_illegal, b->d_first_illegal, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        b->first_illegal = ~0ull;
+        for (int i = 1; i <= 4; i++) CUDA_TRY(cudaEventRecord(ctx->ev[i], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    b->ran = true;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->ms_h2d = b->ms_h2d;
+        stats->ms_scan = ev_ms(ctx->ev[0], ctx->ev[1]);
+        stats->ms_emit = ev_ms(ctx->ev[2], ctx->ev[3]);
+        stats->ms_homology = ev_ms(ctx->ev[3], ctx->ev[4]);
+        stats->ms_kernels = ev_ms(ctx->ev[0], ctx->ev[4]);
+        stats->n_ops = b->n_ops; stats->n_snv = b->n_snv; stats->n_indel = b->n_indel; stats->n_chunks = b->n_chunks;
+        stats->kernel_launches = launches;
+    }
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_fetch(pavgpu_cigar_batch *b, pavgpu_snv_row **snv_out, int64_t *n_snv, pavgpu_indel_row **indel_out,
+                                        int64_t *n_indel, pavgpu_cigar_err *err)
+{
+    if (!b || !b->ran || !snv_out || !n_snv || !indel_out || !n_indel) { pav_set_error("cigar_batch_fetch: bad argument or batch not run"); return PAVGPU_ERR_ARG; }
+    pavgpu_ctx *ctx = b->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    *snv_out = nullptr; *indel_out = nullptr; *n_snv = 0; *n_indel = 0;
+    if (err) memset(err, 0, sizeof *err);
+    if (b->first_illegal != ~0ull) {
+        // Explain the first illegal op on the host (error path only): walk the record up to it.
+        int64_t g = (int64_t)b->first_illegal;
+        int32_t rec = (int32_t)(std::upper_bound(b->h_op_off.begin(), b->h_op_off.end(), g) - b->h_op_off.begin()) - 1;
+        int64_t pr = b->h_pos[rec], pq = 0;
+        for (int64_t i = b->h_op_off[rec]; i < g; i++) {
+            uint32_t code = b->h_ops[i] & 15u, len = b->h_ops[i] >> 4;
+            if ((1u << code) & REF_ADV_MASK) pr += len;
+            if ((1u << code) & QRY_ADV_MASK) pq += len;
+        }
+        if (err) {
+            err->code = 1; err->rec = rec; err->op_index = g - b->h_op_off[rec]; err->opcode = (int32_t)(b->h_ops[g] & 15u);
+            err->pos_ref = (int32_t)pr; err->pos_qry = (int32_t)pq;
+        }
+        return PAVGPU_OK;
+    }
+    pavgpu_snv_row *hs = nullptr;
+    pavgpu_indel_row *hi = nullptr;
+    if (b->n_snv) { hs = (pavgpu_snv_row *)malloc((size_t)b->n_snv * sizeof(pavgpu_snv_row)); if (!hs) { pav_set_error("fetch: out of host memory"); return PAVGPU_ERR_NOMEM; } }
+    if (b->n_indel) { hi = (pavgpu_indel_row *)malloc((size_t)b->n_indel * sizeof(pavgpu_indel_row)); if (!hi) { free(hs); pav_set_error("fetch: out of host memory"); return PAVGPU_ERR_NOMEM; } }
+    int rc = [&]() -> int {
+        CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
+        if (b->n_snv) CUDA_TRY(cudaMemcpyAsync(hs, b->d_snv, (size_t)b->n_snv * sizeof(pavgpu_snv_row), cudaMemcpyDeviceToHost, ctx->stream));
+        if (b->n_indel) CUDA_TRY(cudaMemcpyAsync(hi, b->d_indel, (size_t)b->n_indel * sizeof(pavgpu_indel_row), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev[6], ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PAVGPU_OK;
+    }();
+    if (rc) { free(hs); free(hi); return rc; }
+    *snv_out = hs; *n_snv = b->n_snv; *indel_out = hi; *n_indel = b->n_indel;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_call(pavgpu_ctx *ctx, const pavgpu_seqstore *ref_store, const pavgpu_seqstore *qry_store, int32_t n_rec,
+                                 const int32_t *ref_seq_id, const int32_t *qry_seq_id, const int32_t *pos, const uint8_t *rev,
+                                 const uint32_t *ops, const int64_t *op_off, pavgpu_snv_row **snv_out, int64_t *n_snv,
+                                 pavgpu_indel_row **indel_out, int64_t *n_indel, pavgpu_cigar_err *err, pavgpu_cigar_stats *stats)
+{
+    if (!ref_store || !qry_store) { pav_set_error("cigar_call: store is NULL"); return PAVGPU_ERR_ARG; }
+    for (int32_t i = 0; i < n_rec; i++) {
+        if (ref_seq_id[i] < 0 || ref_seq_id[i] >= ref_store->n_seq || qry_seq_id[i] < 0 || qry_seq_id[i] >= qry_store->n_seq) {
+            pav_set_error("cigar_call: record %d refers to a sequence id outside its store", i);
+            return PAVGPU_ERR_ARG;
+        }
+    }
+    pavgpu_cigar_batch *b = nullptr;
+    int rc = pavgpu_cigar_batch_create(ctx, n_rec, ref_seq_id, qry_seq_id, pos, rev, ops, op_off, &b);
+    if (rc) return rc;
+    rc = pavgpu_cigar_batch_run(b, ref_store, qry_store, stats);
+    if (!rc) rc = pavgpu_cigar_batch_fetch(b, snv_out, n_snv, indel_out, n_indel, err);
+    if (!rc && stats) stats->ms_d2h = ev_ms(ctx->ev[5], ctx->ev[6]);
+    pavgpu_cigar_batch_free(b);
+    return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_homology(pavgpu_ctx *ctx, int32_t n, const uint8_t *seq, int64_t seq_len, const uint8_t *sv, int64_t sv_len,
+                               const int64_t *pos, int32_t *left_out, int32_t *right_out)
+{
+    if (!ctx || n < 0 || !seq || !sv || sv_len <= 0 || !pos || !left_out || !right_out) { pav_set_error("homology: bad argument"); return PAVGPU_ERR_ARG; }
+    const uint8_t *ptrs[2] = {seq, sv};
+    int64_t lens[2] = {seq_len, sv_len};
+    pavgpu_seqstore *st = nullptr;
+    int rc = pavgpu_seqstore_create(ctx, 2, ptrs, lens, &st);
+    if (rc) return rc;
+    int64_t *d_pos = nullptr;
+    int32_t *d_l = nullptr, *d_r = nullptr;
+    rc = [&]() -> int {
+        if (n == 0) return PAVGPU_OK;
+        CUDA_TRY(cudaMalloc(&d_pos, (size_t)n * 8)); CUDA_TRY(cudaMalloc(&d_l, (size_t)n * 4)); CUDA_TRY(cudaMalloc(&d_r, (size_t)n * 4));
+        CUDA_TRY(cudaMemcpyAsync(d_pos, pos, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        homology_probe_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(planes_of(st), n, d_pos, (int32_t)sv_len, d_l, d_r);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(left_out, d_l, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(right_out, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PAVGPU_OK;
+    }();
+    cudaFree(d_pos); cudaFree(d_l); cudaFree(d_r);
+    pavgpu_seqstore_free(st);
+    return rc;
+}

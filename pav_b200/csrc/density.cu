@@ -1,0 +1,808 @@
+// density.cu -- Path B: k-mer orientation states and smoothed state density for inversion windows.
+//
+// Reference semantics: scripts/density.py:423-571 (__main__) and :154-342 (get_smoothed_density),
+// kanapy/util/kmer.py:61-69,118-133,186-221 (k-mer arithmetic / stream), pavlib/seq.py:305-325
+// (reference k-mer Counter), scipy.stats.gaussian_kde (float64 Gaussian KDE). SURVEY appendix A.2.
+//
+// One *batch* of windows is processed per call (one window = one run of scripts/density.py):
+//   D1 ref_insert_kernel   exact k-mers of the reference window -> per-window open-addressing table
+//                          (62-bit keys, counts; count > 100 or no k-mers => status 125)
+//   D2 tig_state_kernel    contig k-mer + reverse complement, two probes -> STATE_MER per position
+//   -- host: keep-mask (state count >= 20), N, dense row offsets --
+//   D3 compact_kernel      order-preserving compaction of informative k-mers -> KMER / INDEX / STATE_MER
+//   D4 kde_prepare_kernel  per state: n, mean, var(ddof=1) of INDEX_DEN -> bandwidth L_s and norm_s
+//   D5 kde_table_kernel    T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both
+//                          live on the integer lattice, so N exps replace N * E exps
+//   D6 kde_eval_kernel     K_s(j) = norm_s * sum_{i: STATE_MER[i]=s} T_s[|i - j|] at the sampled lattice
+//                          (every srs-th point + last); float64, threads sweep data points so that table
+//                          and state reads are coalesced
+//   D7 gap_classify_kernel per gap: state change / argmax change / |delta| > 0.005 => list of points that
+//                          need a full evaluation
+//   D6' kde_eval_kernel    on that list
+//   D8 interp_kernel       numpy.interp for the remaining gaps
+//   D9 finalize_kernel     spikes (> 1 -> reciprocal) and STATE = argmax (first max wins)
+//
+// The k-mer of position g is read straight out of the 2-bit plane with a funnel shift (no rolling
+// state, so every position is independent); validity is k zero bits of the N-mask plane, which is
+// exactly the stream's "load == k" condition.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint64_t EMPTY_KEY = ~0ull;
+constexpr int TILE = 1024;       // positions per block in D2 / D3
+constexpr int EVAL_GROUP = 4;    // evaluation points per block in D6
+constexpr int EVAL_THREADS = 256;
+
+struct WinPlan {  // per window, device-visible
+    // inputs
+    int64_t ref_g0, tig_g0;       // global base offsets of the windows in the planes
+    int32_t ref_len, tig_len;     // window lengths in bases
+    int32_t rev, srs;
+    // tables
+    int64_t tab_off;              // slot offset of this window's hash table
+    int32_t tab_log2;             // log2(capacity)
+    int32_t pad0;
+    int64_t pos_off;              // offset of this window in the per-position scratch (tig positions)
+    int64_t tile_off;             // offset of this window's tiles in the per-tile count array
+    // after the first host sync
+    int32_t status;               // 0 / 125
+    int32_t keep_mask;            // bit s set when state s is kept
+    int32_t n_rows;               // N
+    int32_t smoothed;
+    int64_t row_off;              // dense row offset
+    int32_t n_samp;               // sampled lattice points
+    int32_t pad1;
+};
+
+struct WinCounts {  // written by D1 / D2
+    unsigned long long ref_valid;
+    unsigned int ref_max;
+    unsigned int cnt[3];
+};
+
+struct KdeParams {  // per window, written by D4
+    double L[3];
+    double norm[3];
+    int32_t n[3];
+    int32_t pad;
+};
+
+__device__ __forceinline__ uint64_t hash_kmer(uint64_t k, int log2cap)
+{
+    return (k * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
+}
+
+// kmer.py:118-133 as bit tricks: complement, then reverse the 2-bit groups of the 64-bit word.
+__device__ __forceinline__ uint64_t kmer_revcomp(uint64_t kmer, int k)
+{
+    uint64_t x = ~kmer;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+    return x >> (64 - 2 * k);
+}
+
+// k-mer starting at global base g (first base most significant); returns false if any of its k bases
+// is not ACGT (stream() would not have emitted it, kmer.py:206-221).
+__device__ __forceinline__ bool kmer_at(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t g, int k,
+                                        uint64_t &kmer)
+{
+    int64_t w = g >> 5;
+    int s = (int)(g & 31);
+    uint64_t m = (uint64_t)__ldg(nmask + w) | ((uint64_t)__ldg(nmask + w + 1) << 32);
+    m >>= s;
+    uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+    if (m & kmask) return false;
+    uint64_t hi = __ldg(pack2 + w), lo = __ldg(pack2 + w + 1);
+    uint64_t x = s ? ((hi << (2 * s)) | (lo >> (64 - 2 * s))) : hi;
+    kmer = x >> (64 - 2 * k);
+    return true;
+}
+
+// D1 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ref_insert_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes ref, int k, uint64_t *__restrict__ keys,
+                  uint32_t *__restrict__ counts, WinCounts *__restrict__ wc)
+{
+    int32_t w = win_base + blockIdx.y;
+    const WinPlan P = plan[w];
+    int32_t n_pos = P.ref_len - k + 1;
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    uint64_t kmer = 0;
+    if (i < n_pos) valid = kmer_at(ref.pack2, ref.nmask, P.ref_g0 + i, k, kmer);
+    unsigned int my_cnt = 0;
+    if (valid) {
+        if (P.rev) kmer = kmer_revcomp(kmer, k);  // density.py:538-539: the reference SET is reverse-complemented
+        uint64_t *tk = keys + P.tab_off;
+        uint32_t *tc = counts + P.tab_off;
+        uint64_t mask = (1ull << P.tab_log2) - 1;
+        uint64_t slot = hash_kmer(kmer, P.tab_log2);
+        while (true) {
+            unsigned long long old = atomicCAS((unsigned long long *)(tk + slot), (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
+            if (old == EMPTY_KEY || old == kmer) {
+                my_cnt = atomicAdd(tc + slot, 1u) + 1u;
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+    // block aggregates -> per-window counters
+    unsigned n_valid = __syncthreads_count(valid);
+    unsigned mx = my_cnt;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+    __shared__ unsigned s_mx[8];
+    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned m2 = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) m2 = max(m2, s_mx[q]);
+        if (n_valid) atomicAdd(&wc[w].ref_valid, (unsigned long long)n_valid);
+        if (m2) atomicMax(&wc[w].ref_max, m2);
+    }
+}
+
+// D2 ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool table_has(const uint64_t *__restrict__ tk, int log2cap, uint64_t key)
+{
+    uint64_t mask = (1ull << log2cap) - 1;
+    uint64_t slot = hash_kmer(key, log2cap);
+    while (true) {
+        uint64_t v = __ldg(tk + slot);
+        if (v == key) return true;
+        if (v == EMPTY_KEY) return false;
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(TILE)
+tig_state_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig, int k, const uint64_t *__restrict__ keys,
+                 int8_t *__restrict__ st_pos, uint32_t *__restrict__ tile_cnt, WinCounts *__restrict__ wc)
+{
+    int32_t w = win_base + blockIdx.y;
+    const WinPlan P = plan[w];
+    int32_t n_pos = P.tig_len - k + 1;
+    int32_t n_tiles = (max(n_pos, 0) + TILE - 1) / TILE;
+    if ((int)blockIdx.x >= n_tiles) return;
+    int32_t i = blockIdx.x * TILE + threadIdx.x;
+    int st = -1;
+    if (i < n_pos) {
+        uint64_t kmer;
+        if (kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer)) {
+            const uint64_t *tk = keys + P.tab_off;
+            bool f = table_has(tk, P.tab_log2, kmer);
+            bool r = table_has(tk, P.tab_log2, kmer_revcomp(kmer, k));
+            st = f ? (r ? 1 : 0) : (r ? 2 : -1);  // KMER_ORIENTATION_STATE, density.py:38-43
+        }
+        st_pos[P.pos_off + i] = (int8_t)st;
+    }
+    unsigned c0 = __syncthreads_count(st == 0);
+    unsigned c1 = __syncthreads_count(st == 1);
+    unsigned c2 = __syncthreads_count(st == 2);
+    if (threadIdx.x == 0) {
+        uint32_t *tc = tile_cnt + (P.tile_off + blockIdx.x) * 3;
+        tc[0] = c0; tc[1] = c1; tc[2] = c2;
+        if (c0) atomicAdd(&wc[w].cnt[0], c0);
+        if (c1) atomicAdd(&wc[w].cnt[1], c1);
+        if (c2) atomicAdd(&wc[w].cnt[2], c2);
+    }
+}
+
+// D3 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE)
+compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig, int k, const int8_t *__restrict__ st_pos,
+               const uint32_t *__restrict__ tile_cnt, uint64_t *__restrict__ o_kmer, int32_t *__restrict__ o_index,
+               int8_t *__restrict__ o_state_mer)
+{
+    int32_t w = win_base + blockIdx.y;
+    const WinPlan P = plan[w];
+    if (P.status != 0 || P.n_rows == 0) return;
+    int32_t n_pos = P.tig_len - k + 1;
+    int32_t n_tiles = (max(n_pos, 0) + TILE - 1) / TILE;
+    if ((int)blockIdx.x >= n_tiles) return;
+    __shared__ unsigned s_base;
+    __shared__ unsigned s_warp[TILE / 32];
+    // rows written by earlier tiles of this window
+    unsigned part = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += blockDim.x) {
+        const uint32_t *tc = tile_cnt + (P.tile_off + t) * 3;
+        part += ((P.keep_mask & 1) ? tc[0] : 0) + ((P.keep_mask & 2) ? tc[1] : 0) + ((P.keep_mask & 4) ? tc[2] : 0);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_base, part);
+    __syncthreads();
+    int32_t i = blockIdx.x * TILE + threadIdx.x;
+    int st = (i < n_pos) ? (int)st_pos[P.pos_off + i] : -1;
+    bool keep = st >= 0 && ((P.keep_mask >> st) & 1);
+    unsigned bal = __ballot_sync(FULL, keep);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0;
+    for (int q = 0; q < wid; q++) before += s_warp[q];
+    if (keep) {
+        int64_t row = P.row_off + s_base + before + __popc(bal & ((1u << lane) - 1));
+        uint64_t kmer = 0;
+        kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer);
+        o_kmer[row] = kmer;
+        o_index[row] = i;
+        o_state_mer[row] = (int8_t)st;
+    }
+}
+
+// D4 ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_d(double v, double *s_buf)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += s_buf[q];
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+kde_prepare_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_mer, double smooth, KdeParams *__restrict__ kp)
+{
+    int32_t w = blockIdx.x;
+    const WinPlan P = plan[w];
+    if (!P.smoothed) return;
+    __shared__ double s_buf[8];
+    const int8_t *sm = state_mer + P.row_off;
+    int N = P.n_rows;
+    double bw = pow((double)N, -1.0 / 5.0) * smooth;  // density.py:198
+    for (int s = 0; s < 3; s++) {
+        double n = 0.0, sx = 0.0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            if (sm[i] == s) { n += 1.0; sx += (double)i; }  // exact: integers below 2^53
+        n = block_sum_d(n, s_buf);
+        sx = block_sum_d(sx, s_buf);
+        double L = 1.0, norm = 0.0;
+        if (n > 0.0) {
+            double mean = sx / n, ss = 0.0;
+            for (int i = threadIdx.x; i < N; i += blockDim.x)
+                if (sm[i] == s) { double dv = (double)i - mean; ss += dv * dv; }
+            ss = block_sum_d(ss, s_buf);
+            double var = ss / (n - 1.0);        // np.cov(bias=False)
+            L = sqrt(var) * bw;                 // cho_cov = cholesky(cov) * factor
+            norm = pow(2.0 * M_PI, -0.5) / L;   // (2 pi)^(-d/2) / cho_cov[0,0]
+        } else {
+            (void)block_sum_d(0.0, s_buf);      // keep barrier counts uniform
+        }
+        if (threadIdx.x == 0) { kp[w].L[s] = L; kp[w].norm[s] = norm; kp[w].n[s] = (int32_t)n; }
+    }
+}
+
+// D5 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kde_table_kernel(const WinPlan *__restrict__ plan, int32_t win_base, const KdeParams *__restrict__ kp, double *__restrict__ tab0,
+                 double *__restrict__ tab1, double *__restrict__ tab2)
+{
+    int32_t w = win_base + blockIdx.y;
+    const WinPlan P = plan[w];
+    if (!P.smoothed) return;
+    int32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= P.n_rows) return;
+    const KdeParams K = kp[w];
+    double *tabs[3] = {tab0, tab1, tab2};
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+        double v = 0.0;
+        if (K.n[s] > 0) {
+            double t = (double)d / K.L[s];
+            v = exp(-(t * t) / 2.0);
+        }
+        tabs[s][P.row_off + d] = v;
+    }
+}
+
+// D6 ---------------------------------------------------------------------------------------------
+// grp_off[w] = first block of window w (prefix over ceil(n_eval_w / EVAL_GROUP)). mode 0: sampled lattice
+// (e-th sample = min(e * srs, N-1)); mode 1: explicit list fill_list[row_off + e].
+__global__ void __launch_bounds__(EVAL_THREADS)
+kde_eval_kernel(const WinPlan *__restrict__ plan, int32_t n_win, const int64_t *__restrict__ grp_off, const int32_t *__restrict__ n_eval_w,
+                int mode, const int32_t *__restrict__ fill_list, const KdeParams *__restrict__ kp, const int8_t *__restrict__ state_mer,
+                const double *__restrict__ tab0, const double *__restrict__ tab1, const double *__restrict__ tab2,
+                double *__restrict__ k0, double *__restrict__ k1, double *__restrict__ k2)
+{
+    // window of this block
+    int64_t blk = blockIdx.x;
+    int32_t lo = 0, hi = n_win;
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (grp_off[mid] <= blk) lo = mid; else hi = mid;
+    }
+    int32_t w = lo;
+    const WinPlan P = plan[w];
+    int32_t N = P.n_rows;
+    int32_t e0 = (int32_t)(blk - grp_off[w]) * EVAL_GROUP;
+    int32_t ne = n_eval_w[w];
+    int32_t j[EVAL_GROUP];
+#pragma unroll
+    for (int g = 0; g < EVAL_GROUP; g++) {
+        int32_t e = e0 + g;
+        if (e >= ne) j[g] = -1;
+        else if (mode == 0) { int64_t jj = (int64_t)e * P.srs; j[g] = jj > N - 1 ? N - 1 : (int32_t)jj; }
+        else j[g] = fill_list[P.row_off + e];
+    }
+    const int8_t *sm = state_mer + P.row_off;
+    const double *t0 = tab0 + P.row_off, *t1 = tab1 + P.row_off, *t2 = tab2 + P.row_off;
+    double acc[EVAL_GROUP][3];
+#pragma unroll
+    for (int g = 0; g < EVAL_GROUP; g++) acc[g][0] = acc[g][1] = acc[g][2] = 0.0;
+    for (int32_t i = threadIdx.x; i < N; i += EVAL_THREADS) {
+        int s = sm[i];
+        const double *t = s == 0 ? t0 : (s == 1 ? t1 : t2);
+#pragma unroll
+        for (int g = 0; g < EVAL_GROUP; g++) {
+            if (j[g] >= 0) {
+                int32_t d = i - j[g];
+                d = d < 0 ? -d : d;
+                double v = __ldg(t + d);
+                acc[g][0] += (s == 0) ? v : 0.0;
+                acc[g][1] += (s == 1) ? v : 0.0;
+                acc[g][2] += (s == 2) ? v : 0.0;
+            }
+        }
+    }
+    __shared__ double s_red[EVAL_THREADS / 32][EVAL_GROUP][3];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < EVAL_GROUP; g++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            double v = acc[g][s];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+            if (lane == 0) s_red[wid][g][s] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < EVAL_GROUP * 3) {
+        int g = threadIdx.x / 3, s = threadIdx.x % 3;
+        if (j[g] >= 0) {
+            double v = 0.0;
+            for (int q = 0; q < EVAL_THREADS / 32; q++) v += s_red[q][g][s];
+            v *= kp[w].norm[s];
+            double *dst = s == 0 ? k0 : (s == 1 ? k1 : k2);
+            dst[P.row_off + j[g]] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ int argmax3(double a, double b, double c)
+{
+    int m = 0;
+    double v = a;
+    if (b > v) { m = 1; v = b; }
+    if (c > v) m = 2;
+    return m;
+}
+
+// D7 ---------------------------------------------------------------------------------------------
+// One block per window. Gap g spans samples a = g * srs and b = min(a + srs, N - 1).
+__global__ void __launch_bounds__(256)
+gap_classify_kernel(const WinPlan *__restrict__ plan, double delta, const int8_t *__restrict__ state_mer, const double *__restrict__ k0,
+                    const double *__restrict__ k1, const double *__restrict__ k2, uint8_t *__restrict__ gap_full,
+                    int32_t *__restrict__ fill_list, int32_t *__restrict__ n_fill)
+{
+    int32_t w = blockIdx.x;
+    const WinPlan P = plan[w];
+    if (!P.smoothed) { if (threadIdx.x == 0) n_fill[w] = 0; return; }
+    int32_t N = P.n_rows, srs = P.srs;
+    int32_t n_gap = P.n_samp - 1;
+    const int8_t *sm = state_mer + P.row_off;
+    const double *a0 = k0 + P.row_off, *a1 = k1 + P.row_off, *a2 = k2 + P.row_off;
+    __shared__ int s_scan[256];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int32_t g0 = 0; g0 < n_gap; g0 += blockDim.x) {
+        int32_t g = g0 + threadIdx.x;
+        int cnt = 0;
+        int32_t a = 0, b = 0;
+        if (g < n_gap) {
+            a = g * srs;
+            b = min(a + srs, N - 1);
+            if (b > a + 1) {
+                bool change = argmax3(a0[a], a1[a], a2[a]) != argmax3(a0[b], a1[b], a2[b]);
+                int8_t s0 = sm[a];
+                for (int32_t i = a + 1; i <= b && !change; i++) change = sm[i] != s0;
+                double dm = fmax(fabs(a0[a] - a0[b]), fmax(fabs(a1[a] - a1[b]), fabs(a2[a] - a2[b])));
+                bool full = change || dm > delta;
+                gap_full[P.row_off + g] = full ? 1 : 0;
+                cnt = full ? (b - a - 1) : 0;
+            } else {
+                gap_full[P.row_off + g] = 1;  // nothing to fill
+            }
+        }
+        // block exclusive scan of cnt
+        s_scan[threadIdx.x] = cnt;
+        __syncthreads();
+        for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+            int v = (threadIdx.x >= (unsigned)d) ? s_scan[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        int off = s_base + s_scan[threadIdx.x] - cnt;
+        for (int t = 0; t < cnt; t++) fill_list[P.row_off + off + t] = a + 1 + t;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_base += s_scan[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_fill[w] = s_base;
+}
+
+// D8 / D9 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+interp_kernel(const WinPlan *__restrict__ plan, int32_t win_base, const uint8_t *__restrict__ gap_full, double *__restrict__ k0,
+              double *__restrict__ k1, double *__restrict__ k2)
+{
+    int32_t w = win_base + blockIdx.y;
+    const WinPlan P = plan[w];
+    if (!P.smoothed) return;
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t N = P.n_rows;
+    if (j >= N) return;
+    int32_t g = j / P.srs;
+    int32_t a = g * P.srs, b = min(a + P.srs, N - 1);
+    if (j == a || j == b || gap_full[P.row_off + g]) return;
+    double *ks[3] = {k0 + P.row_off, k1 + P.row_off, k2 + P.row_off};
+#pragma unroll
+    for (int s = 0; s < 3; s++) {  // numpy.interp: slope * (x - x0) + y0
+        double ya = ks[s][a], yb = ks[s][b];
+        double slope = (yb - ya) / ((double)b - (double)a);
+        ks[s][j] = slope * ((double)j - (double)a) + ya;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_kernel(const WinPlan *__restrict__ plan, int32_t win_base, double *__restrict__ k0, double *__restrict__ k1, double *__restrict__ k2,
+                int8_t *__restrict__ state)
+{
+    int32_t w = win_base + blockIdx.y;
+    const WinPlan P = plan[w];
+    if (P.status != 0) return;
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_rows) return;
+    int64_t r = P.row_off + j;
+    if (!P.smoothed) {
+        state[r] = -1;
+        double nan = __longlong_as_double(0x7ff8000000000000ll);
+        k0[r] = nan; k1[r] = nan; k2[r] = nan;
+        return;
+    }
+    double a = k0[r], b = k1[r], c = k2[r];
+    if (a > 1.0) { a = 1.0 / a; k0[r] = a; }   // density.py:330-332
+    if (b > 1.0) { b = 1.0 / b; k1[r] = b; }
+    if (c > 1.0) { c = 1.0 / c; k2[r] = c; }
+    state[r] = (int8_t)argmax3(a, b, c);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+struct pavgpu_density_batch {
+    pavgpu_ctx *ctx;
+    int32_t n_win;
+    pavgpu_density_params prm;
+    std::vector<pavgpu_density_window> win;
+    std::vector<WinPlan> plan;
+    std::vector<pavgpu_density_result> res;
+    int64_t tab_slots, pos_total, tile_total, rows_total, rows_cap;
+    int32_t max_ref_tiles, max_tig_tiles, max_row_tiles;
+    // device
+    WinPlan *d_plan; WinCounts *d_wc; KdeParams *d_kp;
+    uint64_t *d_keys; uint32_t *d_counts;
+    int8_t *d_st_pos; uint32_t *d_tile_cnt;
+    uint64_t *d_kmer; int32_t *d_index; int8_t *d_state_mer, *d_state;
+    double *d_k[3], *d_tab[3];
+    uint8_t *d_gap_full; int32_t *d_fill_list, *d_n_fill, *d_n_eval; int64_t *d_grp_off;
+    bool ran;
+    pavgpu_density_stats stats;
+};
+
+extern "C" __attribute__((visibility("default"))) void pavgpu_density_default_params(pavgpu_density_params *p)
+{
+    if (!p) return;
+    p->k = 31; p->min_informative = 2000; p->min_state_count = 20; p->max_ref_kmer_count = 100;
+    p->smooth = 1.0; p->delta = 0.005;
+}
+
+static void dens_release(pavgpu_density_batch *b)
+{
+    cudaFree(b->d_plan); cudaFree(b->d_wc); cudaFree(b->d_kp); cudaFree(b->d_keys); cudaFree(b->d_counts); cudaFree(b->d_st_pos);
+    cudaFree(b->d_tile_cnt); cudaFree(b->d_kmer); cudaFree(b->d_index); cudaFree(b->d_state_mer); cudaFree(b->d_state);
+    for (int s = 0; s < 3; s++) { cudaFree(b->d_k[s]); cudaFree(b->d_tab[s]); }
+    cudaFree(b->d_gap_full); cudaFree(b->d_fill_list); cudaFree(b->d_n_fill); cudaFree(b->d_n_eval); cudaFree(b->d_grp_off);
+}
+
+extern "C" __attribute__((visibility("default"))) void pavgpu_density_batch_free(pavgpu_density_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    dens_release(b);
+    delete b;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_create(pavgpu_ctx *ctx, int32_t n_win, const pavgpu_density_window *win,
+                                                                                    const pavgpu_density_params *params, pavgpu_density_batch **out)
+{
+    if (!ctx || !out || n_win < 0 || (n_win > 0 && !win) || !params) { pav_set_error("density_batch_create: bad argument"); return PAVGPU_ERR_ARG; }
+    if (params->k < 1 || params->k > 31) {
+        pav_set_error("density: k=%d is not supported on the GPU path (1 <= k <= 31; exact 62-bit keys)", params->k);
+        return PAVGPU_ERR_ARG;
+    }
+    for (int32_t i = 0; i < n_win; i++) {
+        if (win[i].ref_pos < 0 || win[i].ref_end < win[i].ref_pos || win[i].tig_pos < 0 || win[i].tig_end < win[i].tig_pos || win[i].srs < 1) {
+            pav_set_error("density: window %d has invalid coordinates or srs", i);
+            return PAVGPU_ERR_ARG;
+        }
+    }
+    pavgpu_density_batch *b = new pavgpu_density_batch();
+    b->ctx = ctx; b->n_win = n_win; b->prm = *params;
+    b->win.assign(win, win + n_win);
+    b->plan.resize(n_win);
+    b->res.resize(n_win);
+    *out = b;
+    return PAVGPU_OK;
+}
+
+static int log2_ceil(int64_t v)
+{
+    int l = 0;
+    while (((int64_t)1 << l) < v) l++;
+    return l;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(pavgpu_density_batch *b, const pavgpu_seqstore *ref_store,
+                                                                                 const pavgpu_seqstore *tig_store, pavgpu_density_stats *stats)
+{
+    if (!b || !ref_store || !tig_store) { pav_set_error("density_batch_run: bad argument"); return PAVGPU_ERR_ARG; }
+    pavgpu_ctx *ctx = b->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int k = b->prm.k;
+    const int32_t n_win = b->n_win;
+    dens_release(b);
+    b->d_plan = nullptr; b->d_wc = nullptr; b->d_kp = nullptr; b->d_keys = nullptr; b->d_counts = nullptr; b->d_st_pos = nullptr;
+    b->d_tile_cnt = nullptr; b->d_kmer = nullptr; b->d_index = nullptr; b->d_state_mer = b->d_state = nullptr;
+    for (int s = 0; s < 3; s++) b->d_k[s] = b->d_tab[s] = nullptr;
+    b->d_gap_full = nullptr; b->d_fill_list = b->d_n_fill = b->d_n_eval = nullptr; b->d_grp_off = nullptr;
+    memset(&b->stats, 0, sizeof b->stats);
+    b->ran = false;
+    if (n_win == 0) { b->ran = true; b->rows_total = 0; if (stats) *stats = b->stats; return PAVGPU_OK; }
+
+    // ---- plan, part 1 (host)
+    int64_t tab = 0, pos = 0, tiles = 0, bases = 0;
+    int32_t max_ref_blocks = 1, max_tig_tiles = 1;
+    for (int32_t w = 0; w < n_win; w++) {
+        const pavgpu_density_window &W = b->win[w];
+        if (W.ref_seq_id < 0 || W.ref_seq_id >= ref_store->n_seq || W.tig_seq_id < 0 || W.tig_seq_id >= tig_store->n_seq ||
+            W.ref_end > ref_store->h_len[W.ref_seq_id] || W.tig_end > tig_store->h_len[W.tig_seq_id]) {
+            pav_set_error("density: window %d is outside its sequence", w);
+            return PAVGPU_ERR_ARG;
+        }
+        WinPlan &P = b->plan[w];
+        memset(&P, 0, sizeof P);
+        P.ref_g0 = ref_store->h_off[W.ref_seq_id] + W.ref_pos;
+        P.tig_g0 = tig_store->h_off[W.tig_seq_id] + W.tig_pos;
+        P.ref_len = W.ref_end - W.ref_pos;
+        P.tig_len = W.tig_end - W.tig_pos;
+        P.rev = W.rev; P.srs = W.srs;
+        int32_t n_ref = std::max(P.ref_len - k + 1, 0), n_tig = std::max(P.tig_len - k + 1, 0);
+        P.tab_log2 = std::max(log2_ceil(2 * (int64_t)std::max(n_ref, 1)), 4);
+        P.tab_off = tab; tab += (int64_t)1 << P.tab_log2;
+        P.pos_off = pos; pos += n_tig;
+        P.tile_off = tiles; tiles += (n_tig + TILE - 1) / TILE;
+        max_ref_blocks = std::max(max_ref_blocks, (n_ref + 255) / 256);
+        max_tig_tiles = std::max(max_tig_tiles, (n_tig + TILE - 1) / TILE);
+        bases += P.tig_len;
+    }
+    b->tab_slots = tab; b->pos_total = pos; b->tile_total = tiles;
+    b->stats.bases = bases;
+
+    int launches = 0;
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+    CUDA_TRY(cudaMalloc(&b->d_plan, sizeof(WinPlan) * n_win));
+    CUDA_TRY(cudaMalloc(&b->d_wc, sizeof(WinCounts) * n_win));
+    CUDA_TRY(cudaMalloc(&b->d_kp, sizeof(KdeParams) * n_win));
+    CUDA_TRY(cudaMalloc(&b->d_keys, sizeof(uint64_t) * std::max<int64_t>(tab, 1)));
+    CUDA_TRY(cudaMalloc(&b->d_counts, sizeof(uint32_t) * std::max<int64_t>(tab, 1)));
+    CUDA_TRY(cudaMalloc(&b->d_st_pos, std::max<int64_t>(pos, 1)));
+    CUDA_TRY(cudaMalloc(&b->d_tile_cnt, sizeof(uint32_t) * 3 * std::max<int64_t>(tiles, 1)));
+    CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_wc, 0, sizeof(WinCounts) * n_win, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_keys, 0xFF, sizeof(uint64_t) * std::max<int64_t>(tab, 1), st));
+    CUDA_TRY(cudaMemsetAsync(b->d_counts, 0, sizeof(uint32_t) * std::max<int64_t>(tab, 1), st));
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+
+    const int32_t YMAX = 32768;
+    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+        int32_t ny = std::min(YMAX, n_win - w0);
+        ref_insert_kernel<<<dim3(max_ref_blocks, ny), 256, 0, st>>>(b->d_plan, w0, planes_of(ref_store), k, b->d_keys, b->d_counts, b->d_wc);
+        launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+        int32_t ny = std::min(YMAX, n_win - w0);
+        tig_state_kernel<<<dim3(max_tig_tiles, ny), TILE, 0, st>>>(b->d_plan, w0, planes_of(tig_store), k, b->d_keys, b->d_st_pos, b->d_tile_cnt, b->d_wc);
+        launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    std::vector<WinCounts> wc(n_win);
+    CUDA_TRY(cudaMemcpyAsync(wc.data(), b->d_wc, sizeof(WinCounts) * n_win, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+
+    // ---- plan, part 2 (host): status, keep mask, N, dense row offsets, sample counts
+    int64_t rows = 0;
+    int32_t max_rows = 1;
+    std::vector<int64_t> grp_off(n_win + 1, 0);
+    std::vector<int32_t> n_eval(n_win, 0);
+    for (int32_t w = 0; w < n_win; w++) {
+        WinPlan &P = b->plan[w];
+        pavgpu_density_result &R = b->res[w];
+        memset(&R, 0, sizeof R);
+        if (wc[w].ref_valid == 0 || (int64_t)wc[w].ref_max > (int64_t)b->prm.max_ref_kmer_count) {  // density.py:510-527
+            P.status = PAVGPU_INV_FAIL; P.n_rows = 0; P.smoothed = 0; P.keep_mask = 0;
+        } else {
+            P.status = 0; P.keep_mask = 0;
+            int64_t N = 0;
+            for (int s = 0; s < 3; s++)
+                if (wc[w].cnt[s] > 0 && (int64_t)wc[w].cnt[s] >= (int64_t)b->prm.min_state_count) { P.keep_mask |= 1 << s; N += wc[w].cnt[s]; }
+            P.n_rows = (int32_t)N;
+            P.smoothed = (N >= b->prm.min_informative && N > 0) ? 1 : 0;  // density.py:193-194
+        }
+        P.row_off = rows;
+        rows += P.n_rows;
+        max_rows = std::max(max_rows, P.n_rows);
+        P.n_samp = 0;
+        if (P.smoothed) {
+            int32_t N = P.n_rows;
+            P.n_samp = (N - 1) / P.srs + 1 + (((N - 1) % P.srs) ? 1 : 0);  // density.py:211-214
+        }
+        n_eval[w] = P.n_samp;
+        grp_off[w + 1] = grp_off[w] + (P.n_samp + EVAL_GROUP - 1) / EVAL_GROUP;
+        R.status = P.status; R.smoothed = P.smoothed; R.row_off = P.row_off; R.n_rows = P.n_rows; R.n_eval = P.n_samp;
+    }
+    b->rows_total = rows;
+    b->stats.rows = rows;
+    size_t rcap = (size_t)std::max<int64_t>(rows, 1);
+    CUDA_TRY(cudaMalloc(&b->d_kmer, rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_index, rcap * 4));
+    CUDA_TRY(cudaMalloc(&b->d_state_mer, rcap)); CUDA_TRY(cudaMalloc(&b->d_state, rcap));
+    for (int s = 0; s < 3; s++) { CUDA_TRY(cudaMalloc(&b->d_k[s], rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_tab[s], rcap * 8)); }
+    CUDA_TRY(cudaMalloc(&b->d_gap_full, rcap)); CUDA_TRY(cudaMalloc(&b->d_fill_list, rcap * 4));
+    CUDA_TRY(cudaMalloc(&b->d_n_fill, sizeof(int32_t) * n_win)); CUDA_TRY(cudaMalloc(&b->d_n_eval, sizeof(int32_t) * n_win));
+    CUDA_TRY(cudaMalloc(&b->d_grp_off, sizeof(int64_t) * (n_win + 1)));
+    CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_n_eval, n_eval.data(), sizeof(int32_t) * n_win, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_grp_off, grp_off.data(), sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, st));
+
+    int32_t row_blocks = (max_rows + 255) / 256;
+    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+        int32_t ny = std::min(YMAX, n_win - w0);
+        compact_kernel<<<dim3(max_tig_tiles, ny), TILE, 0, st>>>(b->d_plan, w0, planes_of(tig_store), k, b->d_st_pos, b->d_tile_cnt, b->d_kmer,
+                                                                b->d_index, b->d_state_mer);
+        launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+    kde_prepare_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state_mer, b->prm.smooth, b->d_kp);
+    launches++;
+    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+        int32_t ny = std::min(YMAX, n_win - w0);
+        kde_table_kernel<<<dim3(row_blocks, ny), 256, 0, st>>>(b->d_plan, w0, b->d_kp, b->d_tab[0], b->d_tab[1], b->d_tab[2]);
+        launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    int64_t pairs = 0;
+    if (grp_off[n_win] > 0) {
+        kde_eval_kernel<<<(unsigned)grp_off[n_win], EVAL_THREADS, 0, st>>>(b->d_plan, n_win, b->d_grp_off, b->d_n_eval, 0, nullptr, b->d_kp,
+                                                                           b->d_state_mer, b->d_tab[0], b->d_tab[1], b->d_tab[2], b->d_k[0],
+                                                                           b->d_k[1], b->d_k[2]);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    gap_classify_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->prm.delta, b->d_state_mer, b->d_k[0], b->d_k[1], b->d_k[2], b->d_gap_full,
+                                               b->d_fill_list, b->d_n_fill);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int32_t> n_fill(n_win, 0);
+    CUDA_TRY(cudaMemcpyAsync(n_fill.data(), b->d_n_fill, sizeof(int32_t) * n_win, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int32_t w = 0; w < n_win; w++) {
+        pairs += ((int64_t)b->plan[w].n_samp + n_fill[w]) * b->plan[w].n_rows;
+        b->res[w].n_eval += n_fill[w];
+        grp_off[w + 1] = grp_off[w] + (n_fill[w] + EVAL_GROUP - 1) / EVAL_GROUP;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+    if (grp_off[n_win] > 0) {
+        CUDA_TRY(cudaMemcpyAsync(b->d_grp_off, grp_off.data(), sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, st));
+        kde_eval_kernel<<<(unsigned)grp_off[n_win], EVAL_THREADS, 0, st>>>(b->d_plan, n_win, b->d_grp_off, b->d_n_fill, 1, b->d_fill_list,
+                                                                           b->d_kp, b->d_state_mer, b->d_tab[0], b->d_tab[1], b->d_tab[2],
+                                                                           b->d_k[0], b->d_k[1], b->d_k[2]);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+        int32_t ny = std::min(YMAX, n_win - w0);
+        interp_kernel<<<dim3(row_blocks, ny), 256, 0, st>>>(b->d_plan, w0, b->d_gap_full, b->d_k[0], b->d_k[1], b->d_k[2]);
+        finalize_kernel<<<dim3(row_blocks, ny), 256, 0, st>>>(b->d_plan, w0, b->d_k[0], b->d_k[1], b->d_k[2], b->d_state);
+        launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+    b->stats.ms_kmer = ev_ms(ctx->ev[1], ctx->ev[2]);
+    b->stats.ms_kde = ev_ms(ctx->ev[2], ctx->ev[4]);
+    b->stats.ms_fill = ev_ms(ctx->ev[3], ctx->ev[4]);
+    b->stats.ms_kernels = ev_ms(ctx->ev[1], ctx->ev[4]);
+    b->stats.kde_pairs = pairs;
+    b->stats.kernel_launches = launches;
+    b->ran = true;
+    if (stats) *stats = b->stats;
+    return PAVGPU_OK;
+}
+
+template <typename T>
+static int fetch_col(pavgpu_ctx *ctx, const T *d, int64_t n, T **out)
+{
+    *out = nullptr;
+    if (n == 0) return PAVGPU_OK;
+    T *h = (T *)malloc((size_t)n * sizeof(T));
+    if (!h) { pav_set_error("density fetch: out of host memory"); return PAVGPU_ERR_NOMEM; }
+    cudaError_t e = cudaMemcpyAsync(h, d, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) { free(h); pav_set_error("density fetch: %s", cudaGetErrorString(e)); return PAVGPU_ERR_CUDA; }
+    *out = h;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch(pavgpu_density_batch *b, pavgpu_density_result *res, uint64_t **kmer_out,
+                                                                                   int32_t **index_out, int8_t **state_mer_out, int8_t **state_out,
+                                                                                   double **kern_fwd_out, double **kern_fwdrev_out,
+                                                                                   double **kern_rev_out, int64_t *n_rows_total)
+{
+    if (!b || !b->ran || !res || !kmer_out || !index_out || !state_mer_out || !state_out || !kern_fwd_out || !kern_fwdrev_out || !kern_rev_out ||
+        !n_rows_total) {
+        pav_set_error("density_batch_fetch: bad argument or batch not run");
+        return PAVGPU_ERR_ARG;
+    }
+    pavgpu_ctx *ctx = b->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    for (int32_t w = 0; w < b->n_win; w++) res[w] = b->res[w];
+    int64_t n = b->rows_total;
+    *n_rows_total = n;
+    CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
+    int rc = 0;
+    rc |= fetch_col(ctx, b->d_kmer, n, kmer_out);
+    rc |= fetch_col(ctx, b->d_index, n, index_out);
+    rc |= fetch_col(ctx, b->d_state_mer, n, state_mer_out);
+    rc |= fetch_col(ctx, b->d_state, n, state_out);
+    rc |= fetch_col(ctx, b->d_k[0], n, kern_fwd_out);
+    rc |= fetch_col(ctx, b->d_k[1], n, kern_fwdrev_out);
+    rc |= fetch_col(ctx, b->d_k[2], n, kern_rev_out);
+    CUDA_TRY(cudaEventRecord(ctx->ev[6], ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    b->stats.ms_d2h = ev_ms(ctx->ev[5], ctx->ev[6]);
+    if (rc) {
+        free(*kmer_out); free(*index_out); free(*state_mer_out); free(*state_out); free(*kern_fwd_out); free(*kern_fwdrev_out); free(*kern_rev_out);
+        return PAVGPU_ERR_NOMEM;
+    }
+    return PAVGPU_OK;
+}

@@ -1,0 +1,246 @@
+// seqstore.cu -- context management and the packed sequence store (2-bit plane + N-mask plane).
+//
+// Replaces, for the hot path, what the reference does per alignment record on the CPU:
+// pysam fetch of whole chromosomes/contigs, Bio reverse_complement and str.upper()
+// (pavlib/cigarcall.py:58-75) and the per-base dict lookups of kanapy's k-mer stream
+// (dep/svpop/dep/kanapy/util/kmer.py:50-69,206-221).
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void pav_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" __attribute__((visibility("default"))) const char *pavgpu_last_error(void) { return g_err; }
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        pav_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return PAVGPU_ERR_CUDA;
+    }
+    return n;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_ctx_create(int device, pavgpu_ctx **ctx_out)
+{
+    if (!ctx_out) { pav_set_error("ctx_out is NULL"); return PAVGPU_ERR_ARG; }
+    *ctx_out = nullptr;
+    CUDA_TRY(cudaSetDevice(device));
+    pavgpu_ctx *c = new pavgpu_ctx();
+    c->device = device;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    *ctx_out = c;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void pavgpu_ctx_destroy(pavgpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    cudaFree(c->flush_buf);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_ctx_device(const pavgpu_ctx *c) { return c ? c->device : -1; }
+extern "C" __attribute__((visibility("default"))) void pavgpu_free_host(void *p) { free(p); }
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_l2_flush(pavgpu_ctx *ctx, size_t bytes)
+{
+    if (!ctx || bytes == 0) { pav_set_error("l2_flush: bad argument"); return PAVGPU_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->flush_bytes < bytes) {
+        cudaFree(ctx->flush_buf);
+        ctx->flush_buf = nullptr;
+        ctx->flush_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->flush_buf, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->flush_buf, ++ctx->flush_val, bytes, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PAVGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack kernel: ASCII -> (2-bit plane, N-mask plane). One thread per 32 bases = one 64-bit plane word
+// and one 32-bit mask word; two 128-bit loads per thread. Pure streaming: 1 B/base in, 0.375 B/base out.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t code_of(uint32_t ch)
+{
+    // A/a 0, C/c 1, G/g 2, T/t 3, everything else 4
+    ch &= 0xDFu;  // fold case
+    return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, int64_t n_words,
+                                                   uint64_t *__restrict__ pack2, uint32_t *__restrict__ nmask)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(ascii + w * 32);
+    uint4 a = __ldcs(src), b = __ldcs(src + 1);
+    uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint64_t word = 0;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t c = code_of((v[i] >> (8 * j)) & 0xFFu);
+            int pos = i * 4 + j;
+            word |= (uint64_t)(c & 3u) << (62 - 2 * pos);
+            mask |= (c >> 2) << pos;
+        }
+    }
+    pack2[w] = word;
+    nmask[w] = mask;
+}
+
+static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, pavgpu_seqstore **out)
+{
+    if (!ctx || n_seq < 0 || (n_seq > 0 && !seq_len) || !out) { pav_set_error("seqstore: bad argument"); return PAVGPU_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    pavgpu_seqstore *s = new pavgpu_seqstore();
+    s->ctx = ctx;
+    s->n_seq = n_seq;
+    s->h_off.resize(n_seq);
+    s->h_len.assign(seq_len, seq_len + n_seq);
+    int64_t off = 0;
+    for (int32_t i = 0; i < n_seq; i++) {
+        if (seq_len[i] < 0 || seq_len[i] >= (int64_t)1 << 31) {
+            pav_set_error("seqstore: sequence %d has unsupported length %lld", i, (long long)seq_len[i]);
+            delete s;
+            return PAVGPU_ERR_ARG;
+        }
+        s->h_off[i] = off;
+        off += (seq_len[i] + SEQ_ALIGN - 1) / SEQ_ALIGN * SEQ_ALIGN;
+    }
+    off += SEQ_ALIGN;  // tail guard so k-mer windows may read one word past the last base
+    s->total_bases = off;
+    s->pack2_bytes = (size_t)(off / 32) * 8;
+    s->nmask_bytes = (size_t)(off / 32) * 4;
+    s->d_off = s->d_len = nullptr;
+    s->d_pack2 = nullptr;
+    s->d_nmask = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&s->d_pack2, s->pack2_bytes)) != cudaSuccess || (e = cudaMalloc(&s->d_nmask, s->nmask_bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_off, sizeof(int64_t) * (n_seq + 1))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_len, sizeof(int64_t) * (n_seq + 1))) != cudaSuccess) {
+        pav_set_error("seqstore: cudaMalloc failed: %s", cudaGetErrorString(e));
+        pavgpu_seqstore_free(s);
+        return PAVGPU_ERR_NOMEM;
+    }
+    if (n_seq) {
+        CUDA_TRY(cudaMemcpyAsync(s->d_off, s->h_off.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_len, s->h_len.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create_empty(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, pavgpu_seqstore **out)
+{
+    return alloc_store(ctx, n_seq, seq_len, out);
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pavgpu_ctx *ctx, int32_t n_seq, const uint8_t *const *seq_ascii, const int64_t *seq_len,
+                                      pavgpu_seqstore **out)
+{
+    if (n_seq > 0 && !seq_ascii) { pav_set_error("seqstore: seq_ascii is NULL"); return PAVGPU_ERR_ARG; }
+    pavgpu_seqstore *s = nullptr;
+    int rc = alloc_store(ctx, n_seq, seq_len, &s);
+    if (rc) return rc;
+    // Stage ASCII in HBM ('N' in the padding so that padding bases get mask = 1), then pack.
+    uint8_t *d_ascii = nullptr;
+    cudaError_t e = cudaMalloc(&d_ascii, (size_t)s->total_bases);
+    if (e != cudaSuccess) {
+        pav_set_error("seqstore: cudaMalloc(%lld) for ASCII staging failed: %s", (long long)s->total_bases, cudaGetErrorString(e));
+        pavgpu_seqstore_free(s);
+        return PAVGPU_ERR_NOMEM;
+    }
+    rc = [&]() -> int {
+        CUDA_TRY(cudaMemsetAsync(d_ascii, 'N', (size_t)s->total_bases, ctx->stream));
+        for (int32_t i = 0; i < n_seq; i++)
+            if (seq_len[i] > 0)
+                CUDA_TRY(cudaMemcpyAsync(d_ascii + s->h_off[i], seq_ascii[i], (size_t)seq_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        int64_t n_words = s->total_bases / 32;
+        int64_t blocks = (n_words + 255) / 256;
+        pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_ascii, n_words, s->d_pack2, s->d_nmask);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PAVGPU_OK;
+    }();
+    cudaFree(d_ascii);
+    if (rc) { pavgpu_seqstore_free(s); return rc; }
+    *out = s;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create_packed(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, const uint64_t *pack2_host,
+                                             const uint32_t *nmask_host, pavgpu_seqstore **out)
+{
+    pavgpu_seqstore *s = nullptr;
+    int rc = alloc_store(ctx, n_seq, seq_len, &s);
+    if (rc) return rc;
+    rc = [&]() -> int {
+        CUDA_TRY(cudaMemcpyAsync(s->d_pack2, pack2_host, s->pack2_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_nmask, nmask_host, s->nmask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PAVGPU_OK;
+    }();
+    if (rc) { pavgpu_seqstore_free(s); return rc; }
+    *out = s;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void pavgpu_seqstore_free(pavgpu_seqstore *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaFree(s->d_pack2);
+    cudaFree(s->d_nmask);
+    cudaFree(s->d_off);
+    cudaFree(s->d_len);
+    delete s;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t pavgpu_seqstore_n_seq(const pavgpu_seqstore *s) { return s ? s->n_seq : -1; }
+extern "C" __attribute__((visibility("default"))) int64_t pavgpu_seqstore_total_bases(const pavgpu_seqstore *s) { return s ? s->total_bases : -1; }
+extern "C" __attribute__((visibility("default"))) int64_t pavgpu_seqstore_offset(const pavgpu_seqstore *s, int32_t i)
+{
+    return (s && i >= 0 && i < s->n_seq) ? s->h_off[i] : -1;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_planes(const pavgpu_seqstore *s, void **d_pack2, size_t *pack2_bytes, void **d_nmask, size_t *nmask_bytes)
+{
+    if (!s) { pav_set_error("seqstore is NULL"); return PAVGPU_ERR_ARG; }
+    if (d_pack2) *d_pack2 = s->d_pack2;
+    if (pack2_bytes) *pack2_bytes = s->pack2_bytes;
+    if (d_nmask) *d_nmask = s->d_nmask;
+    if (nmask_bytes) *nmask_bytes = s->nmask_bytes;
+    return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_export(const pavgpu_seqstore *s, uint64_t *pack2_host, uint32_t *nmask_host)
+{
+    if (!s) { pav_set_error("seqstore is NULL"); return PAVGPU_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    if (pack2_host) CUDA_TRY(cudaMemcpy(pack2_host, s->d_pack2, s->pack2_bytes, cudaMemcpyDeviceToHost));
+    if (nmask_host) CUDA_TRY(cudaMemcpy(nmask_host, s->d_nmask, s->nmask_bytes, cudaMemcpyDeviceToHost));
+    return PAVGPU_OK;
+}

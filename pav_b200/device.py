@@ -1,0 +1,228 @@
+"""Thin object layer over the C ABI: device contexts, sequence stores, the CIGAR-walk call.
+
+No torch, no CPU fallback: every function here ends in a libpavgpu.so call on a CUDA device.
+Device selection follows SURVEY 8(b): ``PAVGPU_DEVICES`` (comma list, default all visible) and
+``PAVGPU_DEVICE_INDEX`` (which entry this process uses, default 0) so concurrent Snakemake jobs can
+be spread over the GPUs of a box without touching the rule files.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import c_i32, c_i64, c_vp
+
+_CONTEXTS = {}
+
+
+class Context:
+    def __init__(self, device=0):
+        L = _capi.lib()
+        n = L.pavgpu_device_count()
+        if n <= 0:
+            raise RuntimeError('pav_b200: no usable CUDA device (pavgpu_device_count() = %d: %s); '
+                               'the hot path has no CPU fallback' % (n, L.pavgpu_last_error().decode()))
+        if not 0 <= device < n:
+            raise RuntimeError(f'pav_b200: device {device} out of range (0..{n - 1})')
+        h = c_vp()
+        _capi.check(L.pavgpu_ctx_create(device, ctypes.byref(h)), 'pavgpu_ctx_create')
+        self.handle = h
+        self.device = device
+
+    def l2_flush(self, nbytes=256 << 20):
+        _capi.check(_capi.lib().pavgpu_l2_flush(self.handle, nbytes), 'pavgpu_l2_flush')
+
+    def close(self):
+        if self.handle:
+            _capi.lib().pavgpu_ctx_destroy(self.handle)
+            self.handle = None
+
+
+def default_device():
+    devs = os.environ.get('PAVGPU_DEVICES')
+    idx = int(os.environ.get('PAVGPU_DEVICE_INDEX', os.environ.get('LOCAL_RANK', '0')))
+    if devs:
+        lst = [int(x) for x in devs.split(',') if x.strip() != '']
+        return lst[idx % len(lst)]
+    n = _capi.lib().pavgpu_device_count()
+    return idx % n if n > 0 else 0
+
+
+def get_context(device=None):
+    if device is None:
+        device = default_device()
+    ctx = _CONTEXTS.get(device)
+    if ctx is None:
+        ctx = _CONTEXTS[device] = Context(device)
+    return ctx
+
+
+class SeqStore:
+    """Named sequences packed into HBM (2-bit plane + N-mask plane), plus the host bytes for slicing."""
+
+    def __init__(self, ctx, names, arrays, keep_host=True):
+        L = _capi.lib()
+        self.ctx = ctx
+        self.names = [str(n) for n in names]
+        self.ids = {n: i for i, n in enumerate(self.names)}
+        arrays = [np.ascontiguousarray(a, dtype=np.uint8) for a in arrays]
+        self.lengths = np.array([len(a) for a in arrays], dtype=np.int64)
+        n = len(arrays)
+        ptrs = (c_vp * max(n, 1))(*[a.ctypes.data for a in arrays])
+        h = c_vp()
+        _capi.check(L.pavgpu_seqstore_create(ctx.handle, n, ptrs, self.lengths.ctypes.data_as(ctypes.POINTER(c_i64)),
+                                             ctypes.byref(h)), 'pavgpu_seqstore_create')
+        self.handle = h
+        self.host = arrays if keep_host else None
+
+    @classmethod
+    def from_packed(cls, ctx, names, lengths, pack2, nmask):
+        L = _capi.lib()
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.names = [str(n) for n in names]
+        self.ids = {n: i for i, n in enumerate(self.names)}
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        h = c_vp()
+        if pack2 is None:
+            _capi.check(L.pavgpu_seqstore_create_empty(ctx.handle, len(self.names), self.lengths.ctypes.data_as(ctypes.POINTER(c_i64)),
+                                                       ctypes.byref(h)), 'pavgpu_seqstore_create_empty')
+        else:
+            _capi.check(L.pavgpu_seqstore_create_packed(ctx.handle, len(self.names), self.lengths.ctypes.data_as(ctypes.POINTER(c_i64)),
+                                                        _capi.ptr(pack2), _capi.ptr(nmask), ctypes.byref(h)),
+                        'pavgpu_seqstore_create_packed')
+        self.handle = h
+        self.host = None
+        return self
+
+    def plane_sizes(self):
+        L = _capi.lib()
+        p2, pm = c_vp(), c_vp()
+        b2, bm = ctypes.c_size_t(), ctypes.c_size_t()
+        _capi.check(L.pavgpu_seqstore_planes(self.handle, ctypes.byref(p2), ctypes.byref(b2), ctypes.byref(pm), ctypes.byref(bm)))
+        return p2.value, b2.value, pm.value, bm.value
+
+    def export(self):
+        _, b2, _, bm = self.plane_sizes()
+        pack2 = np.empty(b2 // 8, dtype=np.uint64)
+        nmask = np.empty(bm // 4, dtype=np.uint32)
+        _capi.check(_capi.lib().pavgpu_seqstore_export(self.handle, _capi.ptr(pack2), _capi.ptr(nmask)))
+        return pack2, nmask
+
+    def offset(self, i):
+        return int(_capi.lib().pavgpu_seqstore_offset(self.handle, i))
+
+    def broadcast(self, unique_id, rank, n_ranks):
+        """NCCL broadcast of both planes from rank 0. Returns device milliseconds."""
+        ms = ctypes.c_float()
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        _capi.check(_capi.lib().pavgpu_seqstore_broadcast(self.ctx.handle, self.handle, _capi.ptr(buf), rank, n_ranks,
+                                                          ctypes.byref(ms)), 'pavgpu_seqstore_broadcast')
+        return ms.value
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _capi.lib().pavgpu_seqstore_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def nccl_unique_id():
+    buf = np.zeros(128, dtype=np.uint8)
+    _capi.check(_capi.lib().pavgpu_nccl_unique_id(_capi.ptr(buf)), 'pavgpu_nccl_unique_id')
+    return buf.tobytes()
+
+
+def parse_cigars(cigars):
+    """Tokenise CIGAR strings on the host (C): -> (ops uint32, op_off int64[n+1], ParseErr)."""
+    L = _capi.lib()
+    n = len(cigars)
+    enc = [c.encode('ascii') if isinstance(c, str) else bytes(c) for c in cigars]
+    text_off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum([len(e) for e in enc], out=text_off[1:])
+    blob = b''.join(enc)
+    ops_p = c_vp()
+    op_off = np.zeros(n + 1, dtype=np.int64)
+    err = _capi.ParseErr()
+    _capi.check(L.pavgpu_cigar_parse(blob, text_off.ctypes.data_as(ctypes.POINTER(c_i64)), n, ctypes.byref(ops_p),
+                                     op_off.ctypes.data_as(ctypes.POINTER(c_i64)), ctypes.byref(err)), 'pavgpu_cigar_parse')
+    ops = _capi.take_host_array(ops_p.value, int(op_off[n]), np.uint32)
+    return ops, op_off, err
+
+
+class CigarBatch:
+    """Alignment records resident in HBM (what bench.py's device-resident `value` leg times)."""
+
+    def __init__(self, ctx, ref_id, qry_id, pos, rev, ops, op_off):
+        L = _capi.lib()
+        self.ctx = ctx
+        self.n_rec = len(ref_id)
+        a = [np.ascontiguousarray(ref_id, np.int32), np.ascontiguousarray(qry_id, np.int32), np.ascontiguousarray(pos, np.int32),
+             np.ascontiguousarray(rev, np.uint8), np.ascontiguousarray(ops, np.uint32), np.ascontiguousarray(op_off, np.int64)]
+        h = c_vp()
+        _capi.check(L.pavgpu_cigar_batch_create(ctx.handle, self.n_rec, *[_capi.ptr(x) for x in a], ctypes.byref(h)),
+                    'pavgpu_cigar_batch_create')
+        self.handle = h
+
+    def run(self, ref_store, qry_store):
+        st = _capi.CigarStats()
+        _capi.check(_capi.lib().pavgpu_cigar_batch_run(self.handle, ref_store.handle, qry_store.handle, ctypes.byref(st)),
+                    'pavgpu_cigar_batch_run')
+        return st
+
+    def fetch(self):
+        L = _capi.lib()
+        ps, pi = c_vp(), c_vp()
+        ns, ni = c_i64(), c_i64()
+        err = _capi.CigarErr()
+        _capi.check(L.pavgpu_cigar_batch_fetch(self.handle, ctypes.byref(ps), ctypes.byref(ns), ctypes.byref(pi), ctypes.byref(ni),
+                                               ctypes.byref(err)), 'pavgpu_cigar_batch_fetch')
+        snv = _capi.take_host_array(ps.value, ns.value, _capi.SNV_ROW)
+        indel = _capi.take_host_array(pi.value, ni.value, _capi.INDEL_ROW)
+        return snv, indel, err
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _capi.lib().pavgpu_cigar_batch_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def cigar_call(ctx, ref_store, qry_store, ref_id, qry_id, pos, rev, ops, op_off):
+    """One-shot host-buffer call (pavgpu_cigar_call): returns (snv rows, indel rows, CigarErr, CigarStats)."""
+    L = _capi.lib()
+    a = [np.ascontiguousarray(ref_id, np.int32), np.ascontiguousarray(qry_id, np.int32), np.ascontiguousarray(pos, np.int32),
+         np.ascontiguousarray(rev, np.uint8), np.ascontiguousarray(ops, np.uint32), np.ascontiguousarray(op_off, np.int64)]
+    ps, pi = c_vp(), c_vp()
+    ns, ni = c_i64(), c_i64()
+    err, st = _capi.CigarErr(), _capi.CigarStats()
+    _capi.check(L.pavgpu_cigar_call(ctx.handle, ref_store.handle, qry_store.handle, len(a[0]), *[_capi.ptr(x) for x in a],
+                                    ctypes.byref(ps), ctypes.byref(ns), ctypes.byref(pi), ctypes.byref(ni), ctypes.byref(err),
+                                    ctypes.byref(st)), 'pavgpu_cigar_call')
+    snv = _capi.take_host_array(ps.value, ns.value, _capi.SNV_ROW)
+    indel = _capi.take_host_array(pi.value, ni.value, _capi.INDEL_ROW)
+    return snv, indel, err, st
+
+
+def homology(seq, sv, positions, ctx=None):
+    """Device evaluation of left/right homology for upper-case strings (parity helper)."""
+    ctx = ctx or get_context()
+    pos = np.ascontiguousarray(positions, dtype=np.int64)
+    left = np.zeros(len(pos), np.int32)
+    right = np.zeros(len(pos), np.int32)
+    s, v = seq.encode(), sv.encode()
+    _capi.check(_capi.lib().pavgpu_homology(ctx.handle, len(pos), s, len(s), v, len(v), _capi.ptr(pos), _capi.ptr(left), _capi.ptr(right)),
+                'pavgpu_homology')
+    return left, right

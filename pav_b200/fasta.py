@@ -1,0 +1,136 @@
+"""Indexed FASTA access without pysam/htslib (absent from the image and not needed on the hot path).
+
+Replaces ``pysam.FastaFile(fn).fetch(name[, start, end])`` as used by the reference
+(pavlib/cigarcall.py:58-66, pavlib/seq.py:339-351). Sequences come back as ``numpy.uint8`` arrays
+of the original bytes (case and IUPAC codes preserved) -- they are uploaded to the GPU as they are
+and sliced on the host for the REF / ALT / SEQ columns.
+
+Plain FASTA is memory-mapped and addressed through the samtools ``.fai`` (built in memory when the
+index file is missing). gzip / bgzip files are inflated once per process (any multi-member gzip
+stream; ``.gzi`` random access is not needed because the hot path reads whole records).
+"""
+import gzip
+import os
+
+import numpy as np
+
+_CACHE = {}
+
+
+class Fasta:
+    def __init__(self, path):
+        self.path = path
+        self._plain = not str(path).endswith('.gz')
+        if self._plain:
+            self._buf = np.memmap(path, dtype=np.uint8, mode='r') if os.path.getsize(path) else np.zeros(0, np.uint8)
+        else:
+            with gzip.open(path, 'rb') as fh:
+                self._buf = np.frombuffer(fh.read(), dtype=np.uint8)
+        self.index = self._read_fai() if (self._plain and os.path.exists(path + '.fai')) else self._scan_index()
+        self._seq_cache = {}
+
+    def _read_fai(self):
+        idx = {}
+        with open(self.path + '.fai') as fh:
+            for line in fh:
+                tok = line.rstrip('\n').split('\t')
+                if len(tok) >= 5:
+                    idx[tok[0]] = (int(tok[1]), int(tok[2]), int(tok[3]), int(tok[4]))
+        return idx
+
+    def _scan_index(self):
+        buf = self._buf
+        idx = {}
+        gt = np.flatnonzero(buf == ord('>'))
+        nl = np.flatnonzero(buf == 10)
+        # keep only '>' at line starts
+        starts = [g for g in gt.tolist() if g == 0 or buf[g - 1] == 10]
+        for i, g in enumerate(starts):
+            k = np.searchsorted(nl, g)
+            hdr_end = int(nl[k]) if k < len(nl) else len(buf)
+            name = bytes(buf[g + 1:hdr_end]).split()[0].decode() if hdr_end > g + 1 else ''
+            body_start = hdr_end + 1
+            body_end = starts[i + 1] if i + 1 < len(starts) else len(buf)
+            body_nl = nl[np.searchsorted(nl, body_start):np.searchsorted(nl, body_end)]
+            if len(body_nl):
+                linebases = int(body_nl[0]) - body_start
+                if linebases > 0 and body_start + linebases - 1 < len(buf) and buf[body_start + linebases - 1] == 13:
+                    linebases -= 1
+                    linewidth = linebases + 2
+                else:
+                    linewidth = linebases + 1
+            else:
+                linebases = body_end - body_start
+                linewidth = linebases
+            n_nl = len(body_nl)
+            total = body_end - body_start
+            cr = (linewidth - linebases - 1) if linewidth > linebases else 0
+            length = total - n_nl * (1 + max(cr, 0))
+            idx[name] = (int(length), int(body_start), int(max(linebases, 1)), int(max(linewidth, 1)))
+        return idx
+
+    def names(self):
+        return list(self.index.keys())
+
+    def length(self, name):
+        return self.index[str(name)][0]
+
+    def fetch_array(self, name, start=None, end=None):
+        """Bases ``[start, end)`` of record ``name`` as a uint8 array (whole record by default)."""
+        name = str(name)
+        if name not in self.index:
+            raise KeyError(f'sequence {name!r} not found in {self.path}')
+        length, offset, linebases, linewidth = self.index[name]
+        start = 0 if start is None else max(int(start), 0)
+        end = length if end is None else min(int(end), length)
+        if end <= start:
+            return np.zeros(0, dtype=np.uint8)
+        if start == 0 and end == length and name in self._seq_cache:
+            return self._seq_cache[name]
+        first_line, last_line = start // linebases, (end - 1) // linebases
+        b0 = offset + first_line * linewidth
+        b1 = min(offset + last_line * linewidth + linebases, len(self._buf))
+        raw = np.asarray(self._buf[b0:b1])
+        n_lines = last_line - first_line + 1
+        if n_lines == 1:
+            seq = raw
+        else:
+            pad = n_lines * linewidth - len(raw)
+            block = np.concatenate((raw, np.zeros(pad, dtype=np.uint8))) if pad else raw
+            seq = block.reshape(n_lines, linewidth)[:, :linebases].reshape(-1)
+        lo = start - first_line * linebases
+        seq = np.ascontiguousarray(seq[lo:lo + (end - start)])
+        if start == 0 and end == length:
+            if len(self._seq_cache) > 64:
+                self._seq_cache.clear()
+            self._seq_cache[name] = seq
+        return seq
+
+    def fetch(self, name, start=None, end=None):
+        """``pysam.FastaFile.fetch`` look-alike returning ``str``."""
+        return self.fetch_array(name, start, end).tobytes().decode('ascii')
+
+
+def open_fasta(path):
+    """Process-wide cache keyed by (path, mtime, size)."""
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    fa = _CACHE.get(key)
+    if fa is None:
+        if len(_CACHE) > 8:
+            _CACHE.clear()
+        fa = _CACHE[key] = Fasta(path)
+    return fa
+
+
+# Complement over bytes: Biopython's ambiguous-DNA table, case preserved (Bio.Seq.reverse_complement is
+# what the reference applies to REV contigs, pavlib/cigarcall.py:69-70).
+COMPLEMENT = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b'ACGTMRWSYKVHDBNacgtmrwsykvhdbn', b'TGCAKYWSRMBDHVNtgcakywsrmbdhvn'):
+    COMPLEMENT[_a] = _b
+UPPER = np.arange(256, dtype=np.uint8)
+UPPER[ord('a'):ord('z') + 1] -= 32
+
+
+def reverse_complement(arr):
+    return COMPLEMENT[arr[::-1]]

@@ -1,0 +1,297 @@
+"""Inversion scan over flagged loci with the reference's interface (pavlib/inv.py).
+
+``scan_for_inv`` keeps the reference's control flow (expand the region x1.5, balance .25/.5/.75,
+stop rules, breakpoint derivation, size-proportion test, flank annotation: pavlib/inv.py:149-454) but
+each expansion scores its window through ``pavgpu_density_batch_*`` in-process instead of spawning
+``python3 scripts/density.py`` and unpickling its stdout (pavlib/inv.py:249-288).
+"""
+import numpy as np
+import pandas as pd
+
+from . import density as pavdensity
+from . import seq as pavseq
+from .constants import ERR_INV_FAIL
+from .. import fasta
+
+INITIAL_EXPAND = 4000
+EXPAND_FACTOR = 1.5
+MAX_REGION_SIZE = 1200000
+MIN_INFORMATIVE_KMERS = 2000
+MIN_KMER_STATE_COUNT = 20
+DENSITY_SMOOTH_FACTOR = 1
+MIN_INV_KMER_RUN = 100
+MIN_QRY_REF_PROP = 0.6
+DEFAULT_MIN_EXP_COUNT = 1
+DEFAULT_STATE_RUN_SMOOTH = 20
+CALL_SOURCE = 'FLAG-DEN'
+
+# KMER_LOC_STATE[in-upstream, in-dnstream] (pavlib/inv.py:46-51)
+KMER_LOC_STATE = np.asarray([['NA', 'OTHER'], ['SAME', 'NA']])
+
+
+class InvCall:
+    """An inversion call and the density table that supports it (reference: pavlib/inv.py:54-118)."""
+
+    def __init__(self, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner,
+                 region_ref_discovery, region_tig_discovery, region_flag, df):
+        self.region_ref_outer = region_ref_outer
+        self.region_ref_inner = region_ref_inner
+        self.region_tig_outer = region_tig_outer
+        self.region_tig_inner = region_tig_inner
+        self.region_ref_discovery = region_ref_discovery
+        self.region_tig_discovery = region_tig_discovery
+        self.region_flag = region_flag
+        self.df = df
+        self.svlen = len(region_ref_outer)
+        self.id = '{}-{}-INV-{}'.format(region_ref_outer.chrom, region_ref_outer.pos + 1, self.svlen)
+
+    def __repr__(self):
+        return self.id
+
+
+class _Span:
+    __slots__ = ('begin', 'end', 'data')
+
+    def __init__(self, begin, end, data):
+        self.begin, self.end, self.data = begin, end, data
+
+
+class SrsTree:
+    """Minimal stand-in for the intervaltree the reference uses for --staterunsmooth by region size:
+    supports ``tree[a:b] = value`` and ``tree[point]`` -> set of objects with ``.data``."""
+
+    def __init__(self):
+        self._spans = []
+
+    def __setitem__(self, key, value):
+        self._spans.append(_Span(key.start, key.stop, value))
+
+    def __getitem__(self, point):
+        return {s for s in self._spans if s.begin <= point < s.end}
+
+    def __len__(self):
+        return len(self._spans)
+
+
+def get_srs_tree(srs_tuple_list):
+    """(region size limit, state-run-smooth) tuples -> lookup structure (reference: pavlib/inv.py:564-620)."""
+    tree = SrsTree()
+    if srs_tuple_list is None or len(srs_tuple_list) == 0:
+        tree[0:np.inf] = DEFAULT_STATE_RUN_SMOOTH
+        return tree
+    for el in srs_tuple_list:
+        if len(el) != 2:
+            raise RuntimeError('Element in "state run smooth" tuple list that is not length 2: ' + str(el))
+    srs_tuple_list = sorted(srs_tuple_list)
+    last_lim, last_smooth = int(srs_tuple_list[0][0]), int(srs_tuple_list[0][1])
+    if last_lim < 0:
+        raise RuntimeError('State run inversion size limits must be 0 or greater: {}'.format(last_lim))
+    if last_smooth < 4:
+        raise RuntimeError('Not tested with "state run smooth" factor less than 4: {}'.format(last_smooth))
+    if last_lim > 0:
+        tree[0:last_lim] = np.min([last_lim, 20])
+    for lim, smooth in srs_tuple_list[1:]:
+        lim, smooth = int(lim), int(smooth)
+        if smooth < 20:
+            raise RuntimeError('Not tested with "state run smooth" factor less than 20: {}'.format(smooth))
+        if lim == last_lim:
+            raise RuntimeError('Duplicate limit in state run limits: {}'.format(lim))
+        tree[last_lim:lim] = last_smooth
+        last_lim, last_smooth = lim, smooth
+    tree[last_lim:np.inf] = last_smooth
+    return tree
+
+
+def _write_log(message, log):
+    if log is None:
+        return
+    log.write(message)
+    log.write('\n')
+    log.flush()
+
+
+def scan_for_inv(region_flag, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree=None, max_region_size=None, threads=1,
+                 log=None, srs_tree=None, min_exp_count=DEFAULT_MIN_EXP_COUNT):
+    """
+    Scan a flagged region for an inversion, expanding as necessary.
+
+    Same parameters and return value as the reference (``InvCall`` or ``None``). ``k_util`` only needs a
+    ``k_size`` attribute; ``threads`` is accepted and ignored (the window is scored on the GPU);
+    ``align_lift`` needs ``lift_region_to_qry`` / ``lift_region_to_sub`` (the reference's AlignLift or
+    ``pav_b200.pavlib.lift.AlignLift``).
+    """
+    if min_exp_count is None:
+        min_exp_count = DEFAULT_MIN_EXP_COUNT
+    if max_region_size is None:
+        max_region_size = MAX_REGION_SIZE
+    k_size = int(k_util.k_size)
+
+    _write_log('Scanning for inversions in flagged region: {} (flagged region record id = {})'.format(
+        region_flag, region_flag.region_id()), log)
+
+    df_fai = pavseq.get_df_fai(ref_fa_name + '.fai')
+    region_ref = region_flag.copy()
+    region_ref.expand(INITIAL_EXPAND, min_pos=0, max_end=df_fai, shift=True)
+    expansion_count = 0
+
+    n_tree_chrom = n_tree[region_ref.chrom] if (n_tree is not None and region_ref.chrom in n_tree.keys()) else None
+    if srs_tree is None:
+        srs_tree = get_srs_tree(None)
+    elif not hasattr(srs_tree, '__getitem__'):
+        raise NotImplementedError('Custom state-run-smooth parameters are not currently implemented')
+
+    while True:
+        if 0 < max_region_size < len(region_ref):
+            _write_log('Region size exceeds max: {} ({} > {})'.format(region_ref, len(region_ref), max_region_size), log)
+            return None
+        if n_tree_chrom is not None and len(n_tree_chrom[region_ref.pos:region_ref.end]) > 0:
+            _write_log('Region overlaps N bases: {}'.format(region_ref), log)  # logged only, as in the reference
+
+        region_tig = align_lift.lift_region_to_qry(region_ref)
+        if region_tig is None:
+            _write_log('Could not lift reference region onto contigs: {}'.format(region_ref), log)
+            return None
+        expansion_count += 1
+        _write_log('Scanning region: {}'.format(region_ref), log)
+
+        srs = list(srs_tree[len(region_tig)])[0].data
+        returncode, df = pavdensity.density_table(
+            region_ref, region_tig, ref_fa_name, tig_fa_name, k=k_size, rev=bool(region_tig.is_rev), state_run_smooth=int(srs),
+            min_informative=MIN_INFORMATIVE_KMERS, min_state_count=MIN_KMER_STATE_COUNT, smooth=DENSITY_SMOOTH_FACTOR)
+        if returncode != 0:
+            _write_log('Received return code {} from the density scan for region {}:\n'.format(returncode, str(region_ref)), log)
+            if returncode != ERR_INV_FAIL:
+                raise RuntimeError('Density scan failed with code {} for region {}'.format(returncode, region_ref))
+            return None
+
+        if df.shape[0] > 0:
+            state_rl = [record for record in pavdensity.rl_encoder(df)]
+            condensed_states = [record[0] for record in state_rl]
+
+            if len(state_rl) == 1 and state_rl[0][0] in {0, -1} and expansion_count >= min_exp_count:
+                _write_log('Found no inverted k-mer states after {} expansion(s)'.format(expansion_count), log)
+                return None
+
+            if len(condensed_states) > 2 and condensed_states[0] == 0 and condensed_states[-1] == 0:
+                break
+
+            last_len = len(region_ref)
+            expand_bp = np.int32(len(region_ref) * EXPAND_FACTOR)
+            if len(condensed_states) > 2:
+                if condensed_states[0] == 0:
+                    balance = 0.25
+                elif condensed_states[-1] == 0:
+                    balance = 0.75
+                else:
+                    balance = 0.5
+            else:
+                balance = 0.5
+            region_ref.expand(expand_bp, min_pos=0, max_end=df_fai, shift=True, balance=balance)
+            if len(region_ref) == last_len:
+                _write_log('Reached reference limits, cannot expand', log)
+                return None
+        else:
+            _write_log('No informative reference k-mers in forward or reverse orientation in region', log)
+            return None
+
+    # ---- characterise the found region (pavlib/inv.py:346-454)
+    if not np.any([record[0] == 2 for record in state_rl]):
+        _write_log('No inverted states found', log)
+        return None
+    max_inv_run = np.max([record[1] for record in state_rl if record[0] == 2])
+    if max_inv_run < MIN_INV_KMER_RUN:
+        _write_log('Longest run of strictly inverted k-mers ({}) does not meet the minimum threshold ({})'.format(
+            max_inv_run, MIN_INV_KMER_RUN), log)
+        return None
+    if state_rl[0][0] != 0 or state_rl[-1][0] != 0:
+        raise RuntimeError('Found INV region not flanked by reference sequence (program bug): {}'.format(region_ref))
+    state_rl_inv = [record for record in state_rl if record[0] == 2]
+
+    region_tig_outer = pavseq.Region(region_tig.chrom, state_rl[1][2] + region_tig.pos,
+                                     state_rl[-2][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
+    region_tig_inner = pavseq.Region(region_tig.chrom, state_rl_inv[0][2] + region_tig.pos,
+                                     state_rl_inv[-1][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
+
+    region_ref_outer = align_lift.lift_region_to_sub(region_tig_outer)
+    if region_ref_outer is None:
+        _write_log('Failed lifting outer INV region to reference: {}'.format(region_tig_outer), log)
+        return None
+    region_ref_inner = align_lift.lift_region_to_sub(region_tig_inner, gap=True)
+    if region_ref_inner is None:
+        region_ref_inner = region_ref_outer
+
+    print('INV Found: outer={}, inner={} (ref outer={}, inner={})'.format(
+        region_tig_outer, region_tig_inner, region_ref_outer, region_ref_inner))
+
+    if len(region_ref_outer) < len(region_tig_outer) * MIN_QRY_REF_PROP:
+        _write_log('Reference region too short: Reference region length ({:,d}) is not within {:.2f}% of the contig region length ({:,d})'.format(
+            len(region_ref_outer), MIN_QRY_REF_PROP * 100, len(region_tig_outer)), log)
+        return None
+    if len(region_tig_outer) < len(region_ref_outer) * MIN_QRY_REF_PROP:
+        _write_log('Contig region too short: Contig region length ({:,d}) is not within {:.2f}% of the reference region length ({:,d})'.format(
+            len(region_tig_outer), MIN_QRY_REF_PROP * 100, len(region_ref_outer)), log)
+        return None
+
+    # NOTE: the reference passes region_ref where annotate_inv_dup_mers expects the contig discovery region
+    # (pavlib/inv.py:440-442); reproduced as is.
+    df = annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref,
+                               ref_fa_name, k_util)
+    inv_call = InvCall(region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref, region_tig,
+                       region_flag, df)
+    _write_log('Found inversion: {}'.format(inv_call), log)
+    return inv_call
+
+
+_CODE = np.full(256, 255, dtype=np.uint8)
+for _c, _v in zip(b'ACGTacgt', (0, 1, 2, 3, 0, 1, 2, 3)):
+    _CODE[_c] = _v
+
+
+def _region_canonical_kmers(region, fa_name, k):
+    """Set of canonical k-mers (min of k-mer and reverse complement) of a small reference region (host numpy;
+    flank regions are a few kbp -- reference: pavlib/inv.py:507-513, kanapy kmer.py:135-148)."""
+    if len(region) < k:
+        return set()
+    arr = fasta.open_fasta(fa_name).fetch_array(region.chrom, region.pos, region.end)
+    code = _CODE[arr]
+    n = len(code) - k + 1
+    if n <= 0:
+        return set()
+    bad = np.concatenate(([0], np.cumsum(code == 255)))
+    ok = (bad[k:] - bad[:-k]) == 0
+    c64 = np.where(code == 255, 0, code).astype(np.uint64)
+    fwd = np.zeros(n, dtype=np.uint64)
+    rc = np.zeros(n, dtype=np.uint64)
+    for t in range(k):
+        fwd = (fwd << np.uint64(2)) | c64[t:t + n]
+        rc = rc | ((np.uint64(3) - c64[t:t + n]) << np.uint64(2 * t))
+    can = np.minimum(fwd, rc)[ok]
+    return set(int(x) for x in can.tolist())
+
+
+def annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_tig_discovery,
+                          ref_fa, k_util):
+    """Add FLANK (UP / DN / '') and MATCH (SAME / OTHER / NaN) columns for k-mers inside flanking inverted
+    duplications (reference: pavlib/inv.py:457-561; MATCH tests the raw k-mer against canonical sets, as there)."""
+    k = int(k_util.k_size)
+    dup_ref_up = pavseq.Region(region_ref_outer.chrom, region_ref_outer.pos, region_ref_inner.pos)
+    dup_ref_dn = pavseq.Region(region_ref_outer.chrom, region_ref_inner.end, region_ref_outer.end)
+    dup_tig_up = pavseq.Region(region_tig_outer.chrom, region_tig_outer.pos, region_tig_inner.pos)
+    dup_tig_dn = pavseq.Region(region_tig_outer.chrom, region_tig_inner.end, region_tig_outer.end)
+    ref_set_up = _region_canonical_kmers(dup_ref_up, ref_fa, k)
+    ref_set_dn = _region_canonical_kmers(dup_ref_dn, ref_fa, k)
+
+    qry_index = df['INDEX'].to_numpy() + region_tig_discovery.pos
+    flank = np.full(df.shape[0], '', dtype=object)
+    flank[(qry_index >= dup_tig_up.pos) & (qry_index < dup_tig_up.end - k)] = 'UP'
+    flank[(qry_index >= dup_tig_dn.pos) & (qry_index < dup_tig_dn.end - k)] = 'DN'
+    match = np.full(df.shape[0], '', dtype=object)
+    kmers = df['KMER'].tolist()
+    for i in np.flatnonzero(flank == 'UP').tolist():
+        match[i] = KMER_LOC_STATE[int(kmers[i] in ref_set_up), int(kmers[i] in ref_set_dn)]
+    for i in np.flatnonzero(flank == 'DN').tolist():
+        match[i] = KMER_LOC_STATE[int(kmers[i] in ref_set_dn), int(kmers[i] in ref_set_up)]
+    match = [np.nan if v == 'NA' else v for v in match.tolist()]
+    df['FLANK'] = flank
+    df['MATCH'] = match
+    return df

@@ -85,53 +85,97 @@ def _indel_lengths(rng, n, sv_frac):
     return ln
 
 
-def plant_alignment(rng, ref, start, span, n_edit, grid=50, snv_frac=0.8, ins_frac=0.1,
+TR_SPACING = 2500   # one synthetic tandem-repeat array per TR_SPACING bp of reference
+TR_OFFSET = 100
+TR_MAX_LEN = 6 * 50
+
+
+def make_reference(seed, n_chrom, chrom_len, chrom_prefix='chr', tandem_repeats=True):
+    """Reference chromosomes (iid uniform ACGT) with tandem-repeat arrays (unit 1-6 bp x 5-50 copies)
+    planted every ``TR_SPACING`` bp. Depends on ``seed`` only, so every rank of a multi-GPU run
+    regenerates the identical reference. Returns ``(ref dict, tr dict: chrom -> (pos, unit_len, copies))``.
+    """
+    rng = np.random.default_rng([seed, 0xA11])
+    ref, trs = {}, {}
+    for c in range(n_chrom):
+        name = f'{chrom_prefix}{c + 1}'
+        arr = random_seq(rng, chrom_len)
+        n_tr = max((chrom_len - TR_OFFSET - TR_MAX_LEN) // TR_SPACING, 0) if tandem_repeats else 0
+        pos = np.arange(n_tr, dtype=np.int64) * TR_SPACING + TR_OFFSET
+        unit = rng.integers(1, 7, size=n_tr)
+        copies = rng.integers(5, 51, size=n_tr)
+        units = random_seq(rng, 6 * n_tr).reshape(n_tr, 6) if n_tr else np.zeros((0, 6), np.uint8)
+        # fill arrays: base t of array i is units[i, t % unit[i]]
+        tot = unit * copies
+        idx = _ragged_arange(tot)
+        owner = np.repeat(np.arange(n_tr), tot)
+        arr[np.repeat(pos, tot) + idx] = units[owner, idx % np.repeat(unit, tot)]
+        ref[name] = arr
+        trs[name] = (pos, unit, copies)
+    return ref, trs
+
+
+def plant_alignment(rng, ref, tr, start, span, n_edit, grid=50, snv_frac=0.8, ins_frac=0.1,
                     x_run_frac=0.05, sv_frac=0.02, tr_frac=0.2, clip_l=0, clip_r=0, lower_ins=False):
-    """Build one aligned query over ``ref[start:start+span]`` (``ref`` is modified in place where
-    tandem repeats are planted).
+    """Build one aligned query over ``ref[start:start+span]`` (``ref`` is read-only here).
+
+    ``tr`` = ``(pos, unit_len, copies)`` of the tandem-repeat arrays of this chromosome; a fraction
+    ``tr_frac`` of the indels is placed inside such arrays, k whole units after j whole units (not
+    left-aligned, which exercises left-shift and wrap-around homology).
 
     Returns ``(query uint8 array in reference orientation incl. clips, cigar str, ref_span)``.
     """
+    seg = ref[start:start + span]
     n_cells = span // grid - 2
     n_edit = min(n_edit, max(n_cells, 0))
-    cells = np.sort(rng.choice(n_cells, size=n_edit, replace=False)) + 1 if n_edit else np.zeros(0, np.int64)
-    pos = cells.astype(np.int64) * grid + rng.integers(0, grid // 2, size=n_edit)
-
     u = rng.random(n_edit)
     kind = np.where(u < snv_frac, 0, np.where(u < snv_frac + ins_frac, 1, 2))  # 0 X, 1 I, 2 D
+    is_indel = kind > 0
+    want_tr = is_indel & (rng.random(n_edit) < tr_frac)
+
+    # tandem-repeat arrays fully inside the span
+    tpos, tunit, tcopies = tr if tr is not None else (np.zeros(0, np.int64),) * 3
+    inside = np.flatnonzero((tpos >= start + grid) & (tpos + tunit * tcopies <= start + span - grid)) if len(tpos) else np.zeros(0, np.int64)
+    n_tr = min(int(want_tr.sum()), len(inside))
+    tr_idx = np.flatnonzero(want_tr)[:n_tr]
+    arrays = rng.choice(inside, size=n_tr, replace=False) if n_tr else np.zeros(0, np.int64)
+    is_tr = np.zeros(n_edit, dtype=bool)
+    is_tr[tr_idx] = True
+    want_tr &= is_tr
+
+    cells = (np.sort(rng.choice(n_cells, size=n_edit, replace=False)) + 1) if n_edit else np.zeros(0, np.int64)
+    pos = cells.astype(np.int64) * grid + rng.integers(0, grid // 2, size=n_edit)
     ln = np.ones(n_edit, dtype=np.int64)
     xrun = (kind == 0) & (rng.random(n_edit) < x_run_frac)
     ln[xrun] = rng.integers(2, 4, size=int(xrun.sum()))
-    is_indel = kind > 0
     ln[is_indel] = _indel_lengths(rng, int(is_indel.sum()), sv_frac)
 
-    # Tandem repeats: plant unit x copies in the reference right at the site, the indel is k units
-    # placed after j whole units (not left-aligned => exercises left-shift + wrap-around homology).
-    tr = is_indel & (rng.random(n_edit) < tr_frac)
-    tr_unit = rng.integers(1, 7, size=n_edit)
-    tr_copies = rng.integers(5, 51, size=n_edit)
-    tr_k = np.minimum(rng.integers(1, 4, size=n_edit), tr_copies - 1)
-    tr_j = (rng.integers(0, 1 << 30, size=n_edit) % (tr_copies - tr_k + 1))
-    tr_len = np.where(tr, tr_unit * tr_copies, 0)
-    ln = np.where(tr, tr_unit * tr_k, ln)
-    edit_pos = np.where(tr, pos + tr_unit * tr_j, pos)
+    tr_unit = np.ones(n_edit, dtype=np.int64)
+    tr_len = np.zeros(n_edit, dtype=np.int64)
+    edit_pos = pos.copy()
+    if n_tr:
+        a_pos, a_unit, a_cop = tpos[arrays] - start, tunit[arrays], tcopies[arrays]
+        k = np.minimum(rng.integers(1, 4, size=n_tr), a_cop - 1)
+        j = rng.integers(0, 1 << 30, size=n_tr) % (a_cop - k + 1)
+        pos[tr_idx] = a_pos
+        edit_pos[tr_idx] = a_pos + a_unit * j
+        ln[tr_idx] = a_unit * k
+        tr_unit[tr_idx] = a_unit
+        tr_len[tr_idx] = a_unit * a_cop
+    order = np.argsort(pos, kind='stable')
+    pos, edit_pos, kind, ln, is_tr, tr_unit, tr_len = (x[order] for x in (pos, edit_pos, kind, ln, is_tr, tr_unit, tr_len))
 
     # Footprint of every edit on the reference; drop edits overlapping an earlier footprint.
     ref_use = np.where(kind == 1, 0, ln)
     foot_end = np.maximum(edit_pos + ref_use, pos + tr_len) + 2
-    keep = np.ones(n_edit, dtype=bool)
     if n_edit:
         prev_end = np.concatenate(([0], np.maximum.accumulate(foot_end)[:-1]))
         keep = (pos > prev_end) & (foot_end < span - grid)
         # dropping an edit shrinks footprints, which is conservative (never creates overlaps)
+    else:
+        keep = np.ones(0, dtype=bool)
     idx = np.flatnonzero(keep)
-
-    seg = ref[start:start + span]
-    for i in idx[tr[idx]]:  # plant repeat arrays (few; python loop is fine)
-        unit = random_seq(rng, int(tr_unit[i]))
-        seg[pos[i]:pos[i] + tr_len[i]] = np.tile(unit, int(tr_copies[i]))
-
-    kind, ln, edit_pos, tr, tr_unit = kind[idx], ln[idx], edit_pos[idx], tr[idx], tr_unit[idx]
+    kind, ln, edit_pos, tr, tr_unit = kind[idx], ln[idx], edit_pos[idx], is_tr[idx], tr_unit[idx]
     n = len(idx)
 
     q = seg.copy()
@@ -152,10 +196,10 @@ def plant_alignment(rng, ref, start, span, n_edit, grid=50, snv_frac=0.8, ins_fr
         tot = int(ln[ii].sum())
         ins_vals = random_seq(rng, tot)
         off = np.concatenate(([0], np.cumsum(ln[ii])))
-        for a, i in enumerate(ii):
-            if tr[i]:  # inserted sequence = copies of the unit that follows the site
-                unit = seg[edit_pos[i]:edit_pos[i] + tr_unit[i]]
-                ins_vals[off[a]:off[a + 1]] = np.tile(unit, int(ln[i] // tr_unit[i]))
+        for a in np.flatnonzero(tr[ii]).tolist():  # inserted sequence = copies of the unit that follows the site
+            i = ii[a]
+            unit = seg[edit_pos[i]:edit_pos[i] + tr_unit[i]]
+            ins_vals[off[a]:off[a + 1]] = np.tile(unit, int(ln[i] // tr_unit[i]))
         if lower_ins:
             ins_vals = ins_vals | 0x20
         ins_at = np.repeat(edit_pos[ii], ln[ii])
@@ -198,40 +242,51 @@ def _ragged_arange(lengths):
     return np.arange(tot, dtype=np.int64) - np.repeat(starts, lengths)
 
 
-def make_cigar_workload(seed, n_chrom, chrom_len, n_contig, contig_len, edit_rate=0.01,
-                        rev_frac=0.5, clip=(0, 0), soft_mask_frac=0.0, n_block_frac=0.0,
-                        tr_frac=0.2, hap='h1', chrom_prefix='chr', contig_prefix='tig'):
-    """Reference + contigs + alignment table. Contigs tile the chromosomes end to end.
-
-    Returns ``(ref: dict name->uint8, tigs: dict name->uint8 (as stored in the contig FASTA, i.e.
-    reverse-complemented when REV), df_align)``.
-    """
-    rng = np.random.default_rng(seed)
-    ref = {f'{chrom_prefix}{c + 1}': random_seq(rng, chrom_len) for c in range(n_chrom)}
+def make_contigs(ref, trs, hap_seed, n_contig, contig_len, edit_rate=0.01, rev_frac=0.5, clip=(0, 0), tr_frac=0.2,
+                 hap='h1', contig_prefix='tig', index_base=0):
+    """Contigs tiling the chromosomes end to end + their alignment table (one haplotype)."""
+    rng = np.random.default_rng([hap_seed, 0xC16])
     names = list(ref.keys())
-    per_chrom = chrom_len // contig_len
+    chrom_len = len(ref[names[0]])
+    per_chrom = max(chrom_len // contig_len, 1)
     tigs = {}
     rows = []
     n_edit = int(contig_len * edit_rate)
     for t in range(n_contig):
-        chrom = names[(t // per_chrom) % n_chrom]
+        chrom = names[(t // per_chrom) % len(names)]
         start = (t % per_chrom) * contig_len
         rev = bool(rng.random() < rev_frac)
-        q, cigar, span = plant_alignment(rng, ref[chrom], start, contig_len, n_edit,
+        q, cigar, span = plant_alignment(rng, ref[chrom], trs.get(chrom) if trs else None, start, contig_len, n_edit,
                                          clip_l=clip[0], clip_r=clip[1], tr_frac=tr_frac)
         name = f'{contig_prefix}{t:05d}'
         qlen = len(q)
         tigs[name] = revcomp(q) if rev else q
         qpos, qend = clip[0], qlen - clip[1]
-        rows.append((chrom, start, start + span, t, name,
+        rows.append((chrom, start, start + span, index_base + t, name,
                      qlen - qend if rev else qpos, qlen - qpos if rev else qend, qlen,
                      'NA', 'NA', 60, rev, '0x0010' if rev else '0x0000', hap, cigar))
-    if n_block_frac > 0 or soft_mask_frac > 0:
-        for chrom in names:
-            _mask_runs(rng, ref[chrom], soft_mask_frac, n_block_frac)
     df = pd.DataFrame(rows, columns=['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END',
                                      'QRY_LEN', 'RG', 'AO', 'MAPQ', 'REV', 'FLAGS', 'HAP', 'CIGAR'])
     df.sort_values(['#CHROM', 'POS', 'END', 'QRY_ID'], ascending=[True, True, False, True], inplace=True)
+    return tigs, df
+
+
+def make_cigar_workload(seed, n_chrom, chrom_len, n_contig, contig_len, edit_rate=0.01,
+                        rev_frac=0.5, clip=(0, 0), soft_mask_frac=0.0, n_block_frac=0.0,
+                        tr_frac=0.2, hap='h1', chrom_prefix='chr', contig_prefix='tig', hap_seed=None):
+    """Reference + contigs + alignment table. The reference depends on ``seed`` only; the contigs on
+    ``hap_seed`` (default ``seed``), so ranks of a multi-GPU run share one reference.
+
+    Returns ``(ref: dict name->uint8, tigs: dict name->uint8 (as stored in the contig FASTA, i.e.
+    reverse-complemented when REV), df_align)``.
+    """
+    ref, trs = make_reference(seed, n_chrom, chrom_len, chrom_prefix)
+    tigs, df = make_contigs(ref, trs, seed if hap_seed is None else hap_seed, n_contig, contig_len, edit_rate, rev_frac,
+                            clip, tr_frac, hap, contig_prefix)
+    if n_block_frac > 0 or soft_mask_frac > 0:
+        rng = np.random.default_rng([seed, 0x3A5])
+        for chrom in ref:
+            _mask_runs(rng, ref[chrom], soft_mask_frac, n_block_frac)
     return ref, tigs, df
 
 
@@ -253,10 +308,10 @@ def config_c1(seed=1001):
     return make_cigar_workload(seed, 1, 50_000, 1, 50_000, edit_rate=0.01, rev_frac=0.0, clip=(2, 1))
 
 
-def config_c2(seed=1002, n_contig=1000, contig_len=200_000, n_chrom=4):
+def config_c2(seed=1002, n_contig=1000, contig_len=200_000, n_chrom=4, hap_seed=None):
     """BASELINE configs[1]: 1,000 x 200 kbp contigs vs 200 Mbp reference (4 x 50 Mbp)."""
     chrom_len = n_contig * contig_len // n_chrom
-    return make_cigar_workload(seed, n_chrom, chrom_len, n_contig, contig_len, edit_rate=0.01, rev_frac=0.5)
+    return make_cigar_workload(seed, n_chrom, chrom_len, n_contig, contig_len, edit_rate=0.01, rev_frac=0.5, hap_seed=hap_seed)
 
 
 def write_cigar_workload(out_dir, ref, tigs, df_align, prefix='wl'):

@@ -1,0 +1,119 @@
+"""GPU parity for Path B (k-mer orientation density): CUDA through the C ABI against golden tables
+from the unmodified reference (scripts/density.py) and against the CPU oracle on seeded windows."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from pav_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+DENSITY_CASES = sorted(os.listdir(os.path.join(GOLDEN, 'density')))
+
+# float64 KDE: parallel summation order and CUDA's exp differ from scipy's sequential Cython loop in the
+# last bits; discrete outputs (INDEX, KMER, STATE_MER, STATE, run lengths) must be identical.
+KERN_RTOL = 1e-9
+KERN_ATOL = 1e-300
+
+
+def _load(case):
+    from pav_b200 import fasta
+    d = os.path.join(GOLDEN, 'density', case)
+    meta = json.load(open(os.path.join(d, 'meta.json')))
+
+    def sub(path, name, rgn):
+        a, b = rgn.split(':')[1].split('-')
+        return fasta.Fasta(path).fetch_array(name, int(a) - 1, int(b))
+    ref = sub(os.path.join(d, 'ref.fa'), 'chrW', meta['refregion'])
+    tig = sub(os.path.join(d, 'tig.fa'), 'tigW', meta['tigregion'])
+    p = os.path.join(d, 'density.tsv.gz')
+    gold = pd.read_csv(p, sep='\t') if os.path.exists(p) else None
+    return meta, ref, tig, gold
+
+
+@pytest.mark.parametrize('case', DENSITY_CASES)
+def test_density_golden_gpu(case):
+    from pav_b200.pavlib import density
+    meta, ref, tig, gold = _load(case)
+    res = density.density_windows([(ref, tig, meta['rev'], meta['srs'])], k=meta['k'])[0]
+    assert res['status'] == meta['returncode']
+    if res['status'] != 0:
+        return
+    df = density.frame_from_result(res)
+    assert list(df.columns) == meta['columns']
+    assert [str(t) for t in df.dtypes] == meta['dtypes']
+    assert df.shape[0] == meta['n_rows']
+    for col in ('INDEX', 'STATE_MER', 'STATE', 'KMER'):
+        assert (df[col].to_numpy() == gold[col].to_numpy()).all(), col
+    if res['smoothed']:
+        for col in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
+            np.testing.assert_allclose(df[col].to_numpy(), gold[col].to_numpy(), rtol=KERN_RTOL, atol=KERN_ATOL, err_msg=col)
+    assert [list(r) for r in density.rl_encoder(df)] == meta['rl_state']
+
+
+def test_density_batch_vs_oracle():
+    """A mixed batch (inversions, flank repeats, negatives, N runs, failures) in ONE launch equals the oracle window by window."""
+    from oracle import pyoracle
+    from pav_b200.pavlib import density
+    rng = np.random.default_rng(99)
+    wins = []
+    for i in range(12):
+        wl = int(rng.integers(5000, 16000))
+        r, t, _ = synth.make_inv_window(rng, wl, None, flank_rep=int(rng.integers(0, 2)) * int(rng.integers(200, 900)),
+                                        divergence=float(rng.choice([0.0, 0.002, 0.006])), negative=bool(i % 5 == 4),
+                                        n_run=int(rng.choice([0, 0, 90])))
+        wins.append((r, t, bool(i % 3 == 1), int(rng.choice([20, 20, 7, 50]))))
+    wins.append((np.full(400, ord('N'), np.uint8), synth.random_seq(rng, 400), False, 20))              # exit 125: no ref k-mers
+    rep = np.concatenate([synth.random_seq(rng, 1500), np.tile(np.frombuffer(b'ACGTTGCA', np.uint8), 150), synth.random_seq(rng, 1500)])
+    wins.append((rep, rep.copy(), False, 20))                                                           # exit 125: count > 100
+    wins.append((synth.random_seq(rng, 900), synth.random_seq(rng, 25), False, 20))                     # contig shorter than k
+    short = synth.random_seq(rng, 1200)
+    wins.append((short, short.copy(), False, 20))                                                       # < 2000 informative
+    res = density.density_windows(wins)
+    assert len(res) == len(wins)
+    for (r, t, rev, srs), g in zip(wins, res):
+        rc, o = pyoracle.density_arrays(r.tobytes(), t.tobytes(), rev=rev, srs=srs)
+        assert g['status'] == rc
+        if rc != 0:
+            continue
+        assert g['smoothed'] == o['smoothed']
+        for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE'):
+            assert (g[c].astype(np.int64) == o[c].astype(np.int64)).all(), c
+        if o['smoothed']:
+            assert g['n_eval'] == o['n_eval']
+            for c in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
+                np.testing.assert_allclose(g[c], o[c], rtol=KERN_RTOL, atol=KERN_ATOL, err_msg=c)
+
+
+def test_density_c5_window_properties():
+    """One BASELINE-C5-shaped 50 kbp window: size-independent properties + oracle equality of the discrete outputs."""
+    from oracle import pyoracle
+    from pav_b200.pavlib import density
+    ref, tig, meta = synth.make_inv_workload(seed=1005, n_win=2, win_len=50_000)
+    for rn, tn, (a, b), neg in meta:
+        g = density.density_windows([(ref[rn], tig[tn], False, 20)])[0]
+        assert g['status'] == 0 and g['smoothed']
+        ix = g['INDEX']
+        assert (np.diff(ix) > 0).all() and ix.min() >= 0 and ix.max() <= 50_000 - 31
+        assert set(np.unique(g['STATE_MER'])) <= {0, 1, 2} and set(np.unique(g['STATE'])) <= {0, 1, 2}
+        k = np.stack([g['KERN_FWD'], g['KERN_FWDREV'], g['KERN_REV']])
+        assert np.isfinite(k).all() and (k >= 0).all() and (k <= 1.0 + 1e-12).all()
+        assert (np.argmax(k, axis=0) == g['STATE']).all()
+        rc, o = pyoracle.density_arrays(ref[rn].tobytes(), tig[tn].tobytes())
+        for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE'):
+            assert (g[c].astype(np.int64) == o[c].astype(np.int64)).all(), c
+        if not neg:
+            inv_rows = (ix >= a) & (ix < b - 31)
+            assert (g['STATE'][inv_rows] == 2).mean() > 0.9
+
+
+def test_density_k_too_large_raises():
+    from pav_b200.pavlib import density
+    rng = np.random.default_rng(1)
+    s = synth.random_seq(rng, 3000)
+    with pytest.raises(RuntimeError):
+        density.density_windows([(s, s, False, 20)], k=33)

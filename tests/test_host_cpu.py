@@ -1,0 +1,219 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/pavgpu.h, the host
+tokenizer, and the host-side mirrors (FASTA reader, Region, rl_encoder, version_id, AlignLift, srs tree)."""
+import json
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import pyoracle, refenv
+from pav_b200 import _capi, fasta, synth
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, 'tests', 'golden')
+
+
+@pytest.fixture(scope='session', autouse=True)
+def built():
+    from pav_b200 import build
+    build.build()
+
+
+def test_capi_exports_match_header():
+    hdr = open(os.path.join(REPO, 'include', 'pavgpu.h')).read()
+    declared = set(re.findall(r'\b(pavgpu_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    L = _capi.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+    assert _capi.SNV_ROW.itemsize == 16 and _capi.INDEL_ROW.itemsize == 64
+    assert _capi.DENSITY_WINDOW.itemsize == 32 and _capi.DENSITY_RESULT.itemsize == 32
+    assert ctypes.sizeof(_capi.DensityParams) == 32
+    assert ctypes.sizeof(_capi.ParseErr) == 32 and ctypes.sizeof(_capi.CigarErr) == 32
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the hot path must raise, not fall back."""
+    from pav_b200 import device
+    if _capi.lib().pavgpu_device_count() > 0:
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError):
+        device.Context(0)
+    from pav_b200.pavlib import cigarcall
+    d = os.path.join(GOLDEN, 'cigar', 'kat1')
+    df = pd.read_csv(os.path.join(d, 'align.bed'), sep='\t')
+    with pytest.raises(RuntimeError):
+        cigarcall.make_insdel_snv_calls(df, os.path.join(d, 'ref.fa'), os.path.join(d, 'tig.fa'), 'h1')
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, 'pav_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+
+
+def test_cigar_parse_host():
+    from pav_b200 import device
+    from pav_b200.pavlib import align
+    cigs = ['2H9=1X20=3I10=2D16=1H', '', '100=', '5M3N2P7S']
+    ops, off, err = device.parse_cigars(cigs)
+    assert err.code == 0 and off.tolist() == [0, 9, 9, 10, 14]
+    chars = 'MIDNSHP=X'
+    for i, c in enumerate(cigs):
+        exp = list(align.cigar_str_to_tuples(c))
+        got = [(int(o >> 4), chars[int(o & 15)]) for o in ops[off[i]:off[i + 1]]]
+        assert got == exp
+    for bad, code, tp in [('20==100=', 2, 3), ('20=5Q95=', 3, 3), ('120=5', 4, 5)]:
+        ops, off, err = device.parse_cigars(['10=', bad, '7='])
+        assert (err.code, err.rec, err.text_pos) == (code, 1, tp)
+        assert off[3] == off[2]  # nothing after the malformed record
+
+
+def test_cigar_str_to_tuples_errors():
+    from pav_b200.pavlib import align
+    row = pd.Series({'CIGAR': '20=5Q95=', 'QRY_ID': 'tigA', '#CHROM': 'chrA', 'POS': 0})
+    with pytest.raises(RuntimeError, match='Unknown CIGAR operation for contig tigA alignment starting at chrA:0: CIGAR operation 5'):
+        list(align.cigar_str_to_tuples(row))
+    row['CIGAR'] = '20==100='
+    with pytest.raises(RuntimeError, match='Missing length in CIGAR string for contig tigA alignment starting at chrA:0: CIGAR index 3'):
+        list(align.cigar_str_to_tuples(row))
+    with pytest.raises(IndexError):
+        list(align.cigar_str_to_tuples('120=5'))
+
+
+def test_fasta_reader(tmp_path):
+    rng = np.random.default_rng(2)
+    seqs = {'a': synth.random_seq(rng, 1000), 'b b2': synth.random_seq(rng, 61), 'c': synth.random_seq(rng, 0), 'd': synth.random_seq(rng, 60)}
+    seqs = {k.split()[0]: v for k, v in seqs.items()}
+    p = synth.write_fasta(str(tmp_path / 'x.fa'), seqs, line_width=60)
+    for with_fai in (True, False):
+        if not with_fai:
+            os.remove(p + '.fai')
+        fa = fasta.Fasta(p)
+        for n, s in seqs.items():
+            assert fa.length(n) == len(s)
+            assert (fa.fetch_array(n) == s).all()
+            for a, b in [(0, 1), (59, 61), (60, 120), (5, 999)]:
+                if b <= len(s):
+                    assert fa.fetch(n, a, b) == s[a:b].tobytes().decode()
+    import gzip
+    with open(p, 'rb') as fi, gzip.open(p + '.gz', 'wb') as fo:
+        fo.write(fi.read())
+    fz = fasta.Fasta(p + '.gz')
+    assert (fz.fetch_array('a') == seqs['a']).all() and fz.length('d') == 60
+    assert (fasta.reverse_complement(np.frombuffer(b'ACGTNacgtRy', np.uint8)) == np.frombuffer(b'rYacgtNACGT', np.uint8)).all()
+
+
+def test_region_and_expand():
+    from pav_b200.pavlib import seq
+    r = seq.region_from_string('chr1:1,001-2,000')
+    assert (r.chrom, r.pos, r.end, r.is_rev, len(r)) == ('chr1', 1000, 2000, False, 1000)
+    assert str(r) == 'chr1:1001-2000' and r.region_id() == 'chr1-1000-RGN-1000'
+    assert seq.region_from_id('chr1-1001-RGN-1000') == r
+    rr = seq.Region('t', 50, 10)
+    assert (rr.pos, rr.end, rr.is_rev) == (10, 50, True)
+    fai = pd.Series({'chr1': 5000})
+    a = r.copy(); a.expand(4000, min_pos=0, max_end=fai, shift=True)
+    assert (a.pos, a.end) == (0, 5000)
+    b = r.copy(); b.expand(np.int32(1500), min_pos=0, max_end=fai, shift=True, balance=0.25)
+    assert (b.pos, b.end) == (1000 - 375, 2000 + 1125)
+
+
+@pytest.mark.skipif(not refenv.available(), reason='reference tree only exists in the build container')
+def test_region_expand_matches_reference():
+    refenv.activate()
+    import pavlib as ref_pavlib
+    from pav_b200.pavlib import seq
+    rng = np.random.default_rng(5)
+    fai = pd.Series({'c': 100000})
+    for _ in range(300):
+        p = int(rng.integers(0, 90000)); e = p + int(rng.integers(1, 9000))
+        bp = int(rng.integers(0, 60000)); bal = float(rng.choice([0.25, 0.5, 0.75]))
+        a = seq.Region('c', p, e); b = ref_pavlib.seq.Region('c', p, e)
+        a.expand(np.int32(bp), min_pos=0, max_end=fai, shift=True, balance=bal)
+        b.expand(np.int32(bp), min_pos=0, max_end=fai, shift=True, balance=bal)
+        assert (a.pos, a.end) == (b.pos, b.end)
+
+
+def test_rl_encoder_and_version_id():
+    from pav_b200.pavlib import density, variant
+    df = pd.DataFrame({'STATE': [0, 0, 2, 2, 2, 0, 1], 'INDEX': [3, 4, 9, 10, 11, 50, 51]})
+    assert list(density.rl_encoder(df)) == [(0, 2, 3, 4), (2, 3, 9, 11), (0, 1, 50, 50), (1, 1, 51, 51)]
+    assert list(density.rl_encoder(df)) == list(pyoracle.rl_encoder(df))
+    assert list(density.rl_encoder(df.iloc[:0])) == []
+    ids = pd.Series(['a', 'b', 'a', 'a.1', 'c', 'a', 'b'])
+    assert variant.version_id(ids).tolist() == pyoracle.version_id(ids.tolist()) == ['a', 'b', 'a.2', 'a.1', 'c', 'a.3', 'b.1']
+    same = pd.Series(['x', 'y'])
+    assert variant.version_id(same) is same
+
+
+def test_srs_tree():
+    from pav_b200.pavlib import inv
+    t = inv.get_srs_tree(None)
+    assert list(t[12345])[0].data == 20
+    t = inv.get_srs_tree([(1000, 10), (50000, 20), (500000, 40)])
+    assert [list(t[x])[0].data for x in (5, 999, 1000, 49999, 50000, 10 ** 7)] == [20, 20, 10, 10, 20, 40]
+
+
+def _lift_table():
+    rng = np.random.default_rng(21)
+    ref, tigs, df = synth.make_cigar_workload(21, 1, 120_000, 4, 30_000, edit_rate=0.01, rev_frac=0.5, clip=(13, 7))
+    fai = pd.Series({k: len(v) for k, v in tigs.items()})
+    return df.reset_index(drop=True), fai, rng
+
+
+@pytest.mark.skipif(not refenv.available(), reason='reference tree only exists in the build container')
+def test_align_lift_matches_reference():
+    refenv.activate()
+    import pavlib as ref_pavlib
+    from pav_b200.pavlib import lift, seq
+    df, fai, rng = _lift_table()
+    mine, theirs = lift.AlignLift(df, fai), ref_pavlib.align.AlignLift(df, fai)
+    for _ in range(400):
+        row = df.iloc[int(rng.integers(0, df.shape[0]))]
+        p = int(rng.integers(row['POS'] - 50, row['END'] + 50))
+        assert mine.lift_to_qry(row['#CHROM'], p) == theirs.lift_to_qry(row['#CHROM'], p)
+        q = int(rng.integers(max(row['QRY_POS'] - 30, 0), row['QRY_END'] + 30))
+        try:
+            exp = theirs.lift_to_sub(row['QRY_ID'], q)
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                mine.lift_to_sub(row['QRY_ID'], q)
+            continue
+        assert mine.lift_to_sub(row['QRY_ID'], q) == exp
+    for _ in range(100):
+        row = df.iloc[int(rng.integers(0, df.shape[0]))]
+        a = int(rng.integers(row['POS'], row['END'] - 2000)); b = a + int(rng.integers(10, 1900))
+        r1, r2 = mine.lift_region_to_qry(seq.Region(row['#CHROM'], a, b)), theirs.lift_region_to_qry(ref_pavlib.seq.Region(row['#CHROM'], a, b))
+        assert (r1 is None) == (r2 is None)
+        if r1 is not None:
+            assert (r1.chrom, r1.pos, r1.end, r1.is_rev) == (r2.chrom, r2.pos, r2.end, r2.is_rev)
+            b1, b2 = mine.lift_region_to_sub(r1), theirs.lift_region_to_sub(r2)
+            assert (b1 is None) == (b2 is None)
+            if b1 is not None:
+                assert (b1.chrom, b1.pos, b1.end) == (b2.chrom, b2.pos, b2.end)
+
+
+def test_align_lift_roundtrip():
+    """Runs everywhere: ref -> contig -> ref returns the start position inside aligned blocks."""
+    from pav_b200.pavlib import lift
+    df, fai, rng = _lift_table()
+    L = lift.AlignLift(df, fai)
+    ok = 0
+    for _ in range(200):
+        row = df.iloc[int(rng.integers(0, df.shape[0]))]
+        p = int(rng.integers(row['POS'] + 100, row['END'] - 100))
+        q = L.lift_to_qry(row['#CHROM'], p)
+        assert q is not None and q[0] == row['QRY_ID'] and q[2] == row['REV']
+        back = L.lift_to_sub(q[0], q[1])
+        if back is not None and abs(back[1] - p) <= 1:
+            ok += 1
+    assert ok > 150
