@@ -250,8 +250,20 @@ def walk_rows(df_align, ref_fa_name, tig_fa_name):
     return snv, indel, ctx
 
 
-def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=True):
-    """Oracle restatement of pavlib.cigarcall.make_insdel_snv_calls -> (df_snv, df_insdel)."""
+def _frame_like_reference(rows, columns):
+    """Row container built the way the reference builds it (pavlib/cigarcall.py:114-135,188-210,315,338):
+    one ``pd.Series`` per variant, then ``pd.concat(axis=1).T``. This is where the reference spends ~93 % of
+    its time, so the CPU *baseline* legs of bench.py use this mode to stand in for the
+    Python reference, which cannot travel to the GPU box; the parity tests use the fast mode."""
+    series = [pd.Series(list(r), index=columns) for r in rows]
+    return pd.concat(series, axis=1).T
+
+
+def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=True, reference_containers=False):
+    """Oracle restatement of pavlib.cigarcall.make_insdel_snv_calls -> (df_snv, df_insdel).
+
+    ``reference_containers=True`` assembles the frames with the reference's per-variant Series + concat
+    (same result, reference-like cost); the default builds them from tuples (same result, fast checker)."""
     _vid = globals()['version_id']
     snv, indel, ctx = walk_rows(df_align, ref_fa_name, tig_fa_name)
 
@@ -263,7 +275,7 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
         rows.append((chrom, pos, pos + 1, f'{chrom}-{pos + 1}-SNV-{rb.upper()}{ab.upper()}', 'SNV', 1, rb, ab, hap,
                      f'{tig}:{qp + 1}-{qp + 1}', '-' if is_rev else '+', 0, ai, 'CIGAR'))
     if rows:
-        df_snv = pd.DataFrame(rows, columns=SNV_COLS).astype(object)
+        df_snv = _frame_like_reference(rows, SNV_COLS) if reference_containers else pd.DataFrame(rows, columns=SNV_COLS).astype(object)
         if version_id:
             df_snv['ID'] = pd.Series(_vid(list(df_snv['ID'])), index=df_snv.index, dtype=object)
         df_snv.sort_values(['#CHROM', 'POS', 'END', 'ID'], inplace=True)
@@ -283,7 +295,7 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
             rows.append((chrom, pos, end, f'{chrom}-{pos + 1}-DEL-{svlen}', 'DEL', svlen, hap, f'{tig}:{qp + 1}-{qp + 1}',
                          '-' if is_rev else '+', 0, ai, ls, f'{hrl},{hrr}', f'{htl},{htr}', 'CIGAR', seq))
     if rows:
-        df_insdel = pd.DataFrame(rows, columns=INSDEL_COLS).astype(object)
+        df_insdel = _frame_like_reference(rows, INSDEL_COLS) if reference_containers else pd.DataFrame(rows, columns=INSDEL_COLS).astype(object)
         if version_id:
             df_insdel['ID'] = pd.Series(_vid(list(df_insdel['ID'])), index=df_insdel.index, dtype=object)
         df_insdel.sort_values(['#CHROM', 'POS', 'END', 'ID'], inplace=True)

@@ -162,6 +162,13 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     if perr.code != 0:
         _raise_parse(perr, chrom, qry, pos0)
 
+    return build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id)
+
+
+def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id):
+    """Rows from the device (``pavgpu_snv_row`` / ``pavgpu_indel_row`` arrays in emission order) -> the two
+    DataFrames of the reference. Host-side string formatting only; every coordinate comes from the GPU."""
+    n_rec = len(chrom)
     chrom_s = np.array([f'{c}' for c in chrom.tolist()], dtype=object)
     chrom_rank = {c: i for i, c in enumerate(sorted(set(chrom_s.tolist())))}
     chrom_code_rec = np.array([chrom_rank[c] for c in chrom_s.tolist()], dtype=np.int64)

@@ -43,6 +43,11 @@ def test_cigar_golden(case):
     assert [int(i) for i in df_insdel.index] == meta['insdel_index']
     assert [str(t) for t in df_snv.dtypes] == meta['snv_dtypes']
     assert [str(t) for t in df_insdel.dtypes] == meta['insdel_dtypes']
+    if meta['n_snv'] + meta['n_insdel'] < 600:  # the reference-container mode gives the same frames
+        r_snv, r_insdel = pyoracle.make_insdel_snv_calls(*args, version_id=meta['version_id'], reference_containers=True)
+        assert tsv_bytes(r_snv) == tsv_bytes(df_snv) and tsv_bytes(r_insdel) == tsv_bytes(df_insdel)
+        assert (r_snv.index == df_snv.index).all() and (r_insdel.index == df_insdel.index).all()
+        assert [str(t) for t in r_snv.dtypes] == meta['snv_dtypes']
 
 
 def test_homology_golden():
