@@ -104,21 +104,61 @@ def lib():
 _FA_CACHE = {}
 
 
+class _FastaDict:
+    """``{name: bytes}`` view of a FASTA. With a samtools ``.fai`` next to a plain file only the requested
+    records are read (like an indexed pysam fetch); otherwise the whole file is parsed once."""
+
+    def __init__(self, path):
+        self.path = path
+        self.index = None
+        self.cache = {}
+        if not path.endswith('.gz') and os.path.exists(path + '.fai'):
+            self.index = {}
+            with open(path + '.fai') as fh:
+                for line in fh:
+                    t = line.rstrip('\n').split('\t')
+                    self.index[t[0]] = (int(t[1]), int(t[2]), int(t[3]), int(t[4]))
+        else:
+            opener = gzip.open if path.endswith('.gz') else open
+            with opener(path, 'rb') as fh:
+                data = fh.read()
+            for rec in data.split(b'>')[1:]:
+                head, _, body = rec.partition(b'\n')
+                self.cache[head.split()[0].decode()] = body.replace(b'\n', b'').replace(b'\r', b'')
+
+    def __getitem__(self, name):
+        if name in self.cache:
+            return self.cache[name]
+        if self.index is None or name not in self.index:
+            raise KeyError(name)
+        length, offset, linebases, linewidth = self.index[name]
+        n_lines = (length + linebases - 1) // linebases if length else 0
+        with open(self.path, 'rb') as fh:
+            fh.seek(offset)
+            raw = fh.read(n_lines * linewidth)
+        seq = raw.replace(b'\n', b'').replace(b'\r', b'')[:length]
+        if len(self.cache) > 8:
+            self.cache.clear()
+        self.cache[name] = seq
+        return seq
+
+    def __iter__(self):
+        return iter(self.index if self.index is not None else self.cache)
+
+    def keys(self):
+        return list(iter(self))
+
+
 def read_fasta(path):
-    """Whole FASTA as ``{name: bytes}`` (original case). Plain or gzip."""
+    """FASTA as a ``{name: bytes}``-like object (original case). Plain (+ optional .fai) or gzip."""
     key = (path, os.path.getmtime(path))
     if key in _FA_CACHE:
         return _FA_CACHE[key]
-    opener = gzip.open if path.endswith('.gz') else open
-    with opener(path, 'rb') as fh:
-        data = fh.read()
-    seqs = {}
-    for rec in data.split(b'>')[1:]:
-        head, _, body = rec.partition(b'\n')
-        seqs[head.split()[0].decode()] = body.replace(b'\n', b'').replace(b'\r', b'')
-    _FA_CACHE.clear()
-    _FA_CACHE[key] = seqs
-    return seqs
+    fa = _FastaDict(path)
+    if len(_FA_CACHE) > 4:
+        _FA_CACHE.clear()
+    _FA_CACHE[key] = fa
+    return fa
 
 
 _COMP = bytes.maketrans(b'ACGTMRWSYKVHDBNacgtmrwsykvhdbn', b'TGCAKYWSRMBDHVNtgcakywsrmbdhvn')

@@ -28,6 +28,7 @@ def _stale():
 
 def build(force=False, verbose=False):
     if not force and not _stale():
+        build_pyrows()
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
@@ -51,7 +52,24 @@ def build(force=False, verbose=False):
     cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static', '-ldl', '-lrt', '-lpthread']
     subprocess.check_call(cmd)
     os.replace(tmp, LIB)
+    build_pyrows(force)
     return LIB
+
+
+PYROWS = os.path.join(HERE, '_pyrows.so')
+
+
+def build_pyrows(force=False):
+    """CPython helper (host-side row formatting), gcc, in-tree."""
+    import sysconfig
+    src = os.path.join(CSRC, 'pyrows.c')
+    if not force and os.path.exists(PYROWS) and os.path.getmtime(PYROWS) >= os.path.getmtime(src):
+        return PYROWS
+    inc = sysconfig.get_paths()['include']
+    tmp = PYROWS + f'.{os.getpid()}.tmp'
+    subprocess.check_call(['gcc', '-O2', '-fPIC', '-shared', '-std=gnu11', '-I', inc, '-o', tmp, src])
+    os.replace(tmp, PYROWS)
+    return PYROWS
 
 
 if __name__ == '__main__':

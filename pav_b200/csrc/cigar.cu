@@ -294,6 +294,219 @@ cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
     }
 }
 
+// KF (fused K1+K2+K3) -----------------------------------------------------------------------------
+// Single pass over the ops: one CTA = 8 warps = 1024 ops. Tile aggregates travel between CTAs through 16-byte
+// descriptors with a decoupled look-back (status, segment flag, ref/qry advance since the last record head,
+// row counts), so the ops are read once and there is no host round trip for the row totals (the host counted
+// them while packing the ops). Tiles are handed out by an atomic counter so a CTA only ever waits for tiles
+// that are already running.
+//   w0: [1:0] status  [2] has-head  [33:3] ref advance (31 b)  [63:34] indel rows (30 b)
+//   w1: [30:0] qry advance (31 b)   [63:31] SNV rows (33 b)
+constexpr unsigned ST_INVALID = 0, ST_AGG = 1, ST_PREFIX = 2;
+
+struct TileVal {
+    int f, r, q;
+    unsigned long long ns, ni;
+};
+
+__device__ __forceinline__ ulonglong2 tile_pack(unsigned status, const TileVal &v)
+{
+    ulonglong2 d;
+    d.x = (unsigned long long)status | ((unsigned long long)(v.f & 1) << 2) | ((unsigned long long)(unsigned)v.r << 3) | (v.ni << 34);
+    d.y = (unsigned long long)(unsigned)v.q | (v.ns << 31);
+    return d;
+}
+
+__device__ __forceinline__ unsigned tile_unpack(const ulonglong2 &d, TileVal &v)
+{
+    v.f = (int)((d.x >> 2) & 1ull);
+    v.r = (int)((d.x >> 3) & 0x7fffffffull);
+    v.ni = d.x >> 34;
+    v.q = (int)(d.y & 0x7fffffffull);
+    v.ns = d.y >> 31;
+    return (unsigned)(d.x & 3ull);
+}
+
+__device__ __forceinline__ void tile_store(ulonglong2 *p, const ulonglong2 &d)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(d.x), "l"(d.y) : "memory");
+}
+
+__device__ __forceinline__ ulonglong2 tile_load(const ulonglong2 *p)
+{
+    ulonglong2 d;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(d.x), "=l"(d.y) : "l"(p) : "memory");
+    return d;
+}
+
+// older (+) newer for the segmented position sums
+__device__ __forceinline__ void seg_combine(int of, int orr, int oq, int &f, int &r, int &q)
+{
+    if (!f) { r += orr; q += oq; }
+    f |= of;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_tiles, unsigned int *__restrict__ tile_counter,
+                  ulonglong2 *__restrict__ desc, const int64_t *__restrict__ qry_len, int4 *__restrict__ snv_rows,
+                  IndelStub *__restrict__ stubs, unsigned long long *__restrict__ first_illegal, int64_t *__restrict__ totals)
+{
+    __shared__ unsigned s_tile;
+    __shared__ int s_f[WARPS_PER_BLOCK], s_r[WARPS_PER_BLOCK], s_q[WARPS_PER_BLOCK];
+    __shared__ int s_pf[WARPS_PER_BLOCK], s_pr[WARPS_PER_BLOCK], s_pq[WARPS_PER_BLOCK];  // folds over warps 0..w
+    __shared__ unsigned s_ns[WARPS_PER_BLOCK], s_ni[WARPS_PER_BLOCK];
+    __shared__ int s_ex_f, s_ex_r, s_ex_q;
+    __shared__ unsigned long long s_ex_ns, s_ex_ni;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= n_tiles) return;
+    const int64_t chunk = tile * WARPS_PER_BLOCK + wid;
+
+    // ---- per-lane ops and record lookup (one search per warp; per-lane search only when the chunk spans records)
+    LaneOps L;
+    L.g0 = chunk * CHUNK + (int64_t)lane * OPS_PER_LANE;
+    {
+        int64_t rem = n_ops - L.g0;
+        L.nvalid = rem <= 0 ? 0 : (rem >= OPS_PER_LANE ? OPS_PER_LANE : (int)rem);
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (L.nvalid > 0) raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));
+        L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
+        int64_t gfirst = chunk * CHUNK;
+        int32_t rec_lo = 0;
+        if (lane == 0 && gfirst < n_ops) rec_lo = find_rec(rv.op_off, rv.n_rec, gfirst);
+        rec_lo = __shfl_sync(FULL, rec_lo, 0);
+        L.rec0 = rec_lo;
+        if (L.nvalid > 0 && L.g0 >= __ldg(rv.op_off + rec_lo + 1)) L.rec0 = find_rec(rv.op_off, rv.n_rec, L.g0);
+    }
+    int f, r, q; uint32_t ns, ni;
+    lane_aggregate(L, rv, f, r, q, ns, ni);
+    int fi = f, ri = r, qi = q;
+    warp_seg_scan(lane, fi, ri, qi);
+    uint32_t nsi = warp_inc_scan(lane, ns), nii = warp_inc_scan(lane, ni);
+    if (lane == 31) { s_f[wid] = fi; s_r[wid] = ri; s_q[wid] = qi; s_ns[wid] = nsi; s_ni[wid] = nii; }
+    __syncthreads();
+
+    // ---- warp 0: tile aggregate, publish, look back, publish the inclusive prefix
+    if (wid == 0) {
+        TileVal agg{0, 0, 0, 0ull, 0ull};
+        for (int w = 0; w < WARPS_PER_BLOCK; w++) {
+            int nf = s_f[w], nr = s_r[w], nq = s_q[w];
+            seg_combine(agg.f, agg.r, agg.q, nf, nr, nq);   // (nf, nr, nq) = fold(warps 0..w)
+            agg.f = nf; agg.r = nr; agg.q = nq;
+            agg.ns += s_ns[w]; agg.ni += s_ni[w];
+            if (lane == 0) { s_pf[w] = nf; s_pr[w] = nr; s_pq[w] = nq; }
+        }
+        if (lane == 0) tile_store(desc + tile, tile_pack(tile == 0 ? ST_PREFIX : ST_AGG, agg));
+        TileVal ex{0, 0, 0, 0ull, 0ull};
+        if (tile > 0) {
+            int64_t base = tile - 1;
+            bool done = false;
+            while (!done) {
+                int64_t idx = base - lane;
+                TileVal v{0, 0, 0, 0ull, 0ull};
+                unsigned st = ST_PREFIX;  // tiles before the first one: identity prefix
+                if (idx >= 0) {
+                    do { st = tile_unpack(tile_load(desc + idx), v); } while (st == ST_INVALID);
+                }
+                unsigned pm = __ballot_sync(FULL, st == ST_PREFIX);
+                int k = __ffs((int)pm) - 1;              // nearest lane holding an inclusive prefix (-1: none)
+                int last = (k < 0) ? 31 : k;
+                if (lane > last) { v.f = 0; v.r = 0; v.q = 0; v.ns = 0; v.ni = 0; }
+                // fold lanes last..0 in tile order (higher lane = older tile): result in lane 0
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int of = __shfl_down_sync(FULL, v.f, d), orr = __shfl_down_sync(FULL, v.r, d), oq = __shfl_down_sync(FULL, v.q, d);
+                    unsigned long long ons = __shfl_down_sync(FULL, v.ns, d), oni = __shfl_down_sync(FULL, v.ni, d);
+                    if (lane + d < 32) { seg_combine(of, orr, oq, v.f, v.r, v.q); v.ns += ons; v.ni += oni; }
+                }
+                // window (older) (+) what we already have (newer)
+                int wf = __shfl_sync(FULL, v.f, 0), wr = __shfl_sync(FULL, v.r, 0), wq = __shfl_sync(FULL, v.q, 0);
+                unsigned long long wns = __shfl_sync(FULL, v.ns, 0), wni = __shfl_sync(FULL, v.ni, 0);
+                seg_combine(wf, wr, wq, ex.f, ex.r, ex.q);
+                ex.ns += wns; ex.ni += wni;
+                done = (k >= 0);
+                base -= 32;
+            }
+            if (lane == 0) {
+                TileVal inc = agg;
+                seg_combine(ex.f, ex.r, ex.q, inc.f, inc.r, inc.q);
+                inc.ns += ex.ns; inc.ni += ex.ni;
+                tile_store(desc + tile, tile_pack(ST_PREFIX, inc));
+            }
+        }
+        if (lane == 0) {
+            s_ex_f = ex.f; s_ex_r = ex.r; s_ex_q = ex.q; s_ex_ns = ex.ns; s_ex_ni = ex.ni;
+            if (tile == n_tiles - 1) { totals[0] = (int64_t)(ex.ns + agg.ns); totals[1] = (int64_t)(ex.ni + agg.ni); }
+        }
+    }
+    __syncthreads();
+
+    // ---- exclusive prefix of this warp = tile prefix (+) fold of the earlier warps of the tile
+    int cf = s_ex_f, cr = s_ex_r, cq = s_ex_q;
+    unsigned long long cns = s_ex_ns, cni = s_ex_ni;
+    if (wid > 0) {
+        int pf = s_pf[wid - 1], pr = s_pr[wid - 1], pq = s_pq[wid - 1];  // inclusive fold over warps 0..wid-1
+        seg_combine(cf, cr, cq, pf, pr, pq);
+        cf = pf; cr = pr; cq = pq;
+        for (int w = 0; w < wid; w++) { cns += s_ns[w]; cni += s_ni[w]; }
+    }
+    // ---- emit (same as K3)
+    int ef = __shfl_up_sync(FULL, fi, 1), er = __shfl_up_sync(FULL, ri, 1), eq = __shfl_up_sync(FULL, qi, 1);
+    if (lane == 0) { ef = 0; er = 0; eq = 0; }
+    int run_r = ef ? er : er + cr;
+    int run_q = ef ? eq : eq + cq;
+    long long snv_cur = (long long)cns + (long long)(nsi - ns);
+    long long indel_cur = (long long)cni + (long long)(nii - ni);
+    uint32_t prev_op = __shfl_up_sync(FULL, L.op[OPS_PER_LANE - 1], 1);
+    if (lane == 0) prev_op = (L.nvalid > 0 && L.g0 > 0) ? __ldg(ops + L.g0 - 1) : 0u;
+    if (L.nvalid == 0) return;
+
+    int32_t rec = L.rec0;
+    int64_t cur_off = __ldg(rv.op_off + rec), next_off = __ldg(rv.op_off + rec + 1);
+    int32_t rpos = __ldg(rv.pos + rec);
+    int rrev = __ldg(rv.rev + rec);
+    int32_t qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+#pragma unroll
+    for (int j = 0; j < OPS_PER_LANE; j++) {
+        if (j < L.nvalid) {
+            int64_t g = L.g0 + j;
+            bool moved = false;
+            while (g >= next_off) { ++rec; cur_off = next_off; next_off = __ldg(rv.op_off + rec + 1); moved = true; }
+            if (moved) {
+                rpos = __ldg(rv.pos + rec);
+                rrev = __ldg(rv.rev + rec);
+                qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+            }
+            bool head = (g == cur_off);
+            if (head) { run_r = 0; run_q = 0; }
+            uint32_t op = L.op[j], code = op & 15u, len = op >> 4;
+            int32_t op_idx = (int32_t)(g - cur_off);
+            int32_t pos_ref = rpos + run_r, pos_qry = run_q;
+            if (code == PAVGPU_OP_X) {
+                for (uint32_t i = 0; i < len; i++) {
+                    int32_t t = pos_qry + (int32_t)i;
+                    snv_rows[snv_cur + i] = make_int4(pos_ref + (int32_t)i, rrev ? qlen - 1 - t : t, rec, op_idx);
+                }
+                snv_cur += len;
+            } else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) {
+                int4 *dst = reinterpret_cast<int4 *>(stubs + indel_cur);
+                int32_t eqb = (!head && (prev_op & 15u) == PAVGPU_OP_EQ) ? (int32_t)(prev_op >> 4) : 0;
+                dst[0] = make_int4(rec, op_idx, (code == PAVGPU_OP_D), (int32_t)len);
+                dst[1] = make_int4(pos_ref, pos_qry, eqb, 0);
+                ++indel_cur;
+            } else if (!((1u << code) & LEGAL_MASK)) {
+                atomicMin(first_illegal, (unsigned long long)g);
+            }
+            uint32_t bit = 1u << code;
+            if (bit & REF_ADV_MASK) run_r += (int)len;
+            if (bit & QRY_ADV_MASK) run_q += (int)len;
+            prev_op = op;
+        }
+    }
+}
+
 // K4 ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, RecView rv, SeqPlanes ref, SeqPlanes qry,
@@ -377,6 +590,11 @@ struct pavgpu_cigar_batch {
     int4 *d_snv; int64_t cap_snv;
     IndelStub *d_stub; pavgpu_indel_row *d_indel; int64_t cap_indel;
     int64_t n_snv, n_indel;
+    int64_t host_n_snv, host_n_indel;   // counted on the host while the ops were staged
+    int64_t n_tiles;
+    ulonglong2 *d_desc;
+    unsigned int *d_tile_counter;
+    bool fused;
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
@@ -441,6 +659,7 @@ static void batch_release(pavgpu_cigar_batch *b)
     cudaFree(b->d_ref_id); cudaFree(b->d_qry_id); cudaFree(b->d_pos); cudaFree(b->d_rev); cudaFree(b->d_op_off);
     cudaFree(b->d_ops); cudaFree(b->d_agg); cudaFree(b->d_cnt); cudaFree(b->d_pre_rq); cudaFree(b->d_pre_cnt);
     cudaFree(b->d_totals); cudaFree(b->d_first_illegal); cudaFree(b->d_snv); cudaFree(b->d_stub); cudaFree(b->d_indel);
+    cudaFree(b->d_desc); cudaFree(b->d_tile_counter);
 }
 
 extern "C" __attribute__((visibility("default"))) void pavgpu_cigar_batch_free(pavgpu_cigar_batch *b)
@@ -468,6 +687,16 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
     b->h_ops.assign(ops, ops + n_ops);
     b->h_op_off.assign(op_off, op_off + n_rec + 1);
     b->h_pos.assign(pos, pos + n_rec);
+    b->n_tiles = (b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    for (int64_t i = 0; i < n_ops; i++) {
+        uint32_t code = ops[i] & 15u;
+        if (code == PAVGPU_OP_X) b->host_n_snv += ops[i] >> 4;
+        else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) b->host_n_indel += 1;
+    }
+    // single-pass walk unless the descriptor fields would overflow (33-bit SNV count, 30-bit indel count) or the
+    // multi-pass kernels are requested for A/B timing
+    const char *mp = getenv("PAVGPU_CIGAR_MULTIPASS");
+    b->fused = !(mp && mp[0] == '1') && b->host_n_snv < ((int64_t)1 << 33) && b->host_n_indel < ((int64_t)1 << 30);
     size_t ops_padded = (size_t)std::max<int64_t>(b->n_chunks, 1) * CHUNK;
     size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1), nr = (size_t)std::max(n_rec, 1);
     int rc = [&]() -> int {
@@ -478,6 +707,16 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
         CUDA_TRY(cudaMalloc(&b->d_agg, nc * sizeof(int4))); CUDA_TRY(cudaMalloc(&b->d_cnt, nc * sizeof(uint2)));
         CUDA_TRY(cudaMalloc(&b->d_pre_rq, nc * sizeof(int2))); CUDA_TRY(cudaMalloc(&b->d_pre_cnt, nc * sizeof(longlong2)));
         CUDA_TRY(cudaMalloc(&b->d_totals, 2 * 8)); CUDA_TRY(cudaMalloc(&b->d_first_illegal, 8));
+        CUDA_TRY(cudaMalloc(&b->d_desc, sizeof(ulonglong2) * (size_t)std::max<int64_t>(b->n_tiles, 1)));
+        CUDA_TRY(cudaMalloc(&b->d_tile_counter, sizeof(unsigned int)));
+        if (b->fused) {  // row buffers are sized from the host counts: no mid-run round trip
+            if (b->host_n_snv) { CUDA_TRY(cudaMalloc(&b->d_snv, (size_t)b->host_n_snv * sizeof(int4))); b->cap_snv = b->host_n_snv; }
+            if (b->host_n_indel) {
+                CUDA_TRY(cudaMalloc(&b->d_stub, (size_t)b->host_n_indel * sizeof(IndelStub)));
+                CUDA_TRY(cudaMalloc(&b->d_indel, (size_t)b->host_n_indel * sizeof(pavgpu_indel_row)));
+                b->cap_indel = b->host_n_indel;
+            }
+        }
         cudaStream_t st = ctx->stream;
         CUDA_TRY(cudaMemsetAsync(b->d_ops, 0, ops_padded * 4, st));
         if (n_rec) {
@@ -517,7 +756,34 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 16, st));
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
     b->n_snv = b->n_indel = 0;
-    if (b->n_chunks > 0) {
+    if (b->n_chunks > 0 && b->fused) {
+        CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_tiles, st));
+        CUDA_TRY(cudaMemsetAsync(b->d_tile_counter, 0, sizeof(unsigned int), st));
+        cigar_walk_kernel<<<(unsigned)b->n_tiles, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_tiles, b->d_tile_counter, b->d_desc,
+                                                                             qry_store->d_len, b->d_snv, b->d_stub, b->d_first_illegal, b->d_totals);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+        b->n_snv = b->host_n_snv; b->n_indel = b->host_n_indel;
+        if (b->n_indel > 0) {
+            unsigned hb = (unsigned)((b->n_indel + 127) / 128);
+            homology_kernel<<<hb, 128, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel);
+            launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
+        int64_t tot[2];
+        CUDA_TRY(cudaMemcpyAsync(tot, b->d_totals, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&b->first_illegal, b->d_first_illegal, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (tot[0] != b->host_n_snv || tot[1] != b->host_n_indel) {
+            pav_set_error("cigar walk: device row totals (%lld, %lld) differ from the host count (%lld, %lld)", (long long)tot[0], (long long)tot[1],
+                          (long long)b->host_n_snv, (long long)b->host_n_indel);
+            return PAVGPU_ERR_CUDA;
+        }
+    } else if (b->n_chunks > 0) {
         unsigned blocks = (unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         cigar_reduce_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_agg, b->d_cnt);
         chunk_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(b->d_agg, b->d_cnt, b->n_chunks, b->d_pre_rq, b->d_pre_cnt, b->d_totals);

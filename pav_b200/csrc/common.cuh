@@ -83,36 +83,105 @@ __device__ __forceinline__ int oseq_base(const OSeq &s, int64_t t)
     return s.rev ? 3 - c : c;
 }
 
-// pavlib/call.py:542-592. T: sequence searched leftwards from p; the SV sequence is V[v0 : v0+n],
-// read circularly from its end (sv[-((h+1) % n)], index -0 == 0).
-__device__ __forceinline__ int dev_left_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
+// ---- 32-base windows --------------------------------------------------------------------------
+// Reverse the 32 two-bit groups of a word and complement them (reverse complement of 32 bases).
+__device__ __forceinline__ uint64_t revcomp32(uint64_t x)
 {
-    int h = 0;
-    int vi = n - 1;
-    while ((int64_t)h <= p) {
-        int b = oseq_base(T, p - h);
-        if (b == 4) break;
-        if (oseq_base(V, v0 + vi) != b) break;
-        ++h;
-        if (--vi < 0) vi = n - 1;
-    }
-    return h;
+    x = ~x;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    return ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
 }
 
-// pavlib/call.py:595-647
+// Forward-strand window: bases f .. f+31 of a sequence (base i of the window in bits [62-2i, 64-2i) of
+// `bases`, bit i of `mask` set when that base is not ACGT or lies outside [0, len)).
+__device__ __forceinline__ void fwd_window(const OSeq &s, int64_t f, uint64_t &bases, uint32_t &mask)
+{
+    if (f <= -32 || f >= s.len) { bases = 0; mask = 0xffffffffu; return; }
+    int lead = f < 0 ? (int)(-f) : 0;          // window positions before the sequence start
+    int64_t g = s.base + f + lead;
+    int64_t w = g >> 5;
+    int sh = (int)(g & 31);
+    uint64_t hi = __ldg(s.pack2 + w), lo = __ldg(s.pack2 + w + 1);
+    uint64_t b = sh ? ((hi << (2 * sh)) | (lo >> (64 - 2 * sh))) : hi;
+    uint64_t m64 = (uint64_t)__ldg(s.nmask + w) | ((uint64_t)__ldg(s.nmask + w + 1) << 32);
+    uint32_t m = (uint32_t)(m64 >> sh);
+    if (lead) { b >>= 2 * lead; m = (m << lead) | ((1u << lead) - 1u); }
+    int64_t over = f + 32 - s.len;             // window positions past the sequence end
+    if (over > 0) m |= ~0u << (32 - (int)over);
+    bases = b; mask = m;
+}
+
+// Window of 32 bases starting at oriented position t (reverse-complement view when s.rev).
+__device__ __forceinline__ void oseq_window(const OSeq &s, int64_t t, uint64_t &bases, uint32_t &mask)
+{
+    if (!s.rev) { fwd_window(s, t, bases, mask); return; }
+    uint64_t b; uint32_t m;
+    fwd_window(s, s.len - t - 32, b, m);
+    bases = revcomp32(b);
+    mask = __brev(m);
+}
+
+// Longest common prefix of A[a..] and B[b..] (stops at the first mismatch, non-ACGT base or sequence end
+// on either side), capped at `limit`. 32 bases per step.
+__device__ __forceinline__ int64_t lcp_forward(const OSeq &A, int64_t a, const OSeq &B, int64_t b, int64_t limit)
+{
+    int64_t h = 0;
+    while (h < limit) {
+        uint64_t wa, wb; uint32_t ma, mb;
+        oseq_window(A, a + h, wa, ma);
+        oseq_window(B, b + h, wb, mb);
+        uint64_t x = wa ^ wb;
+        uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;      // one bit per differing base
+        int stop_d = d ? (__clzll((long long)d) >> 1) : 32;       // first base = most significant group
+        uint32_t m = ma | mb;
+        int stop_m = m ? (__ffs((int)m) - 1) : 32;
+        int stop = min(stop_d, stop_m);
+        if (stop < 32) { h += stop; return h < limit ? h : limit; }
+        h += 32;
+    }
+    return limit;
+}
+
+// Longest common suffix of A[..a] and B[..b] (positions a, b inclusive, walking towards position 0).
+__device__ __forceinline__ int64_t lcs_backward(const OSeq &A, int64_t a, const OSeq &B, int64_t b, int64_t limit)
+{
+    int64_t h = 0;
+    while (h < limit) {
+        uint64_t wa, wb; uint32_t ma, mb;
+        oseq_window(A, a - h - 31, wa, ma);
+        oseq_window(B, b - h - 31, wb, mb);
+        uint64_t x = wa ^ wb;
+        uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
+        int stop_d = d ? ((__ffsll((long long)d) - 1) >> 1) : 32;  // last base = least significant group
+        uint32_t m = ma | mb;
+        int stop_m = m ? __clz((int)m) : 32;
+        int stop = min(stop_d, stop_m);
+        if (stop < 32) { h += stop; return h < limit ? h : limit; }
+        h += 32;
+    }
+    return limit;
+}
+
+// pavlib/call.py:542-592. T: sequence searched leftwards from p; the SV sequence is V[v0 : v0+n], read
+// circularly from its end (sv[-((h+1) % n)], index -0 == 0). Word-parallel form: the first n steps are a
+// common-suffix of T[..p] with V[v0..v0+n-1]; once a whole copy of V matched, step h compares T[p-h] with
+// V[(n-1-h) mod n] = T[p-h+n], i.e. the scan continues as a common suffix of T[..p-n] with T[..p].
+__device__ __forceinline__ int dev_left_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
+{
+    if (p < 0 || n <= 0) return 0;
+    int64_t h = lcs_backward(T, p, V, v0 + n - 1, n);
+    if (h < n) return (int)h;
+    return (int)(n + lcs_backward(T, p - n, T, p, (int64_t)1 << 40));
+}
+
+// pavlib/call.py:595-647, same idea forwards: T[p+h] vs V[h mod n] = T[p+h-n] after the first copy.
 __device__ __forceinline__ int dev_right_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
 {
-    int h = 0;
-    int vi = 0;
-    int64_t limit = T.len - p;
-    while ((int64_t)h < limit) {
-        int b = oseq_base(T, p + h);
-        if (b == 4) break;
-        if (oseq_base(V, v0 + vi) != b) break;
-        ++h;
-        if (++vi == n) vi = 0;
-    }
-    return h;
+    if (p >= T.len || n <= 0 || p < 0) return 0;
+    int64_t h = lcp_forward(T, p, V, v0, n);
+    if (h < n) return (int)h;
+    return (int)(n + lcp_forward(T, p + n, T, p, (int64_t)1 << 40));
 }
 
 static inline float ev_ms(cudaEvent_t a, cudaEvent_t b)

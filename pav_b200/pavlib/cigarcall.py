@@ -20,7 +20,6 @@ SNV_COLUMNS = ['#CHROM', 'POS', 'END', 'ID', 'SVTYPE', 'SVLEN', 'REF', 'ALT', 'H
 INSDEL_COLUMNS = ['#CHROM', 'POS', 'END', 'ID', 'SVTYPE', 'SVLEN', 'HAP', 'QRY_REGION', 'QRY_STRAND', 'CI', 'ALIGN_INDEX',
                   'LEFT_SHIFT', 'HOM_REF', 'HOM_TIG', 'CALL_SOURCE', 'SEQ']
 
-_S = np.dtypes.StringDType()
 _CHR = np.array([chr(i) for i in range(256)], dtype=object)
 _OP_CHAR = 'MIDNSHP=X'
 
@@ -34,18 +33,6 @@ def _first_seen(values):
         if v not in seen:
             seen[v] = len(seen)
     return seen
-
-
-def _join(*parts):
-    """Element-wise string concatenation of StringDType arrays / scalars -> object array of str."""
-    out = parts[0]
-    for p in parts[1:]:
-        out = np.strings.add(out, p)
-    return out.astype(object)
-
-
-def _istr(a):
-    return np.asarray(a).astype(_S)
 
 
 def _sort_order(chrom_codes, pos, end, ids):
@@ -69,19 +56,6 @@ def _sort_order(chrom_codes, pos, end, ids):
 
 def _empty(columns):
     return pd.DataFrame([], columns=columns)
-
-
-def _frame(cols, columns, order):
-    data = {}
-    for name in columns:
-        v = cols[name]
-        if isinstance(v, np.ndarray):
-            data[name] = v[order]
-        else:  # scalar column
-            a = np.empty(len(order), dtype=object)
-            a[:] = v
-            data[name] = a
-    return pd.DataFrame(data, columns=columns, index=pd.Index(order, dtype=np.int64), dtype=object)
 
 
 def _raise_illegal(err, chrom, qry, align_index):
@@ -110,6 +84,52 @@ def _raise_parse(perr, chrom, qry, pos):
     raise IndexError('string index out of range')
 
 
+class AlignTable:
+    """Columns of the alignment table the walk needs, extracted once (the caller's frame is never modified)."""
+
+    def __init__(self, df_align):
+        self.n_rec = df_align.shape[0]
+        self.chrom = df_align['#CHROM'].to_numpy(dtype=object)
+        self.qry = df_align['QRY_ID'].to_numpy(dtype=object)
+        self.rev = np.array([bool(x) for x in df_align['REV'].tolist()], dtype=bool)
+        self.pos = np.array([int(x) for x in df_align['POS'].tolist()], dtype=np.int64)
+        self.align_index = df_align['INDEX'].to_numpy(dtype=object)
+        self.cigars = df_align['CIGAR'].tolist()
+        self.ref_names = _first_seen(str(c) for c in self.chrom.tolist())
+        self.tig_names = _first_seen(str(q) for q in self.qry.tolist())
+        self.ref_id = np.array([self.ref_names[str(c)] for c in self.chrom.tolist()], dtype=np.int32)
+        self.qry_id = np.array([self.tig_names[str(q)] for q in self.qry.tolist()], dtype=np.int32)
+
+
+def walk_rows(table, ref_arr, tig_arr, ctx=None, ref_store=None):
+    """Run the CIGAR walk for ``table`` on the GPU. ``ref_arr`` / ``tig_arr``: uint8 arrays in the order of
+    ``table.ref_names`` / ``table.tig_names``. ``ref_store`` may be a resident store (multi-GPU: the broadcast
+    reference) whose sequence order matches ``table.ref_names``.
+
+    Returns ``(snv rows, indel rows)`` in emission order; raises the reference's exceptions for bad CIGARs."""
+    global last_stats
+    ctx = ctx or device.get_context()
+    own_ref = ref_store is None
+    if own_ref:
+        ref_store = device.SeqStore(ctx, list(table.ref_names), ref_arr, keep_host=False)
+    tig_store = device.SeqStore(ctx, list(table.tig_names), tig_arr, keep_host=False)
+    try:
+        ops, op_off, perr = device.parse_cigars(table.cigars)
+        snv, indel, cerr, stats = device.cigar_call(ctx, ref_store, tig_store, table.ref_id, table.qry_id,
+                                                    table.pos.astype(np.int32), table.rev.astype(np.uint8), ops, op_off)
+    finally:
+        if own_ref:
+            ref_store.close()
+        tig_store.close()
+    last_stats = stats.as_dict()
+    # Errors surface in walk order (the reference raises lazily while iterating records and ops)
+    if cerr.code == 1 and (perr.code == 0 or (cerr.rec, cerr.op_index) < (perr.rec, perr.op_index)):
+        _raise_illegal(cerr, table.chrom, table.qry, table.align_index)
+    if perr.code != 0:
+        _raise_parse(perr, table.chrom, table.qry, table.pos)
+    return snv, indel
+
+
 def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=True):
     """
     Parse variants from CIGAR strings.
@@ -122,121 +142,121 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
 
     :return: ``(df_snv, df_insdel)`` -- the order the reference actually returns (pavlib/cigarcall.py:362).
     """
-    global last_stats
-    n_rec = df_align.shape[0]
-    if n_rec == 0:
+    if df_align.shape[0] == 0:
         return _empty(SNV_COLUMNS), _empty(INSDEL_COLUMNS)
-
-    chrom = df_align['#CHROM'].to_numpy(dtype=object)
-    qry = df_align['QRY_ID'].to_numpy(dtype=object)
-    rev = np.array([bool(x) for x in df_align['REV'].tolist()], dtype=bool)
-    pos0 = np.array([int(x) for x in df_align['POS'].tolist()], dtype=np.int64)
-    align_index = df_align['INDEX'].to_numpy(dtype=object)
-    cigars = df_align['CIGAR'].tolist()
-
-    ctx = device.get_context()
-
-    # Sequences referenced by this table -> HBM (packed on the device)
-    ref_names = _first_seen(str(c) for c in chrom.tolist())
-    tig_names = _first_seen(str(q) for q in qry.tolist())
+    table = AlignTable(df_align)
     ref_fa = fasta.open_fasta(ref_fa_name)
     tig_fa = fasta.open_fasta(tig_fa_name)
-    ref_arr = [ref_fa.fetch_array(nm) for nm in ref_names]
-    tig_arr = [tig_fa.fetch_array(nm) for nm in tig_names]
-    ref_store = device.SeqStore(ctx, list(ref_names), ref_arr)
-    tig_store = device.SeqStore(ctx, list(tig_names), tig_arr)
-    try:
-        ref_id = np.array([ref_names[str(c)] for c in chrom.tolist()], dtype=np.int32)
-        qry_id = np.array([tig_names[str(q)] for q in qry.tolist()], dtype=np.int32)
-        ops, op_off, perr = device.parse_cigars(cigars)
-        snv, indel, cerr, stats = device.cigar_call(ctx, ref_store, tig_store, ref_id, qry_id, pos0.astype(np.int32),
-                                                    rev.astype(np.uint8), ops, op_off)
-    finally:
-        ref_store.close()
-        tig_store.close()
-    last_stats = stats.as_dict()
+    ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
+    tig_arr = [tig_fa.fetch_array(nm) for nm in table.tig_names]
+    snv, indel = walk_rows(table, ref_arr, tig_arr)
+    return build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
+                        table.qry_id, hap, version_id)
 
-    # Errors surface in walk order (the reference raises lazily while iterating records and ops)
-    if cerr.code == 1 and (perr.code == 0 or (cerr.rec, cerr.op_index) < (perr.rec, perr.op_index)):
-        _raise_illegal(cerr, chrom, qry, align_index)
-    if perr.code != 0:
-        _raise_parse(perr, chrom, qry, pos0)
 
-    return build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id)
+def _obj(values):
+    """list -> object ndarray (one pass, no type inference)."""
+    if isinstance(values, list):
+        a = np.empty(len(values), dtype=object)
+        a[:] = values
+        return a
+    return values
+
+
+def _frame(cols, columns, index):
+    n = len(index)
+    data = {}
+    for name in columns:
+        v = cols[name]
+        if isinstance(v, (list, np.ndarray)):
+            data[name] = _obj(v)
+        else:  # scalar column
+            a = np.empty(n, dtype=object)
+            a[:] = v
+            data[name] = a
+    # copy=False keeps one block per column (no 2-D consolidation copy); dtypes stay object
+    return pd.DataFrame(data, columns=columns, index=pd.Index(index, dtype=np.int64), dtype=object, copy=False)
 
 
 def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id):
     """Rows from the device (``pavgpu_snv_row`` / ``pavgpu_indel_row`` arrays in emission order) -> the two
-    DataFrames of the reference. Host-side string formatting only; every coordinate comes from the GPU."""
+    DataFrames of the reference. Host-side string formatting only (pav_b200/csrc/pyrows.c); every coordinate
+    comes from the GPU. IDs are formatted in emission order (version_id and the sort's tie-break need them),
+    every other column directly in the final row order."""
+    from .. import _pyrows
     n_rec = len(chrom)
-    chrom_s = np.array([f'{c}' for c in chrom.tolist()], dtype=object)
-    chrom_rank = {c: i for i, c in enumerate(sorted(set(chrom_s.tolist())))}
-    chrom_code_rec = np.array([chrom_rank[c] for c in chrom_s.tolist()], dtype=np.int64)
-    qry_s = np.array([f'{q}' for q in qry.tolist()], dtype=object)
+    chrom_l = [f'{c}' for c in chrom.tolist()]
+    qry_l = [f'{q}' for q in qry.tolist()]
+    chrom_rank = {c: i for i, c in enumerate(sorted(set(chrom_l)))}
+    chrom_code_rec = np.array([chrom_rank[c] for c in chrom_l], dtype=np.int64)
     strand_rec = np.where(rev, '-', '+').astype(object)
 
     # ------------------------------------------------------------------ SNV rows (cigarcall.py:98-135)
     if len(snv):
+        n = len(snv)
         rec = snv['rec'].astype(np.int64)
         pos = snv['pos_ref'].astype(np.int64)
         qp = snv['qry_pos'].astype(np.int64)
-        ref_b = np.empty(len(snv), dtype=np.uint8)
-        alt_b = np.empty(len(snv), dtype=np.uint8)
+        ref_b = np.empty(n, dtype=np.uint8)
+        alt_b = np.empty(n, dtype=np.uint8)
         bounds = np.searchsorted(rec, np.arange(n_rec + 1))
         for r in np.flatnonzero(np.diff(bounds)).tolist():
             a, b = bounds[r], bounds[r + 1]
             ref_b[a:b] = ref_arr[ref_id[r]][pos[a:b]]
             t = tig_arr[qry_id[r]][qp[a:b]]
             alt_b[a:b] = fasta.COMPLEMENT[t] if rev[r] else t
-        chrom_row = chrom_s[rec]
-        ids = _join(chrom_row.astype(_S), '-', _istr(pos + 1), '-SNV-', _CHR[fasta.UPPER[ref_b]].astype(_S),
-                    _CHR[fasta.UPPER[alt_b]].astype(_S))
-        qp1 = _istr(qp + 1)
-        cols = {
-            '#CHROM': chrom[rec], 'POS': pos.astype(object), 'END': (pos + 1).astype(object), 'ID': ids,
-            'SVTYPE': 'SNV', 'SVLEN': 1, 'REF': _CHR[ref_b], 'ALT': _CHR[alt_b], 'HAP': hap,
-            'QRY_REGION': _join(qry_s[rec].astype(_S), ':', qp1, '-', qp1), 'QRY_STRAND': strand_rec[rec],
-            'CI': 0, 'ALIGN_INDEX': align_index[rec], 'CALL_SOURCE': CALL_SOURCE,
-        }
+        ids = _pyrows.format(n, [('l', chrom_l, rec), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
+                                 ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
         if version_id:
-            cols['ID'] = variant.version_id(pd.Series(cols['ID'], dtype=object)).to_numpy(dtype=object)
-        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, cols['ID'])
+            ids = variant.version_id(pd.Series(_obj(ids), dtype=object)).tolist()
+        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, ids)
+        rec, pos, qp, ref_b, alt_b = rec[order], pos[order], qp[order], ref_b[order], alt_b[order]
+        pos1, qp1 = pos + 1, qp + 1
+        cols = {
+            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(pos1), 'ID': _obj(ids)[order],
+            'SVTYPE': 'SNV', 'SVLEN': 1, 'REF': _CHR[ref_b], 'ALT': _CHR[alt_b], 'HAP': hap,
+            'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec), ('s', ':'), ('i', qp1), ('s', '-'), ('i', qp1)]),
+            'QRY_STRAND': strand_rec[rec], 'CI': 0, 'ALIGN_INDEX': align_index[rec], 'CALL_SOURCE': CALL_SOURCE,
+        }
         df_snv = _frame(cols, SNV_COLUMNS, order)
     else:
         df_snv = _empty(SNV_COLUMNS)
 
     # ------------------------------------------------------------------ INS / DEL rows (cigarcall.py:141-282)
     if len(indel):
+        n = len(indel)
         rec = indel['rec'].astype(np.int64)
         pos = indel['pos'].astype(np.int64)
         end = indel['end'].astype(np.int64)
         svlen = indel['svlen'].astype(np.int64)
-        is_del = indel['svtype'] == 1
+        svtype_l = ['INS', 'DEL']
+        svt = (indel['svtype'] == 1).astype(np.int64)
+        ids = _pyrows.format(n, [('l', chrom_l, rec), ('s', '-'), ('i', pos + 1), ('s', '-'), ('l', svtype_l, svt), ('s', '-'), ('i', svlen)])
+        if version_id:
+            ids = variant.version_id(pd.Series(_obj(ids), dtype=object)).tolist()
+        order = _sort_order(chrom_code_rec[rec], pos, end, ids)
+        indel = indel[order]
+        rec, pos, end, svlen, svt = rec[order], pos[order], end[order], svlen[order], svt[order]
+        is_del = svt == 1
         qp = indel['qry_pos'].astype(np.int64)
         qe = indel['qry_end'].astype(np.int64)
-        svtype = np.where(is_del, 'DEL', 'INS').astype(object)
-        seq = np.empty(len(indel), dtype=object)
-        for i, (r, d, p, n, a, b) in enumerate(zip(rec.tolist(), is_del.tolist(), pos.tolist(), svlen.tolist(),
-                                                   qp.tolist(), qe.tolist())):
-            if d:
-                seq[i] = ref_arr[ref_id[r]][p:p + n].tobytes().decode('ascii')
-            else:
-                s = tig_arr[qry_id[r]][a:b]
-                seq[i] = (fasta.reverse_complement(s) if rev[r] else s).tobytes().decode('ascii')
-        chrom_row = chrom_s[rec]
-        ids = _join(chrom_row.astype(_S), '-', _istr(pos + 1), '-', svtype.astype(_S), '-', _istr(svlen))
-        qry_region = _join(qry_s[rec].astype(_S), ':', _istr(qp + 1), '-', _istr(np.where(is_del, qp + 1, qe)))
+        # SEQ: DEL = reference[pos : pos+n] (unshifted); INS = forward contig[qry_pos : qry_end], reverse-complemented
+        # when the record is on the minus strand (equals the slice of the reference-oriented contig)
+        n_ref = len(ref_arr)
+        which = np.where(is_del, ref_id[rec].astype(np.int64), n_ref + qry_id[rec].astype(np.int64))
+        start = np.where(is_del, pos, qp)
+        rc = (~is_del & rev[rec]).astype(np.uint8)
         cols = {
-            '#CHROM': chrom[rec], 'POS': pos.astype(object), 'END': end.astype(object), 'ID': ids, 'SVTYPE': svtype,
-            'SVLEN': svlen.astype(object), 'HAP': hap, 'QRY_REGION': qry_region, 'QRY_STRAND': strand_rec[rec], 'CI': 0,
-            'ALIGN_INDEX': align_index[rec], 'LEFT_SHIFT': indel['left_shift'].astype(np.int64).astype(object),
-            'HOM_REF': _join(_istr(indel['hom_ref_l']), ',', _istr(indel['hom_ref_r'])),
-            'HOM_TIG': _join(_istr(indel['hom_tig_l']), ',', _istr(indel['hom_tig_r'])),
-            'CALL_SOURCE': CALL_SOURCE, 'SEQ': seq,
+            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(end), 'ID': _obj(ids)[order],
+            'SVTYPE': np.array(svtype_l, dtype=object)[svt], 'SVLEN': _pyrows.ints(svlen), 'HAP': hap,
+            'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec), ('s', ':'), ('i', qp + 1), ('s', '-'), ('i', np.where(is_del, qp + 1, qe))]),
+            'QRY_STRAND': strand_rec[rec], 'CI': 0, 'ALIGN_INDEX': align_index[rec],
+            'LEFT_SHIFT': _pyrows.ints(indel['left_shift'].astype(np.int64)),
+            'HOM_REF': _pyrows.format(n, [('i', indel['hom_ref_l'].astype(np.int64)), ('s', ','), ('i', indel['hom_ref_r'].astype(np.int64))]),
+            'HOM_TIG': _pyrows.format(n, [('i', indel['hom_tig_l'].astype(np.int64)), ('s', ','), ('i', indel['hom_tig_r'].astype(np.int64))]),
+            'CALL_SOURCE': CALL_SOURCE,
+            'SEQ': _pyrows.slices(list(ref_arr) + list(tig_arr), which, start, svlen, rc, fasta.COMPLEMENT.tobytes()),
         }
-        if version_id:
-            cols['ID'] = variant.version_id(pd.Series(cols['ID'], dtype=object)).to_numpy(dtype=object)
-        order = _sort_order(chrom_code_rec[rec], pos, end, cols['ID'])
         df_insdel = _frame(cols, INSDEL_COLUMNS, order)
     else:
         df_insdel = _empty(INSDEL_COLUMNS)

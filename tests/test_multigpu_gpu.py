@@ -1,0 +1,47 @@
+"""Two-GPU run of the distributed walk (NCCL broadcast of the packed reference + host gather). Skipped on
+single-GPU boxes; the host logic is covered on CPU by tests/test_multigpu_cpu.py."""
+import os
+import sys
+
+import pandas as pd
+import pytest
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, tmp, out_q):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), LOCAL_RANK=str(rank), PAVGPU_DEVICE_INDEX=str(rank))
+    import torch.distributed as dist
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pav_b200 import multigpu
+    df = pd.read_csv(os.path.join(tmp, 'wl_align.bed'), sep='\t', dtype={'#CHROM': str, 'QRY_ID': str}, keep_default_na=False)
+    res = multigpu.make_insdel_snv_calls_dist(df, os.path.join(tmp, 'wl_ref.fa'), os.path.join(tmp, 'wl_tig.fa'), 'h1', version_id=True)
+    if rank == 0:
+        out_q.put((res[0].to_csv(sep='\t', index=False), res[1].to_csv(sep='\t', index=False)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpus_equal_oracle(tmp_path):
+    from pav_b200 import _capi, synth
+    if _capi.lib().pavgpu_device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from oracle import pyoracle
+    ref, tigs, df = synth.make_cigar_workload(41, 2, 400_000, 30, 25_000, edit_rate=0.01, rev_frac=0.5)
+    synth.write_cigar_workload(str(tmp_path), ref, tigs, df)
+    df = pd.read_csv(os.path.join(str(tmp_path), 'wl_align.bed'), sep='\t', dtype={'#CHROM': str, 'QRY_ID': str}, keep_default_na=False)
+    exp = pyoracle.make_insdel_snv_calls(df, str(tmp_path / 'wl_ref.fa'), str(tmp_path / 'wl_tig.fa'), 'h1', version_id=True)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0] == exp[0].to_csv(sep='\t', index=False) and got[1] == exp[1].to_csv(sep='\t', index=False)
