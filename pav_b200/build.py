@@ -65,9 +65,10 @@ def build_pyrows(force=False):
     src = os.path.join(CSRC, 'pyrows.c')
     if not force and os.path.exists(PYROWS) and os.path.getmtime(PYROWS) >= os.path.getmtime(src):
         return PYROWS
+    import numpy
     inc = sysconfig.get_paths()['include']
     tmp = PYROWS + f'.{os.getpid()}.tmp'
-    subprocess.check_call(['gcc', '-O2', '-fPIC', '-shared', '-std=gnu11', '-I', inc, '-o', tmp, src])
+    subprocess.check_call(['gcc', '-O2', '-fPIC', '-shared', '-std=gnu11', '-I', inc, '-I', numpy.get_include(), '-o', tmp, src])
     os.replace(tmp, PYROWS)
     return PYROWS
 

@@ -295,11 +295,13 @@ cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 }
 
 // KF (fused K1+K2+K3) -----------------------------------------------------------------------------
-// Single pass over the ops: one CTA = 8 warps = 1024 ops. Tile aggregates travel between CTAs through 16-byte
-// descriptors with a decoupled look-back (status, segment flag, ref/qry advance since the last record head,
-// row counts), so the ops are read once and there is no host round trip for the row totals (the host counted
-// them while packing the ops). Tiles are handed out by an atomic counter so a CTA only ever waits for tiles
-// that are already running.
+// Single pass over the ops: one CTA = 8 warps = 1024 ops. Everything the walk carries is *segmented by record*:
+// ref/qry advance since the record head and the number of SNV / indel rows the record has emitted so far. The
+// first row slot of every record (rec_snv_off / rec_indel_off, "per-record offset buffer") comes from the host,
+// which counts rows per record while it packs the CIGAR text. Tile aggregates travel between CTAs through 16-byte
+// descriptors with a decoupled look-back that stops at the nearest tile containing a record head, so a tile never
+// waits for more than the tiles of its own record (a few for contig-scale records). Tiles are handed out by an
+// atomic counter so a CTA only waits for tiles that are already running.
 //   w0: [1:0] status  [2] has-head  [33:3] ref advance (31 b)  [63:34] indel rows (30 b)
 //   w1: [30:0] qry advance (31 b)   [63:31] SNV rows (33 b)
 constexpr unsigned ST_INVALID = 0, ST_AGG = 1, ST_PREFIX = 2;
@@ -339,29 +341,27 @@ __device__ __forceinline__ ulonglong2 tile_load(const ulonglong2 *p)
     return d;
 }
 
-// older (+) newer for the segmented position sums
-__device__ __forceinline__ void seg_combine(int of, int orr, int oq, int &f, int &r, int &q)
+// v = older (+) v for the record-segmented tuple
+__device__ __forceinline__ void seg_combine(const TileVal &older, TileVal &v)
 {
-    if (!f) { r += orr; q += oq; }
-    f |= of;
+    if (!v.f) { v.r += older.r; v.q += older.q; v.ns += older.ns; v.ni += older.ni; }
+    v.f |= older.f;
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_tiles, unsigned int *__restrict__ tile_counter,
-                  ulonglong2 *__restrict__ desc, const int64_t *__restrict__ qry_len, int4 *__restrict__ snv_rows,
-                  IndelStub *__restrict__ stubs, unsigned long long *__restrict__ first_illegal, int64_t *__restrict__ totals)
+cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_tiles, const int32_t *__restrict__ chunk_rec,
+                  ulonglong2 *__restrict__ desc, const int64_t *__restrict__ qry_len, const int64_t *__restrict__ rec_snv_off,
+                  const int64_t *__restrict__ rec_indel_off, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
+                  unsigned long long *__restrict__ first_illegal, unsigned long long *__restrict__ totals)
 {
-    __shared__ unsigned s_tile;
-    __shared__ int s_f[WARPS_PER_BLOCK], s_r[WARPS_PER_BLOCK], s_q[WARPS_PER_BLOCK];
-    __shared__ int s_pf[WARPS_PER_BLOCK], s_pr[WARPS_PER_BLOCK], s_pq[WARPS_PER_BLOCK];  // folds over warps 0..w
-    __shared__ unsigned s_ns[WARPS_PER_BLOCK], s_ni[WARPS_PER_BLOCK];
-    __shared__ int s_ex_f, s_ex_r, s_ex_q;
-    __shared__ unsigned long long s_ex_ns, s_ex_ni;
+    __shared__ TileVal s_agg[WARPS_PER_BLOCK];   // per-warp aggregates
+    __shared__ TileVal s_fold[WARPS_PER_BLOCK];  // folds over warps 0..w
+    __shared__ TileVal s_ex;                     // exclusive prefix of the tile
+    __shared__ uint32_t s_tot[WARPS_PER_BLOCK][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= n_tiles) return;
+    // Tiles are taken in blockIdx order (like CUB's scan agents): a CTA only ever waits for lower-numbered tiles,
+    // which the hardware has dispatched before it.
+    const int64_t tile = blockIdx.x;
     const int64_t chunk = tile * WARPS_PER_BLOCK + wid;
 
     // ---- per-lane ops and record lookup (one search per warp; per-lane search only when the chunk spans records)
@@ -373,92 +373,130 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
         uint4 raw = make_uint4(0, 0, 0, 0);
         if (L.nvalid > 0) raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));
         L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
-        int64_t gfirst = chunk * CHUNK;
-        int32_t rec_lo = 0;
-        if (lane == 0 && gfirst < n_ops) rec_lo = find_rec(rv.op_off, rv.n_rec, gfirst);
-        rec_lo = __shfl_sync(FULL, rec_lo, 0);
+        // record of the chunk's first op comes from a host-built index (one load instead of a binary search);
+        // lanes search on their own only when the chunk spans several records
+        int32_t rec_lo = (chunk * CHUNK < n_ops) ? __ldg(chunk_rec + chunk) : 0;
         L.rec0 = rec_lo;
         if (L.nvalid > 0 && L.g0 >= __ldg(rv.op_off + rec_lo + 1)) L.rec0 = find_rec(rv.op_off, rv.n_rec, L.g0);
     }
-    int f, r, q; uint32_t ns, ni;
-    lane_aggregate(L, rv, f, r, q, ns, ni);
+    // lane-local aggregate, counts reset at record heads too
+    int f = 0, r = 0, q = 0;
+    uint32_t ns = 0, ni = 0, ns_all = 0, ni_all = 0;
+    {
+        int32_t rec = L.rec0;
+        int64_t next_off = L.nvalid > 0 ? __ldg(rv.op_off + rec + 1) : 0;
+        int64_t cur_off = L.nvalid > 0 ? __ldg(rv.op_off + rec) : 0;
+#pragma unroll
+        for (int j = 0; j < OPS_PER_LANE; j++) {
+            if (j < L.nvalid) {
+                int64_t g = L.g0 + j;
+                while (g >= next_off) { ++rec; cur_off = next_off; next_off = __ldg(rv.op_off + rec + 1); }
+                if (g == cur_off) { f = 1; r = 0; q = 0; ns = 0; ni = 0; }
+                uint32_t code = L.op[j] & 15u, len = L.op[j] >> 4;
+                uint32_t bit = 1u << code;
+                if (bit & REF_ADV_MASK) r += (int)len;
+                if (bit & QRY_ADV_MASK) q += (int)len;
+                if (code == PAVGPU_OP_X) { ns += len; ns_all += len; }
+                if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) { ni += 1; ni_all += 1; }
+            }
+        }
+    }
+    // segmented inclusive warp scan of (f, r, q, ns, ni)
     int fi = f, ri = r, qi = q;
-    warp_seg_scan(lane, fi, ri, qi);
-    uint32_t nsi = warp_inc_scan(lane, ns), nii = warp_inc_scan(lane, ni);
-    if (lane == 31) { s_f[wid] = fi; s_r[wid] = ri; s_q[wid] = qi; s_ns[wid] = nsi; s_ni[wid] = nii; }
+    uint32_t nsi = ns, nii = ni;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int f2 = __shfl_up_sync(FULL, fi, d), r2 = __shfl_up_sync(FULL, ri, d), q2 = __shfl_up_sync(FULL, qi, d);
+        uint32_t s2 = __shfl_up_sync(FULL, nsi, d), i2 = __shfl_up_sync(FULL, nii, d);
+        if (lane >= d) {
+            if (!fi) { ri += r2; qi += q2; nsi += s2; nii += i2; }
+            fi |= f2;
+        }
+    }
+    // row totals of the tile (plain sums) for the end-of-run consistency check
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { ns_all += __shfl_xor_sync(FULL, ns_all, d); ni_all += __shfl_xor_sync(FULL, ni_all, d); }
+    if (lane == 31) s_agg[wid] = TileVal{fi, ri, qi, (unsigned long long)nsi, (unsigned long long)nii};
+    if (lane == 0) { s_tot[wid][0] = ns_all; s_tot[wid][1] = ni_all; }
     __syncthreads();
 
-    // ---- warp 0: tile aggregate, publish, look back, publish the inclusive prefix
+    // ---- warp 0: tile aggregate, publish, look back to the nearest record head, publish the inclusive prefix
     if (wid == 0) {
         TileVal agg{0, 0, 0, 0ull, 0ull};
         for (int w = 0; w < WARPS_PER_BLOCK; w++) {
-            int nf = s_f[w], nr = s_r[w], nq = s_q[w];
-            seg_combine(agg.f, agg.r, agg.q, nf, nr, nq);   // (nf, nr, nq) = fold(warps 0..w)
-            agg.f = nf; agg.r = nr; agg.q = nq;
-            agg.ns += s_ns[w]; agg.ni += s_ni[w];
-            if (lane == 0) { s_pf[w] = nf; s_pr[w] = nr; s_pq[w] = nq; }
+            TileVal nv = s_agg[w];
+            seg_combine(agg, nv);   // nv = fold(warps 0..w)
+            agg = nv;
+            if (lane == 0) s_fold[w] = nv;
         }
+        const bool self_contained = (tile == 0) || agg.f;  // nothing before this tile can reach past its first head
         if (lane == 0) tile_store(desc + tile, tile_pack(tile == 0 ? ST_PREFIX : ST_AGG, agg));
         TileVal ex{0, 0, 0, 0ull, 0ull};
-        if (tile > 0) {
+        // the tile's first ops still belong to the record of the previous tile unless the tile starts with a head;
+        // the exclusive prefix is needed whenever the first op of the tile is not a head
+        const bool first_is_head = (tile * (int64_t)WARPS_PER_BLOCK * CHUNK) == __ldg(rv.op_off + __shfl_sync(FULL, L.rec0, 0));
+        (void)self_contained;
+        if (tile > 0 && !first_is_head) {
             int64_t base = tile - 1;
             bool done = false;
             while (!done) {
                 int64_t idx = base - lane;
                 TileVal v{0, 0, 0, 0ull, 0ull};
-                unsigned st = ST_PREFIX;  // tiles before the first one: identity prefix
+                unsigned st = ST_PREFIX;  // before the first tile: identity prefix
                 if (idx >= 0) {
                     do { st = tile_unpack(tile_load(desc + idx), v); } while (st == ST_INVALID);
-                }
-                unsigned pm = __ballot_sync(FULL, st == ST_PREFIX);
-                int k = __ffs((int)pm) - 1;              // nearest lane holding an inclusive prefix (-1: none)
+                } else v.f = 1;
+                // nearest lane whose value is final for our purpose: an inclusive prefix, or an aggregate holding a head
+                unsigned pm = __ballot_sync(FULL, st == ST_PREFIX || v.f);
+                int k = __ffs((int)pm) - 1;
                 int last = (k < 0) ? 31 : k;
                 if (lane > last) { v.f = 0; v.r = 0; v.q = 0; v.ns = 0; v.ni = 0; }
                 // fold lanes last..0 in tile order (higher lane = older tile): result in lane 0
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    int of = __shfl_down_sync(FULL, v.f, d), orr = __shfl_down_sync(FULL, v.r, d), oq = __shfl_down_sync(FULL, v.q, d);
-                    unsigned long long ons = __shfl_down_sync(FULL, v.ns, d), oni = __shfl_down_sync(FULL, v.ni, d);
-                    if (lane + d < 32) { seg_combine(of, orr, oq, v.f, v.r, v.q); v.ns += ons; v.ni += oni; }
+                    TileVal o;
+                    o.f = __shfl_down_sync(FULL, v.f, d); o.r = __shfl_down_sync(FULL, v.r, d); o.q = __shfl_down_sync(FULL, v.q, d);
+                    o.ns = __shfl_down_sync(FULL, v.ns, d); o.ni = __shfl_down_sync(FULL, v.ni, d);
+                    if (lane + d < 32) seg_combine(o, v);
                 }
-                // window (older) (+) what we already have (newer)
-                int wf = __shfl_sync(FULL, v.f, 0), wr = __shfl_sync(FULL, v.r, 0), wq = __shfl_sync(FULL, v.q, 0);
-                unsigned long long wns = __shfl_sync(FULL, v.ns, 0), wni = __shfl_sync(FULL, v.ni, 0);
-                seg_combine(wf, wr, wq, ex.f, ex.r, ex.q);
-                ex.ns += wns; ex.ni += wni;
+                TileVal win;
+                win.f = __shfl_sync(FULL, v.f, 0); win.r = __shfl_sync(FULL, v.r, 0); win.q = __shfl_sync(FULL, v.q, 0);
+                win.ns = __shfl_sync(FULL, v.ns, 0); win.ni = __shfl_sync(FULL, v.ni, 0);
+                seg_combine(win, ex);   // window (older) (+) what we already have (newer)
                 done = (k >= 0);
                 base -= 32;
             }
-            if (lane == 0) {
-                TileVal inc = agg;
-                seg_combine(ex.f, ex.r, ex.q, inc.f, inc.r, inc.q);
-                inc.ns += ex.ns; inc.ni += ex.ni;
-                tile_store(desc + tile, tile_pack(ST_PREFIX, inc));
-            }
         }
         if (lane == 0) {
-            s_ex_f = ex.f; s_ex_r = ex.r; s_ex_q = ex.q; s_ex_ns = ex.ns; s_ex_ni = ex.ni;
-            if (tile == n_tiles - 1) { totals[0] = (int64_t)(ex.ns + agg.ns); totals[1] = (int64_t)(ex.ni + agg.ni); }
+            unsigned long long ts = 0, ti = 0;
+            for (int w = 0; w < WARPS_PER_BLOCK; w++) { ts += s_tot[w][0]; ti += s_tot[w][1]; }
+            if (ts) atomicAdd(totals, ts);
+            if (ti) atomicAdd(totals + 1, ti);
+            if (tile > 0) {
+                TileVal inc = agg;
+                seg_combine(ex, inc);
+                tile_store(desc + tile, tile_pack(ST_PREFIX, inc));
+            }
+            s_ex = ex;
         }
     }
     __syncthreads();
 
     // ---- exclusive prefix of this warp = tile prefix (+) fold of the earlier warps of the tile
-    int cf = s_ex_f, cr = s_ex_r, cq = s_ex_q;
-    unsigned long long cns = s_ex_ns, cni = s_ex_ni;
+    TileVal c = s_ex;
     if (wid > 0) {
-        int pf = s_pf[wid - 1], pr = s_pr[wid - 1], pq = s_pq[wid - 1];  // inclusive fold over warps 0..wid-1
-        seg_combine(cf, cr, cq, pf, pr, pq);
-        cf = pf; cr = pr; cq = pq;
-        for (int w = 0; w < wid; w++) { cns += s_ns[w]; cni += s_ni[w]; }
+        TileVal pw = s_fold[wid - 1];
+        seg_combine(c, pw);
+        c = pw;
     }
-    // ---- emit (same as K3)
+    // ---- emit
     int ef = __shfl_up_sync(FULL, fi, 1), er = __shfl_up_sync(FULL, ri, 1), eq = __shfl_up_sync(FULL, qi, 1);
-    if (lane == 0) { ef = 0; er = 0; eq = 0; }
-    int run_r = ef ? er : er + cr;
-    int run_q = ef ? eq : eq + cq;
-    long long snv_cur = (long long)cns + (long long)(nsi - ns);
-    long long indel_cur = (long long)cni + (long long)(nii - ni);
+    uint32_t ens = __shfl_up_sync(FULL, nsi, 1), eni = __shfl_up_sync(FULL, nii, 1);
+    if (lane == 0) { ef = 0; er = 0; eq = 0; ens = 0; eni = 0; }
+    int run_r = ef ? er : er + c.r;
+    int run_q = ef ? eq : eq + c.q;
+    long long run_ns = ef ? (long long)ens : (long long)ens + (long long)c.ns;   // rows this record emitted before this lane
+    long long run_ni = ef ? (long long)eni : (long long)eni + (long long)c.ni;
     uint32_t prev_op = __shfl_up_sync(FULL, L.op[OPS_PER_LANE - 1], 1);
     if (lane == 0) prev_op = (L.nvalid > 0 && L.g0 > 0) ? __ldg(ops + L.g0 - 1) : 0u;
     if (L.nvalid == 0) return;
@@ -468,6 +506,7 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
     int32_t rpos = __ldg(rv.pos + rec);
     int rrev = __ldg(rv.rev + rec);
     int32_t qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+    long long snv_base = __ldg(rec_snv_off + rec), indel_base = __ldg(rec_indel_off + rec);
 #pragma unroll
     for (int j = 0; j < OPS_PER_LANE; j++) {
         if (j < L.nvalid) {
@@ -478,24 +517,27 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
                 rpos = __ldg(rv.pos + rec);
                 rrev = __ldg(rv.rev + rec);
                 qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+                snv_base = __ldg(rec_snv_off + rec);
+                indel_base = __ldg(rec_indel_off + rec);
             }
             bool head = (g == cur_off);
-            if (head) { run_r = 0; run_q = 0; }
+            if (head) { run_r = 0; run_q = 0; run_ns = 0; run_ni = 0; }
             uint32_t op = L.op[j], code = op & 15u, len = op >> 4;
             int32_t op_idx = (int32_t)(g - cur_off);
             int32_t pos_ref = rpos + run_r, pos_qry = run_q;
             if (code == PAVGPU_OP_X) {
+                long long slot = snv_base + run_ns;
                 for (uint32_t i = 0; i < len; i++) {
                     int32_t t = pos_qry + (int32_t)i;
-                    snv_rows[snv_cur + i] = make_int4(pos_ref + (int32_t)i, rrev ? qlen - 1 - t : t, rec, op_idx);
+                    snv_rows[slot + i] = make_int4(pos_ref + (int32_t)i, rrev ? qlen - 1 - t : t, rec, op_idx);
                 }
-                snv_cur += len;
+                run_ns += len;
             } else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) {
-                int4 *dst = reinterpret_cast<int4 *>(stubs + indel_cur);
+                int4 *dst = reinterpret_cast<int4 *>(stubs + indel_base + run_ni);
                 int32_t eqb = (!head && (prev_op & 15u) == PAVGPU_OP_EQ) ? (int32_t)(prev_op >> 4) : 0;
                 dst[0] = make_int4(rec, op_idx, (code == PAVGPU_OP_D), (int32_t)len);
                 dst[1] = make_int4(pos_ref, pos_qry, eqb, 0);
-                ++indel_cur;
+                ++run_ni;
             } else if (!((1u << code) & LEGAL_MASK)) {
                 atomicMin(first_illegal, (unsigned long long)g);
             }
@@ -521,32 +563,45 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, RecView rv
     OSeq R{ref.pack2, ref.nmask, __ldg(ref.off + rid), __ldg(ref.len + rid), 0};
     OSeq Q{qry.pack2, qry.nmask, __ldg(qry.off + qid), __ldg(qry.len + qid), (int)__ldg(rv.rev + rec)};
     int32_t L = (int32_t)Q.len;
+    // Five scans per indel (cigarcall.py:149-155,178-182 / :225-231,247-251): the left shift, then the four
+    // breakpoint homologies at the shifted position. One rolled loop so the scan code exists once in the kernel
+    // (with all five call sites inlined the kernel is instruction-fetch bound).
+    //   INS: SV sequence = contig[sq : sq+n] (re-sliced after the shift); DEL: reference[pr : pr+n] (never re-sliced)
+    const bool ins = (svtype == 0);
+    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
+    int32_t sp = pr, sq = pq;
+#pragma unroll 1
+    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {
+        const bool on_ref = sc <= 2;            // scans 0..2 walk the reference, 3..4 the contig
+        const int left = (sc == 0 || sc == 1 || sc == 3);
+        int64_t p;
+        if (sc == 0) p = (int64_t)pr - 1;
+        else if (sc == 1) p = (int64_t)sp - 1;
+        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
+        else if (sc == 3) p = (int64_t)sq - 1;
+        else p = ins ? (int64_t)sq + n : (int64_t)sq;
+        const OSeq &T = on_ref ? R : Q;
+        const OSeq &V = ins ? Q : R;
+        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;   // sq == pq while sc == 0
+        int h = dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, left);
+        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
+        else if (sc == 1) hom_rl = h;
+        else if (sc == 2) hom_rr = h;
+        else if (sc == 3) hom_tl = h;
+        else hom_tr = h;
+    }
     pavgpu_indel_row o;
     o.rec = rec; o.op_idx = op_idx; o.svtype = svtype; o.svlen = n; o.pad[0] = o.pad[1] = 0;
-    if (svtype == 0) {  // INS, cigarcall.py:141-213
-        int ls = 0;
-        if (eqb > 0) ls = min(eqb, dev_left_homology(R, (int64_t)pr - 1, Q, pq, n));
-        int32_t sp = pr - ls, sq = pq - ls;
-        o.left_shift = ls;
+    o.left_shift = ls;
+    o.hom_ref_l = hom_rl; o.hom_ref_r = hom_rr; o.hom_tig_l = hom_tl; o.hom_tig_r = hom_tr;
+    if (ins) {          // cigarcall.py:157-173
         o.pos = sp; o.end = sp + 1;
         if (Q.rev) { o.qry_end = L - sq; o.qry_pos = o.qry_end - n; } else { o.qry_pos = sq; o.qry_end = sq + n; }
-        o.hom_ref_l = dev_left_homology(R, (int64_t)sp - 1, Q, sq, n);
-        o.hom_ref_r = dev_right_homology(R, sp, Q, sq, n);
-        o.hom_tig_l = dev_left_homology(Q, (int64_t)sq - 1, Q, sq, n);
-        o.hom_tig_r = dev_right_homology(Q, (int64_t)sq + n, Q, sq, n);
         o.seq_start = sq;
-    } else {  // DEL, cigarcall.py:217-282 (POS/END/SEQ stay unshifted)
-        int ls = 0;
-        if (eqb > 0) ls = min(eqb, dev_left_homology(R, (int64_t)pr - 1, R, pr, n));
-        int32_t sp = pr - ls, se = sp + n, sq = pq - ls;
-        o.left_shift = ls;
+    } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
         o.pos = pr; o.end = pr + n;
         o.qry_pos = Q.rev ? L - sq : sq;
         o.qry_end = o.qry_pos + 1;
-        o.hom_ref_l = dev_left_homology(R, (int64_t)sp - 1, R, pr, n);
-        o.hom_ref_r = dev_right_homology(R, se, R, pr, n);
-        o.hom_tig_l = dev_left_homology(Q, (int64_t)sq - 1, R, pr, n);
-        o.hom_tig_r = dev_right_homology(Q, sq, R, pr, n);
         o.seq_start = pr;
     }
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
@@ -594,6 +649,8 @@ struct pavgpu_cigar_batch {
     int64_t n_tiles;
     ulonglong2 *d_desc;
     unsigned int *d_tile_counter;
+    int64_t *d_rec_snv_off, *d_rec_indel_off;   // first row slot of every record (host-counted)
+    int32_t *d_chunk_rec;                        // record of the first op of every 128-op chunk (host-built index)
     bool fused;
     unsigned long long first_illegal;
     bool ran;
@@ -659,7 +716,7 @@ static void batch_release(pavgpu_cigar_batch *b)
     cudaFree(b->d_ref_id); cudaFree(b->d_qry_id); cudaFree(b->d_pos); cudaFree(b->d_rev); cudaFree(b->d_op_off);
     cudaFree(b->d_ops); cudaFree(b->d_agg); cudaFree(b->d_cnt); cudaFree(b->d_pre_rq); cudaFree(b->d_pre_cnt);
     cudaFree(b->d_totals); cudaFree(b->d_first_illegal); cudaFree(b->d_snv); cudaFree(b->d_stub); cudaFree(b->d_indel);
-    cudaFree(b->d_desc); cudaFree(b->d_tile_counter);
+    cudaFree(b->d_desc); cudaFree(b->d_tile_counter); cudaFree(b->d_rec_snv_off); cudaFree(b->d_rec_indel_off); cudaFree(b->d_chunk_rec);
 }
 
 extern "C" __attribute__((visibility("default"))) void pavgpu_cigar_batch_free(pavgpu_cigar_batch *b)
@@ -688,10 +745,24 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
     b->h_op_off.assign(op_off, op_off + n_rec + 1);
     b->h_pos.assign(pos, pos + n_rec);
     b->n_tiles = (b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    for (int64_t i = 0; i < n_ops; i++) {
-        uint32_t code = ops[i] & 15u;
-        if (code == PAVGPU_OP_X) b->host_n_snv += ops[i] >> 4;
-        else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) b->host_n_indel += 1;
+    std::vector<int64_t> rec_snv_off((size_t)n_rec + 1), rec_indel_off((size_t)n_rec + 1);
+    for (int32_t r = 0; r < n_rec; r++) {   // per-record row counts -> first row slot of every record
+        rec_snv_off[r] = b->host_n_snv; rec_indel_off[r] = b->host_n_indel;
+        for (int64_t i = op_off[r]; i < op_off[r + 1]; i++) {
+            uint32_t code = ops[i] & 15u;
+            if (code == PAVGPU_OP_X) b->host_n_snv += ops[i] >> 4;
+            else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) b->host_n_indel += 1;
+        }
+    }
+    rec_snv_off[n_rec] = b->host_n_snv; rec_indel_off[n_rec] = b->host_n_indel;
+    std::vector<int32_t> chunk_rec((size_t)std::max<int64_t>(b->n_chunks, 1), 0);
+    {
+        int32_t r = 0;
+        for (int64_t c = 0; c < b->n_chunks; c++) {
+            int64_t g = c * CHUNK;
+            while (r + 1 < n_rec && op_off[r + 1] <= g) r++;
+            chunk_rec[(size_t)c] = r;
+        }
     }
     // single-pass walk unless the descriptor fields would overflow (33-bit SNV count, 30-bit indel count) or the
     // multi-pass kernels are requested for A/B timing
@@ -709,6 +780,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
         CUDA_TRY(cudaMalloc(&b->d_totals, 2 * 8)); CUDA_TRY(cudaMalloc(&b->d_first_illegal, 8));
         CUDA_TRY(cudaMalloc(&b->d_desc, sizeof(ulonglong2) * (size_t)std::max<int64_t>(b->n_tiles, 1)));
         CUDA_TRY(cudaMalloc(&b->d_tile_counter, sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&b->d_rec_snv_off, (nr + 1) * 8)); CUDA_TRY(cudaMalloc(&b->d_rec_indel_off, (nr + 1) * 8));
+        CUDA_TRY(cudaMemcpyAsync(b->d_rec_snv_off, rec_snv_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->d_rec_indel_off, rec_indel_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMalloc(&b->d_chunk_rec, chunk_rec.size() * 4));
+        CUDA_TRY(cudaMemcpyAsync(b->d_chunk_rec, chunk_rec.data(), chunk_rec.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         if (b->fused) {  // row buffers are sized from the host counts: no mid-run round trip
             if (b->host_n_snv) { CUDA_TRY(cudaMalloc(&b->d_snv, (size_t)b->host_n_snv * sizeof(int4))); b->cap_snv = b->host_n_snv; }
             if (b->host_n_indel) {
@@ -758,9 +834,9 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     b->n_snv = b->n_indel = 0;
     if (b->n_chunks > 0 && b->fused) {
         CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_tiles, st));
-        CUDA_TRY(cudaMemsetAsync(b->d_tile_counter, 0, sizeof(unsigned int), st));
-        cigar_walk_kernel<<<(unsigned)b->n_tiles, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_tiles, b->d_tile_counter, b->d_desc,
-                                                                             qry_store->d_len, b->d_snv, b->d_stub, b->d_first_illegal, b->d_totals);
+        cigar_walk_kernel<<<(unsigned)b->n_tiles, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_tiles, b->d_chunk_rec, b->d_desc,
+                                                                             qry_store->d_len, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
+                                                                             b->d_first_illegal, reinterpret_cast<unsigned long long *>(b->d_totals));
         launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));

@@ -113,29 +113,52 @@ __device__ __forceinline__ void fwd_window(const OSeq &s, int64_t f, uint64_t &b
 }
 
 // Window of 32 bases starting at oriented position t (reverse-complement view when s.rev).
+// (An out-of-line variant of this and of dev_homology_raw was measured on B200: 0.176 ms vs 0.148 ms inlined for the
+// C2 homology kernel -- call overhead and spills cost more than the instruction-fetch stalls they remove.)
+static __device__ __forceinline__ ulonglong2 oseq_window_raw(const uint64_t *pack2, const uint32_t *nmask, int64_t base, int64_t len, int rev,
+                                                          int64_t t)
+{
+    OSeq s{pack2, nmask, base, len, rev};
+    uint64_t b; uint32_t m;
+    if (!rev) {
+        fwd_window(s, t, b, m);
+    } else {
+        fwd_window(s, len - t - 32, b, m);
+        b = revcomp32(b);
+        m = __brev(m);
+    }
+    return make_ulonglong2(b, (unsigned long long)m);
+}
+
 __device__ __forceinline__ void oseq_window(const OSeq &s, int64_t t, uint64_t &bases, uint32_t &mask)
 {
-    if (!s.rev) { fwd_window(s, t, bases, mask); return; }
-    uint64_t b; uint32_t m;
-    fwd_window(s, s.len - t - 32, b, m);
-    bases = revcomp32(b);
-    mask = __brev(m);
+    ulonglong2 r = oseq_window_raw(s.pack2, s.nmask, s.base, s.len, s.rev, t);
+    bases = r.x;
+    mask = (uint32_t)r.y;
 }
 
-// Longest common prefix of A[a..] and B[b..] (stops at the first mismatch, non-ACGT base or sequence end
-// on either side), capped at `limit`. 32 bases per step.
-__device__ __forceinline__ int64_t lcp_forward(const OSeq &A, int64_t a, const OSeq &B, int64_t b, int64_t limit)
+// Longest common extension of A from a and B from b, 32 bases per step, capped at `limit`:
+//   left == 0: common prefix of A[a..] and B[b..]        (window i covers a+32i .. a+32i+31)
+//   left != 0: common suffix of A[..a] and B[..b]         (window i covers a-32i-31 .. a-32i)
+// Stops at the first mismatch, non-ACGT base or sequence end on either side.
+__device__ __forceinline__ int64_t common_extension(const OSeq &A, int64_t a, const OSeq &B, int64_t b, int64_t limit, int left)
 {
     int64_t h = 0;
     while (h < limit) {
         uint64_t wa, wb; uint32_t ma, mb;
-        oseq_window(A, a + h, wa, ma);
-        oseq_window(B, b + h, wb, mb);
+        oseq_window(A, left ? a - h - 31 : a + h, wa, ma);
+        oseq_window(B, left ? b - h - 31 : b + h, wb, mb);
         uint64_t x = wa ^ wb;
         uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;      // one bit per differing base
-        int stop_d = d ? (__clzll((long long)d) >> 1) : 32;       // first base = most significant group
         uint32_t m = ma | mb;
-        int stop_m = m ? (__ffs((int)m) - 1) : 32;
+        int stop_d, stop_m;
+        if (left) {   // last base of the window = least significant group / highest mask bit
+            stop_d = d ? ((__ffsll((long long)d) - 1) >> 1) : 32;
+            stop_m = m ? __clz((int)m) : 32;
+        } else {      // first base = most significant group / lowest mask bit
+            stop_d = d ? (__clzll((long long)d) >> 1) : 32;
+            stop_m = m ? (__ffs((int)m) - 1) : 32;
+        }
         int stop = min(stop_d, stop_m);
         if (stop < 32) { h += stop; return h < limit ? h : limit; }
         h += 32;
@@ -143,45 +166,32 @@ __device__ __forceinline__ int64_t lcp_forward(const OSeq &A, int64_t a, const O
     return limit;
 }
 
-// Longest common suffix of A[..a] and B[..b] (positions a, b inclusive, walking towards position 0).
-__device__ __forceinline__ int64_t lcs_backward(const OSeq &A, int64_t a, const OSeq &B, int64_t b, int64_t limit)
+// pavlib/call.py:542-592 (left != 0) and :595-647 (left == 0). T: flank searched from p away from the
+// breakpoint; the SV sequence is V[v0 : v0+n], read circularly (leftwards from its end: sv[-((h+1) % n)],
+// index -0 == 0; rightwards from its start: sv[h % n]). Word-parallel form: the first n steps are a common
+// suffix/prefix of the flank with V; once a whole copy of V matched, step h compares T[p -/+ h] with
+// V[...] = T[p -/+ h +/- n], i.e. the scan continues as the common extension of the flank with itself
+// shifted by n.
+static __device__ __forceinline__ int dev_homology_raw(const uint64_t *t_pack2, const uint32_t *t_nmask, int64_t t_base, int64_t t_len, int t_rev,
+                                                    int64_t p, const uint64_t *v_pack2, const uint32_t *v_nmask, int64_t v_base, int64_t v_len,
+                                                    int v_rev, int64_t v0, int n, int left)
 {
-    int64_t h = 0;
-    while (h < limit) {
-        uint64_t wa, wb; uint32_t ma, mb;
-        oseq_window(A, a - h - 31, wa, ma);
-        oseq_window(B, b - h - 31, wb, mb);
-        uint64_t x = wa ^ wb;
-        uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
-        int stop_d = d ? ((__ffsll((long long)d) - 1) >> 1) : 32;  // last base = least significant group
-        uint32_t m = ma | mb;
-        int stop_m = m ? __clz((int)m) : 32;
-        int stop = min(stop_d, stop_m);
-        if (stop < 32) { h += stop; return h < limit ? h : limit; }
-        h += 32;
-    }
-    return limit;
+    const OSeq T{t_pack2, t_nmask, t_base, t_len, t_rev};
+    const OSeq V{v_pack2, v_nmask, v_base, v_len, v_rev};
+    if (n <= 0 || p < 0 || p >= T.len) return 0;
+    int64_t h = common_extension(T, p, V, left ? v0 + n - 1 : v0, n, left);
+    if (h < n) return (int)h;
+    return (int)(n + common_extension(T, left ? p - n : p + n, T, p, (int64_t)1 << 40, left));
 }
 
-// pavlib/call.py:542-592. T: sequence searched leftwards from p; the SV sequence is V[v0 : v0+n], read
-// circularly from its end (sv[-((h+1) % n)], index -0 == 0). Word-parallel form: the first n steps are a
-// common-suffix of T[..p] with V[v0..v0+n-1]; once a whole copy of V matched, step h compares T[p-h] with
-// V[(n-1-h) mod n] = T[p-h+n], i.e. the scan continues as a common suffix of T[..p-n] with T[..p].
 __device__ __forceinline__ int dev_left_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
 {
-    if (p < 0 || n <= 0) return 0;
-    int64_t h = lcs_backward(T, p, V, v0 + n - 1, n);
-    if (h < n) return (int)h;
-    return (int)(n + lcs_backward(T, p - n, T, p, (int64_t)1 << 40));
+    return dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, 1);
 }
 
-// pavlib/call.py:595-647, same idea forwards: T[p+h] vs V[h mod n] = T[p+h-n] after the first copy.
 __device__ __forceinline__ int dev_right_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
 {
-    if (p >= T.len || n <= 0 || p < 0) return 0;
-    int64_t h = lcp_forward(T, p, V, v0, n);
-    if (h < n) return (int)h;
-    return (int)(n + lcp_forward(T, p + n, T, p, (int64_t)1 << 40));
+    return dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, 0);
 }
 
 static inline float ev_ms(cudaEvent_t a, cudaEvent_t b)

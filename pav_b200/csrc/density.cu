@@ -11,11 +11,13 @@
 //   -- host: keep-mask (state count >= 20), N, dense row offsets --
 //   D3 compact_kernel      order-preserving compaction of informative k-mers -> KMER / INDEX / STATE_MER
 //   D4 kde_prepare_kernel  per state: n, mean, var(ddof=1) of INDEX_DEN -> bandwidth L_s and norm_s
-//   D5 kde_table_kernel    T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both
-//                          live on the integer lattice, so N exps replace N * E exps
-//   D6 kde_eval_kernel     K_s(j) = norm_s * sum_{i: STATE_MER[i]=s} T_s[|i - j|] at the sampled lattice
-//                          (every srs-th point + last); float64, threads sweep data points so that table
-//                          and state reads are coalesced
+//   D5 runs_kernel         maximal runs of equal STATE_MER in INDEX_DEN space (start, length, state)
+//      kde_tree_kernel     T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both live
+//                          on the integer lattice, so N exps replace N * E exps; the table is the leaf level
+//                          of a binary sum tree (node i = node 2i + node 2i+1, all terms positive)
+//   D6 kde_eval_kernel     K_s(j) = norm_s * sum over runs [a,b] of state s of sum_{i=a..b} T_s[|i - j|]; the
+//                          inner sum is one or two range sums of the tree (<= 2 log2 N reads, no cancellation),
+//                          so a point costs O(#runs * log N) instead of O(N); 8 lanes share one point
 //   D7 gap_classify_kernel per gap: state change / argmax change / |delta| > 0.005 => list of points that
 //                          need a full evaluation
 //   D6' kde_eval_kernel    on that list
@@ -37,8 +39,10 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint64_t EMPTY_KEY = ~0ull;
 constexpr int TILE = 1024;       // positions per block in D2 / D3
-constexpr int EVAL_GROUP = 4;    // evaluation points per block in D6
+constexpr int EVAL_LANES = 8;    // lanes that share one evaluation point in D6
 constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_GROUP = EVAL_THREADS / EVAL_LANES;  // evaluation points per block
+constexpr int TREE_THREADS = 1024;
 
 struct WinPlan {  // per window, device-visible
     // inputs
@@ -58,7 +62,8 @@ struct WinPlan {  // per window, device-visible
     int32_t smoothed;
     int64_t row_off;              // dense row offset
     int32_t n_samp;               // sampled lattice points
-    int32_t pad1;
+    int32_t npad;                 // leaves of the sum tree (power of two >= N)
+    int64_t tree_off;             // offset (doubles) of this window's tree inside each per-state tree slab
 };
 
 struct WinCounts {  // written by D1 / D2
@@ -287,98 +292,149 @@ kde_prepare_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ 
 }
 
 // D5 ---------------------------------------------------------------------------------------------
+// One block per window: maximal runs of equal STATE_MER, in order, at run_start/run_len/run_state[row_off + r].
 __global__ void __launch_bounds__(256)
-kde_table_kernel(const WinPlan *__restrict__ plan, int32_t win_base, const KdeParams *__restrict__ kp, double *__restrict__ tab0,
-                 double *__restrict__ tab1, double *__restrict__ tab2)
+runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_mer, int32_t *__restrict__ run_start,
+            int32_t *__restrict__ run_len, int8_t *__restrict__ run_state, int32_t *__restrict__ n_runs)
 {
-    int32_t w = win_base + blockIdx.y;
+    int32_t w = blockIdx.x;
+    const WinPlan P = plan[w];
+    if (!P.smoothed) { if (threadIdx.x == 0) n_runs[w] = 0; return; }
+    const int8_t *sm = state_mer + P.row_off;
+    int32_t N = P.n_rows;
+    __shared__ int s_scan[256];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {
+        int32_t i = i0 + threadIdx.x;
+        int head = (i < N) && (i == 0 || sm[i] != sm[i - 1]);
+        s_scan[threadIdx.x] = head;
+        __syncthreads();
+        for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+            int v = (threadIdx.x >= (unsigned)d) ? s_scan[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (head) {
+            int32_t r = s_base + s_scan[threadIdx.x] - 1;
+            run_start[P.row_off + r] = i;
+            run_state[P.row_off + r] = sm[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_base += s_scan[threadIdx.x];
+        __syncthreads();
+    }
+    int32_t nr = s_base;
+    for (int32_t r = threadIdx.x; r < nr; r += blockDim.x) {
+        int32_t a = run_start[P.row_off + r];
+        int32_t e = (r + 1 < nr) ? run_start[P.row_off + r + 1] : N;
+        run_len[P.row_off + r] = e - a;
+    }
+    if (threadIdx.x == 0) n_runs[w] = nr;
+}
+
+// One block per (window, state): leaves tree[npad + d] = exp(-(d / L)^2 / 2) for d < N (0 beyond), then the
+// internal nodes level by level (node i = node 2i + node 2i+1).
+__global__ void __launch_bounds__(TREE_THREADS)
+kde_tree_kernel(const WinPlan *__restrict__ plan, const KdeParams *__restrict__ kp, double *__restrict__ tree0, double *__restrict__ tree1,
+                double *__restrict__ tree2)
+{
+    int32_t w = blockIdx.x / 3, s = blockIdx.x % 3;
     const WinPlan P = plan[w];
     if (!P.smoothed) return;
-    int32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= P.n_rows) return;
-    const KdeParams K = kp[w];
-    double *tabs[3] = {tab0, tab1, tab2};
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
+    if (kp[w].n[s] == 0) return;   // state absent: never read
+    double *t = (s == 0 ? tree0 : (s == 1 ? tree1 : tree2)) + P.tree_off;
+    const int32_t N = P.n_rows, npad = P.npad;
+    const double L = kp[w].L[s];
+    for (int32_t d = threadIdx.x; d < npad; d += blockDim.x) {
         double v = 0.0;
-        if (K.n[s] > 0) {
-            double t = (double)d / K.L[s];
-            v = exp(-(t * t) / 2.0);
-        }
-        tabs[s][P.row_off + d] = v;
+        if (d < N) { double x = (double)d / L; v = exp(-(x * x) / 2.0); }
+        t[npad + d] = v;
     }
+    __syncthreads();
+    for (int32_t len = npad >> 1; len >= 1; len >>= 1) {
+        for (int32_t i = len + threadIdx.x; i < 2 * len; i += blockDim.x) t[i] = t[2 * i] + t[2 * i + 1];
+        __syncthreads();
+    }
+}
+
+// Sum of leaves lo..hi (inclusive) of a sum tree with npad leaves; all terms are >= 0.
+__device__ __forceinline__ double tree_range_sum(const double *__restrict__ t, int32_t npad, int32_t lo, int32_t hi)
+{
+    double acc = 0.0;
+    if (hi - lo < 8) {
+        for (int32_t d = lo; d <= hi; d++) acc += __ldg(t + npad + d);
+        return acc;
+    }
+    int32_t l = lo + npad, r = hi + npad + 1;
+    while (l < r) {
+        if (l & 1) acc += __ldg(t + l++);
+        if (r & 1) acc += __ldg(t + --r);
+        l >>= 1; r >>= 1;
+    }
+    return acc;
 }
 
 // D6 ---------------------------------------------------------------------------------------------
 // grp_off[w] = first block of window w (prefix over ceil(n_eval_w / EVAL_GROUP)). mode 0: sampled lattice
-// (e-th sample = min(e * srs, N-1)); mode 1: explicit list fill_list[row_off + e].
+// (e-th sample = min(e * srs, N-1)); mode 1: explicit list fill_list[row_off + e]. EVAL_LANES lanes share a point.
 __global__ void __launch_bounds__(EVAL_THREADS)
 kde_eval_kernel(const WinPlan *__restrict__ plan, int32_t n_win, const int64_t *__restrict__ grp_off, const int32_t *__restrict__ n_eval_w,
-                int mode, const int32_t *__restrict__ fill_list, const KdeParams *__restrict__ kp, const int8_t *__restrict__ state_mer,
-                const double *__restrict__ tab0, const double *__restrict__ tab1, const double *__restrict__ tab2,
+                int mode, const int32_t *__restrict__ fill_list, const KdeParams *__restrict__ kp, const int32_t *__restrict__ run_start,
+                const int32_t *__restrict__ run_len, const int8_t *__restrict__ run_state, const int32_t *__restrict__ n_runs,
+                const double *__restrict__ tree0, const double *__restrict__ tree1, const double *__restrict__ tree2,
                 double *__restrict__ k0, double *__restrict__ k1, double *__restrict__ k2)
 {
-    // window of this block
     int64_t blk = blockIdx.x;
     int32_t lo = 0, hi = n_win;
     while (hi - lo > 1) {
         int32_t mid = (lo + hi) >> 1;
         if (grp_off[mid] <= blk) lo = mid; else hi = mid;
     }
-    int32_t w = lo;
+    const int32_t w = lo;
     const WinPlan P = plan[w];
-    int32_t N = P.n_rows;
-    int32_t e0 = (int32_t)(blk - grp_off[w]) * EVAL_GROUP;
-    int32_t ne = n_eval_w[w];
-    int32_t j[EVAL_GROUP];
-#pragma unroll
-    for (int g = 0; g < EVAL_GROUP; g++) {
-        int32_t e = e0 + g;
-        if (e >= ne) j[g] = -1;
-        else if (mode == 0) { int64_t jj = (int64_t)e * P.srs; j[g] = jj > N - 1 ? N - 1 : (int32_t)jj; }
-        else j[g] = fill_list[P.row_off + e];
+    const int32_t N = P.n_rows, npad = P.npad;
+    const int sub = threadIdx.x % EVAL_LANES;
+    int32_t e = (int32_t)(blk - grp_off[w]) * EVAL_GROUP + threadIdx.x / EVAL_LANES;
+    int32_t j = -1;
+    if (e < n_eval_w[w]) {
+        if (mode == 0) { int64_t jj = (int64_t)e * P.srs; j = jj > N - 1 ? N - 1 : (int32_t)jj; }
+        else j = fill_list[P.row_off + e];
     }
-    const int8_t *sm = state_mer + P.row_off;
-    const double *t0 = tab0 + P.row_off, *t1 = tab1 + P.row_off, *t2 = tab2 + P.row_off;
-    double acc[EVAL_GROUP][3];
-#pragma unroll
-    for (int g = 0; g < EVAL_GROUP; g++) acc[g][0] = acc[g][1] = acc[g][2] = 0.0;
-    for (int32_t i = threadIdx.x; i < N; i += EVAL_THREADS) {
-        int s = sm[i];
-        const double *t = s == 0 ? t0 : (s == 1 ? t1 : t2);
-#pragma unroll
-        for (int g = 0; g < EVAL_GROUP; g++) {
-            if (j[g] >= 0) {
-                int32_t d = i - j[g];
-                d = d < 0 ? -d : d;
-                double v = __ldg(t + d);
-                acc[g][0] += (s == 0) ? v : 0.0;
-                acc[g][1] += (s == 1) ? v : 0.0;
-                acc[g][2] += (s == 2) ? v : 0.0;
+    const double *t0 = tree0 + P.tree_off, *t1 = tree1 + P.tree_off, *t2 = tree2 + P.tree_off;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (j >= 0) {
+        const int32_t nr = n_runs[w];
+        const int32_t *rs = run_start + P.row_off, *rl = run_len + P.row_off;
+        const int8_t *rst = run_state + P.row_off;
+        for (int32_t r = sub; r < nr; r += EVAL_LANES) {
+            int32_t a = __ldg(rs + r), b = a + __ldg(rl + r) - 1;
+            int s = __ldg(rst + r);
+            const double *t = s == 0 ? t0 : (s == 1 ? t1 : t2);
+            double v;
+            if (j < a) v = tree_range_sum(t, npad, a - j, b - j);
+            else if (j > b) v = tree_range_sum(t, npad, j - b, j - a);
+            else {
+                v = tree_range_sum(t, npad, 0, j - a);
+                if (b > j) v += tree_range_sum(t, npad, 1, b - j);
             }
+            a0 += (s == 0) ? v : 0.0;
+            a1 += (s == 1) ? v : 0.0;
+            a2 += (s == 2) ? v : 0.0;
         }
     }
-    __shared__ double s_red[EVAL_THREADS / 32][EVAL_GROUP][3];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int g = 0; g < EVAL_GROUP; g++)
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-            double v = acc[g][s];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-            if (lane == 0) s_red[wid][g][s] = v;
-        }
-    __syncthreads();
-    if (threadIdx.x < EVAL_GROUP * 3) {
-        int g = threadIdx.x / 3, s = threadIdx.x % 3;
-        if (j[g] >= 0) {
-            double v = 0.0;
-            for (int q = 0; q < EVAL_THREADS / 32; q++) v += s_red[q][g][s];
-            v *= kp[w].norm[s];
-            double *dst = s == 0 ? k0 : (s == 1 ? k1 : k2);
-            dst[P.row_off + j[g]] = v;
-        }
+    for (int d = 1; d < EVAL_LANES; d <<= 1) {
+        a0 += __shfl_xor_sync(FULL, a0, d);
+        a1 += __shfl_xor_sync(FULL, a1, d);
+        a2 += __shfl_xor_sync(FULL, a2, d);
+    }
+    if (j >= 0 && sub == 0) {
+        k0[P.row_off + j] = a0 * kp[w].norm[0];
+        k1[P.row_off + j] = a1 * kp[w].norm[1];
+        k2[P.row_off + j] = a2 * kp[w].norm[2];
     }
 }
 
@@ -511,7 +567,9 @@ struct pavgpu_density_batch {
     uint64_t *d_keys; uint32_t *d_counts;
     int8_t *d_st_pos; uint32_t *d_tile_cnt;
     uint64_t *d_kmer; int32_t *d_index; int8_t *d_state_mer, *d_state;
-    double *d_k[3], *d_tab[3];
+    double *d_k[3], *d_tree[3];
+    int32_t *d_run_start, *d_run_len, *d_n_runs; int8_t *d_run_state;
+    int64_t tree_total;
     uint8_t *d_gap_full; int32_t *d_fill_list, *d_n_fill, *d_n_eval; int64_t *d_grp_off;
     bool ran;
     pavgpu_density_stats stats;
@@ -528,7 +586,8 @@ static void dens_release(pavgpu_density_batch *b)
 {
     cudaFree(b->d_plan); cudaFree(b->d_wc); cudaFree(b->d_kp); cudaFree(b->d_keys); cudaFree(b->d_counts); cudaFree(b->d_st_pos);
     cudaFree(b->d_tile_cnt); cudaFree(b->d_kmer); cudaFree(b->d_index); cudaFree(b->d_state_mer); cudaFree(b->d_state);
-    for (int s = 0; s < 3; s++) { cudaFree(b->d_k[s]); cudaFree(b->d_tab[s]); }
+    for (int s = 0; s < 3; s++) { cudaFree(b->d_k[s]); cudaFree(b->d_tree[s]); }
+    cudaFree(b->d_run_start); cudaFree(b->d_run_len); cudaFree(b->d_n_runs); cudaFree(b->d_run_state);
     cudaFree(b->d_gap_full); cudaFree(b->d_fill_list); cudaFree(b->d_n_fill); cudaFree(b->d_n_eval); cudaFree(b->d_grp_off);
 }
 
@@ -582,7 +641,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     dens_release(b);
     b->d_plan = nullptr; b->d_wc = nullptr; b->d_kp = nullptr; b->d_keys = nullptr; b->d_counts = nullptr; b->d_st_pos = nullptr;
     b->d_tile_cnt = nullptr; b->d_kmer = nullptr; b->d_index = nullptr; b->d_state_mer = b->d_state = nullptr;
-    for (int s = 0; s < 3; s++) b->d_k[s] = b->d_tab[s] = nullptr;
+    for (int s = 0; s < 3; s++) b->d_k[s] = b->d_tree[s] = nullptr;
+    b->d_run_start = b->d_run_len = b->d_n_runs = nullptr; b->d_run_state = nullptr;
     b->d_gap_full = nullptr; b->d_fill_list = b->d_n_fill = b->d_n_eval = nullptr; b->d_grp_off = nullptr;
     memset(&b->stats, 0, sizeof b->stats);
     b->ran = false;
@@ -650,7 +710,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaStreamSynchronize(st));
 
     // ---- plan, part 2 (host): status, keep mask, N, dense row offsets, sample counts
-    int64_t rows = 0;
+    int64_t rows = 0, tree_total = 0;
     int32_t max_rows = 1;
     std::vector<int64_t> grp_off(n_win + 1, 0);
     std::vector<int32_t> n_eval(n_win, 0);
@@ -671,9 +731,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         P.row_off = rows;
         rows += P.n_rows;
         max_rows = std::max(max_rows, P.n_rows);
-        P.n_samp = 0;
+        P.n_samp = 0; P.npad = 0; P.tree_off = tree_total;
         if (P.smoothed) {
             int32_t N = P.n_rows;
+            P.npad = 1 << log2_ceil(N);
+            tree_total += 2 * (int64_t)P.npad;
             P.n_samp = (N - 1) / P.srs + 1 + (((N - 1) % P.srs) ? 1 : 0);  // density.py:211-214
         }
         n_eval[w] = P.n_samp;
@@ -685,7 +747,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     size_t rcap = (size_t)std::max<int64_t>(rows, 1);
     CUDA_TRY(cudaMalloc(&b->d_kmer, rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_index, rcap * 4));
     CUDA_TRY(cudaMalloc(&b->d_state_mer, rcap)); CUDA_TRY(cudaMalloc(&b->d_state, rcap));
-    for (int s = 0; s < 3; s++) { CUDA_TRY(cudaMalloc(&b->d_k[s], rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_tab[s], rcap * 8)); }
+    b->tree_total = tree_total;
+    for (int s = 0; s < 3; s++) { CUDA_TRY(cudaMalloc(&b->d_k[s], rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_tree[s], (size_t)std::max<int64_t>(tree_total, 1) * 8)); }
+    CUDA_TRY(cudaMalloc(&b->d_run_start, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_len, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_state, rcap));
+    CUDA_TRY(cudaMalloc(&b->d_n_runs, sizeof(int32_t) * n_win));
     CUDA_TRY(cudaMalloc(&b->d_gap_full, rcap)); CUDA_TRY(cudaMalloc(&b->d_fill_list, rcap * 4));
     CUDA_TRY(cudaMalloc(&b->d_n_fill, sizeof(int32_t) * n_win)); CUDA_TRY(cudaMalloc(&b->d_n_eval, sizeof(int32_t) * n_win));
     CUDA_TRY(cudaMalloc(&b->d_grp_off, sizeof(int64_t) * (n_win + 1)));
@@ -704,17 +769,15 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     kde_prepare_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state_mer, b->prm.smooth, b->d_kp);
     launches++;
-    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
-        int32_t ny = std::min(YMAX, n_win - w0);
-        kde_table_kernel<<<dim3(row_blocks, ny), 256, 0, st>>>(b->d_plan, w0, b->d_kp, b->d_tab[0], b->d_tab[1], b->d_tab[2]);
-        launches++;
-    }
+    runs_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state_mer, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs);
+    kde_tree_kernel<<<n_win * 3, TREE_THREADS, 0, st>>>(b->d_plan, b->d_kp, b->d_tree[0], b->d_tree[1], b->d_tree[2]);
+    launches += 2;
     CUDA_TRY(cudaGetLastError());
     int64_t pairs = 0;
     if (grp_off[n_win] > 0) {
         kde_eval_kernel<<<(unsigned)grp_off[n_win], EVAL_THREADS, 0, st>>>(b->d_plan, n_win, b->d_grp_off, b->d_n_eval, 0, nullptr, b->d_kp,
-                                                                           b->d_state_mer, b->d_tab[0], b->d_tab[1], b->d_tab[2], b->d_k[0],
-                                                                           b->d_k[1], b->d_k[2]);
+                                                                           b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs, b->d_tree[0],
+                                                                           b->d_tree[1], b->d_tree[2], b->d_k[0], b->d_k[1], b->d_k[2]);
         launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -734,8 +797,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     if (grp_off[n_win] > 0) {
         CUDA_TRY(cudaMemcpyAsync(b->d_grp_off, grp_off.data(), sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, st));
         kde_eval_kernel<<<(unsigned)grp_off[n_win], EVAL_THREADS, 0, st>>>(b->d_plan, n_win, b->d_grp_off, b->d_n_fill, 1, b->d_fill_list,
-                                                                           b->d_kp, b->d_state_mer, b->d_tab[0], b->d_tab[1], b->d_tab[2],
-                                                                           b->d_k[0], b->d_k[1], b->d_k[2]);
+                                                                           b->d_kp, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs,
+                                                                           b->d_tree[0], b->d_tree[1], b->d_tree[2], b->d_k[0], b->d_k[1], b->d_k[2]);
         launches++;
         CUDA_TRY(cudaGetLastError());
     }

@@ -4,18 +4,30 @@
  * part of make_insdel_snv_calls that cannot leave the interpreter. Replaces per-row f-strings
  * (reference: pavlib/cigarcall.py:112,121,185,198,254,267 build the same strings one pd.Series at a time).
  *
- *   format(n, parts)  -> list[str]   parts = sequence of ('s', str) | ('i', int64 buffer) |
+ *   format(n, parts)  -> object ndarray of str   parts = sequence of ('s', str) | ('i', int64 buffer) |
  *                                            ('l', list[str], int64 index buffer) | ('c', uint8 buffer)
- *   ints(int64 buffer) -> list[int]
+ *   ints(int64 buffer) -> object ndarray of int
  *   slices(data uint8 buffer list, which int64 buffer, start int64 buffer, length int64 buffer,
- *          rc uint8 buffer, comp bytes[256]) -> list[str]   (reverse-complemented through comp when rc[i])
+ *          rc uint8 buffer, comp bytes[256]) -> object ndarray of str   (reverse-complemented through comp when rc[i])
  *
  * Host-only; no CUDA here. Built in-tree by pav_b200/build.py with gcc.
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#include <numpy/arrayobject.h>
 #include <stdint.h>
 #include <string.h>
+
+/* Results are 1-D numpy object arrays filled in place (no intermediate list, no type inference). */
+static PyObject *new_obj_array(Py_ssize_t n, PyObject ***data)
+{
+    npy_intp dims[1] = {(npy_intp)n};
+    PyObject *arr = PyArray_SimpleNew(1, dims, NPY_OBJECT);   /* object arrays come back NULL-filled */
+    if (!arr) return NULL;
+    *data = (PyObject **)PyArray_DATA((PyArrayObject *)arr);
+    return arr;
+}
 
 enum { P_LIT, P_INT, P_LUT, P_CHR };
 
@@ -95,7 +107,8 @@ static PyObject *py_format(PyObject *self, PyObject *args)
     }
     {
         char *scratch = (char *)PyMem_Malloc((size_t)max_len + 8);
-        PyObject *out = PyList_New(n);
+        PyObject **slots = NULL;
+        PyObject *out = new_obj_array(n, &slots);
         if (!scratch || !out) { PyMem_Free(scratch); Py_XDECREF(out); PyErr_NoMemory(); goto fail; }
         for (Py_ssize_t r = 0; r < n; r++) {
             char *d = scratch;
@@ -114,7 +127,7 @@ static PyObject *py_format(PyObject *self, PyObject *args)
             }
             PyObject *s = PyUnicode_DecodeUTF8(scratch, d - scratch, NULL);
             if (!s) { PyMem_Free(scratch); Py_DECREF(out); goto fail; }
-            PyList_SET_ITEM(out, r, s);
+            slots[r] = s;
         }
         PyMem_Free(scratch);
         parts_free(parts, np_);
@@ -132,13 +145,14 @@ static PyObject *py_ints(PyObject *self, PyObject *arg)
     Py_buffer b;
     if (PyObject_GetBuffer(arg, &b, PyBUF_SIMPLE) < 0) return NULL;
     Py_ssize_t n = b.len / 8;
-    PyObject *out = PyList_New(n);
+    PyObject **slots = NULL;
+    PyObject *out = new_obj_array(n, &slots);
     if (out) {
         const int64_t *v = (const int64_t *)b.buf;
         for (Py_ssize_t i = 0; i < n; i++) {
             PyObject *o = PyLong_FromLongLong(v[i]);
             if (!o) { Py_DECREF(out); out = NULL; break; }
-            PyList_SET_ITEM(out, i, o);
+            slots[i] = o;
         }
     }
     PyBuffer_Release(&b);
@@ -150,6 +164,7 @@ static PyObject *py_slices(PyObject *self, PyObject *args)
     PyObject *data_list; Py_buffer which, start, length, rc, comp;
     if (!PyArg_ParseTuple(args, "O!y*y*y*y*y*", &PyList_Type, &data_list, &which, &start, &length, &rc, &comp)) return NULL;
     PyObject *out = NULL;
+    PyObject **slots = NULL;
     Py_ssize_t n = which.len / 8, nd = PyList_GET_SIZE(data_list);
     Py_buffer *bufs = (Py_buffer *)PyMem_Calloc((size_t)nd + 1, sizeof(Py_buffer));
     Py_ssize_t got = 0;
@@ -158,7 +173,7 @@ static PyObject *py_slices(PyObject *self, PyObject *args)
     if (start.len < n * 8 || length.len < n * 8 || rc.len < n || comp.len < 256) { PyErr_SetString(PyExc_ValueError, "slices: bad buffer sizes"); goto done; }
     for (; got < nd; got++)
         if (PyObject_GetBuffer(PyList_GET_ITEM(data_list, got), &bufs[got], PyBUF_SIMPLE) < 0) goto done;
-    out = PyList_New(n);
+    out = new_obj_array(n, &slots);
     if (!out) goto done;
     for (Py_ssize_t i = 0; i < n; i++) {
         int64_t w = ((const int64_t *)which.buf)[i], s = ((const int64_t *)start.buf)[i], l = ((const int64_t *)length.buf)[i];
@@ -174,7 +189,7 @@ static PyObject *py_slices(PyObject *self, PyObject *args)
             o = PyUnicode_DecodeLatin1((const char *)src, l, NULL);
         }
         if (!o) { Py_CLEAR(out); goto done; }
-        PyList_SET_ITEM(out, i, o);
+        slots[i] = o;
     }
 done:
     PyMem_Free(scratch);
@@ -192,4 +207,8 @@ static PyMethodDef methods[] = {
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_pyrows", "row formatting helpers", -1, methods};
 
-PyMODINIT_FUNC PyInit__pyrows(void) { return PyModule_Create(&moddef); }
+PyMODINIT_FUNC PyInit__pyrows(void)
+{
+    import_array();
+    return PyModule_Create(&moddef);
+}

@@ -6,6 +6,8 @@ arguments, return value ``(df_snv, df_insdel)``, column order, dtypes (all ``obj
 Python loop of the reference (:50-311) is replaced by one ``pavgpu_cigar_call``; this module only
 moves bytes in (FASTA -> HBM, CIGAR text -> packed ops) and formats the rows that come back.
 """
+import time
+
 import numpy as np
 import pandas as pd
 
@@ -25,6 +27,7 @@ _OP_CHAR = 'MIDNSHP=X'
 
 # statistics of the last call (device timings etc.), for bench.py
 last_stats = None
+last_phase_seconds = None   # host-side phase breakdown of the last make_insdel_snv_calls
 
 
 def _first_seen(values):
@@ -142,16 +145,22 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
 
     :return: ``(df_snv, df_insdel)`` -- the order the reference actually returns (pavlib/cigarcall.py:362).
     """
+    global last_phase_seconds
     if df_align.shape[0] == 0:
         return _empty(SNV_COLUMNS), _empty(INSDEL_COLUMNS)
+    t0 = time.perf_counter()
     table = AlignTable(df_align)
     ref_fa = fasta.open_fasta(ref_fa_name)
     tig_fa = fasta.open_fasta(tig_fa_name)
     ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
     tig_arr = [tig_fa.fetch_array(nm) for nm in table.tig_names]
+    t1 = time.perf_counter()
     snv, indel = walk_rows(table, ref_arr, tig_arr)
-    return build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
-                        table.qry_id, hap, version_id)
+    t2 = time.perf_counter()
+    frames = build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
+                          table.qry_id, hap, version_id)
+    last_phase_seconds = {'fasta': t1 - t0, 'device_walk_incl_h2d_d2h': t2 - t1, 'frames': time.perf_counter() - t2}
+    return frames
 
 
 def _obj(values):
@@ -183,6 +192,17 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
     DataFrames of the reference. Host-side string formatting only (pav_b200/csrc/pyrows.c); every coordinate
     comes from the GPU. IDs are formatted in emission order (version_id and the sort's tie-break need them),
     every other column directly in the final row order."""
+    import gc
+    gc_was_on = gc.isenabled()
+    gc.disable()   # tens of millions of str / int objects are created below; none of them can form cycles
+    try:
+        return _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id)
+    finally:
+        if gc_was_on:
+            gc.enable()
+
+
+def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id):
     from .. import _pyrows
     n_rec = len(chrom)
     chrom_l = [f'{c}' for c in chrom.tolist()]
@@ -208,12 +228,12 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
         ids = _pyrows.format(n, [('l', chrom_l, rec), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
                                  ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
         if version_id:
-            ids = variant.version_id(pd.Series(_obj(ids), dtype=object)).tolist()
+            ids = variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object)
         order = _sort_order(chrom_code_rec[rec], pos, pos + 1, ids)
         rec, pos, qp, ref_b, alt_b = rec[order], pos[order], qp[order], ref_b[order], alt_b[order]
         pos1, qp1 = pos + 1, qp + 1
         cols = {
-            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(pos1), 'ID': _obj(ids)[order],
+            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(pos1), 'ID': ids[order],
             'SVTYPE': 'SNV', 'SVLEN': 1, 'REF': _CHR[ref_b], 'ALT': _CHR[alt_b], 'HAP': hap,
             'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec), ('s', ':'), ('i', qp1), ('s', '-'), ('i', qp1)]),
             'QRY_STRAND': strand_rec[rec], 'CI': 0, 'ALIGN_INDEX': align_index[rec], 'CALL_SOURCE': CALL_SOURCE,
@@ -233,7 +253,7 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
         svt = (indel['svtype'] == 1).astype(np.int64)
         ids = _pyrows.format(n, [('l', chrom_l, rec), ('s', '-'), ('i', pos + 1), ('s', '-'), ('l', svtype_l, svt), ('s', '-'), ('i', svlen)])
         if version_id:
-            ids = variant.version_id(pd.Series(_obj(ids), dtype=object)).tolist()
+            ids = variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object)
         order = _sort_order(chrom_code_rec[rec], pos, end, ids)
         indel = indel[order]
         rec, pos, end, svlen, svt = rec[order], pos[order], end[order], svlen[order], svt[order]
@@ -247,7 +267,7 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
         start = np.where(is_del, pos, qp)
         rc = (~is_del & rev[rec]).astype(np.uint8)
         cols = {
-            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(end), 'ID': _obj(ids)[order],
+            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(end), 'ID': ids[order],
             'SVTYPE': np.array(svtype_l, dtype=object)[svt], 'SVLEN': _pyrows.ints(svlen), 'HAP': hap,
             'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec), ('s', ':'), ('i', qp + 1), ('s', '-'), ('i', np.where(is_del, qp + 1, qe))]),
             'QRY_STRAND': strand_rec[rec], 'CI': 0, 'ALIGN_INDEX': align_index[rec],
