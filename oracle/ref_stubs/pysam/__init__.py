@@ -63,3 +63,67 @@ class FastaFile:
 class AlignmentFile:  # import-time placeholder only
     def __init__(self, *a, **k):
         raise NotImplementedError('pysam stub: AlignmentFile is not available')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Minimal SAM-text reader with the record attributes pavlib.align.get_align_bed uses
+# (pavlib/align/align.py:687-770). Attribute semantics follow the pysam documentation:
+#   reference_start  0-based leftmost coordinate            reference_end   start + bases consumed on the reference (M D N = X)
+#   query_alignment_start  index of the first aligned base in the stored SEQ (= leading soft clip; hard clips are not stored)
+#   query_alignment_end    one past the last aligned base in the stored SEQ (= start + M I = X bases)
+#   cigartuples  [(op code, length)] with BAM codes M0 I1 D2 N3 S4 H5 P6 =7 X8
+# ---------------------------------------------------------------------------------------------------------
+_CIGAR_CODE = {c: i for i, c in enumerate('MIDNSHP=X')}
+
+
+class AlignedSegment:
+    def __init__(self, line):
+        import re
+        tok = line.rstrip('\n').split('\t')
+        self.query_name = tok[0]
+        self.flag = int(tok[1])
+        self.reference_name = tok[2]
+        self.reference_start = int(tok[3]) - 1
+        self.mapping_quality = int(tok[4])
+        cig = tok[5]
+        self.cigartuples = [] if cig == '*' else [(_CIGAR_CODE[o], int(n)) for n, o in re.findall(r'(\d+)([MIDNSHP=X])', cig)]
+        self.cigar = self.cigartuples
+        self.is_unmapped = bool(self.flag & 0x4)
+        self.is_reverse = bool(self.flag & 0x10)
+        ref_bp = sum(n for o, n in self.cigartuples if o in (0, 2, 3, 7, 8))
+        self.reference_end = self.reference_start + ref_bp
+        lead_s = 0
+        for o, n in self.cigartuples:
+            if o == 5:
+                continue
+            if o == 4:
+                lead_s += n
+            break
+        self.query_alignment_start = lead_s
+        self.query_alignment_end = lead_s + sum(n for o, n in self.cigartuples if o in (0, 1, 7, 8))
+        self._tags = []
+        for t in tok[11:]:
+            k, ty, v = t.split(':', 2)
+            self._tags.append((k, int(v) if ty == 'i' else (float(v) if ty == 'f' else v)))
+
+    def get_tags(self):
+        return list(self._tags)
+
+
+class AlignmentFile:  # noqa: F811  (replaces the import-time placeholder above)
+    def __init__(self, filename, mode='r', **kw):
+        opener = gzip.open if str(filename).endswith('.gz') else open
+        self._fh = opener(filename, 'rt')
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self._fh.close()
+        return False
+
+    def __iter__(self):
+        for line in self._fh:
+            if line.startswith('@') or not line.strip():
+                continue
+            yield AlignedSegment(line)

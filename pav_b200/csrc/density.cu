@@ -293,7 +293,7 @@ kde_prepare_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ 
 
 // D5 ---------------------------------------------------------------------------------------------
 // One block per window: maximal runs of equal STATE_MER, in order, at run_start/run_len/run_state[row_off + r].
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_mer, int32_t *__restrict__ run_start,
             int32_t *__restrict__ run_len, int8_t *__restrict__ run_state, int32_t *__restrict__ n_runs)
 {
@@ -301,29 +301,27 @@ runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_m
     const WinPlan P = plan[w];
     if (!P.smoothed) { if (threadIdx.x == 0) n_runs[w] = 0; return; }
     const int8_t *sm = state_mer + P.row_off;
-    int32_t N = P.n_rows;
-    __shared__ int s_scan[256];
+    const int32_t N = P.n_rows;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ int s_warp[32];
     __shared__ int s_base;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
-    for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {
+    for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {   // order-preserving compaction of run heads, 1024 rows per step
         int32_t i = i0 + threadIdx.x;
-        int head = (i < N) && (i == 0 || sm[i] != sm[i - 1]);
-        s_scan[threadIdx.x] = head;
+        bool head = (i < N) && (i == 0 || sm[i] != sm[i - 1]);
+        unsigned bal = __ballot_sync(FULL, head);
+        if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
-        for (int d = 1; d < (int)blockDim.x; d <<= 1) {
-            int v = (threadIdx.x >= (unsigned)d) ? s_scan[threadIdx.x - d] : 0;
-            __syncthreads();
-            s_scan[threadIdx.x] += v;
-            __syncthreads();
-        }
+        int before = 0, total = 0;
+        for (int q = 0; q < 32; q++) { int c = s_warp[q]; if (q < wid) before += c; total += c; }
         if (head) {
-            int32_t r = s_base + s_scan[threadIdx.x] - 1;
+            int32_t r = s_base + before + __popc(bal & ((1u << lane) - 1));
             run_start[P.row_off + r] = i;
             run_state[P.row_off + r] = sm[i];
         }
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_base += s_scan[threadIdx.x];
+        if (threadIdx.x == 0) s_base += total;
         __syncthreads();
     }
     int32_t nr = s_base;
@@ -572,6 +570,7 @@ struct pavgpu_density_batch {
     int64_t tree_total;
     uint8_t *d_gap_full; int32_t *d_fill_list, *d_n_fill, *d_n_eval; int64_t *d_grp_off;
     bool ran;
+    bool allocated;   // device buffers live for the lifetime of the batch (sized from upper bounds on the first run)
     pavgpu_density_stats stats;
 };
 
@@ -638,18 +637,12 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     cudaStream_t st = ctx->stream;
     const int k = b->prm.k;
     const int32_t n_win = b->n_win;
-    dens_release(b);
-    b->d_plan = nullptr; b->d_wc = nullptr; b->d_kp = nullptr; b->d_keys = nullptr; b->d_counts = nullptr; b->d_st_pos = nullptr;
-    b->d_tile_cnt = nullptr; b->d_kmer = nullptr; b->d_index = nullptr; b->d_state_mer = b->d_state = nullptr;
-    for (int s = 0; s < 3; s++) b->d_k[s] = b->d_tree[s] = nullptr;
-    b->d_run_start = b->d_run_len = b->d_n_runs = nullptr; b->d_run_state = nullptr;
-    b->d_gap_full = nullptr; b->d_fill_list = b->d_n_fill = b->d_n_eval = nullptr; b->d_grp_off = nullptr;
     memset(&b->stats, 0, sizeof b->stats);
     b->ran = false;
     if (n_win == 0) { b->ran = true; b->rows_total = 0; if (stats) *stats = b->stats; return PAVGPU_OK; }
 
     // ---- plan, part 1 (host)
-    int64_t tab = 0, pos = 0, tiles = 0, bases = 0;
+    int64_t tab = 0, pos = 0, tiles = 0, bases = 0, tree_cap = 0;
     int32_t max_ref_blocks = 1, max_tig_tiles = 1;
     for (int32_t w = 0; w < n_win; w++) {
         const pavgpu_density_window &W = b->win[w];
@@ -673,24 +666,41 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         max_ref_blocks = std::max(max_ref_blocks, (n_ref + 255) / 256);
         max_tig_tiles = std::max(max_tig_tiles, (n_tig + TILE - 1) / TILE);
         bases += P.tig_len;
+        P.tree_off = tree_cap;                                   // upper bound: N <= n_tig
+        tree_cap += 2 * ((int64_t)1 << log2_ceil(std::max(n_tig, 1)));
     }
-    b->tab_slots = tab; b->pos_total = pos; b->tile_total = tiles;
+    b->tab_slots = tab; b->pos_total = pos; b->tile_total = tiles; b->tree_total = tree_cap;
     b->stats.bases = bases;
 
     int launches = 0;
+    if (!b->allocated) {   // everything is sized from upper bounds (rows <= contig k-mer positions), so runs never allocate
+        size_t rcap = (size_t)std::max<int64_t>(pos, 1);
+        CUDA_TRY(cudaMalloc(&b->d_plan, sizeof(WinPlan) * n_win));
+        CUDA_TRY(cudaMalloc(&b->d_wc, sizeof(WinCounts) * n_win));
+        CUDA_TRY(cudaMalloc(&b->d_kp, sizeof(KdeParams) * n_win));
+        CUDA_TRY(cudaMalloc(&b->d_keys, sizeof(uint64_t) * std::max<int64_t>(tab, 1)));
+        CUDA_TRY(cudaMalloc(&b->d_counts, sizeof(uint32_t) * std::max<int64_t>(tab, 1)));
+        CUDA_TRY(cudaMalloc(&b->d_st_pos, std::max<int64_t>(pos, 1)));
+        CUDA_TRY(cudaMalloc(&b->d_tile_cnt, sizeof(uint32_t) * 3 * std::max<int64_t>(tiles, 1)));
+        CUDA_TRY(cudaMalloc(&b->d_kmer, rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_index, rcap * 4));
+        CUDA_TRY(cudaMalloc(&b->d_state_mer, rcap)); CUDA_TRY(cudaMalloc(&b->d_state, rcap));
+        for (int s = 0; s < 3; s++) {
+            CUDA_TRY(cudaMalloc(&b->d_k[s], rcap * 8));
+            CUDA_TRY(cudaMalloc(&b->d_tree[s], (size_t)std::max<int64_t>(tree_cap, 1) * 8));
+        }
+        CUDA_TRY(cudaMalloc(&b->d_run_start, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_len, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_state, rcap));
+        CUDA_TRY(cudaMalloc(&b->d_n_runs, sizeof(int32_t) * n_win));
+        CUDA_TRY(cudaMalloc(&b->d_gap_full, rcap)); CUDA_TRY(cudaMalloc(&b->d_fill_list, rcap * 4));
+        CUDA_TRY(cudaMalloc(&b->d_n_fill, sizeof(int32_t) * n_win)); CUDA_TRY(cudaMalloc(&b->d_n_eval, sizeof(int32_t) * n_win));
+        CUDA_TRY(cudaMalloc(&b->d_grp_off, sizeof(int64_t) * (n_win + 1)));
+        b->allocated = true;
+    }
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
-    CUDA_TRY(cudaMalloc(&b->d_plan, sizeof(WinPlan) * n_win));
-    CUDA_TRY(cudaMalloc(&b->d_wc, sizeof(WinCounts) * n_win));
-    CUDA_TRY(cudaMalloc(&b->d_kp, sizeof(KdeParams) * n_win));
-    CUDA_TRY(cudaMalloc(&b->d_keys, sizeof(uint64_t) * std::max<int64_t>(tab, 1)));
-    CUDA_TRY(cudaMalloc(&b->d_counts, sizeof(uint32_t) * std::max<int64_t>(tab, 1)));
-    CUDA_TRY(cudaMalloc(&b->d_st_pos, std::max<int64_t>(pos, 1)));
-    CUDA_TRY(cudaMalloc(&b->d_tile_cnt, sizeof(uint32_t) * 3 * std::max<int64_t>(tiles, 1)));
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], st));   // the table initialisation below is part of the step
     CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_wc, 0, sizeof(WinCounts) * n_win, st));
     CUDA_TRY(cudaMemsetAsync(b->d_keys, 0xFF, sizeof(uint64_t) * std::max<int64_t>(tab, 1), st));
     CUDA_TRY(cudaMemsetAsync(b->d_counts, 0, sizeof(uint32_t) * std::max<int64_t>(tab, 1), st));
-    CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
 
     const int32_t YMAX = 32768;
     for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
@@ -710,7 +720,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaStreamSynchronize(st));
 
     // ---- plan, part 2 (host): status, keep mask, N, dense row offsets, sample counts
-    int64_t rows = 0, tree_total = 0;
+    int64_t rows = 0;
     int32_t max_rows = 1;
     std::vector<int64_t> grp_off(n_win + 1, 0);
     std::vector<int32_t> n_eval(n_win, 0);
@@ -731,11 +741,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         P.row_off = rows;
         rows += P.n_rows;
         max_rows = std::max(max_rows, P.n_rows);
-        P.n_samp = 0; P.npad = 0; P.tree_off = tree_total;
+        P.n_samp = 0; P.npad = 0;
         if (P.smoothed) {
             int32_t N = P.n_rows;
-            P.npad = 1 << log2_ceil(N);
-            tree_total += 2 * (int64_t)P.npad;
+            P.npad = 1 << log2_ceil(N);   // <= the capacity reserved at tree_off
             P.n_samp = (N - 1) / P.srs + 1 + (((N - 1) % P.srs) ? 1 : 0);  // density.py:211-214
         }
         n_eval[w] = P.n_samp;
@@ -744,16 +753,6 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     }
     b->rows_total = rows;
     b->stats.rows = rows;
-    size_t rcap = (size_t)std::max<int64_t>(rows, 1);
-    CUDA_TRY(cudaMalloc(&b->d_kmer, rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_index, rcap * 4));
-    CUDA_TRY(cudaMalloc(&b->d_state_mer, rcap)); CUDA_TRY(cudaMalloc(&b->d_state, rcap));
-    b->tree_total = tree_total;
-    for (int s = 0; s < 3; s++) { CUDA_TRY(cudaMalloc(&b->d_k[s], rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_tree[s], (size_t)std::max<int64_t>(tree_total, 1) * 8)); }
-    CUDA_TRY(cudaMalloc(&b->d_run_start, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_len, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_state, rcap));
-    CUDA_TRY(cudaMalloc(&b->d_n_runs, sizeof(int32_t) * n_win));
-    CUDA_TRY(cudaMalloc(&b->d_gap_full, rcap)); CUDA_TRY(cudaMalloc(&b->d_fill_list, rcap * 4));
-    CUDA_TRY(cudaMalloc(&b->d_n_fill, sizeof(int32_t) * n_win)); CUDA_TRY(cudaMalloc(&b->d_n_eval, sizeof(int32_t) * n_win));
-    CUDA_TRY(cudaMalloc(&b->d_grp_off, sizeof(int64_t) * (n_win + 1)));
     CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_n_eval, n_eval.data(), sizeof(int32_t) * n_win, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_grp_off, grp_off.data(), sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, st));
@@ -769,7 +768,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     kde_prepare_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state_mer, b->prm.smooth, b->d_kp);
     launches++;
-    runs_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state_mer, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs);
+    runs_kernel<<<n_win, 1024, 0, st>>>(b->d_plan, b->d_state_mer, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs);
     kde_tree_kernel<<<n_win * 3, TREE_THREADS, 0, st>>>(b->d_plan, b->d_kp, b->d_tree[0], b->d_tree[1], b->d_tree[2]);
     launches += 2;
     CUDA_TRY(cudaGetLastError());

@@ -1,9 +1,17 @@
-"""CIGAR tokenizer with the reference's interface and error text (pavlib/align/align.py:286-322).
+"""Alignment-table helpers with the reference's interface and error text (pavlib/align/align.py).
 
-The hot path does not call this generator (records are tokenised in bulk by
-``pavgpu_cigar_parse``); it exists because other PAV code imports it from ``pavlib.align``.
+* ``cigar_str_to_tuples`` (:286-322): the hot path does not call this generator (records are tokenised in bulk
+  by ``pavgpu_cigar_parse``); it exists because other PAV code imports it from ``pavlib.align``.
+* ``get_align_bed`` (:666-794), ``count_cigar`` (:534-663), ``check_record`` (:364-508), ``clip_soft_to_hard``
+  (:797-831): SAM text -> the alignment table that feeds ``make_insdel_snv_calls``, without
+  pysam/htslib. Per-record span counting reuses the bulk tokenizer of libpavgpu (host C) and numpy reductions.
 """
+import gzip
+
+import numpy as np
 import pandas as pd
+
+from .lift import AlignLift  # noqa: F401  (reference: pavlib/align/__init__.py re-exports lift)
 
 _DIGITS = frozenset('0123456789')
 _OPS = frozenset('MIDNSHP=X')
@@ -25,3 +33,185 @@ def cigar_str_to_tuples(record):
                 record['QRY_ID'], record['#CHROM'], record['POS'], cigar[pos]))
         yield int(cigar[pos:end]), cigar[end]
         pos = end + 1
+
+
+CIGAR_M, CIGAR_I, CIGAR_D, CIGAR_N, CIGAR_S, CIGAR_H, CIGAR_P, CIGAR_EQ, CIGAR_X = range(9)
+CIGAR_CODE_TO_CHAR = dict(enumerate('MIDNSHP=X'))
+ALIGN_COLUMNS = ['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END', 'QRY_LEN', 'RG', 'AO', 'MAPQ', 'REV', 'FLAGS',
+                 'HAP', 'CIGAR']
+
+
+def count_cigar(row, allow_m=False):
+    """``(ref_bp, tig_bp, clip_h_l, clip_s_l, clip_h_r, clip_s_r)`` of an alignment record; same structural checks and
+    messages as the reference (clips only at the ends, H outside S, no M unless ``allow_m``)."""
+    ref_bp = tig_bp = clip_s_l = clip_h_l = clip_s_r = clip_h_r = 0
+    ops = list(cigar_str_to_tuples(row))
+    n, i = len(ops), 0
+    while i < n and ops[i][1] in {'S', 'H'}:
+        ln, op = ops[i]
+        if op == 'S':
+            if clip_s_l > 0:
+                raise RuntimeError('Duplicate S records (left) at index {}'.format(i))
+            clip_s_l = ln
+        if op == 'H':
+            if clip_h_l > 0:
+                raise RuntimeError('Duplicate H records (left) at index {}'.format(i))
+            if clip_s_l > 0:
+                raise RuntimeError('S record before H (left) at index {}'.format(i))
+            clip_h_l = ln
+        i += 1
+    while i < n:
+        ln, op = ops[i]
+        if op in {'=', 'X', 'I', 'D'} or op == 'M':
+            if op == 'M' and not allow_m:
+                raise RuntimeError('CIGAR op "M" is not allowed')
+            if clip_s_r > 0 or clip_h_r > 0:
+                raise RuntimeError('Found clipped bases before last non-clipped CIGAR operation at operation {} ({}{})'.format(i, ln, op))
+            if op != 'I':
+                ref_bp += ln
+            if op != 'D':
+                tig_bp += ln
+        elif op == 'S':
+            if clip_s_r > 0:
+                raise RuntimeError('Duplicate S records (right) at operation {}'.format(i))
+            if clip_h_r > 0:
+                raise RuntimeError('H record before S record (right) at operation {}'.format(i))
+            clip_s_r = ln
+        elif op == 'H':
+            if clip_h_r > 0:
+                raise RuntimeError('Duplicate H records (right) at operation {}'.format(i))
+            clip_h_r = ln
+        else:
+            raise RuntimeError('Bad CIGAR op: ' + op)
+        i += 1
+    return ref_bp, tig_bp, clip_h_l, clip_s_l, clip_h_r, clip_s_r
+
+
+def _where(row):
+    return '(INDEX={}, QRY={}:{}-{}, REF={}:{}-{})'.format(row['INDEX'], row['QRY_ID'], row['QRY_POS'], row['QRY_END'], row['#CHROM'],
+                                                            row['POS'], row['END'])
+
+
+def check_record(row, df_tig_fai):
+    """Sanity checks of one alignment-table record (reference: pavlib/align/align.py:364-508); raises ``RuntimeError``."""
+    try:
+        ref_bp, tig_bp, _, _, _, _ = count_cigar(row)
+    except Exception as ex:
+        raise RuntimeError('CIGAR parsing error: {} {}'.format(ex, _where(row)))
+    tig_len = df_tig_fai[row['QRY_ID']]
+    if row['QRY_LEN'] != tig_len:
+        raise RuntimeError('QRY_LEN != length from FAI ({} != {}) {}'.format(row['QRY_LEN'], tig_len, _where(row)))
+    if row['QRY_POS'] >= row['QRY_END']:
+        raise RuntimeError('QRY_POS >= QRY_END ({} >= {}) {}'.format(row['QRY_POS'], row['QRY_END'], _where(row)))
+    if row['POS'] >= row['END']:
+        raise RuntimeError('POS >= END ({} >= {}) {}'.format(row['POS'], row['END'], _where(row)))
+    if row['POS'] < 0:
+        raise RuntimeError('POS ({}) < 0 {}'.format(row['POS'], _where(row)))
+    if row['QRY_POS'] < 0:
+        raise RuntimeError('QRY_POS ({}) < 0 {}'.format(row['QRY_POS'], _where(row)))
+    if row['POS'] + ref_bp != row['END']:
+        raise RuntimeError('END mismatch: POS + ref_bp != END ({} != {}) {}'.format(row['POS'] + ref_bp, row['END'], _where(row)))
+    if row['QRY_POS'] + tig_bp != row['QRY_END']:
+        raise RuntimeError('QRY_POS + tig_bp != QRY_END: {} != {} {}'.format(row['QRY_POS'] + tig_bp, row['QRY_END'], _where(row)))
+    if row['QRY_END'] > tig_len:
+        raise RuntimeError('QRY_END > tig_len ({} > {}) {}'.format(row['QRY_END'], tig_len, _where(row)))
+
+
+def clip_soft_to_hard(cigar_tuples):
+    """Merge leading / trailing S and H ops of ``[(op code, length)]`` into single H ops (reference: :797-831)."""
+    front_n = 0
+    while len(cigar_tuples) > 0 and cigar_tuples[0][0] in {CIGAR_H, CIGAR_S}:
+        front_n += cigar_tuples[0][1]
+        cigar_tuples = cigar_tuples[1:]
+    back_n = 0
+    while len(cigar_tuples) > 0 and cigar_tuples[-1][0] in {CIGAR_H, CIGAR_S}:
+        back_n += cigar_tuples[-1][1]
+        cigar_tuples = cigar_tuples[:-1]
+    if len(cigar_tuples) == 0:
+        if front_n + back_n == 0:
+            raise RuntimeError('Cannot convert soft clipping to hard: No CIGAR records')
+        return [(front_n + back_n, CIGAR_H)]   # (sic) the reference swaps the tuple order in this corner
+    if front_n > 0:
+        cigar_tuples = [(CIGAR_H, front_n)] + cigar_tuples
+    if back_n > 0:
+        cigar_tuples = cigar_tuples + [(CIGAR_H, back_n)]
+    return cigar_tuples
+
+
+def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
+    """
+    Read a SAM text file (plain or gzip) as the alignment table PAV processes (reference: pavlib/align/align.py:666-794,
+    which reads SAM/BAM/CRAM through pysam). Unmapped records, records below ``min_mapq`` and records without a CIGAR are
+    dropped; soft clips become hard clips; ``M`` operations are rejected; the table is sorted by
+    ``#CHROM, POS, END (descending), QRY_ID`` and every record is sanity-checked.
+    """
+    from .. import device
+    recs = []
+    opener = gzip.open if str(align_file).endswith('.gz') else open
+    align_index = -1
+    with opener(align_file, 'rt') as fh:
+        for line in fh:
+            if line.startswith('@') or not line.strip():
+                continue
+            align_index += 1
+            tok = line.rstrip('\n').split('\t')
+            flag, mapq, cigar = int(tok[1]), int(tok[4]), tok[5]
+            if (flag & 0x4) or mapq < min_mapq or cigar == '*' or cigar == '':
+                continue
+            tags = {}
+            for t in tok[11:]:
+                k, ty, v = t.split(':', 2)
+                if k in ('RG', 'AO'):
+                    tags[k] = int(v) if ty == 'i' else v
+            recs.append((align_index, tok[0], flag, tok[2], int(tok[3]) - 1, mapq, cigar, tags))
+    if not recs:
+        return pd.DataFrame([], columns=ALIGN_COLUMNS)
+
+    # bulk tokenise (host C) and reduce per record
+    ops, op_off, perr = device.parse_cigars([r[6] for r in recs])
+    if perr.code != 0:
+        raise RuntimeError('Malformed CIGAR in SAM record {} ({})'.format(recs[perr.rec][0], recs[perr.rec][1]))
+    code = (ops & 15).astype(np.int64)
+    ln = (ops >> 4).astype(np.int64)
+    rows = []
+    for i, (idx, qname, flag, rname, pos, mapq, _, tags) in enumerate(recs):
+        c, n = code[op_off[i]:op_off[i + 1]], ln[op_off[i]:op_off[i + 1]]
+        if (c == CIGAR_M).any():
+            raise RuntimeError(('Found alignment match CIGAR operation (M) for record {} (Start = {}:{}): '
+                                'Alignment requires CIGAR base-level match/mismatch (=X)').format(qname, rname, pos))
+        is_clip = (c == CIGAR_S) | (c == CIGAR_H)
+        body = np.flatnonzero(~is_clip)
+        if len(body) == 0:
+            lead = int(n.sum())
+            trail = 0
+            core_c, core_n = c[:0], n[:0]
+        else:
+            lead = int(n[:body[0]].sum())
+            trail = int(n[body[-1] + 1:].sum())
+            core_c, core_n = c[body[0]:body[-1] + 1], n[body[0]:body[-1] + 1]
+        ref_bp = int(core_n[np.isin(core_c, (CIGAR_D, CIGAR_N, CIGAR_EQ, CIGAR_X))].sum())
+        qry_bp = int(core_n[np.isin(core_c, (CIGAR_I, CIGAR_EQ, CIGAR_X))].sum())
+        # pysam: query_alignment_start counts leading soft clips only; hard clips are added back by the reference
+        clip_h = int(n[0]) if c[0] == CIGAR_H else 0
+        lead_s = 0
+        for cc, nn in zip(c.tolist(), n.tolist()):
+            if cc == CIGAR_H:
+                continue
+            if cc == CIGAR_S:
+                lead_s = nn
+            break
+        tig_map_pos = lead if lead > 0 else 0
+        if lead_s + clip_h != tig_map_pos:
+            raise RuntimeError(f'First aligned based from pysam ({lead_s}) does not match clipping ({tig_map_pos}) at alignment record {idx}')
+        tig_map_end = tig_map_pos + qry_bp
+        parts = ([f'{lead}H'] if lead > 0 else []) + [f'{a}{CIGAR_CODE_TO_CHAR[b]}' for b, a in zip(core_c.tolist(), core_n.tolist())] + \
+                ([f'{trail}H'] if trail > 0 else [])
+        tig_len = df_tig_fai[qname]
+        rev = bool(flag & 0x10)
+        rows.append((rname, pos, pos + ref_bp, idx, qname, tig_len - tig_map_end if rev else tig_map_pos,
+                     tig_len - tig_map_pos if rev else tig_map_end, tig_len, tags.get('RG', 'NA'), tags.get('AO', 'NA'), mapq, rev,
+                     f'0x{flag:04x}', hap, ''.join(parts)))
+    df = pd.DataFrame({col: pd.Series([r[j] for r in rows], dtype=object) for j, col in enumerate(ALIGN_COLUMNS)}, columns=ALIGN_COLUMNS)
+    df.sort_values(['#CHROM', 'POS', 'END', 'QRY_ID'], ascending=[True, True, False, True], inplace=True)
+    df.apply(check_record, df_tig_fai=df_tig_fai, axis=1)
+    return df

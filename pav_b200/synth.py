@@ -373,3 +373,30 @@ def make_inv_workload(seed=1005, n_win=16, win_len=50_000, flank_frac=0.3, diver
         tig[f'tw{w:05d}'] = t
         meta.append((f'rw{w:05d}', f'tw{w:05d}', iv, neg))
     return ref, tig, meta
+
+
+# ----------------------------------------------------------------------------------------------
+# SAM text (input of pavlib.align.get_align_bed)
+# ----------------------------------------------------------------------------------------------
+
+def write_sam(path, df_align, ref, soft_clip_every=2, extra_lines=()):
+    """Write the alignment table as SAM text (SEQ/QUAL omitted). Every ``soft_clip_every``-th record gets its hard
+    clips rewritten as soft clips so that readers exercise soft->hard conversion. ``extra_lines`` are appended verbatim
+    (unmapped / filtered records)."""
+    with open(path, 'w') as fh:
+        fh.write('@HD\tVN:1.6\tSO:unsorted\n')
+        for name, arr in ref.items():
+            fh.write(f'@SQ\tSN:{name}\tLN:{len(arr)}\n')
+        for i, (_, row) in enumerate(df_align.iterrows()):
+            cigar = row['CIGAR']
+            if soft_clip_every and i % soft_clip_every == 1:
+                cigar = cigar.replace('H', 'S')
+            flag = 16 if row['REV'] else 0
+            tags = ['RG:Z:grp1'] if i % 3 == 0 else []
+            if i % 4 == 0:
+                tags.append('AO:i:%d' % i)
+            fh.write('\t'.join([row['QRY_ID'], str(flag), row['#CHROM'], str(int(row['POS']) + 1), str(int(row['MAPQ'])), cigar, '*', '0', '0',
+                                '*', '*'] + tags) + '\n')
+        for line in extra_lines:
+            fh.write(line.rstrip('\n') + '\n')
+    return path

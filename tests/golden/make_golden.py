@@ -324,8 +324,39 @@ def make_inv_case():
     print('inv kat3', meta['id'], meta['region_ref_outer'])
 
 
+def make_align_case():
+    """SAM text -> alignment table with the reference's get_align_bed (pavlib/align/align.py:666-794) on the stub SAM reader."""
+    import svpoplib
+    d = os.path.join(HERE, 'align', 'sam1')
+    os.makedirs(d, exist_ok=True)
+    ref, tigs, dfa = synth.make_cigar_workload(55, 2, 40_000, 7, 9_000, edit_rate=0.01, rev_frac=0.5, clip=(6, 9))
+    tig_fa = os.path.join(d, 'tig.fa')
+    _write_fa(tig_fa, tigs)
+    extra = ['tigU\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*',                                   # unmapped
+             'tig00001\t0\tchr1\t101\t3\t50=\t*\t0\t0\t*\t*',                          # below min_mapq
+             'tig00002\t0\tchr1\t201\t60\t*\t*\t0\t0\t*\t*']                           # no CIGAR
+    sam = synth.write_sam(os.path.join(d, 'align.sam'), dfa, ref, extra_lines=extra)
+    fai = svpoplib.ref.get_df_fai(tig_fa + '.fai')
+    df = pavlib.align.get_align_bed(sam, fai, 'h1', min_mapq=10)
+    df.to_csv(os.path.join(d, 'align.bed'), sep='\t', index=False)
+    meta = {'n': int(df.shape[0]), 'index': [int(i) for i in df.index], 'dtypes': [str(t) for t in df.dtypes], 'min_mapq': 10}
+    # error: M operation
+    with open(os.path.join(d, 'bad_m.sam'), 'w') as fh:
+        fh.write('@HD\tVN:1.6\n')
+        fh.write('tig00000\t0\tchr1\t1\t60\t100M\t*\t0\t0\t*\t*\n')
+    try:
+        pavlib.align.get_align_bed(os.path.join(d, 'bad_m.sam'), fai, 'h1')
+    except Exception as ex:  # noqa: BLE001
+        meta['bad_m'] = [type(ex).__name__, str(ex)]
+    with open(os.path.join(d, 'meta.json'), 'w') as fh:
+        json.dump(meta, fh, indent=1)
+    print('align sam1', meta['n'], meta.get('bad_m'))
+
+
 if __name__ == '__main__':
-    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv'}
+    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align'}
+    if 'align' in what:
+        make_align_case()
     if 'cigar' in what:
         make_cigar_cases()
     if 'homology' in what:

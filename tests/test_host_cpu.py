@@ -217,3 +217,32 @@ def test_align_lift_roundtrip():
         if back is not None and abs(back[1] - p) <= 1:
             ok += 1
     assert ok > 150
+
+
+def test_get_align_bed_matches_reference_golden():
+    """SAM text -> alignment table equals the table produced by the reference's get_align_bed."""
+    from pav_b200.pavlib import align, seq
+    d = os.path.join(GOLDEN, 'align', 'sam1')
+    meta = json.load(open(os.path.join(d, 'meta.json')))
+    fai = seq.get_df_fai(os.path.join(d, 'tig.fa.fai'))
+    df = align.get_align_bed(os.path.join(d, 'align.sam'), fai, 'h1', min_mapq=meta['min_mapq'])
+    assert df.to_csv(sep='\t', index=False).encode() == open(os.path.join(d, 'align.bed'), 'rb').read()
+    assert [int(i) for i in df.index] == meta['index'] and [str(t) for t in df.dtypes] == meta['dtypes']
+    with pytest.raises(RuntimeError) as ei:
+        align.get_align_bed(os.path.join(d, 'bad_m.sam'), fai, 'h1')
+    assert str(ei.value) == meta['bad_m'][1]
+
+
+def test_count_cigar_and_check_record():
+    from pav_b200.pavlib import align
+    assert align.count_cigar('3H2S10=2X4I5D7=1S2H') == (24, 23, 3, 2, 2, 1)
+    with pytest.raises(RuntimeError, match='CIGAR op "M" is not allowed'):
+        align.count_cigar('10M')
+    with pytest.raises(RuntimeError, match='Found clipped bases before last non-clipped'):
+        align.count_cigar('5=2S5=')
+    row = pd.Series({'#CHROM': 'c', 'POS': 10, 'END': 34, 'INDEX': 0, 'QRY_ID': 'q', 'QRY_POS': 5, 'QRY_END': 28, 'QRY_LEN': 31,
+                     'CIGAR': '3H2S10=2X4I5D7=1S2H'})
+    align.check_record(row, pd.Series({'q': 31}))
+    row['END'] = 35
+    with pytest.raises(RuntimeError, match='END mismatch'):
+        align.check_record(row, pd.Series({'q': 31}))
