@@ -115,6 +115,23 @@ class Control:
             self.dist.destroy_process_group()
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """Route C-level writes to fd 1 (e.g. NCCL's "NCCL version ..." banner) to stderr for the duration of the block."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -172,14 +189,25 @@ def measured_peak_gbs():
 
 
 # ----------------------------------------------------------------------------------------------------------
+_POOL = None
+
+
+def _pool(cores):
+    """Worker processes are started once and reused by every step (each task still re-reads the FASTA files)."""
+    global _POOL
+    if _POOL is None:
+        import multiprocessing as mp
+        _POOL = mp.get_context('fork').Pool(cores)
+    return _POOL
+
+
 def cpu_port_rows_per_sec(df_align, ref_fa, tig_fa, n_contigs, cores, fast=False):
     """Oracle port of make_insdel_snv_calls on a bounded sample, one record shard per worker process."""
-    import multiprocessing as mp
     sample = df_align.iloc[:n_contigs]
     shards = [sample.iloc[i::cores] for i in range(cores) if len(sample.iloc[i::cores])]
+    pool = _pool(cores)
     t0 = time.perf_counter()
-    with mp.get_context('fork').Pool(len(shards)) as pool:
-        counts = pool.map(_cpu_shard_fast if fast else _cpu_shard, [(s, ref_fa, tig_fa) for s in shards])
+    counts = pool.map(_cpu_shard_fast if fast else _cpu_shard, [(s, ref_fa, tig_fa) for s in shards], chunksize=1)
     dt = time.perf_counter() - t0
     rows = int(sum(counts))
     return rows / dt, rows, dt, len(shards)
@@ -188,6 +216,7 @@ def cpu_port_rows_per_sec(df_align, ref_fa, tig_fa, n_contigs, cores, fast=False
 def _cpu_shard(args):
     from oracle import pyoracle
     df, ref_fa, tig_fa = args
+    pyoracle._FA_CACHE.clear()   # like a fresh Snakemake job: nothing cached between steps
     # reference_containers=True: frames assembled the way the reference does (pd.Series per variant + concat),
     # measured within 7 % of the unmodified reference's throughput in the build container
     a, b = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False, reference_containers=True)
@@ -197,8 +226,19 @@ def _cpu_shard(args):
 def _cpu_shard_fast(args):
     from oracle import pyoracle
     df, ref_fa, tig_fa = args
+    pyoracle._FA_CACHE.clear()
     a, b = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
     return len(a) + len(b)
+
+
+def cpu_sample_contigs(args, cores, n_steps):
+    """Contigs in the CPU sample: about min(15 s, 150 s / steps) of wall time per step at ~9e3 rows/s/core."""
+    if args.cpu_sample_contigs:
+        return min(args.cpu_sample_contigs, args.contigs)
+    t_step = min(15.0, 150.0 / max(n_steps, 1))
+    rows_per_contig = args.contig_len * 0.00975
+    n = int(9000.0 * cores * t_step / rows_per_contig)
+    return max(min(n, args.contigs), min(cores, args.contigs))
 
 
 def run_reference(args, rank, world):
@@ -209,7 +249,7 @@ def run_reference(args, rank, world):
     from pav_b200 import synth
     pyoracle.build()
     cores = len(os.sched_getaffinity(0))
-    n_sample = args.cpu_sample_contigs or min(args.contigs, max(cores, 96))
+    n_sample = cpu_sample_contigs(args, cores, args.warmup + args.steps)
     tmp = tempfile.mkdtemp(prefix='pavbench_ref_')
     chrom_len = args.contigs * args.contig_len // 4
     ref, trs = synth.make_reference(args.seed, 4, chrom_len)
@@ -266,12 +306,17 @@ def density_secondary(ctx, args, rank):
     out = density.density_windows([(ref[a], tig[b], False, 20) for a, b, _, _ in meta])
     e2e_s = time.perf_counter() - t0
     # spot check window 0 against the oracle
-    ok = None
+    ok, cpu = None, None
     try:
         from oracle import pyoracle
+        t0 = time.perf_counter()
         rc, o = pyoracle.density_arrays(ref[names_r[0]].tobytes(), tig[names_t[0]].tobytes())
+        cpu_s = time.perf_counter() - t0
         ok = bool(rc == out[0]['status'] and all((out[0][c].astype(np.int64) == o[c].astype(np.int64)).all()
                                                  for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE')))
+        cpu = {'value': 50_000 / cpu_s / 1e9, 'unit': 'Gbases/s', 'cores': 1, 'kind': 'port',
+               'sample': f'1 of {n_win} windows (50 kbp) through oracle/pav_oracle.c (scalar C, O(N*E) KDE), {cpu_s:.2f} s',
+               'note': 'the Python reference (scripts/density.py) needs 8.2 s for such a window in the build container = 6.1e-6 Gbases/s/core (BASELINE.md)'}
     except Exception as ex:  # noqa: BLE001
         log('density oracle spot check failed to run:', ex)
     k_ms = float(np.mean(ms))
@@ -281,7 +326,7 @@ def density_secondary(ctx, args, rank):
         'config': {'workload': f'C5-shaped: {n_win} windows x 50 kbp, k=31, srs=20 per GPU', 'l2': 'flushed between iterations'},
         'ms_per_step': k_ms, 'ms_kmer': st.ms_kmer, 'ms_kde': st.ms_kde, 'kde_pairs': int(st.kde_pairs),
         'kde_pairs_per_sec': st.kde_pairs / (st.ms_kde * 1e-3) if st.ms_kde > 0 else None,
-        'rows': int(st.rows), 'gpu_launches': int(st.kernel_launches), 'oracle_spot_check': ok,
+        'rows': int(st.rows), 'gpu_launches': int(st.kernel_launches), 'oracle_spot_check': ok, 'cpu_baseline': cpu,
     }
 
 
@@ -318,7 +363,8 @@ def run_ours(args, rank, world, local):
         uid = device.nccl_unique_id() if rank == 0 else b''
         uid = ctl.bcast_bytes(uid, 128)
         ctl.barrier()
-        bcast_ms = ref_store.broadcast(uid, rank, world)
+        with stdout_to_stderr():   # NCCL prints its version banner on stdout; the driver wants one JSON line there
+            bcast_ms = ref_store.broadcast(uid, rank, world)
         bcast_ms = ctl.max(bcast_ms)
     tig_arrays = [tigs[n] for n in names_t]
     tig_store = device.SeqStore(ctx, names_t, tig_arrays)
@@ -426,7 +472,7 @@ def run_ours(args, rank, world, local):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        n_sample = args.cpu_sample_contigs or min(args.contigs, max(cores, 96))
+        n_sample = cpu_sample_contigs(args, cores, 2)
         rps, rows, dt, used = cpu_port_rows_per_sec(df, ref_fa, tig_fa, n_sample, cores)
         rps_fast, _, _, _ = cpu_port_rows_per_sec(df, ref_fa, tig_fa, n_sample, cores, fast=True)
         cpu = {'value': rps, 'unit': UNIT, 'cores': used, 'kind': 'port',
@@ -455,8 +501,15 @@ def run_ours(args, rank, world, local):
     dom_ms, dom_bytes = kernels[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_bytes = sum(b for _, b in kernels.values())
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel on the same (default C2) input, from the committed ncu capture
+        tj = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic.json')))
+        if tj.get('n_ops') == n_ops and dom in tj.get('kernels', {}):
+            traffic = tj['kernels'][dom]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {
-        'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+        'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
         'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': dom_ms,
         'per_kernel_ms': {k: v[0] for k, v in kernels.items()},
         'step': {'algorithmic_bytes': int(step_bytes), 'achieved': step_bytes / (my_ms * 1e-3) / 1e9, 'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak},

@@ -295,13 +295,13 @@ cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 }
 
 // KF (fused K1+K2+K3) -----------------------------------------------------------------------------
-// Single pass over the ops: one CTA = 8 warps = 1024 ops. Everything the walk carries is *segmented by record*:
+// Single pass over the ops: one warp = one chunk of 128 ops, start to finish. Everything the walk carries is *segmented by record*:
 // ref/qry advance since the record head and the number of SNV / indel rows the record has emitted so far. The
 // first row slot of every record (rec_snv_off / rec_indel_off, "per-record offset buffer") comes from the host,
-// which counts rows per record while it packs the CIGAR text. Tile aggregates travel between CTAs through 16-byte
-// descriptors with a decoupled look-back that stops at the nearest tile containing a record head, so a tile never
-// waits for more than the tiles of its own record (a few for contig-scale records). Tiles are handed out by an
-// atomic counter so a CTA only waits for tiles that are already running.
+// which counts rows per record while it packs the CIGAR text. Chunk aggregates travel between warps through 16-byte
+// descriptors with a decoupled look-back that stops at the nearest chunk containing a record head, so a warp never
+// waits for more than the chunks of its own record (one 32-descriptor window covers 4096 ops). There is no shared
+// memory and no CTA barrier on the critical path (a CTA-level look-back left 6 warps per issue stalled at the barrier).
 //   w0: [1:0] status  [2] has-head  [33:3] ref advance (31 b)  [63:34] indel rows (30 b)
 //   w1: [30:0] qry advance (31 b)   [63:31] SNV rows (33 b)
 constexpr unsigned ST_INVALID = 0, ST_AGG = 1, ST_PREFIX = 2;
@@ -349,33 +349,33 @@ __device__ __forceinline__ void seg_combine(const TileVal &older, TileVal &v)
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_tiles, const int32_t *__restrict__ chunk_rec,
+cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks, const int32_t *__restrict__ chunk_rec,
                   ulonglong2 *__restrict__ desc, const int64_t *__restrict__ qry_len, const int64_t *__restrict__ rec_snv_off,
                   const int64_t *__restrict__ rec_indel_off, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
                   unsigned long long *__restrict__ first_illegal, unsigned long long *__restrict__ totals)
 {
-    __shared__ TileVal s_agg[WARPS_PER_BLOCK];   // per-warp aggregates
-    __shared__ TileVal s_fold[WARPS_PER_BLOCK];  // folds over warps 0..w
-    __shared__ TileVal s_ex;                     // exclusive prefix of the tile
+    // One warp = one 128-op chunk, start to finish: no shared memory and no CTA barrier on the critical path.
+    // Chunks are taken in (blockIdx, warp) order, so a warp only ever waits for chunks that were dispatched before it.
     __shared__ uint32_t s_tot[WARPS_PER_BLOCK][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // Tiles are taken in blockIdx order (like CUB's scan agents): a CTA only ever waits for lower-numbered tiles,
-    // which the hardware has dispatched before it.
-    const int64_t tile = blockIdx.x;
-    const int64_t chunk = tile * WARPS_PER_BLOCK + wid;
+    const int64_t chunk = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid;
+    const bool live = chunk < n_chunks;
 
-    // ---- per-lane ops and record lookup (one search per warp; per-lane search only when the chunk spans records)
+    // ---- per-lane ops and record lookup
     LaneOps L;
     L.g0 = chunk * CHUNK + (int64_t)lane * OPS_PER_LANE;
-    {
+    L.nvalid = 0; L.rec0 = 0;
+    L.op[0] = L.op[1] = L.op[2] = L.op[3] = 0;
+    if (live) {
         int64_t rem = n_ops - L.g0;
         L.nvalid = rem <= 0 ? 0 : (rem >= OPS_PER_LANE ? OPS_PER_LANE : (int)rem);
-        uint4 raw = make_uint4(0, 0, 0, 0);
-        if (L.nvalid > 0) raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));
-        L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
+        if (L.nvalid > 0) {
+            uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));
+            L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
+        }
         // record of the chunk's first op comes from a host-built index (one load instead of a binary search);
         // lanes search on their own only when the chunk spans several records
-        int32_t rec_lo = (chunk * CHUNK < n_ops) ? __ldg(chunk_rec + chunk) : 0;
+        int32_t rec_lo = __ldg(chunk_rec + chunk);
         L.rec0 = rec_lo;
         if (L.nvalid > 0 && L.g0 >= __ldg(rv.op_off + rec_lo + 1)) L.rec0 = find_rec(rv.op_off, rv.n_rec, L.g0);
     }
@@ -413,36 +413,25 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
             fi |= f2;
         }
     }
-    // row totals of the tile (plain sums) for the end-of-run consistency check
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { ns_all += __shfl_xor_sync(FULL, ns_all, d); ni_all += __shfl_xor_sync(FULL, ni_all, d); }
-    if (lane == 31) s_agg[wid] = TileVal{fi, ri, qi, (unsigned long long)nsi, (unsigned long long)nii};
     if (lane == 0) { s_tot[wid][0] = ns_all; s_tot[wid][1] = ni_all; }
-    __syncthreads();
 
-    // ---- warp 0: tile aggregate, publish, look back to the nearest record head, publish the inclusive prefix
-    if (wid == 0) {
-        TileVal agg{0, 0, 0, 0ull, 0ull};
-        for (int w = 0; w < WARPS_PER_BLOCK; w++) {
-            TileVal nv = s_agg[w];
-            seg_combine(agg, nv);   // nv = fold(warps 0..w)
-            agg = nv;
-            if (lane == 0) s_fold[w] = nv;
-        }
-        const bool self_contained = (tile == 0) || agg.f;  // nothing before this tile can reach past its first head
-        if (lane == 0) tile_store(desc + tile, tile_pack(tile == 0 ? ST_PREFIX : ST_AGG, agg));
-        TileVal ex{0, 0, 0, 0ull, 0ull};
-        // the tile's first ops still belong to the record of the previous tile unless the tile starts with a head;
-        // the exclusive prefix is needed whenever the first op of the tile is not a head
-        const bool first_is_head = (tile * (int64_t)WARPS_PER_BLOCK * CHUNK) == __ldg(rv.op_off + __shfl_sync(FULL, L.rec0, 0));
-        (void)self_contained;
-        if (tile > 0 && !first_is_head) {
-            int64_t base = tile - 1;
+    // ---- chunk aggregate -> descriptor; look back to the nearest chunk holding a record head; publish the prefix
+    TileVal agg;
+    agg.f = __shfl_sync(FULL, fi, 31); agg.r = __shfl_sync(FULL, ri, 31); agg.q = __shfl_sync(FULL, qi, 31);
+    agg.ns = __shfl_sync(FULL, nsi, 31); agg.ni = __shfl_sync(FULL, nii, 31);
+    TileVal c{0, 0, 0, 0ull, 0ull};   // exclusive prefix of the chunk
+    if (live) {
+        if (lane == 0) tile_store(desc + chunk, tile_pack(chunk == 0 ? ST_PREFIX : ST_AGG, agg));
+        const bool first_is_head = (chunk * (int64_t)CHUNK) == __ldg(rv.op_off + __shfl_sync(FULL, L.rec0, 0));
+        if (chunk > 0 && !first_is_head) {
+            int64_t base = chunk - 1;
             bool done = false;
             while (!done) {
                 int64_t idx = base - lane;
                 TileVal v{0, 0, 0, 0ull, 0ull};
-                unsigned st = ST_PREFIX;  // before the first tile: identity prefix
+                unsigned st = ST_PREFIX;  // before the first chunk: identity prefix
                 if (idx >= 0) {
                     do { st = tile_unpack(tile_load(desc + idx), v); } while (st == ST_INVALID);
                 } else v.f = 1;
@@ -451,7 +440,7 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
                 int k = __ffs((int)pm) - 1;
                 int last = (k < 0) ? 31 : k;
                 if (lane > last) { v.f = 0; v.r = 0; v.q = 0; v.ns = 0; v.ni = 0; }
-                // fold lanes last..0 in tile order (higher lane = older tile): result in lane 0
+                // fold lanes last..0 in chunk order (higher lane = older chunk): result in lane 0
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     TileVal o;
@@ -462,33 +451,18 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
                 TileVal win;
                 win.f = __shfl_sync(FULL, v.f, 0); win.r = __shfl_sync(FULL, v.r, 0); win.q = __shfl_sync(FULL, v.q, 0);
                 win.ns = __shfl_sync(FULL, v.ns, 0); win.ni = __shfl_sync(FULL, v.ni, 0);
-                seg_combine(win, ex);   // window (older) (+) what we already have (newer)
+                seg_combine(win, c);   // window (older) (+) what we already have (newer)
                 done = (k >= 0);
                 base -= 32;
             }
         }
-        if (lane == 0) {
-            unsigned long long ts = 0, ti = 0;
-            for (int w = 0; w < WARPS_PER_BLOCK; w++) { ts += s_tot[w][0]; ti += s_tot[w][1]; }
-            if (ts) atomicAdd(totals, ts);
-            if (ti) atomicAdd(totals + 1, ti);
-            if (tile > 0) {
-                TileVal inc = agg;
-                seg_combine(ex, inc);
-                tile_store(desc + tile, tile_pack(ST_PREFIX, inc));
-            }
-            s_ex = ex;
+        if (lane == 0 && chunk > 0) {
+            TileVal inc = agg;
+            seg_combine(c, inc);
+            tile_store(desc + chunk, tile_pack(ST_PREFIX, inc));
         }
     }
-    __syncthreads();
 
-    // ---- exclusive prefix of this warp = tile prefix (+) fold of the earlier warps of the tile
-    TileVal c = s_ex;
-    if (wid > 0) {
-        TileVal pw = s_fold[wid - 1];
-        seg_combine(c, pw);
-        c = pw;
-    }
     // ---- emit
     int ef = __shfl_up_sync(FULL, fi, 1), er = __shfl_up_sync(FULL, ri, 1), eq = __shfl_up_sync(FULL, qi, 1);
     uint32_t ens = __shfl_up_sync(FULL, nsi, 1), eni = __shfl_up_sync(FULL, nii, 1);
@@ -499,14 +473,19 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
     long long run_ni = ef ? (long long)eni : (long long)eni + (long long)c.ni;
     uint32_t prev_op = __shfl_up_sync(FULL, L.op[OPS_PER_LANE - 1], 1);
     if (lane == 0) prev_op = (L.nvalid > 0 && L.g0 > 0) ? __ldg(ops + L.g0 - 1) : 0u;
-    if (L.nvalid == 0) return;
 
     int32_t rec = L.rec0;
-    int64_t cur_off = __ldg(rv.op_off + rec), next_off = __ldg(rv.op_off + rec + 1);
-    int32_t rpos = __ldg(rv.pos + rec);
-    int rrev = __ldg(rv.rev + rec);
-    int32_t qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
-    long long snv_base = __ldg(rec_snv_off + rec), indel_base = __ldg(rec_indel_off + rec);
+    int64_t cur_off = 0, next_off = 0;
+    int32_t rpos = 0, qlen = 0;
+    int rrev = 0;
+    long long snv_base = 0, indel_base = 0;
+    if (L.nvalid > 0) {
+        cur_off = __ldg(rv.op_off + rec); next_off = __ldg(rv.op_off + rec + 1);
+        rpos = __ldg(rv.pos + rec);
+        rrev = __ldg(rv.rev + rec);
+        qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+        snv_base = __ldg(rec_snv_off + rec); indel_base = __ldg(rec_indel_off + rec);
+    }
 #pragma unroll
     for (int j = 0; j < OPS_PER_LANE; j++) {
         if (j < L.nvalid) {
@@ -546,6 +525,14 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
             if (bit & QRY_ADV_MASK) run_q += (int)len;
             prev_op = op;
         }
+    }
+    // ---- row totals of the CTA -> global counters (end-of-run consistency check against the host count)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long ts = 0, ti = 0;
+        for (int w = 0; w < WARPS_PER_BLOCK; w++) { ts += s_tot[w][0]; ti += s_tot[w][1]; }
+        if (ts) atomicAdd(totals, ts);
+        if (ti) atomicAdd(totals + 1, ti);
     }
 }
 
@@ -778,7 +765,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
         CUDA_TRY(cudaMalloc(&b->d_agg, nc * sizeof(int4))); CUDA_TRY(cudaMalloc(&b->d_cnt, nc * sizeof(uint2)));
         CUDA_TRY(cudaMalloc(&b->d_pre_rq, nc * sizeof(int2))); CUDA_TRY(cudaMalloc(&b->d_pre_cnt, nc * sizeof(longlong2)));
         CUDA_TRY(cudaMalloc(&b->d_totals, 2 * 8)); CUDA_TRY(cudaMalloc(&b->d_first_illegal, 8));
-        CUDA_TRY(cudaMalloc(&b->d_desc, sizeof(ulonglong2) * (size_t)std::max<int64_t>(b->n_tiles, 1)));
+        CUDA_TRY(cudaMalloc(&b->d_desc, sizeof(ulonglong2) * (size_t)std::max<int64_t>(b->n_chunks, 1)));
         CUDA_TRY(cudaMalloc(&b->d_tile_counter, sizeof(unsigned int)));
         CUDA_TRY(cudaMalloc(&b->d_rec_snv_off, (nr + 1) * 8)); CUDA_TRY(cudaMalloc(&b->d_rec_indel_off, (nr + 1) * 8));
         CUDA_TRY(cudaMemcpyAsync(b->d_rec_snv_off, rec_snv_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -833,8 +820,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
     b->n_snv = b->n_indel = 0;
     if (b->n_chunks > 0 && b->fused) {
-        CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_tiles, st));
-        cigar_walk_kernel<<<(unsigned)b->n_tiles, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_tiles, b->d_chunk_rec, b->d_desc,
+        CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_chunks, st));
+        cigar_walk_kernel<<<(unsigned)b->n_tiles, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, b->d_desc,
                                                                              qry_store->d_len, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
                                                                              b->d_first_illegal, reinterpret_cast<unsigned long long *>(b->d_totals));
         launches++;

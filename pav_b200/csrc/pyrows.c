@@ -125,7 +125,17 @@ static PyObject *py_format(PyObject *self, PyObject *args)
                     break; }
                 }
             }
-            PyObject *s = PyUnicode_DecodeUTF8(scratch, d - scratch, NULL);
+            /* all pieces are ASCII in practice (names, digits, base letters): build the compact str directly */
+            Py_ssize_t len = d - scratch;
+            int ascii = 1;
+            for (Py_ssize_t k = 0; k < len; k++) if ((unsigned char)scratch[k] & 0x80) { ascii = 0; break; }
+            PyObject *s;
+            if (ascii) {
+                s = PyUnicode_New(len, 127);
+                if (s) memcpy(PyUnicode_1BYTE_DATA(s), scratch, (size_t)len);
+            } else {
+                s = PyUnicode_DecodeUTF8(scratch, len, NULL);
+            }
             if (!s) { PyMem_Free(scratch); Py_DECREF(out); goto fail; }
             slots[r] = s;
         }

@@ -38,9 +38,14 @@ def _first_seen(values):
     return seen
 
 
-def _sort_order(chrom_codes, pos, end, ids):
+def _sort_order(chrom_codes, pos, end, ids, end_is_pos_plus_1=False):
     """Permutation equal to pandas' stable ``sort_values(['#CHROM','POS','END','ID'])``."""
-    order = np.lexsort((end, pos, chrom_codes))
+    if end_is_pos_plus_1 and len(pos) and int(pos.max()) < (1 << 40) and int(chrom_codes.max()) < (1 << 22):
+        # SNV rows: END = POS + 1, so one composite key orders them; rows arrive nearly sorted (records are sorted by
+        # #CHROM, POS), which the stable merge sort exploits
+        order = np.argsort((chrom_codes << 40) | pos, kind='stable')
+    else:
+        order = np.lexsort((end, pos, chrom_codes))
     if len(order) > 1:
         c, p, e = chrom_codes[order], pos[order], end[order]
         tie = (c[1:] == c[:-1]) & (p[1:] == p[:-1]) & (e[1:] == e[:-1])
@@ -229,7 +234,7 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
                                  ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
         if version_id:
             ids = variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object)
-        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, ids)
+        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, ids, end_is_pos_plus_1=True)
         rec, pos, qp, ref_b, alt_b = rec[order], pos[order], qp[order], ref_b[order], alt_b[order]
         pos1, qp1 = pos + 1, qp + 1
         cols = {

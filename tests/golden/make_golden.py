@@ -284,20 +284,27 @@ def make_density_cases():
     density_case('k21_srs7', r, t, k=21, srs=7)
 
 
-def make_inv_case():
-    """KAT 3: full pavlib.inv.scan_for_inv incl. AlignLift, 60 kbp, 8 kbp inversion."""
+def make_inv_case(name='kat3', rev=False, seed=3, flank_rep=0):
+    """KAT 3: full pavlib.inv.scan_for_inv incl. AlignLift, 60 kbp, 8 kbp inversion.
+    ``rev``: the contig is stored reverse-complemented and aligned on the minus strand (exercises -r true and the
+    reverse lift); ``flank_rep``: inverted-repeat flanks (inner != outer breakpoints, FLANK / MATCH annotation)."""
     import random
-    random.seed(3)
+    random.seed(seed)
     n = 60000
     s = ''.join(random.choice('ACGT') for _ in range(n))
     comp = {'A': 'T', 'C': 'G', 'G': 'C', 'T': 'A'}
-    t = s[:26000] + ''.join(comp[c] for c in reversed(s[26000:34000])) + s[34000:]
-    d = os.path.join(HERE, 'inv', 'kat3')
+    rc = lambda x: ''.join(comp[c] for c in reversed(x))  # noqa: E731
+    if flank_rep:
+        s = s[:34000] + rc(s[26000 - flank_rep:26000]) + s[34000 + flank_rep:]
+    t = s[:26000] + rc(s[26000:34000]) + s[34000:]
+    if rev:
+        t = rc(t)
+    d = os.path.join(HERE, 'inv', name)
     os.makedirs(d, exist_ok=True)
     ref_fa, tig_fa = os.path.join(d, 'ref.fa'), os.path.join(d, 'tig.fa')
     _write_fa(ref_fa, {'chr1': s})
     _write_fa(tig_fa, {'tig1': t})
-    df_align = pd.DataFrame([('chr1', 0, n, 0, 'tig1', 0, n, n, False, f'{n}=')],
+    df_align = pd.DataFrame([('chr1', 0, n, 0, 'tig1', 0, n, n, rev, f'{n}=')],
                             columns=['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END', 'QRY_LEN',
                                      'REV', 'CIGAR'])
     df_align.to_csv(os.path.join(d, 'align.bed'), sep='\t', index=False)
@@ -321,7 +328,7 @@ def make_inv_case():
         call.df.to_csv(fh, sep='\t', index=False)
     with open(os.path.join(d, 'meta.json'), 'w') as fh:
         json.dump(meta, fh, indent=1)
-    print('inv kat3', meta['id'], meta['region_ref_outer'])
+    print('inv', name, meta['id'], meta['region_ref_outer'], meta['region_ref_inner'], meta['region_tig_outer'])
 
 
 def make_align_case():
@@ -367,3 +374,5 @@ if __name__ == '__main__':
         make_density_cases()
     if 'inv' in what:
         make_inv_case()
+        make_inv_case('kat3_rev', rev=True, seed=4)
+        make_inv_case('kat3_flank', rev=False, seed=5, flank_rep=1500)

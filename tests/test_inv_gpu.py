@@ -19,9 +19,10 @@ class _K:
         self.k_size = k
 
 
-def test_scan_for_inv_kat3(capsys):
+@pytest.mark.parametrize('case', sorted(os.listdir(os.path.join(GOLDEN, 'inv'))))
+def test_scan_for_inv_golden(case, capsys):
     from pav_b200.pavlib import inv, lift, seq
-    d = os.path.join(GOLDEN, 'inv', 'kat3')
+    d = os.path.join(GOLDEN, 'inv', case)
     meta = json.load(open(os.path.join(d, 'meta.json')))
     df_align = pd.read_csv(os.path.join(d, 'align.bed'), sep='\t', dtype={'#CHROM': str, 'QRY_ID': str})
     fai = seq.get_df_fai(os.path.join(d, 'tig.fa.fai'))
@@ -42,9 +43,9 @@ def test_scan_for_inv_kat3(capsys):
     assert call.df['FLANK'].fillna('').tolist() == gold['FLANK'].fillna('').tolist()
     assert call.df['MATCH'].fillna('').tolist() == gold['MATCH'].fillna('').tolist()
     text = log.getvalue()
-    assert 'Scanning region: chr1:26001-34000' in text and 'Scanning region: chr1:20001-40000' in text
-    assert 'Found inversion: chr1-26000-INV-8002' in text
-    assert 'INV Found: outer=tig1:26000-34001' in capsys.readouterr().out
+    assert 'Scanning region: chr1:26001-34000' in text
+    assert 'Found inversion: ' + meta['id'] in text
+    assert 'INV Found: outer=' + meta['region_tig_outer'] in capsys.readouterr().out
 
 
 def test_scan_for_inv_negative_and_limits(tmp_path):
