@@ -485,10 +485,9 @@ def run_ours(args, rank, world, local):
     # ---- roofline of the dominant kernel
     n_ops, n_snv, n_indel, n_chunks = int(st.n_ops), int(st.n_snv), int(st.n_indel), int(st.n_chunks)
     peak, peak_src = measured_peak_gbs()
-    n_tiles = (n_chunks + 7) // 8
     if int(st.kernel_launches) <= 2:   # single-pass walk: K1+K2+K3 fused (cigar_walk_kernel)
         kernels = {
-            'cigar_walk_kernel': (scan_ms, 4 * n_ops + 2 * 16 * n_tiles + 16 * n_snv + 32 * n_indel),
+            'cigar_walk_kernel': (scan_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 32 * n_indel),
             'homology_kernel': (hom_ms, (32 + 64) * n_indel),
         }
     else:

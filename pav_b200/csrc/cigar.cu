@@ -25,8 +25,9 @@
 
 namespace {
 
-constexpr int OPS_PER_LANE = 4;
+constexpr int OPS_PER_LANE = 8;           // two 128-bit loads per lane; 256-op chunks halve the per-op cost of the warp scans / look-back
 constexpr int CHUNK = 32 * OPS_PER_LANE;  // ops per warp
+static_assert(OPS_PER_LANE % 4 == 0, "lanes load whole uint4 vectors");
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -66,15 +67,24 @@ struct LaneOps {
     int32_t rec0;
 };
 
+__device__ __forceinline__ void load_lane_ops(const uint32_t *__restrict__ ops, int64_t g0, uint32_t (&op)[OPS_PER_LANE])
+{
+#pragma unroll
+    for (int v = 0; v < OPS_PER_LANE / 4; v++) {   // the ops buffer is padded to a whole chunk, so full vectors are always readable
+        uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ops + g0) + v);
+        op[4 * v] = raw.x; op[4 * v + 1] = raw.y; op[4 * v + 2] = raw.z; op[4 * v + 3] = raw.w;
+    }
+}
+
 __device__ __forceinline__ LaneOps load_lane(const uint32_t *__restrict__ ops, int64_t n_ops, const RecView &rv, int64_t chunk, int lane)
 {
     LaneOps L;
     L.g0 = chunk * CHUNK + (int64_t)lane * OPS_PER_LANE;
     int64_t rem = n_ops - L.g0;
     L.nvalid = rem <= 0 ? 0 : (rem >= OPS_PER_LANE ? OPS_PER_LANE : (int)rem);
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (L.nvalid > 0) raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));  // buffer is padded to CHUNK
-    L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
+#pragma unroll
+    for (int j = 0; j < OPS_PER_LANE; j++) L.op[j] = 0;
+    if (L.nvalid > 0) load_lane_ops(ops, L.g0, L.op);
     L.rec0 = L.nvalid > 0 ? find_rec(rv.op_off, rv.n_rec, L.g0) : 0;
     return L;
 }
@@ -295,12 +305,12 @@ cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 }
 
 // KF (fused K1+K2+K3) -----------------------------------------------------------------------------
-// Single pass over the ops: one warp = one chunk of 128 ops, start to finish. Everything the walk carries is *segmented by record*:
+// Single pass over the ops: one warp = one chunk of 256 ops, start to finish. Everything the walk carries is *segmented by record*:
 // ref/qry advance since the record head and the number of SNV / indel rows the record has emitted so far. The
 // first row slot of every record (rec_snv_off / rec_indel_off, "per-record offset buffer") comes from the host,
 // which counts rows per record while it packs the CIGAR text. Chunk aggregates travel between warps through 16-byte
 // descriptors with a decoupled look-back that stops at the nearest chunk containing a record head, so a warp never
-// waits for more than the chunks of its own record (one 32-descriptor window covers 4096 ops). There is no shared
+// waits for more than the chunks of its own record (one 32-descriptor window covers 8192 ops). There is no shared
 // memory and no CTA barrier on the critical path (a CTA-level look-back left 6 warps per issue stalled at the barrier).
 //   w0: [1:0] status  [2] has-head  [33:3] ref advance (31 b)  [63:34] indel rows (30 b)
 //   w1: [30:0] qry advance (31 b)   [63:31] SNV rows (33 b)
@@ -354,7 +364,7 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
                   const int64_t *__restrict__ rec_indel_off, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
                   unsigned long long *__restrict__ first_illegal, unsigned long long *__restrict__ totals)
 {
-    // One warp = one 128-op chunk, start to finish: no shared memory and no CTA barrier on the critical path.
+    // One warp = one 256-op chunk, start to finish: no shared memory and no CTA barrier on the critical path.
     // Chunks are taken in (blockIdx, warp) order, so a warp only ever waits for chunks that were dispatched before it.
     __shared__ uint32_t s_tot[WARPS_PER_BLOCK][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -365,14 +375,12 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
     LaneOps L;
     L.g0 = chunk * CHUNK + (int64_t)lane * OPS_PER_LANE;
     L.nvalid = 0; L.rec0 = 0;
-    L.op[0] = L.op[1] = L.op[2] = L.op[3] = 0;
+#pragma unroll
+    for (int j = 0; j < OPS_PER_LANE; j++) L.op[j] = 0;
     if (live) {
         int64_t rem = n_ops - L.g0;
         L.nvalid = rem <= 0 ? 0 : (rem >= OPS_PER_LANE ? OPS_PER_LANE : (int)rem);
-        if (L.nvalid > 0) {
-            uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ops + L.g0));
-            L.op[0] = raw.x; L.op[1] = raw.y; L.op[2] = raw.z; L.op[3] = raw.w;
-        }
+        if (L.nvalid > 0) load_lane_ops(ops, L.g0, L.op);
         // record of the chunk's first op comes from a host-built index (one load instead of a binary search);
         // lanes search on their own only when the chunk spans several records
         int32_t rec_lo = __ldg(chunk_rec + chunk);
@@ -637,7 +645,7 @@ struct pavgpu_cigar_batch {
     ulonglong2 *d_desc;
     unsigned int *d_tile_counter;
     int64_t *d_rec_snv_off, *d_rec_indel_off;   // first row slot of every record (host-counted)
-    int32_t *d_chunk_rec;                        // record of the first op of every 128-op chunk (host-built index)
+    int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (host-built index)
     bool fused;
     unsigned long long first_illegal;
     bool ran;

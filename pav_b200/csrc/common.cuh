@@ -28,7 +28,50 @@ struct pavgpu_ctx {
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
     int flush_val = 0;
+    // Scratch arenas handed back by finished batches / stores and reused by the next ones: a Snakemake job calls the
+    // library many times with similar sizes, and cudaMalloc / cudaFree of ~GB buffers cost tens of milliseconds.
+    static constexpr int N_CACHE = 4;
+    void *cache_ptr[N_CACHE] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cache_bytes[N_CACHE] = {0, 0, 0, 0};
 };
+
+// Take a device buffer of at least `bytes` from the context cache (smallest fit) or allocate one. *got = its real size.
+static inline cudaError_t ctx_arena_take(pavgpu_ctx *ctx, size_t bytes, void **out, size_t *got)
+{
+    int best = -1;
+    for (int i = 0; i < pavgpu_ctx::N_CACHE; i++)
+        if (ctx->cache_ptr[i] && ctx->cache_bytes[i] >= bytes && (best < 0 || ctx->cache_bytes[i] < ctx->cache_bytes[best])) best = i;
+    if (best >= 0) {
+        *out = ctx->cache_ptr[best]; *got = ctx->cache_bytes[best];
+        ctx->cache_ptr[best] = nullptr; ctx->cache_bytes[best] = 0;
+        return cudaSuccess;
+    }
+    *got = bytes;
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {   // make room and retry once
+        for (int i = 0; i < pavgpu_ctx::N_CACHE; i++) { cudaFree(ctx->cache_ptr[i]); ctx->cache_ptr[i] = nullptr; ctx->cache_bytes[i] = 0; }
+        (void)cudaGetLastError();
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+// Give a buffer back: kept if a slot is free or it is larger than the smallest cached one (which is freed instead).
+static inline void ctx_arena_give(pavgpu_ctx *ctx, void *ptr, size_t bytes)
+{
+    if (!ptr) return;
+    int slot = -1, smallest = 0;
+    for (int i = 0; i < pavgpu_ctx::N_CACHE; i++) {
+        if (!ctx->cache_ptr[i]) { slot = i; break; }
+        if (ctx->cache_bytes[i] < ctx->cache_bytes[smallest]) smallest = i;
+    }
+    if (slot < 0) {
+        if (ctx->cache_bytes[smallest] >= bytes) { cudaFree(ptr); return; }
+        cudaFree(ctx->cache_ptr[smallest]);
+        slot = smallest;
+    }
+    ctx->cache_ptr[slot] = ptr; ctx->cache_bytes[slot] = bytes;
+}
 
 // Sequence planes in HBM.
 //   pack2 : 64-bit words, 32 bases per word, base g at bits [62 - 2*(g%32), +2)  (first base most

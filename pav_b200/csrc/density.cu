@@ -10,9 +10,9 @@
 //   D2 tig_state_kernel    contig k-mer + reverse complement, two probes -> STATE_MER per position
 //   -- host: keep-mask (state count >= 20), N, dense row offsets --
 //   D3 compact_kernel      order-preserving compaction of informative k-mers -> KMER / INDEX / STATE_MER
-//   D4 kde_prepare_kernel  per state: n, mean, var(ddof=1) of INDEX_DEN -> bandwidth L_s and norm_s
-//   D5 runs_kernel         maximal runs of equal STATE_MER in INDEX_DEN space (start, length, state)
-//      kde_tree_kernel     T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both live
+//   D4 runs_stats_kernel   one pass: maximal runs of equal STATE_MER in INDEX_DEN space (start, length, state) and, per
+//                          state, n / mean / var(ddof=1) of INDEX_DEN (exact integer sums) -> bandwidth L_s and norm_s
+//   D5 kde_tree_kernel     T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both live
 //                          on the integer lattice, so N exps replace N * E exps; the table is the leaf level
 //                          of a binary sum tree (node i = node 2i + node 2i+1, all terms positive)
 //   D6 kde_eval_kernel     K_s(j) = norm_s * sum over runs [a,b] of state s of sum_{i=a..b} T_s[|i - j|]; the
@@ -246,56 +246,27 @@ compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig
     }
 }
 
-// D4 ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum_d(double v, double *s_buf)
+// D4 + D5a ---------------------------------------------------------------------------------------
+// One block per window, one pass over STATE_MER (INDEX_DEN = row number):
+//   * maximal runs of equal state, in order, at run_start/run_len/run_state[row_off + r] (ballot compaction);
+//   * per state n, sum(i), sum(i^2) as exact integers -> var(ddof=1) = (n*S2 - S1^2) / (n*(n-1)) with a 128-bit
+//     numerator, bandwidth L_s = sqrt(var) * N^(-1/5) * smooth and norm_s = (2 pi)^(-1/2) / L_s (scipy gaussian_kde:
+//     covariance = np.cov(bias=False) * factor^2, cho_cov = cholesky(cov)).
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *s_buf)
 {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
     __syncthreads();
-    double t = 0.0;
+    unsigned long long t = 0;
     for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += s_buf[q];
     return t;
 }
 
-__global__ void __launch_bounds__(256)
-kde_prepare_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_mer, double smooth, KdeParams *__restrict__ kp)
-{
-    int32_t w = blockIdx.x;
-    const WinPlan P = plan[w];
-    if (!P.smoothed) return;
-    __shared__ double s_buf[8];
-    const int8_t *sm = state_mer + P.row_off;
-    int N = P.n_rows;
-    double bw = pow((double)N, -1.0 / 5.0) * smooth;  // density.py:198
-    for (int s = 0; s < 3; s++) {
-        double n = 0.0, sx = 0.0;
-        for (int i = threadIdx.x; i < N; i += blockDim.x)
-            if (sm[i] == s) { n += 1.0; sx += (double)i; }  // exact: integers below 2^53
-        n = block_sum_d(n, s_buf);
-        sx = block_sum_d(sx, s_buf);
-        double L = 1.0, norm = 0.0;
-        if (n > 0.0) {
-            double mean = sx / n, ss = 0.0;
-            for (int i = threadIdx.x; i < N; i += blockDim.x)
-                if (sm[i] == s) { double dv = (double)i - mean; ss += dv * dv; }
-            ss = block_sum_d(ss, s_buf);
-            double var = ss / (n - 1.0);        // np.cov(bias=False)
-            L = sqrt(var) * bw;                 // cho_cov = cholesky(cov) * factor
-            norm = pow(2.0 * M_PI, -0.5) / L;   // (2 pi)^(-d/2) / cho_cov[0,0]
-        } else {
-            (void)block_sum_d(0.0, s_buf);      // keep barrier counts uniform
-        }
-        if (threadIdx.x == 0) { kp[w].L[s] = L; kp[w].norm[s] = norm; kp[w].n[s] = (int32_t)n; }
-    }
-}
-
-// D5 ---------------------------------------------------------------------------------------------
-// One block per window: maximal runs of equal STATE_MER, in order, at run_start/run_len/run_state[row_off + r].
 __global__ void __launch_bounds__(1024)
-runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_mer, int32_t *__restrict__ run_start,
-            int32_t *__restrict__ run_len, int8_t *__restrict__ run_state, int32_t *__restrict__ n_runs)
+runs_stats_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_mer, double smooth, int32_t *__restrict__ run_start,
+                  int32_t *__restrict__ run_len, int8_t *__restrict__ run_state, int32_t *__restrict__ n_runs, KdeParams *__restrict__ kp)
 {
     int32_t w = blockIdx.x;
     const WinPlan P = plan[w];
@@ -305,11 +276,19 @@ runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_m
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __shared__ int s_warp[32];
     __shared__ int s_base;
+    __shared__ unsigned long long s_buf[32];
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
+    unsigned long long cn[3] = {0, 0, 0}, c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
     for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {   // order-preserving compaction of run heads, 1024 rows per step
         int32_t i = i0 + threadIdx.x;
-        bool head = (i < N) && (i == 0 || sm[i] != sm[i - 1]);
+        int st = (i < N) ? (int)sm[i] : -1;
+        bool head = (i < N) && (i == 0 || st != (int)sm[i - 1]);
+        if (st >= 0) {
+#pragma unroll
+            for (int s = 0; s < 3; s++)
+                if (st == s) { cn[s] += 1; c1[s] += (unsigned long long)i; c2[s] += (unsigned long long)i * (unsigned long long)i; }
+        }
         unsigned bal = __ballot_sync(FULL, head);
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
@@ -318,7 +297,7 @@ runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_m
         if (head) {
             int32_t r = s_base + before + __popc(bal & ((1u << lane) - 1));
             run_start[P.row_off + r] = i;
-            run_state[P.row_off + r] = sm[i];
+            run_state[P.row_off + r] = (int8_t)st;
         }
         __syncthreads();
         if (threadIdx.x == 0) s_base += total;
@@ -331,8 +310,26 @@ runs_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state_m
         run_len[P.row_off + r] = e - a;
     }
     if (threadIdx.x == 0) n_runs[w] = nr;
+    // ---- per-state bandwidths
+    double bw = pow((double)N, -1.0 / 5.0) * smooth;  // density.py:198
+    for (int s = 0; s < 3; s++) {
+        unsigned long long n = block_sum_u64(cn[s], s_buf);
+        unsigned long long S1 = block_sum_u64(c1[s], s_buf);
+        unsigned long long S2 = block_sum_u64(c2[s], s_buf);
+        if (threadIdx.x == 0) {
+            double L = 1.0, norm = 0.0;
+            if (n > 0) {
+                unsigned __int128 num = (unsigned __int128)n * S2 - (unsigned __int128)S1 * S1;   // exact: n*sum(i^2) - sum(i)^2 >= 0
+                double var = (double)num / ((double)n * (double)(n - 1));                        // np.cov(bias=False)
+                L = sqrt(var) * bw;                  // cho_cov = cholesky(cov) * factor
+                norm = pow(2.0 * M_PI, -0.5) / L;    // (2 pi)^(-d/2) / cho_cov[0,0]
+            }
+            kp[w].L[s] = L; kp[w].norm[s] = norm; kp[w].n[s] = (int32_t)n;
+        }
+    }
 }
 
+// D5b ---------------------------------------------------------------------------------------------
 // One block per (window, state): leaves tree[npad + d] = exp(-(d / L)^2 / 2) for d < N (0 beyond), then the
 // internal nodes level by level (node i = node 2i + node 2i+1).
 __global__ void __launch_bounds__(TREE_THREADS)
@@ -570,6 +567,8 @@ struct pavgpu_density_batch {
     int64_t tree_total;
     uint8_t *d_gap_full; int32_t *d_fill_list, *d_n_fill, *d_n_eval; int64_t *d_grp_off;
     bool ran;
+    void *d_arena;    // one allocation backs every device buffer below
+    size_t arena_bytes;
     bool allocated;   // device buffers live for the lifetime of the batch (sized from upper bounds on the first run)
     pavgpu_density_stats stats;
 };
@@ -583,11 +582,8 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_density_default_pa
 
 static void dens_release(pavgpu_density_batch *b)
 {
-    cudaFree(b->d_plan); cudaFree(b->d_wc); cudaFree(b->d_kp); cudaFree(b->d_keys); cudaFree(b->d_counts); cudaFree(b->d_st_pos);
-    cudaFree(b->d_tile_cnt); cudaFree(b->d_kmer); cudaFree(b->d_index); cudaFree(b->d_state_mer); cudaFree(b->d_state);
-    for (int s = 0; s < 3; s++) { cudaFree(b->d_k[s]); cudaFree(b->d_tree[s]); }
-    cudaFree(b->d_run_start); cudaFree(b->d_run_len); cudaFree(b->d_n_runs); cudaFree(b->d_run_state);
-    cudaFree(b->d_gap_full); cudaFree(b->d_fill_list); cudaFree(b->d_n_fill); cudaFree(b->d_n_eval); cudaFree(b->d_grp_off);
+    ctx_arena_give(b->ctx, b->d_arena, b->arena_bytes);   // back to the context cache for the next batch
+    b->d_arena = nullptr;
 }
 
 extern "C" __attribute__((visibility("default"))) void pavgpu_density_batch_free(pavgpu_density_batch *b)
@@ -673,26 +669,31 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     b->stats.bases = bases;
 
     int launches = 0;
-    if (!b->allocated) {   // everything is sized from upper bounds (rows <= contig k-mer positions), so runs never allocate
-        size_t rcap = (size_t)std::max<int64_t>(pos, 1);
-        CUDA_TRY(cudaMalloc(&b->d_plan, sizeof(WinPlan) * n_win));
-        CUDA_TRY(cudaMalloc(&b->d_wc, sizeof(WinCounts) * n_win));
-        CUDA_TRY(cudaMalloc(&b->d_kp, sizeof(KdeParams) * n_win));
-        CUDA_TRY(cudaMalloc(&b->d_keys, sizeof(uint64_t) * std::max<int64_t>(tab, 1)));
-        CUDA_TRY(cudaMalloc(&b->d_counts, sizeof(uint32_t) * std::max<int64_t>(tab, 1)));
-        CUDA_TRY(cudaMalloc(&b->d_st_pos, std::max<int64_t>(pos, 1)));
-        CUDA_TRY(cudaMalloc(&b->d_tile_cnt, sizeof(uint32_t) * 3 * std::max<int64_t>(tiles, 1)));
-        CUDA_TRY(cudaMalloc(&b->d_kmer, rcap * 8)); CUDA_TRY(cudaMalloc(&b->d_index, rcap * 4));
-        CUDA_TRY(cudaMalloc(&b->d_state_mer, rcap)); CUDA_TRY(cudaMalloc(&b->d_state, rcap));
-        for (int s = 0; s < 3; s++) {
-            CUDA_TRY(cudaMalloc(&b->d_k[s], rcap * 8));
-            CUDA_TRY(cudaMalloc(&b->d_tree[s], (size_t)std::max<int64_t>(tree_cap, 1) * 8));
-        }
-        CUDA_TRY(cudaMalloc(&b->d_run_start, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_len, rcap * 4)); CUDA_TRY(cudaMalloc(&b->d_run_state, rcap));
-        CUDA_TRY(cudaMalloc(&b->d_n_runs, sizeof(int32_t) * n_win));
-        CUDA_TRY(cudaMalloc(&b->d_gap_full, rcap)); CUDA_TRY(cudaMalloc(&b->d_fill_list, rcap * 4));
-        CUDA_TRY(cudaMalloc(&b->d_n_fill, sizeof(int32_t) * n_win)); CUDA_TRY(cudaMalloc(&b->d_n_eval, sizeof(int32_t) * n_win));
-        CUDA_TRY(cudaMalloc(&b->d_grp_off, sizeof(int64_t) * (n_win + 1)));
+    if (!b->allocated) {   // everything is sized from upper bounds (rows <= contig k-mer positions), so runs never allocate;
+                           // one arena, one cudaMalloc (a dozen separate allocations cost milliseconds per call)
+        size_t rcap = (size_t)std::max<int64_t>(pos, 1), tcap = (size_t)std::max<int64_t>(tab, 1);
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        size_t o_plan = carve(sizeof(WinPlan) * n_win), o_wc = carve(sizeof(WinCounts) * n_win), o_kp = carve(sizeof(KdeParams) * n_win);
+        size_t o_keys = carve(8 * tcap), o_counts = carve(4 * tcap), o_st = carve(rcap), o_tile = carve(12 * (size_t)std::max<int64_t>(tiles, 1));
+        size_t o_kmer = carve(8 * rcap), o_index = carve(4 * rcap), o_sm = carve(rcap), o_state = carve(rcap);
+        size_t o_k[3], o_tree[3];
+        for (int s = 0; s < 3; s++) { o_k[s] = carve(8 * rcap); o_tree[s] = carve(8 * (size_t)std::max<int64_t>(tree_cap, 1)); }
+        size_t o_rs = carve(4 * rcap), o_rl = carve(4 * rcap), o_rst = carve(rcap), o_nr = carve(4 * (size_t)n_win);
+        size_t o_gap = carve(rcap), o_fill = carve(4 * rcap), o_nf = carve(4 * (size_t)n_win), o_ne = carve(4 * (size_t)n_win);
+        size_t o_grp = carve(8 * ((size_t)n_win + 1));
+        CUDA_TRY(ctx_arena_take(ctx, off, &b->d_arena, &b->arena_bytes));
+        char *base = static_cast<char *>(b->d_arena);
+        b->d_plan = (WinPlan *)(base + o_plan); b->d_wc = (WinCounts *)(base + o_wc); b->d_kp = (KdeParams *)(base + o_kp);
+        b->d_keys = (uint64_t *)(base + o_keys); b->d_counts = (uint32_t *)(base + o_counts); b->d_st_pos = (int8_t *)(base + o_st);
+        b->d_tile_cnt = (uint32_t *)(base + o_tile);
+        b->d_kmer = (uint64_t *)(base + o_kmer); b->d_index = (int32_t *)(base + o_index);
+        b->d_state_mer = (int8_t *)(base + o_sm); b->d_state = (int8_t *)(base + o_state);
+        for (int s = 0; s < 3; s++) { b->d_k[s] = (double *)(base + o_k[s]); b->d_tree[s] = (double *)(base + o_tree[s]); }
+        b->d_run_start = (int32_t *)(base + o_rs); b->d_run_len = (int32_t *)(base + o_rl); b->d_run_state = (int8_t *)(base + o_rst);
+        b->d_n_runs = (int32_t *)(base + o_nr);
+        b->d_gap_full = (uint8_t *)(base + o_gap); b->d_fill_list = (int32_t *)(base + o_fill);
+        b->d_n_fill = (int32_t *)(base + o_nf); b->d_n_eval = (int32_t *)(base + o_ne); b->d_grp_off = (int64_t *)(base + o_grp);
         b->allocated = true;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
@@ -766,9 +767,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-    kde_prepare_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state_mer, b->prm.smooth, b->d_kp);
-    launches++;
-    runs_kernel<<<n_win, 1024, 0, st>>>(b->d_plan, b->d_state_mer, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs);
+    runs_stats_kernel<<<n_win, 1024, 0, st>>>(b->d_plan, b->d_state_mer, b->prm.smooth, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs,
+                                              b->d_kp);
     kde_tree_kernel<<<n_win * 3, TREE_THREADS, 0, st>>>(b->d_plan, b->d_kp, b->d_tree[0], b->d_tree[1], b->d_tree[2]);
     launches += 2;
     CUDA_TRY(cudaGetLastError());

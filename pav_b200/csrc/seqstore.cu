@@ -52,6 +52,7 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_ctx_destroy(pavgpu
     cudaSetDevice(c->device);
     for (auto &e : c->ev) cudaEventDestroy(e);
     cudaFree(c->flush_buf);
+    for (int i = 0; i < pavgpu_ctx::N_CACHE; i++) cudaFree(c->cache_ptr[i]);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -167,7 +168,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
     if (rc) return rc;
     // Stage ASCII in HBM ('N' in the padding so that padding bases get mask = 1), then pack.
     uint8_t *d_ascii = nullptr;
-    cudaError_t e = cudaMalloc(&d_ascii, (size_t)s->total_bases);
+    size_t ascii_cap = 0;
+    cudaError_t e = ctx_arena_take(ctx, (size_t)s->total_bases, reinterpret_cast<void **>(&d_ascii), &ascii_cap);
     if (e != cudaSuccess) {
         pav_set_error("seqstore: cudaMalloc(%lld) for ASCII staging failed: %s", (long long)s->total_bases, cudaGetErrorString(e));
         pavgpu_seqstore_free(s);
@@ -185,7 +187,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return PAVGPU_OK;
     }();
-    cudaFree(d_ascii);
+    ctx_arena_give(ctx, d_ascii, ascii_cap);
     if (rc) { pavgpu_seqstore_free(s); return rc; }
     *out = s;
     return PAVGPU_OK;

@@ -17,3 +17,13 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _built_artifacts():
+    """Build libpavgpu.so / _pyrows.so / the oracle library when they are missing or stale (they normally travel with
+    the tree; nvcc cross-compiles without a GPU, so this also works on the CPU box)."""
+    from oracle import pyoracle
+    from pav_b200 import build
+    build.build()
+    pyoracle.build()

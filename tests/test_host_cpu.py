@@ -15,12 +15,6 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(REPO, 'tests', 'golden')
 
 
-@pytest.fixture(scope='session', autouse=True)
-def built():
-    from pav_b200 import build
-    build.build()
-
-
 def test_capi_exports_match_header():
     hdr = open(os.path.join(REPO, 'include', 'pavgpu.h')).read()
     declared = set(re.findall(r'\b(pavgpu_[a-z0-9_]+)\s*\(', hdr))
