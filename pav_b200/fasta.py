@@ -6,13 +6,86 @@ of the original bytes (case and IUPAC codes preserved) -- they are uploaded to t
 and sliced on the host for the REF / ALT / SEQ columns.
 
 Plain FASTA is memory-mapped and addressed through the samtools ``.fai`` (built in memory when the
-index file is missing). gzip / bgzip files are inflated once per process (any multi-member gzip
-stream; ``.gzi`` random access is not needed because the hot path reads whole records).
+index file is missing). bgzip-compressed FASTA (what PAV's ``data/ref/ref.fa.gz`` is; reference:
+rules/data.snakefile:89-118) is read block-wise: BGZF blocks are located through the ``.gzi`` index or, when it is
+missing, by walking the block headers (no inflation), and only the blocks covering the requested record are inflated
+(in parallel threads; zlib releases the GIL). Plain gzip files are inflated once per process.
 """
 import gzip
 import os
+import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
+
+
+class _Bgzf:
+    """Random access into a BGZF file: ``read(u0, u1)`` returns uncompressed bytes [u0, u1)."""
+
+    def __init__(self, path):
+        self.path = path
+        self.raw = np.memmap(path, dtype=np.uint8, mode='r')
+        self.c_off, self.u_off = self._index()
+
+    @staticmethod
+    def is_bgzf(path):
+        with open(path, 'rb') as fh:
+            h = fh.read(18)
+        return len(h) >= 18 and h[:4] == b'\x1f\x8b\x08\x04' and h[12:14] == b'BC'
+
+    def _index(self):
+        gzi = self.path + '.gzi'
+        if os.path.exists(gzi):
+            with open(gzi, 'rb') as fh:
+                n = struct.unpack('<Q', fh.read(8))[0]
+                arr = np.frombuffer(fh.read(16 * n), dtype='<u8').reshape(n, 2)
+            c = np.concatenate(([0], arr[:, 0])).astype(np.int64)
+            u = np.concatenate(([0], arr[:, 1])).astype(np.int64)
+            return c, u
+        # no .gzi: walk the block headers (BSIZE in the 'BC' extra field, ISIZE in the trailer)
+        c, u, pos, upos, n = [], [], 0, 0, len(self.raw)
+        raw = self.raw
+        while pos + 18 <= n:
+            bsize = int(raw[pos + 16]) | (int(raw[pos + 17]) << 8)
+            isize = int.from_bytes(bytes(raw[pos + bsize - 3:pos + bsize + 1]), 'little')
+            c.append(pos)
+            u.append(upos)
+            pos += bsize + 1
+            upos += isize
+        return np.array(c, dtype=np.int64), np.array(u, dtype=np.int64)
+
+    def _inflate(self, lo, hi):
+        """Inflate blocks lo..hi-1 (concatenated gzip members)."""
+        c0 = int(self.c_off[lo])
+        c1 = int(self.c_off[hi]) if hi < len(self.c_off) else len(self.raw)
+        d = zlib.decompressobj(31)
+        data = bytes(self.raw[c0:c1])
+        out = []
+        while data:
+            out.append(d.decompress(data))
+            data = d.unused_data
+            if not data:
+                break
+            d = zlib.decompressobj(31)
+        return b''.join(out)
+
+    def read(self, u0, u1):
+        if u1 <= u0:
+            return b''
+        lo = int(np.searchsorted(self.u_off, u0, side='right')) - 1
+        hi = int(np.searchsorted(self.u_off, u1 - 1, side='right'))
+        n_blk = hi - lo
+        if n_blk > 64:   # ~64 KiB per block: split into ~4 MiB jobs
+            step = 64
+            jobs = [(a, min(a + step, hi)) for a in range(lo, hi, step)]
+            with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
+                parts = list(pool.map(lambda ab: self._inflate(*ab), jobs))
+            data = b''.join(parts)
+        else:
+            data = self._inflate(lo, hi)
+        start = u0 - int(self.u_off[lo])
+        return data[start:start + (u1 - u0)]
 
 _CACHE = {}
 
@@ -21,12 +94,16 @@ class Fasta:
     def __init__(self, path):
         self.path = path
         self._plain = not str(path).endswith('.gz')
+        self._bgzf = None
         if self._plain:
             self._buf = np.memmap(path, dtype=np.uint8, mode='r') if os.path.getsize(path) else np.zeros(0, np.uint8)
+        elif os.path.exists(path + '.fai') and _Bgzf.is_bgzf(path):
+            self._bgzf = _Bgzf(path)      # block-wise access; nothing is inflated until a record is fetched
+            self._buf = None
         else:
             with gzip.open(path, 'rb') as fh:
                 self._buf = np.frombuffer(fh.read(), dtype=np.uint8)
-        self.index = self._read_fai() if (self._plain and os.path.exists(path + '.fai')) else self._scan_index()
+        self.index = self._read_fai() if os.path.exists(path + '.fai') and (self._plain or self._bgzf) else self._scan_index()
         self._seq_cache = {}
 
     def _read_fai(self):
@@ -89,8 +166,12 @@ class Fasta:
             return self._seq_cache[name]
         first_line, last_line = start // linebases, (end - 1) // linebases
         b0 = offset + first_line * linewidth
-        b1 = min(offset + last_line * linewidth + linebases, len(self._buf))
-        raw = np.asarray(self._buf[b0:b1])
+        if self._bgzf is not None:
+            b1 = offset + last_line * linewidth + linebases
+            raw = np.frombuffer(self._bgzf.read(b0, b1), dtype=np.uint8)
+        else:
+            b1 = min(offset + last_line * linewidth + linebases, len(self._buf))
+            raw = np.asarray(self._buf[b0:b1])
         n_lines = last_line - first_line + 1
         if n_lines == 1:
             seq = raw

@@ -400,3 +400,31 @@ def write_sam(path, df_align, ref, soft_clip_every=2, extra_lines=()):
         for line in extra_lines:
             fh.write(line.rstrip('\n') + '\n')
     return path
+
+
+def write_bgzf(path, data, block=0xff00, write_gzi=True):
+    """Write ``data`` (bytes) as a BGZF file (the container bgzip produces) and, optionally, its ``.gzi`` index."""
+    import struct
+    import zlib
+    entries = []
+    c_off = u_off = 0
+    with open(path, 'wb') as fh:
+        for i in range(0, max(len(data), 1), block):
+            chunk = data[i:i + block]
+            if i > 0:
+                entries.append((c_off, u_off))
+            comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = comp.compress(chunk) + comp.flush()
+            bsize = len(body) + 25
+            blk = (b'\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00' + struct.pack('<H', bsize) + body +
+                   struct.pack('<II', zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+            fh.write(blk)
+            c_off += len(blk)
+            u_off += len(chunk)
+        fh.write(bytes.fromhex('1f8b08040000000000ff0600424302001b0003000000000000000000'))  # EOF marker block
+    if write_gzi:
+        with open(path + '.gzi', 'wb') as fh:
+            fh.write(struct.pack('<Q', len(entries)))
+            for c, u in entries:
+                fh.write(struct.pack('<QQ', c, u))
+    return path

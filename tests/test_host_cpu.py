@@ -240,3 +240,24 @@ def test_count_cigar_and_check_record():
     row['END'] = 35
     with pytest.raises(RuntimeError, match='END mismatch'):
         align.check_record(row, pd.Series({'q': 31}))
+
+
+def test_fasta_bgzf_random_access(tmp_path):
+    """bgzip-compressed FASTA + .fai (+/- .gzi): only the blocks of the requested record are inflated."""
+    import gzip
+    import shutil
+    rng = np.random.default_rng(4)
+    seqs = {'chrA': synth.random_seq(rng, 300_000), 'chrB': synth.random_seq(rng, 7), 'chrC': synth.random_seq(rng, 150_001)}
+    plain = synth.write_fasta(str(tmp_path / 'g.fa'), seqs, line_width=60)
+    data = open(plain, 'rb').read()
+    for with_gzi in (True, False):
+        gz = str(tmp_path / f'g{int(with_gzi)}.fa.gz')
+        synth.write_bgzf(gz, data, write_gzi=with_gzi)
+        shutil.copy(plain + '.fai', gz + '.fai')
+        assert gzip.open(gz, 'rb').read() == data      # a valid multi-member gzip stream
+        fa = fasta.Fasta(gz)
+        assert fa._bgzf is not None and fa._buf is None
+        for n, s in seqs.items():
+            assert (fa.fetch_array(n) == s).all()
+        assert fa.fetch('chrA', 65_000, 66_500) == seqs['chrA'][65_000:66_500].tobytes().decode()
+        assert fa.fetch('chrC', 149_990, 150_001) == seqs['chrC'][149_990:].tobytes().decode()
