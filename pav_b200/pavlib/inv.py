@@ -110,136 +110,193 @@ def _write_log(message, log):
     log.flush()
 
 
+class _InvScan:
+    """State machine of one flagged locus: the body of the reference's ``scan_for_inv`` loop (pavlib/inv.py:149-454) cut
+    at the point where it needs a density table, so one locus (``scan_for_inv``) or many loci per GPU batch
+    (``scan_for_inv_batch``) share the same control flow, log lines and stop rules."""
+
+    def __init__(self, region_flag, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree, max_region_size, log, srs_tree, min_exp_count,
+                 df_fai=None):
+        self.region_flag = region_flag
+        self.ref_fa_name, self.tig_fa_name = ref_fa_name, tig_fa_name
+        self.align_lift, self.k_util, self.log = align_lift, k_util, log
+        self.k_size = int(k_util.k_size)
+        self.min_exp_count = DEFAULT_MIN_EXP_COUNT if min_exp_count is None else min_exp_count
+        self.max_region_size = MAX_REGION_SIZE if max_region_size is None else max_region_size
+        _write_log('Scanning for inversions in flagged region: {} (flagged region record id = {})'.format(
+            region_flag, region_flag.region_id()), log)
+        self.df_fai = pavseq.get_df_fai(ref_fa_name + '.fai') if df_fai is None else df_fai
+        self.region_ref = region_flag.copy()
+        self.region_ref.expand(INITIAL_EXPAND, min_pos=0, max_end=self.df_fai, shift=True)
+        self.expansion_count = 0
+        self.n_tree_chrom = n_tree[self.region_ref.chrom] if (n_tree is not None and self.region_ref.chrom in n_tree.keys()) else None
+        if srs_tree is None:
+            srs_tree = get_srs_tree(None)
+        elif not hasattr(srs_tree, '__getitem__'):
+            raise NotImplementedError('Custom state-run-smooth parameters are not currently implemented')
+        self.srs_tree = srs_tree
+        self.region_tig = None
+        self.done = False
+        self.result = None
+
+    def _finish(self, result):
+        self.done, self.result = True, result
+        return None
+
+    def next_window(self):
+        """Next ``(region_ref, region_tig, rev, srs)`` to score, or ``None`` when the scan has ended (see ``result``)."""
+        log, region_ref = self.log, self.region_ref
+        if 0 < self.max_region_size < len(region_ref):
+            _write_log('Region size exceeds max: {} ({} > {})'.format(region_ref, len(region_ref), self.max_region_size), log)
+            return self._finish(None)
+        if self.n_tree_chrom is not None and len(self.n_tree_chrom[region_ref.pos:region_ref.end]) > 0:
+            _write_log('Region overlaps N bases: {}'.format(region_ref), log)  # logged only, as in the reference
+        self.region_tig = self.align_lift.lift_region_to_qry(region_ref)
+        if self.region_tig is None:
+            _write_log('Could not lift reference region onto contigs: {}'.format(region_ref), log)
+            return self._finish(None)
+        self.expansion_count += 1
+        _write_log('Scanning region: {}'.format(region_ref), log)
+        srs = list(self.srs_tree[len(self.region_tig)])[0].data
+        return region_ref, self.region_tig, bool(self.region_tig.is_rev), int(srs)
+
+    def feed(self, returncode, df):
+        """Consume the density table of the window handed out last; afterwards either ``done`` or ready for ``next_window``."""
+        log, region_ref = self.log, self.region_ref
+        if returncode != 0:
+            _write_log('Received return code {} from the density scan for region {}:\n'.format(returncode, str(region_ref)), log)
+            if returncode != ERR_INV_FAIL:
+                raise RuntimeError('Density scan failed with code {} for region {}'.format(returncode, region_ref))
+            return self._finish(None)
+        if df.shape[0] == 0:
+            _write_log('No informative reference k-mers in forward or reverse orientation in region', log)
+            return self._finish(None)
+        state_rl = [record for record in pavdensity.rl_encoder(df)]
+        condensed_states = [record[0] for record in state_rl]
+        if len(state_rl) == 1 and state_rl[0][0] in {0, -1} and self.expansion_count >= self.min_exp_count:
+            _write_log('Found no inverted k-mer states after {} expansion(s)'.format(self.expansion_count), log)
+            return self._finish(None)
+        if len(condensed_states) > 2 and condensed_states[0] == 0 and condensed_states[-1] == 0:
+            return self._finish(self._characterise(df, state_rl))
+        last_len = len(region_ref)
+        expand_bp = np.int32(len(region_ref) * EXPAND_FACTOR)
+        if len(condensed_states) > 2:
+            balance = 0.25 if condensed_states[0] == 0 else (0.75 if condensed_states[-1] == 0 else 0.5)
+        else:
+            balance = 0.5
+        region_ref.expand(expand_bp, min_pos=0, max_end=self.df_fai, shift=True, balance=balance)
+        if len(region_ref) == last_len:
+            _write_log('Reached reference limits, cannot expand', log)
+            return self._finish(None)
+        return None
+
+    def _characterise(self, df, state_rl):
+        """Breakpoints, size-proportion test, flank annotation (pavlib/inv.py:346-454)."""
+        log, region_ref, region_tig, k_size, align_lift = self.log, self.region_ref, self.region_tig, self.k_size, self.align_lift
+        if not np.any([record[0] == 2 for record in state_rl]):
+            _write_log('No inverted states found', log)
+            return None
+        max_inv_run = np.max([record[1] for record in state_rl if record[0] == 2])
+        if max_inv_run < MIN_INV_KMER_RUN:
+            _write_log('Longest run of strictly inverted k-mers ({}) does not meet the minimum threshold ({})'.format(
+                max_inv_run, MIN_INV_KMER_RUN), log)
+            return None
+        if state_rl[0][0] != 0 or state_rl[-1][0] != 0:
+            raise RuntimeError('Found INV region not flanked by reference sequence (program bug): {}'.format(region_ref))
+        state_rl_inv = [record for record in state_rl if record[0] == 2]
+        region_tig_outer = pavseq.Region(region_tig.chrom, state_rl[1][2] + region_tig.pos,
+                                         state_rl[-2][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
+        region_tig_inner = pavseq.Region(region_tig.chrom, state_rl_inv[0][2] + region_tig.pos,
+                                         state_rl_inv[-1][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
+        region_ref_outer = align_lift.lift_region_to_sub(region_tig_outer)
+        if region_ref_outer is None:
+            _write_log('Failed lifting outer INV region to reference: {}'.format(region_tig_outer), log)
+            return None
+        region_ref_inner = align_lift.lift_region_to_sub(region_tig_inner, gap=True)
+        if region_ref_inner is None:
+            region_ref_inner = region_ref_outer
+        print('INV Found: outer={}, inner={} (ref outer={}, inner={})'.format(
+            region_tig_outer, region_tig_inner, region_ref_outer, region_ref_inner))
+        if len(region_ref_outer) < len(region_tig_outer) * MIN_QRY_REF_PROP:
+            _write_log('Reference region too short: Reference region length ({:,d}) is not within {:.2f}% of the contig region length ({:,d})'.format(
+                len(region_ref_outer), MIN_QRY_REF_PROP * 100, len(region_tig_outer)), log)
+            return None
+        if len(region_tig_outer) < len(region_ref_outer) * MIN_QRY_REF_PROP:
+            _write_log('Contig region too short: Contig region length ({:,d}) is not within {:.2f}% of the reference region length ({:,d})'.format(
+                len(region_tig_outer), MIN_QRY_REF_PROP * 100, len(region_ref_outer)), log)
+            return None
+        # NOTE: the reference passes region_ref where annotate_inv_dup_mers expects the contig discovery region
+        # (pavlib/inv.py:440-442); reproduced as is.
+        df = annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref,
+                                   self.ref_fa_name, self.k_util)
+        inv_call = InvCall(region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref, region_tig,
+                           self.region_flag, df)
+        _write_log('Found inversion: {}'.format(inv_call), log)
+        return inv_call
+
+
 def scan_for_inv(region_flag, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree=None, max_region_size=None, threads=1,
                  log=None, srs_tree=None, min_exp_count=DEFAULT_MIN_EXP_COUNT):
     """
     Scan a flagged region for an inversion, expanding as necessary.
 
-    Same parameters and return value as the reference (``InvCall`` or ``None``). ``k_util`` only needs a
-    ``k_size`` attribute; ``threads`` is accepted and ignored (the window is scored on the GPU);
-    ``align_lift`` needs ``lift_region_to_qry`` / ``lift_region_to_sub`` (the reference's AlignLift or
-    ``pav_b200.pavlib.lift.AlignLift``).
+    Same parameters and return value as the reference (``InvCall`` or ``None``, pavlib/inv.py:149-454). ``k_util`` only
+    needs a ``k_size`` attribute; ``threads`` is accepted and ignored (the window is scored on the GPU); ``align_lift``
+    needs ``lift_region_to_qry`` / ``lift_region_to_sub`` (the reference's AlignLift or ``pav_b200.pavlib.lift.AlignLift``).
+    Each expansion scores its window through ``pavgpu_density_batch_*`` in-process instead of spawning
+    ``python3 scripts/density.py`` and unpickling its stdout (pavlib/inv.py:249-288).
     """
-    if min_exp_count is None:
-        min_exp_count = DEFAULT_MIN_EXP_COUNT
-    if max_region_size is None:
-        max_region_size = MAX_REGION_SIZE
-    k_size = int(k_util.k_size)
-
-    _write_log('Scanning for inversions in flagged region: {} (flagged region record id = {})'.format(
-        region_flag, region_flag.region_id()), log)
-
-    df_fai = pavseq.get_df_fai(ref_fa_name + '.fai')
-    region_ref = region_flag.copy()
-    region_ref.expand(INITIAL_EXPAND, min_pos=0, max_end=df_fai, shift=True)
-    expansion_count = 0
-
-    n_tree_chrom = n_tree[region_ref.chrom] if (n_tree is not None and region_ref.chrom in n_tree.keys()) else None
-    if srs_tree is None:
-        srs_tree = get_srs_tree(None)
-    elif not hasattr(srs_tree, '__getitem__'):
-        raise NotImplementedError('Custom state-run-smooth parameters are not currently implemented')
-
-    while True:
-        if 0 < max_region_size < len(region_ref):
-            _write_log('Region size exceeds max: {} ({} > {})'.format(region_ref, len(region_ref), max_region_size), log)
-            return None
-        if n_tree_chrom is not None and len(n_tree_chrom[region_ref.pos:region_ref.end]) > 0:
-            _write_log('Region overlaps N bases: {}'.format(region_ref), log)  # logged only, as in the reference
-
-        region_tig = align_lift.lift_region_to_qry(region_ref)
-        if region_tig is None:
-            _write_log('Could not lift reference region onto contigs: {}'.format(region_ref), log)
-            return None
-        expansion_count += 1
-        _write_log('Scanning region: {}'.format(region_ref), log)
-
-        srs = list(srs_tree[len(region_tig)])[0].data
+    scan = _InvScan(region_flag, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree, max_region_size, log, srs_tree, min_exp_count)
+    while not scan.done:
+        win = scan.next_window()
+        if win is None:
+            break
+        region_ref, region_tig, rev, srs = win
         returncode, df = pavdensity.density_table(
-            region_ref, region_tig, ref_fa_name, tig_fa_name, k=k_size, rev=bool(region_tig.is_rev), state_run_smooth=int(srs),
+            region_ref, region_tig, ref_fa_name, tig_fa_name, k=scan.k_size, rev=rev, state_run_smooth=srs,
             min_informative=MIN_INFORMATIVE_KMERS, min_state_count=MIN_KMER_STATE_COUNT, smooth=DENSITY_SMOOTH_FACTOR)
-        if returncode != 0:
-            _write_log('Received return code {} from the density scan for region {}:\n'.format(returncode, str(region_ref)), log)
-            if returncode != ERR_INV_FAIL:
-                raise RuntimeError('Density scan failed with code {} for region {}'.format(returncode, region_ref))
-            return None
+        scan.feed(returncode, df)
+    return scan.result
 
-        if df.shape[0] > 0:
-            state_rl = [record for record in pavdensity.rl_encoder(df)]
-            condensed_states = [record[0] for record in state_rl]
 
-            if len(state_rl) == 1 and state_rl[0][0] in {0, -1} and expansion_count >= min_exp_count:
-                _write_log('Found no inverted k-mer states after {} expansion(s)'.format(expansion_count), log)
-                return None
+def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree=None, max_region_size=None, log=None,
+                       srs_tree=None, min_exp_count=DEFAULT_MIN_EXP_COUNT):
+    """
+    ``scan_for_inv`` for many flagged loci at once (extension; the reference scans one locus per call,
+    rules/call_inv.snakefile:191-196). All loci that still need a density table are scored together in one GPU batch per
+    expansion round, so a Snakemake batch of thousands of 50 kbp windows costs a handful of launches instead of one
+    ``scripts/density.py`` process per window and expansion.
 
-            if len(condensed_states) > 2 and condensed_states[0] == 0 and condensed_states[-1] == 0:
-                break
-
-            last_len = len(region_ref)
-            expand_bp = np.int32(len(region_ref) * EXPAND_FACTOR)
-            if len(condensed_states) > 2:
-                if condensed_states[0] == 0:
-                    balance = 0.25
-                elif condensed_states[-1] == 0:
-                    balance = 0.75
-                else:
-                    balance = 0.5
+    :return: list with one ``InvCall`` or ``None`` per flagged region, identical to calling ``scan_for_inv`` on each.
+    """
+    from .. import fasta as _fasta
+    df_fai = pavseq.get_df_fai(ref_fa_name + '.fai')
+    scans = [_InvScan(r, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree, max_region_size, log, srs_tree, min_exp_count, df_fai=df_fai)
+             for r in region_flags]
+    ref_fa, tig_fa = _fasta.open_fasta(ref_fa_name), _fasta.open_fasta(tig_fa_name)
+    k_size = int(k_util.k_size)
+    while True:
+        pending, windows = [], []
+        for sc in scans:
+            if sc.done:
+                continue
+            win = sc.next_window()
+            if win is None:
+                continue
+            region_ref, region_tig, rev, srs = win
+            windows.append((ref_fa.fetch_array(region_ref.chrom, region_ref.pos, region_ref.end),
+                            tig_fa.fetch_array(region_tig.chrom, region_tig.pos, region_tig.end), rev, srs))
+            pending.append(sc)
+        if not pending:
+            break
+        results = pavdensity.density_windows(windows, k=k_size, min_informative=MIN_INFORMATIVE_KMERS,
+                                             min_state_count=MIN_KMER_STATE_COUNT, smooth=DENSITY_SMOOTH_FACTOR)
+        for sc, res in zip(pending, results):
+            if res['status'] != 0:
+                sc.feed(ERR_INV_FAIL, None)
             else:
-                balance = 0.5
-            region_ref.expand(expand_bp, min_pos=0, max_end=df_fai, shift=True, balance=balance)
-            if len(region_ref) == last_len:
-                _write_log('Reached reference limits, cannot expand', log)
-                return None
-        else:
-            _write_log('No informative reference k-mers in forward or reverse orientation in region', log)
-            return None
-
-    # ---- characterise the found region (pavlib/inv.py:346-454)
-    if not np.any([record[0] == 2 for record in state_rl]):
-        _write_log('No inverted states found', log)
-        return None
-    max_inv_run = np.max([record[1] for record in state_rl if record[0] == 2])
-    if max_inv_run < MIN_INV_KMER_RUN:
-        _write_log('Longest run of strictly inverted k-mers ({}) does not meet the minimum threshold ({})'.format(
-            max_inv_run, MIN_INV_KMER_RUN), log)
-        return None
-    if state_rl[0][0] != 0 or state_rl[-1][0] != 0:
-        raise RuntimeError('Found INV region not flanked by reference sequence (program bug): {}'.format(region_ref))
-    state_rl_inv = [record for record in state_rl if record[0] == 2]
-
-    region_tig_outer = pavseq.Region(region_tig.chrom, state_rl[1][2] + region_tig.pos,
-                                     state_rl[-2][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
-    region_tig_inner = pavseq.Region(region_tig.chrom, state_rl_inv[0][2] + region_tig.pos,
-                                     state_rl_inv[-1][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
-
-    region_ref_outer = align_lift.lift_region_to_sub(region_tig_outer)
-    if region_ref_outer is None:
-        _write_log('Failed lifting outer INV region to reference: {}'.format(region_tig_outer), log)
-        return None
-    region_ref_inner = align_lift.lift_region_to_sub(region_tig_inner, gap=True)
-    if region_ref_inner is None:
-        region_ref_inner = region_ref_outer
-
-    print('INV Found: outer={}, inner={} (ref outer={}, inner={})'.format(
-        region_tig_outer, region_tig_inner, region_ref_outer, region_ref_inner))
-
-    if len(region_ref_outer) < len(region_tig_outer) * MIN_QRY_REF_PROP:
-        _write_log('Reference region too short: Reference region length ({:,d}) is not within {:.2f}% of the contig region length ({:,d})'.format(
-            len(region_ref_outer), MIN_QRY_REF_PROP * 100, len(region_tig_outer)), log)
-        return None
-    if len(region_tig_outer) < len(region_ref_outer) * MIN_QRY_REF_PROP:
-        _write_log('Contig region too short: Contig region length ({:,d}) is not within {:.2f}% of the reference region length ({:,d})'.format(
-            len(region_tig_outer), MIN_QRY_REF_PROP * 100, len(region_ref_outer)), log)
-        return None
-
-    # NOTE: the reference passes region_ref where annotate_inv_dup_mers expects the contig discovery region
-    # (pavlib/inv.py:440-442); reproduced as is.
-    df = annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref,
-                               ref_fa_name, k_util)
-    inv_call = InvCall(region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref, region_tig,
-                       region_flag, df)
-    _write_log('Found inversion: {}'.format(inv_call), log)
-    return inv_call
+                sc.feed(0, pavdensity.frame_from_result(res))
+    return [sc.result for sc in scans]
 
 
 _CODE = np.full(256, 255, dtype=np.uint8)

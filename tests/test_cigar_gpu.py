@@ -150,3 +150,22 @@ def test_seqstore_pack_roundtrip():
         exp_code = np.searchsorted(np.frombuffer(b'ACGT', np.uint8), up[~exp_n])
         assert (code[~exp_n] == exp_code).all()
     st.close()
+
+
+def test_multipass_walk_matches_single_pass(tmp_path, monkeypatch):
+    """The three-kernel walk (kept for oversized batches, PAVGPU_CIGAR_MULTIPASS=1) gives the same DataFrames as the
+    single-pass kernel and as the oracle."""
+    from oracle import pyoracle
+    from pav_b200.pavlib import cigarcall
+    ref_fa, tig_fa, df = _workload(tmp_path, 15, n_chrom=2, chrom_len=300_000, n_contig=25, contig_len=24_000, edit_rate=0.012,
+                                   rev_frac=0.5, clip=(4, 2))
+    single = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
+    assert cigarcall.last_stats['kernel_launches'] == 2
+    monkeypatch.setenv('PAVGPU_CIGAR_MULTIPASS', '1')
+    multi = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
+    assert cigarcall.last_stats['kernel_launches'] == 4
+    monkeypatch.delenv('PAVGPU_CIGAR_MULTIPASS')
+    orc = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
+    for a, b, c in zip(single, multi, orc):
+        assert tsv_bytes(a) == tsv_bytes(b) == tsv_bytes(c)
+        assert (a.index == b.index).all() and (a.index == c.index).all()

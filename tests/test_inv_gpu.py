@@ -65,3 +65,33 @@ def test_scan_for_inv_negative_and_limits(tmp_path):
     log = io.StringIO()
     assert inv.scan_for_inv(seq.Region('chr1', 18_000, 22_000), ref_fa, tig_fa, al, _K(31), log=log, max_region_size=5000) is None
     assert 'Region size exceeds max' in log.getvalue()
+
+
+def test_scan_for_inv_batch_equals_single(tmp_path):
+    """Many flagged loci scored per GPU batch give the same calls as one scan_for_inv per locus."""
+    from pav_b200 import synth
+    from pav_b200.pavlib import inv, lift, seq
+    rng = np.random.default_rng(77)
+    n = 400_000
+    s = synth.random_seq(rng, n)
+    t = s.copy()
+    flags, truth = [], []
+    for i, start in enumerate(range(20_000, n - 60_000, 60_000)):
+        ln = int(rng.integers(3000, 9000))
+        if i % 3 != 2:                      # two of three loci carry an inversion
+            t[start:start + ln] = synth.revcomp(s[start:start + ln])
+        flags.append(seq.Region('chr1', start + ln // 3, start + 2 * ln // 3))
+        truth.append(i % 3 != 2)
+    ref_fa = synth.write_fasta(str(tmp_path / 'ref.fa'), {'chr1': s})
+    tig_fa = synth.write_fasta(str(tmp_path / 'tig.fa'), {'tig1': t})
+    df_align = pd.DataFrame([('chr1', 0, n, 0, 'tig1', 0, n, n, False, f'{n}=')],
+                            columns=['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END', 'QRY_LEN', 'REV', 'CIGAR'])
+    al = lift.AlignLift(df_align, seq.get_df_fai(tig_fa + '.fai'))
+    batch = inv.scan_for_inv_batch(flags, ref_fa, tig_fa, al, _K(31))
+    single = [inv.scan_for_inv(f, ref_fa, tig_fa, al, _K(31)) for f in flags]
+    assert len(batch) == len(flags)
+    for b, s1, has_inv in zip(batch, single, truth):
+        assert (b is None) == (s1 is None) == (not has_inv)
+        if b is not None:
+            assert b.id == s1.id and str(b.region_ref_inner) == str(s1.region_ref_inner) and str(b.region_tig_outer) == str(s1.region_tig_outer)
+            assert b.df.shape == s1.df.shape and (b.df['STATE'].to_numpy() == s1.df['STATE'].to_numpy()).all()
