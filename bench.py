@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument('--contig-len', type=int, default=200_000)
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--cpu-sample-contigs', type=int, default=0, help='contigs in the CPU baseline sample (0 = 4 per core)')
-    ap.add_argument('--density-windows', type=int, default=48, help='windows in the secondary Path-B measurement (0 = skip)')
+    ap.add_argument('--density-windows', type=int, default=296, help='windows in the secondary Path-B measurement (0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--seed', type=int, default=1002)
     return ap.parse_args()

@@ -545,12 +545,59 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 }
 
 // K4 ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// Thread per indel, but the assignment of indels to threads is re-sorted inside the CTA first: a one-window probe on
+// each side of the breakpoint (uniform cost) tells indels sitting in tandem repeats / homopolymers (scans of hundreds
+// of bases, ~20 % of the C2 indels) from ordinary ones (scans end within a few bases); the CTA then hands the light
+// indels to its first warps and the heavy ones to its last warps, so a warp's lanes run scans of similar length
+// instead of 26 idle lanes waiting for 6 long scans.
+constexpr int HOM_THREADS = 256;
+
+__global__ void __launch_bounds__(HOM_THREADS, 4)
 homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, RecView rv, SeqPlanes ref, SeqPlanes qry,
-                pavgpu_indel_row *__restrict__ rows)
+                pavgpu_indel_row *__restrict__ rows, int do_sort)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_indel) return;
+    __shared__ int s_perm[HOM_THREADS];
+    __shared__ int s_wl[HOM_THREADS / 32], s_wh[HOM_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t block_base = (int64_t)blockIdx.x * HOM_THREADS;
+    if (!do_sort) {
+        s_perm[tid] = (block_base + tid < n_indel) ? tid : -1;
+    } else {   // ---- phase A: probe + stable partition (light first, heavy last)
+        int64_t i0 = block_base + tid;
+        bool valid = i0 < n_indel, heavy = false;
+        if (valid) {
+            const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i0);
+            int4 a = __ldg(sp4), b = __ldg(sp4 + 1);
+            int32_t rec = a.x, svtype = a.z, n = a.w, pr = b.x, pq = b.y;
+            int32_t rid = __ldg(rv.ref_id + rec), qid = __ldg(rv.qry_id + rec);
+            OSeq R{ref.pack2, ref.nmask, __ldg(ref.off + rid), __ldg(ref.len + rid), 0};
+            OSeq Q{qry.pack2, qry.nmask, __ldg(qry.off + qid), __ldg(qry.len + qid), (int)__ldg(rv.rev + rec)};
+            const bool ins = (svtype == 0);
+            const OSeq &V = ins ? Q : R;
+            const int64_t v0 = ins ? (int64_t)pq : (int64_t)pr;
+            int64_t lim = n < 32 ? n : 32;
+            int64_t hl = common_extension(R, (int64_t)pr - 1, V, v0 + n - 1, lim, 1);
+            int64_t hr = common_extension(R, ins ? (int64_t)pr : (int64_t)pr + n, V, v0, lim, 0);
+            heavy = (hl >= lim) || (hr >= lim) || (hl + hr >= 16);
+        }
+        unsigned bl = __ballot_sync(FULL, valid && !heavy), bh = __ballot_sync(FULL, valid && heavy);
+        if (lane == 0) { s_wl[wid] = __popc(bl); s_wh[wid] = __popc(bh); }
+        s_perm[tid] = -1;
+        __syncthreads();
+        int light_before = 0, heavy_before = 0, n_light = 0;
+        for (int q = 0; q < HOM_THREADS / 32; q++) {
+            if (q < wid) { light_before += s_wl[q]; heavy_before += s_wh[q]; }
+            n_light += s_wl[q];
+        }
+        unsigned below = (1u << lane) - 1;
+        if (valid && !heavy) s_perm[light_before + __popc(bl & below)] = tid;
+        if (valid && heavy) s_perm[n_light + heavy_before + __popc(bh & below)] = tid;
+        __syncthreads();
+    }
+    // ---- phase B: this thread now owns indel s_perm[tid] of the CTA
+    const int j = s_perm[tid];
+    if (j < 0) return;
+    const int64_t i = block_base + j;
     const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
     int4 a = __ldg(sp4), b = __ldg(sp4 + 1);
     int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
@@ -647,6 +694,7 @@ struct pavgpu_cigar_batch {
     int64_t *d_rec_snv_off, *d_rec_indel_off;   // first row slot of every record (host-counted)
     int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (host-built index)
     bool fused;
+    int hom_sort;   // re-sort indels inside each CTA by a one-window probe (PAVGPU_HOM_SORT, default off: see DESIGN.md 6.1)
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
@@ -761,6 +809,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
     }
     // single-pass walk unless the descriptor fields would overflow (33-bit SNV count, 30-bit indel count) or the
     // multi-pass kernels are requested for A/B timing
+    const char *hs = getenv("PAVGPU_HOM_SORT");
+    b->hom_sort = (hs && hs[0] == '1') ? 1 : 0;
     const char *mp = getenv("PAVGPU_CIGAR_MULTIPASS");
     b->fused = !(mp && mp[0] == '1') && b->host_n_snv < ((int64_t)1 << 33) && b->host_n_indel < ((int64_t)1 << 30);
     size_t ops_padded = (size_t)std::max<int64_t>(b->n_chunks, 1) * CHUNK;
@@ -839,8 +889,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         b->n_snv = b->host_n_snv; b->n_indel = b->host_n_indel;
         if (b->n_indel > 0) {
-            unsigned hb = (unsigned)((b->n_indel + 127) / 128);
-            homology_kernel<<<hb, 128, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel);
+            unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
+            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel, b->hom_sort);
             launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -883,8 +933,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         if (b->n_indel > 0) {
-            unsigned hb = (unsigned)((b->n_indel + 127) / 128);
-            homology_kernel<<<hb, 128, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel);
+            unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
+            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel, b->hom_sort);
             launches++;
             CUDA_TRY(cudaGetLastError());
         }
