@@ -130,15 +130,31 @@ def check(rc, what='pavgpu'):
         raise RuntimeError(f'{what} failed (code {rc}): {msg}')
 
 
+class _HostBuffer:
+    """Owner of a library-allocated host buffer (pinned memory from the context's pool, see pavgpu_free_host): numpy arrays
+    created over it keep it alive through ``.base``; the buffer goes back to the library when the last view dies."""
+
+    def __init__(self, address, nbytes):
+        self._address = address
+        self.__array_interface__ = {'data': (address, False), 'shape': (nbytes,), 'typestr': '|u1', 'version': 3}
+
+    def __del__(self):
+        addr, self._address = self._address, None
+        if addr:
+            try:
+                lib().pavgpu_free_host(addr)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+
+
 def take_host_array(ptr, n, dtype):
-    """Copy a library-allocated host buffer into a numpy array and release it."""
+    """Wrap a library-allocated host buffer as a numpy array without copying; it is released with the array."""
     dtype = np.dtype(dtype)
-    out = np.empty(n, dtype=dtype)
-    if n and ptr:
-        ctypes.memmove(out.ctypes.data, ptr, n * dtype.itemsize)
-    if ptr:
-        lib().pavgpu_free_host(ptr)
-    return out
+    if not ptr or n == 0:
+        if ptr:
+            lib().pavgpu_free_host(ptr)
+        return np.empty(0, dtype=dtype)
+    return np.asarray(_HostBuffer(ptr, n * dtype.itemsize)).view(dtype)
 
 
 def ptr(arr):

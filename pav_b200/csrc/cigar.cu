@@ -21,6 +21,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_pipeline.h>
+
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
@@ -35,10 +39,44 @@ constexpr uint32_t REF_ADV_MASK = (1u << PAVGPU_OP_D) | (1u << PAVGPU_OP_EQ) | (
 constexpr uint32_t QRY_ADV_MASK = (1u << PAVGPU_OP_I) | (1u << PAVGPU_OP_S) | (1u << PAVGPU_OP_H) | (1u << PAVGPU_OP_EQ) | (1u << PAVGPU_OP_X);
 constexpr uint32_t LEGAL_MASK = REF_ADV_MASK | QRY_ADV_MASK;
 
-struct IndelStub {  // 32 B, written by K3, consumed by K4
+// Work item of the homology kernel, written by the walk: everything K4 needs to start its scans in one 64-byte read
+// (the record's sequences are resolved here, so K4 has no dependent look-ups between the stub and the first window).
+struct IndelStub {  // 64 B
     int32_t rec, op_idx, svtype, n;
-    int32_t pos_ref, pos_qry, eq_before, pad;
+    int32_t pos_ref, pos_qry, eq_before, q_rev;
+    int64_t r_base, q_base;      // offsets of the record's chromosome / contig in the packed planes
+    int32_t r_len, q_len, pad0, pad1;
 };
+static_assert(sizeof(IndelStub) == 64, "stub layout");
+
+// Per-record constants of one run (record -> sequences of the two stores), built on the host, 32 B = two 128-bit loads.
+struct RecDesc {
+    int64_t r_base, q_base;
+    int32_t r_len, q_len, pos, rev;
+};
+static_assert(sizeof(RecDesc) == 32, "record descriptor layout");
+
+__device__ __forceinline__ RecDesc load_recdesc(const RecDesc *__restrict__ t, int32_t rec)
+{
+    const int4 *p = reinterpret_cast<const int4 *>(t + rec);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
+    RecDesc d;
+    d.r_base = (int64_t)(((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x);
+    d.q_base = (int64_t)(((unsigned long long)(unsigned)a.w << 32) | (unsigned)a.z);
+    d.r_len = b.x; d.q_len = b.y; d.pos = b.z; d.rev = b.w;
+    return d;
+}
+
+__device__ __forceinline__ void store_stub(IndelStub *__restrict__ stubs, long long slot, int32_t rec, int32_t op_idx, int is_del, int32_t n,
+                                           int32_t pos_ref, int32_t pos_qry, int32_t eqb, const RecDesc &d)
+{
+    int4 *dst = reinterpret_cast<int4 *>(stubs + slot);
+    dst[0] = make_int4(rec, op_idx, is_del, n);
+    dst[1] = make_int4(pos_ref, pos_qry, eqb, d.rev);
+    dst[2] = make_int4((int)(unsigned)d.r_base, (int)(unsigned)((unsigned long long)d.r_base >> 32), (int)(unsigned)d.q_base,
+                       (int)(unsigned)((unsigned long long)d.q_base >> 32));
+    dst[3] = make_int4(d.r_len, d.q_len, 0, 0);
+}
 
 struct RecView {
     const int32_t *ref_id;
@@ -230,7 +268,7 @@ chunk_scan_kernel(const int4 *__restrict__ agg, const uint2 *__restrict__ cnt, i
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks,
                   const int2 *__restrict__ pre_rq, const longlong2 *__restrict__ pre_cnt,
-                  const int64_t *__restrict__ qry_len, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
+                  const RecDesc *__restrict__ recdesc, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
                   unsigned long long *__restrict__ first_illegal)
 {
     int lane = threadIdx.x & 31;
@@ -258,40 +296,28 @@ cigar_emit_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 
     int32_t rec = L.rec0;
     int64_t cur_off = __ldg(rv.op_off + rec), next_off = __ldg(rv.op_off + rec + 1);
-    int32_t rpos = __ldg(rv.pos + rec);
-    int rrev = __ldg(rv.rev + rec);
-    int32_t qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+    RecDesc rd = load_recdesc(recdesc, rec);
 #pragma unroll
     for (int j = 0; j < OPS_PER_LANE; j++) {
         if (j < L.nvalid) {
             int64_t g = L.g0 + j;
             bool moved = false;
             while (g >= next_off) { ++rec; cur_off = next_off; next_off = __ldg(rv.op_off + rec + 1); moved = true; }
-            if (moved) {
-                rpos = __ldg(rv.pos + rec);
-                rrev = __ldg(rv.rev + rec);
-                qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
-            }
+            if (moved) rd = load_recdesc(recdesc, rec);
             bool head = (g == cur_off);
             if (head) { run_r = 0; run_q = 0; }
             uint32_t op = L.op[j], code = op & 15u, len = op >> 4;
             int32_t op_idx = (int32_t)(g - cur_off);
-            int32_t pos_ref = rpos + run_r, pos_qry = run_q;
+            int32_t pos_ref = rd.pos + run_r, pos_qry = run_q;
             if (code == PAVGPU_OP_X) {
                 for (uint32_t i = 0; i < len; i++) {
                     int32_t t = pos_qry + (int32_t)i;
-                    snv_rows[snv_cur + i] = make_int4(pos_ref + (int32_t)i, rrev ? qlen - 1 - t : t, rec, op_idx);
+                    snv_rows[snv_cur + i] = make_int4(pos_ref + (int32_t)i, rd.rev ? rd.q_len - 1 - t : t, rec, op_idx);
                 }
                 snv_cur += len;
             } else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) {
-                IndelStub s;
-                s.rec = rec; s.op_idx = op_idx; s.svtype = (code == PAVGPU_OP_D); s.n = (int32_t)len;
-                s.pos_ref = pos_ref; s.pos_qry = pos_qry;
-                s.eq_before = (!head && (prev_op & 15u) == PAVGPU_OP_EQ) ? (int32_t)(prev_op >> 4) : 0;
-                s.pad = 0;
-                int4 *dst = reinterpret_cast<int4 *>(stubs + indel_cur);
-                dst[0] = make_int4(s.rec, s.op_idx, s.svtype, s.n);
-                dst[1] = make_int4(s.pos_ref, s.pos_qry, s.eq_before, 0);
+                int32_t eqb = (!head && (prev_op & 15u) == PAVGPU_OP_EQ) ? (int32_t)(prev_op >> 4) : 0;
+                store_stub(stubs, indel_cur, rec, op_idx, code == PAVGPU_OP_D, (int32_t)len, pos_ref, pos_qry, eqb, rd);
                 ++indel_cur;
             } else if (!((1u << code) & LEGAL_MASK)) {
                 atomicMin(first_illegal, (unsigned long long)g);
@@ -360,7 +386,7 @@ __device__ __forceinline__ void seg_combine(const TileVal &older, TileVal &v)
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks, const int32_t *__restrict__ chunk_rec,
-                  ulonglong2 *__restrict__ desc, const int64_t *__restrict__ qry_len, const int64_t *__restrict__ rec_snv_off,
+                  ulonglong2 *__restrict__ desc, const RecDesc *__restrict__ recdesc, const int64_t *__restrict__ rec_snv_off,
                   const int64_t *__restrict__ rec_indel_off, int4 *__restrict__ snv_rows, IndelStub *__restrict__ stubs,
                   unsigned long long *__restrict__ first_illegal, unsigned long long *__restrict__ totals)
 {
@@ -484,14 +510,11 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 
     int32_t rec = L.rec0;
     int64_t cur_off = 0, next_off = 0;
-    int32_t rpos = 0, qlen = 0;
-    int rrev = 0;
+    RecDesc rd{0, 0, 0, 0, 0, 0};
     long long snv_base = 0, indel_base = 0;
     if (L.nvalid > 0) {
         cur_off = __ldg(rv.op_off + rec); next_off = __ldg(rv.op_off + rec + 1);
-        rpos = __ldg(rv.pos + rec);
-        rrev = __ldg(rv.rev + rec);
-        qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+        rd = load_recdesc(recdesc, rec);
         snv_base = __ldg(rec_snv_off + rec); indel_base = __ldg(rec_indel_off + rec);
     }
 #pragma unroll
@@ -501,9 +524,7 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
             bool moved = false;
             while (g >= next_off) { ++rec; cur_off = next_off; next_off = __ldg(rv.op_off + rec + 1); moved = true; }
             if (moved) {
-                rpos = __ldg(rv.pos + rec);
-                rrev = __ldg(rv.rev + rec);
-                qlen = (int32_t)__ldg(qry_len + __ldg(rv.qry_id + rec));
+                rd = load_recdesc(recdesc, rec);
                 snv_base = __ldg(rec_snv_off + rec);
                 indel_base = __ldg(rec_indel_off + rec);
             }
@@ -511,19 +532,17 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
             if (head) { run_r = 0; run_q = 0; run_ns = 0; run_ni = 0; }
             uint32_t op = L.op[j], code = op & 15u, len = op >> 4;
             int32_t op_idx = (int32_t)(g - cur_off);
-            int32_t pos_ref = rpos + run_r, pos_qry = run_q;
+            int32_t pos_ref = rd.pos + run_r, pos_qry = run_q;
             if (code == PAVGPU_OP_X) {
                 long long slot = snv_base + run_ns;
                 for (uint32_t i = 0; i < len; i++) {
                     int32_t t = pos_qry + (int32_t)i;
-                    snv_rows[slot + i] = make_int4(pos_ref + (int32_t)i, rrev ? qlen - 1 - t : t, rec, op_idx);
+                    snv_rows[slot + i] = make_int4(pos_ref + (int32_t)i, rd.rev ? rd.q_len - 1 - t : t, rec, op_idx);
                 }
                 run_ns += len;
             } else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) {
-                int4 *dst = reinterpret_cast<int4 *>(stubs + indel_base + run_ni);
                 int32_t eqb = (!head && (prev_op & 15u) == PAVGPU_OP_EQ) ? (int32_t)(prev_op >> 4) : 0;
-                dst[0] = make_int4(rec, op_idx, (code == PAVGPU_OP_D), (int32_t)len);
-                dst[1] = make_int4(pos_ref, pos_qry, eqb, 0);
+                store_stub(stubs, indel_base + run_ni, rec, op_idx, code == PAVGPU_OP_D, (int32_t)len, pos_ref, pos_qry, eqb, rd);
                 ++run_ni;
             } else if (!((1u << code) & LEGAL_MASK)) {
                 atomicMin(first_illegal, (unsigned long long)g);
@@ -545,112 +564,226 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 }
 
 // K4 ---------------------------------------------------------------------------------------------
-// Thread per indel, but the assignment of indels to threads is re-sorted inside the CTA first: a one-window probe on
-// each side of the breakpoint (uniform cost) tells indels sitting in tandem repeats / homopolymers (scans of hundreds
-// of bases, ~20 % of the C2 indels) from ordinary ones (scans end within a few bases); the CTA then hands the light
-// indels to its first warps and the heavy ones to its last warps, so a warp's lanes run scans of similar length
-// instead of 26 idle lanes waiting for 6 long scans.
+// Left shift + four breakpoint homologies per indel (cigarcall.py:149-155,178-182 / :225-231,247-251 calling
+// call.py:542-647). The unit of work is not the indel but the *window trip* (one 32-base compare of two funnel-shifted
+// windows): scans end after one trip for most indels and after tens of trips for indels inside tandem repeats, so a
+// thread-per-indel kernel leaves most lanes of a warp idle (measured: 6.7 trips per indel on average, 20.4 per warp).
+// Here every lane runs a small state machine (indel -> scan 0..4 -> phase 1/2 -> trip) and a warp owns a block of
+// indels that its lanes pull from one at a time (ballot hand-out, registers only): each loop iteration is exactly one
+// trip on every busy lane, whatever indel, scan or phase that lane is in.
+//   phase 1: common extension of the flank T (from p, away from the breakpoint) with the SV sequence V, capped at n
+//   phase 2: (only if a whole copy of V matched) n + common extension of the flank with itself shifted by n
 constexpr int HOM_THREADS = 256;
 
-__global__ void __launch_bounds__(HOM_THREADS, 4)
-homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, RecView rv, SeqPlanes ref, SeqPlanes qry,
-                pavgpu_indel_row *__restrict__ rows, int do_sort)
+struct HomLane {
+    // indel
+    int64_t idx;
+    int32_t rec, op_idx, n, pr, pq, eqb;
+    int64_t r_base, q_base;
+    int32_t r_len, q_len;
+    int q_rev, ins;
+    int32_t ls, sp, sq, hom_rl, hom_rr, hom_tl, hom_tr;
+    // scan
+    int sc, phase, left, skip, t_is_q;
+    int32_t p, h, pa, pb, limit;
+};
+
+// Stub (already in shared memory) -> lane state.
+__device__ __forceinline__ void hom_take_indel(HomLane &S, const int4 *__restrict__ e, int64_t i)
 {
-    __shared__ int s_perm[HOM_THREADS];
-    __shared__ int s_wl[HOM_THREADS / 32], s_wh[HOM_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t block_base = (int64_t)blockIdx.x * HOM_THREADS;
-    if (!do_sort) {
-        s_perm[tid] = (block_base + tid < n_indel) ? tid : -1;
-    } else {   // ---- phase A: probe + stable partition (light first, heavy last)
-        int64_t i0 = block_base + tid;
-        bool valid = i0 < n_indel, heavy = false;
-        if (valid) {
-            const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i0);
-            int4 a = __ldg(sp4), b = __ldg(sp4 + 1);
-            int32_t rec = a.x, svtype = a.z, n = a.w, pr = b.x, pq = b.y;
-            int32_t rid = __ldg(rv.ref_id + rec), qid = __ldg(rv.qry_id + rec);
-            OSeq R{ref.pack2, ref.nmask, __ldg(ref.off + rid), __ldg(ref.len + rid), 0};
-            OSeq Q{qry.pack2, qry.nmask, __ldg(qry.off + qid), __ldg(qry.len + qid), (int)__ldg(rv.rev + rec)};
-            const bool ins = (svtype == 0);
-            const OSeq &V = ins ? Q : R;
-            const int64_t v0 = ins ? (int64_t)pq : (int64_t)pr;
-            int64_t lim = n < 32 ? n : 32;
-            int64_t hl = common_extension(R, (int64_t)pr - 1, V, v0 + n - 1, lim, 1);
-            int64_t hr = common_extension(R, ins ? (int64_t)pr : (int64_t)pr + n, V, v0, lim, 0);
-            heavy = (hl >= lim) || (hr >= lim) || (hl + hr >= 16);
-        }
-        unsigned bl = __ballot_sync(FULL, valid && !heavy), bh = __ballot_sync(FULL, valid && heavy);
-        if (lane == 0) { s_wl[wid] = __popc(bl); s_wh[wid] = __popc(bh); }
-        s_perm[tid] = -1;
-        __syncthreads();
-        int light_before = 0, heavy_before = 0, n_light = 0;
-        for (int q = 0; q < HOM_THREADS / 32; q++) {
-            if (q < wid) { light_before += s_wl[q]; heavy_before += s_wh[q]; }
-            n_light += s_wl[q];
-        }
-        unsigned below = (1u << lane) - 1;
-        if (valid && !heavy) s_perm[light_before + __popc(bl & below)] = tid;
-        if (valid && heavy) s_perm[n_light + heavy_before + __popc(bh & below)] = tid;
-        __syncthreads();
-    }
-    // ---- phase B: this thread now owns indel s_perm[tid] of the CTA
-    const int j = s_perm[tid];
-    if (j < 0) return;
-    const int64_t i = block_base + j;
-    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
-    int4 a = __ldg(sp4), b = __ldg(sp4 + 1);
-    int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
-    int32_t rid = __ldg(rv.ref_id + rec), qid = __ldg(rv.qry_id + rec);
-    OSeq R{ref.pack2, ref.nmask, __ldg(ref.off + rid), __ldg(ref.len + rid), 0};
-    OSeq Q{qry.pack2, qry.nmask, __ldg(qry.off + qid), __ldg(qry.len + qid), (int)__ldg(rv.rev + rec)};
-    int32_t L = (int32_t)Q.len;
-    // Five scans per indel (cigarcall.py:149-155,178-182 / :225-231,247-251): the left shift, then the four
-    // breakpoint homologies at the shifted position. One rolled loop so the scan code exists once in the kernel
-    // (with all five call sites inlined the kernel is instruction-fetch bound).
-    //   INS: SV sequence = contig[sq : sq+n] (re-sliced after the shift); DEL: reference[pr : pr+n] (never re-sliced)
-    const bool ins = (svtype == 0);
-    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
-    int32_t sp = pr, sq = pq;
-#pragma unroll 1
-    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {
-        const bool on_ref = sc <= 2;            // scans 0..2 walk the reference, 3..4 the contig
-        const int left = (sc == 0 || sc == 1 || sc == 3);
-        int64_t p;
-        if (sc == 0) p = (int64_t)pr - 1;
-        else if (sc == 1) p = (int64_t)sp - 1;
-        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
-        else if (sc == 3) p = (int64_t)sq - 1;
-        else p = ins ? (int64_t)sq + n : (int64_t)sq;
-        const OSeq &T = on_ref ? R : Q;
-        const OSeq &V = ins ? Q : R;
-        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;   // sq == pq while sc == 0
-        int h = dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, left);
-        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
-        else if (sc == 1) hom_rl = h;
-        else if (sc == 2) hom_rr = h;
-        else if (sc == 3) hom_tl = h;
-        else hom_tr = h;
-    }
-    pavgpu_indel_row o;
-    o.rec = rec; o.op_idx = op_idx; o.svtype = svtype; o.svlen = n; o.pad[0] = o.pad[1] = 0;
-    o.left_shift = ls;
-    o.hom_ref_l = hom_rl; o.hom_ref_r = hom_rr; o.hom_tig_l = hom_tl; o.hom_tig_r = hom_tr;
-    if (ins) {          // cigarcall.py:157-173
-        o.pos = sp; o.end = sp + 1;
-        if (Q.rev) { o.qry_end = L - sq; o.qry_pos = o.qry_end - n; } else { o.qry_pos = sq; o.qry_end = sq + n; }
-        o.seq_start = sq;
+    const int4 a = e[0], b = e[1], c = e[2], d = e[3];
+    S.idx = i;
+    S.rec = a.x; S.op_idx = a.y; S.ins = (a.z == 0); S.n = a.w; S.pr = b.x; S.pq = b.y; S.eqb = b.z; S.q_rev = b.w;
+    S.r_base = (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x);
+    S.q_base = (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z);
+    S.r_len = d.x; S.q_len = d.y;
+    S.ls = 0; S.sp = S.pr; S.sq = S.pq;
+    S.hom_rl = S.hom_rr = S.hom_tl = S.hom_tr = 0;
+    S.sc = S.eqb > 0 ? 0 : 1;   // scan 0 (the left shift) only when the previous op was '=' (cigarcall.py:149,225)
+}
+
+// Phase-1 parameters of scan S.sc: sc 0 = left shift, 1/2 = HOM_REF left/right, 3/4 = HOM_TIG left/right.
+__device__ __forceinline__ void hom_setup_scan(HomLane &S)
+{
+    const int sc = S.sc;
+    S.t_is_q = sc >= 3;                        // scans 0..2 walk the reference, 3..4 the contig
+    S.left = (sc == 0) | (sc == 1) | (sc == 3);
+    const int32_t n_ins = S.ins ? S.n : 0, n_del = S.ins ? 0 : S.n;
+    // sc: 0 -> pr-1, 1 -> sp-1, 2 -> sp (INS) / sp+n (DEL), 3 -> sq-1, 4 -> sq+n (INS) / sq (DEL)
+    const int32_t p_ref = sc == 0 ? S.pr - 1 : (sc == 1 ? S.sp - 1 : S.sp + n_del);
+    const int32_t p_qry = sc == 3 ? S.sq - 1 : S.sq + n_ins;
+    const int32_t p = S.t_is_q ? p_qry : p_ref;
+    const int32_t t_len = S.t_is_q ? S.q_len : S.r_len;
+    const int32_t v0 = S.ins ? S.sq : S.pr;   // INS: contig[sq : sq+n], re-sliced after the shift; DEL: reference[pr : pr+n]
+    S.p = p; S.phase = 1; S.h = 0; S.limit = S.n;
+    S.skip = (S.n <= 0) | (p < 0) | (p >= t_len);   // call.py:574,627: nothing to compare -> 0
+    const int32_t b = S.left ? v0 + S.n - 1 : v0;
+    S.pa = S.skip ? 0 : (S.left ? p - 31 : p);
+    S.pb = S.skip ? 0 : (S.left ? b - 31 : b);
+}
+
+__device__ __forceinline__ void hom_write_row(const HomLane &S, pavgpu_indel_row *__restrict__ rows)
+{
+    int32_t pos, end, qry_pos, qry_end, seq_start;
+    if (S.ins) {        // cigarcall.py:157-173
+        pos = S.sp; end = S.sp + 1;
+        if (S.q_rev) { qry_end = S.q_len - S.sq; qry_pos = qry_end - S.n; } else { qry_pos = S.sq; qry_end = S.sq + S.n; }
+        seq_start = S.sq;
     } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
-        o.pos = pr; o.end = pr + n;
-        o.qry_pos = Q.rev ? L - sq : sq;
-        o.qry_end = o.qry_pos + 1;
-        o.seq_start = pr;
+        pos = S.pr; end = S.pr + S.n;
+        qry_pos = S.q_rev ? S.q_len - S.sq : S.sq;
+        qry_end = qry_pos + 1;
+        seq_start = S.pr;
     }
-    int4 *dst = reinterpret_cast<int4 *>(rows + i);
-    dst[0] = make_int4(o.rec, o.op_idx, o.svtype, o.svlen);
-    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
-    dst[2] = make_int4(o.left_shift, o.hom_ref_l, o.hom_ref_r, o.hom_tig_l);
-    dst[3] = make_int4(o.hom_tig_r, o.seq_start, 0, 0);
+    int4 *dst = reinterpret_cast<int4 *>(rows + S.idx);
+    dst[0] = make_int4(S.rec, S.op_idx, S.ins ? 0 : 1, S.n);
+    dst[1] = make_int4(pos, end, qry_pos, qry_end);
+    dst[2] = make_int4(S.ls, S.hom_rl, S.hom_rr, S.hom_tl);
+    dst[3] = make_int4(S.hom_tr, seq_start, 0, 0);
+}
+
+// Stubs reach the lanes through a per-warp ring in shared memory (two blocks of 32 stubs), filled with cp.async two
+// blocks ahead of the hand-out: a lane that finishes an indel finds its next one on chip, so the only global latency
+// inside the loop is the window loads of the trip itself.
+constexpr int HOM_WARPS = HOM_THREADS / 32;
+constexpr int HOM_RING = 64;   // stubs per warp in the ring
+
+__device__ __forceinline__ void hom_prefetch_block(int4 *ring, const IndelStub *__restrict__ stubs, int64_t wbase, int64_t wend, int blk, int lane)
+{
+    const int64_t first = wbase + ((int64_t)blk << 5);
+    if (first < wend) {
+        const int4 *src = reinterpret_cast<const int4 *>(stubs + first);   // the block's 32 stubs are contiguous: 128 16-byte pieces
+        int4 *dst = ring + (size_t)(blk & 1) * 32 * 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = q * 32 + lane;
+            if (first + (c >> 2) < wend) __pipeline_memcpy_async(dst + c, src + c, 16);
+        }
+    }
+    __pipeline_commit();   // one group per block, empty past the end, so "all but the newest group" always means "this block"
+}
+
+__global__ void __launch_bounds__(HOM_THREADS, 4)
+homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, int indels_per_warp, SeqPlanes ref, SeqPlanes qry,
+                pavgpu_indel_row *__restrict__ rows)
+{
+    __shared__ int4 s_ring[HOM_WARPS][HOM_RING * 4];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * HOM_WARPS + (threadIdx.x >> 5);
+    const int64_t wbase = warp * indels_per_warp;
+    if (wbase >= n_indel) return;   // warp-uniform
+    const int64_t wend = min(wbase + (int64_t)indels_per_warp, n_indel);
+    int4 *ring = s_ring[threadIdx.x >> 5];
+    const unsigned lt = (1u << lane) - 1u;
+    hom_prefetch_block(ring, stubs, wbase, wend, 0, lane);
+    hom_prefetch_block(ring, stubs, wbase, wend, 1, lane);
+    HomLane S;
+    bool busy = false;
+    int64_t next = wbase;   // first indel of the warp's range not handed out yet (warp-uniform)
+    for (;;) {
+        // ---- hand the next indels of the current block to idle lanes
+        const unsigned idle = __ballot_sync(FULL, !busy);
+        if (idle && next < wend) {
+            const int blk = (int)((next - wbase) >> 5);
+            const int64_t blk_end = min(wbase + ((int64_t)(blk + 1) << 5), wend);
+            __pipeline_wait_prior(1);   // block blk has landed (block blk+1 may still be in flight)
+            __syncwarp();
+            const int64_t i = next + __popc(idle & lt);
+            if (!busy && i < blk_end) {
+                hom_take_indel(S, ring + (size_t)((i - wbase) & (HOM_RING - 1)) * 4, i);
+                hom_setup_scan(S);
+                busy = true;
+            }
+            next = min(next + (int64_t)__popc(idle), blk_end);
+            if (next == blk_end) {      // block consumed: its half of the ring takes block blk+2
+                __syncwarp();
+                hom_prefetch_block(ring, stubs, wbase, wend, blk + 2, lane);
+            }
+        }
+        if (!__any_sync(FULL, busy)) break;
+        if (busy) {
+            // ---- one trip: 32 bases of A (the flank) against 32 bases of B (V in phase 1, the shifted flank in phase 2)
+            const bool a_q = S.t_is_q != 0;
+            const bool b_q = S.phase == 1 ? (S.ins != 0) : a_q;
+            const WSeq A{a_q ? qry.win : ref.win, a_q ? S.q_base : S.r_base, a_q ? S.q_len : S.r_len, a_q ? S.q_rev : 0};
+            const WSeq B{b_q ? qry.win : ref.win, b_q ? S.q_base : S.r_base, b_q ? S.q_len : S.r_len, b_q ? S.q_rev : 0};
+            uint64_t wa, wb; uint32_t ma, mb;
+            WinReq qa, qb;
+            const uint4 *pa_ = win_request(A, S.pa, qa), *pb_ = win_request(B, S.pb, qb);
+            const uint4 ua = __ldg(pa_), ub = __ldg(pb_);   // one 128-bit load per window (window plane), both in flight together
+            win_extract(A, qa, ua, wa, ma);
+            win_extract(B, qb, ub, wb, mb);
+            const uint64_t x = wa ^ wb;
+            const uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;   // one bit per differing base
+            const uint32_t m = ma | mb;
+            // left scans: last base of the window = least significant group / highest mask bit; right scans: first base =
+            // most significant group / lowest mask bit. Both computed, one selected (no divergence between lanes).
+            const int sd_l = d ? ((__ffsll((long long)d) - 1) >> 1) : 32, sm_l = m ? __clz((int)m) : 32;
+            const int sd_r = d ? (__clzll((long long)d) >> 1) : 32, sm_r = m ? (__ffs((int)m) - 1) : 32;
+            const int stop = S.left ? min(sd_l, sm_l) : min(sd_r, sm_r);
+            // ---- transitions (same arithmetic as common_extension / dev_homology_raw in common.cuh), predicated
+            const bool in_window = stop < 32;
+            const int32_t h32 = S.h + 32;
+            const bool end_phase = S.skip || in_window || h32 >= S.limit;
+            const int32_t hf = in_window ? min(S.h + stop, S.limit) : S.limit;
+            const bool to_phase2 = end_phase && !S.skip && S.phase == 1 && hf >= S.n;   // a whole copy of the SV sequence matched
+            const bool scan_done = end_phase && !to_phase2;
+            const int32_t step = S.left ? -32 : 32;
+            if (!end_phase) { S.h = h32; S.pa += step; S.pb += step; }
+            if (to_phase2) {   // go on as flank vs flank shifted by n
+                S.phase = 2; S.h = 0; S.limit = 0x7fffffff - S.n;
+                const int32_t a = S.left ? S.p - S.n : S.p + S.n;
+                S.pa = S.left ? a - 31 : a; S.pb = S.left ? S.p - 31 : S.p;
+            }
+            if (scan_done) {
+                const int32_t result = S.skip ? 0 : (S.phase == 1 ? hf : S.n + hf);
+                const int sc = S.sc;
+                if (sc == 0) { S.ls = min(S.eqb, result); S.sp = S.pr - S.ls; S.sq = S.pq - S.ls; }
+                S.hom_rl = sc == 1 ? result : S.hom_rl;
+                S.hom_rr = sc == 2 ? result : S.hom_rr;
+                S.hom_tl = sc == 3 ? result : S.hom_tl;
+                S.hom_tr = sc == 4 ? result : S.hom_tr;
+                S.sc = sc + 1;
+                if (sc < 4) hom_setup_scan(S);
+                else { hom_write_row(S, rows); busy = false; }
+            }
+        }
+        __syncwarp();   // lanes leave the transitions at different points; the next trip runs converged again
+    }
+}
+
+// Thread-per-indel variant (PAVGPU_HOM_TPI=1, A/B timing): maximal memory-level parallelism (every indel in flight at once),
+// but a warp runs as long as its longest indel.
+__global__ void __launch_bounds__(HOM_THREADS)
+homology_tpi_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
+{
+    const int64_t i = (int64_t)blockIdx.x * HOM_THREADS + threadIdx.x;
+    if (i >= n_indel) return;
+    HomLane S;
+    hom_take_indel(S, reinterpret_cast<const int4 *>(stubs + i), i);
+    const WSeq R{ref.win, S.r_base, S.r_len, 0}, Q{qry.win, S.q_base, S.q_len, S.q_rev};
+    const int n = S.n;
+#pragma unroll 1
+    for (int sc = S.sc; sc < 5; sc++) {
+        const bool on_ref = sc <= 2;
+        const int left = (sc == 0) | (sc == 1) | (sc == 3);
+        int32_t p;
+        if (sc == 0) p = S.pr - 1;
+        else if (sc == 1) p = S.sp - 1;
+        else if (sc == 2) p = S.ins ? S.sp : S.sp + n;
+        else if (sc == 3) p = S.sq - 1;
+        else p = S.ins ? S.sq + n : S.sq;
+        const WSeq &T = on_ref ? R : Q;
+        const WSeq &V = S.ins ? Q : R;
+        const int32_t v0 = S.ins ? S.sq : S.pr;
+        const int h = wdev_homology(T, p, V, v0, n, left);
+        if (sc == 0) { S.ls = min(S.eqb, h); S.sp = S.pr - S.ls; S.sq = S.pq - S.ls; }
+        else if (sc == 1) S.hom_rl = h;
+        else if (sc == 2) S.hom_rr = h;
+        else if (sc == 3) S.hom_tl = h;
+        else S.hom_tr = h;
+    }
+    hom_write_row(S, rows);
 }
 
 __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,
@@ -670,36 +803,56 @@ __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
+// Indels per warp of the homology kernel: enough warps to fill the chip (24 per SM), blocks long enough that the
+// hand-out evens out short and long scans (>= 64 indels, i.e. >= 2 per lane), multiple of 32.
+static int hom_indels_per_warp(int64_t n_indel, int sm_count)
+{
+    const char *e = getenv("PAVGPU_HOM_IPW");
+    if (e && atoi(e) >= 32) return atoi(e) / 32 * 32;
+    int64_t warps = (int64_t)sm_count * 24;
+    int64_t ipw = (n_indel + warps - 1) / warps;
+    ipw = (ipw + 31) / 32 * 32;
+    if (ipw < 64) ipw = 64;
+    if (ipw > 1024) ipw = 1024;
+    return (int)ipw;
+}
+
 struct pavgpu_cigar_batch {
     pavgpu_ctx *ctx;
     int32_t n_rec;
     int64_t n_ops, n_chunks;
+    void *d_arena;                       // one pooled block; everything below points into it
     int32_t *d_ref_id, *d_qry_id, *d_pos;
     uint8_t *d_rev;
     int64_t *d_op_off;
     uint32_t *d_ops;
-    int4 *d_agg;
+    int4 *d_agg;                         // multi-pass walk only
     uint2 *d_cnt;
     int2 *d_pre_rq;
     longlong2 *d_pre_cnt;
     int64_t *d_totals;                   // [0] n_snv, [1] n_indel
     unsigned long long *d_first_illegal;
-    int4 *d_snv; int64_t cap_snv;
+    int4 *d_snv; int64_t cap_snv;        // multi-pass walk: separate blocks sized after the scan
     IndelStub *d_stub; pavgpu_indel_row *d_indel; int64_t cap_indel;
+    bool rows_in_arena;
     int64_t n_snv, n_indel;
     int64_t host_n_snv, host_n_indel;   // counted on the host while the ops were staged
-    int64_t n_tiles;
     ulonglong2 *d_desc;
-    unsigned int *d_tile_counter;
     int64_t *d_rec_snv_off, *d_rec_indel_off;   // first row slot of every record (host-counted)
     int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (host-built index)
+    RecDesc *d_recdesc;                          // per-record constants of the current (ref_store, qry_store) pair
+    uint64_t recdesc_ref_uid, recdesc_qry_uid;   // stores the table was built for (0 = none yet)
+    std::vector<RecDesc> h_recdesc;
+    std::vector<int32_t> h_ref_id, h_qry_id;
+    std::vector<uint8_t> h_rev;
     bool fused;
-    int hom_sort;   // re-sort indels inside each CTA by a one-window probe (PAVGPU_HOM_SORT, default off: see DESIGN.md 6.1)
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
-    // host copies for error explanation
-    std::vector<uint32_t> h_ops;
+    // host view of the ops for explaining an illegal op (error path only): borrowed from the caller in the one-shot
+    // call, copied for resident batches
+    const uint32_t *h_ops;
+    std::vector<uint32_t> h_ops_copy;
     std::vector<int64_t> h_op_off;
     std::vector<int32_t> h_pos;
 };
@@ -756,10 +909,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_parse(const c
 
 static void batch_release(pavgpu_cigar_batch *b)
 {
-    cudaFree(b->d_ref_id); cudaFree(b->d_qry_id); cudaFree(b->d_pos); cudaFree(b->d_rev); cudaFree(b->d_op_off);
-    cudaFree(b->d_ops); cudaFree(b->d_agg); cudaFree(b->d_cnt); cudaFree(b->d_pre_rq); cudaFree(b->d_pre_cnt);
-    cudaFree(b->d_totals); cudaFree(b->d_first_illegal); cudaFree(b->d_snv); cudaFree(b->d_stub); cudaFree(b->d_indel);
-    cudaFree(b->d_desc); cudaFree(b->d_tile_counter); cudaFree(b->d_rec_snv_off); cudaFree(b->d_rec_indel_off); cudaFree(b->d_chunk_rec);
+    pav_dev_free(b->ctx, b->d_arena);
+    if (!b->rows_in_arena) { pav_dev_free(b->ctx, b->d_snv); pav_dev_free(b->ctx, b->d_stub); pav_dev_free(b->ctx, b->d_indel); }
 }
 
 extern "C" __attribute__((visibility("default"))) void pavgpu_cigar_batch_free(pavgpu_cigar_batch *b)
@@ -770,9 +921,14 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_cigar_batch_free(p
     delete b;
 }
 
-extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_id, const int32_t *qry_seq_id,
-                                         const int32_t *pos, const uint8_t *rev, const uint32_t *ops, const int64_t *op_off,
-                                         pavgpu_cigar_batch **out)
+// Sub-allocation inside the batch arena (256-byte aligned).
+struct ArenaPlan {
+    size_t off = 0;
+    size_t add(size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; }
+};
+
+static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_id, const int32_t *qry_seq_id, const int32_t *pos,
+                        const uint8_t *rev, const uint32_t *ops, const int64_t *op_off, bool borrow_ops, pavgpu_cigar_batch **out)
 {
     if (!ctx || !out || n_rec < 0 || !op_off || (n_rec > 0 && (!ref_seq_id || !qry_seq_id || !pos || !rev))) {
         pav_set_error("cigar_batch_create: bad argument");
@@ -780,22 +936,29 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
     }
     int64_t n_ops = op_off[n_rec] - op_off[0];
     if (op_off[0] != 0 || n_ops < 0 || (n_ops > 0 && !ops)) { pav_set_error("cigar_batch_create: bad op offsets"); return PAVGPU_ERR_ARG; }
+    PavTrace tr("cigar_batch_create");
     CUDA_TRY(cudaSetDevice(ctx->device));
     pavgpu_cigar_batch *b = new pavgpu_cigar_batch();
     b->ctx = ctx; b->n_rec = n_rec; b->n_ops = n_ops;
     b->n_chunks = (n_ops + CHUNK - 1) / CHUNK;
-    b->h_ops.assign(ops, ops + n_ops);
+    if (borrow_ops) b->h_ops = ops;
+    else { b->h_ops_copy.assign(ops, ops + n_ops); b->h_ops = b->h_ops_copy.data(); }
     b->h_op_off.assign(op_off, op_off + n_rec + 1);
     b->h_pos.assign(pos, pos + n_rec);
-    b->n_tiles = (b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    b->h_ref_id.assign(ref_seq_id, ref_seq_id + n_rec); b->h_qry_id.assign(qry_seq_id, qry_seq_id + n_rec); b->h_rev.assign(rev, rev + n_rec);
+    tr.mark("host copies");
+    // one sequential pass over the ops (the host has to touch them anyway to stage them): rows per record -> first row slot
+    // of every record, and the record of every chunk's first op
     std::vector<int64_t> rec_snv_off((size_t)n_rec + 1), rec_indel_off((size_t)n_rec + 1);
-    for (int32_t r = 0; r < n_rec; r++) {   // per-record row counts -> first row slot of every record
+    for (int32_t r = 0; r < n_rec; r++) {
         rec_snv_off[r] = b->host_n_snv; rec_indel_off[r] = b->host_n_indel;
+        int64_t ns = 0, ni = 0;
         for (int64_t i = op_off[r]; i < op_off[r + 1]; i++) {
-            uint32_t code = ops[i] & 15u;
-            if (code == PAVGPU_OP_X) b->host_n_snv += ops[i] >> 4;
-            else if (code == PAVGPU_OP_I || code == PAVGPU_OP_D) b->host_n_indel += 1;
+            const uint32_t op = ops[i], code = op & 15u;
+            ns += (code == PAVGPU_OP_X) ? (op >> 4) : 0u;
+            ni += (code == PAVGPU_OP_I) | (code == PAVGPU_OP_D);
         }
+        b->host_n_snv += ns; b->host_n_indel += ni;
     }
     rec_snv_off[n_rec] = b->host_n_snv; rec_indel_off[n_rec] = b->host_n_indel;
     std::vector<int32_t> chunk_rec((size_t)std::max<int64_t>(b->n_chunks, 1), 0);
@@ -807,39 +970,47 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
             chunk_rec[(size_t)c] = r;
         }
     }
+    tr.mark("host row count pass");
     // single-pass walk unless the descriptor fields would overflow (33-bit SNV count, 30-bit indel count) or the
     // multi-pass kernels are requested for A/B timing
-    const char *hs = getenv("PAVGPU_HOM_SORT");
-    b->hom_sort = (hs && hs[0] == '1') ? 1 : 0;
     const char *mp = getenv("PAVGPU_CIGAR_MULTIPASS");
     b->fused = !(mp && mp[0] == '1') && b->host_n_snv < ((int64_t)1 << 33) && b->host_n_indel < ((int64_t)1 << 30);
-    size_t ops_padded = (size_t)std::max<int64_t>(b->n_chunks, 1) * CHUNK;
-    size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1), nr = (size_t)std::max(n_rec, 1);
+    const size_t ops_padded = (size_t)std::max<int64_t>(b->n_chunks, 1) * CHUNK;
+    const size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1), nr = (size_t)std::max(n_rec, 1);
+    ArenaPlan ap;
+    const size_t o_ref_id = ap.add(nr * 4), o_qry_id = ap.add(nr * 4), o_pos = ap.add(nr * 4), o_rev = ap.add(nr), o_op_off = ap.add((nr + 1) * 8);
+    const size_t o_ops = ap.add(ops_padded * 4), o_totals = ap.add(16), o_illegal = ap.add(8), o_desc = ap.add(nc * sizeof(ulonglong2));
+    const size_t o_rso = ap.add((nr + 1) * 8), o_rio = ap.add((nr + 1) * 8), o_crec = ap.add(nc * 4), o_rdesc = ap.add(nr * sizeof(RecDesc));
+    size_t o_agg = 0, o_cnt = 0, o_prq = 0, o_pcnt = 0, o_snv = 0, o_stub = 0, o_indel = 0;
+    if (!b->fused) { o_agg = ap.add(nc * sizeof(int4)); o_cnt = ap.add(nc * sizeof(uint2)); o_prq = ap.add(nc * sizeof(int2)); o_pcnt = ap.add(nc * sizeof(longlong2)); }
+    else {   // row buffers are sized from the host counts: no mid-run round trip
+        o_snv = ap.add((size_t)b->host_n_snv * sizeof(int4));
+        o_stub = ap.add((size_t)b->host_n_indel * sizeof(IndelStub));
+        o_indel = ap.add((size_t)b->host_n_indel * sizeof(pavgpu_indel_row));
+    }
     int rc = [&]() -> int {
-        CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-        CUDA_TRY(cudaMalloc(&b->d_ref_id, nr * 4)); CUDA_TRY(cudaMalloc(&b->d_qry_id, nr * 4)); CUDA_TRY(cudaMalloc(&b->d_pos, nr * 4));
-        CUDA_TRY(cudaMalloc(&b->d_rev, nr)); CUDA_TRY(cudaMalloc(&b->d_op_off, (nr + 1) * 8));
-        CUDA_TRY(cudaMalloc(&b->d_ops, ops_padded * 4));
-        CUDA_TRY(cudaMalloc(&b->d_agg, nc * sizeof(int4))); CUDA_TRY(cudaMalloc(&b->d_cnt, nc * sizeof(uint2)));
-        CUDA_TRY(cudaMalloc(&b->d_pre_rq, nc * sizeof(int2))); CUDA_TRY(cudaMalloc(&b->d_pre_cnt, nc * sizeof(longlong2)));
-        CUDA_TRY(cudaMalloc(&b->d_totals, 2 * 8)); CUDA_TRY(cudaMalloc(&b->d_first_illegal, 8));
-        CUDA_TRY(cudaMalloc(&b->d_desc, sizeof(ulonglong2) * (size_t)std::max<int64_t>(b->n_chunks, 1)));
-        CUDA_TRY(cudaMalloc(&b->d_tile_counter, sizeof(unsigned int)));
-        CUDA_TRY(cudaMalloc(&b->d_rec_snv_off, (nr + 1) * 8)); CUDA_TRY(cudaMalloc(&b->d_rec_indel_off, (nr + 1) * 8));
-        CUDA_TRY(cudaMemcpyAsync(b->d_rec_snv_off, rec_snv_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(b->d_rec_indel_off, rec_indel_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMalloc(&b->d_chunk_rec, chunk_rec.size() * 4));
-        CUDA_TRY(cudaMemcpyAsync(b->d_chunk_rec, chunk_rec.data(), chunk_rec.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (b->fused) {  // row buffers are sized from the host counts: no mid-run round trip
-            if (b->host_n_snv) { CUDA_TRY(cudaMalloc(&b->d_snv, (size_t)b->host_n_snv * sizeof(int4))); b->cap_snv = b->host_n_snv; }
-            if (b->host_n_indel) {
-                CUDA_TRY(cudaMalloc(&b->d_stub, (size_t)b->host_n_indel * sizeof(IndelStub)));
-                CUDA_TRY(cudaMalloc(&b->d_indel, (size_t)b->host_n_indel * sizeof(pavgpu_indel_row)));
-                b->cap_indel = b->host_n_indel;
-            }
-        }
         cudaStream_t st = ctx->stream;
-        CUDA_TRY(cudaMemsetAsync(b->d_ops, 0, ops_padded * 4, st));
+        cudaError_t e = pav_dev_alloc(ctx, ap.off, &b->d_arena);
+        if (e != cudaSuccess) { pav_set_error("cigar_batch_create: cudaMalloc(%zu) failed: %s", ap.off, cudaGetErrorString(e)); return PAVGPU_ERR_NOMEM; }
+        char *base = static_cast<char *>(b->d_arena);
+        b->d_ref_id = (int32_t *)(base + o_ref_id); b->d_qry_id = (int32_t *)(base + o_qry_id); b->d_pos = (int32_t *)(base + o_pos);
+        b->d_rev = (uint8_t *)(base + o_rev); b->d_op_off = (int64_t *)(base + o_op_off); b->d_ops = (uint32_t *)(base + o_ops);
+        b->d_totals = (int64_t *)(base + o_totals); b->d_first_illegal = (unsigned long long *)(base + o_illegal);
+        b->d_desc = (ulonglong2 *)(base + o_desc); b->d_rec_snv_off = (int64_t *)(base + o_rso); b->d_rec_indel_off = (int64_t *)(base + o_rio);
+        b->d_chunk_rec = (int32_t *)(base + o_crec); b->d_recdesc = (RecDesc *)(base + o_rdesc);
+        if (!b->fused) {
+            b->d_agg = (int4 *)(base + o_agg); b->d_cnt = (uint2 *)(base + o_cnt); b->d_pre_rq = (int2 *)(base + o_prq); b->d_pre_cnt = (longlong2 *)(base + o_pcnt);
+            b->rows_in_arena = false;
+        } else {
+            b->d_snv = (int4 *)(base + o_snv); b->d_stub = (IndelStub *)(base + o_stub); b->d_indel = (pavgpu_indel_row *)(base + o_indel);
+            b->cap_snv = b->host_n_snv; b->cap_indel = b->host_n_indel;
+            b->rows_in_arena = true;
+        }
+        tr.mark("arena");
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_rec_snv_off, rec_snv_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_rec_indel_off, rec_indel_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_chunk_rec, chunk_rec.data(), chunk_rec.size() * 4, cudaMemcpyHostToDevice, st));
         if (n_rec) {
             CUDA_TRY(cudaMemcpyAsync(b->d_ref_id, ref_seq_id, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(b->d_qry_id, qry_seq_id, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
@@ -848,14 +1019,24 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
         }
         CUDA_TRY(cudaMemcpyAsync(b->d_op_off, op_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
         if (n_ops) CUDA_TRY(cudaMemcpyAsync(b->d_ops, ops, (size_t)n_ops * 4, cudaMemcpyHostToDevice, st));
+        if (ops_padded > (size_t)n_ops)   // lanes always load whole vectors: zero the tail of the last chunk
+            CUDA_TRY(cudaMemsetAsync(b->d_ops + n_ops, 0, (ops_padded - (size_t)n_ops) * 4, st));
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // the staging vectors above die with this scope
         b->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+        tr.mark("h2d");
         return PAVGPU_OK;
     }();
     if (rc) { batch_release(b); delete b; return rc; }
     *out = b;
     return PAVGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_id, const int32_t *qry_seq_id,
+                                         const int32_t *pos, const uint8_t *rev, const uint32_t *ops, const int64_t *op_off,
+                                         pavgpu_cigar_batch **out)
+{
+    return batch_create(ctx, n_rec, ref_seq_id, qry_seq_id, pos, rev, ops, op_off, false, out);
 }
 
 extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pavgpu_cigar_batch *b, const pavgpu_seqstore *ref_store, const pavgpu_seqstore *qry_store,
@@ -872,6 +1053,29 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     cudaStream_t st = ctx->stream;
     int launches = 0;
     RecView rv{b->d_ref_id, b->d_qry_id, b->d_pos, b->d_rev, b->d_op_off, b->n_rec};
+    if (b->recdesc_ref_uid != ref_store->uid || b->recdesc_qry_uid != qry_store->uid) {
+        // record -> (plane offsets, lengths, POS, REV) for this pair of stores; rebuilt only when the stores change
+        b->h_recdesc.resize((size_t)b->n_rec);
+        for (int32_t r = 0; r < b->n_rec; r++) {
+            const int32_t ri = b->h_ref_id[r], qi = b->h_qry_id[r];
+            if (ri < 0 || ri >= ref_store->n_seq || qi < 0 || qi >= qry_store->n_seq) {
+                pav_set_error("cigar_batch_run: record %d refers to a sequence id outside its store", r);
+                return PAVGPU_ERR_ARG;
+            }
+            b->h_recdesc[r] = RecDesc{ref_store->h_off[ri], qry_store->h_off[qi], (int32_t)ref_store->h_len[ri], (int32_t)qry_store->h_len[qi],
+                                      b->h_pos[r], b->h_rev[r] ? 1 : 0};
+        }
+        if (b->n_rec) CUDA_TRY(cudaMemcpyAsync(b->d_recdesc, b->h_recdesc.data(), (size_t)b->n_rec * sizeof(RecDesc), cudaMemcpyHostToDevice, st));
+        b->recdesc_ref_uid = ref_store->uid; b->recdesc_qry_uid = qry_store->uid;
+    }
+    // window planes of the two stores (built once per store, before the timed region)
+    const uint4 *w_ref = nullptr, *w_qry = nullptr;
+    if (b->host_n_indel > 0 || !b->fused) {
+        int wrc = pav_seqstore_window_plane(ref_store, &w_ref);
+        if (!wrc) wrc = pav_seqstore_window_plane(qry_store, &w_qry);
+        if (wrc) return wrc;
+    }
+    const SeqPlanes pl_ref = planes_of(ref_store), pl_qry = planes_of(qry_store);
     unsigned long long init = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(b->d_first_illegal, &init, 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 16, st));
@@ -879,8 +1083,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     b->n_snv = b->n_indel = 0;
     if (b->n_chunks > 0 && b->fused) {
         CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_chunks, st));
-        cigar_walk_kernel<<<(unsigned)b->n_tiles, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, b->d_desc,
-                                                                             qry_store->d_len, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
+        cigar_walk_kernel<<<(unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, b->d_desc,
+                                                                             b->d_recdesc, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
                                                                              b->d_first_illegal, reinterpret_cast<unsigned long long *>(b->d_totals));
         launches++;
         CUDA_TRY(cudaGetLastError());
@@ -889,8 +1093,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         b->n_snv = b->host_n_snv; b->n_indel = b->host_n_indel;
         if (b->n_indel > 0) {
-            unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
-            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel, b->hom_sort);
+            const int ipw = hom_indels_per_warp(b->n_indel, ctx->sm_count);
+            unsigned hb = (unsigned)((b->n_indel + (int64_t)ipw * (HOM_THREADS / 32) - 1) / ((int64_t)ipw * (HOM_THREADS / 32)));
+            if (getenv("PAVGPU_HOM_TPI")) homology_tpi_kernel<<<(unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS), HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
+            else homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, ipw, pl_ref, pl_qry, b->d_indel);
             launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -916,25 +1122,27 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaStreamSynchronize(st));
         b->n_snv = tot[0]; b->n_indel = tot[1];
         if (b->n_snv > b->cap_snv) {
-            cudaFree(b->d_snv); b->d_snv = nullptr; b->cap_snv = 0;
-            CUDA_TRY(cudaMalloc(&b->d_snv, (size_t)b->n_snv * sizeof(int4)));
+            pav_dev_free(ctx, b->d_snv); b->d_snv = nullptr; b->cap_snv = 0;
+            CUDA_TRY(pav_dev_alloc_t(ctx, (size_t)b->n_snv, &b->d_snv));
             b->cap_snv = b->n_snv;
         }
         if (b->n_indel > b->cap_indel) {
-            cudaFree(b->d_stub); cudaFree(b->d_indel); b->d_stub = nullptr; b->d_indel = nullptr; b->cap_indel = 0;
-            CUDA_TRY(cudaMalloc(&b->d_stub, (size_t)b->n_indel * sizeof(IndelStub)));
-            CUDA_TRY(cudaMalloc(&b->d_indel, (size_t)b->n_indel * sizeof(pavgpu_indel_row)));
+            pav_dev_free(ctx, b->d_stub); pav_dev_free(ctx, b->d_indel); b->d_stub = nullptr; b->d_indel = nullptr; b->cap_indel = 0;
+            CUDA_TRY(pav_dev_alloc_t(ctx, (size_t)b->n_indel, &b->d_stub));
+            CUDA_TRY(pav_dev_alloc_t(ctx, (size_t)b->n_indel, &b->d_indel));
             b->cap_indel = b->n_indel;
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
         cigar_emit_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_pre_rq, b->d_pre_cnt,
-                                                                   qry_store->d_len, b->d_snv, b->d_stub, b->d_first_illegal);
+                                                                   b->d_recdesc, b->d_snv, b->d_stub, b->d_first_illegal);
         launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         if (b->n_indel > 0) {
-            unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
-            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, rv, planes_of(ref_store), planes_of(qry_store), b->d_indel, b->hom_sort);
+            const int ipw = hom_indels_per_warp(b->n_indel, ctx->sm_count);
+            unsigned hb = (unsigned)((b->n_indel + (int64_t)ipw * (HOM_THREADS / 32) - 1) / ((int64_t)ipw * (HOM_THREADS / 32)));
+            if (getenv("PAVGPU_HOM_TPI")) homology_tpi_kernel<<<(unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS), HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
+            else homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, ipw, pl_ref, pl_qry, b->d_indel);
             launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -986,8 +1194,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_fetch(p
     }
     pavgpu_snv_row *hs = nullptr;
     pavgpu_indel_row *hi = nullptr;
-    if (b->n_snv) { hs = (pavgpu_snv_row *)malloc((size_t)b->n_snv * sizeof(pavgpu_snv_row)); if (!hs) { pav_set_error("fetch: out of host memory"); return PAVGPU_ERR_NOMEM; } }
-    if (b->n_indel) { hi = (pavgpu_indel_row *)malloc((size_t)b->n_indel * sizeof(pavgpu_indel_row)); if (!hi) { free(hs); pav_set_error("fetch: out of host memory"); return PAVGPU_ERR_NOMEM; } }
+    PavTrace tr("cigar_batch_fetch");
+    if (b->n_snv) { int prc = pav_pinned_take(ctx, (size_t)b->n_snv * sizeof(pavgpu_snv_row), (void **)&hs); if (prc) return prc; }
+    if (b->n_indel) { int prc = pav_pinned_take(ctx, (size_t)b->n_indel * sizeof(pavgpu_indel_row), (void **)&hi); if (prc) { pavgpu_free_host(hs); return prc; } }
+    tr.mark("pinned buffers");
     int rc = [&]() -> int {
         CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
         if (b->n_snv) CUDA_TRY(cudaMemcpyAsync(hs, b->d_snv, (size_t)b->n_snv * sizeof(pavgpu_snv_row), cudaMemcpyDeviceToHost, ctx->stream));
@@ -996,7 +1206,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_fetch(p
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return PAVGPU_OK;
     }();
-    if (rc) { free(hs); free(hi); return rc; }
+    tr.mark("d2h");
+    if (rc) { pavgpu_free_host(hs); pavgpu_free_host(hi); return rc; }
     *snv_out = hs; *n_snv = b->n_snv; *indel_out = hi; *n_indel = b->n_indel;
     return PAVGPU_OK;
 }
@@ -1014,11 +1225,15 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_call(pavgpu_c
         }
     }
     pavgpu_cigar_batch *b = nullptr;
-    int rc = pavgpu_cigar_batch_create(ctx, n_rec, ref_seq_id, qry_seq_id, pos, rev, ops, op_off, &b);
+    PavTrace tr("cigar_call");
+    int rc = batch_create(ctx, n_rec, ref_seq_id, qry_seq_id, pos, rev, ops, op_off, true, &b);   // ops stay the caller's for the duration of the call
     if (rc) return rc;
+    tr.mark("create");
     rc = pavgpu_cigar_batch_run(b, ref_store, qry_store, stats);
+    tr.mark("run");
     if (!rc) rc = pavgpu_cigar_batch_fetch(b, snv_out, n_snv, indel_out, n_indel, err);
     if (!rc && stats) stats->ms_d2h = ev_ms(ctx->ev[5], ctx->ev[6]);
+    tr.mark("fetch");
     pavgpu_cigar_batch_free(b);
     return rc;
 }
@@ -1036,7 +1251,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_homology(pavgpu_ctx
     int32_t *d_l = nullptr, *d_r = nullptr;
     rc = [&]() -> int {
         if (n == 0) return PAVGPU_OK;
-        CUDA_TRY(cudaMalloc(&d_pos, (size_t)n * 8)); CUDA_TRY(cudaMalloc(&d_l, (size_t)n * 4)); CUDA_TRY(cudaMalloc(&d_r, (size_t)n * 4));
+        CUDA_TRY(pav_dev_alloc_t(ctx, (size_t)n, &d_pos)); CUDA_TRY(pav_dev_alloc_t(ctx, (size_t)n, &d_l)); CUDA_TRY(pav_dev_alloc_t(ctx, (size_t)n, &d_r));
         CUDA_TRY(cudaMemcpyAsync(d_pos, pos, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
         homology_probe_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(planes_of(st), n, d_pos, (int32_t)sv_len, d_l, d_r);
         CUDA_TRY(cudaGetLastError());
@@ -1045,7 +1260,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_homology(pavgpu_ctx
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return PAVGPU_OK;
     }();
-    cudaFree(d_pos); cudaFree(d_l); cudaFree(d_r);
+    pav_dev_free(ctx, d_pos); pav_dev_free(ctx, d_l); pav_dev_free(ctx, d_r);
     pavgpu_seqstore_free(st);
     return rc;
 }

@@ -209,10 +209,334 @@ done:
     return out;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole-frame builders: every column of df_snv / df_insdel in one pass over the device rows, already in
+ * the final (sorted) row order. Strings are written straight into exactly-sized compact ASCII str objects
+ * (length from digit counts; no scratch copy), shared values (chromosome, strand, HAP, SVTYPE, small
+ * "l,r" homology strings, single bases) are one object referenced many times.
+ * ------------------------------------------------------------------------------------------------ */
+static const char DIG2[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839"
+    "40414243444546474849505152535455565758596061626364656667686970717273747576777879"
+    "8081828384858687888990919293949596979899";
+
+static inline int ndig_u64(uint64_t v)
+{
+    int n = 1;
+    for (;;) {
+        if (v < 10) return n;
+        if (v < 100) return n + 1;
+        if (v < 1000) return n + 2;
+        if (v < 10000) return n + 3;
+        v /= 10000u; n += 4;
+    }
+}
+
+/* digits of v, most significant first, ending just before `end`; returns the first written byte */
+static inline char *put_u64_back(char *end, uint64_t v)
+{
+    while (v >= 100) { unsigned r = (unsigned)(v % 100); v /= 100; end -= 2; memcpy(end, DIG2 + 2 * r, 2); }
+    if (v >= 10) { end -= 2; memcpy(end, DIG2 + 2 * v, 2); }
+    else *--end = (char)('0' + v);
+    return end;
+}
+
+static inline int ndig_i64(int64_t v) { return v < 0 ? 1 + ndig_u64((uint64_t)(-(v + 1)) + 1u) : ndig_u64((uint64_t)v); }
+
+static inline char *put_i64_fwd(char *dst, int64_t v, int nd)   /* nd = ndig_i64(v) */
+{
+    uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1u : (uint64_t)v;
+    if (v < 0) *dst = '-';
+    put_u64_back(dst + nd, u);
+    return dst + nd;
+}
+
+typedef struct {   /* ASCII strings of a list, or failure */
+    Py_ssize_t n;
+    const char **s;
+    Py_ssize_t *len;
+} strtab_t;
+
+static int strtab_load(strtab_t *t, PyObject *list, const char *what)
+{
+    t->n = 0; t->s = NULL; t->len = NULL;
+    if (!PyList_Check(list)) { PyErr_Format(PyExc_TypeError, "%s must be a list of str", what); return -1; }
+    Py_ssize_t n = PyList_GET_SIZE(list);
+    t->s = (const char **)PyMem_Calloc((size_t)n + 1, sizeof(char *));
+    t->len = (Py_ssize_t *)PyMem_Calloc((size_t)n + 1, sizeof(Py_ssize_t));
+    if (!t->s || !t->len) { PyErr_NoMemory(); return -1; }
+    for (Py_ssize_t i = 0; i < n; i++) {
+        PyObject *o = PyList_GET_ITEM(list, i);
+        if (!PyUnicode_Check(o) || !PyUnicode_IS_ASCII(o)) { PyErr_Format(PyExc_ValueError, "%s: entry %zd is not an ASCII str", what, i); return -1; }
+        t->s[i] = (const char *)PyUnicode_1BYTE_DATA(o);
+        t->len[i] = PyUnicode_GET_LENGTH(o);
+    }
+    t->n = n;
+    return 0;
+}
+
+static void strtab_free(strtab_t *t) { PyMem_Free(t->s); PyMem_Free(t->len); }
+
+static int list_of(PyObject *o, Py_ssize_t n, const char *what)
+{
+    if (!PyList_Check(o) || PyList_GET_SIZE(o) < n) { PyErr_Format(PyExc_TypeError, "%s must be a list with one entry per record", what); return -1; }
+    return 0;
+}
+
+static inline void fill_const(PyObject **slots, Py_ssize_t n, PyObject *v)
+{
+    for (Py_ssize_t i = 0; i < n; i++) { Py_INCREF(v); slots[i] = v; }
+}
+
+#define SNV_NCOL 14
+#define INDEL_NCOL 16
+
+typedef struct { int32_t pos_ref, qry_pos, rec, op_idx; } snv_row_t;
+typedef struct { int32_t rec, op_idx, svtype, svlen, pos, end, qry_pos, qry_end, left_shift, hom_ref_l, hom_ref_r, hom_tig_l, hom_tig_r, seq_start, pad[2]; } indel_row_t;
+
+static PyObject *one_char_table[256];
+
+static PyObject *one_char(unsigned c)
+{
+    if (!one_char_table[c]) {
+        char ch = (char)c;
+        one_char_table[c] = PyUnicode_DecodeLatin1(&ch, 1, NULL);
+    }
+    return one_char_table[c];
+}
+
+/* snv_frame(rows, order, ref_b, alt_b, ids|None, chrom_objs, chrom_strs, qry_strs, strand_objs, align_index_objs, consts)
+ *   rows: pavgpu_snv_row buffer (emission order); order: int64 permutation (final row k shows emission row order[k]);
+ *   ref_b / alt_b: uint8 buffers, REF / ALT base per emission row (original case); ids: object ndarray of ready IDs in
+ *   emission order, or None to format "{chrom}-{pos+1}-SNV-{REF}{ALT}" (upper-cased bases) here;
+ *   consts = (svtype 'SNV', svlen 1, hap, ci 0, call_source)
+ * -> tuple of 14 object ndarrays in column order of the reference (pavlib/cigarcall.py:125-134). */
+static PyObject *py_snv_frame(PyObject *self, PyObject *args)
+{
+    Py_buffer rows, order, refb, altb;
+    PyObject *ids, *chrom_objs, *chrom_strs, *qry_strs, *strand_objs, *ai_objs, *consts;
+    if (!PyArg_ParseTuple(args, "y*y*y*y*OOOOOOO", &rows, &order, &refb, &altb, &ids, &chrom_objs, &chrom_strs, &qry_strs, &strand_objs, &ai_objs, &consts))
+        return NULL;
+    PyObject *result = NULL, *cols[SNV_NCOL] = {0};
+    PyObject **slot[SNV_NCOL];
+    strtab_t tc = {0}, tq = {0};
+    PyObject **id_src = NULL;
+    Py_ssize_t n = order.len / 8, n_rows = rows.len / (Py_ssize_t)sizeof(snv_row_t);
+    if (refb.len < n_rows || altb.len < n_rows || n > n_rows) { PyErr_SetString(PyExc_ValueError, "snv_frame: buffer sizes disagree"); goto done; }
+    if (strtab_load(&tc, chrom_strs, "chrom_strs") < 0 || strtab_load(&tq, qry_strs, "qry_strs") < 0) goto done;
+    Py_ssize_t n_rec = tc.n;
+    if (tq.n < n_rec || list_of(chrom_objs, n_rec, "chrom_objs") < 0 || list_of(strand_objs, n_rec, "strand_objs") < 0 || list_of(ai_objs, n_rec, "align_index_objs") < 0) {
+        if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "snv_frame: per-record lists disagree");
+        goto done;
+    }
+    if (!PyTuple_Check(consts) || PyTuple_GET_SIZE(consts) != 5) { PyErr_SetString(PyExc_TypeError, "snv_frame: consts must be a 5-tuple"); goto done; }
+    if (ids != Py_None) {
+        if (!PyArray_Check(ids) || PyArray_TYPE((PyArrayObject *)ids) != NPY_OBJECT || PyArray_NDIM((PyArrayObject *)ids) != 1 ||
+            PyArray_DIM((PyArrayObject *)ids, 0) < n_rows || !PyArray_IS_C_CONTIGUOUS((PyArrayObject *)ids)) {
+            PyErr_SetString(PyExc_TypeError, "snv_frame: ids must be a contiguous 1-D object array with one entry per row"); goto done;
+        }
+        id_src = (PyObject **)PyArray_DATA((PyArrayObject *)ids);
+    }
+    for (int c = 0; c < SNV_NCOL; c++) { cols[c] = new_obj_array(n, &slot[c]); if (!cols[c]) goto done; }
+    {
+        const snv_row_t *R = (const snv_row_t *)rows.buf;
+        const int64_t *ord = (const int64_t *)order.buf;
+        const uint8_t *rb = (const uint8_t *)refb.buf, *ab = (const uint8_t *)altb.buf;
+        PyObject *c_svtype = PyTuple_GET_ITEM(consts, 0), *c_svlen = PyTuple_GET_ITEM(consts, 1), *c_hap = PyTuple_GET_ITEM(consts, 2),
+                 *c_ci = PyTuple_GET_ITEM(consts, 3), *c_src = PyTuple_GET_ITEM(consts, 4);
+        fill_const(slot[4], n, c_svtype); fill_const(slot[5], n, c_svlen); fill_const(slot[8], n, c_hap);
+        fill_const(slot[11], n, c_ci); fill_const(slot[13], n, c_src);
+        for (Py_ssize_t k = 0; k < n; k++) {
+            int64_t i = ord[k];
+            if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "snv_frame: order entry out of range"); goto done; }
+            const snv_row_t r = R[i];
+            if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "snv_frame: record index out of range"); goto done; }
+            PyObject *o;
+            o = PyList_GET_ITEM(chrom_objs, r.rec); Py_INCREF(o); slot[0][k] = o;
+            if (!(slot[1][k] = PyLong_FromLong(r.pos_ref))) goto done;
+            if (!(slot[2][k] = PyLong_FromLong((long)r.pos_ref + 1))) goto done;
+            if (id_src) { o = id_src[i]; Py_INCREF(o); slot[3][k] = o; }
+            else {   /* {chrom}-{pos+1}-SNV-{REF}{ALT} */
+                int64_t p1 = (int64_t)r.pos_ref + 1;
+                int nd = ndig_i64(p1);
+                Py_ssize_t cl = tc.len[r.rec], len = cl + 1 + nd + 5 + 2;
+                if (!(o = PyUnicode_New(len, 127))) goto done;
+                char *d = (char *)PyUnicode_1BYTE_DATA(o);
+                memcpy(d, tc.s[r.rec], (size_t)cl); d += cl;
+                *d++ = '-'; d = put_i64_fwd(d, p1, nd);
+                memcpy(d, "-SNV-", 5); d += 5;
+                unsigned a = rb[i], b = ab[i];
+                *d++ = (char)((a >= 'a' && a <= 'z') ? a - 32 : a);
+                *d++ = (char)((b >= 'a' && b <= 'z') ? b - 32 : b);
+                if ((rb[i] | ab[i]) & 0x80) { Py_DECREF(o); PyErr_SetString(PyExc_ValueError, "snv_frame: non-ASCII base"); goto done; }
+                slot[3][k] = o;
+            }
+            if (!(o = one_char(rb[i]))) goto done; Py_INCREF(o); slot[6][k] = o;
+            if (!(o = one_char(ab[i]))) goto done; Py_INCREF(o); slot[7][k] = o;
+            {   /* {qry}:{qp+1}-{qp+1} */
+                int64_t q1 = (int64_t)r.qry_pos + 1;
+                int nd = ndig_i64(q1);
+                Py_ssize_t ql = tq.len[r.rec], len = ql + 1 + nd + 1 + nd;
+                if (!(o = PyUnicode_New(len, 127))) goto done;
+                char *d = (char *)PyUnicode_1BYTE_DATA(o);
+                memcpy(d, tq.s[r.rec], (size_t)ql); d += ql;
+                *d++ = ':'; d = put_i64_fwd(d, q1, nd);
+                *d++ = '-'; d = put_i64_fwd(d, q1, nd);
+                slot[9][k] = o;
+            }
+            o = PyList_GET_ITEM(strand_objs, r.rec); Py_INCREF(o); slot[10][k] = o;
+            o = PyList_GET_ITEM(ai_objs, r.rec); Py_INCREF(o); slot[12][k] = o;
+        }
+    }
+    result = PyTuple_New(SNV_NCOL);
+    if (result) for (int c = 0; c < SNV_NCOL; c++) { PyTuple_SET_ITEM(result, c, cols[c]); cols[c] = NULL; }
+done:
+    for (int c = 0; c < SNV_NCOL; c++) Py_XDECREF(cols[c]);
+    strtab_free(&tc); strtab_free(&tq);
+    PyBuffer_Release(&rows); PyBuffer_Release(&order); PyBuffer_Release(&refb); PyBuffer_Release(&altb);
+    return result;
+}
+
+#define HOM_CACHE 64
+static PyObject *hom_cache[HOM_CACHE][HOM_CACHE];
+
+static PyObject *hom_str(int32_t l, int32_t r)   /* new reference to "l,r" */
+{
+    int cached = l >= 0 && r >= 0 && l < HOM_CACHE && r < HOM_CACHE;
+    if (cached && hom_cache[l][r]) { Py_INCREF(hom_cache[l][r]); return hom_cache[l][r]; }
+    int nl = ndig_i64(l), nr = ndig_i64(r);
+    PyObject *o = PyUnicode_New(nl + 1 + nr, 127);
+    if (!o) return NULL;
+    char *d = (char *)PyUnicode_1BYTE_DATA(o);
+    d = put_i64_fwd(d, l, nl); *d++ = ','; put_i64_fwd(d, r, nr);
+    if (cached) { hom_cache[l][r] = o; Py_INCREF(o); }
+    return o;
+}
+
+/* indel_frame(rows, order, ids|None, chrom_objs, chrom_strs, qry_strs, strand_objs, align_index_objs, ref_id, qry_id, rev,
+ *             seqs, n_ref, comp, consts)
+ *   rows: pavgpu_indel_row buffer (emission order); ref_id / qry_id: int32 per record; rev: uint8 per record;
+ *   seqs: list of uint8 buffers = reference sequences then contigs (forward strand); comp: 256-byte complement table;
+ *   consts = ('INS', 'DEL', hap, ci 0, call_source)
+ * -> tuple of 16 object ndarrays in column order of the reference (pavlib/cigarcall.py:199-209). */
+static PyObject *py_indel_frame(PyObject *self, PyObject *args)
+{
+    Py_buffer rows, order, ref_id, qry_id, rev, comp;
+    PyObject *ids, *chrom_objs, *chrom_strs, *qry_strs, *strand_objs, *ai_objs, *seqs, *consts;
+    Py_ssize_t n_ref;
+    if (!PyArg_ParseTuple(args, "y*y*OOOOOOy*y*y*O!ny*O", &rows, &order, &ids, &chrom_objs, &chrom_strs, &qry_strs, &strand_objs, &ai_objs,
+                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &consts))
+        return NULL;
+    PyObject *result = NULL, *cols[INDEL_NCOL] = {0};
+    PyObject **slot[INDEL_NCOL];
+    strtab_t tc = {0}, tq = {0};
+    PyObject **id_src = NULL;
+    Py_ssize_t n = order.len / 8, n_rows = rows.len / (Py_ssize_t)sizeof(indel_row_t), nd_seq = PyList_GET_SIZE(seqs), got = 0;
+    Py_buffer *bufs = (Py_buffer *)PyMem_Calloc((size_t)nd_seq + 1, sizeof(Py_buffer));
+    char *scratch = NULL; Py_ssize_t cap = 0;
+    if (!bufs) { PyErr_NoMemory(); goto done; }
+    if (n > n_rows || comp.len < 256) { PyErr_SetString(PyExc_ValueError, "indel_frame: buffer sizes disagree"); goto done; }
+    if (strtab_load(&tc, chrom_strs, "chrom_strs") < 0 || strtab_load(&tq, qry_strs, "qry_strs") < 0) goto done;
+    Py_ssize_t n_rec = tc.n;
+    if (tq.n < n_rec || ref_id.len < n_rec * 4 || qry_id.len < n_rec * 4 || rev.len < n_rec || list_of(chrom_objs, n_rec, "chrom_objs") < 0 ||
+        list_of(strand_objs, n_rec, "strand_objs") < 0 || list_of(ai_objs, n_rec, "align_index_objs") < 0) {
+        if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "indel_frame: per-record arrays disagree");
+        goto done;
+    }
+    if (!PyTuple_Check(consts) || PyTuple_GET_SIZE(consts) != 5) { PyErr_SetString(PyExc_TypeError, "indel_frame: consts must be a 5-tuple"); goto done; }
+    if (ids != Py_None) {
+        if (!PyArray_Check(ids) || PyArray_TYPE((PyArrayObject *)ids) != NPY_OBJECT || PyArray_NDIM((PyArrayObject *)ids) != 1 ||
+            PyArray_DIM((PyArrayObject *)ids, 0) < n_rows || !PyArray_IS_C_CONTIGUOUS((PyArrayObject *)ids)) {
+            PyErr_SetString(PyExc_TypeError, "indel_frame: ids must be a contiguous 1-D object array with one entry per row"); goto done;
+        }
+        id_src = (PyObject **)PyArray_DATA((PyArrayObject *)ids);
+    }
+    for (; got < nd_seq; got++)
+        if (PyObject_GetBuffer(PyList_GET_ITEM(seqs, got), &bufs[got], PyBUF_SIMPLE) < 0) goto done;
+    for (int c = 0; c < INDEL_NCOL; c++) { cols[c] = new_obj_array(n, &slot[c]); if (!cols[c]) goto done; }
+    {
+        const indel_row_t *R = (const indel_row_t *)rows.buf;
+        const int64_t *ord = (const int64_t *)order.buf;
+        const int32_t *rid = (const int32_t *)ref_id.buf, *qid = (const int32_t *)qry_id.buf;
+        const uint8_t *rv = (const uint8_t *)rev.buf, *ct = (const uint8_t *)comp.buf;
+        PyObject *c_ins = PyTuple_GET_ITEM(consts, 0), *c_del = PyTuple_GET_ITEM(consts, 1), *c_hap = PyTuple_GET_ITEM(consts, 2),
+                 *c_ci = PyTuple_GET_ITEM(consts, 3), *c_src = PyTuple_GET_ITEM(consts, 4);
+        fill_const(slot[6], n, c_hap); fill_const(slot[9], n, c_ci); fill_const(slot[14], n, c_src);
+        for (Py_ssize_t k = 0; k < n; k++) {
+            int64_t i = ord[k];
+            if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "indel_frame: order entry out of range"); goto done; }
+            const indel_row_t r = R[i];
+            if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "indel_frame: record index out of range"); goto done; }
+            const int is_del = r.svtype == 1;
+            PyObject *o;
+            o = PyList_GET_ITEM(chrom_objs, r.rec); Py_INCREF(o); slot[0][k] = o;
+            if (!(slot[1][k] = PyLong_FromLong(r.pos))) goto done;
+            if (!(slot[2][k] = PyLong_FromLong(r.end))) goto done;
+            if (id_src) { o = id_src[i]; Py_INCREF(o); slot[3][k] = o; }
+            else {   /* {chrom}-{pos+1}-{INS|DEL}-{svlen} */
+                int64_t p1 = (int64_t)r.pos + 1;
+                int nd = ndig_i64(p1), nl = ndig_i64(r.svlen);
+                Py_ssize_t cl = tc.len[r.rec], len = cl + 1 + nd + 5 + nl;
+                if (!(o = PyUnicode_New(len, 127))) goto done;
+                char *d = (char *)PyUnicode_1BYTE_DATA(o);
+                memcpy(d, tc.s[r.rec], (size_t)cl); d += cl;
+                *d++ = '-'; d = put_i64_fwd(d, p1, nd);
+                memcpy(d, is_del ? "-DEL-" : "-INS-", 5); d += 5;
+                put_i64_fwd(d, r.svlen, nl);
+                slot[3][k] = o;
+            }
+            o = is_del ? c_del : c_ins; Py_INCREF(o); slot[4][k] = o;
+            if (!(slot[5][k] = PyLong_FromLong(r.svlen))) goto done;
+            {   /* {qry}:{qp+1}-{qe}  (DEL: qe = qp+1) */
+                int64_t q1 = (int64_t)r.qry_pos + 1, q2 = is_del ? q1 : (int64_t)r.qry_end;
+                int n1 = ndig_i64(q1), n2 = ndig_i64(q2);
+                Py_ssize_t ql = tq.len[r.rec], len = ql + 1 + n1 + 1 + n2;
+                if (!(o = PyUnicode_New(len, 127))) goto done;
+                char *d = (char *)PyUnicode_1BYTE_DATA(o);
+                memcpy(d, tq.s[r.rec], (size_t)ql); d += ql;
+                *d++ = ':'; d = put_i64_fwd(d, q1, n1);
+                *d++ = '-'; put_i64_fwd(d, q2, n2);
+                slot[7][k] = o;
+            }
+            o = PyList_GET_ITEM(strand_objs, r.rec); Py_INCREF(o); slot[8][k] = o;
+            o = PyList_GET_ITEM(ai_objs, r.rec); Py_INCREF(o); slot[10][k] = o;
+            if (!(slot[11][k] = PyLong_FromLong(r.left_shift))) goto done;
+            if (!(slot[12][k] = hom_str(r.hom_ref_l, r.hom_ref_r))) goto done;
+            if (!(slot[13][k] = hom_str(r.hom_tig_l, r.hom_tig_r))) goto done;
+            {   /* SEQ: DEL = reference[pos : pos+n] (unshifted); INS = forward contig[qry_pos : qry_end], reverse-complemented for
+                 * minus-strand records (equals the slice of the reference-oriented contig, cigarcall.py:160,236) */
+                Py_ssize_t w = is_del ? (Py_ssize_t)rid[r.rec] : n_ref + (Py_ssize_t)qid[r.rec];
+                int64_t s0 = is_del ? r.pos : r.qry_pos, l = r.svlen;
+                if (w < 0 || w >= nd_seq || s0 < 0 || l < 0 || s0 + l > bufs[w].len) { PyErr_SetString(PyExc_IndexError, "indel_frame: SEQ range outside sequence"); goto done; }
+                const uint8_t *src = (const uint8_t *)bufs[w].buf + s0;
+                if (!is_del && rv[r.rec]) {
+                    if (l > cap) { PyMem_Free(scratch); cap = l * 2 + 64; scratch = (char *)PyMem_Malloc((size_t)cap); if (!scratch) { cap = 0; PyErr_NoMemory(); goto done; } }
+                    for (int64_t j = 0; j < l; j++) scratch[j] = (char)ct[src[l - 1 - j]];
+                    o = l == 1 ? one_char((unsigned char)scratch[0]) : PyUnicode_DecodeLatin1(scratch, l, NULL);
+                } else o = l == 1 ? one_char(src[0]) : PyUnicode_DecodeLatin1((const char *)src, l, NULL);
+                if (!o) goto done;
+                if (l == 1) Py_INCREF(o);
+                slot[15][k] = o;
+            }
+        }
+    }
+    result = PyTuple_New(INDEL_NCOL);
+    if (result) for (int c = 0; c < INDEL_NCOL; c++) { PyTuple_SET_ITEM(result, c, cols[c]); cols[c] = NULL; }
+done:
+    for (int c = 0; c < INDEL_NCOL; c++) Py_XDECREF(cols[c]);
+    PyMem_Free(scratch);
+    if (bufs) { for (Py_ssize_t j = 0; j < got; j++) PyBuffer_Release(&bufs[j]); PyMem_Free(bufs); }
+    strtab_free(&tc); strtab_free(&tq);
+    PyBuffer_Release(&rows); PyBuffer_Release(&order); PyBuffer_Release(&ref_id); PyBuffer_Release(&qry_id); PyBuffer_Release(&rev); PyBuffer_Release(&comp);
+    return result;
+}
+
 static PyMethodDef methods[] = {
     {"format", py_format, METH_VARARGS, "format(n, parts) -> list of str"},
     {"ints", py_ints, METH_O, "ints(int64 buffer) -> list of int"},
     {"slices", py_slices, METH_VARARGS, "slices(data list, which, start, length, rc, comp) -> list of str"},
+    {"snv_frame", py_snv_frame, METH_VARARGS, "all 14 columns of df_snv in final row order"},
+    {"indel_frame", py_indel_frame, METH_VARARGS, "all 16 columns of df_insdel in final row order"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_pyrows", "row formatting helpers", -1, methods};

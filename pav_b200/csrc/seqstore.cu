@@ -4,8 +4,12 @@
 // pysam fetch of whole chromosomes/contigs, Bio reverse_complement and str.upper()
 // (pavlib/cigarcall.py:58-75) and the per-base dict lookups of kanapy's k-mer stream
 // (dep/svpop/dep/kanapy/util/kmer.py:50-69,206-221).
+#include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -42,23 +46,120 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_ctx_create(int devi
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    if (const char *mx = getenv("PAVGPU_POOL_MAX_MB")) c->pool_max_free = (size_t)strtoull(mx, nullptr, 10) << 20;
     *ctx_out = c;
     return PAVGPU_OK;
+}
+
+// ---- pinned result buffers ----------------------------------------------------------------------
+static std::mutex g_pinned_mu;
+static std::unordered_map<void *, pavgpu_ctx *> g_pinned_owner;   // in-use pinned blocks -> owning context (nullptr: context gone)
+
+int pav_pinned_take(pavgpu_ctx *ctx, size_t bytes, void **out)
+{
+    size_t need = bytes < 4096 ? 4096 : bytes;
+    int best = -1;
+    for (size_t i = 0; i < ctx->pinned.size(); i++) {
+        const PavDevBlock &b = ctx->pinned[i];
+        if (!b.used && b.bytes >= need && b.bytes / 4 <= need + ((size_t)1 << 20) && (best < 0 || b.bytes < ctx->pinned[best].bytes)) best = (int)i;
+    }
+    if (best < 0) {
+        size_t sz = need < ((size_t)1 << 20) ? (need + 4095) / 4096 * 4096 : (need + need / 8 + ((size_t)1 << 20) - 1) >> 20 << 20;
+        void *p = nullptr;
+        cudaError_t e = cudaHostAlloc(&p, sz, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            pav_set_error("cudaHostAlloc(%zu) failed: %s", sz, cudaGetErrorString(e));
+            return PAVGPU_ERR_NOMEM;
+        }
+        ctx->pinned.push_back(PavDevBlock{p, sz, false});
+        best = (int)ctx->pinned.size() - 1;
+    }
+    ctx->pinned[best].used = true;
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        g_pinned_owner[ctx->pinned[best].ptr] = ctx;
+    }
+    *out = ctx->pinned[best].ptr;
+    return PAVGPU_OK;
+}
+
+bool pav_pinned_give(void *ptr)
+{
+    pavgpu_ctx *ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        auto it = g_pinned_owner.find(ptr);
+        if (it == g_pinned_owner.end()) return false;
+        ctx = it->second;
+        g_pinned_owner.erase(it);
+    }
+    if (!ctx) { cudaFreeHost(ptr); return true; }   // the context was destroyed while the caller still held the buffer
+    size_t free_bytes = 0;
+    for (auto &b : ctx->pinned) if (!b.used) free_bytes += b.bytes;
+    for (size_t i = 0; i < ctx->pinned.size(); i++) {
+        if (ctx->pinned[i].ptr != ptr) continue;
+        if (free_bytes + ctx->pinned[i].bytes > ((size_t)8 << 30)) {   // keep at most 8 GiB of idle pinned memory
+            cudaFreeHost(ptr);
+            ctx->pinned[i] = ctx->pinned.back();
+            ctx->pinned.pop_back();
+        } else ctx->pinned[i].used = false;
+        break;
+    }
+    return true;
+}
+
+// ---- trace ---------------------------------------------------------------------------------------
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+PavTrace::PavTrace(const char *n) : name(n)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("PAVGPU_TRACE"); enabled = (e && e[0] == '1') ? 1 : 0; }
+    on = enabled == 1;
+    if (on) t0 = last = now_ms();
+}
+
+void PavTrace::mark(const char *label)
+{
+    if (!on) return;
+    double t = now_ms();
+    fprintf(stderr, "[pavgpu trace] %-28s %-26s %9.3f ms\n", name, label, t - last);
+    last = t;
+}
+
+PavTrace::~PavTrace()
+{
+    if (on) fprintf(stderr, "[pavgpu trace] %-28s %-26s %9.3f ms\n", name, "TOTAL", now_ms() - t0);
 }
 
 extern "C" __attribute__((visibility("default"))) void pavgpu_ctx_destroy(pavgpu_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
     for (auto &e : c->ev) cudaEventDestroy(e);
     cudaFree(c->flush_buf);
-    for (int i = 0; i < pavgpu_ctx::N_CACHE; i++) cudaFree(c->cache_ptr[i]);
+    for (auto &b : c->pool) cudaFree(b.ptr);   // blocks still marked used belong to objects the caller leaked; the memory goes with the context
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        for (auto &b : c->pinned) {
+            if (!b.used) cudaFreeHost(b.ptr);
+            else g_pinned_owner[b.ptr] = nullptr;   // still held by the caller: released by pavgpu_free_host later
+        }
+    }
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
 extern "C" __attribute__((visibility("default"))) int pavgpu_ctx_device(const pavgpu_ctx *c) { return c ? c->device : -1; }
-extern "C" __attribute__((visibility("default"))) void pavgpu_free_host(void *p) { free(p); }
+extern "C" __attribute__((visibility("default"))) void pavgpu_free_host(void *p)
+{
+    if (p && !pav_pinned_give(p)) free(p);
+}
 
 extern "C" __attribute__((visibility("default"))) int pavgpu_l2_flush(pavgpu_ctx *ctx, size_t bytes)
 {
@@ -111,12 +212,50 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ a
     nmask[w] = mask;
 }
 
+// Window plane (common.cuh, WSeq): unit u = the 40 bases from 8u on + their mask bits, cut out of two consecutive words.
+__global__ void __launch_bounds__(256) win_build_kernel(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t n_words,
+                                                        uint4 *__restrict__ win, int64_t n_units)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const int64_t w0 = u >> 2;
+    const int o = (int)(u & 3) * 8;   // first base of the unit inside word w0: 0, 8, 16, 24
+    const uint64_t p0 = __ldg(pack2 + w0), p1 = (w0 + 1 < n_words) ? __ldg(pack2 + w0 + 1) : 0ull;
+    const uint32_t m0 = __ldg(nmask + w0), m1 = (w0 + 1 < n_words) ? __ldg(nmask + w0 + 1) : 0xffffffffu;
+    const uint64_t hi = o ? ((p0 << (2 * o)) | (p1 >> (64 - 2 * o))) : p0;
+    const uint32_t lo16 = (uint32_t)((p1 << (2 * o)) >> 48);
+    const uint64_t m40 = (((uint64_t)m1 << 32) | (uint64_t)m0) >> o;
+    win[u] = make_uint4((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)m40, (lo16 << 16) | ((uint32_t)(m40 >> 32) & 0xffu));
+}
+
+int pav_seqstore_window_plane(const pavgpu_seqstore *s, const uint4 **out)
+{
+    if (!s->d_win) {
+        const int64_t n_units = s->total_bases / 8, n_words = s->total_bases / 32;
+        uint4 *w = nullptr;
+        cudaError_t e = pav_dev_alloc_t(s->ctx, (size_t)n_units, &w);
+        if (e != cudaSuccess) { pav_set_error("seqstore: cudaMalloc(%lld) for the window plane failed: %s", (long long)n_units * 16, cudaGetErrorString(e)); return PAVGPU_ERR_NOMEM; }
+        win_build_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, s->ctx->stream>>>(s->d_pack2, s->d_nmask, n_words, w, n_units);
+        CUDA_TRY(cudaGetLastError());
+        s->d_win = w;
+    }
+    *out = s->d_win;
+    return PAVGPU_OK;
+}
+
+void pav_seqstore_drop_window_plane(pavgpu_seqstore *s)
+{
+    if (s->d_win) { cudaStreamSynchronize(s->ctx->stream); pav_dev_free(s->ctx, s->d_win); s->d_win = nullptr; }
+}
+
 static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, pavgpu_seqstore **out)
 {
     if (!ctx || n_seq < 0 || (n_seq > 0 && !seq_len) || !out) { pav_set_error("seqstore: bad argument"); return PAVGPU_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(ctx->device));
+    static std::atomic<uint64_t> next_uid{1};
     pavgpu_seqstore *s = new pavgpu_seqstore();
     s->ctx = ctx;
+    s->uid = next_uid.fetch_add(1);
     s->n_seq = n_seq;
     s->h_off.resize(n_seq);
     s->h_len.assign(seq_len, seq_len + n_seq);
@@ -138,9 +277,9 @@ static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, p
     s->d_pack2 = nullptr;
     s->d_nmask = nullptr;
     cudaError_t e;
-    if ((e = cudaMalloc(&s->d_pack2, s->pack2_bytes)) != cudaSuccess || (e = cudaMalloc(&s->d_nmask, s->nmask_bytes)) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_off, sizeof(int64_t) * (n_seq + 1))) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_len, sizeof(int64_t) * (n_seq + 1))) != cudaSuccess) {
+    if ((e = pav_dev_alloc_t(ctx, s->pack2_bytes / 8, &s->d_pack2)) != cudaSuccess || (e = pav_dev_alloc_t(ctx, s->nmask_bytes / 4, &s->d_nmask)) != cudaSuccess ||
+        (e = pav_dev_alloc_t(ctx, (size_t)n_seq + 1, &s->d_off)) != cudaSuccess ||
+        (e = pav_dev_alloc_t(ctx, (size_t)n_seq + 1, &s->d_len)) != cudaSuccess) {
         pav_set_error("seqstore: cudaMalloc failed: %s", cudaGetErrorString(e));
         pavgpu_seqstore_free(s);
         return PAVGPU_ERR_NOMEM;
@@ -163,9 +302,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
                                       pavgpu_seqstore **out)
 {
     if (n_seq > 0 && !seq_ascii) { pav_set_error("seqstore: seq_ascii is NULL"); return PAVGPU_ERR_ARG; }
+    PavTrace tr("seqstore_create");
     pavgpu_seqstore *s = nullptr;
     int rc = alloc_store(ctx, n_seq, seq_len, &s);
     if (rc) return rc;
+    tr.mark("alloc planes");
     // Stage ASCII in HBM ('N' in the padding so that padding bases get mask = 1), then pack.
     uint8_t *d_ascii = nullptr;
     size_t ascii_cap = 0;
@@ -184,7 +325,9 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
         int64_t blocks = (n_words + 255) / 256;
         pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_ascii, n_words, s->d_pack2, s->d_nmask);
         CUDA_TRY(cudaGetLastError());
+        tr.mark("enqueue h2d + pack");
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        tr.mark("sync");
         return PAVGPU_OK;
     }();
     ctx_arena_give(ctx, d_ascii, ascii_cap);
@@ -214,10 +357,11 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_seqstore_free(pavg
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaFree(s->d_pack2);
-    cudaFree(s->d_nmask);
-    cudaFree(s->d_off);
-    cudaFree(s->d_len);
+    pav_dev_free(s->ctx, s->d_win);
+    pav_dev_free(s->ctx, s->d_pack2);
+    pav_dev_free(s->ctx, s->d_nmask);
+    pav_dev_free(s->ctx, s->d_off);
+    pav_dev_free(s->ctx, s->d_len);
     delete s;
 }
 

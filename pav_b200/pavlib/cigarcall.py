@@ -28,6 +28,7 @@ _OP_CHAR = 'MIDNSHP=X'
 # statistics of the last call (device timings etc.), for bench.py
 last_stats = None
 last_phase_seconds = None   # host-side phase breakdown of the last make_insdel_snv_calls
+last_walk_seconds = None    # breakdown of the device phase (stores, CIGAR tokenizer, pavgpu_cigar_call)
 
 
 def _first_seen(values):
@@ -38,8 +39,9 @@ def _first_seen(values):
     return seen
 
 
-def _sort_order(chrom_codes, pos, end, ids, end_is_pos_plus_1=False):
-    """Permutation equal to pandas' stable ``sort_values(['#CHROM','POS','END','ID'])``."""
+def _sort_order(chrom_codes, pos, end, id_of, end_is_pos_plus_1=False):
+    """Permutation equal to pandas' stable ``sort_values(['#CHROM','POS','END','ID'])``. ``id_of(i)`` gives the ID of
+    emission row ``i``; it is only asked for rows that tie on (chrom, pos, end)."""
     if end_is_pos_plus_1 and len(pos) and int(pos.max()) < (1 << 40) and int(chrom_codes.max()) < (1 << 22):
         # SNV rows: END = POS + 1, so one composite key orders them; rows arrive nearly sorted (records are sorted by
         # #CHROM, POS), which the stable merge sort exploits
@@ -57,7 +59,7 @@ def _sort_order(chrom_codes, pos, end, ids, end_is_pos_plus_1=False):
                 while t < len(tie) and tie[t]:
                     t += 1
                 grp = order[s:t + 1]
-                grp_ids = [ids[i] for i in grp.tolist()]
+                grp_ids = [id_of(i) for i in grp.tolist()]
                 order[s:t + 1] = grp[np.array(sorted(range(len(grp)), key=grp_ids.__getitem__), dtype=np.int64)]
     return order
 
@@ -115,20 +117,27 @@ def walk_rows(table, ref_arr, tig_arr, ctx=None, ref_store=None):
     reference) whose sequence order matches ``table.ref_names``.
 
     Returns ``(snv rows, indel rows)`` in emission order; raises the reference's exceptions for bad CIGARs."""
-    global last_stats
+    global last_stats, last_walk_seconds
     ctx = ctx or device.get_context()
     own_ref = ref_store is None
+    t0 = time.perf_counter()
     if own_ref:
         ref_store = device.SeqStore(ctx, list(table.ref_names), ref_arr, keep_host=False)
+    t1 = time.perf_counter()
     tig_store = device.SeqStore(ctx, list(table.tig_names), tig_arr, keep_host=False)
+    t2 = time.perf_counter()
     try:
         ops, op_off, perr = device.parse_cigars(table.cigars)
+        t3 = time.perf_counter()
         snv, indel, cerr, stats = device.cigar_call(ctx, ref_store, tig_store, table.ref_id, table.qry_id,
                                                     table.pos.astype(np.int32), table.rev.astype(np.uint8), ops, op_off)
+        t4 = time.perf_counter()
     finally:
         if own_ref:
             ref_store.close()
         tig_store.close()
+    last_walk_seconds = {'ref_store': t1 - t0, 'tig_store': t2 - t1, 'cigar_parse': t3 - t2, 'cigar_call': t4 - t3,
+                         'close': time.perf_counter() - t4}
     last_stats = stats.as_dict()
     # Errors surface in walk order (the reference raises lazily while iterating records and ops)
     if cerr.code == 1 and (perr.code == 0 or (cerr.rec, cerr.op_index) < (perr.rec, perr.op_index)):
@@ -231,18 +240,24 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
 def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id):
     from .. import _pyrows
     n_rec = len(chrom)
-    chrom_l = [f'{c}' for c in chrom.tolist()]
+    chrom_objs, ai_objs = chrom.tolist(), align_index.tolist()
+    chrom_l = [f'{c}' for c in chrom_objs]
     qry_l = [f'{q}' for q in qry.tolist()]
     chrom_rank = {c: i for i, c in enumerate(sorted(set(chrom_l)))}
     chrom_code_rec = np.array([chrom_rank[c] for c in chrom_l], dtype=np.int64)
-    strand_rec = np.where(rev, '-', '+').astype(object)
+    strand_objs = ['-' if r else '+' for r in rev.tolist()]
+    ref_id32 = np.ascontiguousarray(ref_id, dtype=np.int32)
+    qry_id32 = np.ascontiguousarray(qry_id, dtype=np.int32)
+    rev8 = np.ascontiguousarray(rev, dtype=np.uint8)
+    ascii_names = all(x.isascii() for x in chrom_l) and all(x.isascii() for x in qry_l)
 
     # ------------------------------------------------------------------ SNV rows (cigarcall.py:98-135)
     if len(snv):
         n = len(snv)
-        rec = snv['rec'].astype(np.int64)
+        snv = np.ascontiguousarray(snv)
+        rec = snv['rec']
         pos = snv['pos_ref'].astype(np.int64)
-        qp = snv['qry_pos'].astype(np.int64)
+        qp = snv['qry_pos']
         ref_b = np.empty(n, dtype=np.uint8)
         alt_b = np.empty(n, dtype=np.uint8)
         bounds = np.searchsorted(rec, np.arange(n_rec + 1))
@@ -251,59 +266,81 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
             ref_b[a:b] = ref_arr[ref_id[r]][pos[a:b]]
             t = tig_arr[qry_id[r]][qp[a:b]]
             alt_b[a:b] = fasta.COMPLEMENT[t] if rev[r] else t
-        ids = _pyrows.format(n, [('l', chrom_l, rec), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
-                                 ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
-        if version_id:
-            ids = variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object)
-        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, ids, end_is_pos_plus_1=True)
-        rec, pos, qp, ref_b, alt_b = rec[order], pos[order], qp[order], ref_b[order], alt_b[order]
-        pos1, qp1 = pos + 1, qp + 1
-        cols = {
-            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(pos1), 'ID': ids[order],
-            'SVTYPE': 'SNV', 'SVLEN': 1, 'REF': _CHR[ref_b], 'ALT': _CHR[alt_b], 'HAP': hap,
-            'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec), ('s', ':'), ('i', qp1), ('s', '-'), ('i', qp1)]),
-            'QRY_STRAND': strand_rec[rec], 'CI': 0, 'ALIGN_INDEX': align_index[rec], 'CALL_SOURCE': CALL_SOURCE,
-        }
-        df_snv = _frame(cols, SNV_COLUMNS, order)
+        ids = None
+        if version_id or not ascii_names:
+            ids = _pyrows.format(n, [('l', chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
+                                     ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
+            if version_id:
+                ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
+            id_of = ids.__getitem__
+        else:
+            def id_of(i):
+                return f'{chrom_l[rec[i]]}-{pos[i] + 1}-SNV-{chr(fasta.UPPER[ref_b[i]])}{chr(fasta.UPPER[alt_b[i]])}'
+        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, id_of, end_is_pos_plus_1=True)
+        if ascii_names:
+            cols = _pyrows.snv_frame(snv.view(np.uint8), order, ref_b, alt_b, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs,
+                                     ('SNV', 1, hap, 0, CALL_SOURCE))
+            df_snv = _frame(dict(zip(SNV_COLUMNS, cols)), SNV_COLUMNS, order)
+        else:   # names outside ASCII: generic formatter
+            rec64, pos_o, qp1 = rec[order].astype(np.int64), pos[order], qp[order].astype(np.int64) + 1
+            cols = {
+                '#CHROM': chrom[rec64], 'POS': _pyrows.ints(pos_o), 'END': _pyrows.ints(pos_o + 1), 'ID': ids[order],
+                'SVTYPE': 'SNV', 'SVLEN': 1, 'REF': _CHR[ref_b[order]], 'ALT': _CHR[alt_b[order]], 'HAP': hap,
+                'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec64), ('s', ':'), ('i', qp1), ('s', '-'), ('i', qp1)]),
+                'QRY_STRAND': np.array(strand_objs, dtype=object)[rec64], 'CI': 0, 'ALIGN_INDEX': align_index[rec64],
+                'CALL_SOURCE': CALL_SOURCE,
+            }
+            df_snv = _frame(cols, SNV_COLUMNS, order)
     else:
         df_snv = _empty(SNV_COLUMNS)
 
     # ------------------------------------------------------------------ INS / DEL rows (cigarcall.py:141-282)
     if len(indel):
         n = len(indel)
-        rec = indel['rec'].astype(np.int64)
+        indel = np.ascontiguousarray(indel)
+        rec = indel['rec']
         pos = indel['pos'].astype(np.int64)
         end = indel['end'].astype(np.int64)
-        svlen = indel['svlen'].astype(np.int64)
+        svlen = indel['svlen']
         svtype_l = ['INS', 'DEL']
-        svt = (indel['svtype'] == 1).astype(np.int64)
-        ids = _pyrows.format(n, [('l', chrom_l, rec), ('s', '-'), ('i', pos + 1), ('s', '-'), ('l', svtype_l, svt), ('s', '-'), ('i', svlen)])
-        if version_id:
-            ids = variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object)
-        order = _sort_order(chrom_code_rec[rec], pos, end, ids)
-        indel = indel[order]
-        rec, pos, end, svlen, svt = rec[order], pos[order], end[order], svlen[order], svt[order]
-        is_del = svt == 1
-        qp = indel['qry_pos'].astype(np.int64)
-        qe = indel['qry_end'].astype(np.int64)
-        # SEQ: DEL = reference[pos : pos+n] (unshifted); INS = forward contig[qry_pos : qry_end], reverse-complemented
-        # when the record is on the minus strand (equals the slice of the reference-oriented contig)
-        n_ref = len(ref_arr)
-        which = np.where(is_del, ref_id[rec].astype(np.int64), n_ref + qry_id[rec].astype(np.int64))
-        start = np.where(is_del, pos, qp)
-        rc = (~is_del & rev[rec]).astype(np.uint8)
-        cols = {
-            '#CHROM': chrom[rec], 'POS': _pyrows.ints(pos), 'END': _pyrows.ints(end), 'ID': ids[order],
-            'SVTYPE': np.array(svtype_l, dtype=object)[svt], 'SVLEN': _pyrows.ints(svlen), 'HAP': hap,
-            'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec), ('s', ':'), ('i', qp + 1), ('s', '-'), ('i', np.where(is_del, qp + 1, qe))]),
-            'QRY_STRAND': strand_rec[rec], 'CI': 0, 'ALIGN_INDEX': align_index[rec],
-            'LEFT_SHIFT': _pyrows.ints(indel['left_shift'].astype(np.int64)),
-            'HOM_REF': _pyrows.format(n, [('i', indel['hom_ref_l'].astype(np.int64)), ('s', ','), ('i', indel['hom_ref_r'].astype(np.int64))]),
-            'HOM_TIG': _pyrows.format(n, [('i', indel['hom_tig_l'].astype(np.int64)), ('s', ','), ('i', indel['hom_tig_r'].astype(np.int64))]),
-            'CALL_SOURCE': CALL_SOURCE,
-            'SEQ': _pyrows.slices(list(ref_arr) + list(tig_arr), which, start, svlen, rc, fasta.COMPLEMENT.tobytes()),
-        }
-        df_insdel = _frame(cols, INSDEL_COLUMNS, order)
+        svt = indel['svtype']
+        ids = None
+        if version_id or not ascii_names:
+            ids = _pyrows.format(n, [('l', chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-'),
+                                     ('l', svtype_l, (svt == 1).astype(np.int64)), ('s', '-'), ('i', svlen.astype(np.int64))])
+            if version_id:
+                ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
+            id_of = ids.__getitem__
+        else:
+            def id_of(i):
+                return f'{chrom_l[rec[i]]}-{pos[i] + 1}-{svtype_l[int(svt[i] == 1)]}-{svlen[i]}'
+        order = _sort_order(chrom_code_rec[rec], pos, end, id_of)
+        if ascii_names:
+            cols = _pyrows.indel_frame(indel.view(np.uint8), order, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs, ref_id32, qry_id32, rev8,
+                                       list(ref_arr) + list(tig_arr), len(ref_arr), fasta.COMPLEMENT.tobytes(), ('INS', 'DEL', hap, 0, CALL_SOURCE))
+            df_insdel = _frame(dict(zip(INSDEL_COLUMNS, cols)), INSDEL_COLUMNS, order)
+        else:
+            indel_o = indel[order]
+            rec64, pos_o, end_o = rec[order].astype(np.int64), pos[order], end[order]
+            svlen_o, is_del = svlen[order].astype(np.int64), svt[order] == 1
+            qp = indel_o['qry_pos'].astype(np.int64)
+            qe = indel_o['qry_end'].astype(np.int64)
+            n_ref = len(ref_arr)
+            which = np.where(is_del, ref_id[rec64].astype(np.int64), n_ref + qry_id[rec64].astype(np.int64))
+            start = np.where(is_del, pos_o, qp)
+            rc = (~is_del & rev[rec64]).astype(np.uint8)
+            cols = {
+                '#CHROM': chrom[rec64], 'POS': _pyrows.ints(pos_o), 'END': _pyrows.ints(end_o), 'ID': ids[order],
+                'SVTYPE': np.array(svtype_l, dtype=object)[is_del.astype(np.int64)], 'SVLEN': _pyrows.ints(svlen_o), 'HAP': hap,
+                'QRY_REGION': _pyrows.format(n, [('l', qry_l, rec64), ('s', ':'), ('i', qp + 1), ('s', '-'), ('i', np.where(is_del, qp + 1, qe))]),
+                'QRY_STRAND': np.array(strand_objs, dtype=object)[rec64], 'CI': 0, 'ALIGN_INDEX': align_index[rec64],
+                'LEFT_SHIFT': _pyrows.ints(indel_o['left_shift'].astype(np.int64)),
+                'HOM_REF': _pyrows.format(n, [('i', indel_o['hom_ref_l'].astype(np.int64)), ('s', ','), ('i', indel_o['hom_ref_r'].astype(np.int64))]),
+                'HOM_TIG': _pyrows.format(n, [('i', indel_o['hom_tig_l'].astype(np.int64)), ('s', ','), ('i', indel_o['hom_tig_r'].astype(np.int64))]),
+                'CALL_SOURCE': CALL_SOURCE,
+                'SEQ': _pyrows.slices(list(ref_arr) + list(tig_arr), which, start, svlen_o, rc, fasta.COMPLEMENT.tobytes()),
+            }
+            df_insdel = _frame(cols, INSDEL_COLUMNS, order)
     else:
         df_insdel = _empty(INSDEL_COLUMNS)
 
