@@ -21,10 +21,6 @@
 #include <cstdlib>
 #include <cstring>
 
-#include <cuda_pipeline.h>
-
-#include <atomic>
-
 #include "common.cuh"
 
 namespace {
@@ -564,226 +560,68 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 }
 
 // K4 ---------------------------------------------------------------------------------------------
-// Left shift + four breakpoint homologies per indel (cigarcall.py:149-155,178-182 / :225-231,247-251 calling
-// call.py:542-647). The unit of work is not the indel but the *window trip* (one 32-base compare of two funnel-shifted
-// windows): scans end after one trip for most indels and after tens of trips for indels inside tandem repeats, so a
-// thread-per-indel kernel leaves most lanes of a warp idle (measured: 6.7 trips per indel on average, 20.4 per warp).
-// Here every lane runs a small state machine (indel -> scan 0..4 -> phase 1/2 -> trip) and a warp owns a block of
-// indels that its lanes pull from one at a time (ballot hand-out, registers only): each loop iteration is exactly one
-// trip on every busy lane, whatever indel, scan or phase that lane is in.
-//   phase 1: common extension of the flank T (from p, away from the breakpoint) with the SV sequence V, capped at n
-//   phase 2: (only if a whole copy of V matched) n + common extension of the flank with itself shifted by n
+// Thread per indel: the left shift, then the four breakpoint homologies at the shifted position (cigarcall.py:149-155,
+// 178-182 / :225-231,247-251 calling call.py:542-647), 32 bases per step on the packed planes. Everything the thread needs
+// is in its 64-byte stub (one coalesced read, no look-ups through the record tables). Lanes of a warp work on neighbouring
+// indels of the same record, so the strand branches inside the window code are warp-uniform.
+// What was measured and rejected for this kernel on C2: a trip-level state machine with dynamic hand-out of
+// indels to lanes, a cp.async ring of stubs, a "window plane" giving every window in one 128-bit load, branch-free window
+// extraction -- all between 0.101 and 0.16 ms against 0.083 ms for this form.
 constexpr int HOM_THREADS = 256;
 
-struct HomLane {
-    // indel
-    int64_t idx;
-    int32_t rec, op_idx, n, pr, pq, eqb;
-    int64_t r_base, q_base;
-    int32_t r_len, q_len;
-    int q_rev, ins;
-    int32_t ls, sp, sq, hom_rl, hom_rr, hom_tl, hom_tr;
-    // scan
-    int sc, phase, left, skip, t_is_q;
-    int32_t p, h, pa, pb, limit;
-};
-
-// Stub (already in shared memory) -> lane state.
-__device__ __forceinline__ void hom_take_indel(HomLane &S, const int4 *__restrict__ e, int64_t i)
-{
-    const int4 a = e[0], b = e[1], c = e[2], d = e[3];
-    S.idx = i;
-    S.rec = a.x; S.op_idx = a.y; S.ins = (a.z == 0); S.n = a.w; S.pr = b.x; S.pq = b.y; S.eqb = b.z; S.q_rev = b.w;
-    S.r_base = (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x);
-    S.q_base = (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z);
-    S.r_len = d.x; S.q_len = d.y;
-    S.ls = 0; S.sp = S.pr; S.sq = S.pq;
-    S.hom_rl = S.hom_rr = S.hom_tl = S.hom_tr = 0;
-    S.sc = S.eqb > 0 ? 0 : 1;   // scan 0 (the left shift) only when the previous op was '=' (cigarcall.py:149,225)
-}
-
-// Phase-1 parameters of scan S.sc: sc 0 = left shift, 1/2 = HOM_REF left/right, 3/4 = HOM_TIG left/right.
-__device__ __forceinline__ void hom_setup_scan(HomLane &S)
-{
-    const int sc = S.sc;
-    S.t_is_q = sc >= 3;                        // scans 0..2 walk the reference, 3..4 the contig
-    S.left = (sc == 0) | (sc == 1) | (sc == 3);
-    const int32_t n_ins = S.ins ? S.n : 0, n_del = S.ins ? 0 : S.n;
-    // sc: 0 -> pr-1, 1 -> sp-1, 2 -> sp (INS) / sp+n (DEL), 3 -> sq-1, 4 -> sq+n (INS) / sq (DEL)
-    const int32_t p_ref = sc == 0 ? S.pr - 1 : (sc == 1 ? S.sp - 1 : S.sp + n_del);
-    const int32_t p_qry = sc == 3 ? S.sq - 1 : S.sq + n_ins;
-    const int32_t p = S.t_is_q ? p_qry : p_ref;
-    const int32_t t_len = S.t_is_q ? S.q_len : S.r_len;
-    const int32_t v0 = S.ins ? S.sq : S.pr;   // INS: contig[sq : sq+n], re-sliced after the shift; DEL: reference[pr : pr+n]
-    S.p = p; S.phase = 1; S.h = 0; S.limit = S.n;
-    S.skip = (S.n <= 0) | (p < 0) | (p >= t_len);   // call.py:574,627: nothing to compare -> 0
-    const int32_t b = S.left ? v0 + S.n - 1 : v0;
-    S.pa = S.skip ? 0 : (S.left ? p - 31 : p);
-    S.pb = S.skip ? 0 : (S.left ? b - 31 : b);
-}
-
-__device__ __forceinline__ void hom_write_row(const HomLane &S, pavgpu_indel_row *__restrict__ rows)
-{
-    int32_t pos, end, qry_pos, qry_end, seq_start;
-    if (S.ins) {        // cigarcall.py:157-173
-        pos = S.sp; end = S.sp + 1;
-        if (S.q_rev) { qry_end = S.q_len - S.sq; qry_pos = qry_end - S.n; } else { qry_pos = S.sq; qry_end = S.sq + S.n; }
-        seq_start = S.sq;
-    } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
-        pos = S.pr; end = S.pr + S.n;
-        qry_pos = S.q_rev ? S.q_len - S.sq : S.sq;
-        qry_end = qry_pos + 1;
-        seq_start = S.pr;
-    }
-    int4 *dst = reinterpret_cast<int4 *>(rows + S.idx);
-    dst[0] = make_int4(S.rec, S.op_idx, S.ins ? 0 : 1, S.n);
-    dst[1] = make_int4(pos, end, qry_pos, qry_end);
-    dst[2] = make_int4(S.ls, S.hom_rl, S.hom_rr, S.hom_tl);
-    dst[3] = make_int4(S.hom_tr, seq_start, 0, 0);
-}
-
-// Stubs reach the lanes through a per-warp ring in shared memory (two blocks of 32 stubs), filled with cp.async two
-// blocks ahead of the hand-out: a lane that finishes an indel finds its next one on chip, so the only global latency
-// inside the loop is the window loads of the trip itself.
-constexpr int HOM_WARPS = HOM_THREADS / 32;
-constexpr int HOM_RING = 64;   // stubs per warp in the ring
-
-__device__ __forceinline__ void hom_prefetch_block(int4 *ring, const IndelStub *__restrict__ stubs, int64_t wbase, int64_t wend, int blk, int lane)
-{
-    const int64_t first = wbase + ((int64_t)blk << 5);
-    if (first < wend) {
-        const int4 *src = reinterpret_cast<const int4 *>(stubs + first);   // the block's 32 stubs are contiguous: 128 16-byte pieces
-        int4 *dst = ring + (size_t)(blk & 1) * 32 * 4;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int c = q * 32 + lane;
-            if (first + (c >> 2) < wend) __pipeline_memcpy_async(dst + c, src + c, 16);
-        }
-    }
-    __pipeline_commit();   // one group per block, empty past the end, so "all but the newest group" always means "this block"
-}
-
 __global__ void __launch_bounds__(HOM_THREADS, 4)
-homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, int indels_per_warp, SeqPlanes ref, SeqPlanes qry,
-                pavgpu_indel_row *__restrict__ rows)
-{
-    __shared__ int4 s_ring[HOM_WARPS][HOM_RING * 4];
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * HOM_WARPS + (threadIdx.x >> 5);
-    const int64_t wbase = warp * indels_per_warp;
-    if (wbase >= n_indel) return;   // warp-uniform
-    const int64_t wend = min(wbase + (int64_t)indels_per_warp, n_indel);
-    int4 *ring = s_ring[threadIdx.x >> 5];
-    const unsigned lt = (1u << lane) - 1u;
-    hom_prefetch_block(ring, stubs, wbase, wend, 0, lane);
-    hom_prefetch_block(ring, stubs, wbase, wend, 1, lane);
-    HomLane S;
-    bool busy = false;
-    int64_t next = wbase;   // first indel of the warp's range not handed out yet (warp-uniform)
-    for (;;) {
-        // ---- hand the next indels of the current block to idle lanes
-        const unsigned idle = __ballot_sync(FULL, !busy);
-        if (idle && next < wend) {
-            const int blk = (int)((next - wbase) >> 5);
-            const int64_t blk_end = min(wbase + ((int64_t)(blk + 1) << 5), wend);
-            __pipeline_wait_prior(1);   // block blk has landed (block blk+1 may still be in flight)
-            __syncwarp();
-            const int64_t i = next + __popc(idle & lt);
-            if (!busy && i < blk_end) {
-                hom_take_indel(S, ring + (size_t)((i - wbase) & (HOM_RING - 1)) * 4, i);
-                hom_setup_scan(S);
-                busy = true;
-            }
-            next = min(next + (int64_t)__popc(idle), blk_end);
-            if (next == blk_end) {      // block consumed: its half of the ring takes block blk+2
-                __syncwarp();
-                hom_prefetch_block(ring, stubs, wbase, wend, blk + 2, lane);
-            }
-        }
-        if (!__any_sync(FULL, busy)) break;
-        if (busy) {
-            // ---- one trip: 32 bases of A (the flank) against 32 bases of B (V in phase 1, the shifted flank in phase 2)
-            const bool a_q = S.t_is_q != 0;
-            const bool b_q = S.phase == 1 ? (S.ins != 0) : a_q;
-            const WSeq A{a_q ? qry.win : ref.win, a_q ? S.q_base : S.r_base, a_q ? S.q_len : S.r_len, a_q ? S.q_rev : 0};
-            const WSeq B{b_q ? qry.win : ref.win, b_q ? S.q_base : S.r_base, b_q ? S.q_len : S.r_len, b_q ? S.q_rev : 0};
-            uint64_t wa, wb; uint32_t ma, mb;
-            WinReq qa, qb;
-            const uint4 *pa_ = win_request(A, S.pa, qa), *pb_ = win_request(B, S.pb, qb);
-            const uint4 ua = __ldg(pa_), ub = __ldg(pb_);   // one 128-bit load per window (window plane), both in flight together
-            win_extract(A, qa, ua, wa, ma);
-            win_extract(B, qb, ub, wb, mb);
-            const uint64_t x = wa ^ wb;
-            const uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;   // one bit per differing base
-            const uint32_t m = ma | mb;
-            // left scans: last base of the window = least significant group / highest mask bit; right scans: first base =
-            // most significant group / lowest mask bit. Both computed, one selected (no divergence between lanes).
-            const int sd_l = d ? ((__ffsll((long long)d) - 1) >> 1) : 32, sm_l = m ? __clz((int)m) : 32;
-            const int sd_r = d ? (__clzll((long long)d) >> 1) : 32, sm_r = m ? (__ffs((int)m) - 1) : 32;
-            const int stop = S.left ? min(sd_l, sm_l) : min(sd_r, sm_r);
-            // ---- transitions (same arithmetic as common_extension / dev_homology_raw in common.cuh), predicated
-            const bool in_window = stop < 32;
-            const int32_t h32 = S.h + 32;
-            const bool end_phase = S.skip || in_window || h32 >= S.limit;
-            const int32_t hf = in_window ? min(S.h + stop, S.limit) : S.limit;
-            const bool to_phase2 = end_phase && !S.skip && S.phase == 1 && hf >= S.n;   // a whole copy of the SV sequence matched
-            const bool scan_done = end_phase && !to_phase2;
-            const int32_t step = S.left ? -32 : 32;
-            if (!end_phase) { S.h = h32; S.pa += step; S.pb += step; }
-            if (to_phase2) {   // go on as flank vs flank shifted by n
-                S.phase = 2; S.h = 0; S.limit = 0x7fffffff - S.n;
-                const int32_t a = S.left ? S.p - S.n : S.p + S.n;
-                S.pa = S.left ? a - 31 : a; S.pb = S.left ? S.p - 31 : S.p;
-            }
-            if (scan_done) {
-                const int32_t result = S.skip ? 0 : (S.phase == 1 ? hf : S.n + hf);
-                const int sc = S.sc;
-                if (sc == 0) { S.ls = min(S.eqb, result); S.sp = S.pr - S.ls; S.sq = S.pq - S.ls; }
-                S.hom_rl = sc == 1 ? result : S.hom_rl;
-                S.hom_rr = sc == 2 ? result : S.hom_rr;
-                S.hom_tl = sc == 3 ? result : S.hom_tl;
-                S.hom_tr = sc == 4 ? result : S.hom_tr;
-                S.sc = sc + 1;
-                if (sc < 4) hom_setup_scan(S);
-                else { hom_write_row(S, rows); busy = false; }
-            }
-        }
-        __syncwarp();   // lanes leave the transitions at different points; the next trip runs converged again
-    }
-}
-
-// Thread-per-indel variant (PAVGPU_HOM_TPI=1, A/B timing): maximal memory-level parallelism (every indel in flight at once),
-// but a warp runs as long as its longest indel.
-__global__ void __launch_bounds__(HOM_THREADS)
-homology_tpi_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
+homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
 {
     const int64_t i = (int64_t)blockIdx.x * HOM_THREADS + threadIdx.x;
     if (i >= n_indel) return;
-    HomLane S;
-    hom_take_indel(S, reinterpret_cast<const int4 *>(stubs + i), i);
-    const WSeq R{ref.win, S.r_base, S.r_len, 0}, Q{qry.win, S.q_base, S.q_len, S.q_rev};
-    const int n = S.n;
+    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
+    const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
+    const int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
+    const OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0};
+    const OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w};
+    const int32_t L = (int32_t)Q.len;
+    // Five scans, one rolled loop so the scan code exists once in the kernel (with all five call sites inlined the kernel
+    // is instruction-fetch bound).
+    //   INS: SV sequence = contig[sq : sq+n] (re-sliced after the shift); DEL: reference[pr : pr+n] (never re-sliced)
+    const bool ins = (svtype == 0);
+    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
+    int32_t sp = pr, sq = pq;
 #pragma unroll 1
-    for (int sc = S.sc; sc < 5; sc++) {
-        const bool on_ref = sc <= 2;
-        const int left = (sc == 0) | (sc == 1) | (sc == 3);
-        int32_t p;
-        if (sc == 0) p = S.pr - 1;
-        else if (sc == 1) p = S.sp - 1;
-        else if (sc == 2) p = S.ins ? S.sp : S.sp + n;
-        else if (sc == 3) p = S.sq - 1;
-        else p = S.ins ? S.sq + n : S.sq;
-        const WSeq &T = on_ref ? R : Q;
-        const WSeq &V = S.ins ? Q : R;
-        const int32_t v0 = S.ins ? S.sq : S.pr;
-        const int h = wdev_homology(T, p, V, v0, n, left);
-        if (sc == 0) { S.ls = min(S.eqb, h); S.sp = S.pr - S.ls; S.sq = S.pq - S.ls; }
-        else if (sc == 1) S.hom_rl = h;
-        else if (sc == 2) S.hom_rr = h;
-        else if (sc == 3) S.hom_tl = h;
-        else S.hom_tr = h;
+    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {   // scan 0 (the left shift) only when the previous op was '=' (cigarcall.py:149,225)
+        const bool on_ref = sc <= 2;            // scans 0..2 walk the reference, 3..4 the contig
+        const int left = (sc == 0 || sc == 1 || sc == 3);
+        int64_t p;
+        if (sc == 0) p = (int64_t)pr - 1;
+        else if (sc == 1) p = (int64_t)sp - 1;
+        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
+        else if (sc == 3) p = (int64_t)sq - 1;
+        else p = ins ? (int64_t)sq + n : (int64_t)sq;
+        const OSeq &T = on_ref ? R : Q;
+        const OSeq &V = ins ? Q : R;
+        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;   // sq == pq while sc == 0
+        int h = dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, left);
+        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
+        else if (sc == 1) hom_rl = h;
+        else if (sc == 2) hom_rr = h;
+        else if (sc == 3) hom_tl = h;
+        else hom_tr = h;
     }
-    hom_write_row(S, rows);
+    int32_t pos, end, qry_pos, qry_end, seq_start;
+    if (ins) {          // cigarcall.py:157-173
+        pos = sp; end = sp + 1;
+        if (Q.rev) { qry_end = L - sq; qry_pos = qry_end - n; } else { qry_pos = sq; qry_end = sq + n; }
+        seq_start = sq;
+    } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
+        pos = pr; end = pr + n;
+        qry_pos = Q.rev ? L - sq : sq;
+        qry_end = qry_pos + 1;
+        seq_start = pr;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(rec, op_idx, svtype, n);
+    dst[1] = make_int4(pos, end, qry_pos, qry_end);
+    dst[2] = make_int4(ls, hom_rl, hom_rr, hom_tl);
+    dst[3] = make_int4(hom_tr, seq_start, 0, 0);
 }
 
 __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,
@@ -803,20 +641,6 @@ __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-// Indels per warp of the homology kernel: enough warps to fill the chip (24 per SM), blocks long enough that the
-// hand-out evens out short and long scans (>= 64 indels, i.e. >= 2 per lane), multiple of 32.
-static int hom_indels_per_warp(int64_t n_indel, int sm_count)
-{
-    const char *e = getenv("PAVGPU_HOM_IPW");
-    if (e && atoi(e) >= 32) return atoi(e) / 32 * 32;
-    int64_t warps = (int64_t)sm_count * 24;
-    int64_t ipw = (n_indel + warps - 1) / warps;
-    ipw = (ipw + 31) / 32 * 32;
-    if (ipw < 64) ipw = 64;
-    if (ipw > 1024) ipw = 1024;
-    return (int)ipw;
-}
-
 struct pavgpu_cigar_batch {
     pavgpu_ctx *ctx;
     int32_t n_rec;
@@ -1068,13 +892,6 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         if (b->n_rec) CUDA_TRY(cudaMemcpyAsync(b->d_recdesc, b->h_recdesc.data(), (size_t)b->n_rec * sizeof(RecDesc), cudaMemcpyHostToDevice, st));
         b->recdesc_ref_uid = ref_store->uid; b->recdesc_qry_uid = qry_store->uid;
     }
-    // window planes of the two stores (built once per store, before the timed region)
-    const uint4 *w_ref = nullptr, *w_qry = nullptr;
-    if (b->host_n_indel > 0 || !b->fused) {
-        int wrc = pav_seqstore_window_plane(ref_store, &w_ref);
-        if (!wrc) wrc = pav_seqstore_window_plane(qry_store, &w_qry);
-        if (wrc) return wrc;
-    }
     const SeqPlanes pl_ref = planes_of(ref_store), pl_qry = planes_of(qry_store);
     unsigned long long init = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(b->d_first_illegal, &init, 8, cudaMemcpyHostToDevice, st));
@@ -1093,10 +910,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         b->n_snv = b->host_n_snv; b->n_indel = b->host_n_indel;
         if (b->n_indel > 0) {
-            const int ipw = hom_indels_per_warp(b->n_indel, ctx->sm_count);
-            unsigned hb = (unsigned)((b->n_indel + (int64_t)ipw * (HOM_THREADS / 32) - 1) / ((int64_t)ipw * (HOM_THREADS / 32)));
-            if (getenv("PAVGPU_HOM_TPI")) homology_tpi_kernel<<<(unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS), HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
-            else homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, ipw, pl_ref, pl_qry, b->d_indel);
+            const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
+            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
             launches++;
             CUDA_TRY(cudaGetLastError());
         }
@@ -1139,10 +954,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         if (b->n_indel > 0) {
-            const int ipw = hom_indels_per_warp(b->n_indel, ctx->sm_count);
-            unsigned hb = (unsigned)((b->n_indel + (int64_t)ipw * (HOM_THREADS / 32) - 1) / ((int64_t)ipw * (HOM_THREADS / 32)));
-            if (getenv("PAVGPU_HOM_TPI")) homology_tpi_kernel<<<(unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS), HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
-            else homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, ipw, pl_ref, pl_qry, b->d_indel);
+            const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
+            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
             launches++;
             CUDA_TRY(cudaGetLastError());
         }

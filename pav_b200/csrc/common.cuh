@@ -147,24 +147,18 @@ struct pavgpu_seqstore {
     uint64_t *d_pack2;
     uint32_t *d_nmask;
     size_t pack2_bytes, nmask_bytes;
-    mutable uint4 *d_win = nullptr;   // window plane (see WSeq), derived from the two planes on first use by the CIGAR walk
 };
-
-// Builds the window plane of a store if it does not exist yet (on the context stream). Defined in seqstore.cu.
-int pav_seqstore_window_plane(const pavgpu_seqstore *s, const uint4 **out);
-void pav_seqstore_drop_window_plane(pavgpu_seqstore *s);   // after the planes were overwritten (broadcast receiver)
 
 struct SeqPlanes {
     const uint64_t *pack2;
     const uint32_t *nmask;
     const int64_t *off;
     const int64_t *len;
-    const uint4 *win;   // window plane, nullptr unless requested (pav_seqstore_window_plane)
 };
 
 static inline SeqPlanes planes_of(const pavgpu_seqstore *s)
 {
-    return SeqPlanes{s->d_pack2, s->d_nmask, s->d_off, s->d_len, s->d_win};
+    return SeqPlanes{s->d_pack2, s->d_nmask, s->d_off, s->d_len};
 }
 
 // A sequence seen in alignment orientation: position t maps to the forward base t, or to the
@@ -232,101 +226,6 @@ __device__ __forceinline__ void oseq_window(const OSeq &s, int32_t t, uint64_t &
     fwd_window(s, (int32_t)s.len - t - 32, b, m);
     bases = revcomp32(b);
     mask = __brev(m);
-}
-
-// ---- window plane ------------------------------------------------------------------------------
-// The homology scans read 32-base windows at arbitrary, scattered positions. From the two planes such a window costs
-// four load instructions (two plane words, two mask words), and with every lane at a different genome position each
-// of them occupies the L1 for 32 cycles -- that, not HBM or issue slots, bounded the kernel. The window
-// plane trades memory for that: one 16-byte unit per 8 bases holding the 40 bases that start there (80 bits, first
-// base most significant) and their 40 mask bits, so ANY 32-base window is one aligned 128-bit load:
-//   .y:.x  bases 8u .. 8u+31 (pack2 word format)      .z  mask bits of bases 8u .. 8u+31
-//   .w     [31:16] bases 8u+32 .. 8u+39               .w  [7:0] mask bits of bases 8u+32 .. 8u+39
-// 2 B/base, derived on the device from pack2 + nmask (win_build_kernel), only for stores the CIGAR walk touches.
-struct WSeq {
-    const uint4 *win;
-    int64_t base;
-    int32_t len;
-    int rev;
-};
-
-// Address of the unit a window starts in, branch-free (so the loads of several windows can be issued back to back, before
-// any of them is used -- the scans are DRAM-latency bound). t = oriented start of the window.
-struct WinReq {
-    int32_t f;       // forward-strand start of the 32-base window (may lie partly or wholly outside the sequence)
-    int lead;        // window positions before the sequence start
-    int sh;          // first base of the window inside its unit (0..7)
-    bool outside;    // no base of the window lies inside the sequence
-};
-
-__device__ __forceinline__ const uint4 *win_request(const WSeq &s, int32_t t, WinReq &q)
-{
-    q.f = s.rev ? s.len - t - 32 : t;
-    q.outside = (q.f <= -32) | (q.f >= s.len);
-    q.lead = (q.f < 0 && !q.outside) ? -q.f : 0;
-    const int64_t g = s.base + (int64_t)(q.outside ? 0 : q.f + q.lead);
-    q.sh = (int)(g & 7);
-    return s.win + (g >> 3);
-}
-
-// Unit -> (bases, mask) of the oriented window: cut the 32 bases out of the 40, blank what lies outside the sequence,
-// reverse-complement for minus-strand views.
-__device__ __forceinline__ void win_extract(const WSeq &s, const WinReq &q, const uint4 &u, uint64_t &bases, uint32_t &mask)
-{
-    const uint64_t hi = ((uint64_t)u.y << 32) | (uint64_t)u.x;
-    const int sh = q.sh;
-    uint64_t b = (hi << (2 * sh)) | (uint64_t)(((u.w >> 16) << (2 * sh)) >> 16);      // sh == 0: the second term is 0
-    uint32_t m = (uint32_t)(((((uint64_t)(u.w & 0xffu)) << 32) | (uint64_t)u.z) >> sh);
-    b >>= 2 * q.lead;
-    m = (m << q.lead) | ((1u << q.lead) - 1u);
-    const int over = q.f + 32 - s.len;         // window positions past the sequence end
-    m |= over > 0 ? (~0u << (32 - min(over, 32))) : 0u;
-    m = q.outside ? 0xffffffffu : m;
-    const uint64_t rb = revcomp32(b);
-    bases = s.rev ? rb : b;
-    mask = s.rev ? __brev(m) : m;
-}
-
-__device__ __forceinline__ void wseq_window(const WSeq &s, int32_t t, uint64_t &bases, uint32_t &mask)
-{
-    WinReq q;
-    const uint4 u = __ldg(win_request(s, t, q));
-    win_extract(s, q, u, bases, mask);
-}
-
-// common_extension / dev_homology_raw (below) on the window plane: same arithmetic, one 128-bit load per window and both
-// windows of a step in flight together.
-__device__ __forceinline__ int32_t wcommon_extension(const WSeq &A, int32_t a, const WSeq &B, int32_t b, int32_t limit, int left)
-{
-    int32_t h = 0;
-    const int32_t step = left ? -32 : 32;
-    int32_t pa = left ? a - 31 : a, pb = left ? b - 31 : b;
-    while (h < limit) {
-        WinReq qa, qb;
-        const uint4 *ga = win_request(A, pa, qa), *gb = win_request(B, pb, qb);
-        const uint4 ua = __ldg(ga), ub = __ldg(gb);
-        uint64_t wa, wb; uint32_t ma, mb;
-        win_extract(A, qa, ua, wa, ma);
-        win_extract(B, qb, ub, wb, mb);
-        const uint64_t x = wa ^ wb;
-        const uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
-        const uint32_t m = ma | mb;
-        const int sd_l = d ? ((__ffsll((long long)d) - 1) >> 1) : 32, sm_l = m ? __clz((int)m) : 32;
-        const int sd_r = d ? (__clzll((long long)d) >> 1) : 32, sm_r = m ? (__ffs((int)m) - 1) : 32;
-        const int stop = left ? min(sd_l, sm_l) : min(sd_r, sm_r);
-        if (stop < 32) { h += stop; return h < limit ? h : limit; }
-        h += 32; pa += step; pb += step;
-        if (h < 0) return limit;
-    }
-    return limit;
-}
-
-__device__ __forceinline__ int wdev_homology(const WSeq &T, int32_t p, const WSeq &V, int32_t v0, int n, int left)
-{
-    if (n <= 0 || p < 0 || p >= T.len) return 0;
-    int32_t h = wcommon_extension(T, p, V, left ? v0 + n - 1 : v0, n, left);
-    if (h < n) return h;
-    return n + wcommon_extension(T, left ? p - n : p + n, T, p, 0x7fffffff - n, left);
 }
 
 // Longest common extension of A from a and B from b, 32 bases per step, capped at `limit`:

@@ -88,7 +88,6 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_broadcast(
     int rc = load_nccl();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (rank != 0) pav_seqstore_drop_window_plane(store);   // the planes are about to be overwritten; every rank derives its own window plane
     NcclUniqueId id;
     memcpy(id.internal, id_in, 128);
     NcclComm comm = nullptr;

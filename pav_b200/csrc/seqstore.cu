@@ -212,42 +212,6 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ a
     nmask[w] = mask;
 }
 
-// Window plane (common.cuh, WSeq): unit u = the 40 bases from 8u on + their mask bits, cut out of two consecutive words.
-__global__ void __launch_bounds__(256) win_build_kernel(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t n_words,
-                                                        uint4 *__restrict__ win, int64_t n_units)
-{
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
-    const int64_t w0 = u >> 2;
-    const int o = (int)(u & 3) * 8;   // first base of the unit inside word w0: 0, 8, 16, 24
-    const uint64_t p0 = __ldg(pack2 + w0), p1 = (w0 + 1 < n_words) ? __ldg(pack2 + w0 + 1) : 0ull;
-    const uint32_t m0 = __ldg(nmask + w0), m1 = (w0 + 1 < n_words) ? __ldg(nmask + w0 + 1) : 0xffffffffu;
-    const uint64_t hi = o ? ((p0 << (2 * o)) | (p1 >> (64 - 2 * o))) : p0;
-    const uint32_t lo16 = (uint32_t)((p1 << (2 * o)) >> 48);
-    const uint64_t m40 = (((uint64_t)m1 << 32) | (uint64_t)m0) >> o;
-    win[u] = make_uint4((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)m40, (lo16 << 16) | ((uint32_t)(m40 >> 32) & 0xffu));
-}
-
-int pav_seqstore_window_plane(const pavgpu_seqstore *s, const uint4 **out)
-{
-    if (!s->d_win) {
-        const int64_t n_units = s->total_bases / 8, n_words = s->total_bases / 32;
-        uint4 *w = nullptr;
-        cudaError_t e = pav_dev_alloc_t(s->ctx, (size_t)n_units, &w);
-        if (e != cudaSuccess) { pav_set_error("seqstore: cudaMalloc(%lld) for the window plane failed: %s", (long long)n_units * 16, cudaGetErrorString(e)); return PAVGPU_ERR_NOMEM; }
-        win_build_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, s->ctx->stream>>>(s->d_pack2, s->d_nmask, n_words, w, n_units);
-        CUDA_TRY(cudaGetLastError());
-        s->d_win = w;
-    }
-    *out = s->d_win;
-    return PAVGPU_OK;
-}
-
-void pav_seqstore_drop_window_plane(pavgpu_seqstore *s)
-{
-    if (s->d_win) { cudaStreamSynchronize(s->ctx->stream); pav_dev_free(s->ctx, s->d_win); s->d_win = nullptr; }
-}
-
 static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, pavgpu_seqstore **out)
 {
     if (!ctx || n_seq < 0 || (n_seq > 0 && !seq_len) || !out) { pav_set_error("seqstore: bad argument"); return PAVGPU_ERR_ARG; }
@@ -357,7 +321,6 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_seqstore_free(pavg
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    pav_dev_free(s->ctx, s->d_win);
     pav_dev_free(s->ctx, s->d_pack2);
     pav_dev_free(s->ctx, s->d_nmask);
     pav_dev_free(s->ctx, s->d_off);

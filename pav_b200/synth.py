@@ -93,12 +93,15 @@ TR_MAX_LEN = 6 * 50
 def make_reference(seed, n_chrom, chrom_len, chrom_prefix='chr', tandem_repeats=True):
     """Reference chromosomes (iid uniform ACGT) with tandem-repeat arrays (unit 1-6 bp x 5-50 copies)
     planted every ``TR_SPACING`` bp. Depends on ``seed`` only, so every rank of a multi-GPU run
-    regenerates the identical reference. Returns ``(ref dict, tr dict: chrom -> (pos, unit_len, copies))``.
+    regenerates the identical reference. ``chrom_len`` is one length for all chromosomes or a sequence of
+    ``n_chrom`` lengths. Returns ``(ref dict, tr dict: chrom -> (pos, unit_len, copies))``.
     """
     rng = np.random.default_rng([seed, 0xA11])
     ref, trs = {}, {}
+    lens = [int(chrom_len)] * n_chrom if np.isscalar(chrom_len) else [int(x) for x in chrom_len]
     for c in range(n_chrom):
         name = f'{chrom_prefix}{c + 1}'
+        chrom_len = lens[c]
         arr = random_seq(rng, chrom_len)
         n_tr = max((chrom_len - TR_OFFSET - TR_MAX_LEN) // TR_SPACING, 0) if tandem_repeats else 0
         pos = np.arange(n_tr, dtype=np.int64) * TR_SPACING + TR_OFFSET
@@ -269,6 +272,62 @@ def make_contigs(ref, trs, hap_seed, n_contig, contig_len, edit_rate=0.01, rev_f
                                      'QRY_LEN', 'RG', 'AO', 'MAPQ', 'REV', 'FLAGS', 'HAP', 'CIGAR'])
     df.sort_values(['#CHROM', 'POS', 'END', 'QRY_ID'], ascending=[True, True, False, True], inplace=True)
     return tigs, df
+
+
+# hg38 primary assembly, chr1..chr22, chrX, chrY (sum 3.09 Gbp) -- the shape of BASELINE configs[2]/[3]
+HG38_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422,
+                135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167,
+                46709983, 50818468, 156040895, 57227415]
+
+# edit regimes of SURVEY 8(d) for C3/C4: (edits per base, SNV fraction, INS fraction)
+C3_REGIMES = {'human': (1.2e-3, 1.0 / 1.2, 0.1 / 1.2), 'stress': (1e-2, 0.8, 0.1)}
+
+
+def make_contigs_tiled(ref, trs, hap_seed, contig_len, edit_rate=0.01, snv_frac=0.8, ins_frac=0.1, rev_frac=0.5, tr_frac=0.2,
+                       hap='h1', contig_prefix='tig', min_len=20_000):
+    """Contigs of ``contig_len`` tiling every chromosome end to end (the last one of a chromosome is shorter; tails under
+    ``min_len`` are left uncovered) + their alignment table. Chromosomes may have different lengths (hg38 shape)."""
+    rng = np.random.default_rng([hap_seed, 0xC17])
+    tigs, rows, t = {}, [], 0
+    for chrom, arr in ref.items():
+        for start in range(0, len(arr), contig_len):
+            span = min(contig_len, len(arr) - start)
+            if span < min_len:
+                break
+            rev = bool(rng.random() < rev_frac)
+            q, cigar, span = plant_alignment(rng, arr, trs.get(chrom) if trs else None, start, span, int(span * edit_rate),
+                                             snv_frac=snv_frac, ins_frac=ins_frac, tr_frac=tr_frac)
+            name = f'{contig_prefix}{t:05d}'
+            qlen = len(q)
+            tigs[name] = revcomp(q) if rev else q
+            rows.append((chrom, start, start + span, t, name, 0, qlen, qlen, 'NA', 'NA', 60, rev, '0x0010' if rev else '0x0000', hap, cigar))
+            t += 1
+    df = pd.DataFrame(rows, columns=['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END',
+                                     'QRY_LEN', 'RG', 'AO', 'MAPQ', 'REV', 'FLAGS', 'HAP', 'CIGAR'])
+    df.sort_values(['#CHROM', 'POS', 'END', 'QRY_ID'], ascending=[True, True, False, True], inplace=True)
+    return tigs, df.reset_index(drop=True)
+
+
+def config_c3_reference(seed=1003, scale=1.0, soft_mask_frac=0.5, n_block_frac=0.05):
+    """BASELINE configs[2] reference: 24 chromosomes with hg38 primary lengths (x ``scale``), 50 % soft-masked runs, 5 % of the
+    bases in N blocks. Returns ``(ref, trs, ref_pristine_is_masked)`` -- the contigs are derived from the reference *before*
+    masking (use ``config_c3_haplotype``), as real assemblies carry sequence where the reference has N."""
+    lens = [max(int(x * scale), 40_000) for x in HG38_LENGTHS]
+    return make_reference(seed, len(lens), lens)
+
+
+def config_c3_mask(ref, seed=1003, soft_mask_frac=0.5, n_block_frac=0.05):
+    rng = np.random.default_rng([seed, 0x3A5])
+    for chrom in ref:
+        _mask_runs(rng, ref[chrom], soft_mask_frac, n_block_frac)
+
+
+def config_c3_haplotype(ref, trs, hap, seed=1003, scale=1.0, regime='human', contig_len=10_000_000):
+    """One haplotype of BASELINE configs[2]: 10 Mbp contigs (x ``scale``) tiling the (still unmasked) reference."""
+    rate, snv_frac, ins_frac = C3_REGIMES[regime]
+    hap_seed = seed * 10 + (1 if hap == 'h1' else 2)
+    return make_contigs_tiled(ref, trs, hap_seed, max(int(contig_len * scale), 40_000), edit_rate=rate, snv_frac=snv_frac,
+                              ins_frac=ins_frac, hap=hap, contig_prefix=f'{hap}tig')
 
 
 def make_cigar_workload(seed, n_chrom, chrom_len, n_contig, contig_len, edit_rate=0.01,
