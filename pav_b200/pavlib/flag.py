@@ -1,0 +1,243 @@
+"""Flagging rules between the CIGAR walk and the inversion scan, as sorted scans over columns.
+
+The reference implements these inside Snakemake ``run:`` blocks as ``DataFrame.iterrows()`` loops that build one
+``pd.Series`` per output row -- over the multi-million-row tables the CIGAR walk now returns in milliseconds:
+
+    cigar_filter          rules/call.snakefile:813-846        FILTER = PASS / TRIM against the trimmed alignments
+    cluster_variants      rules/call_inv.snakefile:616-690    clusters of SNVs / indels
+    flag_insdel_cluster   rules/call_inv.snakefile:493-583    INS matched to nearby DELs, merged
+    merge_flagged_loci    rules/call_inv.snakefile:331-474    merge of the four flag tables, TRY_INV, BATCH
+
+Every loop there carries only "the previous row" (or a running maximum), so each is a break-point mask + segment
+reduction here. The reference's behaviours that look accidental are kept, because the tables must come out identical
+(tests/golden/flag/, produced by executing the reference's own rule bodies): the cluster rule ignores
+``cluster_win_min`` (it reads ``cluster_win`` twice, :617-618), clusters variants by midpoint in POS order, and the
+INS/DEL merge never records its last open interval (:551-571).
+
+Host-side numpy: these tables are already pandas frames on the host and a pass over them is cheaper than a round trip to
+the device; the GPU work of this stage is the walk that produced them.
+"""
+import numpy as np
+import pandas as pd
+
+BATCH_COUNT_DEFAULT = 60   # rules/call_inv.snakefile:81
+
+
+# ------------------------------------------------------------------------------------------------ call_cigar FILTER
+def cigar_filter(df, df_trim):
+    """FILTER column of a call table: PASS when the variant lies strictly inside the trimmed alignment of its
+    ``ALIGN_INDEX``, TRIM otherwise (also when the record disappeared in trimming). ``df_trim``: POS, END indexed by INDEX."""
+    if df.shape[0] == 0:
+        return pd.Series([], index=df.index, dtype=object)
+    idx = df_trim.index.to_numpy()
+    order = np.argsort(idx, kind='stable')
+    idx_s = idx[order]
+    ai = np.array([int(x) for x in df['ALIGN_INDEX'].tolist()], dtype=np.int64)
+    k = np.searchsorted(idx_s, ai)
+    k_ok = np.minimum(k, max(len(idx_s) - 1, 0))
+    found = (k < len(idx_s)) & (idx_s[k_ok] == ai) if len(idx_s) else np.zeros(len(ai), dtype=bool)
+    t_pos = np.where(found, df_trim['POS'].to_numpy().astype(np.int64)[order][k_ok], -1) if len(idx_s) else np.full(len(ai), -1)
+    t_end = np.where(found, df_trim['END'].to_numpy().astype(np.int64)[order][k_ok], -1) if len(idx_s) else np.full(len(ai), -1)
+    pos = np.array([int(x) for x in df['POS'].tolist()], dtype=np.int64)
+    end = np.array([int(x) for x in df['END'].tolist()], dtype=np.int64)
+    ok = (pos > t_pos) & (end < t_end)
+    return pd.Series(np.where(ok, 'PASS', 'TRIM').astype(object), index=df.index)
+
+
+def call_cigar(df_align, batch, ref_fa_name, tig_fa_name, hap, df_trim):
+    """Body of ``rule call_cigar`` (rules/call.snakefile:800-846): walk the records of one CALL_BATCH on the GPU, add FILTER."""
+    from . import cigarcall
+    df_align = df_align.loc[df_align['CALL_BATCH'] == batch]
+    df_snv, df_insdel = cigarcall.make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=False)
+    df_snv['FILTER'] = cigar_filter(df_snv, df_trim)
+    df_insdel['FILTER'] = cigar_filter(df_insdel, df_trim)
+    return df_snv, df_insdel
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _chrom_codes(chrom):
+    """Integer codes that sort like the strings do (one hash pass over the column, then a sort of the few distinct names)."""
+    codes, uniq = pd.factorize(np.asarray(chrom, dtype=object), sort=False)
+    uniq = np.array([str(u) for u in uniq], dtype=object)
+    rank = np.empty(len(uniq), dtype=np.int64)
+    order = np.argsort(uniq.astype(str), kind='stable')
+    rank[order] = np.arange(len(uniq))
+    return rank[codes] if len(uniq) else codes.astype(np.int64), uniq[order].astype(str) if len(uniq) else np.zeros(0, dtype=str)
+
+
+def _sorted_by_chrom_pos(df):
+    """``df.sort_values(['#CHROM', 'POS'])`` (stable) as a positional permutation."""
+    codes, _ = _chrom_codes(df['#CHROM'].to_numpy())
+    return np.lexsort((df['POS'].to_numpy().astype(np.int64), codes))
+
+
+def _segments(breaks):
+    """Start / end (exclusive) positions of the runs delimited by ``breaks`` (True = a new run starts here)."""
+    starts = np.flatnonzero(breaks)
+    ends = np.concatenate((starts[1:], [len(breaks)]))
+    return starts, ends
+
+
+# ------------------------------------------------------------------------------------------------ call_inv_cluster
+def cluster_variants(tables, vartype, cluster_win=200, cluster_win_min=500, cluster_min_snv=20, cluster_min_indel=10):
+    """Clusters of SNVs (``vartype='snv'``) or indels (``'indel'``). ``tables``: call tables with #CHROM POS END SVTYPE SVLEN FILTER
+    (the rule reads the INS/DEL table for indels and the SNV table for SNVs). -> #CHROM POS END COUNT."""
+    if vartype == 'indel':
+        cluster_min = cluster_min_indel
+    elif vartype == 'snv':
+        cluster_min = cluster_min_snv
+    else:
+        raise RuntimeError('Bad variant type {}: Expected "indel" or "snv"')
+    win_min = cluster_win   # sic: the reference assigns params.cluster_win to cluster_win_min (call_inv.snakefile:617-618)
+    df = pd.concat([t[['#CHROM', 'POS', 'END', 'SVTYPE', 'SVLEN', 'FILTER']] for t in tables], axis=0)
+    df = df.iloc[_sorted_by_chrom_pos(df)]
+    df = df.loc[df['FILTER'] == 'PASS']
+    if vartype == 'indel':
+        df = df.loc[df['SVLEN'] < 50]
+    empty = pd.DataFrame([], columns=['#CHROM', 'POS', 'END', 'COUNT'])
+    if df.shape[0] == 0:
+        return empty
+    codes, names = _chrom_codes(df['#CHROM'].to_numpy())
+    mid = (df['END'].to_numpy().astype(np.int64) + df['POS'].to_numpy().astype(np.int64)) // 2   # DEL to midpoint, in POS order
+    brk = np.ones(len(mid), dtype=bool)
+    brk[1:] = ~((mid[1:] < mid[:-1] + cluster_win) & (codes[1:] == codes[:-1]))
+    s, e = _segments(brk)
+    c_pos, c_end, count = mid[s], mid[e - 1], e - s
+    keep = (count >= cluster_min) & (c_end - c_pos >= win_min)
+    if not keep.any():
+        return empty
+    return pd.DataFrame({'#CHROM': names[codes[s][keep]].astype(object), 'POS': c_pos[keep], 'END': c_end[keep], 'COUNT': count[keep]},
+                        columns=['#CHROM', 'POS', 'END', 'COUNT']).reset_index(drop=True)
+
+
+# ------------------------------------------------------------------------------------------------ call_inv_flag_insdel_cluster
+def flag_insdel_cluster(df, vartype, flank_cluster=2, flank_merge=2000, cluster_min_svlen=4):
+    """Loci where an insertion sits next to deletions (``vartype`` 'sv': SVLEN >= 50, 'indel': cluster_min_svlen <= SVLEN < 50).
+    ``df``: merged INS/DEL calls with #CHROM POS END ID SVTYPE SVLEN FILTER. -> #CHROM POS END."""
+    svlen_min = cluster_min_svlen if vartype == 'indel' else 50
+    empty = pd.DataFrame([], columns=['#CHROM', 'POS', 'END'])
+    df = df.loc[df['FILTER'] == 'PASS']
+    df = df.loc[df['SVLEN'] >= svlen_min]
+    if vartype == 'indel':
+        df = df.loc[df['SVLEN'] < 50]
+    if df.shape[0] == 0:
+        return empty
+    codes, names = _chrom_codes(df['#CHROM'].to_numpy())
+    svtype = df['SVTYPE'].to_numpy()
+    pos, end = df['POS'].to_numpy().astype(np.int64), df['END'].to_numpy().astype(np.int64)
+    svlen = df['SVLEN'].to_numpy().astype(np.int64)
+    is_ins, is_del = svtype == 'INS', svtype == 'DEL'
+    m_chrom, m_pos, m_end = [], [], []
+    # Every INS against the DELs of its chromosome that overlap [POS - flank, POS + flank): with the DELs sorted by POS and a
+    # running maximum of END, the candidates are a prefix range; the exact overlap test runs on that range only.
+    for c in np.unique(codes[is_ins]).tolist():
+        d = np.flatnonzero(is_del & (codes == c))
+        if not len(d):
+            continue
+        d = d[np.argsort(pos[d], kind='stable')]
+        d_pos, d_end = pos[d], end[d]
+        run_end = np.maximum.accumulate(d_end)
+        ins = np.flatnonzero(is_ins & (codes == c))
+        lo_q, hi_q = pos[ins] - svlen[ins] * flank_cluster, pos[ins] + svlen[ins] * flank_cluster
+        hi_i = np.searchsorted(d_pos, hi_q, side='left')            # DELs with POS < hi
+        lo_i = np.searchsorted(run_end, lo_q, side='right')          # first DEL whose running END exceeds lo
+        for a, b, lo in zip(lo_i.tolist(), hi_i.tolist(), lo_q.tolist()):
+            if b <= a:
+                continue
+            sel = d_end[a:b] > lo
+            if sel.any():
+                m_chrom.append(c)
+                m_pos.append(int(d_pos[a:b][sel].min()))
+                m_end.append(int(d_end[a:b][sel].max()))
+    if not m_chrom:
+        return empty
+    m_chrom, m_pos, m_end = np.array(m_chrom), np.array(m_pos, dtype=np.int64), np.array(m_end, dtype=np.int64)
+    order = np.lexsort((m_pos, m_chrom))
+    m_chrom, m_pos, m_end = m_chrom[order], m_pos[order], m_end[order]
+    # merge intervals closer than flank_merge (running END per chromosome)
+    brk = np.ones(len(m_pos), dtype=bool)
+    run_end = m_end.copy()
+    for c in np.unique(m_chrom).tolist():
+        w = np.flatnonzero(m_chrom == c)
+        run_end[w] = np.maximum.accumulate(m_end[w])
+        brk[w[1:]] = m_pos[w[1:]] - flank_merge > run_end[w[:-1]]
+    s, e = _segments(brk)
+    s, e = s[:-1], e[:-1]       # sic: the reference never records the interval still open when its loop ends (call_inv.snakefile:551-571)
+    if not len(s):
+        return empty
+    out = pd.DataFrame({'#CHROM': names[m_chrom[s]].astype(object), 'POS': m_pos[s], 'END': run_end[e - 1]}, columns=['#CHROM', 'POS', 'END'])
+    return out.reset_index(drop=True)
+
+
+# ------------------------------------------------------------------------------------------------ call_inv_merge_flagged_loci
+def accept_flagged_region(type_set, allow_single_cluster=False, match_any=frozenset()):
+    """rules/call_inv.snakefile:56-79."""
+    if not allow_single_cluster and (type_set == {'CLUSTER_SNV'} or type_set == {'CLUSTER_INDEL'}):
+        return False
+    if match_any and not type_set & match_any:
+        return False
+    return True
+
+
+_TYPE_BITS = {'MATCH_SV': 1, 'MATCH_INDEL': 2, 'CLUSTER_INDEL': 4, 'CLUSTER_SNV': 8}
+
+
+def merge_flagged_loci(df_insdel_sv, df_insdel_indel, df_cluster_indel, df_cluster_snv, flank=500, batch_count=BATCH_COUNT_DEFAULT,
+                       inv_sig_filter='svindel'):
+    """Merge the four flag tables into candidate regions, decide which ones the inversion caller tries (TRY_INV) and deal them
+    round-robin into ``batch_count`` batches. -> #CHROM POS END ID SVTYPE SVLEN TYPE COUNT_INDEL COUNT_SNV TRY_INV BATCH."""
+    allow_single_cluster, match_any = False, set()
+    if inv_sig_filter is not None:
+        if inv_sig_filter == 'single_cluster':
+            allow_single_cluster = True
+        elif inv_sig_filter == 'svindel':
+            match_any = {'MATCH_SV', 'MATCH_INDEL'}
+        elif inv_sig_filter == 'sv':
+            match_any = {'MATCH_SV'}
+        else:
+            raise RuntimeError(f'Unrecognized region filter: {inv_sig_filter} (must be "single_cluster", "svindel", or "sv")')
+    columns = ['#CHROM', 'POS', 'END', 'ID', 'SVTYPE', 'SVLEN', 'TYPE', 'COUNT_INDEL', 'COUNT_SNV', 'TRY_INV', 'BATCH']
+    chrom, pos, end, c_indel, c_snv, bits = [], [], [], [], [], []
+    for df, name, col in ((df_insdel_sv, 'MATCH_SV', None), (df_insdel_indel, 'MATCH_INDEL', None),
+                          (df_cluster_indel, 'CLUSTER_INDEL', 'COUNT_INDEL'), (df_cluster_snv, 'CLUSTER_SNV', 'COUNT_SNV')):
+        n = df.shape[0]
+        if n == 0:
+            continue
+        chrom.append(df['#CHROM'].to_numpy().astype(str))
+        pos.append(df['POS'].to_numpy().astype(np.int64))
+        end.append(df['END'].to_numpy().astype(np.int64))
+        cnt = df['COUNT'].to_numpy().astype(np.int64) if col else np.zeros(n, dtype=np.int64)
+        c_indel.append(cnt if col == 'COUNT_INDEL' else np.zeros(n, dtype=np.int64))
+        c_snv.append(cnt if col == 'COUNT_SNV' else np.zeros(n, dtype=np.int64))
+        bits.append(np.full(n, _TYPE_BITS[name], dtype=np.int64))
+    if not chrom:
+        return pd.DataFrame([], columns=columns)
+    chrom, pos, end = np.concatenate(chrom), np.concatenate(pos), np.concatenate(end)
+    c_indel, c_snv, bits = np.concatenate(c_indel), np.concatenate(c_snv), np.concatenate(bits)
+    codes, names = _chrom_codes(chrom)
+    order = np.lexsort((pos, codes))       # concat order is kept among equal (#CHROM, POS), like the stable sort of the reference
+    codes, pos, end, c_indel, c_snv, bits = codes[order], pos[order], end[order], c_indel[order], c_snv[order], bits[order]
+    # a row joins the open region when it starts before (END of the *previous row*) + flank -- the reference overwrites the region
+    # end with every row it adds (call_inv.snakefile:404-412)
+    brk = np.ones(len(pos), dtype=bool)
+    brk[1:] = ~((pos[1:] < end[:-1] + flank) & (codes[1:] == codes[:-1]))
+    s, e = _segments(brk)
+    r_pos, r_end = pos[s], end[e - 1]
+    r_indel = np.add.reduceat(c_indel, s)
+    r_snv = np.add.reduceat(c_snv, s)
+    r_bits = np.bitwise_or.reduceat(bits, s)
+    r_chrom = names[codes[s]]
+    # pd.concat(...).T.sort_values(['#CHROM', 'POS']) of the regions: already in that order except that regions of one chromosome
+    # may repeat a POS; the stable sort keeps emission order for those
+    order = np.lexsort((r_pos, codes[s]))
+    r_chrom, r_pos, r_end, r_indel, r_snv, r_bits = r_chrom[order], r_pos[order], r_end[order], r_indel[order], r_snv[order], r_bits[order]
+    type_sets = [{t for t, b in _TYPE_BITS.items() if v & b} for v in r_bits.tolist()]
+    try_inv = np.array([accept_flagged_region(t, allow_single_cluster, match_any) for t in type_sets], dtype=bool)
+    batch = np.full(len(r_pos), -1, dtype=np.int64)
+    batch[try_inv] = np.arange(int(try_inv.sum())) % int(batch_count)
+    return pd.DataFrame({
+        '#CHROM': r_chrom.astype(object), 'POS': r_pos, 'END': r_end,
+        'ID': [f'{c}-{p}-RGN-{e_ - p}' for c, p, e_ in zip(r_chrom.tolist(), r_pos.tolist(), r_end.tolist())],
+        'SVTYPE': 'RGN', 'SVLEN': r_end - r_pos, 'TYPE': [','.join(sorted(t)) for t in type_sets],
+        'COUNT_INDEL': r_indel, 'COUNT_SNV': r_snv, 'TRY_INV': try_inv, 'BATCH': batch,
+    }, columns=columns)
