@@ -111,32 +111,40 @@ class AlignTable:
         self.qry_id = np.array([self.tig_names[str(q)] for q in self.qry.tolist()], dtype=np.int32)
 
 
-def walk_rows(table, ref_arr, tig_arr, ctx=None, ref_store=None):
+def _resolve(x):
+    """Inputs of walk_rows may be ``concurrent.futures.Future`` objects (FASTA read / CIGAR tokenizer running beside the uploads)."""
+    return x.result() if hasattr(x, 'result') else x
+
+
+def walk_rows(table, ref_arr, tig_arr, ctx=None, ref_store=None, parsed=None):
     """Run the CIGAR walk for ``table`` on the GPU. ``ref_arr`` / ``tig_arr``: uint8 arrays in the order of
-    ``table.ref_names`` / ``table.tig_names``. ``ref_store`` may be a resident store (multi-GPU: the broadcast
-    reference) whose sequence order matches ``table.ref_names``.
+    ``table.ref_names`` / ``table.tig_names`` (or futures resolving to them). ``ref_store`` may be a resident store
+    (multi-GPU: the broadcast reference) whose sequence order matches ``table.ref_names``. ``parsed``: result of
+    ``device.parse_cigars(table.cigars)`` (or a future) when the caller tokenised the CIGARs already.
 
     Returns ``(snv rows, indel rows)`` in emission order; raises the reference's exceptions for bad CIGARs."""
     global last_stats, last_walk_seconds
     ctx = ctx or device.get_context()
     own_ref = ref_store is None
+    tig_store = None
     t0 = time.perf_counter()
-    if own_ref:
-        ref_store = device.SeqStore(ctx, list(table.ref_names), ref_arr, keep_host=False)
-    t1 = time.perf_counter()
-    tig_store = device.SeqStore(ctx, list(table.tig_names), tig_arr, keep_host=False)
-    t2 = time.perf_counter()
     try:
-        ops, op_off, perr = device.parse_cigars(table.cigars)
+        if own_ref:
+            ref_store = device.SeqStore(ctx, list(table.ref_names), _resolve(ref_arr), keep_host=False)
+        t1 = time.perf_counter()
+        tig_store = device.SeqStore(ctx, list(table.tig_names), _resolve(tig_arr), keep_host=False)
+        t2 = time.perf_counter()
+        ops, op_off, perr = _resolve(parsed) if parsed is not None else device.parse_cigars(table.cigars)
         t3 = time.perf_counter()
         snv, indel, cerr, stats = device.cigar_call(ctx, ref_store, tig_store, table.ref_id, table.qry_id,
                                                     table.pos.astype(np.int32), table.rev.astype(np.uint8), ops, op_off)
         t4 = time.perf_counter()
     finally:
-        if own_ref:
+        if own_ref and ref_store is not None:
             ref_store.close()
-        tig_store.close()
-    last_walk_seconds = {'ref_store': t1 - t0, 'tig_store': t2 - t1, 'cigar_parse': t3 - t2, 'cigar_call': t4 - t3,
+        if tig_store is not None:
+            tig_store.close()
+    last_walk_seconds = {'ref_store': t1 - t0, 'tig_store_incl_wait_for_read': t2 - t1, 'cigar_parse_wait': t3 - t2, 'cigar_call': t4 - t3,
                          'close': time.perf_counter() - t4}
     last_stats = stats.as_dict()
     # Errors surface in walk order (the reference raises lazily while iterating records and ops)
@@ -162,18 +170,29 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     global last_phase_seconds
     if df_align.shape[0] == 0:
         return _empty(SNV_COLUMNS), _empty(INSDEL_COLUMNS)
+    from concurrent.futures import ThreadPoolExecutor
     t0 = time.perf_counter()
     table = AlignTable(df_align)
     ref_fa = fasta.open_fasta(ref_fa_name)
     tig_fa = fasta.open_fasta(tig_fa_name)
-    ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
-    tig_arr = [tig_fa.fetch_array(nm) for nm in table.tig_names]
-    t1 = time.perf_counter()
-    snv, indel = walk_rows(table, ref_arr, tig_arr)
+    # The contig FASTA is read and the CIGARs are tokenised beside the reference read / upload / pack (file reads, numpy
+    # copies and the C calls all release the GIL).
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        f_tig = pool.submit(lambda: [tig_fa.fetch_array(nm) for nm in table.tig_names])
+        f_ops = pool.submit(device.parse_cigars, table.cigars)
+        try:
+            ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
+            t1 = time.perf_counter()
+            snv, indel = walk_rows(table, ref_arr, f_tig, parsed=f_ops)
+        except BaseException:
+            f_tig.cancel()
+            f_ops.cancel()
+            raise
+        tig_arr = f_tig.result()
     t2 = time.perf_counter()
     frames = build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
                           table.qry_id, hap, version_id)
-    last_phase_seconds = {'fasta': t1 - t0, 'device_walk_incl_h2d_d2h': t2 - t1, 'frames': time.perf_counter() - t2}
+    last_phase_seconds = {'fasta_reference': t1 - t0, 'device_walk_incl_contig_read_h2d_d2h': t2 - t1, 'frames': time.perf_counter() - t2}
     return frames
 
 
