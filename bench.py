@@ -302,9 +302,15 @@ def density_secondary(ctx, args, rank):
     batch.close()
     rs.close()
     ts.close()
-    t0 = time.perf_counter()
-    out = density.density_windows([(ref[a], tig[b], False, 20) for a, b, _, _ in meta])
-    e2e_s = time.perf_counter() - t0
+    e2e_runs = []
+    for i in range(3):   # one warm-up call (first-use allocation of the pinned result pool), two timed ones
+        out = None       # releasing the previous result is not part of the call
+        t0 = time.perf_counter()
+        out = density.density_windows([(ref[a], tig[b], False, 20) for a, b, _, _ in meta])
+        if i >= 1:
+            e2e_runs.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_runs))
+    e2e_d2h = int(sum(sum(v.nbytes for k, v in d.items() if hasattr(v, 'nbytes')) for d in out))
     # spot check window 0 against the oracle
     ok, cpu = None, None
     try:
@@ -322,7 +328,8 @@ def density_secondary(ctx, args, rank):
     k_ms = float(np.mean(ms))
     return {
         'metric': 'inv_kmer_density_gbases_per_sec', 'unit': 'Gbases/s', 'value': bases / (k_ms * 1e-3) / 1e9,
-        'e2e': {'value': bases / e2e_s / 1e9, 'unit': 'Gbases/s'},
+        'e2e': {'value': bases / e2e_s / 1e9, 'unit': 'Gbases/s', 'ms_per_step': e2e_s * 1e3, 'h2d_bytes_per_step': 2 * bases, 'd2h_bytes_per_step': e2e_d2h,
+                'api': 'pav_b200.pavlib.density.density_windows (ASCII windows in host memory -> column arrays in host memory)'},
         'config': {'workload': f'C5-shaped: {n_win} windows x 50 kbp, k=31, srs=20 per GPU', 'l2': 'flushed between iterations'},
         'ms_per_step': k_ms, 'ms_kmer': st.ms_kmer, 'ms_kde': st.ms_kde, 'kde_pairs': int(st.kde_pairs),
         'kde_pairs_per_sec': st.kde_pairs / (st.ms_kde * 1e-3) if st.ms_kde > 0 else None,
@@ -458,6 +465,29 @@ def run_ours(args, rank, world, local):
         e2e_val = ctl.sum(e2e_rows) / ctl.max(float(np.mean(e2e_s)))
     h2d_api = int(sum(len(ref[n]) for n in names_r) + h2d_cabi)
 
+    # ---- the same public call with a packed-reference sidecar next to the reference FASTA (pav_b200/sidecar.py; built once per
+    # reference, outside the timed region): reference bases are views of the mapped file, the upload is the packed planes
+    sc_s = []
+    if args.e2e_steps > 0:
+        from pav_b200 import sidecar
+        sc_path = sidecar.build(ref_fa)
+        for i in range(1 + min(args.e2e_steps, 3)):
+            ctl.barrier()
+            fasta_mod._CACHE.clear()
+            sidecar._OPEN.clear()
+            df_snv = df_insdel = None
+            t0 = time.perf_counter()
+            df_snv, df_insdel = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
+            dt = time.perf_counter() - t0
+            assert cigarcall.last_phase_seconds['sidecar'] and len(df_snv) + len(df_insdel) == n_rows
+            if i >= 1:
+                sc_s.append(dt)
+        os.unlink(sc_path)
+        df_snv = df_insdel = None
+    e2e_sidecar = {'value': ctl.sum(n_rows) / ctl.max(float(np.mean(sc_s))), 'unit': UNIT, 'ms_per_step': float(np.mean(sc_s)) * 1e3,
+                   'h2d_bytes_per_step': int(h2d_cabi + 0.375 * sum(len(ref[n]) for n in names_r)), 'd2h_bytes_per_step': d2h_cabi,
+                   'api': 'make_insdel_snv_calls with <ref>.pavsc present (packed planes + mapped bases; sidecar built once, untimed)'} if sc_s else None
+
     # ---- secondary metric (Path B)
     secondary = None
     if args.density_windows > 0:
@@ -536,6 +566,7 @@ def run_ours(args, rank, world, local):
                     'phase_seconds_last_step': cigarcall.last_phase_seconds},
             'e2e_cabi': {'value': cabi_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d_cabi, 'd2h_bytes_per_step': d2h_cabi,
                          'api': 'pavgpu_seqstore_create(contigs) + pavgpu_cigar_call (host buffers)', 'ms_per_step': float(np.mean(cabi_s)) * 1e3 if cabi_s else None},
+            'e2e_sidecar': e2e_sidecar,
             'gpu_launches': int(st.kernel_launches) * args.steps, 'wall_ms_per_step_incl_flush': wall_ms,
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clk, 'ref_broadcast_ms': bcast_ms, 'oracle_spot_check': parity,
             'secondary': secondary,

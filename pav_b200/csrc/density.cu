@@ -636,6 +636,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     memset(&b->stats, 0, sizeof b->stats);
     b->ran = false;
     if (n_win == 0) { b->ran = true; b->rows_total = 0; if (stats) *stats = b->stats; return PAVGPU_OK; }
+    PavTrace tr("density_batch_run");
 
     // ---- plan, part 1 (host)
     int64_t tab = 0, pos = 0, tiles = 0, bases = 0, tree_cap = 0;
@@ -719,6 +720,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     std::vector<WinCounts> wc(n_win);
     CUDA_TRY(cudaMemcpyAsync(wc.data(), b->d_wc, sizeof(WinCounts) * n_win, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    tr.mark("plan + k-mer kernels");
 
     // ---- plan, part 2 (host): status, keep mask, N, dense row offsets, sample counts
     int64_t rows = 0;
@@ -787,6 +789,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     std::vector<int32_t> n_fill(n_win, 0);
     CUDA_TRY(cudaMemcpyAsync(n_fill.data(), b->d_n_fill, sizeof(int32_t) * n_win, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    tr.mark("compact + KDE sampled");
     for (int32_t w = 0; w < n_win; w++) {
         pairs += ((int64_t)b->plan[w].n_samp + n_fill[w]) * b->plan[w].n_rows;
         b->res[w].n_eval += n_fill[w];
@@ -827,10 +830,11 @@ static int fetch_col(pavgpu_ctx *ctx, const T *d, int64_t n, T **out)
 {
     *out = nullptr;
     if (n == 0) return PAVGPU_OK;
-    T *h = (T *)malloc((size_t)n * sizeof(T));
-    if (!h) { pav_set_error("density fetch: out of host memory"); return PAVGPU_ERR_NOMEM; }
+    T *h = nullptr;   // pinned result buffer from the context's pool (released with pavgpu_free_host)
+    int prc = pav_pinned_take(ctx, (size_t)n * sizeof(T), reinterpret_cast<void **>(&h));
+    if (prc) return prc;
     cudaError_t e = cudaMemcpyAsync(h, d, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e != cudaSuccess) { free(h); pav_set_error("density fetch: %s", cudaGetErrorString(e)); return PAVGPU_ERR_CUDA; }
+    if (e != cudaSuccess) { pavgpu_free_host(h); pav_set_error("density fetch: %s", cudaGetErrorString(e)); return PAVGPU_ERR_CUDA; }
     *out = h;
     return PAVGPU_OK;
 }
@@ -850,6 +854,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch
     for (int32_t w = 0; w < b->n_win; w++) res[w] = b->res[w];
     int64_t n = b->rows_total;
     *n_rows_total = n;
+    PavTrace tr("density_batch_fetch");
     CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
     int rc = 0;
     rc |= fetch_col(ctx, b->d_kmer, n, kmer_out);
@@ -860,10 +865,13 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch
     rc |= fetch_col(ctx, b->d_k[1], n, kern_fwdrev_out);
     rc |= fetch_col(ctx, b->d_k[2], n, kern_rev_out);
     CUDA_TRY(cudaEventRecord(ctx->ev[6], ctx->stream));
+    tr.mark("pinned buffers + enqueue");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    tr.mark("d2h");
     b->stats.ms_d2h = ev_ms(ctx->ev[5], ctx->ev[6]);
     if (rc) {
-        free(*kmer_out); free(*index_out); free(*state_mer_out); free(*state_out); free(*kern_fwd_out); free(*kern_fwdrev_out); free(*kern_rev_out);
+        pavgpu_free_host(*kmer_out); pavgpu_free_host(*index_out); pavgpu_free_host(*state_mer_out); pavgpu_free_host(*state_out);
+        pavgpu_free_host(*kern_fwd_out); pavgpu_free_host(*kern_fwdrev_out); pavgpu_free_host(*kern_rev_out);
         return PAVGPU_ERR_NOMEM;
     }
     return PAVGPU_OK;

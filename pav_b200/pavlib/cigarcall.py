@@ -11,7 +11,7 @@ import time
 import numpy as np
 import pandas as pd
 
-from .. import device, fasta
+from .. import device, fasta, sidecar
 from . import variant
 
 CALL_SOURCE = 'CIGAR'          # pavlib/cigarcall.py:19
@@ -177,22 +177,38 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     tig_fa = fasta.open_fasta(tig_fa_name)
     # The contig FASTA is read and the CIGARs are tokenised beside the reference read / upload / pack (file reads, numpy
     # copies and the C calls all release the GIL).
+    sc = sidecar.find(ref_fa_name)    # packed-reference sidecar next to the FASTA (pav_b200/sidecar.py), when there is a fresh one
+    ref_store, own_store = None, False
     with ThreadPoolExecutor(max_workers=2) as pool:
         f_tig = pool.submit(lambda: [tig_fa.fetch_array(nm) for nm in table.tig_names])
         f_ops = pool.submit(device.parse_cigars, table.cigars)
         try:
-            ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
+            if sc is not None:
+                # host arrays are views of the mapped file, the upload is the packed planes; records index the sidecar's order
+                missing = [nm for nm in table.ref_names if nm not in sc.ids]
+                if missing:
+                    raise KeyError(f'sequence {missing[0]!r} not found in {sc.path}')
+                ref_arr = sc.arrays()
+                ref_id = np.array([sc.ids[nm] for nm in table.ref_names], dtype=np.int32)[table.ref_id]
+                table.ref_names, table.ref_id = {nm: i for i, nm in enumerate(sc.names)}, ref_id
+                ref_store, own_store = sidecar.reference_store(sc)
+            else:
+                ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
             t1 = time.perf_counter()
-            snv, indel = walk_rows(table, ref_arr, f_tig, parsed=f_ops)
+            snv, indel = walk_rows(table, ref_arr, f_tig, ref_store=ref_store, parsed=f_ops)
         except BaseException:
             f_tig.cancel()
             f_ops.cancel()
             raise
+        finally:
+            if own_store:
+                ref_store.close()
         tig_arr = f_tig.result()
     t2 = time.perf_counter()
     frames = build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
                           table.qry_id, hap, version_id)
-    last_phase_seconds = {'fasta_reference': t1 - t0, 'device_walk_incl_contig_read_h2d_d2h': t2 - t1, 'frames': time.perf_counter() - t2}
+    last_phase_seconds = {'fasta_reference': t1 - t0, 'device_walk_incl_contig_read_h2d_d2h': t2 - t1, 'frames': time.perf_counter() - t2,
+                          'sidecar': sc is not None}
     return frames
 
 

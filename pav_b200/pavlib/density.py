@@ -93,23 +93,34 @@ def density_windows(windows, k=31, ctx=None, **kw):
     windows = list(windows)
     refs = [np.ascontiguousarray(w[0], dtype=np.uint8) for w in windows]
     tigs = [np.ascontiguousarray(w[1], dtype=np.uint8) for w in windows]
+    import time
+    t0 = time.perf_counter()
     rs = device.SeqStore(ctx, [f'r{i}' for i in range(len(refs))], refs, keep_host=False)
     ts = device.SeqStore(ctx, [f't{i}' for i in range(len(tigs))], tigs, keep_host=False)
+    t1 = time.perf_counter()
     try:
         win = np.zeros(len(windows), dtype=_capi.DENSITY_WINDOW)
-        for i, w in enumerate(windows):
-            win[i] = (i, i, 0, len(refs[i]), 0, len(tigs[i]), int(bool(w[2])), int(w[3]))
+        win['ref_seq_id'] = win['tig_seq_id'] = np.arange(len(windows))
+        win['ref_end'] = [len(r) for r in refs]
+        win['tig_end'] = [len(t) for t in tigs]
+        win['rev'] = [int(bool(w[2])) for w in windows]
+        win['srs'] = [int(w[3]) for w in windows]
         batch = DensityBatch(ctx, win, default_params(k=k, **kw))
+        t2 = time.perf_counter()
         try:
             st = batch.run(rs, ts)
+            t3 = time.perf_counter()
             res, cols = batch.fetch()
+            t4 = time.perf_counter()
         finally:
             batch.close()
     finally:
         rs.close()
         ts.close()
+    out = _split(res, cols)
     last_stats = st.as_dict()
-    return _split(res, cols)
+    last_stats['seconds'] = {'stores': t1 - t0, 'batch_create': t2 - t1, 'run': t3 - t2, 'fetch': t4 - t3, 'split': time.perf_counter() - t4}
+    return out
 
 
 def frame_from_result(d):
