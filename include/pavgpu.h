@@ -56,6 +56,10 @@ int pavgpu_ctx_create(int device, pavgpu_ctx **ctx_out);
 void pavgpu_ctx_destroy(pavgpu_ctx *ctx);
 int pavgpu_ctx_device(const pavgpu_ctx *ctx);
 void pavgpu_free_host(void *p);
+/* Pinned host buffer from the context's pool (released with pavgpu_free_host): staging for sequences a caller is about to hand
+ * to pavgpu_seqstore_create -- copies out of pinned memory run at PCIe speed instead of through the driver's bounce buffers.
+ * Replaces nothing in the reference (pysam hands out Python strings, pavlib/cigarcall.py:59-66). */
+int pavgpu_host_alloc(pavgpu_ctx *ctx, size_t bytes, void **buf_out);
 /* Evict L2 between timed iterations: overwrites a scratch buffer of `bytes` (> 126 MB L2) on the context stream. */
 int pavgpu_l2_flush(pavgpu_ctx *ctx, size_t bytes);
 

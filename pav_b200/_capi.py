@@ -60,7 +60,7 @@ _lib = None
 
 EXPORTS = [
     'pavgpu_last_error', 'pavgpu_device_count', 'pavgpu_ctx_create', 'pavgpu_ctx_destroy', 'pavgpu_ctx_device',
-    'pavgpu_free_host', 'pavgpu_l2_flush', 'pavgpu_seqstore_create', 'pavgpu_seqstore_create_packed', 'pavgpu_seqstore_create_empty',
+    'pavgpu_free_host', 'pavgpu_host_alloc', 'pavgpu_l2_flush', 'pavgpu_seqstore_create', 'pavgpu_seqstore_create_packed', 'pavgpu_seqstore_create_empty',
     'pavgpu_seqstore_free', 'pavgpu_seqstore_n_seq', 'pavgpu_seqstore_total_bases', 'pavgpu_seqstore_planes',
     'pavgpu_seqstore_export', 'pavgpu_seqstore_offset', 'pavgpu_cigar_parse', 'pavgpu_cigar_batch_create',
     'pavgpu_cigar_batch_free', 'pavgpu_cigar_batch_run', 'pavgpu_cigar_batch_fetch', 'pavgpu_cigar_call',
@@ -85,6 +85,7 @@ def lib():
     L.pavgpu_ctx_destroy.restype = None
     L.pavgpu_ctx_device.argtypes = [c_vp]
     L.pavgpu_free_host.argtypes = [c_vp]
+    L.pavgpu_host_alloc.argtypes = [c_vp, ctypes.c_size_t, P(c_vp)]
     L.pavgpu_free_host.restype = None
     L.pavgpu_l2_flush.argtypes = [c_vp, ctypes.c_size_t]
     L.pavgpu_seqstore_create.argtypes = [c_vp, c_i32, P(c_vp), P(c_i64), P(c_vp)]

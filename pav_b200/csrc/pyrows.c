@@ -305,28 +305,35 @@ static PyObject *one_char(unsigned c)
     return one_char_table[c];
 }
 
-/* snv_frame(rows, order, ref_b, alt_b, ids|None, chrom_objs, chrom_strs, qry_strs, strand_objs, align_index_objs, consts)
+/* snv_frame(rows, order, ids|None, chrom_objs, chrom_strs, qry_strs, strand_objs, align_index_objs, ref_id, qry_id, rev,
+ *           seqs, n_ref, comp, consts)
  *   rows: pavgpu_snv_row buffer (emission order); order: int64 permutation (final row k shows emission row order[k]);
- *   ref_b / alt_b: uint8 buffers, REF / ALT base per emission row (original case); ids: object ndarray of ready IDs in
- *   emission order, or None to format "{chrom}-{pos+1}-SNV-{REF}{ALT}" (upper-cased bases) here;
- *   consts = (svtype 'SNV', svlen 1, hap, ci 0, call_source)
+ *   ids: object ndarray of ready IDs in emission order, or None to format "{chrom}-{pos+1}-SNV-{REF}{ALT}" (upper-cased bases)
+ *   here; ref_id / qry_id: int32 per record; rev: uint8 per record; seqs: list of uint8 buffers = reference sequences then
+ *   contigs (forward strand): REF = reference[pos], ALT = contig[qry_pos], complemented through comp for minus-strand records
+ *   (cigarcall.py:69-70,105-106); consts = (svtype 'SNV', svlen 1, hap, ci 0, call_source)
  * -> tuple of 14 object ndarrays in column order of the reference (pavlib/cigarcall.py:125-134). */
 static PyObject *py_snv_frame(PyObject *self, PyObject *args)
 {
-    Py_buffer rows, order, refb, altb;
-    PyObject *ids, *chrom_objs, *chrom_strs, *qry_strs, *strand_objs, *ai_objs, *consts;
-    if (!PyArg_ParseTuple(args, "y*y*y*y*OOOOOOO", &rows, &order, &refb, &altb, &ids, &chrom_objs, &chrom_strs, &qry_strs, &strand_objs, &ai_objs, &consts))
+    Py_buffer rows, order, ref_id, qry_id, rev, comp;
+    PyObject *ids, *chrom_objs, *chrom_strs, *qry_strs, *strand_objs, *ai_objs, *seqs, *consts;
+    Py_ssize_t n_ref;
+    if (!PyArg_ParseTuple(args, "y*y*OOOOOOy*y*y*O!ny*O", &rows, &order, &ids, &chrom_objs, &chrom_strs, &qry_strs, &strand_objs, &ai_objs,
+                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &consts))
         return NULL;
     PyObject *result = NULL, *cols[SNV_NCOL] = {0};
     PyObject **slot[SNV_NCOL];
     strtab_t tc = {0}, tq = {0};
     PyObject **id_src = NULL;
-    Py_ssize_t n = order.len / 8, n_rows = rows.len / (Py_ssize_t)sizeof(snv_row_t);
-    if (refb.len < n_rows || altb.len < n_rows || n > n_rows) { PyErr_SetString(PyExc_ValueError, "snv_frame: buffer sizes disagree"); goto done; }
+    Py_ssize_t n = order.len / 8, n_rows = rows.len / (Py_ssize_t)sizeof(snv_row_t), nd_seq = PyList_GET_SIZE(seqs), got = 0;
+    Py_buffer *bufs = (Py_buffer *)PyMem_Calloc((size_t)nd_seq + 1, sizeof(Py_buffer));
+    if (!bufs) { PyErr_NoMemory(); goto done; }
+    if (n > n_rows || comp.len < 256) { PyErr_SetString(PyExc_ValueError, "snv_frame: buffer sizes disagree"); goto done; }
     if (strtab_load(&tc, chrom_strs, "chrom_strs") < 0 || strtab_load(&tq, qry_strs, "qry_strs") < 0) goto done;
     Py_ssize_t n_rec = tc.n;
-    if (tq.n < n_rec || list_of(chrom_objs, n_rec, "chrom_objs") < 0 || list_of(strand_objs, n_rec, "strand_objs") < 0 || list_of(ai_objs, n_rec, "align_index_objs") < 0) {
-        if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "snv_frame: per-record lists disagree");
+    if (tq.n < n_rec || ref_id.len < n_rec * 4 || qry_id.len < n_rec * 4 || rev.len < n_rec || list_of(chrom_objs, n_rec, "chrom_objs") < 0 ||
+        list_of(strand_objs, n_rec, "strand_objs") < 0 || list_of(ai_objs, n_rec, "align_index_objs") < 0) {
+        if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "snv_frame: per-record arrays disagree");
         goto done;
     }
     if (!PyTuple_Check(consts) || PyTuple_GET_SIZE(consts) != 5) { PyErr_SetString(PyExc_TypeError, "snv_frame: consts must be a 5-tuple"); goto done; }
@@ -337,11 +344,14 @@ static PyObject *py_snv_frame(PyObject *self, PyObject *args)
         }
         id_src = (PyObject **)PyArray_DATA((PyArrayObject *)ids);
     }
+    for (; got < nd_seq; got++)
+        if (PyObject_GetBuffer(PyList_GET_ITEM(seqs, got), &bufs[got], PyBUF_SIMPLE) < 0) goto done;
     for (int c = 0; c < SNV_NCOL; c++) { cols[c] = new_obj_array(n, &slot[c]); if (!cols[c]) goto done; }
     {
         const snv_row_t *R = (const snv_row_t *)rows.buf;
         const int64_t *ord = (const int64_t *)order.buf;
-        const uint8_t *rb = (const uint8_t *)refb.buf, *ab = (const uint8_t *)altb.buf;
+        const int32_t *rid = (const int32_t *)ref_id.buf, *qid = (const int32_t *)qry_id.buf;
+        const uint8_t *rv = (const uint8_t *)rev.buf, *ct = (const uint8_t *)comp.buf;
         PyObject *c_svtype = PyTuple_GET_ITEM(consts, 0), *c_svlen = PyTuple_GET_ITEM(consts, 1), *c_hap = PyTuple_GET_ITEM(consts, 2),
                  *c_ci = PyTuple_GET_ITEM(consts, 3), *c_src = PyTuple_GET_ITEM(consts, 4);
         fill_const(slot[4], n, c_svtype); fill_const(slot[5], n, c_svlen); fill_const(slot[8], n, c_hap);
@@ -351,12 +361,20 @@ static PyObject *py_snv_frame(PyObject *self, PyObject *args)
             if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "snv_frame: order entry out of range"); goto done; }
             const snv_row_t r = R[i];
             if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "snv_frame: record index out of range"); goto done; }
+            const Py_ssize_t wr = rid[r.rec], wq = n_ref + (Py_ssize_t)qid[r.rec];
+            if (wr < 0 || wr >= n_ref || wq < n_ref || wq >= nd_seq || r.pos_ref < 0 || r.pos_ref >= bufs[wr].len || r.qry_pos < 0 || r.qry_pos >= bufs[wq].len) {
+                PyErr_SetString(PyExc_IndexError, "snv_frame: position outside its sequence"); goto done;
+            }
+            const unsigned rb = ((const uint8_t *)bufs[wr].buf)[r.pos_ref];
+            unsigned ab = ((const uint8_t *)bufs[wq].buf)[r.qry_pos];
+            if (rv[r.rec]) ab = ct[ab];
             PyObject *o;
             o = PyList_GET_ITEM(chrom_objs, r.rec); Py_INCREF(o); slot[0][k] = o;
             if (!(slot[1][k] = PyLong_FromLong(r.pos_ref))) goto done;
             if (!(slot[2][k] = PyLong_FromLong((long)r.pos_ref + 1))) goto done;
             if (id_src) { o = id_src[i]; Py_INCREF(o); slot[3][k] = o; }
             else {   /* {chrom}-{pos+1}-SNV-{REF}{ALT} */
+                if ((rb | ab) & 0x80) { PyErr_SetString(PyExc_ValueError, "snv_frame: non-ASCII base"); goto done; }
                 int64_t p1 = (int64_t)r.pos_ref + 1;
                 int nd = ndig_i64(p1);
                 Py_ssize_t cl = tc.len[r.rec], len = cl + 1 + nd + 5 + 2;
@@ -365,14 +383,14 @@ static PyObject *py_snv_frame(PyObject *self, PyObject *args)
                 memcpy(d, tc.s[r.rec], (size_t)cl); d += cl;
                 *d++ = '-'; d = put_i64_fwd(d, p1, nd);
                 memcpy(d, "-SNV-", 5); d += 5;
-                unsigned a = rb[i], b = ab[i];
-                *d++ = (char)((a >= 'a' && a <= 'z') ? a - 32 : a);
-                *d++ = (char)((b >= 'a' && b <= 'z') ? b - 32 : b);
-                if ((rb[i] | ab[i]) & 0x80) { Py_DECREF(o); PyErr_SetString(PyExc_ValueError, "snv_frame: non-ASCII base"); goto done; }
+                *d++ = (char)((rb >= 'a' && rb <= 'z') ? rb - 32 : rb);
+                *d++ = (char)((ab >= 'a' && ab <= 'z') ? ab - 32 : ab);
                 slot[3][k] = o;
             }
-            if (!(o = one_char(rb[i]))) goto done; Py_INCREF(o); slot[6][k] = o;
-            if (!(o = one_char(ab[i]))) goto done; Py_INCREF(o); slot[7][k] = o;
+            if (!(o = one_char(rb))) goto done;
+            Py_INCREF(o); slot[6][k] = o;
+            if (!(o = one_char(ab))) goto done;
+            Py_INCREF(o); slot[7][k] = o;
             {   /* {qry}:{qp+1}-{qp+1} */
                 int64_t q1 = (int64_t)r.qry_pos + 1;
                 int nd = ndig_i64(q1);
@@ -392,8 +410,9 @@ static PyObject *py_snv_frame(PyObject *self, PyObject *args)
     if (result) for (int c = 0; c < SNV_NCOL; c++) { PyTuple_SET_ITEM(result, c, cols[c]); cols[c] = NULL; }
 done:
     for (int c = 0; c < SNV_NCOL; c++) Py_XDECREF(cols[c]);
+    if (bufs) { for (Py_ssize_t j = 0; j < got; j++) PyBuffer_Release(&bufs[j]); PyMem_Free(bufs); }
     strtab_free(&tc); strtab_free(&tq);
-    PyBuffer_Release(&rows); PyBuffer_Release(&order); PyBuffer_Release(&refb); PyBuffer_Release(&altb);
+    PyBuffer_Release(&rows); PyBuffer_Release(&order); PyBuffer_Release(&ref_id); PyBuffer_Release(&qry_id); PyBuffer_Release(&rev); PyBuffer_Release(&comp);
     return result;
 }
 
@@ -531,10 +550,57 @@ done:
     return result;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Arena recycling. A 2 M-row result is ~8 M small str / int objects = several hundred MB of pymalloc arenas. CPython maps
+ * every arena fresh (mmap, 1 MiB) and unmaps it as soon as it is empty, so each call pays the first-touch page faults
+ * for all of it again (measured: ~0.4 ns per byte, a third of the frame-building time). keep_arenas(max_mb) installs an
+ * arena allocator (PyObject_SetArenaAllocator, the documented hook) that keeps up to max_mb of released arenas and hands them
+ * out again; anything beyond goes back to the OS as before. Arenas need not be zeroed (pymalloc initialises the pools it carves).
+ * ------------------------------------------------------------------------------------------------ */
+#include <sys/mman.h>
+
+static struct {
+    void **ptr;
+    size_t n, cap, size;
+    int installed;
+} g_arena;
+
+static void *arena_alloc(void *ctx, size_t size)
+{
+    if (g_arena.n > 0 && size == g_arena.size) return g_arena.ptr[--g_arena.n];
+    void *p = mmap(NULL, size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    return p == MAP_FAILED ? NULL : p;
+}
+
+static void arena_free(void *ctx, void *ptr, size_t size)
+{
+    if (g_arena.n < g_arena.cap && (g_arena.size == 0 || g_arena.size == size)) {
+        g_arena.size = size;
+        g_arena.ptr[g_arena.n++] = ptr;
+        return;
+    }
+    munmap(ptr, size);
+}
+
+static PyObject *py_keep_arenas(PyObject *self, PyObject *arg)
+{
+    long max_mb = PyLong_AsLong(arg);
+    if (max_mb == -1 && PyErr_Occurred()) return NULL;
+    if (g_arena.installed || max_mb <= 0) Py_RETURN_FALSE;
+    g_arena.cap = (size_t)max_mb;   /* arenas are 1 MiB on 64-bit CPython >= 3.10 (256 KiB before: the cap is then a quarter) */
+    g_arena.ptr = (void **)malloc(g_arena.cap * sizeof(void *));
+    if (!g_arena.ptr) return PyErr_NoMemory();
+    PyObjectArenaAllocator a = {NULL, arena_alloc, arena_free};
+    PyObject_SetArenaAllocator(&a);
+    g_arena.installed = 1;
+    Py_RETURN_TRUE;
+}
+
 static PyMethodDef methods[] = {
     {"format", py_format, METH_VARARGS, "format(n, parts) -> list of str"},
     {"ints", py_ints, METH_O, "ints(int64 buffer) -> list of int"},
     {"slices", py_slices, METH_VARARGS, "slices(data list, which, start, length, rc, comp) -> list of str"},
+    {"keep_arenas", py_keep_arenas, METH_O, "keep_arenas(max_mb): recycle up to max_mb of released pymalloc arenas"},
     {"snv_frame", py_snv_frame, METH_VARARGS, "all 14 columns of df_snv in final row order"},
     {"indel_frame", py_indel_frame, METH_VARARGS, "all 16 columns of df_insdel in final row order"},
     {NULL, NULL, 0, NULL}};

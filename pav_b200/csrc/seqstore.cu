@@ -161,6 +161,14 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_free_host(void *p)
     if (p && !pav_pinned_give(p)) free(p);
 }
 
+extern "C" __attribute__((visibility("default"))) int pavgpu_host_alloc(pavgpu_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) { pav_set_error("host_alloc: bad argument"); return PAVGPU_ERR_ARG; }
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return pav_pinned_take(ctx, bytes, out);
+}
+
 extern "C" __attribute__((visibility("default"))) int pavgpu_l2_flush(pavgpu_ctx *ctx, size_t bytes)
 {
     if (!ctx || bytes == 0) { pav_set_error("l2_flush: bad argument"); return PAVGPU_ERR_ARG; }

@@ -133,6 +133,13 @@ class SeqStore:
             pass
 
 
+def pinned_empty(ctx, nbytes):
+    """uint8 array over a pinned host buffer from the context's pool (goes back to the pool when the array and its views die)."""
+    p = c_vp()
+    _capi.check(_capi.lib().pavgpu_host_alloc(ctx.handle, int(max(nbytes, 1)), ctypes.byref(p)), 'pavgpu_host_alloc')
+    return _capi.take_host_array(p.value, int(max(nbytes, 1)), np.uint8)[:nbytes]
+
+
 def nccl_unique_id():
     buf = np.zeros(128, dtype=np.uint8)
     _capi.check(_capi.lib().pavgpu_nccl_unique_id(_capi.ptr(buf)), 'pavgpu_nccl_unique_id')

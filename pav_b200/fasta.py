@@ -187,6 +187,34 @@ class Fasta:
             self._seq_cache[name] = seq
         return seq
 
+    def fetch_into(self, name, out):
+        """Whole record ``name`` written into ``out`` (uint8, at least the record's length; e.g. a pinned staging buffer):
+        one strided copy of the full lines + the last partial line. Returns ``out[:length]``."""
+        name = str(name)
+        if name not in self.index:
+            raise KeyError(f'sequence {name!r} not found in {self.path}')
+        length, offset, linebases, linewidth = self.index[name]
+        dst = out[:length]
+        if length == 0:
+            return dst
+        if self._bgzf is not None or self._buf is None or len(self._buf) < offset:
+            dst[:] = self.fetch_array(name)
+            return dst
+        full = length // linebases
+        if full:
+            end_full = offset + full * linewidth
+            if end_full <= len(self._buf):
+                src = self._buf[offset:end_full].reshape(full, linewidth)[:, :linebases]
+            else:   # the file ends right after the last full line, without its newline
+                full -= 1
+                src = self._buf[offset:offset + full * linewidth].reshape(full, linewidth)[:, :linebases]
+            np.copyto(dst[:full * linebases].reshape(full, linebases), src)
+        rem = length - full * linebases
+        if rem:
+            b0 = offset + full * linewidth
+            dst[full * linebases:] = self._buf[b0:b0 + rem]
+        return dst
+
     def fetch(self, name, start=None, end=None):
         """``pysam.FastaFile.fetch`` look-alike returning ``str``."""
         return self.fetch_array(name, start, end).tobytes().decode('ascii')

@@ -6,6 +6,7 @@ arguments, return value ``(df_snv, df_insdel)``, column order, dtypes (all ``obj
 Python loop of the reference (:50-311) is replaced by one ``pavgpu_cigar_call``; this module only
 moves bytes in (FASTA -> HBM, CIGAR text -> packed ops) and formats the rows that come back.
 """
+import os
 import time
 
 import numpy as np
@@ -43,9 +44,16 @@ def _sort_order(chrom_codes, pos, end, id_of, end_is_pos_plus_1=False):
     """Permutation equal to pandas' stable ``sort_values(['#CHROM','POS','END','ID'])``. ``id_of(i)`` gives the ID of
     emission row ``i``; it is only asked for rows that tie on (chrom, pos, end)."""
     if end_is_pos_plus_1 and len(pos) and int(pos.max()) < (1 << 40) and int(chrom_codes.max()) < (1 << 22):
-        # SNV rows: END = POS + 1, so one composite key orders them; rows arrive nearly sorted (records are sorted by
-        # #CHROM, POS), which the stable merge sort exploits
-        order = np.argsort((chrom_codes << 40) | pos, kind='stable')
+        # SNV rows: END = POS + 1, so one composite key orders them. Rows arrive in (record, op) order and the records are sorted
+        # by #CHROM, POS: without overlapping records the rows are sorted already (one linear check instead of a sort)
+        key = (chrom_codes << 40) | pos
+        if bool((key[1:] >= key[:-1]).all()):
+            order = np.arange(len(key), dtype=np.int64)
+        else:
+            order = np.argsort(key, kind='stable')
+    elif len(pos) and int(pos.max()) < (1 << 40) and int(chrom_codes.max()) < (1 << 22) and \
+            bool((((chrom_codes[1:] << 40) | pos[1:]) > ((chrom_codes[:-1] << 40) | pos[:-1])).all()):
+        return np.arange(len(pos), dtype=np.int64)      # strictly increasing (#CHROM, POS): sorted, and no ties to break
     else:
         order = np.lexsort((end, pos, chrom_codes))
     if len(order) > 1:
@@ -111,6 +119,19 @@ class AlignTable:
         self.qry_id = np.array([self.tig_names[str(q)] for q in self.qry.tolist()], dtype=np.int32)
 
 
+class _Awaited:
+    """``value`` once ``futures`` are done (future-like for walk_rows). A module-level class on purpose: a class defined inside
+    the calling function would sit in a reference cycle and keep the 200 MB staging buffers alive until the cyclic GC runs."""
+
+    def __init__(self, futures, value):
+        self.futures, self.value = futures, value
+
+    def result(self):
+        for f in self.futures:
+            f.result()
+        return self.value
+
+
 def _resolve(x):
     """Inputs of walk_rows may be ``concurrent.futures.Future`` objects (FASTA read / CIGAR tokenizer running beside the uploads)."""
     return x.result() if hasattr(x, 'result') else x
@@ -171,39 +192,76 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     if df_align.shape[0] == 0:
         return _empty(SNV_COLUMNS), _empty(INSDEL_COLUMNS)
     from concurrent.futures import ThreadPoolExecutor
+    global _CALLS
     t0 = time.perf_counter()
     table = AlignTable(df_align)
     ref_fa = fasta.open_fasta(ref_fa_name)
     tig_fa = fasta.open_fasta(tig_fa_name)
-    # The contig FASTA is read and the CIGARs are tokenised beside the reference read / upload / pack (file reads, numpy
-    # copies and the C calls all release the GIL).
     sc = sidecar.find(ref_fa_name)    # packed-reference sidecar next to the FASTA (pav_b200/sidecar.py), when there is a fresh one
     ref_store, own_store = None, False
-    with ThreadPoolExecutor(max_workers=2) as pool:
-        f_tig = pool.submit(lambda: [tig_fa.fetch_array(nm) for nm in table.tig_names])
-        f_ops = pool.submit(device.parse_cigars, table.cigars)
+    # Sequences are read by a few threads (file reads, numpy copies and the C calls release the GIL) while the main thread
+    # uploads what is ready; the CIGAR tokenizer runs beside them. From the second call of a process on, the bases are read
+    # straight into pinned staging buffers of the context's pool (H2D at PCIe speed; the first call would only pay for pinning).
+    ctx = device.get_context()
+    pinned = _CALLS >= 1 if os.environ.get('PAVGPU_PINNED_STAGING') is None else os.environ['PAVGPU_PINNED_STAGING'] == '1'
+    _CALLS += 1
+
+    def read_all(fa, names):
+        """-> list of uint8 arrays in the order of ``names``, read in up to ``_READERS`` slices of about equal size."""
+        names = list(names)
+        for nm in names:
+            if str(nm) not in fa.index:
+                raise KeyError(f'sequence {str(nm)!r} not found in {fa.path}')
+        lens = [fa.length(nm) for nm in names]
+        offs = np.concatenate(([0], np.cumsum([(ln + 63) // 64 * 64 for ln in lens]))).astype(np.int64)
+        buf = device.pinned_empty(ctx, int(offs[-1])) if pinned else np.empty(int(offs[-1]), dtype=np.uint8)
+        out = [buf[offs[i]:offs[i] + lens[i]] for i in range(len(names))]
+        target, parts, cur, acc = max(int(offs[-1]) // _READERS, 1), [], [], 0
+        for i in range(len(names)):
+            cur.append(i)
+            acc += lens[i]
+            if acc >= target and len(parts) < _READERS - 1:
+                parts.append(cur)
+                cur, acc = [], 0
+        if cur:
+            parts.append(cur)
+
+        def job(idx):
+            for i in idx:
+                fa.fetch_into(names[i], out[i])
+        return out, [pool.submit(job, idx) for idx in parts]
+
+    with ThreadPoolExecutor(max_workers=2 * _READERS + 1) as pool:
+        futs = []
         try:
             if sc is not None:
                 # host arrays are views of the mapped file, the upload is the packed planes; records index the sidecar's order
                 missing = [nm for nm in table.ref_names if nm not in sc.ids]
                 if missing:
                     raise KeyError(f'sequence {missing[0]!r} not found in {sc.path}')
-                ref_arr = sc.arrays()
+                ref_arr, ref_futs = sc.arrays(), []
                 ref_id = np.array([sc.ids[nm] for nm in table.ref_names], dtype=np.int32)[table.ref_id]
                 table.ref_names, table.ref_id = {nm: i for i, nm in enumerate(sc.names)}, ref_id
-                ref_store, own_store = sidecar.reference_store(sc)
             else:
-                ref_arr = [ref_fa.fetch_array(nm) for nm in table.ref_names]
+                ref_arr, ref_futs = read_all(ref_fa, table.ref_names)
+            tig_arr, tig_futs = read_all(tig_fa, table.tig_names)
+            f_ops = pool.submit(device.parse_cigars, table.cigars)
+            futs = ref_futs + tig_futs + [f_ops]
+            if sc is not None:
+                ref_store, own_store = sidecar.reference_store(sc)
+            for f in ref_futs:
+                f.result()
             t1 = time.perf_counter()
-            snv, indel = walk_rows(table, ref_arr, f_tig, ref_store=ref_store, parsed=f_ops)
+
+            # walk_rows resolves its inputs lazily: the contigs are awaited after the reference is uploaded
+            snv, indel = walk_rows(table, ref_arr, _Awaited(tig_futs, tig_arr), ctx=ctx, ref_store=ref_store, parsed=f_ops)
         except BaseException:
-            f_tig.cancel()
-            f_ops.cancel()
+            for f in futs:
+                f.cancel()
             raise
         finally:
             if own_store:
                 ref_store.close()
-        tig_arr = f_tig.result()
     t2 = time.perf_counter()
     frames = build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
                           table.qry_id, hap, version_id)
@@ -213,21 +271,36 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
 
 
 _MALLOC_TUNED = False
+_CALLS = 0        # make_insdel_snv_calls calls in this process (pinned staging starts with the second one)
+_READERS = 3      # reader threads per FASTA
 
 
 def _tune_malloc():
-    """Large tables create tens of millions of small objects in a fresh job process; without this glibc grows the heap
-    in 128 KiB steps and trims it back after every temporary (measured: first call 2.0 s -> 1.1 s for 2 M rows)."""
+    """Large tables create millions of small objects and a few dozen multi-MB pointer arrays per call; by default every byte of
+    them is freshly mapped memory (first-touch page faults) that goes straight back to the OS when the result dies:
+      * glibc: keep freed heap (no trim), grow it in big steps, and serve arrays up to 32 MiB from the heap instead of mmap
+        (measured: first call 2.0 s -> 1.1 s for 2 M rows before the C formatter existed);
+      * pymalloc: recycle released arenas (``_pyrows.keep_arenas``) instead of unmapping and re-faulting them every call.
+    Process-wide settings, applied on the first large result; ``PAVGPU_TUNE_ALLOC=0`` leaves the allocators alone."""
     global _MALLOC_TUNED
     if _MALLOC_TUNED:
         return
     _MALLOC_TUNED = True
+    import os
+    if os.environ.get('PAVGPU_TUNE_ALLOC', '1') == '0':
+        return
     try:
         import ctypes
         libc = ctypes.CDLL('libc.so.6')
         libc.mallopt(-1, 2 ** 31 - 1)      # M_TRIM_THRESHOLD: keep freed heap
         libc.mallopt(-2, 256 << 20)        # M_TOP_PAD: grow the heap 256 MiB at a time
+        libc.mallopt(-3, 32 << 20)         # M_MMAP_THRESHOLD: column arrays (8 B x rows) come from the heap and are reused
     except Exception:  # noqa: BLE001  (non-glibc platforms)
+        pass
+    try:
+        from .. import _pyrows
+        _pyrows.keep_arenas(int(os.environ.get('PAVGPU_ARENA_CACHE_MB', '2048')))
+    except Exception:  # noqa: BLE001
         pass
 
 
@@ -287,22 +360,30 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
     ascii_names = all(x.isascii() for x in chrom_l) and all(x.isascii() for x in qry_l)
 
     # ------------------------------------------------------------------ SNV rows (cigarcall.py:98-135)
+    seqs = list(ref_arr) + list(tig_arr)
+    comp = fasta.COMPLEMENT.tobytes()
     if len(snv):
         n = len(snv)
         snv = np.ascontiguousarray(snv)
         rec = snv['rec']
         pos = snv['pos_ref'].astype(np.int64)
         qp = snv['qry_pos']
-        ref_b = np.empty(n, dtype=np.uint8)
-        alt_b = np.empty(n, dtype=np.uint8)
-        bounds = np.searchsorted(rec, np.arange(n_rec + 1))
-        for r in np.flatnonzero(np.diff(bounds)).tolist():
-            a, b = bounds[r], bounds[r + 1]
-            ref_b[a:b] = ref_arr[ref_id[r]][pos[a:b]]
-            t = tig_arr[qry_id[r]][qp[a:b]]
-            alt_b[a:b] = fasta.COMPLEMENT[t] if rev[r] else t
+
+        def bases_of(idx):
+            """(REF, ALT) bytes of emission rows ``idx`` (whole table for ID versioning, tie groups of the sort otherwise)."""
+            ref_b = np.empty(len(idx), dtype=np.uint8)
+            alt_b = np.empty(len(idx), dtype=np.uint8)
+            r_of = rec[idx]
+            for r in np.unique(r_of).tolist():
+                m = r_of == r
+                ref_b[m] = ref_arr[ref_id[r]][pos[idx][m]]
+                t = tig_arr[qry_id[r]][qp[idx][m]]
+                alt_b[m] = fasta.COMPLEMENT[t] if rev[r] else t
+            return ref_b, alt_b
+
         ids = None
         if version_id or not ascii_names:
+            ref_b, alt_b = bases_of(np.arange(n))
             ids = _pyrows.format(n, [('l', chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
                                      ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
             if version_id:
@@ -310,11 +391,12 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
             id_of = ids.__getitem__
         else:
             def id_of(i):
-                return f'{chrom_l[rec[i]]}-{pos[i] + 1}-SNV-{chr(fasta.UPPER[ref_b[i]])}{chr(fasta.UPPER[alt_b[i]])}'
+                rb, ab = bases_of(np.array([i]))
+                return f'{chrom_l[rec[i]]}-{pos[i] + 1}-SNV-{chr(fasta.UPPER[rb[0]])}{chr(fasta.UPPER[ab[0]])}'
         order = _sort_order(chrom_code_rec[rec], pos, pos + 1, id_of, end_is_pos_plus_1=True)
         if ascii_names:
-            cols = _pyrows.snv_frame(snv.view(np.uint8), order, ref_b, alt_b, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs,
-                                     ('SNV', 1, hap, 0, CALL_SOURCE))
+            cols = _pyrows.snv_frame(snv.view(np.uint8), order, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs, ref_id32, qry_id32, rev8,
+                                     seqs, len(ref_arr), comp, ('SNV', 1, hap, 0, CALL_SOURCE))
             df_snv = _frame(dict(zip(SNV_COLUMNS, cols)), SNV_COLUMNS, order)
         else:   # names outside ASCII: generic formatter
             rec64, pos_o, qp1 = rec[order].astype(np.int64), pos[order], qp[order].astype(np.int64) + 1
@@ -352,7 +434,7 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
         order = _sort_order(chrom_code_rec[rec], pos, end, id_of)
         if ascii_names:
             cols = _pyrows.indel_frame(indel.view(np.uint8), order, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs, ref_id32, qry_id32, rev8,
-                                       list(ref_arr) + list(tig_arr), len(ref_arr), fasta.COMPLEMENT.tobytes(), ('INS', 'DEL', hap, 0, CALL_SOURCE))
+                                       seqs, len(ref_arr), comp, ('INS', 'DEL', hap, 0, CALL_SOURCE))
             df_insdel = _frame(dict(zip(INSDEL_COLUMNS, cols)), INSDEL_COLUMNS, order)
         else:
             indel_o = indel[order]
