@@ -5,11 +5,12 @@ spans, insert INS sequences at their *left-shifted* positions) must give back th
 what the CIGARs say; rows must come in emission order. Path B: INDEX strictly increasing inside the window, states in
 range, the dominant state is the planted orientation.
 
-Host-side numpy only; used by tests/ and profiles/run_c3.py. Nothing here is on the product path.
+TEST INFRASTRUCTURE (like the rest of oracle/): host-side numpy, used by tests/ and the full-size drivers under profiles/.
+Nothing under pav_b200/ imports it.
 """
 import numpy as np
 
-from . import fasta
+from pav_b200 import fasta
 
 OP_I, OP_D, OP_X, OP_H, OP_S = 1, 2, 8, 5, 4
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE configs[2] at full size on one B200: 2 haplotypes (h1/h2) of 10 Mbp contigs against a 3.1 Gbp hg38-shaped
 reference (24 chromosomes, 50 % soft-masked, 5 % N), CIGAR walk + k=31 inversion density scan on the flagged windows
-(one 50 kbp window per 300 kbp of contig), with the size-independent parity properties of pav_b200/checks.py and an
+(one 50 kbp window per 300 kbp of contig), with the size-independent parity properties of oracle/properties.py and an
 oracle comparison on a sample of records / windows.
 
     python profiles/run_c3.py [--scale 1.0] [--regime human|stress] [--out profiles/rNN_c3.json]
@@ -20,7 +20,8 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-from pav_b200 import _capi, checks, device, synth  # noqa: E402
+from oracle import properties as checks  # noqa: E402
+from pav_b200 import _capi, device, synth  # noqa: E402
 from pav_b200.pavlib import density  # noqa: E402
 
 

@@ -16,7 +16,8 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-from pav_b200 import _capi, checks, device, synth  # noqa: E402
+from oracle import properties as checks  # noqa: E402
+from pav_b200 import _capi, device, synth  # noqa: E402
 from pav_b200.pavlib import density  # noqa: E402
 
 

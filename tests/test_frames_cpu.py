@@ -101,3 +101,24 @@ def test_frames_non_ascii_names(tmp_path):
                                             table.qry_id, 'h1', True)
     o_snv, o_indel = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
     assert tsv(g_snv) == tsv(o_snv) and tsv(g_indel) == tsv(o_indel)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_sort_order_equals_pandas(seed):
+    """_sort_order (with its already-sorted shortcuts) == pandas' stable sort_values(['#CHROM', 'POS', 'END', 'ID'])."""
+    rng = np.random.default_rng(seed)
+    n = 400
+    chrom_codes = np.sort(rng.integers(0, 3, n)).astype(np.int64)
+    pos = rng.integers(0, 60, n).astype(np.int64)
+    if seed % 2 == 0:      # rows that arrive sorted by (#CHROM, POS), with ties
+        o = np.lexsort((pos, chrom_codes))
+        chrom_codes, pos = chrom_codes[o], pos[o]
+    if seed == 4:          # strictly increasing: the tie-free shortcut
+        pos = np.arange(n, dtype=np.int64)
+    ids = np.array([f'id{int(x)}' for x in rng.integers(0, 50, n)], dtype=object)
+    for snv_like in (True, False):
+        end = pos + 1 if snv_like else pos + rng.integers(1, 4, n)
+        got = cigarcall._sort_order(chrom_codes, pos, end, ids.__getitem__, end_is_pos_plus_1=snv_like)
+        df = pd.DataFrame({'#CHROM': chrom_codes, 'POS': pos, 'END': end, 'ID': ids})
+        exp = df.sort_values(['#CHROM', 'POS', 'END', 'ID']).index.to_numpy()
+        assert (got == exp).all()

@@ -1,6 +1,6 @@
 """BASELINE configs[2] shape (2 haplotypes vs an hg38-shaped reference: 24 chromosomes of unequal length, soft-masked runs,
 N blocks; CIGAR walk + density scan of the flagged windows) at 1/250 scale through the same driver that runs it at full size
-(profiles/run_c3.py, result in profiles/): size-independent properties over every record (pav_b200/checks.py: row counts,
+(profiles/run_c3.py, result in profiles/): size-independent properties over every record (oracle/properties.py: row counts,
 emission order, REF != ALT, decode(reference, rows) == contig) + oracle equality on sampled records and one window."""
 import importlib.util
 import os
