@@ -214,7 +214,14 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
                 raise KeyError(f'sequence {str(nm)!r} not found in {fa.path}')
         lens = [fa.length(nm) for nm in names]
         offs = np.concatenate(([0], np.cumsum([(ln + 63) // 64 * 64 for ln in lens]))).astype(np.int64)
-        buf = device.pinned_empty(ctx, int(offs[-1])) if pinned else np.empty(int(offs[-1]), dtype=np.uint8)
+        buf = None
+        if pinned and int(offs[-1]) <= _PINNED_STAGING_MAX:
+            try:
+                buf = device.pinned_empty(ctx, int(offs[-1]))
+            except RuntimeError:   # no pinned memory to be had: ordinary memory works, only slower
+                buf = None
+        if buf is None:
+            buf = np.empty(int(offs[-1]), dtype=np.uint8)
         out = [buf[offs[i]:offs[i] + lens[i]] for i in range(len(names))]
         target, parts, cur, acc = max(int(offs[-1]) // _READERS, 1), [], [], 0
         for i in range(len(names)):
@@ -273,6 +280,7 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
 _MALLOC_TUNED = False
 _CALLS = 0        # make_insdel_snv_calls calls in this process (pinned staging starts with the second one)
 _READERS = 3      # reader threads per FASTA
+_PINNED_STAGING_MAX = int(os.environ.get('PAVGPU_PINNED_STAGING_MAX_MB', '1024')) << 20   # larger inputs stay in ordinary memory
 
 
 def _tune_malloc():
