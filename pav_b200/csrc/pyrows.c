@@ -551,6 +551,210 @@ done:
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * TSV writers: the text `DataFrame.to_csv(sep='\t', index=False)` would produce for the call tables (plus a FILTER
+ * column), straight from the device rows -- for callers that write the table to a file at once, as `rule call_cigar` does
+ * (rules/call.snakefile:813-846), without creating a single per-row Python object. No header line; fields are written
+ * unquoted (the caller falls back to pandas when a name would need quoting).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { char *p; size_t len, cap; } obuf_t;
+
+static int obuf_reserve(obuf_t *b, size_t more)
+{
+    if (b->len + more <= b->cap) return 0;
+    size_t cap = b->cap ? b->cap : (1u << 20);
+    while (cap < b->len + more) cap += cap / 2 + (1u << 20);
+    char *q = (char *)realloc(b->p, cap);
+    if (!q) { PyErr_NoMemory(); return -1; }
+    b->p = q; b->cap = cap;
+    return 0;
+}
+
+static inline void ob_mem(obuf_t *b, const char *s, size_t n) { memcpy(b->p + b->len, s, n); b->len += n; }
+static inline void ob_ch(obuf_t *b, char c) { b->p[b->len++] = c; }
+static inline void ob_i64(obuf_t *b, int64_t v) { int nd = ndig_i64(v); put_i64_fwd(b->p + b->len, v, nd); b->len += (size_t)nd; }
+
+static size_t strtab_max(const strtab_t *t)
+{
+    size_t m = 0;
+    for (Py_ssize_t i = 0; i < t->n; i++) if ((size_t)t->len[i] > m) m = (size_t)t->len[i];
+    return m;
+}
+
+/* snv_tsv(rows, order, ids|None, chrom_strs, qry_strs, strand_strs, ai_strs, ref_id, qry_id, rev, seqs, n_ref, comp, hap, source, pass)
+ *   as snv_frame, with per-record *strings* for every per-record column, `pass`: uint8 per emission row (1 = PASS, 0 = TRIM),
+ *   or None for no FILTER column -> bytes */
+static PyObject *py_snv_tsv(PyObject *self, PyObject *args)
+{
+    Py_buffer rows, order, ref_id, qry_id, rev, comp;
+    PyObject *ids, *chrom_strs, *qry_strs, *strand_strs, *ai_strs, *seqs, *pass_obj;
+    const char *hap, *source; Py_ssize_t hap_n, source_n, n_ref;
+    if (!PyArg_ParseTuple(args, "y*y*OOOOOy*y*y*O!ny*s#s#O", &rows, &order, &ids, &chrom_strs, &qry_strs, &strand_strs, &ai_strs,
+                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &hap, &hap_n, &source, &source_n, &pass_obj))
+        return NULL;
+    PyObject *result = NULL;
+    strtab_t tc = {0}, tq = {0}, ts = {0}, ta = {0};
+    PyObject **id_src = NULL;
+    Py_buffer pass; int has_pass = 0;
+    obuf_t ob = {0};
+    Py_ssize_t n = order.len / 8, n_rows = rows.len / (Py_ssize_t)sizeof(snv_row_t), nd_seq = PyList_GET_SIZE(seqs), got = 0;
+    Py_buffer *bufs = (Py_buffer *)PyMem_Calloc((size_t)nd_seq + 1, sizeof(Py_buffer));
+    if (!bufs) { PyErr_NoMemory(); goto done; }
+    if (pass_obj != Py_None) { if (PyObject_GetBuffer(pass_obj, &pass, PyBUF_SIMPLE) < 0) goto done; has_pass = 1; }
+    if (n > n_rows || comp.len < 256 || (has_pass && pass.len < n_rows)) { PyErr_SetString(PyExc_ValueError, "snv_tsv: buffer sizes disagree"); goto done; }
+    if (strtab_load(&tc, chrom_strs, "chrom_strs") < 0 || strtab_load(&tq, qry_strs, "qry_strs") < 0 || strtab_load(&ts, strand_strs, "strand_strs") < 0 ||
+        strtab_load(&ta, ai_strs, "ai_strs") < 0) goto done;
+    Py_ssize_t n_rec = tc.n;
+    if (tq.n < n_rec || ts.n < n_rec || ta.n < n_rec || ref_id.len < n_rec * 4 || qry_id.len < n_rec * 4 || rev.len < n_rec) {
+        PyErr_SetString(PyExc_ValueError, "snv_tsv: per-record arrays disagree"); goto done;
+    }
+    if (ids != Py_None) {
+        if (!PyArray_Check(ids) || PyArray_TYPE((PyArrayObject *)ids) != NPY_OBJECT || PyArray_NDIM((PyArrayObject *)ids) != 1 ||
+            PyArray_DIM((PyArrayObject *)ids, 0) < n_rows || !PyArray_IS_C_CONTIGUOUS((PyArrayObject *)ids)) {
+            PyErr_SetString(PyExc_TypeError, "snv_tsv: ids must be a contiguous 1-D object array with one entry per row"); goto done;
+        }
+        id_src = (PyObject **)PyArray_DATA((PyArrayObject *)ids);
+    }
+    for (; got < nd_seq; got++)
+        if (PyObject_GetBuffer(PyList_GET_ITEM(seqs, got), &bufs[got], PyBUF_SIMPLE) < 0) goto done;
+    {
+        const snv_row_t *R = (const snv_row_t *)rows.buf;
+        const int64_t *ord = (const int64_t *)order.buf;
+        const int32_t *rid = (const int32_t *)ref_id.buf, *qid = (const int32_t *)qry_id.buf;
+        const uint8_t *rv = (const uint8_t *)rev.buf, *ct = (const uint8_t *)comp.buf;
+        const size_t fixed = 2 * strtab_max(&tc) + strtab_max(&tq) + strtab_max(&ts) + strtab_max(&ta) + (size_t)hap_n + (size_t)source_n + 160;
+        for (Py_ssize_t k = 0; k < n; k++) {
+            int64_t i = ord[k];
+            if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "snv_tsv: order entry out of range"); goto done; }
+            const snv_row_t r = R[i];
+            if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "snv_tsv: record index out of range"); goto done; }
+            const Py_ssize_t wr = rid[r.rec], wq = n_ref + (Py_ssize_t)qid[r.rec];
+            if (wr < 0 || wr >= n_ref || wq < n_ref || wq >= nd_seq || r.pos_ref < 0 || r.pos_ref >= bufs[wr].len || r.qry_pos < 0 || r.qry_pos >= bufs[wq].len) {
+                PyErr_SetString(PyExc_IndexError, "snv_tsv: position outside its sequence"); goto done;
+            }
+            const unsigned rb = ((const uint8_t *)bufs[wr].buf)[r.pos_ref];
+            unsigned ab = ((const uint8_t *)bufs[wq].buf)[r.qry_pos];
+            if (rv[r.rec]) ab = ct[ab];
+            size_t need = fixed;
+            const char *idp = NULL; Py_ssize_t idn = 0;
+            if (id_src) { idp = PyUnicode_AsUTF8AndSize(id_src[i], &idn); if (!idp) goto done; need += (size_t)idn; }
+            if (obuf_reserve(&ob, need) < 0) goto done;
+            const int64_t p1 = (int64_t)r.pos_ref + 1, q1 = (int64_t)r.qry_pos + 1;
+            ob_mem(&ob, tc.s[r.rec], (size_t)tc.len[r.rec]); ob_ch(&ob, '\t');
+            ob_i64(&ob, r.pos_ref); ob_ch(&ob, '\t'); ob_i64(&ob, p1); ob_ch(&ob, '\t');
+            if (idp) ob_mem(&ob, idp, (size_t)idn);
+            else {
+                ob_mem(&ob, tc.s[r.rec], (size_t)tc.len[r.rec]); ob_ch(&ob, '-'); ob_i64(&ob, p1); ob_mem(&ob, "-SNV-", 5);
+                ob_ch(&ob, (char)((rb >= 'a' && rb <= 'z') ? rb - 32 : rb)); ob_ch(&ob, (char)((ab >= 'a' && ab <= 'z') ? ab - 32 : ab));
+            }
+            ob_mem(&ob, "\tSNV\t1\t", 7); ob_ch(&ob, (char)rb); ob_ch(&ob, '\t'); ob_ch(&ob, (char)ab); ob_ch(&ob, '\t');
+            ob_mem(&ob, hap, (size_t)hap_n); ob_ch(&ob, '\t');
+            ob_mem(&ob, tq.s[r.rec], (size_t)tq.len[r.rec]); ob_ch(&ob, ':'); ob_i64(&ob, q1); ob_ch(&ob, '-'); ob_i64(&ob, q1); ob_ch(&ob, '\t');
+            ob_mem(&ob, ts.s[r.rec], (size_t)ts.len[r.rec]); ob_mem(&ob, "\t0\t", 3);
+            ob_mem(&ob, ta.s[r.rec], (size_t)ta.len[r.rec]); ob_ch(&ob, '\t');
+            ob_mem(&ob, source, (size_t)source_n);
+            if (has_pass) ob_mem(&ob, ((const uint8_t *)pass.buf)[i] ? "\tPASS" : "\tTRIM", 5);
+            ob_ch(&ob, '\n');
+        }
+    }
+    result = PyBytes_FromStringAndSize(ob.p ? ob.p : "", (Py_ssize_t)ob.len);
+done:
+    free(ob.p);
+    if (has_pass) PyBuffer_Release(&pass);
+    if (bufs) { for (Py_ssize_t j = 0; j < got; j++) PyBuffer_Release(&bufs[j]); PyMem_Free(bufs); }
+    strtab_free(&tc); strtab_free(&tq); strtab_free(&ts); strtab_free(&ta);
+    PyBuffer_Release(&rows); PyBuffer_Release(&order); PyBuffer_Release(&ref_id); PyBuffer_Release(&qry_id); PyBuffer_Release(&rev); PyBuffer_Release(&comp);
+    return result;
+}
+
+/* indel_tsv(rows, order, ids|None, chrom_strs, qry_strs, strand_strs, ai_strs, ref_id, qry_id, rev, seqs, n_ref, comp, hap, source, pass) -> bytes */
+static PyObject *py_indel_tsv(PyObject *self, PyObject *args)
+{
+    Py_buffer rows, order, ref_id, qry_id, rev, comp;
+    PyObject *ids, *chrom_strs, *qry_strs, *strand_strs, *ai_strs, *seqs, *pass_obj;
+    const char *hap, *source; Py_ssize_t hap_n, source_n, n_ref;
+    if (!PyArg_ParseTuple(args, "y*y*OOOOOy*y*y*O!ny*s#s#O", &rows, &order, &ids, &chrom_strs, &qry_strs, &strand_strs, &ai_strs,
+                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &hap, &hap_n, &source, &source_n, &pass_obj))
+        return NULL;
+    PyObject *result = NULL;
+    strtab_t tc = {0}, tq = {0}, ts = {0}, ta = {0};
+    PyObject **id_src = NULL;
+    Py_buffer pass; int has_pass = 0;
+    obuf_t ob = {0};
+    Py_ssize_t n = order.len / 8, n_rows = rows.len / (Py_ssize_t)sizeof(indel_row_t), nd_seq = PyList_GET_SIZE(seqs), got = 0;
+    Py_buffer *bufs = (Py_buffer *)PyMem_Calloc((size_t)nd_seq + 1, sizeof(Py_buffer));
+    if (!bufs) { PyErr_NoMemory(); goto done; }
+    if (pass_obj != Py_None) { if (PyObject_GetBuffer(pass_obj, &pass, PyBUF_SIMPLE) < 0) goto done; has_pass = 1; }
+    if (n > n_rows || comp.len < 256 || (has_pass && pass.len < n_rows)) { PyErr_SetString(PyExc_ValueError, "indel_tsv: buffer sizes disagree"); goto done; }
+    if (strtab_load(&tc, chrom_strs, "chrom_strs") < 0 || strtab_load(&tq, qry_strs, "qry_strs") < 0 || strtab_load(&ts, strand_strs, "strand_strs") < 0 ||
+        strtab_load(&ta, ai_strs, "ai_strs") < 0) goto done;
+    Py_ssize_t n_rec = tc.n;
+    if (tq.n < n_rec || ts.n < n_rec || ta.n < n_rec || ref_id.len < n_rec * 4 || qry_id.len < n_rec * 4 || rev.len < n_rec) {
+        PyErr_SetString(PyExc_ValueError, "indel_tsv: per-record arrays disagree"); goto done;
+    }
+    if (ids != Py_None) {
+        if (!PyArray_Check(ids) || PyArray_TYPE((PyArrayObject *)ids) != NPY_OBJECT || PyArray_NDIM((PyArrayObject *)ids) != 1 ||
+            PyArray_DIM((PyArrayObject *)ids, 0) < n_rows || !PyArray_IS_C_CONTIGUOUS((PyArrayObject *)ids)) {
+            PyErr_SetString(PyExc_TypeError, "indel_tsv: ids must be a contiguous 1-D object array with one entry per row"); goto done;
+        }
+        id_src = (PyObject **)PyArray_DATA((PyArrayObject *)ids);
+    }
+    for (; got < nd_seq; got++)
+        if (PyObject_GetBuffer(PyList_GET_ITEM(seqs, got), &bufs[got], PyBUF_SIMPLE) < 0) goto done;
+    {
+        const indel_row_t *R = (const indel_row_t *)rows.buf;
+        const int64_t *ord = (const int64_t *)order.buf;
+        const int32_t *rid = (const int32_t *)ref_id.buf, *qid = (const int32_t *)qry_id.buf;
+        const uint8_t *rv = (const uint8_t *)rev.buf, *ct = (const uint8_t *)comp.buf;
+        const size_t fixed = 2 * strtab_max(&tc) + strtab_max(&tq) + strtab_max(&ts) + strtab_max(&ta) + (size_t)hap_n + (size_t)source_n + 400;
+        for (Py_ssize_t k = 0; k < n; k++) {
+            int64_t i = ord[k];
+            if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "indel_tsv: order entry out of range"); goto done; }
+            const indel_row_t r = R[i];
+            if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "indel_tsv: record index out of range"); goto done; }
+            const int is_del = r.svtype == 1;
+            const Py_ssize_t w = is_del ? (Py_ssize_t)rid[r.rec] : n_ref + (Py_ssize_t)qid[r.rec];
+            const int64_t s0 = is_del ? r.pos : r.qry_pos, l = r.svlen;
+            if (w < 0 || w >= nd_seq || s0 < 0 || l < 0 || s0 + l > bufs[w].len) { PyErr_SetString(PyExc_IndexError, "indel_tsv: SEQ range outside sequence"); goto done; }
+            size_t need = fixed + (size_t)l;
+            const char *idp = NULL; Py_ssize_t idn = 0;
+            if (id_src) { idp = PyUnicode_AsUTF8AndSize(id_src[i], &idn); if (!idp) goto done; need += (size_t)idn; }
+            if (obuf_reserve(&ob, need) < 0) goto done;
+            const int64_t p1 = (int64_t)r.pos + 1, q1 = (int64_t)r.qry_pos + 1, q2 = is_del ? q1 : (int64_t)r.qry_end;
+            ob_mem(&ob, tc.s[r.rec], (size_t)tc.len[r.rec]); ob_ch(&ob, '\t');
+            ob_i64(&ob, r.pos); ob_ch(&ob, '\t'); ob_i64(&ob, r.end); ob_ch(&ob, '\t');
+            if (idp) ob_mem(&ob, idp, (size_t)idn);
+            else { ob_mem(&ob, tc.s[r.rec], (size_t)tc.len[r.rec]); ob_ch(&ob, '-'); ob_i64(&ob, p1); ob_mem(&ob, is_del ? "-DEL-" : "-INS-", 5); ob_i64(&ob, r.svlen); }
+            ob_mem(&ob, is_del ? "\tDEL\t" : "\tINS\t", 5); ob_i64(&ob, r.svlen); ob_ch(&ob, '\t');
+            ob_mem(&ob, hap, (size_t)hap_n); ob_ch(&ob, '\t');
+            ob_mem(&ob, tq.s[r.rec], (size_t)tq.len[r.rec]); ob_ch(&ob, ':'); ob_i64(&ob, q1); ob_ch(&ob, '-'); ob_i64(&ob, q2); ob_ch(&ob, '\t');
+            ob_mem(&ob, ts.s[r.rec], (size_t)ts.len[r.rec]); ob_mem(&ob, "\t0\t", 3);
+            ob_mem(&ob, ta.s[r.rec], (size_t)ta.len[r.rec]); ob_ch(&ob, '\t');
+            ob_i64(&ob, r.left_shift); ob_ch(&ob, '\t');
+            ob_i64(&ob, r.hom_ref_l); ob_ch(&ob, ','); ob_i64(&ob, r.hom_ref_r); ob_ch(&ob, '\t');
+            ob_i64(&ob, r.hom_tig_l); ob_ch(&ob, ','); ob_i64(&ob, r.hom_tig_r); ob_ch(&ob, '\t');
+            ob_mem(&ob, source, (size_t)source_n); ob_ch(&ob, '\t');
+            {
+                const uint8_t *src = (const uint8_t *)bufs[w].buf + s0;
+                char *d = ob.p + ob.len;
+                if (!is_del && rv[r.rec]) for (int64_t j = 0; j < l; j++) d[j] = (char)ct[src[l - 1 - j]];
+                else memcpy(d, src, (size_t)l);
+                ob.len += (size_t)l;
+            }
+            if (has_pass) ob_mem(&ob, ((const uint8_t *)pass.buf)[i] ? "\tPASS" : "\tTRIM", 5);
+            ob_ch(&ob, '\n');
+        }
+    }
+    result = PyBytes_FromStringAndSize(ob.p ? ob.p : "", (Py_ssize_t)ob.len);
+done:
+    free(ob.p);
+    if (has_pass) PyBuffer_Release(&pass);
+    if (bufs) { for (Py_ssize_t j = 0; j < got; j++) PyBuffer_Release(&bufs[j]); PyMem_Free(bufs); }
+    strtab_free(&tc); strtab_free(&tq); strtab_free(&ts); strtab_free(&ta);
+    PyBuffer_Release(&rows); PyBuffer_Release(&order); PyBuffer_Release(&ref_id); PyBuffer_Release(&qry_id); PyBuffer_Release(&rev); PyBuffer_Release(&comp);
+    return result;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Arena recycling. A 2 M-row result is ~8 M small str / int objects = several hundred MB of pymalloc arenas. CPython maps
  * every arena fresh (mmap, 1 MiB) and unmaps it as soon as it is empty, so each call pays the first-touch page faults
  * for all of it again (measured: ~0.4 ns per byte, a third of the frame-building time). keep_arenas(max_mb) installs an
@@ -600,6 +804,8 @@ static PyMethodDef methods[] = {
     {"format", py_format, METH_VARARGS, "format(n, parts) -> list of str"},
     {"ints", py_ints, METH_O, "ints(int64 buffer) -> list of int"},
     {"slices", py_slices, METH_VARARGS, "slices(data list, which, start, length, rc, comp) -> list of str"},
+    {"snv_tsv", py_snv_tsv, METH_VARARGS, "TSV text of df_snv (+ FILTER) without building the frame"},
+    {"indel_tsv", py_indel_tsv, METH_VARARGS, "TSV text of df_insdel (+ FILTER) without building the frame"},
     {"keep_arenas", py_keep_arenas, METH_O, "keep_arenas(max_mb): recycle up to max_mb of released pymalloc arenas"},
     {"snv_frame", py_snv_frame, METH_VARARGS, "all 14 columns of df_snv in final row order"},
     {"indel_frame", py_indel_frame, METH_VARARGS, "all 16 columns of df_insdel in final row order"},

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _capi
-from ._capi import c_i32, c_i64, c_vp
+from ._capi import c_i64, c_vp
 
 _CONTEXTS = {}
 

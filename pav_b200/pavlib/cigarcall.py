@@ -191,6 +191,20 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     global last_phase_seconds
     if df_align.shape[0] == 0:
         return _empty(SNV_COLUMNS), _empty(INSDEL_COLUMNS)
+    table, snv, indel, ref_arr, tig_arr, phases = call_rows(df_align, ref_fa_name, tig_fa_name)
+    t2 = time.perf_counter()
+    frames = build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
+                          table.qry_id, hap, version_id)
+    phases['frames'] = time.perf_counter() - t2
+    last_phase_seconds = phases
+    return frames
+
+
+def call_rows(df_align, ref_fa_name, tig_fa_name):
+    """First half of ``make_insdel_snv_calls`` (``df_align`` not empty): read the sequences, run the walk on the GPU.
+
+    Returns ``(table, snv rows, indel rows, ref_arr, tig_arr, phase seconds)``; ``ref_arr`` / ``tig_arr`` are indexed by
+    ``table.ref_id`` / ``table.qry_id`` (with a sidecar ``ref_arr`` holds every sequence of the reference, in file order)."""
     from concurrent.futures import ThreadPoolExecutor
     global _CALLS
     t0 = time.perf_counter()
@@ -270,11 +284,7 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
             if own_store:
                 ref_store.close()
     t2 = time.perf_counter()
-    frames = build_frames(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id,
-                          table.qry_id, hap, version_id)
-    last_phase_seconds = {'fasta_reference': t1 - t0, 'device_walk_incl_contig_read_h2d_d2h': t2 - t1, 'frames': time.perf_counter() - t2,
-                          'sidecar': sc is not None}
-    return frames
+    return table, snv, indel, ref_arr, tig_arr, {'fasta_reference': t1 - t0, 'device_walk_incl_contig_read_h2d_d2h': t2 - t1, 'sidecar': sc is not None}
 
 
 _MALLOC_TUNED = False
@@ -353,19 +363,124 @@ def build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref
             gc.enable()
 
 
+def tables_tsv(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id, pass_snv=None, pass_indel=None):
+    """The two call tables as TSV text (bytes, header included) exactly as ``DataFrame.to_csv(sep='\t', index=False)`` writes the
+    frames of ``build_frames`` -- without building them (no per-row Python objects). ``pass_snv`` / ``pass_indel``: uint8 per
+    emission row, 1 = PASS / 0 = TRIM, adds the FILTER column of ``rule call_cigar``. Returns ``None`` when a name needs CSV
+    quoting or is not ASCII (the caller then goes through the frames)."""
+    from .. import _pyrows
+    R = _Records(chrom, qry, rev, align_index, ref_id, qry_id)
+    ai_l = [f'{x}' for x in R.ai_objs]
+    special = ('\t', '\n', '\r', '"')
+    if not R.ascii_names or not hap.isascii() or any(ch in x for x in R.chrom_l + R.qry_l + ai_l + [hap] for ch in special) or \
+            not all(x.isascii() for x in ai_l) or (len(indel) and int(indel['svlen'].min()) <= 0):
+        return None
+    seqs = list(ref_arr) + list(tig_arr)
+    comp = fasta.COMPLEMENT.tobytes()
+    out = []
+    for rows, cols, passes, is_snv in ((snv, SNV_COLUMNS, pass_snv, True), (indel, INSDEL_COLUMNS, pass_indel, False)):
+        header = ('\t'.join(cols + (['FILTER'] if passes is not None else [])) + '\n').encode()
+        if len(rows) == 0:
+            out.append(header)
+            continue
+        rows = np.ascontiguousarray(rows)
+        if is_snv:
+            ids, order, _ = _snv_ids_order(rows, R, ref_arr, tig_arr, version_id)
+            fn = _pyrows.snv_tsv
+        else:
+            ids, order = _indel_ids_order(rows, R, version_id)
+            fn = _pyrows.indel_tsv
+        if ids is not None and any(ch in x for x in ids.tolist() for ch in special):
+            return None
+        body = fn(rows.view(np.uint8), order, ids, R.chrom_l, R.qry_l, R.strand_objs, ai_l, R.ref_id32, R.qry_id32, R.rev8, seqs, len(ref_arr), comp,
+                  hap, CALL_SOURCE, None if passes is None else np.ascontiguousarray(passes, dtype=np.uint8))
+        out.append(header + body)
+    return out[0], out[1]
+
+
+class _Records:
+    """Per-record columns in the forms the formatters want (objects for frame cells, ASCII strings for text)."""
+
+    def __init__(self, chrom, qry, rev, align_index, ref_id, qry_id):
+        self.n_rec = len(chrom)
+        self.chrom, self.align_index = chrom, align_index
+        self.chrom_objs, self.ai_objs = chrom.tolist(), align_index.tolist()
+        self.chrom_l = [f'{c}' for c in self.chrom_objs]
+        self.qry_l = [f'{q}' for q in qry.tolist()]
+        chrom_rank = {c: i for i, c in enumerate(sorted(set(self.chrom_l)))}
+        self.chrom_code_rec = np.array([chrom_rank[c] for c in self.chrom_l], dtype=np.int64)
+        self.strand_objs = ['-' if r else '+' for r in rev.tolist()]
+        self.rev, self.ref_id, self.qry_id = rev, ref_id, qry_id
+        self.ref_id32 = np.ascontiguousarray(ref_id, dtype=np.int32)
+        self.qry_id32 = np.ascontiguousarray(qry_id, dtype=np.int32)
+        self.rev8 = np.ascontiguousarray(rev, dtype=np.uint8)
+        self.ascii_names = all(x.isascii() for x in self.chrom_l) and all(x.isascii() for x in self.qry_l)
+
+
+def _snv_ids_order(snv, R, ref_arr, tig_arr, version_id):
+    """``(ids in emission order or None, final row order, bases_of)`` for the SNV rows: IDs are only materialised when they are
+    versioned (or names are not ASCII); otherwise the sort asks for the ID of a row only inside tie groups."""
+    from .. import _pyrows
+    n = len(snv)
+    rec = snv['rec']
+    pos = snv['pos_ref'].astype(np.int64)
+    qp = snv['qry_pos']
+
+    def bases_of(idx):
+        """(REF, ALT) bytes of emission rows ``idx`` (whole table for ID versioning, tie groups of the sort otherwise)."""
+        ref_b = np.empty(len(idx), dtype=np.uint8)
+        alt_b = np.empty(len(idx), dtype=np.uint8)
+        r_of = rec[idx]
+        for r in np.unique(r_of).tolist():
+            m = r_of == r
+            ref_b[m] = ref_arr[R.ref_id[r]][pos[idx][m]]
+            t = tig_arr[R.qry_id[r]][qp[idx][m]]
+            alt_b[m] = fasta.COMPLEMENT[t] if R.rev[r] else t
+        return ref_b, alt_b
+
+    ids = None
+    if version_id or not R.ascii_names:
+        ref_b, alt_b = bases_of(np.arange(n))
+        ids = _pyrows.format(n, [('l', R.chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
+                                 ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
+        if version_id:
+            ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
+        id_of = ids.__getitem__
+    else:
+        def id_of(i):
+            rb, ab = bases_of(np.array([i]))
+            return f'{R.chrom_l[rec[i]]}-{pos[i] + 1}-SNV-{chr(fasta.UPPER[rb[0]])}{chr(fasta.UPPER[ab[0]])}'
+    order = _sort_order(R.chrom_code_rec[rec], pos, pos + 1, id_of, end_is_pos_plus_1=True)
+    return ids, order, bases_of
+
+
+def _indel_ids_order(indel, R, version_id):
+    """``(ids in emission order or None, final row order)`` for the INS / DEL rows."""
+    from .. import _pyrows
+    n = len(indel)
+    rec = indel['rec']
+    pos = indel['pos'].astype(np.int64)
+    end = indel['end'].astype(np.int64)
+    svlen = indel['svlen']
+    svt = indel['svtype']
+    ids = None
+    if version_id or not R.ascii_names:
+        ids = _pyrows.format(n, [('l', R.chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-'),
+                                 ('l', ['INS', 'DEL'], (svt == 1).astype(np.int64)), ('s', '-'), ('i', svlen.astype(np.int64))])
+        if version_id:
+            ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
+        id_of = ids.__getitem__
+    else:
+        def id_of(i):
+            return f'{R.chrom_l[rec[i]]}-{pos[i] + 1}-{("INS", "DEL")[int(svt[i] == 1)]}-{svlen[i]}'
+    return ids, _sort_order(R.chrom_code_rec[rec], pos, end, id_of)
+
+
 def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_id, qry_id, hap, version_id):
     from .. import _pyrows
-    n_rec = len(chrom)
-    chrom_objs, ai_objs = chrom.tolist(), align_index.tolist()
-    chrom_l = [f'{c}' for c in chrom_objs]
-    qry_l = [f'{q}' for q in qry.tolist()]
-    chrom_rank = {c: i for i, c in enumerate(sorted(set(chrom_l)))}
-    chrom_code_rec = np.array([chrom_rank[c] for c in chrom_l], dtype=np.int64)
-    strand_objs = ['-' if r else '+' for r in rev.tolist()]
-    ref_id32 = np.ascontiguousarray(ref_id, dtype=np.int32)
-    qry_id32 = np.ascontiguousarray(qry_id, dtype=np.int32)
-    rev8 = np.ascontiguousarray(rev, dtype=np.uint8)
-    ascii_names = all(x.isascii() for x in chrom_l) and all(x.isascii() for x in qry_l)
+    R = _Records(chrom, qry, rev, align_index, ref_id, qry_id)
+    chrom_l, qry_l, chrom_objs, ai_objs, strand_objs = R.chrom_l, R.qry_l, R.chrom_objs, R.ai_objs, R.strand_objs
+    ref_id32, qry_id32, rev8, ascii_names = R.ref_id32, R.qry_id32, R.rev8, R.ascii_names
 
     # ------------------------------------------------------------------ SNV rows (cigarcall.py:98-135)
     seqs = list(ref_arr) + list(tig_arr)
@@ -373,40 +488,14 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
     if len(snv):
         n = len(snv)
         snv = np.ascontiguousarray(snv)
-        rec = snv['rec']
-        pos = snv['pos_ref'].astype(np.int64)
-        qp = snv['qry_pos']
-
-        def bases_of(idx):
-            """(REF, ALT) bytes of emission rows ``idx`` (whole table for ID versioning, tie groups of the sort otherwise)."""
-            ref_b = np.empty(len(idx), dtype=np.uint8)
-            alt_b = np.empty(len(idx), dtype=np.uint8)
-            r_of = rec[idx]
-            for r in np.unique(r_of).tolist():
-                m = r_of == r
-                ref_b[m] = ref_arr[ref_id[r]][pos[idx][m]]
-                t = tig_arr[qry_id[r]][qp[idx][m]]
-                alt_b[m] = fasta.COMPLEMENT[t] if rev[r] else t
-            return ref_b, alt_b
-
-        ids = None
-        if version_id or not ascii_names:
-            ref_b, alt_b = bases_of(np.arange(n))
-            ids = _pyrows.format(n, [('l', chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
-                                     ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
-            if version_id:
-                ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
-            id_of = ids.__getitem__
-        else:
-            def id_of(i):
-                rb, ab = bases_of(np.array([i]))
-                return f'{chrom_l[rec[i]]}-{pos[i] + 1}-SNV-{chr(fasta.UPPER[rb[0]])}{chr(fasta.UPPER[ab[0]])}'
-        order = _sort_order(chrom_code_rec[rec], pos, pos + 1, id_of, end_is_pos_plus_1=True)
+        ids, order, bases_of = _snv_ids_order(snv, R, ref_arr, tig_arr, version_id)
         if ascii_names:
             cols = _pyrows.snv_frame(snv.view(np.uint8), order, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs, ref_id32, qry_id32, rev8,
                                      seqs, len(ref_arr), comp, ('SNV', 1, hap, 0, CALL_SOURCE))
             df_snv = _frame(dict(zip(SNV_COLUMNS, cols)), SNV_COLUMNS, order)
         else:   # names outside ASCII: generic formatter
+            rec, pos, qp = snv['rec'], snv['pos_ref'].astype(np.int64), snv['qry_pos']
+            ref_b, alt_b = bases_of(np.arange(n))
             rec64, pos_o, qp1 = rec[order].astype(np.int64), pos[order], qp[order].astype(np.int64) + 1
             cols = {
                 '#CHROM': chrom[rec64], 'POS': _pyrows.ints(pos_o), 'END': _pyrows.ints(pos_o + 1), 'ID': ids[order],
@@ -429,17 +518,7 @@ def _build_frames(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, re
         svlen = indel['svlen']
         svtype_l = ['INS', 'DEL']
         svt = indel['svtype']
-        ids = None
-        if version_id or not ascii_names:
-            ids = _pyrows.format(n, [('l', chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-'),
-                                     ('l', svtype_l, (svt == 1).astype(np.int64)), ('s', '-'), ('i', svlen.astype(np.int64))])
-            if version_id:
-                ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
-            id_of = ids.__getitem__
-        else:
-            def id_of(i):
-                return f'{chrom_l[rec[i]]}-{pos[i] + 1}-{svtype_l[int(svt[i] == 1)]}-{svlen[i]}'
-        order = _sort_order(chrom_code_rec[rec], pos, end, id_of)
+        ids, order = _indel_ids_order(indel, R, version_id)
         if ascii_names:
             cols = _pyrows.indel_frame(indel.view(np.uint8), order, ids, chrom_objs, chrom_l, qry_l, strand_objs, ai_objs, ref_id32, qry_id32, rev8,
                                        seqs, len(ref_arr), comp, ('INS', 'DEL', hap, 0, CALL_SOURCE))

@@ -24,6 +24,15 @@ BATCH_COUNT_DEFAULT = 60   # rules/call_inv.snakefile:81
 
 
 # ------------------------------------------------------------------------------------------------ call_cigar FILTER
+def _as_int64(col):
+    """Column of ints (object dtype in the call tables) -> int64 array, converted in C where numpy can."""
+    a = col.to_numpy()
+    try:
+        return a.astype(np.int64)
+    except (TypeError, ValueError):
+        return np.array([int(x) for x in a.tolist()], dtype=np.int64)
+
+
 def cigar_filter(df, df_trim):
     """FILTER column of a call table: PASS when the variant lies strictly inside the trimmed alignment of its
     ``ALIGN_INDEX``, TRIM otherwise (also when the record disappeared in trimming). ``df_trim``: POS, END indexed by INDEX."""
@@ -32,14 +41,13 @@ def cigar_filter(df, df_trim):
     idx = df_trim.index.to_numpy()
     order = np.argsort(idx, kind='stable')
     idx_s = idx[order]
-    ai = np.array([int(x) for x in df['ALIGN_INDEX'].tolist()], dtype=np.int64)
+    ai = _as_int64(df['ALIGN_INDEX'])
     k = np.searchsorted(idx_s, ai)
     k_ok = np.minimum(k, max(len(idx_s) - 1, 0))
     found = (k < len(idx_s)) & (idx_s[k_ok] == ai) if len(idx_s) else np.zeros(len(ai), dtype=bool)
     t_pos = np.where(found, df_trim['POS'].to_numpy().astype(np.int64)[order][k_ok], -1) if len(idx_s) else np.full(len(ai), -1)
     t_end = np.where(found, df_trim['END'].to_numpy().astype(np.int64)[order][k_ok], -1) if len(idx_s) else np.full(len(ai), -1)
-    pos = np.array([int(x) for x in df['POS'].tolist()], dtype=np.int64)
-    end = np.array([int(x) for x in df['END'].tolist()], dtype=np.int64)
+    pos, end = _as_int64(df['POS']), _as_int64(df['END'])
     ok = (pos > t_pos) & (end < t_end)
     return pd.Series(np.where(ok, 'PASS', 'TRIM').astype(object), index=df.index)
 
@@ -52,6 +60,73 @@ def call_cigar(df_align, batch, ref_fa_name, tig_fa_name, hap, df_trim):
     df_snv['FILTER'] = cigar_filter(df_snv, df_trim)
     df_insdel['FILTER'] = cigar_filter(df_insdel, df_trim)
     return df_snv, df_insdel
+
+
+def _trim_bounds(table, df_trim):
+    """Per alignment record: (POS, END) of its trimmed alignment, (-1, -1) when the record did not survive trimming."""
+    idx = df_trim.index.to_numpy()
+    order = np.argsort(idx, kind='stable')
+    idx_s = idx[order]
+    ai = np.array([int(x) for x in table.align_index.tolist()], dtype=np.int64)
+    if not len(idx_s):
+        return np.full(len(ai), -1, dtype=np.int64), np.full(len(ai), -1, dtype=np.int64)
+    k = np.minimum(np.searchsorted(idx_s, ai), len(idx_s) - 1)
+    found = idx_s[k] == ai
+    return (np.where(found, df_trim['POS'].to_numpy().astype(np.int64)[order][k], -1),
+            np.where(found, df_trim['END'].to_numpy().astype(np.int64)[order][k], -1))
+
+
+def write_gzip_members(path, data, threads=None, block=8 << 20, level=6):
+    """``data`` (bytes) -> gzip file made of independently compressed members (cut at line ends), compressed by a thread pool
+    (zlib releases the GIL). Any gzip reader, ``pd.read_csv`` included, reads the concatenation as one stream."""
+    import os
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    cuts, p = [0], 0
+    while len(data) - p > block:
+        q = data.find(b'\n', p + block)
+        if q < 0:
+            break
+        p = q + 1
+        cuts.append(p)
+    cuts.append(len(data))
+
+    def comp(i):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31)
+        return c.compress(data[cuts[i]:cuts[i + 1]]) + c.flush()
+    n = len(cuts) - 1
+    with ThreadPoolExecutor(max_workers=max(1, min(threads or (os.cpu_count() or 4), n))) as pool, open(path, 'wb') as fh:
+        for part in pool.map(comp, range(n)):
+            fh.write(part)
+
+
+def call_cigar_to_files(df_align, batch, ref_fa_name, tig_fa_name, hap, df_trim, bed_insdel, bed_snv, threads=None):
+    """Body of ``rule call_cigar`` including its two ``to_csv(..., compression='gzip')`` calls (rules/call.snakefile:800-846): the
+    tables go from device rows to TSV text in C and to disk through a parallel gzip writer -- no DataFrame, no per-row Python
+    object. The files decompress to exactly what the reference's rule writes. Returns ``(n_snv, n_insdel)``."""
+    from . import cigarcall
+    df_align = df_align.loc[df_align['CALL_BATCH'] == batch]
+    text = None
+    if df_align.shape[0] > 0:
+        table, snv, indel, ref_arr, tig_arr, _ = cigarcall.call_rows(df_align, ref_fa_name, tig_fa_name)
+        t_pos, t_end = _trim_bounds(table, df_trim)
+        pass_snv = ((snv['pos_ref'] > t_pos[snv['rec']]) & (snv['pos_ref'].astype(np.int64) + 1 < t_end[snv['rec']])).astype(np.uint8)
+        pass_indel = ((indel['pos'] > t_pos[indel['rec']]) & (indel['end'] < t_end[indel['rec']])).astype(np.uint8)
+        text = cigarcall.tables_tsv(snv, indel, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id, table.qry_id,
+                                    hap, False, pass_snv, pass_indel)
+        n = (len(snv), len(indel))
+    if text is None:   # empty batch, or names that need CSV quoting: the frames + pandas
+        df_snv, df_insdel = call_cigar(df_align, batch, ref_fa_name, tig_fa_name, hap, df_trim) if df_align.shape[0] else \
+            (cigarcall._empty(cigarcall.SNV_COLUMNS), cigarcall._empty(cigarcall.INSDEL_COLUMNS))
+        if df_align.shape[0] == 0:
+            df_snv['FILTER'] = pd.Series([], dtype=object)
+            df_insdel['FILTER'] = pd.Series([], dtype=object)
+        df_insdel.to_csv(bed_insdel, sep='\t', index=False, compression='gzip')
+        df_snv.to_csv(bed_snv, sep='\t', index=False, compression='gzip')
+        return len(df_snv), len(df_insdel)
+    write_gzip_members(bed_snv, text[0], threads)
+    write_gzip_members(bed_insdel, text[1], threads)
+    return n
 
 
 # ------------------------------------------------------------------------------------------------ helpers

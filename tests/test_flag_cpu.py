@@ -1,7 +1,6 @@
 """Flagging rules between Path A and Path B (pav_b200/pavlib/flag.py) against golden tables produced by executing the
 reference's own rule bodies (tests/golden/make_golden_flag.py): call_inv_cluster, call_inv_flag_insdel_cluster,
 call_inv_merge_flagged_loci and the FILTER step of call_cigar. Tables are compared as the TSV text the rules write."""
-import io
 import os
 
 import pandas as pd

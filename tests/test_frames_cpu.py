@@ -122,3 +122,41 @@ def test_sort_order_equals_pandas(seed):
         df = pd.DataFrame({'#CHROM': chrom_codes, 'POS': pos, 'END': end, 'ID': ids})
         exp = df.sort_values(['#CHROM', 'POS', 'END', 'ID']).index.to_numpy()
         assert (got == exp).all()
+
+
+@pytest.mark.parametrize('case', OK_CASES)
+def test_tables_tsv_equals_to_csv(case):
+    """The C TSV writer (no frames) produces the bytes DataFrame.to_csv writes for the frames, FILTER column included."""
+    d = os.path.join(GOLDEN, 'cigar', case)
+    meta = json.load(open(os.path.join(d, 'meta.json')))
+    df_align = pd.read_csv(os.path.join(d, 'align.bed'), sep='\t', dtype={'#CHROM': str, 'QRY_ID': str}, keep_default_na=False)
+    if df_align.shape[0] == 0:
+        return
+    ref_fa, tig_fa = os.path.join(d, 'ref.fa'), os.path.join(d, 'tig.fa')
+    s, i = device_rows_from_oracle(df_align, ref_fa, tig_fa)
+    table = cigarcall.AlignTable(df_align)
+    rf, tf = fasta.open_fasta(ref_fa), fasta.open_fasta(tig_fa)
+    ref_arr = [rf.fetch_array(nm) for nm in table.ref_names]
+    tig_arr = [tf.fetch_array(nm) for nm in table.tig_names]
+    args = (s, i, table.chrom, table.qry, table.rev, table.align_index, ref_arr, tig_arr, table.ref_id, table.qry_id, meta['hap'], meta['version_id'])
+    text = cigarcall.tables_tsv(*args)
+    assert text[0] == open(os.path.join(d, 'snv.tsv'), 'rb').read() and text[1] == open(os.path.join(d, 'insdel.tsv'), 'rb').read()
+    rng = np.random.default_rng(0)
+    ps, pi = rng.integers(0, 2, len(s)).astype(np.uint8), rng.integers(0, 2, len(i)).astype(np.uint8)
+    text = cigarcall.tables_tsv(*args, pass_snv=ps, pass_indel=pi)
+    df_snv, df_insdel = cigarcall.build_frames(*args)
+    df_snv['FILTER'] = pd.Series(np.where(ps, 'PASS', 'TRIM'), dtype=object).to_numpy()[df_snv.index.to_numpy()] if len(s) else []
+    df_insdel['FILTER'] = pd.Series(np.where(pi, 'PASS', 'TRIM'), dtype=object).to_numpy()[df_insdel.index.to_numpy()] if len(i) else []
+    assert text[0] == tsv(df_snv) and text[1] == tsv(df_insdel)
+
+
+def test_gzip_members_roundtrip(tmp_path):
+    import gzip
+    from pav_b200.pavlib import flag
+    data = b''.join(b'line %d\tsome text\n' % k for k in range(200_000))
+    p = str(tmp_path / 'x.tsv.gz')
+    flag.write_gzip_members(p, data, threads=3, block=1 << 18)
+    assert gzip.open(p, 'rb').read() == data
+    assert pd.read_csv(p, sep='\t', header=None).shape == (200_000, 2)
+    flag.write_gzip_members(p, b'', threads=2)
+    assert gzip.open(p, 'rb').read() == b''
