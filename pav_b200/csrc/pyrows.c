@@ -288,11 +288,28 @@ static inline void fill_const(PyObject **slots, Py_ssize_t n, PyObject *v)
     for (Py_ssize_t i = 0; i < n; i++) { Py_INCREF(v); slots[i] = v; }
 }
 
+/* REF / ALT of consecutive rows sit ~100 bases apart in two multi-hundred-MB arrays: one cache miss each per row unless the
+ * lines are requested a few rows ahead. */
+#define PREFETCH_AHEAD 16
 #define SNV_NCOL 14
 #define INDEL_NCOL 16
 
 typedef struct { int32_t pos_ref, qry_pos, rec, op_idx; } snv_row_t;
 typedef struct { int32_t rec, op_idx, svtype, svlen, pos, end, qry_pos, qry_end, left_shift, hom_ref_l, hom_ref_r, hom_tig_l, hom_tig_r, seq_start, pad[2]; } indel_row_t;
+
+static inline void prefetch_snv(const snv_row_t *R, const int64_t *ord, Py_ssize_t k, Py_ssize_t n, Py_ssize_t n_rows, Py_ssize_t n_rec,
+                                const int32_t *rid, const int32_t *qid, const Py_buffer *bufs, Py_ssize_t n_ref, Py_ssize_t nd_seq)
+{
+    if (k + PREFETCH_AHEAD >= n) return;
+    const int64_t i = ord[k + PREFETCH_AHEAD];
+    if (i < 0 || i >= n_rows) return;
+    const snv_row_t *r = &R[i];
+    __builtin_prefetch(r + 8);
+    if (r->rec < 0 || r->rec >= n_rec) return;
+    const Py_ssize_t wr = rid[r->rec], wq = n_ref + (Py_ssize_t)qid[r->rec];
+    if (wr >= 0 && wr < n_ref && r->pos_ref >= 0 && r->pos_ref < bufs[wr].len) __builtin_prefetch((const char *)bufs[wr].buf + r->pos_ref);
+    if (wq >= n_ref && wq < nd_seq && r->qry_pos >= 0 && r->qry_pos < bufs[wq].len) __builtin_prefetch((const char *)bufs[wq].buf + r->qry_pos);
+}
 
 static PyObject *one_char_table[256];
 
@@ -358,6 +375,7 @@ static PyObject *py_snv_frame(PyObject *self, PyObject *args)
         fill_const(slot[11], n, c_ci); fill_const(slot[13], n, c_src);
         for (Py_ssize_t k = 0; k < n; k++) {
             int64_t i = ord[k];
+            prefetch_snv(R, ord, k, n, n_rows, n_rec, rid, qid, bufs, n_ref, nd_seq);
             if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "snv_frame: order entry out of range"); goto done; }
             const snv_row_t r = R[i];
             if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "snv_frame: record index out of range"); goto done; }
@@ -587,9 +605,9 @@ static PyObject *py_snv_tsv(PyObject *self, PyObject *args)
 {
     Py_buffer rows, order, ref_id, qry_id, rev, comp;
     PyObject *ids, *chrom_strs, *qry_strs, *strand_strs, *ai_strs, *seqs, *pass_obj;
-    const char *hap, *source; Py_ssize_t hap_n, source_n, n_ref;
-    if (!PyArg_ParseTuple(args, "y*y*OOOOOy*y*y*O!ny*s#s#O", &rows, &order, &ids, &chrom_strs, &qry_strs, &strand_strs, &ai_strs,
-                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &hap, &hap_n, &source, &source_n, &pass_obj))
+    const char *hap, *source, *header; Py_ssize_t hap_n, source_n, header_n, n_ref;
+    if (!PyArg_ParseTuple(args, "y*y*OOOOOy*y*y*O!ny*s#s#Oy#", &rows, &order, &ids, &chrom_strs, &qry_strs, &strand_strs, &ai_strs,
+                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &hap, &hap_n, &source, &source_n, &pass_obj, &header, &header_n))
         return NULL;
     PyObject *result = NULL;
     strtab_t tc = {0}, tq = {0}, ts = {0}, ta = {0};
@@ -621,9 +639,12 @@ static PyObject *py_snv_tsv(PyObject *self, PyObject *args)
         const int64_t *ord = (const int64_t *)order.buf;
         const int32_t *rid = (const int32_t *)ref_id.buf, *qid = (const int32_t *)qry_id.buf;
         const uint8_t *rv = (const uint8_t *)rev.buf, *ct = (const uint8_t *)comp.buf;
+        if (obuf_reserve(&ob, (size_t)header_n + (size_t)n * 96) < 0) goto done;   /* header line first; a first guess at the size */
+        ob_mem(&ob, header, (size_t)header_n);
         const size_t fixed = 2 * strtab_max(&tc) + strtab_max(&tq) + strtab_max(&ts) + strtab_max(&ta) + (size_t)hap_n + (size_t)source_n + 160;
         for (Py_ssize_t k = 0; k < n; k++) {
             int64_t i = ord[k];
+            prefetch_snv(R, ord, k, n, n_rows, n_rec, rid, qid, bufs, n_ref, nd_seq);
             if (i < 0 || i >= n_rows) { PyErr_SetString(PyExc_IndexError, "snv_tsv: order entry out of range"); goto done; }
             const snv_row_t r = R[i];
             if (r.rec < 0 || r.rec >= n_rec) { PyErr_SetString(PyExc_IndexError, "snv_tsv: record index out of range"); goto done; }
@@ -671,9 +692,9 @@ static PyObject *py_indel_tsv(PyObject *self, PyObject *args)
 {
     Py_buffer rows, order, ref_id, qry_id, rev, comp;
     PyObject *ids, *chrom_strs, *qry_strs, *strand_strs, *ai_strs, *seqs, *pass_obj;
-    const char *hap, *source; Py_ssize_t hap_n, source_n, n_ref;
-    if (!PyArg_ParseTuple(args, "y*y*OOOOOy*y*y*O!ny*s#s#O", &rows, &order, &ids, &chrom_strs, &qry_strs, &strand_strs, &ai_strs,
-                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &hap, &hap_n, &source, &source_n, &pass_obj))
+    const char *hap, *source, *header; Py_ssize_t hap_n, source_n, header_n, n_ref;
+    if (!PyArg_ParseTuple(args, "y*y*OOOOOy*y*y*O!ny*s#s#Oy#", &rows, &order, &ids, &chrom_strs, &qry_strs, &strand_strs, &ai_strs,
+                          &ref_id, &qry_id, &rev, &PyList_Type, &seqs, &n_ref, &comp, &hap, &hap_n, &source, &source_n, &pass_obj, &header, &header_n))
         return NULL;
     PyObject *result = NULL;
     strtab_t tc = {0}, tq = {0}, ts = {0}, ta = {0};
@@ -705,6 +726,8 @@ static PyObject *py_indel_tsv(PyObject *self, PyObject *args)
         const int64_t *ord = (const int64_t *)order.buf;
         const int32_t *rid = (const int32_t *)ref_id.buf, *qid = (const int32_t *)qry_id.buf;
         const uint8_t *rv = (const uint8_t *)rev.buf, *ct = (const uint8_t *)comp.buf;
+        if (obuf_reserve(&ob, (size_t)header_n + (size_t)n * 128) < 0) goto done;
+        ob_mem(&ob, header, (size_t)header_n);
         const size_t fixed = 2 * strtab_max(&tc) + strtab_max(&tq) + strtab_max(&ts) + strtab_max(&ta) + (size_t)hap_n + (size_t)source_n + 400;
         for (Py_ssize_t k = 0; k < n; k++) {
             int64_t i = ord[k];

@@ -392,9 +392,8 @@ def tables_tsv(snv, indel, chrom, qry, rev, align_index, ref_arr, tig_arr, ref_i
             fn = _pyrows.indel_tsv
         if ids is not None and any(ch in x for x in ids.tolist() for ch in special):
             return None
-        body = fn(rows.view(np.uint8), order, ids, R.chrom_l, R.qry_l, R.strand_objs, ai_l, R.ref_id32, R.qry_id32, R.rev8, seqs, len(ref_arr), comp,
-                  hap, CALL_SOURCE, None if passes is None else np.ascontiguousarray(passes, dtype=np.uint8))
-        out.append(header + body)
+        out.append(fn(rows.view(np.uint8), order, ids, R.chrom_l, R.qry_l, R.strand_objs, ai_l, R.ref_id32, R.qry_id32, R.rev8, seqs, len(ref_arr), comp,
+                      hap, CALL_SOURCE, None if passes is None else np.ascontiguousarray(passes, dtype=np.uint8), header))
     return out[0], out[1]
 
 
