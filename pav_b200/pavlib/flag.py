@@ -4,6 +4,8 @@ The reference implements these inside Snakemake ``run:`` blocks as ``DataFrame.i
 ``pd.Series`` per output row -- over the multi-million-row tables the CIGAR walk now returns in milliseconds:
 
     cigar_filter          rules/call.snakefile:813-846        FILTER = PASS / TRIM against the trimmed alignments
+    call_cigar(_to_files) rules/call.snakefile:800-846        the whole rule body (walk on the GPU + FILTER [+ the two bed.gz files])
+    call_cigar_merge      rules/call.snakefile:755-790        concatenate + sort the per-batch tables
     cluster_variants      rules/call_inv.snakefile:616-690    clusters of SNVs / indels
     flag_insdel_cluster   rules/call_inv.snakefile:493-583    INS matched to nearby DELs, merged
     merge_flagged_loci    rules/call_inv.snakefile:331-474    merge of the four flag tables, TRY_INV, BATCH
@@ -127,6 +129,35 @@ def call_cigar_to_files(df_align, batch, ref_fa_name, tig_fa_name, hap, df_trim,
     write_gzip_members(bed_snv, text[0], threads)
     write_gzip_members(bed_insdel, text[1], threads)
     return n
+
+
+def call_cigar_merge(bed_insdel_files, bed_snv_files, bed_insdel_out, bed_snv_out, threads=None):
+    """Body of ``rule call_cigar_merge`` (rules/call.snakefile:755-790): concatenate the per-batch call tables and sort them
+    (INS/DEL by #CHROM, POS, END, ID; SNVs by #CHROM, POS). The reference parses every column of every file into a DataFrame and
+    formats all of them again; a row of the output is a line of the input, so only the key columns go through pandas here (read
+    and sorted exactly as the reference does, type inference included) and the lines themselves are re-ordered as bytes and
+    written through the parallel gzip writer."""
+    import gzip
+    for files, out, keys in ((bed_insdel_files, bed_insdel_out, ['#CHROM', 'POS', 'END', 'ID']), (bed_snv_files, bed_snv_out, ['#CHROM', 'POS'])):
+        headers, lines, key_frames = [], [], []
+        for fn in files:
+            with gzip.open(fn, 'rb') as fh:
+                data = fh.read()
+            first, _, body = data.partition(b'\n')
+            headers.append(first)
+            rows = body.split(b'\n')
+            if rows and rows[-1] == b'':
+                rows.pop()
+            lines.extend(rows)
+            key_frames.append(pd.read_csv(fn, sep='\t', keep_default_na=False, usecols=keys))
+        if len(set(headers)) > 1:
+            raise RuntimeError('call_cigar_merge: batch tables have different columns')
+        df_key = pd.concat(key_frames, axis=0).reset_index(drop=True)
+        if df_key.shape[0] != len(lines):
+            raise RuntimeError('call_cigar_merge: a batch table has fields with embedded newlines; merge it through pandas')
+        order = df_key.sort_values(keys).index.to_numpy()
+        text = headers[0] + b'\n' + b''.join(lines[i] + b'\n' for i in order.tolist()) if headers else b''
+        write_gzip_members(out, text, threads)
 
 
 # ------------------------------------------------------------------------------------------------ helpers

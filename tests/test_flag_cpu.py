@@ -69,3 +69,13 @@ def test_cigar_filter(batch, kind):
     got = flag.cigar_filter(gold.drop(columns=['FILTER']), df_trim)
     assert got.tolist() == gold['FILTER'].tolist()
     assert set(got) == {'PASS', 'TRIM'}
+
+
+def test_call_cigar_merge(tmp_path):
+    """rule call_cigar_merge over three batches == the tables the reference's rule body wrote."""
+    d = os.path.join(GOLDEN, 'filter')
+    out_i, out_s = str(tmp_path / 'i.bed.gz'), str(tmp_path / 's.bed.gz')
+    flag.call_cigar_merge([os.path.join(d, f'insdel_{b}.bed.gz') for b in (0, 1, 2)], [os.path.join(d, f'snv_{b}.bed.gz') for b in (0, 1, 2)],
+                          out_i, out_s, threads=2)
+    assert golden_text(out_i) == golden_text(os.path.join(d, 'merged_insdel.bed.gz'))
+    assert golden_text(out_s) == golden_text(os.path.join(d, 'merged_snv.bed.gz'))
