@@ -9,6 +9,7 @@ The reference implements these inside Snakemake ``run:`` blocks as ``DataFrame.i
     cluster_variants      rules/call_inv.snakefile:616-690    clusters of SNVs / indels
     flag_insdel_cluster   rules/call_inv.snakefile:493-583    INS matched to nearby DELs, merged
     merge_flagged_loci    rules/call_inv.snakefile:331-474    merge of the four flag tables, TRY_INV, BATCH
+    call_inv_batch        rules/call_inv.snakefile:127-311    flagged regions of a batch -> inversion calls (all loci per GPU batch)
 
 Every loop there carries only "the previous row" (or a running maximum), so each is a break-point mask + segment
 reduction here. The reference's behaviours that look accidental are kept, because the tables must come out identical
@@ -158,6 +159,72 @@ def call_cigar_merge(bed_insdel_files, bed_snv_files, bed_insdel_out, bed_snv_ou
         order = df_key.sort_values(keys).index.to_numpy()
         text = headers[0] + b'\n' + b''.join(lines[i] + b'\n' for i in order.tolist()) if headers else b''
         write_gzip_members(out, text, threads)
+
+
+# ------------------------------------------------------------------------------------------------ call_inv_batch
+INV_BED_COLUMNS = ['#CHROM', 'POS', 'END', 'ID', 'SVTYPE', 'SVLEN', 'HAP', 'QRY_REGION', 'QRY_STRAND', 'CI', 'RGN_REF_INNER', 'RGN_QRY_INNER',
+                   'RGN_REF_DISC', 'RGN_QRY_DISC', 'FLAG_ID', 'FLAG_TYPE', 'ALIGN_INDEX', 'CALL_SOURCE', 'FILTER', 'SEQ']
+
+
+def _collapse_to_set(values, to_type=None):
+    """pavlib/util.py:107-122."""
+    stack, out = list(values), set()
+    while stack:
+        v = stack.pop()
+        if isinstance(v, (tuple, list)):
+            stack.extend(v)
+        else:
+            out.add(to_type(v) if to_type is not None else v)
+    return out
+
+
+class _KUtil:
+    def __init__(self, k_size):
+        self.k_size = k_size
+
+
+def call_inv_batch(df_flag, batch, ref_fa_name, tig_fa_name, df_aln, df_fai, hap, k_size=31, inv_region_limit=None, inv_min_expand=None,
+                   srs_list=None, log=None, density_out_dir=None, threads=1):
+    """Body of ``rule call_inv_batch`` (rules/call_inv.snakefile:127-311): resolve the flagged regions of one batch into inversion
+    calls. Every expansion round of every region still open is scored in one GPU batch (``scan_for_inv_batch``) instead of one
+    ``scripts/density.py`` process per region and expansion; the table is the reference's, row for row (duplicates of an inversion
+    found through a second flagged region are dropped, columns and their order are kept -- including the missing FILTER column
+    of the reference's empty table when a non-empty batch yields no call).
+
+    ``df_flag``: flagged regions (``merge_flagged_loci``); ``df_aln`` / ``df_fai``: trimmed alignments and contig lengths for the
+    coordinate lift; ``log``: open text file or None; ``density_out_dir``: where to write the per-call density tables, or None."""
+    import os
+
+    from . import inv, lift, seq
+    df_flag = df_flag.loc[df_flag['BATCH'] == batch]
+    if df_flag.shape[0] == 0:
+        return pd.DataFrame([], columns=INV_BED_COLUMNS)
+    srs_tree = inv.get_srs_tree(srs_list)
+    align_lift = lift.AlignLift(df_aln, df_fai)
+    regions = [seq.Region(row['#CHROM'], row['POS'], row['END']) for _, row in df_flag.iterrows()]
+    calls = inv.scan_for_inv_batch(regions, ref_fa_name, tig_fa_name, align_lift, _KUtil(k_size), max_region_size=inv_region_limit, log=log,
+                                   srs_tree=srs_tree, min_exp_count=inv_min_expand, catch=True)
+    id_set, rows = set(), []
+    for (_, row), inv_call in zip(df_flag.iterrows(), calls):
+        if inv_call is None or isinstance(inv_call, RuntimeError) or inv_call.id in id_set:   # errors are logged and skipped (call_inv.snakefile:198-200)
+            continue
+        sequence = seq.region_seq_fasta(inv_call.region_tig_outer, tig_fa_name, rev_compl=inv_call.region_tig_outer.is_rev)
+        align_index = ','.join(sorted(_collapse_to_set((inv_call.region_ref_outer.pos_aln_index, inv_call.region_ref_outer.end_aln_index,
+                                                         inv_call.region_ref_inner.pos_aln_index, inv_call.region_ref_inner.end_aln_index), to_type=str)))
+        rows.append([
+            inv_call.region_ref_outer.chrom, inv_call.region_ref_outer.pos, inv_call.region_ref_outer.end, inv_call.id, 'INV', inv_call.svlen, hap,
+            inv_call.region_tig_outer.to_base1_string(), '-' if inv_call.region_tig_outer.is_rev else '+', 0,
+            inv_call.region_ref_inner.to_base1_string(), inv_call.region_tig_inner.to_base1_string(),
+            inv_call.region_ref_discovery.to_base1_string(), inv_call.region_tig_discovery.to_base1_string(),
+            inv_call.region_flag.region_id(), row['TYPE'], align_index, inv.CALL_SOURCE, 'PASS', sequence])
+        id_set.add(inv_call.id)
+        if density_out_dir is not None:
+            os.makedirs(density_out_dir, exist_ok=True)
+            inv_call.df.to_csv(os.path.join(density_out_dir, 'density_{}_{}.tsv.gz'.format(inv_call.id, hap)), sep='\t', index=False, compression='gzip')
+    if not rows:
+        return pd.DataFrame([], columns=[c for c in INV_BED_COLUMNS if c != 'FILTER'])   # sic (call_inv.snakefile:293-307)
+    df_bed = pd.DataFrame(np.array(rows, dtype=object), columns=INV_BED_COLUMNS)
+    return df_bed.sort_values(['#CHROM', 'POS', 'END', 'ID'])
 
 
 # ------------------------------------------------------------------------------------------------ helpers

@@ -260,19 +260,43 @@ def scan_for_inv(region_flag, ref_fa_name, tig_fa_name, align_lift, k_util, n_tr
 
 
 def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree=None, max_region_size=None, log=None,
-                       srs_tree=None, min_exp_count=DEFAULT_MIN_EXP_COUNT):
+                       srs_tree=None, min_exp_count=DEFAULT_MIN_EXP_COUNT, catch=False):
     """
     ``scan_for_inv`` for many flagged loci at once (extension; the reference scans one locus per call,
     rules/call_inv.snakefile:191-196). All loci that still need a density table are scored together in one GPU batch per
     expansion round, so a Snakemake batch of thousands of 50 kbp windows costs a handful of launches instead of one
     ``scripts/density.py`` process per window and expansion.
 
+    The log lines of every locus are buffered and written to ``log`` locus by locus, so the log reads as if the loci had been
+    scanned one after the other. ``catch=True``: a ``RuntimeError`` raised while scanning a locus becomes that locus' result
+    instead of ending the batch (``rule call_inv_batch`` logs it and goes on, rules/call_inv.snakefile:198-200).
+
     :return: list with one ``InvCall`` or ``None`` per flagged region, identical to calling ``scan_for_inv`` on each.
     """
+    import io
+
     from .. import fasta as _fasta
     df_fai = pavseq.get_df_fai(ref_fa_name + '.fai')
-    scans = [_InvScan(r, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree, max_region_size, log, srs_tree, min_exp_count, df_fai=df_fai)
-             for r in region_flags]
+    logs = [io.StringIO() if log is not None else None for _ in region_flags]
+
+    class _Log:   # StringIO without flush noise
+        def __init__(self, buf):
+            self.buf = buf
+
+        def write(self, text):
+            self.buf.write(text)
+
+        def flush(self):
+            pass
+    scans = []
+    for r, lg in zip(region_flags, logs):
+        try:
+            scans.append(_InvScan(r, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree, max_region_size, None if lg is None else _Log(lg),
+                                  srs_tree, min_exp_count, df_fai=df_fai))
+        except RuntimeError as ex:
+            if not catch:
+                raise
+            scans.append(_Failed(ex))
     ref_fa, tig_fa = _fasta.open_fasta(ref_fa_name), _fasta.open_fasta(tig_fa_name)
     k_size = int(k_util.k_size)
     while True:
@@ -280,7 +304,12 @@ def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_uti
         for sc in scans:
             if sc.done:
                 continue
-            win = sc.next_window()
+            try:
+                win = sc.next_window()
+            except RuntimeError as ex:
+                if not catch:
+                    raise
+                sc.done, sc.result, win = True, ex, None
             if win is None:
                 continue
             region_ref, region_tig, rev, srs = win
@@ -292,11 +321,29 @@ def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_uti
         results = pavdensity.density_windows(windows, k=k_size, min_informative=MIN_INFORMATIVE_KMERS,
                                              min_state_count=MIN_KMER_STATE_COUNT, smooth=DENSITY_SMOOTH_FACTOR)
         for sc, res in zip(pending, results):
-            if res['status'] != 0:
-                sc.feed(ERR_INV_FAIL, None)
-            else:
-                sc.feed(0, pavdensity.frame_from_result(res))
+            try:
+                if res['status'] != 0:
+                    sc.feed(ERR_INV_FAIL, None)
+                else:
+                    sc.feed(0, pavdensity.frame_from_result(res))
+            except RuntimeError as ex:
+                if not catch:
+                    raise
+                sc.done, sc.result = True, ex
+    if log is not None:
+        for lg, sc in zip(logs, scans):
+            log.write(lg.getvalue())
+            if isinstance(sc.result, RuntimeError):
+                log.write('RuntimeError in scan_for_inv(): {}\n'.format(sc.result))
+        log.flush()
     return [sc.result for sc in scans]
+
+
+class _Failed:
+    """A locus whose scan could not even start (``catch=True``)."""
+
+    def __init__(self, ex):
+        self.done, self.result = True, ex
 
 
 _CODE = np.full(256, 255, dtype=np.uint8)

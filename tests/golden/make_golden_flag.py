@@ -63,11 +63,15 @@ def function_source(snakefile, name):
 
 def run_rule(snakefile, rule, input, output, params=None, wildcards=None, config=None, extra=None):
     g = {'pd': pd, 'np': np, 'collections': collections, 'intervaltree': intervaltree, 'pavlib': pavlib, 'os': os,
-         'get_config': lambda wc, key, default=None, default_none=False: (config or {}).get(key, default), 'BATCH_COUNT_DEFAULT': 60}
+         'get_config': lambda wc, key=None, default=None, default_none=False: dict(config or {}) if key is None else (config or {}).get(key, default),
+         'BATCH_COUNT_DEFAULT': 60}
     g.update(extra or {})
     exec(compile(rule_body(snakefile, rule), f'{snakefile}:{rule}', 'exec'), g)
     ns = types.SimpleNamespace
-    g['run'](ns(**input), ns(**output), ns(**(params or {})), ns(**(wildcards or {})))
+
+    class Wildcards(dict):   # attribute access and ``**wildcards`` both work in rule bodies
+        __getattr__ = dict.__getitem__
+    g['run'](ns(**input), ns(**output), ns(**(params or {})), Wildcards(wildcards or {}))
 
 
 def variant_tables(seed):
@@ -175,7 +179,59 @@ def filter_case(name, seed):
         print(name, batch, pd.read_csv(os.path.join(d, f'snv_{batch}.bed.gz'), sep='\t')['FILTER'].value_counts().to_dict())
 
 
+def inv_batch_case(name, seed=17):
+    """rule call_inv_batch end to end (rules/call_inv.snakefile:115-311): a 120 kbp locus with two inversions, a flagged table with
+    a region per inversion, a second region that finds the first inversion again (dropped as a duplicate), a region without an
+    inversion, and a row of another batch. The reference's scan_for_inv spawns scripts/density.py per expansion, as in production."""
+    import gc
+    import random
+
+    import kanapy.util.kmer
+    import svpoplib
+    d = os.path.join(OUT, name)
+    os.makedirs(d, exist_ok=True)
+    random.seed(seed)
+    n = 120_000
+    s0 = ''.join(random.choice('ACGT') for _ in range(n))
+    comp = {'A': 'T', 'C': 'G', 'G': 'C', 'T': 'A'}
+    rc = lambda x: ''.join(comp[c] for c in reversed(x))  # noqa: E731
+    t = s0[:26000] + rc(s0[26000:34000]) + s0[34000:86000] + rc(s0[86000:91000]) + s0[91000:]
+    ref_fa, tig_fa = os.path.join(d, 'ref.fa'), os.path.join(d, 'tig.fa')
+    synth.write_fasta(ref_fa, {'chr1': np.frombuffer(s0.encode(), dtype=np.uint8)}, line_width=60)
+    synth.write_fasta(tig_fa, {'tig1': np.frombuffer(t.encode(), dtype=np.uint8)}, line_width=60)
+    pd.DataFrame([('chr1', 0, n, 0, 'tig1', 0, n, n, False, f'{n}=')],
+                 columns=['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END', 'QRY_LEN', 'REV', 'CIGAR']
+                 ).to_csv(os.path.join(d, 'align.bed'), sep='\t', index=False)
+    flag_rows = [('chr1', 28000, 32000, 'chr1-28000-RGN-4000', 'RGN', 4000, 'MATCH_SV', 0, 0, True, 0),
+                 ('chr1', 29000, 31000, 'chr1-29000-RGN-2000', 'RGN', 2000, 'CLUSTER_SNV,MATCH_INDEL', 0, 25, True, 0),
+                 ('chr1', 60000, 61000, 'chr1-60000-RGN-1000', 'RGN', 1000, 'MATCH_INDEL', 0, 0, True, 0),
+                 ('chr1', 87000, 90000, 'chr1-87000-RGN-3000', 'RGN', 3000, 'MATCH_SV', 0, 0, True, 0),
+                 ('chr1', 100000, 101000, 'chr1-100000-RGN-1000', 'RGN', 1000, 'MATCH_SV', 0, 0, True, 1)]
+    pd.DataFrame(flag_rows, columns=['#CHROM', 'POS', 'END', 'ID', 'SVTYPE', 'SVLEN', 'TYPE', 'COUNT_INDEL', 'COUNT_SNV', 'TRY_INV', 'BATCH']
+                 ).to_csv(os.path.join(d, 'flagged.bed.gz'), sep='\t', index=False, compression='gzip')
+    os.environ['PYTHONPATH'] = os.pathsep.join(refenv.pythonpath_entries())   # for the scripts/density.py children
+    cwd = os.getcwd()
+    work = os.path.join(d, '_work')
+    os.makedirs(work, exist_ok=True)
+    os.chdir(work)
+    try:
+        for batch in (0, 1, 5):
+            run_rule('call_inv.snakefile', 'call_inv_batch',
+                     {'bed_flag': os.path.join(d, 'flagged.bed.gz'), 'bed_aln': os.path.join(d, 'align.bed'), 'tig_fa': tig_fa, 'fai': tig_fa + '.fai'},
+                     {'bed': os.path.join(d, f'inv_call_{batch}.bed.gz')}, wildcards={'asm_name': 'asm', 'hap': 'h1', 'batch': str(batch)},
+                     extra={'REF_FA': ref_fa, 'kanapy': kanapy, 'svpoplib': svpoplib, 'gc': gc, 'threads': 1,
+                            'log': types.SimpleNamespace(log=os.path.join(d, f'inv_call_{batch}.log'))})
+            print(name, batch, pd.read_csv(os.path.join(d, f'inv_call_{batch}.bed.gz'), sep='\t').iloc[:, :6].to_string())
+    finally:
+        os.chdir(cwd)
+    import shutil
+    shutil.rmtree(work)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'inv':
+        inv_batch_case('inv_batch')
+        sys.exit(0)
     flag_case('a', 501)
     flag_case('b', 502, config={'inv_sig_merge_flank': 5000, 'inv_sig_batch_count': 7})
     flag_case('empty', 503)
