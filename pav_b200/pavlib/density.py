@@ -20,6 +20,7 @@ SMOOTHED_COLUMNS = ['INDEX', 'STATE_MER', 'STATE', 'KERN_FWD', 'KERN_FWDREV', 'K
 RAW_COLUMNS = ['KMER', 'INDEX', 'STATE', 'STATE_MER']
 
 last_stats = None
+MAX_WINDOWS_PER_BATCH = 512   # windows scored per device batch by density_windows (larger requests are split)
 
 
 def default_params(k=31, min_informative=2000, min_state_count=20, smooth=1.0, delta=0.005, max_ref_kmer_count=100):
@@ -91,6 +92,11 @@ def density_windows(windows, k=31, ctx=None, **kw):
     global last_stats
     ctx = ctx or device.get_context()
     windows = list(windows)
+    if len(windows) > MAX_WINDOWS_PER_BATCH:   # bound the device arena and the pinned result buffers (~5 MB + ~2 MB per 50 kbp window)
+        out = []
+        for a in range(0, len(windows), MAX_WINDOWS_PER_BATCH):
+            out.extend(density_windows(windows[a:a + MAX_WINDOWS_PER_BATCH], k=k, ctx=ctx, **kw))
+        return out
     refs = [np.ascontiguousarray(w[0], dtype=np.uint8) for w in windows]
     tigs = [np.ascontiguousarray(w[1], dtype=np.uint8) for w in windows]
     import time

@@ -117,3 +117,24 @@ def test_density_k_too_large_raises():
     s = synth.random_seq(rng, 3000)
     with pytest.raises(RuntimeError):
         density.density_windows([(s, s, False, 20)], k=33)
+
+
+def test_density_windows_split_requests(monkeypatch):
+    """Requests larger than MAX_WINDOWS_PER_BATCH are scored in several device batches with identical results."""
+    from pav_b200 import synth
+    from pav_b200.pavlib import density
+    rng = np.random.default_rng(77)
+    wins = []
+    for i in range(8):
+        r, t, _ = synth.make_inv_window(rng, 9000 + 500 * i, 2500, flank_rep=300 if i % 2 else 0, divergence=0.004, negative=(i == 5))
+        wins.append((r, t, False, 20))
+    whole = density.density_windows(wins)
+    monkeypatch.setattr(density, 'MAX_WINDOWS_PER_BATCH', 3)
+    split = density.density_windows(wins)
+    assert len(split) == len(whole) == 8
+    for a, b in zip(whole, split):
+        assert a['status'] == b['status'] and a['smoothed'] == b['smoothed']
+        for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE'):
+            assert (a[c] == b[c]).all()
+        for c in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
+            assert np.array_equal(a[c], b[c], equal_nan=True)
