@@ -145,6 +145,37 @@ def frame_from_result(d):
     }, columns=RAW_COLUMNS)
 
 
+class DensityTable:
+    """Result of one window whose DataFrame is built only when somebody needs it: the scan driver decides from the run lengths of
+    STATE alone whether to expand the locus again, and most tables are dropped at that point."""
+
+    def __init__(self, res):
+        self.res = res
+        self._df = None
+
+    @property
+    def shape(self):
+        return (len(self.res['INDEX']), len(SMOOTHED_COLUMNS) if self.res['smoothed'] else len(RAW_COLUMNS))
+
+    def rl(self):
+        """``rl_encoder(frame)`` straight from the column arrays."""
+        ix = self.res['INDEX']
+        st = self.res['STATE'] if self.res['smoothed'] else np.full(len(ix), -1, dtype=np.int8)
+        n = len(st)
+        if n == 0:
+            return
+        brk = np.flatnonzero(st[1:] != st[:-1]) + 1
+        starts = np.concatenate(([0], brk))
+        ends = np.concatenate((brk, [n]))
+        for a, b in zip(starts.tolist(), ends.tolist()):
+            yield (st[a].item(), b - a, ix[a].item(), ix[b - 1].item())
+
+    def frame(self):
+        if self._df is None:
+            self._df = frame_from_result(self.res)
+        return self._df
+
+
 def density_table(region_ref, region_tig, ref_fa_name, tig_fa_name, k=31, rev=False, state_run_smooth=20, **kw):
     """One window addressed like ``scripts/density.py --refregion/--tigregion/--ref/--tig -k -r --staterunsmooth``.
 

@@ -171,13 +171,14 @@ class _InvScan:
         if df.shape[0] == 0:
             _write_log('No informative reference k-mers in forward or reverse orientation in region', log)
             return self._finish(None)
-        state_rl = [record for record in pavdensity.rl_encoder(df)]
+        lazy = isinstance(df, pavdensity.DensityTable)      # batch driver: the frame is only built when a call is characterised
+        state_rl = [record for record in (df.rl() if lazy else pavdensity.rl_encoder(df))]
         condensed_states = [record[0] for record in state_rl]
         if len(state_rl) == 1 and state_rl[0][0] in {0, -1} and self.expansion_count >= self.min_exp_count:
             _write_log('Found no inverted k-mer states after {} expansion(s)'.format(self.expansion_count), log)
             return self._finish(None)
         if len(condensed_states) > 2 and condensed_states[0] == 0 and condensed_states[-1] == 0:
-            return self._finish(self._characterise(df, state_rl))
+            return self._finish(self._characterise(df.frame() if lazy else df, state_rl))
         last_len = len(region_ref)
         expand_bp = np.int32(len(region_ref) * EXPAND_FACTOR)
         if len(condensed_states) > 2:
@@ -325,7 +326,7 @@ def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_uti
                 if res['status'] != 0:
                     sc.feed(ERR_INV_FAIL, None)
                 else:
-                    sc.feed(0, pavdensity.frame_from_result(res))
+                    sc.feed(0, pavdensity.DensityTable(res))
             except RuntimeError as ex:
                 if not catch:
                     raise
@@ -386,16 +387,15 @@ def annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_out
     ref_set_dn = _region_canonical_kmers(dup_ref_dn, ref_fa, k)
 
     qry_index = df['INDEX'].to_numpy() + region_tig_discovery.pos
-    flank = np.full(df.shape[0], '', dtype=object)
-    flank[(qry_index >= dup_tig_up.pos) & (qry_index < dup_tig_up.end - k)] = 'UP'
-    flank[(qry_index >= dup_tig_dn.pos) & (qry_index < dup_tig_dn.end - k)] = 'DN'
+    up = (qry_index >= dup_tig_up.pos) & (qry_index < dup_tig_up.end - k)
+    dn = (qry_index >= dup_tig_dn.pos) & (qry_index < dup_tig_dn.end - k)
+    flank = np.array(['', 'UP', 'DN'], dtype=object)[np.where(dn, 2, np.where(up, 1, 0))]     # DN is assigned last, as in the reference
     match = np.full(df.shape[0], '', dtype=object)
-    kmers = df['KMER'].tolist()
-    for i in np.flatnonzero(flank == 'UP').tolist():
-        match[i] = KMER_LOC_STATE[int(kmers[i] in ref_set_up), int(kmers[i] in ref_set_dn)]
-    for i in np.flatnonzero(flank == 'DN').tolist():
-        match[i] = KMER_LOC_STATE[int(kmers[i] in ref_set_dn), int(kmers[i] in ref_set_up)]
-    match = [np.nan if v == 'NA' else v for v in match.tolist()]
-    df['FLANK'] = flank
-    df['MATCH'] = match
+    kmer_col = df['KMER'].to_numpy()
+    for idx, first, second in ((np.flatnonzero(up & ~dn), ref_set_up, ref_set_dn), (np.flatnonzero(dn), ref_set_dn, ref_set_up)):
+        for i, km in zip(idx.tolist(), kmer_col[idx].tolist()):      # only the k-mers inside the flanking duplications
+            v = KMER_LOC_STATE[int(km in first), int(km in second)]
+            match[i] = np.nan if v == 'NA' else v
+    df['FLANK'] = pd.Series(flank, index=df.index, dtype=object)   # explicit dtype: no string-dtype inference pass over 50 k cells
+    df['MATCH'] = pd.Series(match, index=df.index, dtype=object)
     return df

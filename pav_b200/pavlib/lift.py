@@ -34,6 +34,16 @@ class AlignLift:
         self._qid = df['QRY_ID'].to_numpy(dtype=object)
         self._qpos = df['QRY_POS'].to_numpy(dtype=np.int64)
         self._qend = df['QRY_END'].to_numpy(dtype=np.int64)
+        # per-record values handed out with every lift, read once (a ``df.iloc[i]`` per lookup costs more than the lift itself)
+        self._rev = df['REV'].to_numpy()
+        self._aln_index = df['INDEX'].to_numpy()
+        self._cigar = df['CIGAR'].to_numpy(dtype=object)
+        self._by_chrom, self._by_qid = {}, {}
+        for i, (c, q) in enumerate(zip(self._chrom.tolist(), self._qid.tolist())):
+            self._by_chrom.setdefault(c, []).append(i)
+            self._by_qid.setdefault(q, []).append(i)
+        self._by_chrom = {c: np.array(v, dtype=np.int64) for c, v in self._by_chrom.items()}
+        self._by_qid = {q: np.array(v, dtype=np.int64) for q, v in self._by_qid.items()}
         self._cache = {}
         self._order = []
 
@@ -45,8 +55,8 @@ class AlignLift:
             return self._cache[i]
         while len(self._order) >= self.cache_align:
             del self._cache[self._order.pop()]
-        row = self.df.iloc[i]
-        ops, _, perr = device.parse_cigars([row['CIGAR']])
+        row = {'#CHROM': self._chrom[i], 'POS': self._pos[i], 'QRY_ID': self._qid[i]}
+        ops, _, perr = device.parse_cigars([self._cigar[i]])
         if perr.code != 0:
             raise RuntimeError('Malformed CIGAR for alignment {}:{} ({})'.format(row['#CHROM'], row['POS'], row['QRY_ID']))
         code = (ops & 15).astype(np.int64)
@@ -92,13 +102,14 @@ class AlignLift:
             coord = (coord,)
         out = []
         for pos in coord:
-            hit = np.flatnonzero((self._chrom == subject_id) & (self._pos <= pos) & (self._end > pos))
+            cand = self._by_chrom.get(subject_id)
+            hit = cand[(self._pos[cand] <= pos) & (self._end[cand] > pos)] if cand is not None else ()
             if len(hit) != 1:
                 out.append(None)
                 continue
             i = int(hit[0])
             m = self._record_map(i)
-            row = self.df.iloc[i]
+            row = {'#CHROM': self._chrom[i], 'QRY_ID': self._qid[i], 'REV': self._rev[i], 'INDEX': self._aln_index[i]}
             k = self._block(m.r_begin, m.r_end, pos)
             if k < 0:
                 raise RuntimeError(('Program bug: Found no matches in a lift-tree for a record withing a '
@@ -120,7 +131,8 @@ class AlignLift:
         out = []
         for pos in coord:
             pos_org = pos
-            hit = np.flatnonzero((self._qid == query_id) & (self._qpos <= pos) & (self._qend > pos))
+            cand = self._by_qid.get(query_id)
+            hit = cand[(self._qpos[cand] <= pos) & (self._qend[cand] > pos)] if cand is not None else ()
             if len(hit) == 0 and gap:
                 out.append(self._get_subject_gap(query_id, pos))
                 continue
@@ -129,7 +141,7 @@ class AlignLift:
                 continue
             i = int(hit[0])
             m = self._record_map(i)
-            row = self.df.iloc[i]
+            row = {'#CHROM': self._chrom[i], 'QRY_ID': self._qid[i], 'REV': self._rev[i], 'INDEX': self._aln_index[i]}
             if row['REV']:
                 pos = self.df_fai[query_id] - pos
             k = self._block(m.q_begin, m.q_end, pos)
