@@ -261,3 +261,40 @@ def test_fasta_bgzf_random_access(tmp_path):
             assert (fa.fetch_array(n) == s).all()
         assert fa.fetch('chrA', 65_000, 66_500) == seqs['chrA'][65_000:66_500].tobytes().decode()
         assert fa.fetch('chrC', 149_990, 150_001) == seqs['chrC'][149_990:].tobytes().decode()
+
+
+def test_fasta_fetch_into(tmp_path):
+    """Whole-record reads straight into a caller buffer (pinned staging): every line width, partial last lines, empty records,
+    a file without a trailing newline, and the BGZF fallback."""
+    import numpy as np
+
+    from pav_b200 import fasta, synth
+    rng = np.random.default_rng(1)
+    seqs = {'a': synth.random_seq(rng, 1000), 'b': synth.random_seq(rng, 80), 'c': synth.random_seq(rng, 81), 'd': synth.random_seq(rng, 7),
+            'e': np.zeros(0, np.uint8), 'f': synth.random_seq(rng, 160)}
+    for lw in (80, 60, 7):
+        p = str(tmp_path / f'x{lw}.fa')
+        synth.write_fasta(p, seqs, line_width=lw)
+        fa = fasta.open_fasta(p)
+        for k, v in seqs.items():
+            out = np.full(len(v) + 5, 255, np.uint8)
+            got = fa.fetch_into(k, out)
+            assert (got == v).all() and (out[len(v):] == 255).all(), (lw, k)
+            assert (fa.fetch_array(k) == v).all()
+    p = str(tmp_path / 'nonl.fa')
+    open(p, 'wb').write(b'>s\nACGTACGT\nACGTACGT')
+    out = np.zeros(16, np.uint8)
+    assert bytes(fasta.open_fasta(p).fetch_into('s', out)) == b'ACGTACGTACGTACGT'
+    # bgzip-compressed FASTA: block-wise reader behind the same call
+    plain = str(tmp_path / 'x80.fa')
+    gz = str(tmp_path / 'z.fa.gz')
+    synth.write_bgzf(gz, open(plain, 'rb').read(), block=300)
+    import shutil
+    shutil.copy(plain + '.fai', gz + '.fai')
+    fz = fasta.open_fasta(gz)
+    for k, v in seqs.items():
+        out = np.zeros(len(v), np.uint8)
+        assert (fz.fetch_into(k, out) == v).all()
+    import pytest
+    with pytest.raises(KeyError):
+        fa.fetch_into('nope', np.zeros(4, np.uint8))
