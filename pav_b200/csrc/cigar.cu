@@ -25,7 +25,10 @@
 
 namespace {
 
-constexpr int OPS_PER_LANE = 8;           // two 128-bit loads per lane; 256-op chunks halve the per-op cost of the warp scans / look-back
+#ifndef OPS_PER_LANE_N
+#define OPS_PER_LANE_N 8
+#endif
+constexpr int OPS_PER_LANE = OPS_PER_LANE_N;           // two 128-bit loads per lane; 256-op chunks halve the per-op cost of the warp scans / look-back
 constexpr int CHUNK = 32 * OPS_PER_LANE;  // ops per warp
 static_assert(OPS_PER_LANE % 4 == 0, "lanes load whole uint4 vectors");
 constexpr int WARPS_PER_BLOCK = 8;
