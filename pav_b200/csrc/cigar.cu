@@ -31,7 +31,10 @@ namespace {
 constexpr int OPS_PER_LANE = OPS_PER_LANE_N;           // two 128-bit loads per lane; 256-op chunks halve the per-op cost of the warp scans / look-back
 constexpr int CHUNK = 32 * OPS_PER_LANE;  // ops per warp
 static_assert(OPS_PER_LANE % 4 == 0, "lanes load whole uint4 vectors");
-constexpr int WARPS_PER_BLOCK = 8;
+#ifndef WARPS_PER_BLOCK_N
+#define WARPS_PER_BLOCK_N 4
+#endif
+constexpr int WARPS_PER_BLOCK = WARPS_PER_BLOCK_N;
 constexpr unsigned FULL = 0xffffffffu;
 
 constexpr uint32_t REF_ADV_MASK = (1u << PAVGPU_OP_D) | (1u << PAVGPU_OP_EQ) | (1u << PAVGPU_OP_X);
