@@ -8,6 +8,10 @@ return types and error behaviour as the reference), implemented on libpavgpu.so.
     pavlib.density.rl_encoder                (reference: pavlib/density.py:330)
     pavlib.inv.scan_for_inv                  (reference: pavlib/inv.py:149)
 
+and, as functions, the bodies of the Snakemake rules either side of the two paths (``pavlib.flag``; the reference has them
+inline in rules/call.snakefile and rules/call_inv.snakefile): call_cigar (+ direct gz-TSV writer), call_cigar_merge,
+call_inv_cluster, call_inv_flag_insdel_cluster, call_inv_merge_flagged_loci, call_inv_batch.
+
 INTEGRATION.md shows how a PAV checkout binds these names.
 """
-from . import align, call, cigarcall, constants, density, inv, lift, seq, variant  # noqa: F401
+from . import align, call, cigarcall, constants, density, flag, inv, lift, seq, variant  # noqa: F401
