@@ -7,6 +7,7 @@
   pysam/htslib. Per-record span counting reuses the bulk tokenizer of libpavgpu (host C) and numpy reductions.
 """
 import gzip
+import re
 
 import numpy as np
 import pandas as pd
@@ -41,9 +42,51 @@ ALIGN_COLUMNS = ['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END'
                  'HAP', 'CIGAR']
 
 
+def _count_cigar_fast(cigar, allow_m):
+    """``count_cigar`` for a well-formed record: the C tokenizer of libpavgpu + numpy sums. Returns ``None`` for anything irregular
+    (syntax error, op outside =XID[M], clips not of the form [H][S] ... [S][H]); the caller then takes the op-by-op path, which raises
+    the reference's exceptions."""
+    from .. import device
+    try:
+        ops, _, perr = device.parse_cigars([cigar])
+    except Exception:  # noqa: BLE001  (e.g. an op length beyond the packed format)
+        return None
+    if perr.code != 0 or len(ops) == 0:
+        return None
+    code, ln = (ops & 15).astype(np.int64), (ops >> 4).astype(np.int64)
+    is_clip = (code == CIGAR_S) | (code == CIGAR_H)
+    body = np.flatnonzero(~is_clip)
+    if len(body) == 0:
+        return None
+    a, b = int(body[0]), int(body[-1]) + 1
+    if a > 2 or len(code) - b > 2 or is_clip[a:b].any():
+        return None
+    lead, tail = code[:a].tolist(), code[b:].tolist()
+    if lead not in ([], [CIGAR_H], [CIGAR_S], [CIGAR_H, CIGAR_S]) or tail not in ([], [CIGAR_S], [CIGAR_H], [CIGAR_S, CIGAR_H]):
+        return None
+    allowed = (CIGAR_EQ, CIGAR_X, CIGAR_I, CIGAR_D) + ((CIGAR_M,) if allow_m else ())
+    cb, lb = code[a:b], ln[a:b]
+    if not np.isin(cb, allowed).all():
+        return None
+    if (ln[:a] == 0).any() or (ln[b:] == 0).any():
+        return None     # zero-length clips make the op-by-op checks ("duplicate", "before") behave differently: leave them to it
+    ref_bp = int(lb[cb != CIGAR_I].sum())
+    tig_bp = int(lb[cb != CIGAR_D].sum())
+    clip = {CIGAR_H: 0, CIGAR_S: 0}
+    clip_l, clip_r = dict(clip), dict(clip)
+    for c, n_ in zip(lead, ln[:a].tolist()):
+        clip_l[c] = n_
+    for c, n_ in zip(tail, ln[b:].tolist()):
+        clip_r[c] = n_
+    return ref_bp, tig_bp, clip_l[CIGAR_H], clip_l[CIGAR_S], clip_r[CIGAR_H], clip_r[CIGAR_S]
+
+
 def count_cigar(row, allow_m=False):
     """``(ref_bp, tig_bp, clip_h_l, clip_s_l, clip_h_r, clip_s_r)`` of an alignment record; same structural checks and
     messages as the reference (clips only at the ends, H outside S, no M unless ``allow_m``)."""
+    fast = _count_cigar_fast(row['CIGAR'] if isinstance(row, pd.Series) else row, allow_m)
+    if fast is not None:
+        return fast
     ref_bp = tig_bp = clip_s_l = clip_h_l = clip_s_r = clip_h_r = 0
     ops = list(cigar_str_to_tuples(row))
     n, i = len(ops), 0
@@ -138,6 +181,19 @@ def clip_soft_to_hard(cigar_tuples):
     return cigar_tuples
 
 
+_LEAD_CLIPS = re.compile(r'^(?:\d+[SH])*')
+_TAIL_CLIPS = re.compile(r'(?:\d+[SH])*$')
+_LEADING_ZERO = re.compile(r'(?<!\d)0\d')
+
+
+def _core_text(cigar, core_c, core_n):
+    """CIGAR text of the ops between the clips, as ``str(length) + op`` per op. That is a substring of the SAM field unless a length
+    was written with leading zeros, so the common case costs two regex matches instead of one f-string per op."""
+    if _LEADING_ZERO.search(cigar) is None:
+        return cigar[_LEAD_CLIPS.match(cigar).end():_TAIL_CLIPS.search(cigar).start()]
+    return ''.join(f'{a}{CIGAR_CODE_TO_CHAR[b]}' for b, a in zip(core_c.tolist(), core_n.tolist()))
+
+
 def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
     """
     Read a SAM text file (plain or gzip) as the alignment table PAV processes (reference: pavlib/align/align.py:666-794,
@@ -204,8 +260,7 @@ def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
         if lead_s + clip_h != tig_map_pos:
             raise RuntimeError(f'First aligned based from pysam ({lead_s}) does not match clipping ({tig_map_pos}) at alignment record {idx}')
         tig_map_end = tig_map_pos + qry_bp
-        parts = ([f'{lead}H'] if lead > 0 else []) + [f'{a}{CIGAR_CODE_TO_CHAR[b]}' for b, a in zip(core_c.tolist(), core_n.tolist())] + \
-                ([f'{trail}H'] if trail > 0 else [])
+        parts = ([f'{lead}H'] if lead > 0 else []) + [_core_text(recs[i][6], core_c, core_n)] + ([f'{trail}H'] if trail > 0 else [])
         tig_len = df_tig_fai[qname]
         rev = bool(flag & 0x10)
         rows.append((rname, pos, pos + ref_bp, idx, qname, tig_len - tig_map_end if rev else tig_map_pos,
