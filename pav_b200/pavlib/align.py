@@ -190,7 +190,15 @@ def _core_text(cigar, core_c, core_n):
     """CIGAR text of the ops between the clips, as ``str(length) + op`` per op. That is a substring of the SAM field unless a length
     was written with leading zeros, so the common case costs two regex matches instead of one f-string per op."""
     if _LEADING_ZERO.search(cigar) is None:
-        return cigar[_LEAD_CLIPS.match(cigar).end():_TAIL_CLIPS.search(cigar).start()]
+        end = len(cigar)
+        while end > 0 and cigar[end - 1] in 'SH':      # strip trailing clip ops from the back (a regex anchored at '$' rescans the field)
+            k = end - 1
+            while k > 0 and cigar[k - 1] in _DIGITS:
+                k -= 1
+            if k == end - 1:
+                break
+            end = k
+        return cigar[_LEAD_CLIPS.match(cigar).end():end]
     return ''.join(f'{a}{CIGAR_CODE_TO_CHAR[b]}' for b, a in zip(core_c.tolist(), core_n.tolist()))
 
 
