@@ -182,14 +182,17 @@ def clip_soft_to_hard(cigar_tuples):
 
 
 _LEAD_CLIPS = re.compile(r'^(?:\d+[SH])*')
-_TAIL_CLIPS = re.compile(r'(?:\d+[SH])*$')
-_LEADING_ZERO = re.compile(r'(?<!\d)0\d')
 
 
-def _core_text(cigar, core_c, core_n):
+def _n_digits(n):
+    """Decimal digits of non-negative int64 lengths (< 2^28)."""
+    return 1 + (n >= 10).astype(np.int64) + (n >= 100) + (n >= 1000) + (n >= 10_000) + (n >= 100_000) + (n >= 1_000_000) + (n >= 10_000_000) + (n >= 100_000_000)
+
+
+def _core_text(cigar, core_c, core_n, all_n):
     """CIGAR text of the ops between the clips, as ``str(length) + op`` per op. That is a substring of the SAM field unless a length
     was written with leading zeros, so the common case costs two regex matches instead of one f-string per op."""
-    if _LEADING_ZERO.search(cigar) is None:
+    if int(_n_digits(all_n).sum()) + len(all_n) == len(cigar):    # every length is written without leading zeros
         end = len(cigar)
         while end > 0 and cigar[end - 1] in 'SH':      # strip trailing clip ops from the back (a regex anchored at '$' rescans the field)
             k = end - 1
@@ -253,8 +256,9 @@ def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
             lead = int(n[:body[0]].sum())
             trail = int(n[body[-1] + 1:].sum())
             core_c, core_n = c[body[0]:body[-1] + 1], n[body[0]:body[-1] + 1]
-        ref_bp = int(core_n[np.isin(core_c, (CIGAR_D, CIGAR_N, CIGAR_EQ, CIGAR_X))].sum())
-        qry_bp = int(core_n[np.isin(core_c, (CIGAR_I, CIGAR_EQ, CIGAR_X))].sum())
+        eqx = (core_c == CIGAR_EQ) | (core_c == CIGAR_X)
+        ref_bp = int(core_n[eqx | (core_c == CIGAR_D) | (core_c == CIGAR_N)].sum())
+        qry_bp = int(core_n[eqx | (core_c == CIGAR_I)].sum())
         # pysam: query_alignment_start counts leading soft clips only; hard clips are added back by the reference
         clip_h = int(n[0]) if c[0] == CIGAR_H else 0
         lead_s = 0
@@ -268,7 +272,7 @@ def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
         if lead_s + clip_h != tig_map_pos:
             raise RuntimeError(f'First aligned based from pysam ({lead_s}) does not match clipping ({tig_map_pos}) at alignment record {idx}')
         tig_map_end = tig_map_pos + qry_bp
-        parts = ([f'{lead}H'] if lead > 0 else []) + [_core_text(recs[i][6], core_c, core_n)] + ([f'{trail}H'] if trail > 0 else [])
+        parts = ([f'{lead}H'] if lead > 0 else []) + [_core_text(recs[i][6], core_c, core_n, n)] + ([f'{trail}H'] if trail > 0 else [])
         tig_len = df_tig_fai[qname]
         rev = bool(flag & 0x10)
         rows.append((rname, pos, pos + ref_bp, idx, qname, tig_len - tig_map_end if rev else tig_map_pos,
