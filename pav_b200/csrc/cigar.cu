@@ -713,7 +713,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_parse(const c
         while (p < len) {
             int64_t q = p;
             uint64_t v = 0;
-            while (q < len && s[q] >= '0' && s[q] <= '9') { v = v * 10 + (uint64_t)(s[q] - '0'); q++; }
+            while (q < len && s[q] >= '0' && s[q] <= '9') {
+                v = v * 10 + (uint64_t)(s[q] - '0');
+                if (v > (1ull << 40)) v = 1ull << 40;   // saturate: a run of digits must not wrap back under the 2^28 limit
+                q++;
+            }
             int ecode = 0;
             if (q >= len) ecode = 4;
             else if (q == p) ecode = 2;
@@ -1037,6 +1041,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_call(pavgpu_c
                                  pavgpu_indel_row **indel_out, int64_t *n_indel, pavgpu_cigar_err *err, pavgpu_cigar_stats *stats)
 {
     if (!ref_store || !qry_store) { pav_set_error("cigar_call: store is NULL"); return PAVGPU_ERR_ARG; }
+    if (n_rec > 0 && (!ref_seq_id || !qry_seq_id)) { pav_set_error("cigar_call: sequence ids are NULL"); return PAVGPU_ERR_ARG; }
     for (int32_t i = 0; i < n_rec; i++) {
         if (ref_seq_id[i] < 0 || ref_seq_id[i] >= ref_store->n_seq || qry_seq_id[i] < 0 || qry_seq_id[i] >= qry_store->n_seq) {
             pav_set_error("cigar_call: record %d refers to a sequence id outside its store", i);

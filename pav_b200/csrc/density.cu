@@ -629,6 +629,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
 {
     if (!b || !ref_store || !tig_store) { pav_set_error("density_batch_run: bad argument"); return PAVGPU_ERR_ARG; }
     pavgpu_ctx *ctx = b->ctx;
+    if (ref_store->ctx->device != ctx->device || tig_store->ctx->device != ctx->device) {
+        pav_set_error("density_batch_run: stores live on another device");
+        return PAVGPU_ERR_ARG;
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int k = b->prm.k;

@@ -256,11 +256,15 @@ static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, p
         pavgpu_seqstore_free(s);
         return PAVGPU_ERR_NOMEM;
     }
-    if (n_seq) {
-        CUDA_TRY(cudaMemcpyAsync(s->d_off, s->h_off.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(s->d_len, s->h_len.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int rc = [&]() -> int {
+        if (n_seq) {
+            CUDA_TRY(cudaMemcpyAsync(s->d_off, s->h_off.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(s->d_len, s->h_len.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PAVGPU_OK;
+    }();
+    if (rc) { pavgpu_seqstore_free(s); return rc; }
     *out = s;
     return PAVGPU_OK;
 }

@@ -71,6 +71,16 @@ def test_cigar_parse_host():
         assert off[3] == off[2]  # nothing after the malformed record
 
 
+def test_cigar_parse_oversize_length():
+    from pav_b200 import device
+    ops, off, err = device.parse_cigars(['%d=' % (2 ** 28 - 1)])
+    assert err.code == 0 and int(ops[0] >> 4) == 2 ** 28 - 1
+    # 2^64 + 5 would wrap to a legal length if the digits were accumulated blindly
+    for big in (2 ** 28, 2 ** 32 + 1, 2 ** 64 + 5, 10 ** 40):
+        with pytest.raises(RuntimeError, match='exceeds 2\\^28-1'):
+            device.parse_cigars(['10=', '%d=' % big])
+
+
 def test_cigar_str_to_tuples_errors():
     from pav_b200.pavlib import align
     row = pd.Series({'CIGAR': '20=5Q95=', 'QRY_ID': 'tigA', '#CHROM': 'chrA', 'POS': 0})
