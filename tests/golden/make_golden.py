@@ -360,8 +360,53 @@ def make_align_case():
     print('align sam1', meta['n'], meta.get('bad_m'))
 
 
+def make_density_cli():
+    """What the reference's scripts/density.py process itself says on the existing density cases: exit code, the text it
+    prints for the two soft failures (one on stdout, one on stderr, scripts/density.py:510-527), the pickle's frame layout
+    on stdout, and a .tsv written through the positional outfile argument."""
+    import tempfile
+    env = dict(os.environ)
+    env['PYTHONPATH'] = os.pathsep.join(refenv.pythonpath_entries())
+    out = {}
+    for case in ('exit125_repeat', 'exit125_empty', 'few_informative', 'kat4'):
+        d = os.path.join(HERE, 'density', case)
+        meta = json.load(open(os.path.join(d, 'meta.json')))
+        args = [sys.executable, os.path.join(refenv.REF_ROOT, 'scripts', 'density.py'),
+                '--tigregion', meta['tigregion'], '--refregion', meta['refregion'], '--ref', 'ref.fa', '--tig', 'tig.fa',
+                '-k', str(meta['k']), '-t', '1', '-r', 'true' if meta['rev'] else 'false', '--staterunsmooth', str(meta['srs'])]
+        proc = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, cwd=d)
+        rec = {'returncode': proc.returncode, 'stderr': proc.stderr.decode()}
+        if proc.returncode == 0:
+            df = pickle.loads(codecs.decode(proc.stdout, 'base64'))
+            rec['index_name'] = df.index.name
+            rec['index_equals_INDEX'] = bool((df.index.to_numpy() == df['INDEX'].to_numpy()).all())
+            rec['columns'] = list(df.columns)
+        else:
+            rec['stdout'] = proc.stdout.decode()
+        out[case] = rec
+    d = os.path.join(HERE, 'density', 'few_informative')
+    meta = json.load(open(os.path.join(d, 'meta.json')))
+    with tempfile.TemporaryDirectory() as tmp:
+        tsv = os.path.join(tmp, 'out.tsv')
+        args = [sys.executable, os.path.join(refenv.REF_ROOT, 'scripts', 'density.py'),
+                '--tigregion', meta['tigregion'], '--refregion', meta['refregion'], '--ref', 'ref.fa', '--tig', 'tig.fa',
+                '-k', str(meta['k']), '-r', 'F', tsv]
+        proc = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, cwd=d)
+        out['few_informative_tsv'] = {'returncode': proc.returncode, 'stdout': proc.stdout.decode(), 'tsv': open(tsv).read()}
+        proc = subprocess.run(args[:-1] + [os.path.join(tmp, 'out.csv')], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, cwd=d)
+        out['bad_extension'] = {'returncode': proc.returncode, 'stderr_last': proc.stderr.decode().strip().splitlines()[-1].replace(tmp, 'TMP')}
+        proc = subprocess.run(args[:-3] + ['-r', 'maybe'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, cwd=d)
+        out['bad_bool'] = {'returncode': proc.returncode, 'stderr_last': proc.stderr.decode().strip().splitlines()[-1]}
+    with open(os.path.join(HERE, 'density_cli.json'), 'w') as fh:
+        json.dump(out, fh, indent=1)
+    for k, v in out.items():
+        print('density cli', k, {a: (b if len(str(b)) < 100 else str(b)[:100] + '...') for a, b in v.items()})
+
+
 if __name__ == '__main__':
-    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align'}
+    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli'}
+    if 'density_cli' in what:
+        make_density_cli()
     if 'align' in what:
         make_align_case()
     if 'cigar' in what:

@@ -138,3 +138,44 @@ def test_density_windows_split_requests(monkeypatch):
             assert (a[c] == b[c]).all()
         for c in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
             assert np.array_equal(a[c], b[c], equal_nan=True)
+
+
+def _run_cli(case, extra=(), rflag=None):
+    import subprocess
+    import sys
+    d = os.path.join(GOLDEN, 'density', case)
+    meta = json.load(open(os.path.join(d, 'meta.json')))
+    cli = os.path.join(os.path.dirname(GOLDEN), '..', 'pav_b200', 'scripts', 'density.py')
+    args = [sys.executable, os.path.abspath(cli), '--tigregion', meta['tigregion'], '--refregion', meta['refregion'], '--ref', 'ref.fa',
+            '--tig', 'tig.fa', '-k', str(meta['k']), '-t', '1', '-r', rflag or ('true' if meta['rev'] else 'false'),
+            '--staterunsmooth', str(meta['srs'])] + list(extra)
+    return subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=d, timeout=300)
+
+
+def test_density_cli_process_boundary(tmp_path):
+    """`python3 scripts/density.py ...` spawned the way pavlib/inv.py:249-266 spawns it: exit code, the soft-failure text on the
+    stream the reference uses, the pickled frame on stdout and a .tsv outfile, against the reference's own process."""
+    import codecs
+    import pickle
+    gold = json.load(open(os.path.join(GOLDEN, 'density_cli.json')))
+    for case in ('exit125_repeat', 'exit125_empty'):
+        p = _run_cli(case)
+        assert p.returncode == gold[case]['returncode'] == 125
+        assert p.stdout.decode() == gold[case]['stdout']
+        assert p.stderr.decode() == gold[case]['stderr']
+    for case in ('few_informative', 'kat4'):
+        p = _run_cli(case)
+        assert p.returncode == 0, p.stderr.decode()
+        df = pickle.loads(codecs.decode(p.stdout, 'base64'))
+        assert list(df.columns) == gold[case]['columns'] and df.index.name == gold[case]['index_name']
+        assert (df.index.to_numpy() == df['INDEX'].to_numpy()).all()
+        _, _, _, table = _load(case)
+        for col in ('INDEX', 'STATE_MER', 'STATE', 'KMER'):
+            assert (df[col].to_numpy() == table[col].to_numpy()).all(), col
+        if case == 'kat4':
+            for col in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
+                np.testing.assert_allclose(df[col].to_numpy(), table[col].to_numpy(), rtol=KERN_RTOL, atol=KERN_ATOL, err_msg=col)
+    out = str(tmp_path / 'out.tsv')
+    p = _run_cli('few_informative', extra=[out], rflag='F')
+    assert p.returncode == 0 and p.stdout == b''
+    assert open(out).read() == gold['few_informative_tsv']['tsv']   # integer-only table: the file is byte-identical

@@ -308,3 +308,27 @@ def test_fasta_fetch_into(tmp_path):
     import pytest
     with pytest.raises(KeyError):
         fa.fetch_into('nope', np.zeros(4, np.uint8))
+
+
+def test_density_cli_host_side():
+    """The parts of the scripts/density.py twin that need no GPU: argument errors raised before any work, and the text of the
+    two soft failures, against what the reference's own process printed (tests/golden/density_cli.json)."""
+    import json
+    from pav_b200 import fasta
+    from pav_b200.scripts import density as cli
+    gold = json.load(open(os.path.join(REPO, 'tests', 'golden', 'density_cli.json')))
+    d = os.path.join(REPO, 'tests', 'golden', 'density')
+    base = ['--tigregion', 'tigW:1-1500', '--refregion', 'chrW:1-1500', '--ref', os.path.join(d, 'few_informative', 'ref.fa'),
+            '--tig', os.path.join(d, 'few_informative', 'tig.fa')]
+    with pytest.raises(RuntimeError) as e:
+        cli.main(base + ['-r', 'maybe'])
+    assert 'RuntimeError: ' + str(e.value) == gold['bad_bool']['stderr_last']
+    with pytest.raises(RuntimeError) as e:
+        cli.main(base + ['-r', 'F', 'TMP/out.csv'])
+    assert 'RuntimeError: ' + str(e.value) == gold['bad_extension']['stderr_last']
+    assert [cli.get_bool(s) for s in ('TRUE', 't', '1', 'False', 'f', '0')] == [True, True, True, False, False, False]
+    ref = fasta.Fasta(os.path.join(d, 'exit125_repeat', 'ref.fa')).fetch_array('chrW')
+    n, mer = cli.ref_kmer_failure(ref, 31)
+    assert 'K-mer count exceeds max: {} > {} ({}): {}\n'.format(n, cli.MAX_REF_KMER_COUNT, mer, 'chrW:1-5200') == gold['exit125_repeat']['stderr']
+    ref = fasta.Fasta(os.path.join(d, 'exit125_empty', 'ref.fa')).fetch_array('chrW')
+    assert cli.ref_kmer_failure(ref, 31) is None and cli.ref_kmer_failure(ref[:10], 31) is None
