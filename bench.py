@@ -517,16 +517,17 @@ def run_ours(args, rank, world, local):
     # ---- roofline of the dominant kernel
     n_ops, n_snv, n_indel, n_chunks = int(st.n_ops), int(st.n_snv), int(st.n_indel), int(st.n_chunks)
     peak, peak_src = measured_peak_gbs()
+    hom_name = 'homology_tiled_kernel' if int(st.homology_tiled) else 'homology_kernel'   # picked per batch from the indel density
     if int(st.kernel_launches) <= 2:   # single-pass walk: K1+K2+K3 fused (cigar_walk_kernel)
         kernels = {
             'cigar_walk_kernel': (scan_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 64 * n_indel),
-            'homology_kernel': (hom_ms, (64 + 64) * n_indel),
+            hom_name: (hom_ms, (64 + 64) * n_indel),
         }
     else:
         kernels = {
             'cigar_reduce+chunk_scan': (scan_ms, 4 * n_ops + 24 * n_chunks + 2 * 48 * n_chunks),
             'cigar_emit_kernel': (emit_ms, 4 * n_ops + 24 * n_chunks + 16 * n_snv + 64 * n_indel),
-            'homology_kernel': (hom_ms, (64 + 64) * n_indel),
+            hom_name: (hom_ms, (64 + 64) * n_indel),
         }
     dom = max(kernels, key=lambda k: kernels[k][0])
     dom_ms, dom_bytes = kernels[dom]

@@ -630,6 +630,134 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes 
     dst[3] = make_int4(hom_tr, seq_start, 0, 0);
 }
 
+// K4t: the same scans with the sequence neighbourhood of every warp's 32 indels staged in shared memory.
+// Indels leave the walk in (record, op) order, so the breakpoints of 32 consecutive indels lie within a short span of the
+// reference plane and of the contig plane (C2: 1 indel / 540 bp => ~17 kbp per warp). Reading that span once with 16-byte
+// cp.async copies moves more bytes than the gathers of homology_kernel (~420 against ~310 B per indel at C2), but as full
+// lines at the streaming rate instead of scattered 32-byte sectors at a quarter of it. A warp whose span does not fit its
+// tile (sparse indels, a jump between distant records) keeps the gathers; windows that leave the tile (long tandem-repeat
+// scans) fall through to global memory one by one. The host launches this kernel only when indels are dense enough
+// (pavgpu_cigar_batch_run).
+#ifndef HOM_TILE_WORDS_N
+#define HOM_TILE_WORDS_N 768
+#endif
+constexpr int HOMT_WARPS = 4;
+constexpr int HOMT_THREADS = HOMT_WARPS * 32;
+constexpr int HOM_TILE_WORDS = HOM_TILE_WORDS_N;          // 32-base words per sequence and warp (768 words = 24.5 kbp)
+constexpr int HOM_TILE_MARGIN = 160;                      // bases staged beyond the outermost breakpoints
+constexpr size_t HOMT_SMEM = (size_t)HOMT_WARPS * HOM_TILE_WORDS * 24;   // per warp: 2 x (8 B pack2 + 4 B mask) per word
+static_assert(HOM_TILE_WORDS % 4 == 0, "tiles are copied in 16-byte pieces");
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ long long warp_min_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+__device__ __forceinline__ long long warp_max_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// Word range [w0, w0 + nw) of a plane covering breakpoints lo_g..hi_g (plane base coordinates) plus the margin, 4-word aligned
+// and clamped to the plane; nw = 0 when it does not fit the tile.
+__device__ __forceinline__ void tile_range(long long lo_g, long long hi_g, int64_t plane_words, int64_t &w0, int32_t &nw)
+{
+    long long a = (lo_g - HOM_TILE_MARGIN) >> 5, b = ((hi_g + HOM_TILE_MARGIN) >> 5) + 2;
+    a = max(a, 0ll) & ~3ll;
+    b = min((b + 3) & ~3ll, (long long)plane_words);
+    w0 = a;
+    nw = (b > a && b - a <= HOM_TILE_WORDS) ? (int32_t)(b - a) : 0;
+}
+
+__global__ void __launch_bounds__(HOMT_THREADS, 3)
+homology_tiled_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, int64_t ref_words, int64_t qry_words,
+                      pavgpu_indel_row *__restrict__ rows)
+{
+    extern __shared__ __align__(16) unsigned char hom_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *s_rp = reinterpret_cast<uint64_t *>(hom_smem + (size_t)warp * HOM_TILE_WORDS * 24);
+    uint64_t *s_qp = s_rp + HOM_TILE_WORDS;
+    uint32_t *s_rm = reinterpret_cast<uint32_t *>(s_qp + HOM_TILE_WORDS);
+    uint32_t *s_qm = s_rm + HOM_TILE_WORDS;
+    const int64_t i = (int64_t)blockIdx.x * HOMT_THREADS + threadIdx.x;
+    if ((int64_t)blockIdx.x * HOMT_THREADS + (threadIdx.x & ~31) >= n_indel) return;   // whole warp past the end
+    const bool live = i < n_indel;
+    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + (live ? i : n_indel - 1));   // idle lanes of the last warp repeat the last stub
+    const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
+    const int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
+    OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, s_rp, s_rm, 0, 0};
+    OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, s_qp, s_qm, 0, 0};
+    const int32_t L = (int32_t)Q.len;
+    {
+        // span of the warp's breakpoints in plane coordinates; the SV sequence right of the breakpoint is covered up to 256 bases
+        const int32_t nn = min(n, 256);
+        const long long gr = R.base + pr;
+        const long long gq0 = Q.rev ? Q.base + ((long long)L - 1 - pq - nn) : Q.base + pq;
+        const long long gq1 = Q.rev ? Q.base + ((long long)L - 1 - pq) : Q.base + pq + nn;
+        int32_t nw_r, nw_q;
+        tile_range(warp_min_ll(gr), warp_max_ll(gr + nn), ref_words, R.t_w0, nw_r);
+        tile_range(warp_min_ll(gq0), warp_max_ll(gq1), qry_words, Q.t_w0, nw_q);
+        for (int k = lane; k < nw_r / 2; k += 32) cp_async16(s_rp + 2 * k, ref.pack2 + R.t_w0 + 2 * k);
+        for (int k = lane; k < nw_q / 2; k += 32) cp_async16(s_qp + 2 * k, qry.pack2 + Q.t_w0 + 2 * k);
+        for (int k = lane; k < nw_r / 4; k += 32) cp_async16(s_rm + 4 * k, ref.nmask + R.t_w0 + 4 * k);
+        for (int k = lane; k < nw_q / 4; k += 32) cp_async16(s_qm + 4 * k, qry.nmask + Q.t_w0 + 4 * k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        R.t_nw1 = max(nw_r - 1, 0);
+        Q.t_nw1 = max(nw_q - 1, 0);
+    }
+    if (!live) return;
+    const bool ins = (svtype == 0);
+    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
+    int32_t sp = pr, sq = pq;
+#pragma unroll 1
+    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {   // same five scans as homology_kernel
+        const bool on_ref = sc <= 2;
+        const int left = (sc == 0 || sc == 1 || sc == 3);
+        int64_t p;
+        if (sc == 0) p = (int64_t)pr - 1;
+        else if (sc == 1) p = (int64_t)sp - 1;
+        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
+        else if (sc == 3) p = (int64_t)sq - 1;
+        else p = ins ? (int64_t)sq + n : (int64_t)sq;
+        const OSeq &T = on_ref ? R : Q;
+        const OSeq &V = ins ? Q : R;
+        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;
+        int h = dev_homology_tiled(T, p, V, v0, n, left);
+        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
+        else if (sc == 1) hom_rl = h;
+        else if (sc == 2) hom_rr = h;
+        else if (sc == 3) hom_tl = h;
+        else hom_tr = h;
+    }
+    int32_t pos, end, qry_pos, qry_end, seq_start;
+    if (ins) {
+        pos = sp; end = sp + 1;
+        if (Q.rev) { qry_end = L - sq; qry_pos = qry_end - n; } else { qry_pos = sq; qry_end = sq + n; }
+        seq_start = sq;
+    } else {
+        pos = pr; end = pr + n;
+        qry_pos = Q.rev ? L - sq : sq;
+        qry_end = qry_pos + 1;
+        seq_start = pr;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(rec, op_idx, svtype, n);
+    dst[1] = make_int4(pos, end, qry_pos, qry_end);
+    dst[2] = make_int4(ls, hom_rl, hom_rr, hom_tl);
+    dst[3] = make_int4(hom_tr, seq_start, 0, 0);
+}
+
 __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,
                                       int32_t *__restrict__ left, int32_t *__restrict__ right)
 {
@@ -667,6 +795,7 @@ struct pavgpu_cigar_batch {
     bool rows_in_arena;
     int64_t n_snv, n_indel;
     int64_t host_n_snv, host_n_indel;   // counted on the host while the ops were staged
+    int64_t host_ref_span;              // reference bases the records advance over (same pass): indel density picks the homology kernel
     ulonglong2 *d_desc;
     int64_t *d_rec_snv_off, *d_rec_indel_off;   // first row slot of every record (host-counted)
     int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (host-built index)
@@ -676,6 +805,7 @@ struct pavgpu_cigar_batch {
     std::vector<int32_t> h_ref_id, h_qry_id;
     std::vector<uint8_t> h_rev;
     bool fused;
+    bool hom_tiled;                      // which homology kernel the last run used
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
@@ -786,13 +916,14 @@ static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_i
     std::vector<int64_t> rec_snv_off((size_t)n_rec + 1), rec_indel_off((size_t)n_rec + 1);
     for (int32_t r = 0; r < n_rec; r++) {
         rec_snv_off[r] = b->host_n_snv; rec_indel_off[r] = b->host_n_indel;
-        int64_t ns = 0, ni = 0;
+        int64_t ns = 0, ni = 0, ra = 0;
         for (int64_t i = op_off[r]; i < op_off[r + 1]; i++) {
             const uint32_t op = ops[i], code = op & 15u;
             ns += (code == PAVGPU_OP_X) ? (op >> 4) : 0u;
             ni += (code == PAVGPU_OP_I) | (code == PAVGPU_OP_D);
+            ra += ((REF_ADV_MASK >> code) & 1u) ? (op >> 4) : 0u;
         }
-        b->host_n_snv += ns; b->host_n_indel += ni;
+        b->host_n_snv += ns; b->host_n_indel += ni; b->host_ref_span += ra;
     }
     rec_snv_off[n_rec] = b->host_n_snv; rec_indel_off[n_rec] = b->host_n_indel;
     std::vector<int32_t> chunk_rec((size_t)std::max<int64_t>(b->n_chunks, 1), 0);
@@ -873,6 +1004,37 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
     return batch_create(ctx, n_rec, ref_seq_id, qry_seq_id, pos, rev, ops, op_off, false, out);
 }
 
+// K4 launch. Dense indels (C2: one per 540 reference bases) go through the tiled kernel, which streams the span of every warp's
+// indels into shared memory; sparse ones (a human assembly: one per several kbp) keep the gathers, where a span would move an
+// order of magnitude more bytes than the sectors actually needed. PAVGPU_HOMOLOGY_TILED=0/1 forces either kernel (A/B timing).
+constexpr int64_t HOM_TILED_MAX_SPACING = 700;   // mean reference bases per indel up to which 32 indels fit a 24.5 kbp tile
+constexpr int64_t HOM_TILED_MIN_INDELS = 4096;
+
+static int launch_homology(pavgpu_cigar_batch *b, cudaStream_t st, const pavgpu_seqstore *ref_store, const pavgpu_seqstore *qry_store)
+{
+    const SeqPlanes pl_ref = planes_of(ref_store), pl_qry = planes_of(qry_store);
+    const char *force = getenv("PAVGPU_HOMOLOGY_TILED");
+    bool tiled = b->n_indel >= HOM_TILED_MIN_INDELS && b->host_ref_span <= HOM_TILED_MAX_SPACING * b->n_indel;
+    if (force && (force[0] == '0' || force[0] == '1')) tiled = force[0] == '1';
+    b->hom_tiled = tiled;
+    if (tiled) {
+        static bool attr_set[64] = {};
+        const int dev = b->ctx->device;
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(homology_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOMT_SMEM));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        const unsigned hb = (unsigned)((b->n_indel + HOMT_THREADS - 1) / HOMT_THREADS);
+        homology_tiled_kernel<<<hb, HOMT_THREADS, HOMT_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, ref_store->total_bases / 32,
+                                                                  qry_store->total_bases / 32, b->d_indel);
+    } else {
+        const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
+        homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PAVGPU_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pavgpu_cigar_batch *b, const pavgpu_seqstore *ref_store, const pavgpu_seqstore *qry_store,
                                       pavgpu_cigar_stats *stats)
 {
@@ -902,7 +1064,6 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         if (b->n_rec) CUDA_TRY(cudaMemcpyAsync(b->d_recdesc, b->h_recdesc.data(), (size_t)b->n_rec * sizeof(RecDesc), cudaMemcpyHostToDevice, st));
         b->recdesc_ref_uid = ref_store->uid; b->recdesc_qry_uid = qry_store->uid;
     }
-    const SeqPlanes pl_ref = planes_of(ref_store), pl_qry = planes_of(qry_store);
     unsigned long long init = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(b->d_first_illegal, &init, 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 16, st));
@@ -920,10 +1081,9 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         b->n_snv = b->host_n_snv; b->n_indel = b->host_n_indel;
         if (b->n_indel > 0) {
-            const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
-            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
+            int hrc = launch_homology(b, st, ref_store, qry_store);
+            if (hrc) return hrc;
             launches++;
-            CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         int64_t tot[2];
@@ -964,10 +1124,9 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
         if (b->n_indel > 0) {
-            const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
-            homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
+            int hrc = launch_homology(b, st, ref_store, qry_store);
+            if (hrc) return hrc;
             launches++;
-            CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         CUDA_TRY(cudaMemcpyAsync(&b->first_illegal, b->d_first_illegal, 8, cudaMemcpyDeviceToHost, st));
@@ -987,6 +1146,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         stats->ms_kernels = ev_ms(ctx->ev[0], ctx->ev[4]);
         stats->n_ops = b->n_ops; stats->n_snv = b->n_snv; stats->n_indel = b->n_indel; stats->n_chunks = b->n_chunks;
         stats->kernel_launches = launches;
+        stats->homology_tiled = (b->n_indel > 0 && b->hom_tiled) ? 1 : 0;
     }
     return PAVGPU_OK;
 }

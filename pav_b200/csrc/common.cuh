@@ -170,6 +170,12 @@ struct OSeq {
     int64_t base;  // offset of the sequence in the planes
     int64_t len;
     int rev;
+    // Optional staged copy of plane words [t_w0, t_w0 + t_nw1 + 1) in shared memory (homology_tiled_kernel); windows whose two
+    // words lie inside are served from it, all others from global memory. t_nw1 == 0: no tile.
+    const uint64_t *t_pack2;
+    const uint32_t *t_nmask;
+    int64_t t_w0;
+    int32_t t_nw1;
 };
 
 // Upper-cased base as 0..3 (ACGT) or 4 (anything else, or out of range).
@@ -196,6 +202,7 @@ __device__ __forceinline__ uint64_t revcomp32(uint64_t x)
 // Forward-strand window: bases f .. f+31 of a sequence (base i of the window in bits [62-2i, 64-2i) of
 // `bases`, bit i of `mask` set when that base is not ACGT or lies outside [0, len)). Positions inside a sequence
 // are 32-bit (sequences are shorter than 2^31, checked when the store is built); only the plane offset is 64-bit.
+template <bool TILED = false>
 __device__ __forceinline__ void fwd_window(const OSeq &s, int32_t f, uint64_t &bases, uint32_t &mask)
 {
     const int32_t len = (int32_t)s.len;
@@ -204,9 +211,18 @@ __device__ __forceinline__ void fwd_window(const OSeq &s, int32_t f, uint64_t &b
     const int64_t g = s.base + (int64_t)(f + lead);
     const int64_t w = g >> 5;
     const int sh = (int)(g & 31);
-    const uint64_t hi = __ldg(s.pack2 + w), lo = __ldg(s.pack2 + w + 1);
+    uint64_t hi, lo;
+    uint32_t m0, m1;
+    if (TILED && (uint64_t)(w - s.t_w0) < (uint64_t)s.t_nw1) {   // words w and w+1 are staged
+        const int o = (int)(w - s.t_w0);
+        hi = s.t_pack2[o]; lo = s.t_pack2[o + 1];
+        m0 = s.t_nmask[o]; m1 = s.t_nmask[o + 1];
+    } else {
+        hi = __ldg(s.pack2 + w); lo = __ldg(s.pack2 + w + 1);
+        m0 = __ldg(s.nmask + w); m1 = __ldg(s.nmask + w + 1);
+    }
     uint64_t b = sh ? ((hi << (2 * sh)) | (lo >> (64 - 2 * sh))) : hi;
-    uint32_t m = __funnelshift_r(__ldg(s.nmask + w), __ldg(s.nmask + w + 1), sh);
+    uint32_t m = __funnelshift_r(m0, m1, sh);
     if (lead | (f + 32 > len)) {               // sequence edges only
         if (lead) { b >>= 2 * lead; m = (m << lead) | ((1u << lead) - 1u); }
         const int over = f + 32 - len;         // window positions past the sequence end
@@ -219,11 +235,12 @@ __device__ __forceinline__ void fwd_window(const OSeq &s, int32_t f, uint64_t &b
 // (An out-of-line variant of this and of dev_homology_raw was measured on B200: 0.176 ms vs 0.148 ms inlined for the
 // C2 homology kernel -- call overhead and spills cost more than the instruction-fetch stalls they remove. 16-base
 // windows with 32-bit funnel shifts were measured too: 0.147 ms vs 0.102 ms, twice the loop trips for long scans.)
+template <bool TILED = false>
 __device__ __forceinline__ void oseq_window(const OSeq &s, int32_t t, uint64_t &bases, uint32_t &mask)
 {
-    if (!s.rev) { fwd_window(s, t, bases, mask); return; }
+    if (!s.rev) { fwd_window<TILED>(s, t, bases, mask); return; }
     uint64_t b; uint32_t m;
-    fwd_window(s, (int32_t)s.len - t - 32, b, m);
+    fwd_window<TILED>(s, (int32_t)s.len - t - 32, b, m);
     bases = revcomp32(b);
     mask = __brev(m);
 }
@@ -232,6 +249,7 @@ __device__ __forceinline__ void oseq_window(const OSeq &s, int32_t t, uint64_t &
 //   left == 0: common prefix of A[a..] and B[b..]        (window i covers a+32i .. a+32i+31)
 //   left != 0: common suffix of A[..a] and B[..b]         (window i covers a-32i-31 .. a-32i)
 // Stops at the first mismatch, non-ACGT base or sequence end on either side.
+template <bool TILED = false>
 __device__ __forceinline__ int32_t common_extension(const OSeq &A, int32_t a, const OSeq &B, int32_t b, int32_t limit, int left)
 {
     int32_t h = 0;
@@ -239,8 +257,8 @@ __device__ __forceinline__ int32_t common_extension(const OSeq &A, int32_t a, co
     int32_t pa = a0, pb = b0;
     while (h < limit) {
         uint64_t wa, wb; uint32_t ma, mb;
-        oseq_window(A, pa, wa, ma);
-        oseq_window(B, pb, wb, mb);
+        oseq_window<TILED>(A, pa, wa, ma);
+        oseq_window<TILED>(B, pb, wb, mb);
         uint64_t x = wa ^ wb;
         uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;      // one bit per differing base
         uint32_t m = ma | mb;
@@ -270,14 +288,24 @@ static __device__ __forceinline__ int dev_homology_raw(const uint64_t *t_pack2, 
                                                     int64_t p, const uint64_t *v_pack2, const uint32_t *v_nmask, int64_t v_base, int64_t v_len,
                                                     int v_rev, int64_t v0, int n, int left)
 {
-    const OSeq T{t_pack2, t_nmask, t_base, t_len, t_rev};
-    const OSeq V{v_pack2, v_nmask, v_base, v_len, v_rev};
+    const OSeq T{t_pack2, t_nmask, t_base, t_len, t_rev, nullptr, nullptr, 0, 0};
+    const OSeq V{v_pack2, v_nmask, v_base, v_len, v_rev, nullptr, nullptr, 0, 0};
     if (n <= 0 || p < 0 || p >= T.len) return 0;
     const int32_t p32 = (int32_t)p, v32 = (int32_t)v0;
     int32_t h = common_extension(T, p32, V, left ? v32 + n - 1 : v32, n, left);
     if (h < n) return h;
     // the flank is shorter than 2^31, so the self-comparison ends at a sequence edge long before the cap
     return n + common_extension(T, left ? p32 - n : p32 + n, T, p32, 0x7fffffff - n, left);
+}
+
+// The same scan over sequences that may carry a staged tile.
+static __device__ __forceinline__ int dev_homology_tiled(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n, int left)
+{
+    if (n <= 0 || p < 0 || p >= T.len) return 0;
+    const int32_t p32 = (int32_t)p, v32 = (int32_t)v0;
+    int32_t h = common_extension<true>(T, p32, V, left ? v32 + n - 1 : v32, n, left);
+    if (h < n) return h;
+    return n + common_extension<true>(T, left ? p32 - n : p32 + n, T, p32, 0x7fffffff - n, left);
 }
 
 __device__ __forceinline__ int dev_left_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)

@@ -169,3 +169,62 @@ def test_multipass_walk_matches_single_pass(tmp_path, monkeypatch):
     for a, b, c in zip(single, multi, orc):
         assert tsv_bytes(a) == tsv_bytes(b) == tsv_bytes(c)
         assert (a.index == b.index).all() and (a.index == c.index).all()
+
+
+@pytest.mark.parametrize('case', CIGAR_CASES)
+def test_cigar_golden_gpu_tiled_homology(case, monkeypatch):
+    """The golden cases again with the shared-memory-tile homology kernel forced (it is picked automatically only for large,
+    dense batches): partial warps, REV records, N runs, tandem repeats that leave the tile."""
+    monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', '1')
+    test_cigar_golden_gpu(case)
+
+
+@pytest.mark.parametrize('seed,kw', [
+    (11, dict(n_chrom=2, chrom_len=400_000, n_contig=40, contig_len=20_000, edit_rate=0.01, rev_frac=0.5)),
+    (12, dict(n_chrom=1, chrom_len=300_000, n_contig=3, contig_len=100_000, edit_rate=0.02, rev_frac=0.5, clip=(11, 3),
+              soft_mask_frac=0.5, n_block_frac=0.05)),
+    (13, dict(n_chrom=3, chrom_len=60_000, n_contig=180, contig_len=1_000, edit_rate=0.004, rev_frac=0.3)),  # warps span many records
+    (14, dict(n_chrom=1, chrom_len=2_000_000, n_contig=1, contig_len=2_000_000, edit_rate=0.01, rev_frac=1.0)),
+    (16, dict(n_chrom=1, chrom_len=3_000_000, n_contig=3, contig_len=1_000_000, edit_rate=0.0004, rev_frac=0.5)),  # sparse: spans overflow the tile
+])
+def test_homology_kernels_agree(tmp_path, monkeypatch, seed, kw):
+    """Gather kernel, tiled kernel and the oracle give the same indel rows; the stats say which kernel ran."""
+    from oracle import pyoracle
+    from pav_b200.pavlib import cigarcall
+    ref_fa, tig_fa, df = _workload(tmp_path, seed, **kw)
+    orc = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
+    for mode in ('0', '1'):
+        monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
+        got = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
+        assert cigarcall.last_stats['homology_tiled'] == int(mode)
+        assert tsv_bytes(got[1]) == tsv_bytes(orc[1]) and tsv_bytes(got[0]) == tsv_bytes(orc[0])
+        assert got[1].shape[0] > 0
+
+
+def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
+    """A C2-shaped slice (1 indel / ~540 bp) picks the tiled kernel by itself, a sparse batch the gathers; both equal the oracle."""
+    from oracle import pyoracle
+    from pav_b200 import device
+    monkeypatch.delenv('PAVGPU_HOMOLOGY_TILED', raising=False)
+    ref, tigs, df = synth.config_c2(n_contig=100)
+    ref_fa, tig_fa, _ = synth.write_cigar_workload(str(tmp_path), ref, tigs, df)
+    _, o_indel, _ = pyoracle.walk_rows(df, ref_fa, tig_fa)
+    ctx = device.get_context()
+    names_r, names_t = list(ref), list(tigs)
+    rs = device.SeqStore(ctx, names_r, [ref[n] for n in names_r])
+    ts = device.SeqStore(ctx, names_t, [tigs[n] for n in names_t])
+    ops, op_off, _ = device.parse_cigars(df['CIGAR'].tolist())
+    rid = np.array([names_r.index(c) for c in df['#CHROM']], np.int32)
+    qid = np.array([names_t.index(c) for c in df['QRY_ID']], np.int32)
+    out = {}
+    for mode in (None, '0'):
+        if mode is not None:
+            monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
+        _, indel, err, st = device.cigar_call(ctx, rs, ts, rid, qid, df['POS'].to_numpy(np.int32), df['REV'].to_numpy(np.uint8), ops, op_off)
+        assert err.code == 0
+        out[mode] = (indel.copy(), st.homology_tiled)
+    assert out[None][1] == 1 and out['0'][1] == 0
+    assert out[None][0].tobytes() == out['0'][0].tobytes()
+    for f in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r', 'hom_tig_l', 'hom_tig_r', 'rec', 'svtype'):
+        assert (out[None][0][f] == o_indel[f]).all(), f
+    rs.close(); ts.close()
