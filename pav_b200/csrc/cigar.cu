@@ -636,8 +636,8 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes 
 // cp.async copies moves more bytes than the gathers of homology_kernel (~420 against ~310 B per indel at C2), but as full
 // lines at the streaming rate instead of scattered 32-byte sectors at a quarter of it. A warp whose span does not fit its
 // tile (sparse indels, a jump between distant records) keeps the gathers; windows that leave the tile (long tandem-repeat
-// scans) fall through to global memory one by one. The host launches this kernel only when indels are dense enough
-// (pavgpu_cigar_batch_run).
+// scans) fall through to global memory one by one. Opt-in (PAVGPU_HOMOLOGY_TILED, see launch_homology): on C2 it trades the
+// DRAM bound of the gathers for an issue-latency bound at 12 warps/SM and is slower as it stands.
 #ifndef HOM_TILE_WORDS_N
 #define HOM_TILE_WORDS_N 768
 #endif
@@ -1004,9 +1004,13 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
     return batch_create(ctx, n_rec, ref_seq_id, qry_seq_id, pos, rev, ops, op_off, false, out);
 }
 
-// K4 launch. Dense indels (C2: one per 540 reference bases) go through the tiled kernel, which streams the span of every warp's
-// indels into shared memory; sparse ones (a human assembly: one per several kbp) keep the gathers, where a span would move an
-// order of magnitude more bytes than the sectors actually needed. PAVGPU_HOMOLOGY_TILED=0/1 forces either kernel (A/B timing).
+// K4 launch. The gather kernel is the default. PAVGPU_HOMOLOGY_TILED=1 selects the tiled kernel for every batch,
+// PAVGPU_HOMOLOGY_TILED=auto for batches whose indels are dense enough for a warp's span to fit its tile (C2: one per 540
+// reference bases; a human assembly has one per several kbp, where a span would move an order of magnitude more bytes than the
+// sectors actually needed). Measured on C2 (B200, profiles/r01_ncu_homology_tiled.txt): the tile does remove the DRAM bound
+// (DRAM 19 % busy, long-scoreboard stall 0.7 against 14 for the gathers) but at 12 warps/SM (18 KB of tile per warp) the kernel
+// is then bound by issue latency on its 58 M warp instructions: 0.123 ms against 0.082 ms. It stays in the library, bit-exact
+// and tested, as the base for the next step (cooperative tails + mask-free tiles).
 constexpr int64_t HOM_TILED_MAX_SPACING = 700;   // mean reference bases per indel up to which 32 indels fit a 24.5 kbp tile
 constexpr int64_t HOM_TILED_MIN_INDELS = 4096;
 
@@ -1014,8 +1018,9 @@ static int launch_homology(pavgpu_cigar_batch *b, cudaStream_t st, const pavgpu_
 {
     const SeqPlanes pl_ref = planes_of(ref_store), pl_qry = planes_of(qry_store);
     const char *force = getenv("PAVGPU_HOMOLOGY_TILED");
-    bool tiled = b->n_indel >= HOM_TILED_MIN_INDELS && b->host_ref_span <= HOM_TILED_MAX_SPACING * b->n_indel;
-    if (force && (force[0] == '0' || force[0] == '1')) tiled = force[0] == '1';
+    bool tiled = false;
+    if (force && force[0] == '1') tiled = true;
+    else if (force && force[0] == 'a') tiled = b->n_indel >= HOM_TILED_MIN_INDELS && b->host_ref_span <= HOM_TILED_MAX_SPACING * b->n_indel;
     b->hom_tiled = tiled;
     if (tiled) {
         static bool attr_set[64] = {};

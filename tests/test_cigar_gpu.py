@@ -202,7 +202,8 @@ def test_homology_kernels_agree(tmp_path, monkeypatch, seed, kw):
 
 
 def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
-    """A C2-shaped slice (1 indel / ~540 bp) picks the tiled kernel by itself, a sparse batch the gathers; both equal the oracle."""
+    """A C2-shaped slice (1 indel / ~540 bp): gathers by default, the tiled kernel under PAVGPU_HOMOLOGY_TILED=auto (dense batch)
+    and =1; all three give the same bytes and equal the oracle."""
     from oracle import pyoracle
     from pav_b200 import device
     monkeypatch.delenv('PAVGPU_HOMOLOGY_TILED', raising=False)
@@ -217,14 +218,14 @@ def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
     rid = np.array([names_r.index(c) for c in df['#CHROM']], np.int32)
     qid = np.array([names_t.index(c) for c in df['QRY_ID']], np.int32)
     out = {}
-    for mode in (None, '0'):
+    for mode in (None, 'auto', '1'):
         if mode is not None:
             monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
         _, indel, err, st = device.cigar_call(ctx, rs, ts, rid, qid, df['POS'].to_numpy(np.int32), df['REV'].to_numpy(np.uint8), ops, op_off)
         assert err.code == 0
         out[mode] = (indel.copy(), st.homology_tiled)
-    assert out[None][1] == 1 and out['0'][1] == 0
-    assert out[None][0].tobytes() == out['0'][0].tobytes()
+    assert out[None][1] == 0 and out['auto'][1] == 1 and out['1'][1] == 1
+    assert out[None][0].tobytes() == out['auto'][0].tobytes() == out['1'][0].tobytes()
     for f in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r', 'hom_tig_l', 'hom_tig_r', 'rec', 'svtype'):
         assert (out[None][0][f] == o_indel[f]).all(), f
     rs.close(); ts.close()
