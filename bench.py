@@ -517,7 +517,7 @@ def run_ours(args, rank, world, local):
     # ---- roofline of the dominant kernel
     n_ops, n_snv, n_indel, n_chunks = int(st.n_ops), int(st.n_snv), int(st.n_indel), int(st.n_chunks)
     peak, peak_src = measured_peak_gbs()
-    hom_name = 'homology_tiled_kernel' if int(st.homology_tiled) else 'homology_kernel'   # picked per batch from the indel density
+    hom_name = ['homology_kernel', 'homology_tiled_kernel', 'homology_nbr_kernel'][int(st.homology_tiled)]   # opt-in variants via PAVGPU_HOMOLOGY_*
     if int(st.kernel_launches) <= 2:   # single-pass walk: K1+K2+K3 fused (cigar_walk_kernel)
         kernels = {
             'cigar_walk_kernel': (scan_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 64 * n_indel),

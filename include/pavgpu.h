@@ -140,7 +140,7 @@ typedef struct {
     float ms_scan, ms_emit, ms_homology;    /* per-kernel breakdown */
     int64_t n_ops, n_snv, n_indel, n_chunks;
     int32_t kernel_launches;
-    int32_t homology_tiled;                 /* 1: the homology kernel staged every warp's sequence span in shared memory (dense indels) */
+    int32_t homology_tiled;                 /* homology kernel used: 0 gathers (default), 1 per-warp shared-memory tiles, 2 per-indel neighbourhoods */
 } pavgpu_cigar_stats;
 
 /* Upload a batch of alignment records (SoA). All arrays have n_rec entries except op_off (n_rec+1).

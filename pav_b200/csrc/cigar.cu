@@ -758,6 +758,110 @@ homology_tiled_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
     dst[3] = make_int4(hom_tr, seq_start, 0, 0);
 }
 
+// K4n (opt-in, PAVGPU_HOMOLOGY_NBR=1): thread per indel like homology_kernel, but the 256-base neighbourhood of the breakpoint
+// in each sequence (8 plane words = two 32-byte sectors, 8 mask words = one or two) is copied into a private shared-memory slot
+// right after the stub is read -- all sectors of an indel requested at once instead of one dependent window at a time, and
+// each fetched once instead of once per scan that touches it. Windows outside the neighbourhood (long SVs, tandem repeats) use
+// the global loads. Slots are padded (9 / 9 words) so a warp's accesses spread over the banks.
+constexpr int NBR_WORDS = 8;
+constexpr int NBR_P_STRIDE = 72;   // bytes per thread and sequence: 8 x 8 B + 8 B padding
+constexpr int NBR_M_STRIDE = 36;   //                                8 x 4 B + 4 B padding
+constexpr size_t NBR_SMEM = (size_t)2 * HOM_THREADS * (NBR_P_STRIDE + NBR_M_STRIDE);
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// First word of the 8-word neighbourhood around plane coordinate c (sector-aligned, inside the plane); -1 if the plane is too small.
+__device__ __forceinline__ int64_t nbr_first_word(long long c, int64_t plane_words)
+{
+    if (plane_words < NBR_WORDS) return -1;
+    long long w = ((c - 64) >> 5) & ~3ll;
+    w = max(w, 0ll);
+    return (int64_t)min(w, (long long)plane_words - NBR_WORDS);
+}
+
+__global__ void __launch_bounds__(HOM_THREADS, 4)
+homology_nbr_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, int64_t ref_words, int64_t qry_words,
+                    pavgpu_indel_row *__restrict__ rows)
+{
+    extern __shared__ __align__(16) unsigned char nbr_smem[];
+    const int64_t i = (int64_t)blockIdx.x * HOM_THREADS + threadIdx.x;
+    if (i >= n_indel) return;
+    unsigned char *pbase = nbr_smem, *mbase = nbr_smem + (size_t)2 * HOM_THREADS * NBR_P_STRIDE;
+    uint64_t *s_rp = reinterpret_cast<uint64_t *>(pbase + (size_t)threadIdx.x * NBR_P_STRIDE);
+    uint64_t *s_qp = reinterpret_cast<uint64_t *>(pbase + (size_t)(HOM_THREADS + threadIdx.x) * NBR_P_STRIDE);
+    uint32_t *s_rm = reinterpret_cast<uint32_t *>(mbase + (size_t)threadIdx.x * NBR_M_STRIDE);
+    uint32_t *s_qm = reinterpret_cast<uint32_t *>(mbase + (size_t)(HOM_THREADS + threadIdx.x) * NBR_M_STRIDE);
+    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
+    const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
+    const int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
+    OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, s_rp, s_rm, 0, 0};
+    OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, s_qp, s_qm, 0, 0};
+    const int32_t L = (int32_t)Q.len;
+    {
+        const int64_t wr = nbr_first_word(R.base + pr, ref_words);
+        const int64_t wq = nbr_first_word(Q.rev ? Q.base + ((long long)L - 1 - pq) : Q.base + pq, qry_words);
+        if (wr >= 0) {
+#pragma unroll
+            for (int k = 0; k < NBR_WORDS; k++) { cp_async8(s_rp + k, ref.pack2 + wr + k); cp_async4(s_rm + k, ref.nmask + wr + k); }
+        }
+        if (wq >= 0) {
+#pragma unroll
+            for (int k = 0; k < NBR_WORDS; k++) { cp_async8(s_qp + k, qry.pack2 + wq + k); cp_async4(s_qm + k, qry.nmask + wq + k); }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (wr >= 0) { R.t_w0 = wr; R.t_nw1 = NBR_WORDS - 1; }
+        if (wq >= 0) { Q.t_w0 = wq; Q.t_nw1 = NBR_WORDS - 1; }
+    }
+    const bool ins = (svtype == 0);
+    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
+    int32_t sp = pr, sq = pq;
+#pragma unroll 1
+    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {   // same five scans as homology_kernel
+        const bool on_ref = sc <= 2;
+        const int left = (sc == 0 || sc == 1 || sc == 3);
+        int64_t p;
+        if (sc == 0) p = (int64_t)pr - 1;
+        else if (sc == 1) p = (int64_t)sp - 1;
+        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
+        else if (sc == 3) p = (int64_t)sq - 1;
+        else p = ins ? (int64_t)sq + n : (int64_t)sq;
+        const OSeq &T = on_ref ? R : Q;
+        const OSeq &V = ins ? Q : R;
+        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;
+        int h = dev_homology_tiled(T, p, V, v0, n, left);
+        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
+        else if (sc == 1) hom_rl = h;
+        else if (sc == 2) hom_rr = h;
+        else if (sc == 3) hom_tl = h;
+        else hom_tr = h;
+    }
+    int32_t pos, end, qry_pos, qry_end, seq_start;
+    if (ins) {
+        pos = sp; end = sp + 1;
+        if (Q.rev) { qry_end = L - sq; qry_pos = qry_end - n; } else { qry_pos = sq; qry_end = sq + n; }
+        seq_start = sq;
+    } else {
+        pos = pr; end = pr + n;
+        qry_pos = Q.rev ? L - sq : sq;
+        qry_end = qry_pos + 1;
+        seq_start = pr;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(rec, op_idx, svtype, n);
+    dst[1] = make_int4(pos, end, qry_pos, qry_end);
+    dst[2] = make_int4(ls, hom_rl, hom_rr, hom_tl);
+    dst[3] = make_int4(hom_tr, seq_start, 0, 0);
+}
+
 __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,
                                       int32_t *__restrict__ left, int32_t *__restrict__ right)
 {
@@ -805,7 +909,7 @@ struct pavgpu_cigar_batch {
     std::vector<int32_t> h_ref_id, h_qry_id;
     std::vector<uint8_t> h_rev;
     bool fused;
-    bool hom_tiled;                      // which homology kernel the last run used
+    int hom_kernel;                      // homology kernel of the last run: 0 gathers, 1 warp tiles, 2 per-indel neighbourhoods
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
@@ -1021,8 +1125,20 @@ static int launch_homology(pavgpu_cigar_batch *b, cudaStream_t st, const pavgpu_
     bool tiled = false;
     if (force && force[0] == '1') tiled = true;
     else if (force && force[0] == 'a') tiled = b->n_indel >= HOM_TILED_MIN_INDELS && b->host_ref_span <= HOM_TILED_MAX_SPACING * b->n_indel;
-    b->hom_tiled = tiled;
-    if (tiled) {
+    b->hom_kernel = tiled ? 1 : 0;
+    const char *nbr = getenv("PAVGPU_HOMOLOGY_NBR");
+    if (!tiled && nbr && nbr[0] == '1') {
+        static bool nbr_attr_set[64] = {};
+        const int dev = b->ctx->device;
+        if (dev < 0 || dev >= 64 || !nbr_attr_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(homology_nbr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NBR_SMEM));
+            if (dev >= 0 && dev < 64) nbr_attr_set[dev] = true;
+        }
+        const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
+        homology_nbr_kernel<<<hb, HOM_THREADS, NBR_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, ref_store->total_bases / 32,
+                                                              qry_store->total_bases / 32, b->d_indel);
+        b->hom_kernel = 2;
+    } else if (tiled) {
         static bool attr_set[64] = {};
         const int dev = b->ctx->device;
         if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -1151,7 +1267,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         stats->ms_kernels = ev_ms(ctx->ev[0], ctx->ev[4]);
         stats->n_ops = b->n_ops; stats->n_snv = b->n_snv; stats->n_indel = b->n_indel; stats->n_chunks = b->n_chunks;
         stats->kernel_launches = launches;
-        stats->homology_tiled = (b->n_indel > 0 && b->hom_tiled) ? 1 : 0;
+        stats->homology_tiled = b->n_indel > 0 ? b->hom_kernel : 0;
     }
     return PAVGPU_OK;
 }

@@ -172,10 +172,11 @@ def test_multipass_walk_matches_single_pass(tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize('case', CIGAR_CASES)
-def test_cigar_golden_gpu_tiled_homology(case, monkeypatch):
-    """The golden cases again with the shared-memory-tile homology kernel forced (it is picked automatically only for large,
-    dense batches): partial warps, REV records, N runs, tandem repeats that leave the tile."""
-    monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', '1')
+@pytest.mark.parametrize('env', ['PAVGPU_HOMOLOGY_TILED', 'PAVGPU_HOMOLOGY_NBR'])
+def test_cigar_golden_gpu_tiled_homology(case, env, monkeypatch):
+    """The golden cases again with each opt-in homology kernel (per-warp shared-memory tiles, per-indel neighbourhoods): partial
+    warps, REV records, N runs, tandem repeats that leave the staged words, planes smaller than a neighbourhood."""
+    monkeypatch.setenv(env, '1')
     test_cigar_golden_gpu(case)
 
 
@@ -193,10 +194,11 @@ def test_homology_kernels_agree(tmp_path, monkeypatch, seed, kw):
     from pav_b200.pavlib import cigarcall
     ref_fa, tig_fa, df = _workload(tmp_path, seed, **kw)
     orc = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
-    for mode in ('0', '1'):
-        monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
+    for kernel, (tiled, nbr) in enumerate([('0', '0'), ('1', '0'), ('0', '1')]):   # gathers, warp tiles, per-indel neighbourhoods
+        monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', tiled)
+        monkeypatch.setenv('PAVGPU_HOMOLOGY_NBR', nbr)
         got = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
-        assert cigarcall.last_stats['homology_tiled'] == int(mode)
+        assert cigarcall.last_stats['homology_tiled'] == kernel
         assert tsv_bytes(got[1]) == tsv_bytes(orc[1]) and tsv_bytes(got[0]) == tsv_bytes(orc[0])
         assert got[1].shape[0] > 0
 
@@ -218,14 +220,18 @@ def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
     rid = np.array([names_r.index(c) for c in df['#CHROM']], np.int32)
     qid = np.array([names_t.index(c) for c in df['QRY_ID']], np.int32)
     out = {}
-    for mode in (None, 'auto', '1'):
-        if mode is not None:
+    monkeypatch.delenv('PAVGPU_HOMOLOGY_NBR', raising=False)
+    for mode in (None, 'auto', '1', 'nbr'):
+        if mode == 'nbr':
+            monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', '0')
+            monkeypatch.setenv('PAVGPU_HOMOLOGY_NBR', '1')
+        elif mode is not None:
             monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
         _, indel, err, st = device.cigar_call(ctx, rs, ts, rid, qid, df['POS'].to_numpy(np.int32), df['REV'].to_numpy(np.uint8), ops, op_off)
         assert err.code == 0
         out[mode] = (indel.copy(), st.homology_tiled)
-    assert out[None][1] == 0 and out['auto'][1] == 1 and out['1'][1] == 1
-    assert out[None][0].tobytes() == out['auto'][0].tobytes() == out['1'][0].tobytes()
+    assert [out[m][1] for m in (None, 'auto', '1', 'nbr')] == [0, 1, 1, 2]
+    assert out[None][0].tobytes() == out['auto'][0].tobytes() == out['1'][0].tobytes() == out['nbr'][0].tobytes()
     for f in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r', 'hom_tig_l', 'hom_tig_r', 'rec', 'svtype'):
         assert (out[None][0][f] == o_indel[f]).all(), f
     rs.close(); ts.close()
