@@ -585,49 +585,13 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes 
     const int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
     const OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0};
     const OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w};
-    const int32_t L = (int32_t)Q.len;
-    // Five scans, one rolled loop so the scan code exists once in the kernel (with all five call sites inlined the kernel
-    // is instruction-fetch bound).
-    //   INS: SV sequence = contig[sq : sq+n] (re-sliced after the shift); DEL: reference[pr : pr+n] (never re-sliced)
-    const bool ins = (svtype == 0);
-    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
-    int32_t sp = pr, sq = pq;
-#pragma unroll 1
-    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {   // scan 0 (the left shift) only when the previous op was '=' (cigarcall.py:149,225)
-        const bool on_ref = sc <= 2;            // scans 0..2 walk the reference, 3..4 the contig
-        const int left = (sc == 0 || sc == 1 || sc == 3);
-        int64_t p;
-        if (sc == 0) p = (int64_t)pr - 1;
-        else if (sc == 1) p = (int64_t)sp - 1;
-        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
-        else if (sc == 3) p = (int64_t)sq - 1;
-        else p = ins ? (int64_t)sq + n : (int64_t)sq;
-        const OSeq &T = on_ref ? R : Q;
-        const OSeq &V = ins ? Q : R;
-        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;   // sq == pq while sc == 0
-        int h = dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, left);
-        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
-        else if (sc == 1) hom_rl = h;
-        else if (sc == 2) hom_rr = h;
-        else if (sc == 3) hom_tl = h;
-        else hom_tr = h;
-    }
-    int32_t pos, end, qry_pos, qry_end, seq_start;
-    if (ins) {          // cigarcall.py:157-173
-        pos = sp; end = sp + 1;
-        if (Q.rev) { qry_end = L - sq; qry_pos = qry_end - n; } else { qry_pos = sq; qry_end = sq + n; }
-        seq_start = sq;
-    } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
-        pos = pr; end = pr + n;
-        qry_pos = Q.rev ? L - sq : sq;
-        qry_end = qry_pos + 1;
-        seq_start = pr;
-    }
+    IndelScore o;
+    score_indel<false>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
     dst[0] = make_int4(rec, op_idx, svtype, n);
-    dst[1] = make_int4(pos, end, qry_pos, qry_end);
-    dst[2] = make_int4(ls, hom_rl, hom_rr, hom_tl);
-    dst[3] = make_int4(hom_tr, seq_start, 0, 0);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
+    dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
 }
 
 // K4t: the same scans with the sequence neighbourhood of every warp's 32 indels staged in shared memory.
@@ -638,13 +602,8 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes 
 // tile (sparse indels, a jump between distant records) keeps the gathers; windows that leave the tile (long tandem-repeat
 // scans) fall through to global memory one by one. Opt-in (PAVGPU_HOMOLOGY_TILED, see launch_homology): on C2 it trades the
 // DRAM bound of the gathers for an issue-latency bound at 12 warps/SM and is slower as it stands.
-#ifndef HOM_TILE_WORDS_N
-#define HOM_TILE_WORDS_N 768
-#endif
 constexpr int HOMT_WARPS = 4;
 constexpr int HOMT_THREADS = HOMT_WARPS * 32;
-constexpr int HOM_TILE_WORDS = HOM_TILE_WORDS_N;          // 32-base words per sequence and warp (768 words = 24.5 kbp)
-constexpr int HOM_TILE_MARGIN = 160;                      // bases staged beyond the outermost breakpoints
 constexpr size_t HOMT_SMEM = (size_t)HOMT_WARPS * HOM_TILE_WORDS * 24;   // per warp: 2 x (8 B pack2 + 4 B mask) per word
 static_assert(HOM_TILE_WORDS % 4 == 0, "tiles are copied in 16-byte pieces");
 
@@ -665,17 +624,6 @@ __device__ __forceinline__ long long warp_max_ll(long long v)
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
     return v;
-}
-
-// Word range [w0, w0 + nw) of a plane covering breakpoints lo_g..hi_g (plane base coordinates) plus the margin, 4-word aligned
-// and clamped to the plane; nw = 0 when it does not fit the tile.
-__device__ __forceinline__ void tile_range(long long lo_g, long long hi_g, int64_t plane_words, int64_t &w0, int32_t &nw)
-{
-    long long a = (lo_g - HOM_TILE_MARGIN) >> 5, b = ((hi_g + HOM_TILE_MARGIN) >> 5) + 2;
-    a = max(a, 0ll) & ~3ll;
-    b = min((b + 3) & ~3ll, (long long)plane_words);
-    w0 = a;
-    nw = (b > a && b - a <= HOM_TILE_WORDS) ? (int32_t)(b - a) : 0;
 }
 
 __global__ void __launch_bounds__(HOMT_THREADS, 3)
@@ -717,45 +665,13 @@ homology_tiled_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
         Q.t_nw1 = max(nw_q - 1, 0);
     }
     if (!live) return;
-    const bool ins = (svtype == 0);
-    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
-    int32_t sp = pr, sq = pq;
-#pragma unroll 1
-    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {   // same five scans as homology_kernel
-        const bool on_ref = sc <= 2;
-        const int left = (sc == 0 || sc == 1 || sc == 3);
-        int64_t p;
-        if (sc == 0) p = (int64_t)pr - 1;
-        else if (sc == 1) p = (int64_t)sp - 1;
-        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
-        else if (sc == 3) p = (int64_t)sq - 1;
-        else p = ins ? (int64_t)sq + n : (int64_t)sq;
-        const OSeq &T = on_ref ? R : Q;
-        const OSeq &V = ins ? Q : R;
-        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;
-        int h = dev_homology_tiled(T, p, V, v0, n, left);
-        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
-        else if (sc == 1) hom_rl = h;
-        else if (sc == 2) hom_rr = h;
-        else if (sc == 3) hom_tl = h;
-        else hom_tr = h;
-    }
-    int32_t pos, end, qry_pos, qry_end, seq_start;
-    if (ins) {
-        pos = sp; end = sp + 1;
-        if (Q.rev) { qry_end = L - sq; qry_pos = qry_end - n; } else { qry_pos = sq; qry_end = sq + n; }
-        seq_start = sq;
-    } else {
-        pos = pr; end = pr + n;
-        qry_pos = Q.rev ? L - sq : sq;
-        qry_end = qry_pos + 1;
-        seq_start = pr;
-    }
+    IndelScore o;
+    score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
     dst[0] = make_int4(rec, op_idx, svtype, n);
-    dst[1] = make_int4(pos, end, qry_pos, qry_end);
-    dst[2] = make_int4(ls, hom_rl, hom_rr, hom_tl);
-    dst[3] = make_int4(hom_tr, seq_start, 0, 0);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
+    dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
 }
 
 // K4n (opt-in, PAVGPU_HOMOLOGY_NBR=1): thread per indel like homology_kernel, but the 256-base neighbourhood of the breakpoint
@@ -763,7 +679,6 @@ homology_tiled_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
 // right after the stub is read -- all sectors of an indel requested at once instead of one dependent window at a time, and
 // each fetched once instead of once per scan that touches it. Windows outside the neighbourhood (long SVs, tandem repeats) use
 // the global loads. Slots are padded (9 / 9 words) so a warp's accesses spread over the banks.
-constexpr int NBR_WORDS = 8;
 constexpr int NBR_P_STRIDE = 72;   // bytes per thread and sequence: 8 x 8 B + 8 B padding
 constexpr int NBR_M_STRIDE = 36;   //                                8 x 4 B + 4 B padding
 constexpr size_t NBR_SMEM = (size_t)2 * HOM_THREADS * (NBR_P_STRIDE + NBR_M_STRIDE);
@@ -776,15 +691,6 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-
-// First word of the 8-word neighbourhood around plane coordinate c (sector-aligned, inside the plane); -1 if the plane is too small.
-__device__ __forceinline__ int64_t nbr_first_word(long long c, int64_t plane_words)
-{
-    if (plane_words < NBR_WORDS) return -1;
-    long long w = ((c - 64) >> 5) & ~3ll;
-    w = max(w, 0ll);
-    return (int64_t)min(w, (long long)plane_words - NBR_WORDS);
 }
 
 __global__ void __launch_bounds__(HOM_THREADS, 4)
@@ -821,45 +727,13 @@ homology_nbr_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPla
         if (wr >= 0) { R.t_w0 = wr; R.t_nw1 = NBR_WORDS - 1; }
         if (wq >= 0) { Q.t_w0 = wq; Q.t_nw1 = NBR_WORDS - 1; }
     }
-    const bool ins = (svtype == 0);
-    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
-    int32_t sp = pr, sq = pq;
-#pragma unroll 1
-    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {   // same five scans as homology_kernel
-        const bool on_ref = sc <= 2;
-        const int left = (sc == 0 || sc == 1 || sc == 3);
-        int64_t p;
-        if (sc == 0) p = (int64_t)pr - 1;
-        else if (sc == 1) p = (int64_t)sp - 1;
-        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
-        else if (sc == 3) p = (int64_t)sq - 1;
-        else p = ins ? (int64_t)sq + n : (int64_t)sq;
-        const OSeq &T = on_ref ? R : Q;
-        const OSeq &V = ins ? Q : R;
-        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;
-        int h = dev_homology_tiled(T, p, V, v0, n, left);
-        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
-        else if (sc == 1) hom_rl = h;
-        else if (sc == 2) hom_rr = h;
-        else if (sc == 3) hom_tl = h;
-        else hom_tr = h;
-    }
-    int32_t pos, end, qry_pos, qry_end, seq_start;
-    if (ins) {
-        pos = sp; end = sp + 1;
-        if (Q.rev) { qry_end = L - sq; qry_pos = qry_end - n; } else { qry_pos = sq; qry_end = sq + n; }
-        seq_start = sq;
-    } else {
-        pos = pr; end = pr + n;
-        qry_pos = Q.rev ? L - sq : sq;
-        qry_end = qry_pos + 1;
-        seq_start = pr;
-    }
+    IndelScore o;
+    score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
     dst[0] = make_int4(rec, op_idx, svtype, n);
-    dst[1] = make_int4(pos, end, qry_pos, qry_end);
-    dst[2] = make_int4(ls, hom_rl, hom_rr, hom_tl);
-    dst[3] = make_int4(hom_tr, seq_start, 0, 0);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
+    dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
 }
 
 __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,

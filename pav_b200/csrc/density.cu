@@ -79,38 +79,6 @@ struct KdeParams {  // per window, written by D4
     int32_t pad;
 };
 
-__device__ __forceinline__ uint64_t hash_kmer(uint64_t k, int log2cap)
-{
-    return (k * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
-}
-
-// kmer.py:118-133 as bit tricks: complement, then reverse the 2-bit groups of the 64-bit word.
-__device__ __forceinline__ uint64_t kmer_revcomp(uint64_t kmer, int k)
-{
-    uint64_t x = ~kmer;
-    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
-    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
-    x = ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
-    return x >> (64 - 2 * k);
-}
-
-// k-mer starting at global base g (first base most significant); returns false if any of its k bases
-// is not ACGT (stream() would not have emitted it, kmer.py:206-221).
-__device__ __forceinline__ bool kmer_at(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t g, int k,
-                                        uint64_t &kmer)
-{
-    int64_t w = g >> 5;
-    int s = (int)(g & 31);
-    uint64_t m = (uint64_t)__ldg(nmask + w) | ((uint64_t)__ldg(nmask + w + 1) << 32);
-    m >>= s;
-    uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
-    if (m & kmask) return false;
-    uint64_t hi = __ldg(pack2 + w), lo = __ldg(pack2 + w + 1);
-    uint64_t x = s ? ((hi << (2 * s)) | (lo >> (64 - 2 * s))) : hi;
-    kmer = x >> (64 - 2 * k);
-    return true;
-}
-
 // D1 ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ref_insert_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes ref, int k, uint64_t *__restrict__ keys,

@@ -1,0 +1,309 @@
+// seqbits.cuh -- bit-level primitives over the packed sequence planes: base codes and word packing, 32-base windows,
+// the word-parallel homology scans, k-mers. Device code (every function is __device__ __forceinline__ under nvcc); the same
+// text also compiles as plain C++ when PAV_DEV is predefined and the handful of CUDA intrinsics it uses (__ldg, __funnelshift_r,
+// __byte_perm, __brev, __clz, __clzll, __ffs, __ffsll, min) are supplied by the includer -- tests/host_emul does that to run
+// these exact functions against the oracle and the golden vectors on a machine without a GPU.
+#pragma once
+#include <cstdint>
+
+#ifndef PAV_DEV
+#define PAV_DEV __device__ __forceinline__
+#endif
+
+// ---- base codes and plane words ----------------------------------------------------------------
+// A/a 0, C/c 1, G/g 2, T/t 3, everything else 4
+PAV_DEV uint32_t base_code(uint32_t ch)
+{
+    ch &= 0xDFu;  // fold case
+    return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
+}
+
+// 32 ASCII bases (eight little-endian 32-bit loads) -> one 2-bit plane word (first base most significant) and one mask word
+// (bit i set when base i is not ACGTacgt).
+PAV_DEV void pack_word32(const uint32_t (&v)[8], uint64_t &word, uint32_t &mask)
+{
+    word = 0;
+    mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t c = base_code((v[i] >> (8 * j)) & 0xFFu);
+            int pos = i * 4 + j;
+            word |= (uint64_t)(c & 3u) << (62 - 2 * pos);
+            mask |= (c >> 2) << pos;
+        }
+    }
+}
+
+// ---- oriented sequences, 32-base windows, homology scans ---------------------------------------
+// A sequence seen in alignment orientation: position t maps to the forward base t, or to the
+// complement of forward base len-1-t when rev (what Bio.Seq.reverse_complement materialises in
+// pavlib/cigarcall.py:69-70; here it is index arithmetic).
+struct OSeq {
+    const uint64_t *pack2;
+    const uint32_t *nmask;
+    int64_t base;  // offset of the sequence in the planes
+    int64_t len;
+    int rev;
+    // Optional staged copy of plane words [t_w0, t_w0 + t_nw1 + 1) in shared memory (homology_tiled_kernel); windows whose two
+    // words lie inside are served from it, all others from global memory. t_nw1 == 0: no tile.
+    const uint64_t *t_pack2;
+    const uint32_t *t_nmask;
+    int64_t t_w0;
+    int32_t t_nw1;
+};
+
+// Upper-cased base as 0..3 (ACGT) or 4 (anything else, or out of range).
+PAV_DEV int oseq_base(const OSeq &s, int64_t t)
+{
+    if (t < 0 || t >= s.len) return 4;
+    int64_t g = s.base + (s.rev ? (s.len - 1 - t) : t);
+    uint32_t m = (__ldg(s.nmask + (g >> 5)) >> (g & 31)) & 1u;
+    if (m) return 4;
+    int c = (int)((__ldg(s.pack2 + (g >> 5)) >> (62 - 2 * (int)(g & 31))) & 3ull);
+    return s.rev ? 3 - c : c;
+}
+
+// ---- 32-base windows --------------------------------------------------------------------------
+// Reverse the 32 two-bit groups of a word and complement them (reverse complement of 32 bases).
+PAV_DEV uint64_t revcomp32(uint64_t x)
+{
+    x = ~x;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    return ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+}
+
+// Forward-strand window: bases f .. f+31 of a sequence (base i of the window in bits [62-2i, 64-2i) of
+// `bases`, bit i of `mask` set when that base is not ACGT or lies outside [0, len)). Positions inside a sequence
+// are 32-bit (sequences are shorter than 2^31, checked when the store is built); only the plane offset is 64-bit.
+template <bool TILED = false>
+PAV_DEV void fwd_window(const OSeq &s, int32_t f, uint64_t &bases, uint32_t &mask)
+{
+    const int32_t len = (int32_t)s.len;
+    if (f <= -32 || f >= len) { bases = 0; mask = 0xffffffffu; return; }
+    const int lead = f < 0 ? -f : 0;           // window positions before the sequence start
+    const int64_t g = s.base + (int64_t)(f + lead);
+    const int64_t w = g >> 5;
+    const int sh = (int)(g & 31);
+    uint64_t hi, lo;
+    uint32_t m0, m1;
+    if (TILED && (uint64_t)(w - s.t_w0) < (uint64_t)s.t_nw1) {   // words w and w+1 are staged
+        const int o = (int)(w - s.t_w0);
+        hi = s.t_pack2[o]; lo = s.t_pack2[o + 1];
+        m0 = s.t_nmask[o]; m1 = s.t_nmask[o + 1];
+    } else {
+        hi = __ldg(s.pack2 + w); lo = __ldg(s.pack2 + w + 1);
+        m0 = __ldg(s.nmask + w); m1 = __ldg(s.nmask + w + 1);
+    }
+    uint64_t b = sh ? ((hi << (2 * sh)) | (lo >> (64 - 2 * sh))) : hi;
+    uint32_t m = __funnelshift_r(m0, m1, sh);
+    if (lead | (f + 32 > len)) {               // sequence edges only
+        if (lead) { b >>= 2 * lead; m = (m << lead) | ((1u << lead) - 1u); }
+        const int over = f + 32 - len;         // window positions past the sequence end
+        if (over > 0) m |= ~0u << (32 - over);
+    }
+    bases = b; mask = m;
+}
+
+// Window of 32 bases starting at oriented position t (reverse-complement view when s.rev).
+// (An out-of-line variant of this and of dev_homology_raw was measured on B200: 0.176 ms vs 0.148 ms inlined for the
+// C2 homology kernel -- call overhead and spills cost more than the instruction-fetch stalls they remove. 16-base
+// windows with 32-bit funnel shifts were measured too: 0.147 ms vs 0.102 ms, twice the loop trips for long scans.)
+template <bool TILED = false>
+PAV_DEV void oseq_window(const OSeq &s, int32_t t, uint64_t &bases, uint32_t &mask)
+{
+    if (!s.rev) { fwd_window<TILED>(s, t, bases, mask); return; }
+    uint64_t b; uint32_t m;
+    fwd_window<TILED>(s, (int32_t)s.len - t - 32, b, m);
+    bases = revcomp32(b);
+    mask = __brev(m);
+}
+
+// Longest common extension of A from a and B from b, 32 bases per step, capped at `limit`:
+//   left == 0: common prefix of A[a..] and B[b..]        (window i covers a+32i .. a+32i+31)
+//   left != 0: common suffix of A[..a] and B[..b]         (window i covers a-32i-31 .. a-32i)
+// Stops at the first mismatch, non-ACGT base or sequence end on either side.
+template <bool TILED = false>
+PAV_DEV int32_t common_extension(const OSeq &A, int32_t a, const OSeq &B, int32_t b, int32_t limit, int left)
+{
+    int32_t h = 0;
+    const int32_t a0 = left ? a - 31 : a, b0 = left ? b - 31 : b, step = left ? -32 : 32;
+    int32_t pa = a0, pb = b0;
+    while (h < limit) {
+        uint64_t wa, wb; uint32_t ma, mb;
+        oseq_window<TILED>(A, pa, wa, ma);
+        oseq_window<TILED>(B, pb, wb, mb);
+        uint64_t x = wa ^ wb;
+        uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;      // one bit per differing base
+        uint32_t m = ma | mb;
+        int stop_d, stop_m;
+        if (left) {   // last base of the window = least significant group / highest mask bit
+            stop_d = d ? ((__ffsll((long long)d) - 1) >> 1) : 32;
+            stop_m = m ? __clz((int)m) : 32;
+        } else {      // first base = most significant group / lowest mask bit
+            stop_d = d ? (__clzll((long long)d) >> 1) : 32;
+            stop_m = m ? (__ffs((int)m) - 1) : 32;
+        }
+        int stop = min(stop_d, stop_m);
+        if (stop < 32) { h += stop; return h < limit ? h : limit; }
+        h += 32; pa += step; pb += step;
+        if (h < 0) return limit;   // (cannot happen for sequences < 2^31; guards the 32-bit counter)
+    }
+    return limit;
+}
+
+// pavlib/call.py:542-592 (left != 0) and :595-647 (left == 0). T: flank searched from p away from the
+// breakpoint; the SV sequence is V[v0 : v0+n], read circularly (leftwards from its end: sv[-((h+1) % n)],
+// index -0 == 0; rightwards from its start: sv[h % n]). Word-parallel form: the first n steps are a common
+// suffix/prefix of the flank with V; once a whole copy of V matched, step h compares T[p -/+ h] with
+// V[...] = T[p -/+ h +/- n], i.e. the scan continues as the common extension of the flank with itself
+// shifted by n.
+PAV_DEV int dev_homology_raw(const uint64_t *t_pack2, const uint32_t *t_nmask, int64_t t_base, int64_t t_len, int t_rev,
+                                                    int64_t p, const uint64_t *v_pack2, const uint32_t *v_nmask, int64_t v_base, int64_t v_len,
+                                                    int v_rev, int64_t v0, int n, int left)
+{
+    const OSeq T{t_pack2, t_nmask, t_base, t_len, t_rev, nullptr, nullptr, 0, 0};
+    const OSeq V{v_pack2, v_nmask, v_base, v_len, v_rev, nullptr, nullptr, 0, 0};
+    if (n <= 0 || p < 0 || p >= T.len) return 0;
+    const int32_t p32 = (int32_t)p, v32 = (int32_t)v0;
+    int32_t h = common_extension(T, p32, V, left ? v32 + n - 1 : v32, n, left);
+    if (h < n) return h;
+    // the flank is shorter than 2^31, so the self-comparison ends at a sequence edge long before the cap
+    return n + common_extension(T, left ? p32 - n : p32 + n, T, p32, 0x7fffffff - n, left);
+}
+
+// The same scan over sequences that may carry a staged tile.
+PAV_DEV int dev_homology_tiled(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n, int left)
+{
+    if (n <= 0 || p < 0 || p >= T.len) return 0;
+    const int32_t p32 = (int32_t)p, v32 = (int32_t)v0;
+    int32_t h = common_extension<true>(T, p32, V, left ? v32 + n - 1 : v32, n, left);
+    if (h < n) return h;
+    return n + common_extension<true>(T, left ? p32 - n : p32 + n, T, p32, 0x7fffffff - n, left);
+}
+
+PAV_DEV int dev_left_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
+{
+    return dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, 1);
+}
+
+PAV_DEV int dev_right_homology(const OSeq &T, int64_t p, const OSeq &V, int64_t v0, int n)
+{
+    return dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, 0);
+}
+
+// One indel scored the way pavlib/cigarcall.py:137-266 does it: the left shift (only when the previous op was '=',
+// :149,225), then the breakpoint homology on both sides in the reference and in the contig. INS: SV sequence =
+// contig[sq : sq+n] (re-sliced after the shift); DEL: reference[pr : pr+n] (never re-sliced, POS/END/SEQ stay unshifted).
+// The five scans run as one rolled loop so the scan code exists once in the kernel (with all five call sites inlined the
+// kernel is instruction-fetch bound). TILED: the sequences carry staged words (dev_homology_tiled), else plain global loads.
+struct IndelScore {
+    int32_t pos, end, qry_pos, qry_end;
+    int32_t ls, hom_rl, hom_rr, hom_tl;
+    int32_t hom_tr, seq_start;
+};
+
+template <bool TILED>
+PAV_DEV void score_indel(const OSeq &R, const OSeq &Q, int32_t svtype, int32_t n, int32_t pr, int32_t pq, int32_t eqb, IndelScore &o)
+{
+    const int32_t L = (int32_t)Q.len;
+    const bool ins = (svtype == 0);
+    int ls = 0, hom_rl = 0, hom_rr = 0, hom_tl = 0, hom_tr = 0;
+    int32_t sp = pr, sq = pq;
+#pragma unroll 1
+    for (int sc = (eqb > 0 ? 0 : 1); sc < 5; sc++) {
+        const bool on_ref = sc <= 2;            // scans 0..2 walk the reference, 3..4 the contig
+        const int left = (sc == 0 || sc == 1 || sc == 3);
+        int64_t p;
+        if (sc == 0) p = (int64_t)pr - 1;
+        else if (sc == 1) p = (int64_t)sp - 1;
+        else if (sc == 2) p = ins ? (int64_t)sp : (int64_t)sp + n;
+        else if (sc == 3) p = (int64_t)sq - 1;
+        else p = ins ? (int64_t)sq + n : (int64_t)sq;
+        const OSeq &T = on_ref ? R : Q;
+        const OSeq &V = ins ? Q : R;
+        const int64_t v0 = ins ? (int64_t)sq : (int64_t)pr;   // sq == pq while sc == 0
+        int h;
+        if (TILED) h = dev_homology_tiled(T, p, V, v0, n, left);
+        else h = dev_homology_raw(T.pack2, T.nmask, T.base, T.len, T.rev, p, V.pack2, V.nmask, V.base, V.len, V.rev, v0, n, left);
+        if (sc == 0) { ls = min(eqb, h); sp = pr - ls; sq = pq - ls; }
+        else if (sc == 1) hom_rl = h;
+        else if (sc == 2) hom_rr = h;
+        else if (sc == 3) hom_tl = h;
+        else hom_tr = h;
+    }
+    if (ins) {          // cigarcall.py:157-173
+        o.pos = sp; o.end = sp + 1;
+        if (Q.rev) { o.qry_end = L - sq; o.qry_pos = o.qry_end - n; } else { o.qry_pos = sq; o.qry_end = sq + n; }
+        o.seq_start = sq;
+    } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
+        o.pos = pr; o.end = pr + n;
+        o.qry_pos = Q.rev ? L - sq : sq;
+        o.qry_end = o.qry_pos + 1;
+        o.seq_start = pr;
+    }
+    o.ls = ls; o.hom_rl = hom_rl; o.hom_rr = hom_rr; o.hom_tl = hom_tl; o.hom_tr = hom_tr;
+}
+
+// ---- staged words: which part of a plane the opt-in homology kernels copy on chip ---------------
+#ifndef HOM_TILE_WORDS_N
+#define HOM_TILE_WORDS_N 768
+#endif
+constexpr int HOM_TILE_WORDS = HOM_TILE_WORDS_N;   // homology_tiled_kernel: 32-base words per sequence and warp (768 words = 24.5 kbp)
+constexpr int HOM_TILE_MARGIN = 160;               //   bases staged beyond the outermost breakpoints
+constexpr int NBR_WORDS = 8;                       // homology_nbr_kernel: words per sequence and indel (256 bases)
+
+// Word range [w0, w0 + nw) of a plane covering breakpoints lo_g..hi_g (plane base coordinates) plus the margin, 4-word aligned
+// and clamped to the plane; nw = 0 when it does not fit the tile.
+PAV_DEV void tile_range(long long lo_g, long long hi_g, int64_t plane_words, int64_t &w0, int32_t &nw)
+{
+    long long a = (lo_g - HOM_TILE_MARGIN) >> 5, b = ((hi_g + HOM_TILE_MARGIN) >> 5) + 2;
+    a = max(a, 0ll) & ~3ll;
+    b = min((b + 3) & ~3ll, (long long)plane_words);
+    w0 = a;
+    nw = (b > a && b - a <= HOM_TILE_WORDS) ? (int32_t)(b - a) : 0;
+}
+
+// First word of the 8-word neighbourhood around plane coordinate c (sector-aligned, inside the plane); -1 if the plane is too small.
+PAV_DEV int64_t nbr_first_word(long long c, int64_t plane_words)
+{
+    if (plane_words < NBR_WORDS) return -1;
+    long long w = ((c - 64) >> 5) & ~3ll;
+    w = max(w, 0ll);
+    return (int64_t)min(w, (long long)plane_words - NBR_WORDS);
+}
+
+// ---- k-mers ---------------------------------------------------------------------------------------
+PAV_DEV uint64_t hash_kmer(uint64_t k, int log2cap)
+{
+    return (k * 0x9E3779B97F4A7C15ull) >> (64 - log2cap);
+}
+
+// kmer.py:118-133 as bit tricks: complement, then reverse the 2-bit groups of the 64-bit word.
+PAV_DEV uint64_t kmer_revcomp(uint64_t kmer, int k)
+{
+    uint64_t x = ~kmer;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(x >> 32), 0, 0x0123);
+    return x >> (64 - 2 * k);
+}
+
+// k-mer starting at global base g (first base most significant); returns false if any of its k bases
+// is not ACGT (stream() would not have emitted it, kmer.py:206-221).
+PAV_DEV bool kmer_at(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t g, int k,
+                                        uint64_t &kmer)
+{
+    int64_t w = g >> 5;
+    int s = (int)(g & 31);
+    uint64_t m = (uint64_t)__ldg(nmask + w) | ((uint64_t)__ldg(nmask + w + 1) << 32);
+    m >>= s;
+    uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+    if (m & kmask) return false;
+    uint64_t hi = __ldg(pack2 + w), lo = __ldg(pack2 + w + 1);
+    uint64_t x = s ? ((hi << (2 * s)) | (lo >> (64 - 2 * s))) : hi;
+    kmer = x >> (64 - 2 * k);
+    return true;
+}

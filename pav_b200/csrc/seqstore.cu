@@ -189,13 +189,6 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_l2_flush(pavgpu_ctx
 // pack kernel: ASCII -> (2-bit plane, N-mask plane). One thread per 32 bases = one 64-bit plane word
 // and one 32-bit mask word; two 128-bit loads per thread. Pure streaming: 1 B/base in, 0.375 B/base out.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t code_of(uint32_t ch)
-{
-    // A/a 0, C/c 1, G/g 2, T/t 3, everything else 4
-    ch &= 0xDFu;  // fold case
-    return ch == 'A' ? 0u : ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 4u;
-}
-
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ ascii, int64_t n_words,
                                                    uint64_t *__restrict__ pack2, uint32_t *__restrict__ nmask)
 {
@@ -204,18 +197,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ a
     const uint4 *src = reinterpret_cast<const uint4 *>(ascii + w * 32);
     uint4 a = __ldcs(src), b = __ldcs(src + 1);
     uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint64_t word = 0;
-    uint32_t mask = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t c = code_of((v[i] >> (8 * j)) & 0xFFu);
-            int pos = i * 4 + j;
-            word |= (uint64_t)(c & 3u) << (62 - 2 * pos);
-            mask |= (c >> 2) << pos;
-        }
-    }
+    uint64_t word;
+    uint32_t mask;
+    pack_word32(v, word, mask);
     pack2[w] = word;
     nmask[w] = mask;
 }
