@@ -129,15 +129,20 @@ def density_windows(windows, k=31, ctx=None, **kw):
     return out
 
 
-def frame_from_result(d):
-    """Column arrays of one window -> the DataFrame scripts/density.py would have pickled."""
+def frame_from_result(d, extra=None):
+    """Column arrays of one window -> the DataFrame scripts/density.py would have pickled. ``extra``: further columns (name ->
+    array) appended in the same construction (a column added to a finished frame costs about as much as the frame)."""
     if d['smoothed']:
-        df = pd.DataFrame({
-            'INDEX': d['INDEX'].astype(np.int64), 'STATE_MER': d['STATE_MER'].astype(np.int64), 'STATE': d['STATE'].astype(np.int64),
+        index = d['INDEX'].astype(np.int64)
+        cols = {
+            'INDEX': index, 'STATE_MER': d['STATE_MER'].astype(np.int64), 'STATE': d['STATE'].astype(np.int64),
             'KERN_FWD': d['KERN_FWD'], 'KERN_FWDREV': d['KERN_FWDREV'], 'KERN_REV': d['KERN_REV'], 'KMER': d['KMER'].astype(np.int64),
-        }, columns=SMOOTHED_COLUMNS)
-        df.set_index(df['INDEX'], inplace=True, drop=False)
-        return df
+        }
+        ix = pd.Index(index, name='INDEX')
+        for name, arr in (extra or {}).items():     # object columns stay object (a bare object array would be inferred as str dtype)
+            cols[name] = pd.Series(arr, index=ix, dtype=object)
+        return pd.DataFrame(cols, columns=SMOOTHED_COLUMNS + list(extra or ()), index=ix)
+    assert not extra
     # fewer than --mininf informative k-mers: frame returned before smoothing (density.py:193-194)
     return pd.DataFrame({
         'KMER': d['KMER'].astype(np.int64), 'INDEX': d['INDEX'].astype(np.int64), 'STATE': d['STATE'].astype(np.int64),
@@ -170,7 +175,9 @@ class DensityTable:
         for a, b in zip(starts.tolist(), ends.tolist()):
             yield (st[a].item(), b - a, ix[a].item(), ix[b - 1].item())
 
-    def frame(self):
+    def frame(self, extra=None):
+        if extra:
+            return frame_from_result(self.res, extra)
         if self._df is None:
             self._df = frame_from_result(self.res)
         return self._df

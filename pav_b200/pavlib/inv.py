@@ -178,7 +178,7 @@ class _InvScan:
             _write_log('Found no inverted k-mer states after {} expansion(s)'.format(self.expansion_count), log)
             return self._finish(None)
         if len(condensed_states) > 2 and condensed_states[0] == 0 and condensed_states[-1] == 0:
-            return self._finish(self._characterise(df.frame() if lazy else df, state_rl))
+            return self._finish(self._characterise(df, state_rl))
         last_len = len(region_ref)
         expand_bp = np.int32(len(region_ref) * EXPAND_FACTOR)
         if len(condensed_states) > 2:
@@ -228,8 +228,14 @@ class _InvScan:
             return None
         # NOTE: the reference passes region_ref where annotate_inv_dup_mers expects the contig discovery region
         # (pavlib/inv.py:440-442); reproduced as is.
-        df = annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref,
-                                   self.ref_fa_name, self.k_util)
+        if isinstance(df, pavdensity.DensityTable):   # batch driver: the frame is built once, with the two flank columns already in it
+            res = df.res
+            flank, match = _dup_mer_columns(res['INDEX'], res['KMER'].astype(np.int64), region_ref_outer, region_ref_inner, region_tig_outer,
+                                            region_tig_inner, region_ref, self.ref_fa_name, self.k_util)
+            df = df.frame(extra={'FLANK': flank, 'MATCH': match})
+        else:
+            df = annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref,
+                                       self.ref_fa_name, self.k_util)
         inv_call = InvCall(region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref, region_tig,
                            self.region_flag, df)
         _write_log('Found inversion: {}'.format(inv_call), log)
@@ -378,6 +384,16 @@ def annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_out
                           ref_fa, k_util):
     """Add FLANK (UP / DN / '') and MATCH (SAME / OTHER / NaN) columns for k-mers inside flanking inverted
     duplications (reference: pavlib/inv.py:457-561; MATCH tests the raw k-mer against canonical sets, as there)."""
+    flank, match = _dup_mer_columns(df['INDEX'].to_numpy(), df['KMER'].to_numpy(), region_ref_outer, region_ref_inner, region_tig_outer,
+                                    region_tig_inner, region_tig_discovery, ref_fa, k_util)
+    df['FLANK'] = pd.Series(flank, index=df.index, dtype=object)   # explicit dtype: no string-dtype inference pass over 50 k cells
+    df['MATCH'] = pd.Series(match, index=df.index, dtype=object)
+    return df
+
+
+def _dup_mer_columns(index_col, kmer_col, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_tig_discovery,
+                     ref_fa, k_util):
+    """The FLANK and MATCH columns of ``annotate_inv_dup_mers`` as object arrays, from the INDEX and KMER columns."""
     k = int(k_util.k_size)
     dup_ref_up = pavseq.Region(region_ref_outer.chrom, region_ref_outer.pos, region_ref_inner.pos)
     dup_ref_dn = pavseq.Region(region_ref_outer.chrom, region_ref_inner.end, region_ref_outer.end)
@@ -386,16 +402,13 @@ def annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_out
     ref_set_up = _region_canonical_kmers(dup_ref_up, ref_fa, k)
     ref_set_dn = _region_canonical_kmers(dup_ref_dn, ref_fa, k)
 
-    qry_index = df['INDEX'].to_numpy() + region_tig_discovery.pos
+    qry_index = index_col.astype(np.int64) + region_tig_discovery.pos
     up = (qry_index >= dup_tig_up.pos) & (qry_index < dup_tig_up.end - k)
     dn = (qry_index >= dup_tig_dn.pos) & (qry_index < dup_tig_dn.end - k)
     flank = np.array(['', 'UP', 'DN'], dtype=object)[np.where(dn, 2, np.where(up, 1, 0))]     # DN is assigned last, as in the reference
-    match = np.full(df.shape[0], '', dtype=object)
-    kmer_col = df['KMER'].to_numpy()
+    match = np.full(len(index_col), '', dtype=object)
     for idx, first, second in ((np.flatnonzero(up & ~dn), ref_set_up, ref_set_dn), (np.flatnonzero(dn), ref_set_dn, ref_set_up)):
         for i, km in zip(idx.tolist(), kmer_col[idx].tolist()):      # only the k-mers inside the flanking duplications
             v = KMER_LOC_STATE[int(km in first), int(km in second)]
             match[i] = np.nan if v == 'NA' else v
-    df['FLANK'] = pd.Series(flank, index=df.index, dtype=object)   # explicit dtype: no string-dtype inference pass over 50 k cells
-    df['MATCH'] = pd.Series(match, index=df.index, dtype=object)
-    return df
+    return flank, match
