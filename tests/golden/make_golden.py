@@ -403,10 +403,51 @@ def make_density_cli():
         print('density cli', k, {a: (b if len(str(b)) < 100 else str(b)[:100] + '...') for a, b in v.items()})
 
 
+def count_cigar_cases(n_cases=2500, seed=31):
+    """pavlib.align.count_cigar of the reference on random CIGAR strings: well-formed ones (clips in every legal and illegal
+    arrangement, zero lengths, M with and without allow_m, N / P ops) and malformed text; result tuple or exception class + text."""
+    import random
+    rnd = random.Random(seed)
+    out = []
+    for _ in range(n_cases):
+        kind = rnd.random()
+        body = ''.join('{}{}'.format(rnd.choice([0, 1, 1, 2, 7, 30, 1234, 99999]) if rnd.random() < 0.2 else rnd.randint(1, 60),
+                                     rnd.choice('==XXIDM' if rnd.random() < 0.15 else '==XXID')) for _ in range(rnd.randint(0, 12)))
+        def clips():
+            k = rnd.random()
+            if k < 0.35:
+                return []
+            pool = ['S', 'H'] if k < 0.9 else ['S', 'H', 'S', 'H']
+            return rnd.sample(pool, rnd.randint(1, len(pool)))
+        lead = ''.join('{}{}'.format(rnd.choice([0, 3, 17, 250]), c) for c in clips())
+        tail = ''.join('{}{}'.format(rnd.choice([0, 3, 17, 250]), c) for c in clips())
+        cigar = lead + body + tail
+        if kind < 0.08 and body:      # a clip or an exotic op in the middle
+            ops = [m for m in __import__('re').findall(r'\d+.', cigar)]
+            ops.insert(rnd.randint(0, len(ops)), '{}{}'.format(rnd.randint(1, 9), rnd.choice('SHNP')))
+            cigar = ''.join(ops)
+        elif kind < 0.12:             # malformed text
+            cigar = rnd.choice([cigar + '12', '=' + cigar, cigar.replace('=', 'Q', 1) if '=' in cigar else cigar + '5Q', cigar + '3==', ''])
+        allow_m = rnd.random() < 0.3
+        rec = {'cigar': cigar, 'allow_m': allow_m}
+        row = pd.Series({'CIGAR': cigar, 'QRY_ID': 'tigA', '#CHROM': 'chrA', 'POS': 5})
+        try:
+            rec['result'] = [int(x) for x in pavlib.align.count_cigar(row, allow_m=allow_m)]
+        except Exception as ex:   # noqa: BLE001
+            rec['error'] = [type(ex).__name__, str(ex)]
+        out.append(rec)
+    with open(os.path.join(HERE, 'count_cigar.json'), 'w') as fh:
+        json.dump(out, fh)
+    n_err = sum('error' in r for r in out)
+    print('count_cigar', len(out), 'cases,', n_err, 'errors,', len({r['error'][1].split(' at ')[0][:40] for r in out if 'error' in r}), 'kinds of message')
+
+
 if __name__ == '__main__':
-    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli'}
+    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar'}
     if 'density_cli' in what:
         make_density_cli()
+    if 'count_cigar' in what:
+        count_cigar_cases()
     if 'align' in what:
         make_align_case()
     if 'cigar' in what:

@@ -332,3 +332,22 @@ def test_density_cli_host_side():
     assert 'K-mer count exceeds max: {} > {} ({}): {}\n'.format(n, cli.MAX_REF_KMER_COUNT, mer, 'chrW:1-5200') == gold['exit125_repeat']['stderr']
     ref = fasta.Fasta(os.path.join(d, 'exit125_empty', 'ref.fa')).fetch_array('chrW')
     assert cli.ref_kmer_failure(ref, 31) is None and cli.ref_kmer_failure(ref[:10], 31) is None
+
+
+def test_count_cigar_matches_reference_golden():
+    """count_cigar (vectorised fast path and op-by-op path) on 2,500 random CIGAR strings, legal and not: the tuple or the
+    exception class + text of the reference's own pavlib.align.count_cigar (tests/golden/count_cigar.json)."""
+    import json
+    from pav_b200.pavlib import align
+    cases = json.load(open(os.path.join(REPO, 'tests', 'golden', 'count_cigar.json')))
+    n_fast = 0
+    for c in cases:
+        row = pd.Series({'CIGAR': c['cigar'], 'QRY_ID': 'tigA', '#CHROM': 'chrA', 'POS': 5})
+        n_fast += align._count_cigar_fast(c['cigar'], c['allow_m']) is not None
+        try:
+            got = {'result': [int(x) for x in align.count_cigar(row, allow_m=c['allow_m'])]}
+        except Exception as ex:   # noqa: BLE001
+            got = {'error': [type(ex).__name__, str(ex)]}
+        want = {k: c[k] for k in ('result', 'error') if k in c}
+        assert got == want, c['cigar']
+    assert n_fast > 500      # the fast path really took part
