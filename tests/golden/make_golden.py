@@ -403,6 +403,58 @@ def make_density_cli():
         print('density cli', k, {a: (b if len(str(b)) < 100 else str(b)[:100] + '...') for a, b in v.items()})
 
 
+def lift_cases(seed=21):
+    """pavlib.align.AlignLift of the reference on a 4-record alignment table with clips, both strands and 1 % edits: point
+    lifts in both directions (inside, at and beyond record ends, inside insertions / deletions, with and without gap=True) and
+    region lifts; the table is stored with the answers."""
+    d = os.path.join(HERE, 'lift')
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ref, tigs, df = synth.make_cigar_workload(seed, 1, 120_000, 4, 30_000, edit_rate=0.01, rev_frac=0.5, clip=(13, 7))
+    df = df.reset_index(drop=True)
+    fai = pd.Series({k: len(v) for k, v in tigs.items()})
+    df.to_csv(os.path.join(d, 'align.bed'), sep='\t', index=False)
+    fai.to_csv(os.path.join(d, 'tig.fai.tsv'), sep='\t', header=False)
+    al = pavlib.align.AlignLift(df, fai)
+
+    def plain(x):
+        if x is None:
+            return None
+        return [x[0], int(x[1]), bool(x[2]), int(x[3]), int(x[4]), [int(i) for i in x[5]]]
+
+    def call(f, *a, **k):
+        try:
+            return {'result': f(*a, **k)}
+        except RuntimeError as ex:
+            return {'error': str(ex)}
+    out = []
+    for _ in range(1500):
+        row = df.iloc[int(rng.integers(0, df.shape[0]))]
+        p = int(rng.integers(row['POS'] - 50, row['END'] + 50))
+        r = call(al.lift_to_qry, row['#CHROM'], p)
+        out.append({'f': 'to_qry', 'id': row['#CHROM'], 'pos': p, **({'result': plain(r['result'])} if 'result' in r else r)})
+        q = int(rng.integers(max(row['QRY_POS'] - 30, 0), row['QRY_END'] + 30))
+        gap = bool(rng.random() < 0.5)
+        r = call(al.lift_to_sub, row['QRY_ID'], q, gap=gap)
+        out.append({'f': 'to_sub', 'id': row['QRY_ID'], 'pos': q, 'gap': gap, **({'result': plain(r['result'])} if 'result' in r else r)})
+    for _ in range(400):
+        row = df.iloc[int(rng.integers(0, df.shape[0]))]
+        a = int(rng.integers(row['POS'], row['END'] - 2000))
+        b = a + int(rng.integers(10, 1900))
+        rq = al.lift_region_to_qry(pavlib.seq.Region(row['#CHROM'], a, b))
+        rec = {'f': 'region', 'chrom': row['#CHROM'], 'pos': a, 'end': b,
+               'qry': None if rq is None else [rq.chrom, int(rq.pos), int(rq.end), bool(rq.is_rev)]}
+        if rq is not None:
+            for gap in (False, True):
+                rs = al.lift_region_to_sub(rq, gap=gap)
+                rec['sub_gap' if gap else 'sub'] = None if rs is None else [rs.chrom, int(rs.pos), int(rs.end), bool(rs.is_rev)]
+        out.append(rec)
+    with open(os.path.join(d, 'queries.json'), 'w') as fh:
+        json.dump(out, fh)
+    print('lift', len(out), 'queries,', sum(1 for r in out if r.get('result') is None and 'error' not in r and r['f'] != 'region'), 'None,',
+          sum('error' in r for r in out), 'errors')
+
+
 def count_cigar_cases(n_cases=2500, seed=31):
     """pavlib.align.count_cigar of the reference on random CIGAR strings: well-formed ones (clips in every legal and illegal
     arrangement, zero lengths, M with and without allow_m, N / P ops) and malformed text; result tuple or exception class + text."""
@@ -443,11 +495,13 @@ def count_cigar_cases(n_cases=2500, seed=31):
 
 
 if __name__ == '__main__':
-    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar'}
+    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar', 'lift'}
     if 'density_cli' in what:
         make_density_cli()
     if 'count_cigar' in what:
         count_cigar_cases()
+    if 'lift' in what:
+        lift_cases()
     if 'align' in what:
         make_align_case()
     if 'cigar' in what:

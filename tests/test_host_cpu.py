@@ -351,3 +351,36 @@ def test_count_cigar_matches_reference_golden():
         want = {k: c[k] for k in ('result', 'error') if k in c}
         assert got == want, c['cigar']
     assert n_fast > 500      # the fast path really took part
+
+
+def test_align_lift_matches_reference_golden():
+    """AlignLift against the answers of the reference's own pavlib.align.AlignLift stored with the table (tests/golden/lift: 3,000
+    point lifts in both directions incl. gap=True, 400 region lifts there and back)."""
+    import json
+    from pav_b200.pavlib import lift, seq
+    d = os.path.join(REPO, 'tests', 'golden', 'lift')
+    df = pd.read_csv(os.path.join(d, 'align.bed'), sep='\t')
+    fai = pd.read_csv(os.path.join(d, 'tig.fai.tsv'), sep='\t', header=None, index_col=0)[1]
+    al = lift.AlignLift(df, fai)
+
+    def plain(x):
+        return None if x is None else [x[0], int(x[1]), bool(x[2]), int(x[3]), int(x[4]), [int(i) for i in x[5]]]
+    n = 0
+    for q in json.load(open(os.path.join(d, 'queries.json'))):
+        if q['f'] == 'region':
+            rq = al.lift_region_to_qry(seq.Region(q['chrom'], q['pos'], q['end']))
+            assert (None if rq is None else [rq.chrom, rq.pos, rq.end, bool(rq.is_rev)]) == q['qry'], q
+            if rq is not None:
+                for gap, key in ((False, 'sub'), (True, 'sub_gap')):
+                    rs = al.lift_region_to_sub(rq, gap=gap)
+                    assert (None if rs is None else [rs.chrom, rs.pos, rs.end, bool(rs.is_rev)]) == q[key], (q, gap)
+        else:
+            f = al.lift_to_qry if q['f'] == 'to_qry' else al.lift_to_sub
+            kw = {'gap': q['gap']} if q['f'] == 'to_sub' else {}
+            if 'error' in q:
+                with pytest.raises(RuntimeError):
+                    f(q['id'], q['pos'], **kw)
+            else:
+                assert plain(f(q['id'], q['pos'], **kw)) == q['result'], q
+        n += 1
+    assert n == 3400
