@@ -455,6 +455,30 @@ def lift_cases(seed=21):
           sum('error' in r for r in out), 'errors')
 
 
+def region_expand_cases(seed=5):
+    """pavlib.seq.Region.expand of the reference: random regions, expansions, balances, with / without shifting, limits given as
+    a Series of chromosome lengths, an int, or absent."""
+    rng = np.random.default_rng(seed)
+    fai = pd.Series({'c': 100000})
+    out = []
+    for _ in range(1200):
+        p = int(rng.integers(0, 99000))
+        e = p + int(rng.integers(1, 9000))
+        bp = int(rng.integers(0, 60000))
+        bal = float(rng.choice([0.25, 0.5, 0.75, 0.0, 1.0, 0.1]))
+        shift = bool(rng.random() < 0.7)
+        lim = ['fai', 'int', 'none'][int(rng.integers(0, 3))]
+        min_pos = int(rng.choice([0, 0, 0, 500]))
+        r = pavlib.seq.Region('c', p, min(e, 100000))
+        r.expand(np.int32(bp) if rng.random() < 0.5 else bp, min_pos=min_pos, max_end={'fai': fai, 'int': 100000, 'none': None}[lim], shift=shift,
+                 balance=bal)
+        out.append({'pos': p, 'end': min(e, 100000), 'bp': bp, 'balance': bal, 'shift': shift, 'max_end': lim, 'min_pos': min_pos,
+                    'result': [int(r.pos), int(r.end)]})
+    with open(os.path.join(HERE, 'region_expand.json'), 'w') as fh:
+        json.dump(out, fh)
+    print('region_expand', len(out))
+
+
 def count_cigar_cases(n_cases=2500, seed=31):
     """pavlib.align.count_cigar of the reference on random CIGAR strings: well-formed ones (clips in every legal and illegal
     arrangement, zero lengths, M with and without allow_m, N / P ops) and malformed text; result tuple or exception class + text."""
@@ -495,13 +519,15 @@ def count_cigar_cases(n_cases=2500, seed=31):
 
 
 if __name__ == '__main__':
-    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar', 'lift'}
+    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar', 'lift', 'region_expand'}
     if 'density_cli' in what:
         make_density_cli()
     if 'count_cigar' in what:
         count_cigar_cases()
     if 'lift' in what:
         lift_cases()
+    if 'region_expand' in what:
+        region_expand_cases()
     if 'align' in what:
         make_align_case()
     if 'cigar' in what:

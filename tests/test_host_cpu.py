@@ -384,3 +384,17 @@ def test_align_lift_matches_reference_golden():
                 assert plain(f(q['id'], q['pos'], **kw)) == q['result'], q
         n += 1
     assert n == 3400
+
+
+def test_region_expand_matches_reference_golden():
+    """Region.expand against stored results of the reference's Region.expand (tests/golden/region_expand.json)."""
+    import json
+    from pav_b200.pavlib import seq
+    fai = pd.Series({'c': 100000})
+    for c in json.load(open(os.path.join(REPO, 'tests', 'golden', 'region_expand.json'))):
+        r = seq.Region('c', c['pos'], c['end'])
+        r.expand(c['bp'], min_pos=c['min_pos'], max_end={'fai': fai, 'int': 100000, 'none': None}[c['max_end']], shift=c['shift'], balance=c['balance'])
+        assert [r.pos, r.end] == c['result'], c
+        r = seq.Region('c', c['pos'], c['end'])
+        r.expand(np.int32(c['bp']), min_pos=c['min_pos'], max_end={'fai': fai, 'int': 100000, 'none': None}[c['max_end']], shift=c['shift'], balance=c['balance'])
+        assert [r.pos, r.end] == c['result'], c
