@@ -326,7 +326,27 @@ def density_secondary(ctx, args, rank):
     except Exception as ex:  # noqa: BLE001
         log('density oracle spot check failed to run:', ex)
     k_ms = float(np.mean(ms))
+    # two roofs for Path B. The k-mer part (reference table, state per contig k-mer, compaction) is HBM work:
+    # per window of W bases ceil(2W/4) plane bytes + 8W table insert + 2*8*(W-k+1) probes + (W-k+1)*(8+4+1) out. The KDE part is
+    # float64 arithmetic on CUDA cores (exp + FMA), not HBM and not tensor cores: no HBM fraction is claimed for it; its size is
+    # the number of evaluated lattice points E against the N informative rows (the reference evaluates every sampled point against
+    # every k-mer of a state: N*E "logical pairs"; the kernels here get the same values from run prefix trees).
+    W, K = 50_000, 31
+    rows = int(st.rows)
+    kmer_bytes = n_win * (-(-2 * W // 4) + 8 * W + 16 * (W - K + 1) + 13 * (W - K + 1))
+    peak, peak_src = measured_peak_gbs()
+    n_eval = int(np.asarray(res['n_eval'], dtype=np.int64).sum())
+    roofs = {
+        'kmer_part': {'bound': 'hbm', 'kernels': 'ref_insert + tig_state + compact', 'algorithmic_bytes': int(kmer_bytes), 'ms': float(st.ms_kmer),
+                      'achieved': kmer_bytes / (st.ms_kmer * 1e-3) / 1e9 if st.ms_kmer > 0 else None, 'peak': peak, 'unit': 'GB/s',
+                      'frac': kmer_bytes / (st.ms_kmer * 1e-3) / 1e9 / peak if st.ms_kmer > 0 else None, 'peak_source': peak_src},
+        'kde_part': {'bound': 'float64 CUDA-core arithmetic (exp + FMA), not HBM', 'kernels': 'runs_stats + kde_tree + kde_eval x2 + gap_classify + interp + finalize',
+                     'ms': float(st.ms_kde), 'rows_N': rows, 'evaluated_points_E': n_eval, 'eval_fraction_E_over_N': n_eval / rows if rows else None,
+                     'logical_pairs': int(st.kde_pairs), 'logical_pairs_per_sec': st.kde_pairs / (st.ms_kde * 1e-3) if st.ms_kde > 0 else None,
+                     'output_bytes': rows * 25},
+    }
     return {
+        'roofline': roofs,
         'metric': 'inv_kmer_density_gbases_per_sec', 'unit': 'Gbases/s', 'value': bases / (k_ms * 1e-3) / 1e9,
         'e2e': {'value': bases / e2e_s / 1e9, 'unit': 'Gbases/s', 'ms_per_step': e2e_s * 1e3, 'h2d_bytes_per_step': 2 * bases, 'd2h_bytes_per_step': e2e_d2h,
                 'api': 'pav_b200.pavlib.density.density_windows (ASCII windows in host memory -> column arrays in host memory)'},
