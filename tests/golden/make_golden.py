@@ -455,6 +455,21 @@ def lift_cases(seed=21):
           sum('error' in r for r in out), 'errors')
 
 
+def make_cigar_cases_extra():
+    """Cases added after the first fixture set (kept separate so the earlier fixtures are not rewritten)."""
+    # records out of order (chromosomes interleaved, later positions first), a non-default frame index, two contigs over the
+    # same reference span (ties on #CHROM, POS, END broken by ID; identical IDs versioned in sorted order)
+    ref, tigs, dfa = synth.make_cigar_workload(78, 2, 40_000, 6, 12_000, edit_rate=0.015, rev_frac=0.5, clip=(3, 4))
+    twin = dfa.iloc[[1, 4]].copy()
+    twin['INDEX'] = [501, 502]
+    dfx = pd.concat([dfa, twin], axis=0)
+    rng = np.random.default_rng(78)
+    dfx = dfx.iloc[rng.permutation(dfx.shape[0])]
+    dfx.index = ['r%02d' % i for i in rng.permutation(dfx.shape[0])]
+    cigar_case('unsorted_overlap_vid', ref, tigs, dfx, hap='h1', version_id=True)
+    cigar_case('unsorted_overlap', ref, tigs, dfx, hap='h1', version_id=False)
+
+
 def region_expand_cases(seed=5):
     """pavlib.seq.Region.expand of the reference: random regions, expansions, balances, with / without shifting, limits given as
     a Series of chromosome lengths, an int, or absent."""
@@ -519,11 +534,13 @@ def count_cigar_cases(n_cases=2500, seed=31):
 
 
 if __name__ == '__main__':
-    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar', 'lift', 'region_expand'}
+    what = set(sys.argv[1:]) or {'cigar', 'homology', 'kmer', 'density', 'inv', 'align', 'density_cli', 'count_cigar', 'lift', 'region_expand', 'cigar_extra'}
     if 'density_cli' in what:
         make_density_cli()
     if 'count_cigar' in what:
         count_cigar_cases()
+    if 'cigar_extra' in what:
+        make_cigar_cases_extra()
     if 'lift' in what:
         lift_cases()
     if 'region_expand' in what:
