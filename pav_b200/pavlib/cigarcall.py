@@ -416,6 +416,23 @@ class _Records:
         self.ascii_names = all(x.isascii() for x in self.chrom_l) and all(x.isascii() for x in self.qry_l)
 
 
+def _any_repeat(*keys):
+    """True when two rows agree on every key array (most significant first). Rows usually arrive sorted by the first key, so a
+    linear pass decides; otherwise one lexsort."""
+    n = len(keys[0])
+    if n < 2:
+        return False
+    k0 = keys[0]
+    if bool((k0[1:] > k0[:-1]).all()):     # strictly increasing first key: no two rows can agree
+        return False
+    order = np.lexsort(keys[::-1])
+    same = np.ones(n - 1, dtype=bool)
+    for k in keys:
+        ks = k[order]
+        same &= ks[1:] == ks[:-1]
+    return bool(same.any())
+
+
 def _snv_ids_order(snv, R, ref_arr, tig_arr, version_id):
     """``(ids in emission order or None, final row order, bases_of)`` for the SNV rows: IDs are only materialised when they are
     versioned (or names are not ASCII); otherwise the sort asks for the ID of a row only inside tie groups."""
@@ -429,12 +446,16 @@ def _snv_ids_order(snv, R, ref_arr, tig_arr, version_id):
         """(REF, ALT) bytes of emission rows ``idx`` (whole table for ID versioning, tie groups of the sort otherwise)."""
         ref_b = np.empty(len(idx), dtype=np.uint8)
         alt_b = np.empty(len(idx), dtype=np.uint8)
-        r_of = rec[idx]
-        for r in np.unique(r_of).tolist():
-            m = r_of == r
-            ref_b[m] = ref_arr[R.ref_id[r]][pos[idx][m]]
-            t = tig_arr[R.qry_id[r]][qp[idx][m]]
-            alt_b[m] = fasta.COMPLEMENT[t] if R.rev[r] else t
+        r_of, p_of, q_of = rec[idx], pos[idx], qp[idx]
+        # one gather per run of rows of the same record (rows arrive in record order: as many runs as records)
+        cut = np.flatnonzero(r_of[1:] != r_of[:-1]) + 1
+        for a, b in zip([0] + cut.tolist(), cut.tolist() + [len(idx)]):
+            if a == b:
+                continue
+            r = int(r_of[a])
+            ref_b[a:b] = ref_arr[R.ref_id[r]][p_of[a:b]]
+            t = tig_arr[R.qry_id[r]][q_of[a:b]]
+            alt_b[a:b] = fasta.COMPLEMENT[t] if R.rev[r] else t
         return ref_b, alt_b
 
     ids = None
@@ -442,7 +463,9 @@ def _snv_ids_order(snv, R, ref_arr, tig_arr, version_id):
         ref_b, alt_b = bases_of(np.arange(n))
         ids = _pyrows.format(n, [('l', R.chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-SNV-'),
                                  ('c', fasta.UPPER[ref_b]), ('c', fasta.UPPER[alt_b])])
-        if version_id:
+        # an ID is '{chrom}-{pos+1}-SNV-{REF}{ALT}': two rows share one exactly when they agree on these four values, so the
+        # string pass of version_id (a Counter over every ID) only runs when such rows exist
+        if version_id and _any_repeat((R.chrom_code_rec[rec] << 40) | pos, (fasta.UPPER[ref_b].astype(np.int64) << 8) | fasta.UPPER[alt_b]):
             ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
         id_of = ids.__getitem__
     else:
@@ -466,8 +489,8 @@ def _indel_ids_order(indel, R, version_id):
     if version_id or not R.ascii_names:
         ids = _pyrows.format(n, [('l', R.chrom_l, rec.astype(np.int64)), ('s', '-'), ('i', pos + 1), ('s', '-'),
                                  ('l', ['INS', 'DEL'], (svt == 1).astype(np.int64)), ('s', '-'), ('i', svlen.astype(np.int64))])
-        if version_id:
-            ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))
+        if version_id and _any_repeat((R.chrom_code_rec[rec] << 40) | pos, ((svt == 1).astype(np.int64) << 40) | svlen.astype(np.int64)):
+            ids = np.ascontiguousarray(variant.version_id(pd.Series(ids, dtype=object)).to_numpy(dtype=object))   # same argument as for SNVs
         id_of = ids.__getitem__
     else:
         def id_of(i):

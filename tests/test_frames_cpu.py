@@ -160,3 +160,27 @@ def test_gzip_members_roundtrip(tmp_path):
     assert pd.read_csv(p, sep='\t', header=None).shape == (200_000, 2)
     flag.write_gzip_members(p, b'', threads=2)
     assert gzip.open(p, 'rb').read() == b''
+
+
+def test_any_repeat_and_versioned_ids_many_records(tmp_path):
+    """_any_repeat (the numeric test that decides whether the string pass of version_id is needed) against a set-based count, and
+    version_id=True on a 60-record table (REF/ALT gathered per run of rows of a record) equal to the oracle's frames."""
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        n = int(rng.integers(0, 12))
+        a, b = rng.integers(0, 4, n), rng.integers(0, 3, n)
+        assert cigarcall._any_repeat(a, b) == (len(set(zip(a.tolist(), b.tolist()))) < n)
+        assert cigarcall._any_repeat(a) == (len(set(a.tolist())) < n)
+        s = np.sort(a)
+        assert cigarcall._any_repeat(s, b) == (len(set(zip(s.tolist(), b.tolist()))) < n)
+    ref, tigs, df = synth.make_cigar_workload(41, 3, 80_000, 60, 4_000, edit_rate=0.02, rev_frac=0.5)
+    twin = df.iloc[[5, 17]].copy()
+    twin['INDEX'] = [900, 901]
+    df = pd.concat([df, twin], axis=0)
+    ref_fa, tig_fa, _ = synth.write_cigar_workload(str(tmp_path), ref, tigs, df)
+    for vid in (True, False):
+        got = frames_from_oracle_rows(df, ref_fa, tig_fa, 'h1', vid)
+        want = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=vid)
+        assert tsv(got[0]) == tsv(want[0]) and tsv(got[1]) == tsv(want[1])
+        assert (got[0].index == want[0].index).all() and (got[1].index == want[1].index).all()
+    assert got[0].shape[0] > 1000
