@@ -74,10 +74,14 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f'libpavgpu.so not built ({LIB_PATH}); run `python -m pav_b200.build`. '
+    path = LIB_PATH
+    tuned = os.environ.get('PAVGPU_LIB')      # tuning builds only (python -m pav_b200.build --variant NAME ...): a path or a variant name
+    if tuned:
+        path = tuned if os.sep in tuned else os.path.join(os.path.dirname(LIB_PATH), f'libpavgpu.{tuned}.so')
+    if not os.path.exists(path):
+        raise RuntimeError(f'libpavgpu.so not built ({path}); run `python -m pav_b200.build`. '
                            'There is no CPU fallback for the hot path.')
-    L = ctypes.CDLL(LIB_PATH)
+    L = ctypes.CDLL(path)
     L.pavgpu_last_error.restype = ctypes.c_char_p
     L.pavgpu_device_count.restype = ctypes.c_int
     L.pavgpu_ctx_create.argtypes = [ctypes.c_int, P(c_vp)]

@@ -1,6 +1,6 @@
 """Build libpavgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m pav_b200.build [--force]
+    python -m pav_b200.build [--force] [-v] [--variant NAME -DMACRO=VALUE ...]
 
 The shared library lands at pav_b200/libpavgpu.so (git-ignored, travels with gpurun snapshots).
 """
@@ -26,18 +26,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, variant=None, defs=()):
+    """Default library, or with ``variant`` a tuning build ``libpavgpu.<variant>.so`` compiled with extra ``defs`` (-D flags):
+    several variants can be built here (no GPU needed), travel to the GPU box with the tree and be A/B-timed in one call by
+    pointing ``PAVGPU_LIB`` at them (pav_b200/_capi.py) -- no nvcc run on GPU time."""
+    lib_path = LIB if variant is None else os.path.join(HERE, f'libpavgpu.{variant}.so')
+    if variant is None and not force and not _stale():
         build_pyrows()
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    obj_dir = os.path.join(HERE, 'build') if variant is None else os.path.join(HERE, 'build', variant)
+    os.makedirs(obj_dir, exist_ok=True)
     for s in srcs:
-        o = os.path.join(HERE, 'build', os.path.basename(s) + '.o')
+        o = os.path.join(obj_dir, os.path.basename(s) + '.o')
         objs.append(o)
-        cmd = [NVCC] + FLAGS + ['-I', os.path.join(REPO, 'include'), '-I', CSRC, '-c', s, '-o', o]
+        cmd = [NVCC] + FLAGS + list(defs) + ['-I', os.path.join(REPO, 'include'), '-I', CSRC, '-c', s, '-o', o]
         if verbose:
             cmd.insert(1, '-Xptxas')
             cmd.insert(2, '-v')
@@ -48,12 +53,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    tmp = LIB + f'.{os.getpid()}.tmp'
+    tmp = lib_path + f'.{os.getpid()}.tmp'
     cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static', '-ldl', '-lrt', '-lpthread']
     subprocess.check_call(cmd)
-    os.replace(tmp, LIB)
+    os.replace(tmp, lib_path)
     build_pyrows(force)
-    return LIB
+    return lib_path
 
 
 PYROWS = os.path.join(HERE, '_pyrows.so')
@@ -74,4 +79,6 @@ def build_pyrows(force=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    # python -m pav_b200.build [--force] [-v] [--variant NAME -DX=1 -DY=2 ...]
+    name = sys.argv[sys.argv.index('--variant') + 1] if '--variant' in sys.argv else None
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, variant=name, defs=[a for a in sys.argv[1:] if a.startswith('-D')]))
