@@ -398,3 +398,64 @@ def test_region_expand_matches_reference_golden():
         r = seq.Region('c', c['pos'], c['end'])
         r.expand(np.int32(c['bp']), min_pos=c['min_pos'], max_end={'fai': fai, 'int': 100000, 'none': None}[c['max_end']], shift=c['shift'], balance=c['balance'])
         assert [r.pos, r.end] == c['result'], c
+
+
+def test_binding_layouts_match_header(tmp_path):
+    """Every struct of include/pavgpu.h as the C compiler lays it out (sizeof + offsetof of each field, from a program compiled
+    against the header) equals the ctypes Structure / numpy dtype the binding uses for it."""
+    import ctypes
+    import subprocess
+    from pav_b200 import _capi
+    bound = {
+        'pavgpu_parse_err': _capi.ParseErr, 'pavgpu_cigar_err': _capi.CigarErr, 'pavgpu_cigar_stats': _capi.CigarStats,
+        'pavgpu_density_params': _capi.DensityParams, 'pavgpu_density_stats': _capi.DensityStats,
+        'pavgpu_snv_row': _capi.SNV_ROW, 'pavgpu_indel_row': _capi.INDEL_ROW, 'pavgpu_density_window': _capi.DENSITY_WINDOW,
+        'pavgpu_density_result': _capi.DENSITY_RESULT,
+    }
+
+    def fields(b):
+        if isinstance(b, np.dtype):
+            return [(n, b.fields[n][1]) for n in b.names], b.itemsize
+        return [(n, getattr(b, n).offset) for n, _ in b._fields_], ctypes.sizeof(b)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pavgpu.h"', 'int main(void) {']
+    for name, b in bound.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for f, _ in fields(b)[0]:
+            lines.append(f'  printf("{name} {f} %zu\\n", offsetof({name}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = str(tmp_path / 'layout')
+    subprocess.check_call(['gcc', '-std=c11', '-I', os.path.join(REPO, 'include'), '-o', exe, str(src)])
+    got = {}
+    for ln in subprocess.check_output([exe]).decode().split('\n'):
+        if ln:
+            s, f, v = ln.split()
+            got[(s, f)] = int(v)
+    for name, b in bound.items():
+        fl, size = fields(b)
+        assert got[(name, 'size')] == size, name
+        for f, off in fl:
+            assert got[(name, f)] == off, (name, f)
+    # every struct typedef of the header is bound (a new struct must come with its binding)
+    import re
+    hdr = open(os.path.join(REPO, 'include', 'pavgpu.h')).read()
+    assert set(re.findall(r'^\} (pavgpu_\w+);', hdr, flags=re.M)) == set(bound)
+
+
+def test_binding_arity_matches_header():
+    """Every prototype of include/pavgpu.h has as many parameters as the argtypes the binding declares for it."""
+    import re
+    from pav_b200 import _capi
+    L = _capi.lib()
+    hdr = re.sub(r'/\*.*?\*/', '', open(os.path.join(REPO, 'include', 'pavgpu.h')).read(), flags=re.S)
+    protos = re.findall(r'\b(pavgpu_\w+)\s*\(([^;{]*?)\)\s*;', hdr)
+    assert {n for n, _ in protos} == set(_capi.EXPORTS)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        fn = getattr(L, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, n, len(fn.argtypes))
+        else:
+            assert n == 0 or name in ('pavgpu_device_count', 'pavgpu_last_error'), name
