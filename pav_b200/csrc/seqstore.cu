@@ -47,6 +47,13 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_ctx_create(int devi
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     if (const char *mx = getenv("PAVGPU_POOL_MAX_MB")) c->pool_max_free = (size_t)strtoull(mx, nullptr, 10) << 20;
+    // PAVGPU_L2_FETCH=32|64|128 (tuning, off by default): hint for the granularity at which L2 fetches from DRAM. The homology
+    // gathers miss L1 on 3.8 M sectors but L2 is asked for 6.3 M and DRAM delivers 4.3 M (ncu, C2): neighbours of scattered
+    // sectors are fetched along; 32 asks the device not to. A hint only -- errors are ignored.
+    if (const char *fg = getenv("PAVGPU_L2_FETCH")) {
+        const size_t v = (size_t)strtoull(fg, nullptr, 10);
+        if (v == 32 || v == 64 || v == 128) { (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v); (void)cudaGetLastError(); }
+    }
     *ctx_out = c;
     return PAVGPU_OK;
 }
