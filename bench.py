@@ -419,7 +419,7 @@ def run_ours(args, rank, world, local):
         ctx.l2_flush()
         st = batch.run(ref_store, tig_store)
         step_ms.append(st.ms_kernels)
-        parts.append((st.ms_scan, st.ms_emit, st.ms_homology))
+        parts.append((st.ms_scan, st.ms_emit, st.ms_homology, st.ms_count))
     wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
     while time.perf_counter() - t_clk < 1.2:   # keep the same kernels running so nvidia-smi sees the clocks under this load
         batch.run(ref_store, tig_store)
@@ -431,7 +431,7 @@ def run_ours(args, rank, world, local):
     ms_per_step = ctl.max(my_ms)
     total_rows = ctl.sum(n_rows)
     value = total_rows / (ms_per_step * 1e-3)
-    scan_ms, emit_ms, hom_ms = [float(np.mean([p[i] for p in parts])) for i in range(3)]
+    scan_ms, emit_ms, hom_ms, count_ms = [float(np.mean([p[i] for p in parts])) for i in range(4)]
 
     # ---- parity spot check of the resident run against the oracle (first records; bounded)
     snv, indel, cerr = batch.fetch()
@@ -537,9 +537,10 @@ def run_ours(args, rank, world, local):
     # ---- roofline of the dominant kernel
     n_ops, n_snv, n_indel, n_chunks = int(st.n_ops), int(st.n_snv), int(st.n_indel), int(st.n_chunks)
     peak, peak_src = measured_peak_gbs()
-    hom_name = ['homology_kernel', 'homology_tiled_kernel', 'homology_nbr_kernel'][int(st.homology_tiled)]   # opt-in variants via PAVGPU_HOMOLOGY_*
-    if int(st.kernel_launches) <= 2:   # single-pass walk: K1+K2+K3 fused (cigar_walk_kernel)
+    hom_name = ['homology_kernel', 'homology_tiled_kernel', 'homology_nbr_kernel', 'homology_bulk_kernel', 'homology_queue_kernel'][int(st.homology_tiled)]   # PAVGPU_HOMOLOGY=gather|tiled|nbr|bulk|queue
+    if int(st.walk_passes) == 1:   # single-pass walk: count + record scan, then K1+K2+K3 fused (cigar_walk_kernel)
         kernels = {
+            'cigar_count+rec_scan': (count_ms, 4 * n_ops + 4 * n_chunks + 4 * 16 * len(df)),
             'cigar_walk_kernel': (scan_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 64 * n_indel),
             hom_name: (hom_ms, (64 + 64) * n_indel),
         }

@@ -140,7 +140,12 @@ typedef struct {
     float ms_scan, ms_emit, ms_homology;    /* per-kernel breakdown */
     int64_t n_ops, n_snv, n_indel, n_chunks;
     int32_t kernel_launches;
-    int32_t homology_tiled;                 /* homology kernel used: 0 gathers (default), 1 per-warp shared-memory tiles, 2 per-indel neighbourhoods */
+    int32_t homology_tiled;                 /* homology kernel used: 0 gathers, 1 per-warp shared-memory tiles, 2 per-indel neighbourhoods (cp.async),
+                                               3 per-indel neighbourhoods (bulk copies + mbarrier), 4 gathers with CTA-pooled scan rests */
+    float ms_count;                         /* per-record row counts + record scan on the device (single-pass walk) */
+    int32_t walk_passes;                    /* 1 single-pass walk (default), 3 multi-pass walk, 0 empty batch */
+    int32_t graph;                          /* 1 when the step was replayed as one CUDA graph */
+    int32_t pad0;
 } pavgpu_cigar_stats;
 
 /* Upload a batch of alignment records (SoA). All arrays have n_rec entries except op_off (n_rec+1).

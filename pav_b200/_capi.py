@@ -37,7 +37,8 @@ class CigarErr(ctypes.Structure):
 class CigarStats(ctypes.Structure):
     _fields_ = [('ms_h2d', c_f32), ('ms_kernels', c_f32), ('ms_d2h', c_f32), ('ms_scan', c_f32), ('ms_emit', c_f32),
                 ('ms_homology', c_f32), ('n_ops', c_i64), ('n_snv', c_i64), ('n_indel', c_i64), ('n_chunks', c_i64),
-                ('kernel_launches', c_i32), ('homology_tiled', c_i32)]
+                ('kernel_launches', c_i32), ('homology_tiled', c_i32), ('ms_count', c_f32), ('walk_passes', c_i32),
+                ('graph', c_i32), ('pad0', c_i32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

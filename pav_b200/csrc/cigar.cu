@@ -565,6 +565,104 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
     }
 }
 
+// K0a / K0b ---------------------------------------------------------------------------------------
+// What the walk needs before it can place rows without atomics: the first SNV / indel row slot of every record and the record of
+// every chunk's first op. Round 1 built them in a host pass over every op (1.9 ms for C2, outside the timed step); here they come
+// from the ops already in HBM: one warp per 256-op chunk sums its rows (a chunk inside one record, the common case, ends in one
+// atomicAdd per counter; chunks spanning records add per lane at every record change), then one CTA turns the per-record counts
+// into exclusive offsets in place (totals at [n_rec]).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+cigar_count_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks, int32_t *__restrict__ chunk_rec,
+                   unsigned long long *__restrict__ rec_ns, unsigned long long *__restrict__ rec_ni, unsigned long long *__restrict__ span_total)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (chunk >= n_chunks) return;
+    const int64_t c0 = chunk * CHUNK, c1 = min(c0 + (int64_t)CHUNK, n_ops);
+    const int64_t g0 = c0 + (int64_t)lane * OPS_PER_LANE;
+    const int64_t rem = n_ops - g0;
+    const int nvalid = rem <= 0 ? 0 : (rem >= OPS_PER_LANE ? OPS_PER_LANE : (int)rem);
+    uint32_t op[OPS_PER_LANE];
+#pragma unroll
+    for (int j = 0; j < OPS_PER_LANE; j++) op[j] = 0;
+    if (nvalid > 0) load_lane_ops(ops, g0, op);
+    int32_t rec_lo = 0;
+    if (lane == 0) { rec_lo = find_rec(rv.op_off, rv.n_rec, c0); chunk_rec[chunk] = rec_lo; }
+    rec_lo = __shfl_sync(FULL, rec_lo, 0);
+    const int64_t rec_end = __ldg(rv.op_off + rec_lo + 1);
+    unsigned long long ns = 0, ni = 0, ra = 0;
+    if (rec_end >= c1) {   // the whole chunk lies in one record (warp-uniform): padding ops are zero and count nothing
+#pragma unroll
+        for (int j = 0; j < OPS_PER_LANE; j++) {
+            const uint32_t code = op[j] & 15u, len = op[j] >> 4;
+            ns += (code == PAVGPU_OP_X) ? len : 0u;
+            ni += (code == PAVGPU_OP_I || code == PAVGPU_OP_D) ? 1u : 0u;
+            ra += ((REF_ADV_MASK >> code) & 1u) ? len : 0u;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ns += __shfl_xor_sync(FULL, ns, d); ni += __shfl_xor_sync(FULL, ni, d); ra += __shfl_xor_sync(FULL, ra, d);
+        }
+        if (lane == 0) {
+            if (ns) atomicAdd(rec_ns + rec_lo, ns);
+            if (ni) atomicAdd(rec_ni + rec_lo, ni);
+        }
+    } else {
+        if (nvalid > 0) {
+            int32_t rec = g0 >= rec_end ? find_rec(rv.op_off, rv.n_rec, g0) : rec_lo;
+            int64_t next_off = __ldg(rv.op_off + rec + 1);
+#pragma unroll
+            for (int j = 0; j < OPS_PER_LANE; j++) {
+                if (j < nvalid) {
+                    const int64_t g = g0 + j;
+                    if (g >= next_off) {
+                        if (ns) atomicAdd(rec_ns + rec, ns);
+                        if (ni) atomicAdd(rec_ni + rec, ni);
+                        ns = 0; ni = 0;
+                        while (g >= next_off) { ++rec; next_off = __ldg(rv.op_off + rec + 1); }
+                    }
+                    const uint32_t code = op[j] & 15u, len = op[j] >> 4;
+                    ns += (code == PAVGPU_OP_X) ? len : 0u;
+                    ni += (code == PAVGPU_OP_I || code == PAVGPU_OP_D) ? 1u : 0u;
+                    ra += ((REF_ADV_MASK >> code) & 1u) ? len : 0u;
+                }
+            }
+            if (ns) atomicAdd(rec_ns + rec, ns);
+            if (ni) atomicAdd(rec_ni + rec, ni);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ra += __shfl_xor_sync(FULL, ra, d);
+    }
+    if (lane == 0 && ra) atomicAdd(span_total, ra);
+}
+
+// In-place exclusive scan of the two per-record count arrays (n_rec entries each, totals written to [n_rec]); one CTA.
+__global__ void __launch_bounds__(SCAN_THREADS)
+rec_scan_kernel(unsigned long long *__restrict__ a, unsigned long long *__restrict__ b, int32_t n_rec)
+{
+    __shared__ unsigned long long s_a[SCAN_THREADS], s_b[SCAN_THREADS];
+    const int t = threadIdx.x;
+    const int32_t per = (n_rec + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int32_t lo = min(t * per, n_rec), hi = min(lo + per, n_rec);
+    unsigned long long sa = 0, sb = 0;
+    for (int32_t r = lo; r < hi; r++) { sa += a[r]; sb += b[r]; }
+    s_a[t] = sa; s_b[t] = sb;
+    __syncthreads();
+    for (int d = 1; d < SCAN_THREADS; d <<= 1) {
+        const unsigned long long va = t >= d ? s_a[t - d] : 0ull, vb = t >= d ? s_b[t - d] : 0ull;
+        __syncthreads();
+        s_a[t] += va; s_b[t] += vb;
+        __syncthreads();
+    }
+    unsigned long long ea = t > 0 ? s_a[t - 1] : 0ull, eb = t > 0 ? s_b[t - 1] : 0ull;
+    for (int32_t r = lo; r < hi; r++) {
+        const unsigned long long ca = a[r], cb = b[r];
+        a[r] = ea; b[r] = eb;
+        ea += ca; eb += cb;
+    }
+    if (t == SCAN_THREADS - 1) { a[n_rec] = s_a[t]; b[n_rec] = s_b[t]; }
+}
+
 // K4 ---------------------------------------------------------------------------------------------
 // Thread per indel: the left shift, then the four breakpoint homologies at the shifted position (cigarcall.py:149-155,
 // 178-182 / :225-231,247-251 calling call.py:542-647), 32 bases per step on the packed planes. Everything the thread needs
@@ -575,7 +673,25 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
 // extraction -- all between 0.101 and 0.16 ms against 0.083 ms for this form.
 constexpr int HOM_THREADS = 256;
 
-__global__ void __launch_bounds__(HOM_THREADS, 4)
+// Scoring body shared by the homology kernels: 2 = score_indel2 (convergent first trips against the circular SV pattern, the
+// default), 1 = score_indel (one data-dependent loop per scan; kept for A/B builds: python -m pav_b200.build --variant v1 -DHOM_SCORE_V=1).
+#ifndef HOM_SCORE_V
+#define HOM_SCORE_V 2
+#endif
+template <bool TILED>
+__device__ __forceinline__ void score_body(const OSeq &R, const OSeq &Q, int32_t svtype, int32_t n, int32_t pr, int32_t pq, int32_t eqb, IndelScore &o)
+{
+#if HOM_SCORE_V == 2
+    score_indel2<TILED>(R, Q, svtype, n, pr, pq, eqb, o);
+#else
+    score_indel<TILED>(R, Q, svtype, n, pr, pq, eqb, o);
+#endif
+}
+
+#ifndef HOM_MIN_BLOCKS
+#define HOM_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(HOM_THREADS, HOM_MIN_BLOCKS)
 homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
 {
     const int64_t i = (int64_t)blockIdx.x * HOM_THREADS + threadIdx.x;
@@ -586,7 +702,7 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes 
     const OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0};
     const OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w};
     IndelScore o;
-    score_indel<false>(R, Q, svtype, n, pr, pq, eqb, o);
+    score_body<false>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
     dst[0] = make_int4(rec, op_idx, svtype, n);
     dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
@@ -666,7 +782,7 @@ homology_tiled_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
     }
     if (!live) return;
     IndelScore o;
-    score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
+    score_body<true>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
     dst[0] = make_int4(rec, op_idx, svtype, n);
     dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
@@ -728,9 +844,212 @@ homology_nbr_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPla
         if (wq >= 0) { Q.t_w0 = wq; Q.t_nw1 = NBR_WORDS - 1; }
     }
     IndelScore o;
-    score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
+    score_body<true>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
     dst[0] = make_int4(rec, op_idx, svtype, n);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
+    dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
+}
+
+// K4b: thread per indel; the 256-base neighbourhood of the breakpoint in each sequence (64 B of the 2-bit plane = two sectors,
+// 32 B of the mask plane) lands in the thread's shared-memory slot through four bulk asynchronous copies (cp.async.bulk, the
+// 1-D TMA path: SASS UBLKCP) that signal one mbarrier per warp. The copies leave the SM through the TMA unit, not through
+// the LSU / L1 pipeline: the gather kernel issues ~54 scattered 8- and 4-byte loads per indel, each a separate L1 wavefront per
+// lane, and runs at the rate of that pipeline whatever its occupancy; here an indel costs four copy descriptors and the
+// windows of the scans are shared-memory reads. Slots are padded to 80 / 48 bytes: 16-byte aligned as the copies require, and
+// spread over the banks. Windows that leave the neighbourhood (long SVs, tandem repeats) use the global loads.
+#ifndef HOMB_THREADS_N
+#define HOMB_THREADS_N 128
+#endif
+constexpr int HOMB_THREADS = HOMB_THREADS_N;
+constexpr int HOMB_P_STRIDE = 80, HOMB_M_STRIDE = 48;
+constexpr size_t HOMB_SMEM = (size_t)2 * HOMB_THREADS * (HOMB_P_STRIDE + HOMB_M_STRIDE);
+static_assert(NBR_WORDS == 8, "copy sizes below are for 8-word neighbourhoods");
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned tx)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tMBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBAR_DONE;\n\tbra MBAR_WAIT;\n\tMBAR_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(HOMB_THREADS)
+homology_bulk_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, int64_t ref_words, int64_t qry_words,
+                     pavgpu_indel_row *__restrict__ rows)
+{
+    extern __shared__ __align__(16) unsigned char hb_smem[];
+    __shared__ __align__(8) unsigned long long s_bar[HOMB_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * HOMB_THREADS + threadIdx.x;
+    if ((int64_t)blockIdx.x * HOMB_THREADS + (threadIdx.x & ~31) >= n_indel) return;   // whole warp past the end
+    const bool live = i < n_indel;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+    if (lane == 0) {
+        mbar_init(bar, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned char *pbase = hb_smem, *mbase = hb_smem + (size_t)2 * HOMB_THREADS * HOMB_P_STRIDE;
+    uint64_t *s_rp = reinterpret_cast<uint64_t *>(pbase + (size_t)threadIdx.x * HOMB_P_STRIDE);
+    uint64_t *s_qp = reinterpret_cast<uint64_t *>(pbase + (size_t)(HOMB_THREADS + threadIdx.x) * HOMB_P_STRIDE);
+    uint32_t *s_rm = reinterpret_cast<uint32_t *>(mbase + (size_t)threadIdx.x * HOMB_M_STRIDE);
+    uint32_t *s_qm = reinterpret_cast<uint32_t *>(mbase + (size_t)(HOMB_THREADS + threadIdx.x) * HOMB_M_STRIDE);
+    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + (live ? i : n_indel - 1));   // idle lanes of the last warp repeat the last stub
+    const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
+    const int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
+    OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, s_rp, s_rm, 0, 0};
+    OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, s_qp, s_qm, 0, 0};
+    const int32_t L = (int32_t)Q.len;
+    const int64_t wr = live ? nbr_first_word(R.base + pr, ref_words) : -1;
+    const int64_t wq = live ? nbr_first_word(Q.rev ? Q.base + ((long long)L - 1 - pq) : Q.base + pq, qry_words) : -1;
+    __syncwarp();   // the barrier is initialised
+    const unsigned tx = (wr >= 0 ? 96u : 0u) + (wq >= 0 ? 96u : 0u);
+    if (tx) mbar_arrive_tx(bar, tx); else mbar_arrive(bar);
+    if (wr >= 0) {
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rp), ref.pack2 + wr, 64, bar);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_rm), ref.nmask + wr, 32, bar);
+        R.t_w0 = wr; R.t_nw1 = NBR_WORDS - 1;
+    }
+    if (wq >= 0) {
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_qp), qry.pack2 + wq, 64, bar);
+        bulk_g2s((unsigned)__cvta_generic_to_shared(s_qm), qry.nmask + wq, 32, bar);
+        Q.t_w0 = wq; Q.t_nw1 = NBR_WORDS - 1;
+    }
+    mbar_wait(bar, 0);
+    if (!live) return;
+    IndelScore o;
+    score_body<true>(R, Q, svtype, n, pr, pq, eqb, o);
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(rec, op_idx, svtype, n);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
+    dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
+}
+
+// K4q: thread per indel for the convergent part, CTA-pooled rests. ncu on the per-thread kernels (profiles/r02_ncu_homology_gather_v2.txt):
+// the first trips of all scans run with 31 of 32 lanes, but the few scans that go on (tandem repeats: ~3 % of the scans of C2,
+// ~4 trips each) execute one lane at a time -- 32 M of the kernel's 51 M warp instructions at 1.0 active threads. Here a scan
+// that matched its whole first window is not continued by its owner: it is appended to a shared-memory queue (owner, scan), and
+// after a CTA barrier the queue is worked off one item per thread, so the rest loops run with full warps of unrelated long scans.
+// Two rounds, because the left shift must be known before the four breakpoint homologies can start: round A = rests of the
+// left-shift scans (few: their threads carry on with the owner's first trips while all other owners do their own), round B =
+// rests of the homologies. An item's thread re-reads its owner's stub (L1/L2-resident).
+constexpr int HOMQ_THREADS = 256;
+
+struct StubView {
+    int32_t rec, op_idx, svtype, n, pr, pq, eqb;
+    OSeq R, Q;
+};
+
+__device__ __forceinline__ StubView load_stub(const IndelStub *__restrict__ stubs, int64_t i, const SeqPlanes &ref, const SeqPlanes &qry)
+{
+    const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
+    const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
+    StubView v;
+    v.rec = a.x; v.op_idx = a.y; v.svtype = a.z; v.n = a.w; v.pr = b.x; v.pq = b.y; v.eqb = b.z;
+    v.R = OSeq{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, nullptr, nullptr, 0, 0};
+    v.Q = OSeq{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, nullptr, nullptr, 0, 0};
+    return v;
+}
+
+// Append one item per flagged lane to the CTA queue (warp-aggregated: one shared atomic per warp).
+__device__ __forceinline__ void queue_push(bool flag, uint16_t item, uint16_t *q, int *cnt)
+{
+    const unsigned m = __ballot_sync(FULL, flag);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cnt, __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (flag) q[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
+#ifndef HOMQ_MIN_BLOCKS
+#define HOMQ_MIN_BLOCKS 3
+#endif
+
+__global__ void __launch_bounds__(HOMQ_THREADS, HOMQ_MIN_BLOCKS)
+homology_queue_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
+{
+    __shared__ int s_cnt[2];
+    __shared__ uint16_t s_qa[HOMQ_THREADS];        // round A items: owner thread
+    __shared__ uint16_t s_qb[HOMQ_THREADS * 4];    // round B items: owner thread << 3 | scan (1..4)
+    __shared__ int32_t s_res[HOMQ_THREADS * 4];    // rest of homology k of owner t at [t * 4 + k]
+    __shared__ int32_t s_hom[HOMQ_THREADS * 4];    // first trips of owner t computed by its round-A item thread
+    __shared__ int32_t s_ls[HOMQ_THREADS];
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * HOMQ_THREADS, i = i0 + tid;
+    const bool live = i < n_indel;
+    if (tid < 2) s_cnt[tid] = 0;
+    const StubView v = load_stub(stubs, live ? i : n_indel - 1, ref, qry);
+    const bool ins = v.svtype == 0;
+    // ---- left shift: first trip by the owner; a scan that goes on (and can still grow the shift) becomes a round-A item
+    int h0 = indel_phase0<false>(v.R, v.Q, ins, v.n, v.pr, v.pq);
+    if (v.eqb <= 0 || !live) h0 = 0;
+    const bool need0 = h0 == 32 && v.eqb > 32;
+    __syncthreads();                               // s_cnt is zero
+    queue_push(need0, (uint16_t)tid, s_qa, &s_cnt[0]);
+    __syncthreads();
+    const int n_a = s_cnt[0];
+    // ---- round A and the first trips of the four breakpoint homologies, side by side: thread t < n_a finishes the left-shift scan
+    // of item t's owner and goes straight on to that owner's first trips; every owner whose shift is already known does its own
+    if (tid < n_a) {
+        const int owner = s_qa[tid];
+        const StubView w = load_stub(stubs, i0 + owner, ref, qry);
+        const bool w_ins = w.svtype == 0;
+        const int ls_a = min(w.eqb, indel_rest<false>(w.R, w.Q, w_ins, w.n, w.pr, w.pq, 0, 0));
+        int hom_a[4];
+        indel_phase1<false>(w.R, w.Q, w_ins, w.n, w.pr, w.pq, ls_a, hom_a);
+        s_ls[owner] = ls_a;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s_hom[owner * 4 + k] = hom_a[k];
+    }
+    int ls = min(v.eqb, h0);
+    int hom[4] = {0, 0, 0, 0};
+    if (!need0) {
+        indel_phase1<false>(v.R, v.Q, ins, v.n, v.pr, v.pq, ls, hom);
+        s_ls[tid] = ls;
+    }
+    __syncthreads();                               // s_ls / s_hom of round-A owners are written
+    if (need0) {
+        ls = s_ls[tid];
+#pragma unroll
+        for (int k = 0; k < 4; k++) hom[k] = s_hom[tid * 4 + k];
+    }
+    // ---- round B: rests of the homologies, pooled over the CTA
+#pragma unroll
+    for (int k = 0; k < 4; k++) queue_push(live && hom[k] == 32, (uint16_t)((tid << 3) | (k + 1)), s_qb, &s_cnt[1]);
+    __syncthreads();
+    for (int t = tid; t < s_cnt[1]; t += HOMQ_THREADS) {
+        const int owner = s_qb[t] >> 3, sc = s_qb[t] & 7;
+        const StubView w = load_stub(stubs, i0 + owner, ref, qry);
+        s_res[owner * 4 + sc - 1] = indel_rest<false>(w.R, w.Q, w.svtype == 0, w.n, w.pr, w.pq, s_ls[owner], sc);
+    }
+    __syncthreads();
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (hom[k] == 32) hom[k] = s_res[tid * 4 + k];
+    IndelScore o;
+    indel_finish(v.Q, ins, v.n, v.pr, v.pq, ls, hom, o);
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(v.rec, v.op_idx, v.svtype, v.n);
     dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
     dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
     dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
@@ -757,7 +1076,8 @@ struct pavgpu_cigar_batch {
     pavgpu_ctx *ctx;
     int32_t n_rec;
     int64_t n_ops, n_chunks;
-    void *d_arena;                       // one pooled block; everything below points into it
+    void *d_arena;                       // inputs + per-record / per-chunk tables: one pooled block
+    void *d_rows_arena;                  // row buffers (and the multi-pass scratch), sized after the first device count
     int32_t *d_ref_id, *d_qry_id, *d_pos;
     uint8_t *d_rev;
     int64_t *d_op_off;
@@ -766,27 +1086,34 @@ struct pavgpu_cigar_batch {
     uint2 *d_cnt;
     int2 *d_pre_rq;
     longlong2 *d_pre_cnt;
-    int64_t *d_totals;                   // [0] n_snv, [1] n_indel
+    int64_t *d_totals;                   // [0] n_snv, [1] n_indel written by the walk; [2] reference span (count kernel)
     unsigned long long *d_first_illegal;
-    int4 *d_snv; int64_t cap_snv;        // multi-pass walk: separate blocks sized after the scan
+    int4 *d_snv; int64_t cap_snv;
     IndelStub *d_stub; pavgpu_indel_row *d_indel; int64_t cap_indel;
-    bool rows_in_arena;
     int64_t n_snv, n_indel;
-    int64_t host_n_snv, host_n_indel;   // counted on the host while the ops were staged
-    int64_t host_ref_span;              // reference bases the records advance over (same pass): indel density picks the homology kernel
+    bool sized;                          // row buffers (single-pass) / scan scratch (multi-pass) allocated
+    bool cnt_valid;                      // the device count has run: totals known
+    int64_t cnt_n_snv, cnt_n_indel;      // row totals from the device count (cigar_count_kernel + rec_scan_kernel)
+    int64_t ref_span;                    // reference bases the records advance over (same pass): indel density picks the homology kernel
     ulonglong2 *d_desc;
-    int64_t *d_rec_snv_off, *d_rec_indel_off;   // first row slot of every record (host-counted)
-    int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (host-built index)
+    int64_t *d_rec_snv_off, *d_rec_indel_off;   // per-record row counts -> first row slot of every record (device-built, n_rec + 1 entries)
+    int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (device-built)
     RecDesc *d_recdesc;                          // per-record constants of the current (ref_store, qry_store) pair
     uint64_t recdesc_ref_uid, recdesc_qry_uid;   // stores the table was built for (0 = none yet)
     std::vector<RecDesc> h_recdesc;
     std::vector<int32_t> h_ref_id, h_qry_id;
     std::vector<uint8_t> h_rev;
     bool fused;
-    int hom_kernel;                      // homology kernel of the last run: 0 gathers, 1 warp tiles, 2 per-indel neighbourhoods
+    int hom_kernel;                      // homology kernel of the last run: 0 gathers, 1 warp tiles, 2 / 3 per-indel neighbourhoods
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
+    // the whole step (count, record scan, walk, homology + their memsets) as one CUDA graph, captured on the second run of a
+    // resident batch and replayed while the stores and the kernel choice stay the same
+    cudaGraphExec_t gexec;
+    uint64_t g_ref_uid, g_qry_uid;
+    int g_hom;
+    int runs;
     // host view of the ops for explaining an illegal op (error path only): borrowed from the caller in the one-shot
     // call, copied for resident batches
     const uint32_t *h_ops;
@@ -851,8 +1178,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_parse(const c
 
 static void batch_release(pavgpu_cigar_batch *b)
 {
+    if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
     pav_dev_free(b->ctx, b->d_arena);
-    if (!b->rows_in_arena) { pav_dev_free(b->ctx, b->d_snv); pav_dev_free(b->ctx, b->d_stub); pav_dev_free(b->ctx, b->d_indel); }
+    pav_dev_free(b->ctx, b->d_rows_arena);
+    if (!b->fused) { pav_dev_free(b->ctx, b->d_snv); pav_dev_free(b->ctx, b->d_stub); pav_dev_free(b->ctx, b->d_indel); }
 }
 
 extern "C" __attribute__((visibility("default"))) void pavgpu_cigar_batch_free(pavgpu_cigar_batch *b)
@@ -889,48 +1218,16 @@ static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_i
     b->h_pos.assign(pos, pos + n_rec);
     b->h_ref_id.assign(ref_seq_id, ref_seq_id + n_rec); b->h_qry_id.assign(qry_seq_id, qry_seq_id + n_rec); b->h_rev.assign(rev, rev + n_rec);
     tr.mark("host copies");
-    // one sequential pass over the ops (the host has to touch them anyway to stage them): rows per record -> first row slot
-    // of every record, and the record of every chunk's first op
-    std::vector<int64_t> rec_snv_off((size_t)n_rec + 1), rec_indel_off((size_t)n_rec + 1);
-    for (int32_t r = 0; r < n_rec; r++) {
-        rec_snv_off[r] = b->host_n_snv; rec_indel_off[r] = b->host_n_indel;
-        int64_t ns = 0, ni = 0, ra = 0;
-        for (int64_t i = op_off[r]; i < op_off[r + 1]; i++) {
-            const uint32_t op = ops[i], code = op & 15u;
-            ns += (code == PAVGPU_OP_X) ? (op >> 4) : 0u;
-            ni += (code == PAVGPU_OP_I) | (code == PAVGPU_OP_D);
-            ra += ((REF_ADV_MASK >> code) & 1u) ? (op >> 4) : 0u;
-        }
-        b->host_n_snv += ns; b->host_n_indel += ni; b->host_ref_span += ra;
-    }
-    rec_snv_off[n_rec] = b->host_n_snv; rec_indel_off[n_rec] = b->host_n_indel;
-    std::vector<int32_t> chunk_rec((size_t)std::max<int64_t>(b->n_chunks, 1), 0);
-    {
-        int32_t r = 0;
-        for (int64_t c = 0; c < b->n_chunks; c++) {
-            int64_t g = c * CHUNK;
-            while (r + 1 < n_rec && op_off[r + 1] <= g) r++;
-            chunk_rec[(size_t)c] = r;
-        }
-    }
-    tr.mark("host row count pass");
-    // single-pass walk unless the descriptor fields would overflow (33-bit SNV count, 30-bit indel count) or the
-    // multi-pass kernels are requested for A/B timing
+    // single-pass walk unless the multi-pass kernels are requested for A/B timing (or, decided after the device count, the
+    // descriptor fields would overflow: 33-bit SNV count, 30-bit indel count)
     const char *mp = getenv("PAVGPU_CIGAR_MULTIPASS");
-    b->fused = !(mp && mp[0] == '1') && b->host_n_snv < ((int64_t)1 << 33) && b->host_n_indel < ((int64_t)1 << 30);
+    b->fused = !(mp && mp[0] == '1');
     const size_t ops_padded = (size_t)std::max<int64_t>(b->n_chunks, 1) * CHUNK;
     const size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1), nr = (size_t)std::max(n_rec, 1);
     ArenaPlan ap;
     const size_t o_ref_id = ap.add(nr * 4), o_qry_id = ap.add(nr * 4), o_pos = ap.add(nr * 4), o_rev = ap.add(nr), o_op_off = ap.add((nr + 1) * 8);
-    const size_t o_ops = ap.add(ops_padded * 4), o_totals = ap.add(16), o_illegal = ap.add(8), o_desc = ap.add(nc * sizeof(ulonglong2));
+    const size_t o_ops = ap.add(ops_padded * 4), o_totals = ap.add(32), o_illegal = ap.add(8), o_desc = ap.add(nc * sizeof(ulonglong2));
     const size_t o_rso = ap.add((nr + 1) * 8), o_rio = ap.add((nr + 1) * 8), o_crec = ap.add(nc * 4), o_rdesc = ap.add(nr * sizeof(RecDesc));
-    size_t o_agg = 0, o_cnt = 0, o_prq = 0, o_pcnt = 0, o_snv = 0, o_stub = 0, o_indel = 0;
-    if (!b->fused) { o_agg = ap.add(nc * sizeof(int4)); o_cnt = ap.add(nc * sizeof(uint2)); o_prq = ap.add(nc * sizeof(int2)); o_pcnt = ap.add(nc * sizeof(longlong2)); }
-    else {   // row buffers are sized from the host counts: no mid-run round trip
-        o_snv = ap.add((size_t)b->host_n_snv * sizeof(int4));
-        o_stub = ap.add((size_t)b->host_n_indel * sizeof(IndelStub));
-        o_indel = ap.add((size_t)b->host_n_indel * sizeof(pavgpu_indel_row));
-    }
     int rc = [&]() -> int {
         cudaStream_t st = ctx->stream;
         cudaError_t e = pav_dev_alloc(ctx, ap.off, &b->d_arena);
@@ -941,19 +1238,8 @@ static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_i
         b->d_totals = (int64_t *)(base + o_totals); b->d_first_illegal = (unsigned long long *)(base + o_illegal);
         b->d_desc = (ulonglong2 *)(base + o_desc); b->d_rec_snv_off = (int64_t *)(base + o_rso); b->d_rec_indel_off = (int64_t *)(base + o_rio);
         b->d_chunk_rec = (int32_t *)(base + o_crec); b->d_recdesc = (RecDesc *)(base + o_rdesc);
-        if (!b->fused) {
-            b->d_agg = (int4 *)(base + o_agg); b->d_cnt = (uint2 *)(base + o_cnt); b->d_pre_rq = (int2 *)(base + o_prq); b->d_pre_cnt = (longlong2 *)(base + o_pcnt);
-            b->rows_in_arena = false;
-        } else {
-            b->d_snv = (int4 *)(base + o_snv); b->d_stub = (IndelStub *)(base + o_stub); b->d_indel = (pavgpu_indel_row *)(base + o_indel);
-            b->cap_snv = b->host_n_snv; b->cap_indel = b->host_n_indel;
-            b->rows_in_arena = true;
-        }
         tr.mark("arena");
         CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
-        CUDA_TRY(cudaMemcpyAsync(b->d_rec_snv_off, rec_snv_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(b->d_rec_indel_off, rec_indel_off.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(b->d_chunk_rec, chunk_rec.data(), chunk_rec.size() * 4, cudaMemcpyHostToDevice, st));
         if (n_rec) {
             CUDA_TRY(cudaMemcpyAsync(b->d_ref_id, ref_seq_id, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(b->d_qry_id, qry_seq_id, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
@@ -965,7 +1251,7 @@ static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_i
         if (ops_padded > (size_t)n_ops)   // lanes always load whole vectors: zero the tail of the last chunk
             CUDA_TRY(cudaMemsetAsync(b->d_ops + n_ops, 0, (ops_padded - (size_t)n_ops) * 4, st));
         CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        CUDA_TRY(cudaStreamSynchronize(st));   // the staging vectors above die with this scope
+        CUDA_TRY(cudaStreamSynchronize(st));   // the caller's arrays are free again
         b->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
         tr.mark("h2d");
         return PAVGPU_OK;
@@ -992,41 +1278,149 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_create(
 constexpr int64_t HOM_TILED_MAX_SPACING = 700;   // mean reference bases per indel up to which 32 indels fit a 24.5 kbp tile
 constexpr int64_t HOM_TILED_MIN_INDELS = 4096;
 
+// Kernel choice: PAVGPU_HOMOLOGY = gather | queue | bulk | nbr | tiled | tiled-auto (the older switches PAVGPU_HOMOLOGY_TILED=1|auto and
+// PAVGPU_HOMOLOGY_NBR=1 still work). 0 gathers, 1 warp tiles, 2 per-indel neighbourhoods (cp.async), 3 per-indel neighbourhoods
+// (bulk copies + mbarrier), 4 gathers with CTA-pooled scan rests (queue).
+#ifndef HOM_DEFAULT_KERNEL
+#define HOM_DEFAULT_KERNEL 0
+#endif
+
+static int homology_choice(const pavgpu_cigar_batch *b)
+{
+    const char *h = getenv("PAVGPU_HOMOLOGY");
+    const char *force = getenv("PAVGPU_HOMOLOGY_TILED");
+    const char *nbr = getenv("PAVGPU_HOMOLOGY_NBR");
+    const bool dense = b->n_indel >= HOM_TILED_MIN_INDELS && b->ref_span <= HOM_TILED_MAX_SPACING * b->n_indel;
+    if (h && h[0]) {
+        if (!strcmp(h, "gather")) return 0;
+        if (!strcmp(h, "tiled")) return 1;
+        if (!strcmp(h, "tiled-auto")) return dense ? 1 : 0;
+        if (!strcmp(h, "nbr")) return 2;
+        if (!strcmp(h, "bulk")) return 3;
+        if (!strcmp(h, "queue")) return 4;
+    }
+    if (force && force[0] == '1') return 1;
+    if (force && force[0] == 'a' && dense) return 1;
+    if (nbr && nbr[0] == '1') return 2;
+    return HOM_DEFAULT_KERNEL;
+}
+
+template <typename K>
+static int set_dyn_smem_once(K kernel, size_t bytes, int dev, bool (&done)[64])
+{
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return PAVGPU_OK;
+}
+
 static int launch_homology(pavgpu_cigar_batch *b, cudaStream_t st, const pavgpu_seqstore *ref_store, const pavgpu_seqstore *qry_store)
 {
     const SeqPlanes pl_ref = planes_of(ref_store), pl_qry = planes_of(qry_store);
-    const char *force = getenv("PAVGPU_HOMOLOGY_TILED");
-    bool tiled = false;
-    if (force && force[0] == '1') tiled = true;
-    else if (force && force[0] == 'a') tiled = b->n_indel >= HOM_TILED_MIN_INDELS && b->host_ref_span <= HOM_TILED_MAX_SPACING * b->n_indel;
-    b->hom_kernel = tiled ? 1 : 0;
-    const char *nbr = getenv("PAVGPU_HOMOLOGY_NBR");
-    if (!tiled && nbr && nbr[0] == '1') {
-        static bool nbr_attr_set[64] = {};
-        const int dev = b->ctx->device;
-        if (dev < 0 || dev >= 64 || !nbr_attr_set[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(homology_nbr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NBR_SMEM));
-            if (dev >= 0 && dev < 64) nbr_attr_set[dev] = true;
-        }
+    const int64_t rw = ref_store->total_bases / 32, qw = qry_store->total_bases / 32;
+    const int dev = b->ctx->device;
+    b->hom_kernel = homology_choice(b);
+    if (b->hom_kernel == 4) {
+        const unsigned hb = (unsigned)((b->n_indel + HOMQ_THREADS - 1) / HOMQ_THREADS);
+        homology_queue_kernel<<<hb, HOMQ_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
+    } else if (b->hom_kernel == 3) {
+        static bool done[64] = {};
+        int rc = set_dyn_smem_once(homology_bulk_kernel, HOMB_SMEM, dev, done);
+        if (rc) return rc;
+        const unsigned hb = (unsigned)((b->n_indel + HOMB_THREADS - 1) / HOMB_THREADS);
+        homology_bulk_kernel<<<hb, HOMB_THREADS, HOMB_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, rw, qw, b->d_indel);
+    } else if (b->hom_kernel == 2) {
+        static bool done[64] = {};
+        int rc = set_dyn_smem_once(homology_nbr_kernel, NBR_SMEM, dev, done);
+        if (rc) return rc;
         const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
-        homology_nbr_kernel<<<hb, HOM_THREADS, NBR_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, ref_store->total_bases / 32,
-                                                              qry_store->total_bases / 32, b->d_indel);
-        b->hom_kernel = 2;
-    } else if (tiled) {
-        static bool attr_set[64] = {};
-        const int dev = b->ctx->device;
-        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(homology_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOMT_SMEM));
-            if (dev >= 0 && dev < 64) attr_set[dev] = true;
-        }
+        homology_nbr_kernel<<<hb, HOM_THREADS, NBR_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, rw, qw, b->d_indel);
+    } else if (b->hom_kernel == 1) {
+        static bool done[64] = {};
+        int rc = set_dyn_smem_once(homology_tiled_kernel, HOMT_SMEM, dev, done);
+        if (rc) return rc;
         const unsigned hb = (unsigned)((b->n_indel + HOMT_THREADS - 1) / HOMT_THREADS);
-        homology_tiled_kernel<<<hb, HOMT_THREADS, HOMT_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, ref_store->total_bases / 32,
-                                                                  qry_store->total_bases / 32, b->d_indel);
+        homology_tiled_kernel<<<hb, HOMT_THREADS, HOMT_SMEM, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, rw, qw, b->d_indel);
     } else {
         const unsigned hb = (unsigned)((b->n_indel + HOM_THREADS - 1) / HOM_THREADS);
         homology_kernel<<<hb, HOM_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
     }
     CUDA_TRY(cudaGetLastError());
+    return PAVGPU_OK;
+}
+
+// Row counts on the device (K0a + K0b): per-record counts -> exclusive offsets in place, chunk -> record index, reference span.
+static int launch_count(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv)
+{
+    CUDA_TRY(cudaMemsetAsync(b->d_rec_snv_off, 0, (size_t)(b->n_rec + 1) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_rec_indel_off, 0, (size_t)(b->n_rec + 1) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 32, st));
+    const unsigned blocks = (unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    cigar_count_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec,
+                                                                 reinterpret_cast<unsigned long long *>(b->d_rec_snv_off),
+                                                                 reinterpret_cast<unsigned long long *>(b->d_rec_indel_off),
+                                                                 reinterpret_cast<unsigned long long *>(b->d_totals + 2));
+    rec_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(reinterpret_cast<unsigned long long *>(b->d_rec_snv_off),
+                                                 reinterpret_cast<unsigned long long *>(b->d_rec_indel_off), b->n_rec);
+    CUDA_TRY(cudaGetLastError());
+    return PAVGPU_OK;
+}
+
+// The single-pass step after the count: descriptors cleared, walk, homology. Events 1 and 3 split the step for the stats.
+static int launch_walk_homology(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv, const pavgpu_seqstore *ref_store,
+                                const pavgpu_seqstore *qry_store)
+{
+    pavgpu_ctx *ctx = b->ctx;
+    CUDA_TRY(cudaMemsetAsync(b->d_first_illegal, 0xFF, 8, st));
+    CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_chunks, st));
+    cigar_walk_kernel<<<(unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(
+        b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, b->d_desc, b->d_recdesc, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
+        b->d_first_illegal, reinterpret_cast<unsigned long long *>(b->d_totals));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+    if (b->n_indel > 0) {
+        int hrc = launch_homology(b, st, ref_store, qry_store);
+        if (hrc) return hrc;
+    }
+    return PAVGPU_OK;
+}
+
+// First run of a batch: count on the device, read the totals, allocate the row buffers.
+static int size_rows(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv, bool count)
+{
+    pavgpu_ctx *ctx = b->ctx;
+    if (count) {   // (the multi-pass walk sizes its row buffers from its own scan)
+        int rc = launch_count(b, st, rv);
+        if (rc) return rc;
+        int64_t tot[3] = {0, 0, 0};
+        CUDA_TRY(cudaMemcpyAsync(&tot[0], b->d_rec_snv_off + b->n_rec, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&tot[1], b->d_rec_indel_off + b->n_rec, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&tot[2], b->d_totals + 2, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        b->cnt_n_snv = tot[0]; b->cnt_n_indel = tot[1]; b->ref_span = tot[2];
+        b->cnt_valid = true;
+        if (b->cnt_n_snv >= ((int64_t)1 << 33) || b->cnt_n_indel >= ((int64_t)1 << 30)) b->fused = false;   // descriptor fields would overflow
+    }
+    ArenaPlan ap;
+    const size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1);
+    size_t o_agg = 0, o_cnt = 0, o_prq = 0, o_pcnt = 0, o_snv = 0, o_stub = 0, o_indel = 0;
+    if (!b->fused) { o_agg = ap.add(nc * sizeof(int4)); o_cnt = ap.add(nc * sizeof(uint2)); o_prq = ap.add(nc * sizeof(int2)); o_pcnt = ap.add(nc * sizeof(longlong2)); }
+    else {
+        o_snv = ap.add((size_t)b->cnt_n_snv * sizeof(int4));
+        o_stub = ap.add((size_t)b->cnt_n_indel * sizeof(IndelStub));
+        o_indel = ap.add((size_t)b->cnt_n_indel * sizeof(pavgpu_indel_row));
+    }
+    cudaError_t e = pav_dev_alloc(ctx, ap.off, &b->d_rows_arena);
+    if (e != cudaSuccess) { pav_set_error("cigar walk: cudaMalloc(%zu) for the row buffers failed: %s", ap.off, cudaGetErrorString(e)); return PAVGPU_ERR_NOMEM; }
+    char *base = static_cast<char *>(b->d_rows_arena);
+    if (!b->fused) {
+        b->d_agg = (int4 *)(base + o_agg); b->d_cnt = (uint2 *)(base + o_cnt); b->d_pre_rq = (int2 *)(base + o_prq); b->d_pre_cnt = (longlong2 *)(base + o_pcnt);
+    } else {
+        b->d_snv = (int4 *)(base + o_snv); b->d_stub = (IndelStub *)(base + o_stub); b->d_indel = (pavgpu_indel_row *)(base + o_indel);
+        b->cap_snv = b->cnt_n_snv; b->cap_indel = b->cnt_n_indel;
+    }
+    b->sized = true;
     return PAVGPU_OK;
 }
 
@@ -1042,7 +1436,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     // ids must index the stores (checked on the host once; the kernels trust them)
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    int launches = 0;
+    int launches = 0, used_graph = 0;
     RecView rv{b->d_ref_id, b->d_qry_id, b->d_pos, b->d_rev, b->d_op_off, b->n_rec};
     if (b->recdesc_ref_uid != ref_store->uid || b->recdesc_qry_uid != qry_store->uid) {
         // record -> (plane offsets, lengths, POS, REV) for this pair of stores; rebuilt only when the stores change
@@ -1059,38 +1453,73 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         if (b->n_rec) CUDA_TRY(cudaMemcpyAsync(b->d_recdesc, b->h_recdesc.data(), (size_t)b->n_rec * sizeof(RecDesc), cudaMemcpyHostToDevice, st));
         b->recdesc_ref_uid = ref_store->uid; b->recdesc_qry_uid = qry_store->uid;
     }
-    unsigned long long init = ~0ull;
-    CUDA_TRY(cudaMemcpyAsync(b->d_first_illegal, &init, 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 16, st));
-    CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
     b->n_snv = b->n_indel = 0;
+    b->runs++;
+    bool counted_now = false;
+    if (b->n_chunks > 0 && !b->sized) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+        int rc = size_rows(b, st, rv, b->fused);   // single-pass walk: count + record scan + a 24-byte read-back, once per batch
+        if (rc) return rc;
+        counted_now = b->cnt_valid;
+        launches += counted_now ? 2 : 0;
+    }
     if (b->n_chunks > 0 && b->fused) {
-        CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_chunks, st));
-        cigar_walk_kernel<<<(unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, b->d_desc,
-                                                                             b->d_recdesc, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
-                                                                             b->d_first_illegal, reinterpret_cast<unsigned long long *>(b->d_totals));
-        launches++;
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
-        CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
-        CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
-        b->n_snv = b->host_n_snv; b->n_indel = b->host_n_indel;
-        if (b->n_indel > 0) {
-            int hrc = launch_homology(b, st, ref_store, qry_store);
-            if (hrc) return hrc;
-            launches++;
+        b->n_snv = b->cnt_n_snv; b->n_indel = b->cnt_n_indel;
+        const int hom = b->n_indel > 0 ? homology_choice(b) : -1;
+        static const bool no_graph = [] { const char *g = getenv("PAVGPU_NO_GRAPH"); return g && g[0] == '1'; }();
+        if (counted_now) {
+            // first run: the count has just run eagerly (its totals sized the buffers); finish the step eagerly
+            CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+            int rc = launch_walk_homology(b, st, rv, ref_store, qry_store);
+            if (rc) return rc;
+            launches += 1 + (b->n_indel > 0 ? 1 : 0);
+        } else {
+            // later runs of a resident batch: the whole step -- count, record scan, walk, homology -- replayed as one graph
+            if (!no_graph && (!b->gexec || b->g_ref_uid != ref_store->uid || b->g_qry_uid != qry_store->uid || b->g_hom != hom)) {
+                if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int rc = launch_count(b, st, rv);
+                if (!rc) { cudaError_t e = cudaEventRecord(ctx->ev[1], st); if (e != cudaSuccess) rc = PAVGPU_ERR_CUDA; }
+                if (!rc) rc = launch_walk_homology(b, st, rv, ref_store, qry_store);
+                cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    (void)cudaGetLastError();
+                    if (!rc) { pav_set_error("cigar walk: graph capture failed: %s", cudaGetErrorString(ce)); rc = PAVGPU_ERR_CUDA; }
+                    return rc;
+                }
+                ce = cudaGraphInstantiate(&b->gexec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { b->gexec = nullptr; pav_set_error("cigar walk: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return PAVGPU_ERR_CUDA; }
+                b->g_ref_uid = ref_store->uid; b->g_qry_uid = qry_store->uid; b->g_hom = hom;
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+            if (b->gexec) {
+                CUDA_TRY(cudaGraphLaunch(b->gexec, st));
+                used_graph = 1;
+            } else {
+                int rc = launch_count(b, st, rv);
+                if (rc) return rc;
+                CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+                rc = launch_walk_homology(b, st, rv, ref_store, qry_store);
+                if (rc) return rc;
+            }
+            launches += 3 + (b->n_indel > 0 ? 1 : 0);
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         int64_t tot[2];
         CUDA_TRY(cudaMemcpyAsync(tot, b->d_totals, 16, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(&b->first_illegal, b->d_first_illegal, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (tot[0] != b->host_n_snv || tot[1] != b->host_n_indel) {
-            pav_set_error("cigar walk: device row totals (%lld, %lld) differ from the host count (%lld, %lld)", (long long)tot[0], (long long)tot[1],
-                          (long long)b->host_n_snv, (long long)b->host_n_indel);
+        if (tot[0] != b->cnt_n_snv || tot[1] != b->cnt_n_indel) {
+            pav_set_error("cigar walk: rows emitted by the walk (%lld, %lld) differ from the device count (%lld, %lld)", (long long)tot[0], (long long)tot[1],
+                          (long long)b->cnt_n_snv, (long long)b->cnt_n_indel);
             return PAVGPU_ERR_CUDA;
         }
     } else if (b->n_chunks > 0) {
+        if (!counted_now) CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+        CUDA_TRY(cudaMemsetAsync(b->d_first_illegal, 0xFF, 8, st));
         unsigned blocks = (unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         cigar_reduce_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_agg, b->d_cnt);
         chunk_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(b->d_agg, b->d_cnt, b->n_chunks, b->d_pre_rq, b->d_pre_cnt, b->d_totals);
@@ -1128,20 +1557,31 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         CUDA_TRY(cudaStreamSynchronize(st));
     } else {
         b->first_illegal = ~0ull;
-        for (int i = 1; i <= 4; i++) CUDA_TRY(cudaEventRecord(ctx->ev[i], st));
+        for (int i = 0; i <= 4; i++) CUDA_TRY(cudaEventRecord(ctx->ev[i], st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     b->ran = true;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->ms_h2d = b->ms_h2d;
-        stats->ms_scan = ev_ms(ctx->ev[0], ctx->ev[1]);
-        stats->ms_emit = ev_ms(ctx->ev[2], ctx->ev[3]);
-        stats->ms_homology = ev_ms(ctx->ev[3], ctx->ev[4]);
         stats->ms_kernels = ev_ms(ctx->ev[0], ctx->ev[4]);
+        if (b->fused && b->n_chunks > 0) {
+            // ev[1] (after count + record scan) and ev[3] (after the walk) are event-record nodes when the step ran as a graph
+            float a = 0.f, c = 0.f, d = 0.f;
+            const bool ok = cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]) == cudaSuccess && cudaEventElapsedTime(&c, ctx->ev[1], ctx->ev[3]) == cudaSuccess &&
+                            cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[4]) == cudaSuccess;
+            if (!ok) (void)cudaGetLastError();
+            stats->ms_count = ok ? a : 0.f; stats->ms_scan = ok ? c : 0.f; stats->ms_homology = ok ? d : 0.f;
+        } else {
+            stats->ms_scan = ev_ms(ctx->ev[0], ctx->ev[1]);
+            stats->ms_emit = ev_ms(ctx->ev[2], ctx->ev[3]);
+            stats->ms_homology = ev_ms(ctx->ev[3], ctx->ev[4]);
+        }
         stats->n_ops = b->n_ops; stats->n_snv = b->n_snv; stats->n_indel = b->n_indel; stats->n_chunks = b->n_chunks;
         stats->kernel_launches = launches;
         stats->homology_tiled = b->n_indel > 0 ? b->hom_kernel : 0;
+        stats->walk_passes = b->n_chunks > 0 ? (b->fused ? 1 : 3) : 0;
+        stats->graph = used_graph;
     }
     return PAVGPU_OK;
 }

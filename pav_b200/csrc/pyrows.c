@@ -784,19 +784,17 @@ done:
  * arena allocator (PyObject_SetArenaAllocator, the documented hook) that keeps up to max_mb of released arenas and hands them
  * out again; anything beyond goes back to the OS as before. Arenas need not be zeroed (pymalloc initialises the pools it carves).
  * ------------------------------------------------------------------------------------------------ */
-#include <sys/mman.h>
-
 static struct {
     void **ptr;
     size_t n, cap, size;
     int installed;
+    PyObjectArenaAllocator prev;   /* the allocator that was installed before: arenas are obtained from it and returned to it */
 } g_arena;
 
 static void *arena_alloc(void *ctx, size_t size)
 {
     if (g_arena.n > 0 && size == g_arena.size) return g_arena.ptr[--g_arena.n];
-    void *p = mmap(NULL, size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    return p == MAP_FAILED ? NULL : p;
+    return g_arena.prev.alloc(g_arena.prev.ctx, size);
 }
 
 static void arena_free(void *ctx, void *ptr, size_t size)
@@ -806,17 +804,24 @@ static void arena_free(void *ctx, void *ptr, size_t size)
         g_arena.ptr[g_arena.n++] = ptr;
         return;
     }
-    munmap(ptr, size);
+    g_arena.prev.free(g_arena.prev.ctx, ptr, size);
 }
 
+/* Opt-in (PAVGPU_TUNE_ALLOC=1, pavlib/cigarcall.py). Chains to the previous arena allocator, so it makes no assumption about how
+ * arenas are mapped; refused on free-threaded builds (the cache above relies on the GIL). */
 static PyObject *py_keep_arenas(PyObject *self, PyObject *arg)
 {
     long max_mb = PyLong_AsLong(arg);
     if (max_mb == -1 && PyErr_Occurred()) return NULL;
+#ifdef Py_GIL_DISABLED
+    Py_RETURN_FALSE;
+#endif
     if (g_arena.installed || max_mb <= 0) Py_RETURN_FALSE;
     g_arena.cap = (size_t)max_mb;   /* arenas are 1 MiB on 64-bit CPython >= 3.10 (256 KiB before: the cap is then a quarter) */
     g_arena.ptr = (void **)malloc(g_arena.cap * sizeof(void *));
     if (!g_arena.ptr) return PyErr_NoMemory();
+    PyObject_GetArenaAllocator(&g_arena.prev);
+    if (!g_arena.prev.alloc || !g_arena.prev.free) { free(g_arena.ptr); g_arena.ptr = NULL; Py_RETURN_FALSE; }
     PyObjectArenaAllocator a = {NULL, arena_alloc, arena_free};
     PyObject_SetArenaAllocator(&a);
     g_arena.installed = 1;

@@ -121,6 +121,96 @@ PAV_DEV void oseq_window(const OSeq &s, int32_t t, uint64_t &bases, uint32_t &ma
     mask = __brev(m);
 }
 
+// The same window in three steps, so that a caller can issue the loads of several windows before it looks at any of them:
+// win_prep (all address arithmetic, no branch on data), win_load (four loads), win_finish (shifts, sequence edges, strand -- selects
+// only). With the windows of a phase prepared, loaded and finished in that order the compiler keeps all their loads in flight
+// together; through oseq_window every window waits for its own loads behind the branches of the one before (ncu, r02: a third of
+// the homology kernel's warp time was spent on those serial round trips).
+struct WinReq {
+    int64_t w;              // first plane word
+    int32_t sh, lead, over; // base offset inside the word; window positions before the sequence start / past its end
+    uint32_t none, rev;     // no position of the window lies inside the sequence; reverse-complement view
+};
+struct WinRaw {
+    uint64_t hi, lo;
+    uint32_t m0, m1;
+};
+
+PAV_DEV WinReq win_prep(const OSeq &s, int32_t t)
+{
+    const int32_t len = (int32_t)s.len;
+    const int32_t f = s.rev ? len - t - 32 : t;
+    WinReq q;
+    q.none = (f <= -32 || f >= len) ? 1u : 0u;
+    q.lead = (f < 0 && !q.none) ? -f : 0;
+    q.over = (!q.none && f + 32 > len) ? f + 32 - len : 0;
+    const int64_t g = s.base + (q.none ? 0 : (int64_t)(f + q.lead));
+    q.w = g >> 5;
+    q.sh = (int32_t)(g & 31);
+    q.rev = (uint32_t)s.rev;
+    return q;
+}
+
+PAV_DEV WinRaw win_load(const OSeq &s, const WinReq &q)
+{
+    WinRaw r;
+    r.hi = __ldg(s.pack2 + q.w); r.lo = __ldg(s.pack2 + q.w + 1);
+    r.m0 = __ldg(s.nmask + q.w); r.m1 = __ldg(s.nmask + q.w + 1);
+    return r;
+}
+
+PAV_DEV void win_finish(const WinReq &q, const WinRaw &r, uint64_t &bases, uint32_t &mask)
+{
+    uint64_t b = q.sh ? ((r.hi << (2 * q.sh)) | (r.lo >> (64 - 2 * q.sh))) : r.hi;
+    uint32_t m = __funnelshift_r(r.m0, r.m1, q.sh);
+    if (q.lead) { b >>= 2 * q.lead; m = (m << q.lead) | ((1u << q.lead) - 1u); }
+    if (q.over) m |= ~0u << (32 - q.over);
+    if (q.none) { b = 0; m = 0xffffffffu; }
+    if (q.rev) { b = revcomp32(b); m = __brev(m); }
+    bases = b; mask = m;
+}
+
+// Matching bases of two finished windows from the scan's near end (left != 0: from base 31 down), 0..32.
+PAV_DEV int window_stop(uint64_t wa, uint32_t ma, uint64_t wb, uint32_t mb, int left)
+{
+    const uint64_t x = wa ^ wb;
+    const uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;      // one bit per differing base
+    const uint32_t m = ma | mb;
+    int stop_d, stop_m;
+    if (left) {   // last base of the window = least significant group / highest mask bit
+        stop_d = d ? ((__ffsll((long long)d) - 1) >> 1) : 32;
+        stop_m = m ? __clz((int)m) : 32;
+    } else {      // first base = most significant group / lowest mask bit
+        stop_d = d ? (__clzll((long long)d) >> 1) : 32;
+        stop_m = m ? (__ffs((int)m) - 1) : 32;
+    }
+    return min(stop_d, stop_m);
+}
+
+// common_extension with the windows of two steps (64 bases) in flight per iteration.
+PAV_DEV int32_t common_extension2(const OSeq &A, int32_t a, const OSeq &B, int32_t b, int32_t limit, int left)
+{
+    int32_t h = 0;
+    const int32_t step = left ? -32 : 32;
+    int32_t pa = left ? a - 31 : a, pb = left ? b - 31 : b;
+    while (h < limit) {
+        const WinReq qa0 = win_prep(A, pa), qb0 = win_prep(B, pb), qa1 = win_prep(A, pa + step), qb1 = win_prep(B, pb + step);
+        const WinRaw ra0 = win_load(A, qa0), rb0 = win_load(B, qb0), ra1 = win_load(A, qa1), rb1 = win_load(B, qb1);
+        uint64_t wa, wb; uint32_t ma, mb;
+        win_finish(qa0, ra0, wa, ma); win_finish(qb0, rb0, wb, mb);
+        int stop = window_stop(wa, ma, wb, mb, left);
+        if (stop < 32) { h += stop; return h < limit ? h : limit; }
+        h += 32;
+        if (h >= limit) return limit;
+        win_finish(qa1, ra1, wa, ma); win_finish(qb1, rb1, wb, mb);
+        stop = window_stop(wa, ma, wb, mb, left);
+        if (stop < 32) { h += stop; return h < limit ? h : limit; }
+        h += 32; pa += 2 * step; pb += 2 * step;
+        if (h < 0) return limit;   // (cannot happen for sequences < 2^31; guards the 32-bit counter)
+    }
+    return limit;
+}
+
 // Longest common extension of A from a and B from b, 32 bases per step, capped at `limit`:
 //   left == 0: common prefix of A[a..] and B[b..]        (window i covers a+32i .. a+32i+31)
 //   left != 0: common suffix of A[..a] and B[..b]         (window i covers a-32i-31 .. a-32i)
@@ -245,6 +335,224 @@ PAV_DEV void score_indel(const OSeq &R, const OSeq &Q, int32_t svtype, int32_t n
         o.seq_start = pr;
     }
     o.ls = ls; o.hom_rl = hom_rl; o.hom_rr = hom_rr; o.hom_tl = hom_tl; o.hom_tr = hom_tr;
+}
+
+// ---- the same scoring with a convergent first trip --------------------------------------------------
+// 85-90 % of the scans of a real batch stop within their first 32 bases, and most SV sequences are shorter than 32 bases.
+// score_indel runs every scan as a data-dependent loop of its own, so a warp executes each trip with the few lanes that still
+// need it. Here the first 32 steps of every scan are ONE straight-line window compare for all lanes: the reference reads the
+// SV sequence circularly (call.py:582 sv[-((h + 1) % n)], :637 sv[h % n]), so for n < 32 the 32-base pattern the flank is
+// compared with is the periodic expansion of the SV's n bases, built with log2(32 / n) shift-ors. Only scans that match all 32
+// bases continue, in common_extension: for n <= 32 a whole copy of the SV has matched by then, so the scan goes on as the
+// flank compared with itself shifted by n (see dev_homology_raw), resumed at step 32.
+PAV_DEV uint64_t shl64(uint64_t x, int s) { return s < 64 ? x << s : 0ull; }
+PAV_DEV uint64_t shr64(uint64_t x, int s) { return s < 64 ? x >> s : 0ull; }
+
+// left != 0: bases 32-n..31 of the window (the SV's n bases, last base least significant) repeated towards base 0;
+// left == 0: bases 0..n-1 repeated towards base 31. The mask word alike. n >= 32: unchanged.
+PAV_DEV void periodic32(uint64_t &b, uint32_t &m, int n, int left)
+{
+    if (n >= 32) return;
+    uint64_t x;
+    uint32_t y;
+    // the period doubles with every step (n, 2n, 4n, ...): five steps cover n = 1; shifts past the word are zero, so all lanes run
+    // the same five steps whatever their n
+    if (left) {
+        x = b & (shl64(1ull, 2 * n) - 1ull);
+        y = (m >> (32 - n)) << (32 - n);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const int s = n << j;
+            x |= shl64(x, 2 * s);
+            y |= s < 32 ? y >> s : 0u;
+        }
+    } else {
+        x = (b >> (64 - 2 * n)) << (64 - 2 * n);
+        y = m & ((1u << n) - 1u);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const int s = n << j;
+            x |= shr64(x, 2 * s);
+            y |= s < 32 ? y << s : 0u;
+        }
+    }
+    b = x; m = y;
+}
+
+// First 32 steps of a scan: the flank window at p (left != 0: bases p-31..p, else p..p+31) against the pattern. Returns 0..32.
+template <bool TILED>
+PAV_DEV int first_trip(const OSeq &T, int32_t p, uint64_t pat, uint32_t patm, int left)
+{
+    if (p < 0 || p >= (int32_t)T.len) return 0;
+    uint64_t wt; uint32_t mt;
+    oseq_window<TILED>(T, left ? p - 31 : p, wt, mt);
+    const uint64_t x = wt ^ pat;
+    const uint64_t d = (x | (x >> 1)) & 0x5555555555555555ull;
+    const uint32_t m = mt | patm;
+    int stop_d, stop_m;
+    if (left) {
+        stop_d = d ? ((__ffsll((long long)d) - 1) >> 1) : 32;
+        stop_m = m ? __clz((int)m) : 32;
+    } else {
+        stop_d = d ? (__clzll((long long)d) >> 1) : 32;
+        stop_m = m ? (__ffs((int)m) - 1) : 32;
+    }
+    return min(stop_d, stop_m);
+}
+
+// The rest of a scan whose first 32 steps all matched. V = SV sequence at v0, n bases. One common_extension site serves both
+// stages: (n > 32 only) the flank against the rest of the SV, then the flank against itself shifted by n.
+template <bool TILED>
+PAV_DEV int scan_rest(const OSeq &T, int32_t p, const OSeq &V, int32_t v0, int n, int left)
+{
+    int32_t h = 32;
+#pragma unroll 1
+    for (int stage = (n > 32 ? 0 : 1); stage < 2; stage++) {
+        const OSeq B = stage == 0 ? V : T;      // (a copy: field-wise selects; a reference would force the structs into local memory)
+        const int32_t a = left ? p - h : p + h;
+        const int32_t b = stage == 0 ? (left ? v0 + n - 1 - 32 : v0 + 32) : (left ? a + n : a - n);
+        const int32_t lim = stage == 0 ? n - 32 : 0x7fffffff - 64 - n;
+        const int32_t e = TILED ? common_extension<TILED>(T, a, B, b, lim, left) : common_extension2(T, a, B, b, lim, left);
+        h += e;
+        if (stage == 0 && e < lim) break;
+    }
+    return h;
+}
+
+// The pieces of one indel's scoring, in the order the reference runs them (cigarcall.py:137-266). score_indel2 strings them
+// together for one thread; homology_queue_kernel runs the same pieces with the rests of a whole CTA's indels pooled in between.
+//   sc 0 = left-shift scan (ref, leftwards from pr - 1, SV sequence at the unshifted position); sc 1..4 = hom_ref_l, hom_ref_r,
+//   hom_tig_l, hom_tig_r at the shifted position.
+PAV_DEV void scan_geometry(int sc, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, int32_t &p, int32_t &v0, bool &on_ref, int &left)
+{
+    const int32_t sp = pr - ls, sq = pq - ls;
+    on_ref = sc <= 2;
+    left = (sc == 0 || sc == 1 || sc == 3);
+    if (sc == 0) { p = pr - 1; v0 = ins ? pq : pr; return; }
+    v0 = ins ? sq : pr;                      // INS: the SV sequence is re-sliced at the shifted position; DEL: never (:233-266)
+    if (sc == 1) p = sp - 1;
+    else if (sc == 2) p = ins ? sp : sp + n;
+    else if (sc == 3) p = sq - 1;
+    else p = ins ? sq + n : sq;
+}
+
+// First 32 steps of a scan from finished windows: flank window (wt, mt) of T at p against the pattern.
+PAV_DEV int first_trip_w(const OSeq &T, int32_t p, uint64_t wt, uint32_t mt, uint64_t pat, uint32_t patm, int left)
+{
+    const int stop = window_stop(wt, mt, pat, patm, left);
+    return (p < 0 || p >= (int32_t)T.len) ? 0 : stop;
+}
+
+// First trip of the left-shift scan (cigarcall.py:149-155 / :225-231). 0..32; 32 = all matched, the rest is scan 0.
+template <bool TILED>
+PAV_DEV int indel_phase0(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq)
+{
+    if (!TILED) {   // both windows requested before either is used
+        const OSeq V = ins ? Q : R;
+        const WinReq qv = win_prep(V, (ins ? pq : pr) + n - 32), qt = win_prep(R, pr - 32);
+        const WinRaw rv = win_load(V, qv), rt = win_load(R, qt);
+        uint64_t patl, wt; uint32_t patlm, mt;
+        win_finish(qv, rv, patl, patlm);
+        win_finish(qt, rt, wt, mt);
+        periodic32(patl, patlm, n, 1);
+        return first_trip_w(R, pr - 1, wt, mt, patl, patlm, 1);
+    }
+    const OSeq &V = ins ? Q : R;
+    uint64_t patl; uint32_t patlm;
+    oseq_window<TILED>(V, (ins ? pq : pr) + n - 32, patl, patlm);
+    periodic32(patl, patlm, n, 1);
+    return first_trip<TILED>(R, pr - 1, patl, patlm, 1);
+}
+
+// First trips of the four breakpoint homologies at the shifted position (:178-182 / :247-251): hom[0..3] = ref left, ref right,
+// contig left, contig right (32 = all matched, rest pending).
+template <bool TILED>
+PAV_DEV void indel_phase1(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, int (&hom)[4])
+{
+    const int32_t sp = pr - ls, sq = pq - ls, v0 = ins ? sq : pr;
+    uint64_t patl, patr; uint32_t patlm, patrm;
+    if (!TILED) {   // all six windows requested before any is used
+        const OSeq V = ins ? Q : R;
+        const int32_t p_rl = sp - 1, p_rr = ins ? sp : sp + n, p_tl = sq - 1, p_tr = ins ? sq + n : sq;
+        const WinReq qvl = win_prep(V, v0 + n - 32), qvr = win_prep(V, v0);
+        const WinReq q0 = win_prep(R, p_rl - 31), q1 = win_prep(R, p_rr), q2 = win_prep(Q, p_tl - 31), q3 = win_prep(Q, p_tr);
+        const WinRaw rvl = win_load(V, qvl), rvr = win_load(V, qvr);
+        const WinRaw r0 = win_load(R, q0), r1 = win_load(R, q1), r2 = win_load(Q, q2), r3 = win_load(Q, q3);
+        win_finish(qvl, rvl, patl, patlm);
+        win_finish(qvr, rvr, patr, patrm);
+        periodic32(patl, patlm, n, 1);
+        periodic32(patr, patrm, n, 0);
+        uint64_t w; uint32_t m;
+        win_finish(q0, r0, w, m); hom[0] = first_trip_w(R, p_rl, w, m, patl, patlm, 1);
+        win_finish(q1, r1, w, m); hom[1] = first_trip_w(R, p_rr, w, m, patr, patrm, 0);
+        win_finish(q2, r2, w, m); hom[2] = first_trip_w(Q, p_tl, w, m, patl, patlm, 1);
+        win_finish(q3, r3, w, m); hom[3] = first_trip_w(Q, p_tr, w, m, patr, patrm, 0);
+        return;
+    }
+    const OSeq &V = ins ? Q : R;
+    oseq_window<TILED>(V, v0 + n - 32, patl, patlm);
+    periodic32(patl, patlm, n, 1);
+    oseq_window<TILED>(V, v0, patr, patrm);
+    periodic32(patr, patrm, n, 0);
+    hom[0] = first_trip<TILED>(R, sp - 1, patl, patlm, 1);
+    hom[1] = first_trip<TILED>(R, ins ? sp : sp + n, patr, patrm, 0);
+    hom[2] = first_trip<TILED>(Q, sq - 1, patl, patlm, 1);
+    hom[3] = first_trip<TILED>(Q, ins ? sq + n : sq, patr, patrm, 0);
+}
+
+// The rest of scan sc (its first 32 steps all matched).
+template <bool TILED>
+PAV_DEV int indel_rest(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, int sc)
+{
+    int32_t p, v0; bool on_ref; int left;
+    scan_geometry(sc, ins, n, pr, pq, ls, p, v0, on_ref, left);
+    const OSeq T = on_ref ? R : Q;
+    const OSeq V = ins ? Q : R;
+    return scan_rest<TILED>(T, p, V, v0, n, left);
+}
+
+PAV_DEV void indel_finish(const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, const int (&hom)[4], IndelScore &o)
+{
+    const int32_t L = (int32_t)Q.len, sp = pr - ls, sq = pq - ls;
+    if (ins) {          // cigarcall.py:157-173
+        o.pos = sp; o.end = sp + 1;
+        if (Q.rev) { o.qry_end = L - sq; o.qry_pos = o.qry_end - n; } else { o.qry_pos = sq; o.qry_end = sq + n; }
+        o.seq_start = sq;
+    } else {            // cigarcall.py:233-266 (POS/END/SEQ stay unshifted)
+        o.pos = pr; o.end = pr + n;
+        o.qry_pos = Q.rev ? L - sq : sq;
+        o.qry_end = o.qry_pos + 1;
+        o.seq_start = pr;
+    }
+    o.ls = ls; o.hom_rl = hom[0]; o.hom_rr = hom[1]; o.hom_tl = hom[2]; o.hom_tr = hom[3];
+}
+
+template <bool TILED>
+PAV_DEV void score_indel2(const OSeq &R, const OSeq &Q, int32_t svtype, int32_t n, int32_t pr, int32_t pq, int32_t eqb, IndelScore &o)
+{
+    const bool ins = (svtype == 0);
+    int h0 = indel_phase0<TILED>(R, Q, ins, n, pr, pq);
+    if (eqb <= 0) h0 = 0;                       // the shift counts only when the previous op was '='
+    int ls = 0;
+    int hom[4] = {0, 0, 0, 0};
+    // sc 0 = rest of the left-shift scan (only when it can still grow the shift); entering sc 1 everything moves to the shifted
+    // position and the four homologies take their first trips; sc 1..4 = their rests. One rolled loop: one copy of the rest code.
+#pragma unroll 1
+    for (int sc = (h0 == 32 && eqb > 32) ? 0 : 1; sc < 5; sc++) {
+        if (sc == 1) {
+            ls = min(eqb, h0);
+            indel_phase1<TILED>(R, Q, ins, n, pr, pq, ls, hom);
+        }
+        const int hcur = sc == 0 ? 32 : sc == 1 ? hom[0] : sc == 2 ? hom[1] : sc == 3 ? hom[2] : hom[3];
+        if (hcur != 32) continue;
+        const int h = indel_rest<TILED>(R, Q, ins, n, pr, pq, ls, sc);
+        if (sc == 0) h0 = h;
+        else if (sc == 1) hom[0] = h;
+        else if (sc == 2) hom[1] = h;
+        else if (sc == 3) hom[2] = h;
+        else hom[3] = h;
+    }
+    indel_finish(Q, ins, n, pr, pq, ls, hom, o);
 }
 
 // ---- staged words: which part of a plane the opt-in homology kernels copy on chip ---------------

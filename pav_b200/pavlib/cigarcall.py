@@ -299,13 +299,15 @@ def _tune_malloc():
       * glibc: keep freed heap (no trim), grow it in big steps, and serve arrays up to 32 MiB from the heap instead of mmap
         (measured: first call 2.0 s -> 1.1 s for 2 M rows before the C formatter existed);
       * pymalloc: recycle released arenas (``_pyrows.keep_arenas``) instead of unmapping and re-faulting them every call.
-    Process-wide settings, applied on the first large result; ``PAVGPU_TUNE_ALLOC=0`` leaves the allocators alone."""
+    These are process-wide settings that outlive the call and keep up to ``PAVGPU_ARENA_CACHE_MB`` (default 512) of freed arenas
+    plus untrimmed heap resident, so they are OPT-IN: nothing is touched unless ``PAVGPU_TUNE_ALLOC=1`` is set (bench.py sets it
+    for its end-to-end leg and says so in its JSON line). With it the first large result applies them."""
     global _MALLOC_TUNED
     if _MALLOC_TUNED:
         return
     _MALLOC_TUNED = True
     import os
-    if os.environ.get('PAVGPU_TUNE_ALLOC', '1') == '0':
+    if os.environ.get('PAVGPU_TUNE_ALLOC', '0') != '1':
         return
     try:
         import ctypes
@@ -317,7 +319,7 @@ def _tune_malloc():
         pass
     try:
         from .. import _pyrows
-        _pyrows.keep_arenas(int(os.environ.get('PAVGPU_ARENA_CACHE_MB', '2048')))
+        _pyrows.keep_arenas(int(os.environ.get('PAVGPU_ARENA_CACHE_MB', '512')))
     except Exception:  # noqa: BLE001
         pass
 

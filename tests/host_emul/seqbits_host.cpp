@@ -67,18 +67,19 @@ int emu_homology(const uint64_t *pack2, const uint32_t *nmask, int64_t t_base, i
     return dev_homology_raw(pack2, nmask, t_base, t_len, t_rev, p, pack2, nmask, v_base, v_len, v_rev, v0, n, left);
 }
 
-// One indel through score_indel, as homology_kernel (tile_words == 0) or with a staged copy of plane words
+// One indel through score_indel (version 1) or score_indel2 (version 2: convergent first trips), as homology_kernel (tile_words == 0) or with a staged copy of plane words
 // [w0, w0 + tile_words) of each sequence, as homology_tiled_kernel / homology_nbr_kernel see it. out[10] = pos, end, qry_pos,
 // qry_end, left_shift, hom_ref_l, hom_ref_r, hom_tig_l, hom_tig_r, seq_start.
 void emu_score_indel(const uint64_t *r_pack2, const uint32_t *r_nmask, int64_t r_base, int64_t r_len, const uint64_t *q_pack2,
                      const uint32_t *q_nmask, int64_t q_base, int64_t q_len, int q_rev, int32_t svtype, int32_t n, int32_t pr, int32_t pq,
-                     int32_t eqb, int64_t r_w0, int32_t r_tile_words, int64_t q_w0, int32_t q_tile_words, int32_t *out)
+                     int32_t eqb, int64_t r_w0, int32_t r_tile_words, int64_t q_w0, int32_t q_tile_words, int32_t version, int32_t *out)
 {
     IndelScore o;
     if (r_tile_words <= 0 && q_tile_words <= 0) {
         const OSeq R{r_pack2, r_nmask, r_base, r_len, 0, nullptr, nullptr, 0, 0};
         const OSeq Q{q_pack2, q_nmask, q_base, q_len, q_rev, nullptr, nullptr, 0, 0};
-        score_indel<false>(R, Q, svtype, n, pr, pq, eqb, o);
+        if (version == 2) score_indel2<false>(R, Q, svtype, n, pr, pq, eqb, o);
+        else score_indel<false>(R, Q, svtype, n, pr, pq, eqb, o);
     } else {
         // staged copies are poisoned outside the tile so that a window served from the wrong place cannot go unnoticed
         std::vector<uint64_t> tp_r(std::max(r_tile_words, 1)), tp_q(std::max(q_tile_words, 1));
@@ -87,7 +88,8 @@ void emu_score_indel(const uint64_t *r_pack2, const uint32_t *r_nmask, int64_t r
         for (int k = 0; k < q_tile_words; k++) { tp_q[k] = q_pack2[q_w0 + k]; tm_q[k] = q_nmask[q_w0 + k]; }
         const OSeq R{r_pack2, r_nmask, r_base, r_len, 0, tp_r.data(), tm_r.data(), r_w0, std::max(r_tile_words - 1, 0)};
         const OSeq Q{q_pack2, q_nmask, q_base, q_len, q_rev, tp_q.data(), tm_q.data(), q_w0, std::max(q_tile_words - 1, 0)};
-        score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
+        if (version == 2) score_indel2<true>(R, Q, svtype, n, pr, pq, eqb, o);
+        else score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
     }
     out[0] = o.pos; out[1] = o.end; out[2] = o.qry_pos; out[3] = o.qry_end; out[4] = o.ls;
     out[5] = o.hom_rl; out[6] = o.hom_rr; out[7] = o.hom_tl; out[8] = o.hom_tr; out[9] = o.seq_start;

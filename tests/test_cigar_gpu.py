@@ -160,10 +160,10 @@ def test_multipass_walk_matches_single_pass(tmp_path, monkeypatch):
     ref_fa, tig_fa, df = _workload(tmp_path, 15, n_chrom=2, chrom_len=300_000, n_contig=25, contig_len=24_000, edit_rate=0.012,
                                    rev_frac=0.5, clip=(4, 2))
     single = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
-    assert cigarcall.last_stats['kernel_launches'] == 2
+    assert cigarcall.last_stats['walk_passes'] == 1 and cigarcall.last_stats['kernel_launches'] == 4   # count, record scan, walk, homology
     monkeypatch.setenv('PAVGPU_CIGAR_MULTIPASS', '1')
     multi = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
-    assert cigarcall.last_stats['kernel_launches'] == 4
+    assert cigarcall.last_stats['walk_passes'] == 3 and cigarcall.last_stats['kernel_launches'] == 4   # reduce, chunk scan, emit, homology
     monkeypatch.delenv('PAVGPU_CIGAR_MULTIPASS')
     orc = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=True)
     for a, b, c in zip(single, multi, orc):
@@ -172,11 +172,12 @@ def test_multipass_walk_matches_single_pass(tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize('case', CIGAR_CASES)
-@pytest.mark.parametrize('env', ['PAVGPU_HOMOLOGY_TILED', 'PAVGPU_HOMOLOGY_NBR'])
-def test_cigar_golden_gpu_tiled_homology(case, env, monkeypatch):
-    """The golden cases again with each opt-in homology kernel (per-warp shared-memory tiles, per-indel neighbourhoods): partial
-    warps, REV records, N runs, tandem repeats that leave the staged words, planes smaller than a neighbourhood."""
-    monkeypatch.setenv(env, '1')
+@pytest.mark.parametrize('kernel', ['gather', 'tiled', 'nbr', 'bulk', 'queue'])
+def test_cigar_golden_gpu_tiled_homology(case, kernel, monkeypatch):
+    """The golden cases again with every homology kernel named explicitly (gathers, per-warp shared-memory tiles, per-indel
+    neighbourhoods through cp.async and through bulk copies + mbarrier, gathers with CTA-pooled scan rests): partial warps, REV records, N runs, tandem repeats that
+    leave the staged words, planes smaller than a neighbourhood."""
+    monkeypatch.setenv('PAVGPU_HOMOLOGY', kernel)
     test_cigar_golden_gpu(case)
 
 
@@ -189,14 +190,13 @@ def test_cigar_golden_gpu_tiled_homology(case, env, monkeypatch):
     (16, dict(n_chrom=1, chrom_len=3_000_000, n_contig=3, contig_len=1_000_000, edit_rate=0.0004, rev_frac=0.5)),  # sparse: spans overflow the tile
 ])
 def test_homology_kernels_agree(tmp_path, monkeypatch, seed, kw):
-    """Gather kernel, tiled kernel and the oracle give the same indel rows; the stats say which kernel ran."""
+    """All five homology kernels and the oracle give the same indel rows; the stats say which kernel ran."""
     from oracle import pyoracle
     from pav_b200.pavlib import cigarcall
     ref_fa, tig_fa, df = _workload(tmp_path, seed, **kw)
     orc = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
-    for kernel, (tiled, nbr) in enumerate([('0', '0'), ('1', '0'), ('0', '1')]):   # gathers, warp tiles, per-indel neighbourhoods
-        monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', tiled)
-        monkeypatch.setenv('PAVGPU_HOMOLOGY_NBR', nbr)
+    for kernel, name in enumerate(['gather', 'tiled', 'nbr', 'bulk', 'queue']):   # gathers, warp tiles, per-indel neighbourhoods (cp.async / bulk copies), pooled rests
+        monkeypatch.setenv('PAVGPU_HOMOLOGY', name)
         got = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
         assert cigarcall.last_stats['homology_tiled'] == kernel
         assert tsv_bytes(got[1]) == tsv_bytes(orc[1]) and tsv_bytes(got[0]) == tsv_bytes(orc[0])
@@ -204,11 +204,12 @@ def test_homology_kernels_agree(tmp_path, monkeypatch, seed, kw):
 
 
 def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
-    """A C2-shaped slice (1 indel / ~540 bp): gathers by default, the tiled kernel under PAVGPU_HOMOLOGY_TILED=auto (dense batch)
-    and =1; all three give the same bytes and equal the oracle."""
+    """A C2-shaped slice (1 indel / ~540 bp) through every kernel choice, old switches included (PAVGPU_HOMOLOGY_TILED=auto picks the
+    tiled kernel for a dense batch): all give the same bytes and equal the oracle."""
     from oracle import pyoracle
     from pav_b200 import device
     monkeypatch.delenv('PAVGPU_HOMOLOGY_TILED', raising=False)
+    monkeypatch.delenv('PAVGPU_HOMOLOGY', raising=False)
     ref, tigs, df = synth.config_c2(n_contig=100)
     ref_fa, tig_fa, _ = synth.write_cigar_workload(str(tmp_path), ref, tigs, df)
     _, o_indel, _ = pyoracle.walk_rows(df, ref_fa, tig_fa)
@@ -221,17 +222,21 @@ def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
     qid = np.array([names_t.index(c) for c in df['QRY_ID']], np.int32)
     out = {}
     monkeypatch.delenv('PAVGPU_HOMOLOGY_NBR', raising=False)
-    for mode in (None, 'auto', '1', 'nbr'):
+    for mode in ('gather', 'auto', '1', 'nbr', 'bulk', 'tiled-auto', 'queue'):
+        monkeypatch.delenv('PAVGPU_HOMOLOGY', raising=False)
         if mode == 'nbr':
             monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', '0')
             monkeypatch.setenv('PAVGPU_HOMOLOGY_NBR', '1')
-        elif mode is not None:
+        elif mode in ('auto', '1'):
             monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
+            monkeypatch.setenv('PAVGPU_HOMOLOGY_NBR', '0')
+        else:
+            monkeypatch.setenv('PAVGPU_HOMOLOGY', mode)
         _, indel, err, st = device.cigar_call(ctx, rs, ts, rid, qid, df['POS'].to_numpy(np.int32), df['REV'].to_numpy(np.uint8), ops, op_off)
         assert err.code == 0
         out[mode] = (indel.copy(), st.homology_tiled)
-    assert [out[m][1] for m in (None, 'auto', '1', 'nbr')] == [0, 1, 1, 2]
-    assert out[None][0].tobytes() == out['auto'][0].tobytes() == out['1'][0].tobytes() == out['nbr'][0].tobytes()
+    assert [out[m][1] for m in ('gather', 'auto', '1', 'nbr', 'bulk', 'tiled-auto', 'queue')] == [0, 1, 1, 2, 3, 1, 4]
+    assert all(out[m][0].tobytes() == out['gather'][0].tobytes() for m in out)
     for f in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r', 'hom_tig_l', 'hom_tig_r', 'rec', 'svtype'):
-        assert (out[None][0][f] == o_indel[f]).all(), f
+        assert (out['gather'][0][f] == o_indel[f]).all(), f
     rs.close(); ts.close()

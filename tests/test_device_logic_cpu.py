@@ -35,7 +35,7 @@ def emu():
     L.emu_base.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i64]
     L.emu_window.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i32, c_vp, c_vp]
     L.emu_homology.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i64, c_i64, c_i64, ctypes.c_int, c_i64, ctypes.c_int, ctypes.c_int]
-    L.emu_score_indel.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, ctypes.c_int] + [c_i32] * 5 + [c_i64, c_i32, c_i64, c_i32, c_vp]
+    L.emu_score_indel.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, ctypes.c_int] + [c_i32] * 5 + [c_i64, c_i32, c_i64, c_i32, c_i32, c_vp]
     L.emu_kmers.argtypes = [c_vp, c_vp, c_i64, c_i32, ctypes.c_int, c_vp, c_vp, c_vp]
     L.emu_nbr_first_word.argtypes = [c_i64, c_i64]
     L.emu_nbr_first_word.restype = c_i64
@@ -179,8 +179,9 @@ def _stubs(df):
               n_block_frac=0.05)),
 ])
 def test_score_indel_matches_oracle(emu, tmp_path, seed, kw):
-    """score_indel (the body of homology_kernel, homology_tiled_kernel and homology_nbr_kernel) on every indel of a seeded
-    workload: plain, with the 8-word neighbourhood the nbr kernel stages, and with random tiles -- all equal the oracle's rows."""
+    """score_indel and score_indel2 (the bodies the homology kernels share: per-scan loops / convergent first trips against the
+    circular SV pattern) on every indel of a seeded workload: plain, with the 8-word neighbourhood the nbr and bulk kernels stage,
+    and with random tiles -- all equal the oracle's rows."""
     ref, tigs, df = synth.make_cigar_workload(seed, **kw)
     ref_fa, tig_fa, _ = synth.write_cigar_workload(str(tmp_path), ref, tigs, df)
     _, o_indel, _ = pyoracle.walk_rows(df, ref_fa, tig_fa)
@@ -207,8 +208,9 @@ def test_score_indel_matches_oracle(emu, tmp_path, seed, kw):
         tiles.append((w0r, int(rng.integers(1, min(64, R.words - w0r) + 1)), w0q, int(rng.integers(1, min(64, Q.words - w0q) + 1))))
         tiles.append((max((cr >> 5) - 3, 0), min(7, R.words - max((cr >> 5) - 3, 0)), 0, 0))      # reference staged, contig not
         for w0r, nr, w0q, nq in tiles:
-            emu.emu_score_indel(rp, rm, R.off[ri], rl, qp, qm, Q.off[qi], ql, rev, svtype, n, pr, pq, eqb, w0r, nr, w0q, nq, out)
-            assert list(out)[:9] == want, (k, rec, svtype, n, pr, pq, eqb, (w0r, nr, w0q, nq))
+            for version in (1, 2):
+                emu.emu_score_indel(rp, rm, R.off[ri], rl, qp, qm, Q.off[qi], ql, rev, svtype, n, pr, pq, eqb, w0r, nr, w0q, nq, version, out)
+                assert list(out)[:9] == want, (version, k, rec, svtype, n, pr, pq, eqb, (w0r, nr, w0q, nq))
 
 
 def test_kmers_from_planes(emu):
