@@ -1,30 +1,35 @@
 #!/usr/bin/env python3
-"""Benchmark of the PAV hot path on B200 (driver contract: one JSON line on stdout from rank 0).
+"""Benchmark of the PAV hot path on B200 (driver contract: ONE JSON line on stdout from rank 0).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--metric walk|density]
 
-Metric (BASELINE.json): CIGAR-walk variant records/s on BASELINE configs[1] -- one synthetic haplotype,
-1,000 contigs x 200 kbp against a 200 Mbp reference (4 x 50 Mbp), ~1 edit / 100 bp, 50 % reverse-strand
-records. A "step" is one pass of the walk over the whole batch of alignment records.
+Workloads (BASELINE.json configs, SURVEY 8(d) generators, all synthetic and seeded):
 
-  value   device-resident: packed reference/contig planes, packed ops and record descriptors already in
-          HBM; per step = K1 reduce + K2 scan + K3 emit + K4 homology, timed with CUDA events on the
-          library's stream, L2 flushed (256 MB memset) between steps; rows stay in HBM.
-  e2e     the public API call PAV makes: pavlib.cigarcall.make_insdel_snv_calls(df_align, ref.fa, tig.fa, hap)
-          -> two DataFrames (FASTA read, H2D of ASCII sequences + packed ops, kernels, D2H of rows, DataFrame
-          assembly), wall clock.
-  e2e_cabi the same work through the C-ABI call with host buffers only (pavgpu_seqstore_create for the contigs +
-          pavgpu_cigar_call), i.e. without FASTA parsing and DataFrame formatting.
-  secondary  inversion k-mer density scan (Path B) Gbases/s on BASELINE configs[4]-shaped 50 kbp windows.
+  C3  (top-level line, every N)  2 phased haplotypes (h1/h2) of 10 Mbp contigs against a 3.1 Gbp hg38-shaped reference
+      (24 chromosomes, 50 % soft-masked, 5 % N), human-like edit regime (1 SNV / kbp + 1 indel / 5 kbp). With N GPUs the
+      alignment records of both haplotypes are sharded over the ranks by longest-processing-time-first, rank 0 packs the
+      reference and broadcasts the packed planes with one NCCL broadcast, every rank checks the planes it received against rank
+      0's checksum -- BASELINE configs[2] at N = 1, configs[3] at N > 1: STRONG scaling (total work fixed).
+        value  device-resident: packed planes, packed CIGAR ops and record descriptors already in HBM; one step = per-record
+               row counts + record scan + CIGAR walk + homology for this rank's records of both haplotypes, replayed as CUDA
+               graphs, timed with CUDA events on the library stream, L2 flushed (256 MB memset) between steps; rows stay in HBM.
+               value = rows of all ranks / max over ranks of the mean step time.
+        e2e    the call PAV makes, FASTA in -> DataFrames out: pavlib.cigarcall.make_insdel_snv_calls per haplotype at N = 1,
+               pav_b200.multigpu.make_insdel_snv_calls_dist at N > 1 (LPT shards -> NCCL broadcast -> per-rank walk -> host
+               gather -> frames on rank 0); wall clock, max over ranks.
+  C5  (`secondary`, every N; top level with --metric density)  10,000 flagged 50 kbp windows, k = 31 (BASELINE configs[4]),
+      split evenly over the ranks: inv k-mer Gbases/s device-resident and through pavlib.density.density_windows(lazy=True)
+      (ASCII windows in host memory -> run lengths of STATE in host memory, the columns stay in HBM until a window becomes a call).
+  C2  (`c2`, N = 1 only)  the round-1 line kept for continuity: 1 haplotype, 1,000 contigs x 200 kbp vs 200 Mbp, 1 edit / 100 bp;
+      the per-kernel roofline with ncu traffic (captures under profiles/ are taken on this input) lives here.
 
-Multi-GPU (weak scaling): every rank owns a different haplotype (1,000 contigs) against the same reference;
-rank 0 packs the reference and broadcasts the packed planes with one NCCL broadcast (libpavgpu dlopens NCCL);
-torch.distributed (gloo) is only the control plane (unique-id exchange, barriers, max-reduction of times).
-
---impl reference times the CPU oracle port (oracle/, the reference's algorithm restated in C + pandas row
-assembly; the Python reference itself cannot travel to the GPU box) on a bounded sample with all host cores.
+--impl reference times the UNMODIFIED reference (PAV 2.4.6.0, staged byte for byte under oracle/_ref by oracle/stage_ref.py, run
+with the stub third-party modules of oracle/ref_stubs) on the box's host cores: pavlib.cigarcall.make_insdel_snv_calls over a
+seeded sample of the C3 records, one record per worker process per step, and scripts/density.py spawned per window exactly like
+pavlib/inv.py:249-266 does (-t 1, one window per worker, all cores), start-up reported separately.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -39,7 +44,22 @@ sys.path.insert(0, REPO)
 
 METRIC = 'cigar_walk_variant_records_per_sec'
 UNIT = 'variant rows/s'
-WORKLOAD = 'C2: 1 haplotype, 1000 contigs x 200 kbp vs 200 Mbp reference (4 x 50 Mbp), 1 edit/100 bp, 50% REV'
+METRIC_B = 'inv_kmer_density_gbases_per_sec'
+UNIT_B = 'Gbases/s'
+WORKLOAD_C2 = 'C2: 1 haplotype, 1000 contigs x 200 kbp vs 200 Mbp reference (4 x 50 Mbp), 1 edit/100 bp, 50% REV'
+WIN_LEN = 50_000
+HOM_NAMES = ['homology_kernel', 'homology_tiled_kernel', 'homology_nbr_kernel', 'homology_bulk_kernel', 'homology_queue_kernel', 'homology_split_kernels']
+
+
+def workload_c3(args, world):
+    sc = '' if args.scale == 1.0 else f' [scale {args.scale}]'
+    return (f'C3{sc}: 2 phased haplotypes (h1/h2) of 10 Mbp contigs vs 3.1 Gbp hg38-shaped reference (24 chromosomes, 50% soft-masked, 5% N), '
+            f'{args.regime} edit regime, records sharded by alignment record (LPT) over {world} GPU(s)'
+            + (', one NCCL broadcast of the packed reference, host gather of the rows' if world > 1 else ''))
+
+
+def workload_c5(args, world):
+    return f'C5: {args.c5_windows} flagged windows x 50 kbp, k=31, srs=20, split over {world} GPU(s)'
 
 
 def log(*a):
@@ -49,73 +69,71 @@ def log(*a):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--contigs', type=int, default=1000, help='contigs per GPU (C2 = 1000)')
-    ap.add_argument('--contig-len', type=int, default=200_000)
-    ap.add_argument('--e2e-steps', type=int, default=4)
-    ap.add_argument('--cpu-sample-contigs', type=int, default=0, help='contigs in the CPU baseline sample (0 = 4 per core)')
-    ap.add_argument('--density-windows', type=int, default=296, help='windows in the secondary Path-B measurement (0 = skip)')
+    ap.add_argument('--metric', default='walk', choices=['walk', 'density'], help='which path is the top-level line (the other one is `secondary`)')
+    ap.add_argument('--scale', type=float, default=1.0, help='C3 size factor (1.0 = 3.1 Gbp; tests use 0.004)')
+    ap.add_argument('--regime', default='human', choices=['human', 'stress'])
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--c5-windows', type=int, default=10_000, help='windows of the Path-B sweep over all ranks (0 = skip)')
+    ap.add_argument('--c2', type=int, default=1, help='1: also run the C2 continuity leg at N = 1')
+    ap.add_argument('--c2-contigs', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--seed', type=int, default=1002)
+    ap.add_argument('--cpu-sample-records', type=int, default=0, help='C3 records in the CPU sample (0 = one per core)')
+    ap.add_argument('--cpu-density-windows', type=int, default=0,
+                    help='windows of the CPU density leg (0 = max(64, cores) for --impl reference, one per core otherwise)')
+    ap.add_argument('--seed', type=int, default=1003)
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------------
 def dist_env():
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    return rank, world, local
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
 
 
 class Control:
-    """Control plane: torch.distributed (gloo) when WORLD_SIZE > 1, no-ops otherwise."""
+    """Control plane: torch.distributed (gloo) when WORLD_SIZE > 1, no-ops otherwise. No tensor of the data path goes through it."""
 
     def __init__(self, rank, world):
         self.rank, self.world = rank, world
         self.dist = None
         if world > 1:
-            import torch
+            import datetime
+
             import torch.distributed as dist
             os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-            dist.init_process_group('gloo', rank=rank, world_size=world)
-            self.dist, self.torch = dist, torch
+            dist.init_process_group('gloo', rank=rank, world_size=world, timeout=datetime.timedelta(minutes=30))
+            self.dist = dist
 
     def barrier(self):
         if self.dist:
             self.dist.barrier()
 
-    def max(self, v):
+    def gather(self, obj):
+        """list with every rank's ``obj`` (on every rank)."""
         if not self.dist:
-            return v
-        t = self.torch.tensor([float(v)], dtype=self.torch.float64)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t[0])
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def max(self, v):
+        return max(self.gather(float(v)))
 
     def sum(self, v):
-        if not self.dist:
-            return v
-        t = self.torch.tensor([float(v)], dtype=self.torch.float64)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return float(t[0])
+        return sum(self.gather(float(v)))
 
-    def bcast_bytes(self, b, n):
+    def bcast(self, obj):
         if not self.dist:
-            return b
-        t = self.torch.zeros(n, dtype=self.torch.uint8)
-        if self.rank == 0:
-            t = self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8).clone()
-        self.dist.broadcast(t, 0)
-        return bytes(t.numpy().tobytes())
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
 
     def close(self):
         if self.dist:
             self.dist.destroy_process_group()
-
-
-import contextlib
 
 
 @contextlib.contextmanager
@@ -188,12 +206,75 @@ def measured_peak_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def read_align(path):
+    import pandas as pd
+    return pd.read_csv(path, sep='\t', dtype={'#CHROM': str, 'QRY_ID': str}, keep_default_na=False)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Workload files (rank 0 writes, every rank reads)
+# ----------------------------------------------------------------------------------------------------------
+def make_c3_files(args, tmp, only_records=None):
+    """Generate C3 and write ref.fa, {h1,h2}_tig.fa, {h1,h2}_align.bed under ``tmp``. ``only_records``: {hap: record indices} --
+    write only those records, their contigs and their chromosomes (the CPU sample of --impl reference)."""
+    from pav_b200 import synth
+    t0 = time.perf_counter()
+    ref, trs = synth.config_c3_reference(seed=args.seed, scale=args.scale)
+    haps = {h: synth.config_c3_haplotype(ref, trs, h, seed=args.seed, scale=args.scale, regime=args.regime) for h in ('h1', 'h2')}
+    synth.config_c3_mask(ref, seed=args.seed)
+    t1 = time.perf_counter()
+    keep_chrom = set()
+    n_rec = {h: len(d[1]) for h, d in haps.items()}
+    for h, (tigs, df) in haps.items():
+        if only_records is not None:
+            df = df.iloc[only_records[h]]
+            tigs = {q: tigs[q] for q in df['QRY_ID']}
+            keep_chrom.update(df['#CHROM'])
+        synth.write_fasta(os.path.join(tmp, f'{h}_tig.fa'), tigs)
+        df.to_csv(os.path.join(tmp, f'{h}_align.bed'), sep='\t', index=False)
+    ref_bp = int(sum(len(v) for v in ref.values()))
+    if only_records is not None:
+        ref = {c: a for c, a in ref.items() if c in keep_chrom}
+    synth.write_fasta(os.path.join(tmp, 'ref.fa'), ref)
+    log(f'C3 generated in {t1 - t0:.1f}s, written in {time.perf_counter() - t1:.1f}s: reference {ref_bp / 1e9:.3f} Gbp, records {n_rec}')
+    return {'reference_bp': ref_bp, 'records': n_rec, 'seconds_generate': t1 - t0, 'seconds_write': time.perf_counter() - t1}
+
+
+def c3_record_counts(args):
+    """Records per C3 haplotype without generating it (one per contig length of every chromosome, tails under 20 kbp dropped)."""
+    from pav_b200 import synth
+    contig_len = max(int(10_000_000 * args.scale), 40_000)
+    n = 0
+    for x in synth.HG38_LENGTHS:
+        ln = max(int(x * args.scale), 40_000)
+        for start in range(0, ln, contig_len):
+            if min(contig_len, ln - start) < 20_000:
+                break
+            n += 1
+    return {'h1': n, 'h2': n}
+
+
+def c5_windows_range(seed, lo, hi):
+    """Windows lo..hi-1 of the C5 sweep, each from its own seeded generator (so any rank can make its share): 30 % with 1-3 kbp
+    inverted-repeat flanks, 0.5 % divergence, 10 % negative controls, inversion of 2-20 kbp."""
+    from pav_b200 import synth
+    out = []
+    for w in range(lo, hi):
+        rng = np.random.default_rng([seed, 0xC5, w])
+        neg = bool(rng.random() < 0.1)
+        flank = int(rng.integers(1000, 3001)) if rng.random() < 0.3 else 0
+        r, t, iv = synth.make_inv_window(rng, WIN_LEN, None, flank, 0.005, neg)
+        out.append((r, t, iv, neg))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU legs: the unmodified reference
 # ----------------------------------------------------------------------------------------------------------
 _POOL = None
 
 
 def _pool(cores):
-    """Worker processes are started once and reused by every step (each task still re-reads the FASTA files)."""
     global _POOL
     if _POOL is None:
         import multiprocessing as mp
@@ -201,160 +282,614 @@ def _pool(cores):
     return _POOL
 
 
-def cpu_port_rows_per_sec(df_align, ref_fa, tig_fa, n_contigs, cores, fast=False):
-    """Oracle port of make_insdel_snv_calls on a bounded sample, one record shard per worker process."""
-    sample = df_align.iloc[:n_contigs]
-    shards = [sample.iloc[i::cores] for i in range(cores) if len(sample.iloc[i::cores])]
+def _ref_shard(task):
+    """One worker = one Snakemake-style job: the reference's own make_insdel_snv_calls on its records (rules/call.snakefile:810)."""
+    bed, rows, ref_fa, tig_fa, hap = task
+    from oracle import refenv
+    refenv.activate()
+    import pavlib.cigarcall
+    import pysam
+    pysam._CACHE.clear()      # nothing cached between steps, like a fresh job
+    df = read_align(bed).iloc[rows]
+    a, b = pavlib.cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, hap, version_id=False)
+    return len(a) + len(b)
+
+
+def reference_walk_step(tasks, cores):
     pool = _pool(cores)
     t0 = time.perf_counter()
-    counts = pool.map(_cpu_shard_fast if fast else _cpu_shard, [(s, ref_fa, tig_fa) for s in shards], chunksize=1)
+    counts = pool.map(_ref_shard, tasks, chunksize=1)
     dt = time.perf_counter() - t0
-    rows = int(sum(counts))
-    return rows / dt, rows, dt, len(shards)
+    return int(sum(counts)), dt
 
 
-def _cpu_shard(args):
-    from oracle import pyoracle
-    df, ref_fa, tig_fa = args
-    pyoracle._FA_CACHE.clear()   # like a fresh Snakemake job: nothing cached between steps
-    # reference_containers=True: frames assembled the way the reference does (pd.Series per variant + concat),
-    # measured within 7 % of the unmodified reference's throughput in the build container (DESIGN.md)
-    a, b = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False, reference_containers=True)
-    return len(a) + len(b)
+def reference_density(windows, tmp, cores):
+    """scripts/density.py per window, spawned like pavlib/inv.py:249-266 (-t 1), ``cores`` processes at a time. Returns
+    (Gbases/s, seconds, start-up seconds per process, return codes)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import refenv
+    from pav_b200 import synth
+    env = dict(os.environ)
+    env['PYTHONPATH'] = os.pathsep.join(refenv.pythonpath_entries())
+    script = os.path.join(refenv.REF_ROOT, 'scripts', 'density.py')
+    jobs = []
+    for i, (r, t, _, _) in enumerate(windows):
+        d = os.path.join(tmp, f'dw{i}')
+        os.makedirs(d, exist_ok=True)
+        synth.write_fasta(os.path.join(d, 'ref.fa'), {'chrW': r})
+        synth.write_fasta(os.path.join(d, 'tig.fa'), {'tigW': t})
+        jobs.append([sys.executable, script, '--tigregion', f'tigW:1-{len(t)}', '--refregion', f'chrW:1-{len(r)}', '--ref', os.path.join(d, 'ref.fa'),
+                     '--tig', os.path.join(d, 'tig.fa'), '-k', '31', '-t', '1', '-r', 'false', '--staterunsmooth', '20'])
+
+    def run(cmd):
+        return subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env).returncode
+    t0 = time.perf_counter()
+    subprocess.run([sys.executable, '-c', 'import scipy.stats, pandas, numpy, pavlib, kanapy.util.kmer'], env=env,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    startup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        rcs = list(ex.map(run, jobs))
+    dt = time.perf_counter() - t0
+    bases = sum(len(w[1]) for w in windows)
+    return bases / dt / 1e9, dt, startup, rcs
 
 
-def _cpu_shard_fast(args):
-    from oracle import pyoracle
-    df, ref_fa, tig_fa = args
-    pyoracle._FA_CACHE.clear()
-    a, b = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
-    return len(a) + len(b)
-
-
-def cpu_sample_contigs(args, cores, n_steps):
-    """Contigs in the CPU sample: about min(15 s, 150 s / steps) of wall time per step at ~9e3 rows/s/core."""
-    if args.cpu_sample_contigs:
-        return min(args.cpu_sample_contigs, args.contigs)
-    t_step = min(15.0, 150.0 / max(n_steps, 1))
-    rows_per_contig = args.contig_len * 0.00975
-    n = int(9000.0 * cores * t_step / rows_per_contig)
-    return max(min(n, args.contigs), min(cores, args.contigs))
+def cpu_sample(args, cores, n_rec):
+    """{hap: record indices}: a seeded sample of the C3 records, one per core by default, alternating haplotypes."""
+    n = args.cpu_sample_records or cores
+    rng = np.random.default_rng([args.seed, 0x5A])
+    pick = {'h1': [], 'h2': []}
+    order = {h: rng.permutation(n_rec[h]).tolist() for h in ('h1', 'h2')}
+    for i in range(n):
+        h = 'h1' if i % 2 == 0 else 'h2'
+        if order[h]:
+            pick[h].append(order[h].pop())
+    return {h: sorted(v) for h, v in pick.items()}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: CPU oracle port, rank 0 only."""
+    """--impl reference: the unmodified reference on the host cores, rank 0 only."""
     if rank != 0:
         return
-    from oracle import pyoracle
-    from pav_b200 import synth
-    pyoracle.build()
+    from oracle import refenv
+    if not refenv.available():
+        print(json.dumps({'impl': 'reference', 'unavailable': 'neither /root/reference nor the staged copy oracle/_ref is present '
+                                                              '(oracle/stage_ref.py stages it in the build container)'}), flush=True)
+        return
     cores = len(os.sched_getaffinity(0))
-    n_sample = cpu_sample_contigs(args, cores, args.warmup + args.steps)
     tmp = tempfile.mkdtemp(prefix='pavbench_ref_')
-    chrom_len = args.contigs * args.contig_len // 4
-    ref, trs = synth.make_reference(args.seed, 4, chrom_len)
-    tigs, df = synth.make_contigs(ref, trs, args.seed, n_sample, args.contig_len)
-    ref_fa, tig_fa, _ = synth.write_cigar_workload(tmp, ref, tigs, df)
-    vals = []
+    n_rec = c3_record_counts(args)
+    pick = cpu_sample(args, cores, n_rec)
+    info = make_c3_files(args, tmp, only_records=pick)     # only the sample's contigs and chromosomes are written
+    tasks = []
+    for h in ('h1', 'h2'):
+        bed = os.path.join(tmp, f'{h}_align.bed')
+        tasks += [(bed, [i], os.path.join(tmp, 'ref.fa'), os.path.join(tmp, f'{h}_tig.fa'), h) for i in range(len(pick[h]))]
+    vals, rows = [], 0
     for i in range(args.warmup + args.steps):
-        rps, rows, dt, used = cpu_port_rows_per_sec(df, ref_fa, tig_fa, n_sample, cores)
+        rows, dt = reference_walk_step(tasks, cores)
         if i >= args.warmup:
-            vals.append((rps, dt))
-        log(f'[reference] step {i}: {rows} rows in {dt:.2f}s -> {rps:.0f} rows/s on {used} processes')
+            vals.append((rows / dt, dt))
+        log(f'[reference] step {i}: {rows} rows in {dt:.2f}s -> {rows / dt:.0f} rows/s on {min(cores, len(tasks))} processes')
+        if i >= args.warmup and sum(d for _, d in vals) > 120 and len(vals) >= 3:
+            log('[reference] time budget reached: stopping the timed steps early')
+            break
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([d for _, d in vals]) * 1e3)
-    sample = f'{n_sample} of {args.contigs} contigs ({rows} variant rows), FASTA read + C walk + reference-style DataFrame assembly per step'
+    sample = (f'{len(tasks)} of {sum(info["records"].values())} C3 records (seeded sample, one per worker process; {rows} variant rows per step): FASTA read '
+              f'by .fai offset + the reference\'s own make_insdel_snv_calls (pavlib/cigarcall.py:24-362, unmodified, oracle/_ref) per step; '
+              f'{len(vals)} timed steps')
+    sec = None
+    if args.c5_windows > 0:
+        n_w = min(args.cpu_density_windows or max(64, cores), args.c5_windows)
+        wins = c5_windows_range(1005, 0, n_w)
+        gb, dt, startup, rcs = reference_density(wins, tmp, cores)
+        sec = {'impl': 'reference', 'metric': METRIC_B, 'value': gb, 'unit': UNIT_B, 'seconds': dt, 'cores': cores,
+               'config': {'workload': workload_c5(args, args.gpus)},
+               'cpu_baseline': {'value': gb, 'unit': UNIT_B, 'cores': cores, 'kind': 'reference',
+                                'sample': f'first {n_w} of {args.c5_windows} C5 windows, one `python3 scripts/density.py ... -t 1` process per window '
+                                          f'(spawned like pavlib/inv.py:249-266), {cores} at a time; interpreter + import start-up ({startup:.2f}s per '
+                                          f'process, measured separately) is inside the time',
+                                'startup_seconds_per_process': startup, 'return_codes': {str(c): rcs.count(c) for c in set(rcs)}}}
+        log(f'[reference] density: {n_w} windows in {dt:.1f}s = {gb:.3e} Gbases/s on {cores} cores (start-up {startup:.2f}s per process)')
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'int32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'contigs_per_gpu': args.contigs, 'contig_len': args.contig_len, 'reference_bp': 4 * chrom_len},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': sample},
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
+        'config': {'workload': workload_c3(args, args.gpus), 'reference_bp': info['reference_bp'], 'records': info['records']},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': min(cores, len(tasks)), 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'note': 'CPU oracle port: oracle/pav_oracle.c walk + frames assembled with the reference\'s own idiom (pd.Series per variant + concat); '
-                'this port measured 9.1e3 rows/s/core vs 8.5e3 for the unmodified Python reference on the same input in the build container (DESIGN.md)',
+        'secondary': sec,
     }
+    if args.metric == 'density' and sec is not None:
+        top = dict(sec)
+        top.update({'n_gpus': args.gpus, 'steps': 1, 'warmup': 0, 'ms_per_step': sec['seconds'] * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+                    'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                    'e2e': {'value': sec['value'], 'unit': UNIT_B, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                    'secondary': {k: v for k, v in line.items() if k != 'secondary'}})
+        line = top
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------
-def density_secondary(ctx, args, rank):
-    """Path B: inv k-mer Gbases/s on C5-shaped windows (device-resident value + public-API e2e) + an oracle spot check."""
-    from pav_b200 import _capi, device, synth
-    from pav_b200.pavlib import density
-    n_win = args.density_windows
-    ref, tig, meta = synth.make_inv_workload(seed=1005 + rank, n_win=n_win, win_len=50_000)
-    names_r, names_t = list(ref), list(tig)
-    rs = device.SeqStore(ctx, names_r, [ref[n] for n in names_r], keep_host=False)
-    ts = device.SeqStore(ctx, names_t, [tig[n] for n in names_t], keep_host=False)
-    win = np.zeros(n_win, dtype=_capi.DENSITY_WINDOW)
-    for i in range(n_win):
-        win[i] = (i, i, 0, 50_000, 0, 50_000, 0, 20)
-    batch = density.DensityBatch(ctx, win, density.default_params())
-    ms, st = [], None
-    for i in range(1 + 2):
-        ctx.l2_flush()
-        st = batch.run(rs, ts)
-        if i >= 1:
-            ms.append(st.ms_kernels)
-    bases = n_win * 50_000
-    res, cols = batch.fetch()
-    batch.close()
-    rs.close()
-    ts.close()
-    e2e_runs = []
-    for i in range(3):   # one warm-up call (first-use allocation of the pinned result pool), two timed ones
-        out = None       # releasing the previous result is not part of the call
-        t0 = time.perf_counter()
-        out = density.density_windows([(ref[a], tig[b], False, 20) for a, b, _, _ in meta])
-        if i >= 1:
-            e2e_runs.append(time.perf_counter() - t0)
-    e2e_s = float(np.mean(e2e_runs))
-    e2e_d2h = int(sum(sum(v.nbytes for k, v in d.items() if hasattr(v, 'nbytes')) for d in out))
-    # spot check window 0 against the oracle
-    ok, cpu = None, None
+# Our arm
+# ----------------------------------------------------------------------------------------------------------
+def shard_plan(dfs, world):
+    """{hap: list of index arrays, one per rank}: LPT over the records of both haplotypes together (one cost model, one balance)."""
+    from pav_b200 import multigpu
+    costs, owner = [], []
+    for h, df in dfs.items():
+        span = (df['END'] - df['POS']).to_numpy(np.int64)
+        costs.append(multigpu.record_costs(df['CIGAR'].tolist(), span))
+        owner += [(h, i) for i in range(len(df))]
+    shards = multigpu.lpt_shards(np.concatenate(costs), world)
+    plan = {h: [[] for _ in range(world)] for h in dfs}
+    for r, idx in enumerate(shards):
+        for j in idx.tolist():
+            h, i = owner[j]
+            plan[h][r].append(i)
+    return {h: [np.array(sorted(v), dtype=np.int64) for v in plan[h]] for h in plan}
+
+
+class ResidentHap:
+    """This rank's records of one haplotype resident in HBM (contig planes + packed ops)."""
+
+    def __init__(self, ctx, hap, df, rows, tig_fa, ref_names):
+        from pav_b200 import device
+        from pav_b200 import fasta as fasta_mod
+        self.hap, self.tig_fa_path = hap, tig_fa
+        self.df = df.iloc[rows].reset_index(drop=True)
+        fa = fasta_mod.open_fasta(tig_fa)
+        names_t = list(dict.fromkeys(self.df['QRY_ID']))
+        self.tig_store = device.SeqStore(ctx, names_t, [fa.fetch_array(n) for n in names_t], keep_host=False)
+        tidx = {n: i for i, n in enumerate(names_t)}
+        ridx = {n: i for i, n in enumerate(ref_names)}
+        rid = np.array([ridx[c] for c in self.df['#CHROM']], np.int32)
+        qid = np.array([tidx[c] for c in self.df['QRY_ID']], np.int32)
+        ops, op_off, perr = device.parse_cigars(self.df['CIGAR'].tolist())
+        assert perr.code == 0
+        self.batch = None
+        if len(self.df):
+            self.batch = device.CigarBatch(ctx, rid, qid, self.df['POS'].to_numpy(np.int32), self.df['REV'].to_numpy(np.uint8), ops, op_off)
+
+    def run(self, ref_store):
+        return self.batch.run(ref_store, self.tig_store) if self.batch is not None else None
+
+    def close(self):
+        if self.batch is not None:
+            self.batch.close()
+        self.tig_store.close()
+
+
+def oracle_check_records(rh, tmp, ref_fa, tag, n_chk=2):
+    """Rows of up to ``n_chk`` of this rank's records (on its smallest chromosome) against the oracle. True / False / None."""
+    if rh.batch is None or len(rh.df) == 0:
+        return None
     try:
         from oracle import pyoracle
-        t0 = time.perf_counter()
-        rc, o = pyoracle.density_arrays(ref[names_r[0]].tobytes(), tig[names_t[0]].tobytes())
-        cpu_s = time.perf_counter() - t0
-        ok = bool(rc == out[0]['status'] and all((out[0][c].astype(np.int64) == o[c].astype(np.int64)).all()
-                                                 for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE')))
-        cpu = {'value': 50_000 / cpu_s / 1e9, 'unit': 'Gbases/s', 'cores': 1, 'kind': 'port',
-               'sample': f'1 of {n_win} windows (50 kbp) through oracle/pav_oracle.c (scalar C, O(N*E) KDE), {cpu_s:.2f} s',
-               'note': 'the Python reference (scripts/density.py) needs 8.2 s for such a window in the build container = 6.1e-6 Gbases/s/core (BASELINE.md)'}
+        from pav_b200 import fasta as fasta_mod
+        from pav_b200 import synth
+        fa_r = fasta_mod.open_fasta(ref_fa)
+        small = min(set(rh.df['#CHROM']), key=fa_r.length)
+        pick = np.flatnonzero((rh.df['#CHROM'] == small).to_numpy())[:n_chk]
+        sub = rh.df.iloc[pick]
+        fa_t = fasta_mod.open_fasta(rh.tig_fa_path)
+        ref_p, tig_p, _ = synth.write_cigar_workload(os.path.join(tmp, f'chk_{tag}'), {small: fa_r.fetch_array(small)},
+                                                     {q: fa_t.fetch_array(q) for q in sub['QRY_ID']}, sub)
+        o_snv, o_indel, _ = pyoracle.walk_rows(sub, ref_p, tig_p)
+        snv, indel, cerr = rh.batch.fetch()
+        assert cerr.code == 0
+        g_snv, g_indel = snv[np.isin(snv['rec'], pick)], indel[np.isin(indel['rec'], pick)]
+        return bool(len(g_snv) == len(o_snv) and (g_snv['pos_ref'] == o_snv['pos_ref']).all() and (g_snv['qry_pos'] == o_snv['qry_pos']).all()
+                    and len(g_indel) == len(o_indel)
+                    and all((g_indel[c] == o_indel[c]).all() for c in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r',
+                                                                         'hom_tig_l', 'hom_tig_r')))
     except Exception as ex:  # noqa: BLE001
-        log('density oracle spot check failed to run:', ex)
-    k_ms = float(np.mean(ms))
-    # SURVEY 8(d): two roofs for Path B. The k-mer part (reference table, state per contig k-mer, compaction) is HBM work:
-    # per window of W bases ceil(2W/4) plane bytes + 8W table insert + 2*8*(W-k+1) probes + (W-k+1)*(8+4+1) out. The KDE part is
-    # float64 arithmetic on CUDA cores (exp + FMA), not HBM and not tensor cores: no HBM fraction is claimed for it; its size is
-    # the number of evaluated lattice points E against the N informative rows (the reference evaluates every sampled point against
-    # every k-mer of a state: N*E "logical pairs"; the kernels here get the same values from run prefix trees).
-    W, K = 50_000, 31
-    rows = int(st.rows)
-    kmer_bytes = n_win * (-(-2 * W // 4) + 8 * W + 16 * (W - K + 1) + 13 * (W - K + 1))
-    peak, peak_src = measured_peak_gbs()
-    n_eval = int(np.asarray(res['n_eval'], dtype=np.int64).sum())
-    roofs = {
-        'kmer_part': {'bound': 'hbm', 'kernels': 'ref_insert + tig_state + compact', 'algorithmic_bytes': int(kmer_bytes), 'ms': float(st.ms_kmer),
-                      'achieved': kmer_bytes / (st.ms_kmer * 1e-3) / 1e9 if st.ms_kmer > 0 else None, 'peak': peak, 'unit': 'GB/s',
-                      'frac': kmer_bytes / (st.ms_kmer * 1e-3) / 1e9 / peak if st.ms_kmer > 0 else None, 'peak_source': peak_src},
-        'kde_part': {'bound': 'float64 CUDA-core arithmetic (exp + FMA), not HBM', 'kernels': 'runs_stats + kde_tree + kde_eval x2 + gap_classify + interp + finalize',
-                     'ms': float(st.ms_kde), 'rows_N': rows, 'evaluated_points_E': n_eval, 'eval_fraction_E_over_N': n_eval / rows if rows else None,
-                     'logical_pairs': int(st.kde_pairs), 'logical_pairs_per_sec': st.kde_pairs / (st.ms_kde * 1e-3) if st.ms_kde > 0 else None,
-                     'output_bytes': rows * 25},
-    }
+        log(f'[{tag}] oracle spot check failed to run: {ex!r}')
+        return None
+
+
+def kernel_table(count_ms, walk_ms, hom_ms, hom_kernel, n_ops, n_chunks, n_snv, n_indel):
+    """kernel -> (ms, algorithmic bytes per launch): DESIGN.md section 3."""
     return {
-        'roofline': roofs,
-        'metric': 'inv_kmer_density_gbases_per_sec', 'unit': 'Gbases/s', 'value': bases / (k_ms * 1e-3) / 1e9,
-        'e2e': {'value': bases / e2e_s / 1e9, 'unit': 'Gbases/s', 'ms_per_step': e2e_s * 1e3, 'h2d_bytes_per_step': 2 * bases, 'd2h_bytes_per_step': e2e_d2h,
-                'api': 'pav_b200.pavlib.density.density_windows (ASCII windows in host memory -> column arrays in host memory)'},
-        'config': {'workload': f'C5-shaped: {n_win} windows x 50 kbp, k=31, srs=20 per GPU', 'l2': 'flushed between iterations'},
-        'ms_per_step': k_ms, 'ms_kmer': st.ms_kmer, 'ms_kde': st.ms_kde, 'kde_pairs': int(st.kde_pairs),
-        'kde_pairs_per_sec': st.kde_pairs / (st.ms_kde * 1e-3) if st.ms_kde > 0 else None,
-        'rows': int(st.rows), 'gpu_launches': int(st.kernel_launches), 'oracle_spot_check': ok, 'cpu_baseline': cpu,
+        'cigar_count+rec_scan': (count_ms, 4 * n_ops + 4 * n_chunks),
+        'cigar_walk_kernel': (walk_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 64 * n_indel),
+        HOM_NAMES[hom_kernel]: (hom_ms, (64 + 64 + 128) * n_indel),
     }
+
+
+BYTES_MODEL = ('4 B/op + 4 B/chunk (count); 4 B/op + 32 B/chunk descriptors + 16 B/SNV row + 64 B/indel stub (walk); 64 B stub + 64 B row + 128 B of '
+               'sequence = one 32-byte DRAM sector from each of the four planes an indel touches (homology); DESIGN.md section 3')
+
+
+def leg_c3(args, ctl, ctx, tmp, rank, world):
+    """C3 sharded over the ranks: device-resident value + end-to-end call. Returns the fields of the top-level line."""
+    from pav_b200 import device, multigpu
+    from pav_b200 import fasta as fasta_mod
+    from pav_b200.pavlib import cigarcall
+    info = make_c3_files(args, tmp) if rank == 0 else None
+    ctl.barrier()
+    info = ctl.bcast(info)
+    ref_fa = os.path.join(tmp, 'ref.fa')
+    tig_fa = {h: os.path.join(tmp, f'{h}_tig.fa') for h in ('h1', 'h2')}
+    dfs = {h: read_align(os.path.join(tmp, f'{h}_align.bed')) for h in ('h1', 'h2')}
+    plan = shard_plan(dfs, world)
+
+    # ---- reference planes: rank 0 packs, everyone else receives them over NCCL; every rank verifies what it holds
+    fa_r = fasta_mod.open_fasta(ref_fa)
+    ref_names = [str(n) for n in fa_r.index]
+    t0 = time.perf_counter()
+    if rank == 0:
+        ref_store = device.SeqStore(ctx, ref_names, [fa_r.fetch_array(n) for n in ref_names], keep_host=False)
+    else:
+        ref_store = device.SeqStore.from_packed(ctx, ref_names, [fa_r.length(n) for n in ref_names], None, None)
+    t_pack = time.perf_counter() - t0
+    bcast_ms = 0.0
+    if world > 1:
+        uid = ctl.bcast(device.nccl_unique_id() if rank == 0 else None)
+        ctl.barrier()
+        with stdout_to_stderr():   # NCCL prints its version banner on stdout; the driver wants one JSON line there
+            bcast_ms = ref_store.broadcast(uid, rank, world)
+    sums = ctl.gather(ref_store.checksum())
+    planes_ok = [s == sums[0] for s in sums]
+    if not all(planes_ok):
+        raise RuntimeError(f'reference planes differ between ranks after the broadcast: {sums}')
+    bcast_ms = ctl.max(bcast_ms)
+    _, b2, _, bm = ref_store.plane_sizes()
+
+    # ---- this rank's records -> HBM
+    haps = [ResidentHap(ctx, h, dfs[h], plan[h][rank], tig_fa[h], ref_names) for h in ('h1', 'h2')]
+    ctl.barrier()
+
+    def step():
+        ctx.l2_flush()
+        return [s for s in (rh.run(ref_store) for rh in haps) if s is not None]
+
+    clocks = ClockSampler(ctx.device)   # spans warm-up, the timed steps and identical untimed steps (the timed region is milliseconds)
+    t_clk = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctl.barrier()
+    step_ms, launches, graph_used = [], 0, True
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        sts = step()
+        step_ms.append(sum(s.ms_kernels for s in sts))
+        launches += sum(int(s.kernel_launches) for s in sts)
+        graph_used = graph_used and all(int(s.graph) == 1 for s in sts)
+    wall_ms = (time.perf_counter() - wall0) * 1e3 / max(args.steps, 1)
+    while time.perf_counter() - t_clk < 1.2:
+        step()
+    clk = clocks.stop()
+    clk['window'] = 'warm-up + timed steps + identical untimed steps, >= 1.2 s in total, nvidia-smi -lms 50'
+    ctl.barrier()
+    # per-kernel split: the same steps once more without the graph (events between the launches)
+    os.environ['PAVGPU_NO_GRAPH'] = '1'
+    parts = []
+    for _ in range(6):
+        sts = step()
+        parts.append((sum(s.ms_count for s in sts), sum(s.ms_scan for s in sts), sum(s.ms_homology for s in sts), sum(s.ms_kernels for s in sts)))
+    os.environ.pop('PAVGPU_NO_GRAPH', None)
+    count_ms, walk_ms, hom_ms, nograph_ms = [float(np.mean([p[i] for p in parts[2:]])) for i in range(4)]
+    sts = step()
+    n_snv, n_indel = sum(int(s.n_snv) for s in sts), sum(int(s.n_indel) for s in sts)
+    n_ops, n_chunks = sum(int(s.n_ops) for s in sts), sum(int(s.n_chunks) for s in sts)
+    hom_kernel = max((int(s.homology_tiled) for s in sts), default=0)
+    my_rows = n_snv + n_indel
+    my_ms = float(np.mean(step_ms)) if step_ms else 0.0
+    parity = [oracle_check_records(rh, tmp, ref_fa, f'r{rank}_{rh.hap}') for rh in haps]
+    per_rank = ctl.gather({'rank': rank, 'records': int(sum(len(rh.df) for rh in haps)), 'ops': n_ops, 'rows': my_rows, 'ms_per_step': my_ms,
+                           'ms_count_scan': count_ms, 'ms_walk': walk_ms, 'ms_homology': hom_ms, 'ms_per_step_without_graph': nograph_ms,
+                           'planes_checksum_equal_rank0': planes_ok[rank], 'oracle_spot_check': parity, 'graph': graph_used,
+                           'sm_mhz': clk.get('sm_mhz'), 'clock_reasons': clk.get('reasons')})
+    ms_per_step = max(p['ms_per_step'] for p in per_rank)
+    total_rows = sum(p['rows'] for p in per_rank)
+    value = total_rows / (ms_per_step * 1e-3) if ms_per_step > 0 else 0.0
+    span = int(sum((rh.df['END'] - rh.df['POS']).sum() for rh in haps))
+    for rh in haps:
+        rh.close()
+    checks = [x for p in per_rank for x in p['oracle_spot_check']]
+
+    # ---- end to end: FASTA in -> DataFrames out (on rank 0 when sharded)
+    e2e_s, e2e_rows, phases = [], 0, None
+    E2E_WARMUP = 1
+    os.environ.setdefault('PAVGPU_TUNE_ALLOC', '1')    # opt-in allocator tuning of the frame builder (INTEGRATION.md), declared in `config`
+    for i in range((E2E_WARMUP + args.e2e_steps) if args.e2e_steps > 0 else 0):
+        fasta_mod._CACHE.clear()   # every step re-opens and re-reads the FASTA files, like a fresh Snakemake job would
+        out = None                 # the previous step's frames are released before the clock starts (the CPU arm's workers exit with theirs)
+        ctl.barrier()
+        t0 = time.perf_counter()
+        rows_step, ph = 0, {}
+        for h in ('h1', 'h2'):
+            if world > 1:
+                with stdout_to_stderr():
+                    out = multigpu.make_insdel_snv_calls_dist(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
+                ph[h] = multigpu.last_dist_stats['seconds']
+            else:
+                out = cigarcall.make_insdel_snv_calls(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
+                ph[h] = cigarcall.last_phase_seconds
+            if out is not None:
+                rows_step += len(out[0]) + len(out[1])
+            out = None
+        dt = ctl.max(time.perf_counter() - t0)
+        if i >= E2E_WARMUP:
+            e2e_s.append(dt)
+            e2e_rows, phases = rows_step, ph
+        log(f'[rank {rank}] e2e step {i}: {dt:.2f}s ({rows_step} rows formatted on this rank) {ph}')
+    e2e_rows = int(ctl.max(e2e_rows))
+    if e2e_s:
+        assert e2e_rows == total_rows, (e2e_rows, total_rows)
+    contig_bytes = int(sum(fasta_mod.open_fasta(tig_fa[h]).length(n) for h in ('h1', 'h2') for n in set(dfs[h]['QRY_ID'])))
+    # per e2e step: each of the two haplotype calls uploads the reference (ASCII, packing rank) and every rank its contigs and ops
+    h2d = int(2 * info['reference_bp'] + contig_bytes + 4 * ctl.sum(n_ops))
+    d2h = int(16 * ctl.sum(n_snv) + 64 * ctl.sum(n_indel))
+    e2e_val = total_rows / float(np.mean(e2e_s)) if e2e_s else None
+
+    # ---- roofline of the dominant kernel on rank 0's shard (SURVEY 8(d) model beside this design's own)
+    peak, peak_src = measured_peak_gbs()
+    kernels = kernel_table(count_ms, walk_ms, hom_ms, hom_kernel, n_ops, n_chunks, n_snv, n_indel)
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels[dom]
+    step_bytes = sum(b for _, b in kernels.values())
+    survey_bytes = 4 * n_ops + -(-2 * span // 4) + -(-2 * span // 8) + 32 * n_snv + 64 * n_indel
+    roofline = {
+        'bound': 'hbm', 'kernel': dom, 'achieved': dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, 'peak': peak, 'unit': 'GB/s',
+        'frac': dom_bytes / (dom_ms * 1e-3) / 1e9 / peak if dom_ms > 0 else 0.0, 'traffic': None, 'peak_source': peak_src,
+        'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': dom_ms, 'per_kernel_ms': {k: v[0] for k, v in kernels.items()},
+        'per_kernel_ms_source': 'rank 0, both haplotype batches, the timed steps repeated without the CUDA graph (events between the launches); '
+                                'the timed steps themselves replay one graph per haplotype batch',
+        'step': {'algorithmic_bytes': int(step_bytes), 'achieved': step_bytes / (my_ms * 1e-3) / 1e9 if my_ms else None,
+                 'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak if my_ms else None},
+        'survey_8d_model': {'algorithmic_bytes': int(survey_bytes), 'achieved': survey_bytes / (my_ms * 1e-3) / 1e9 if my_ms else None,
+                            'frac': survey_bytes / (my_ms * 1e-3) / 1e9 / peak if my_ms else None, 'per': 'whole step of rank 0 (count + walk + homology)'},
+        'bytes_model': BYTES_MODEL,
+        'note': 'traffic (DRAM bytes from ncu) is reported for the C2 leg (`c2.roofline`), the input the ncu captures under profiles/ are taken on',
+    }
+    ref_store.close()
+    return {
+        'value': value, 'ms_per_step': ms_per_step, 'per_rank': per_rank, 'rows': total_rows, 'gpu_launches': int(ctl.sum(launches)),
+        'wall_ms_per_step_incl_flush': wall_ms, 'roofline': roofline, 'clocks': clk, 'ref_broadcast_ms': bcast_ms,
+        'ref_broadcast_bytes': int(b2 + bm) if world > 1 else 0, 'ref_pack_seconds_rank0': ctl.bcast(t_pack),
+        'planes_verified_on_every_rank': all(planes_ok), 'oracle_spot_check': bool(checks) and all(x is not False for x in checks) and any(x for x in checks),
+        'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': args.e2e_steps, 'warmup': E2E_WARMUP,
+                'ms_per_step': float(np.mean(e2e_s)) * 1e3 if e2e_s else None,
+                'api': ('pav_b200.multigpu.make_insdel_snv_calls_dist per haplotype (LPT shards, NCCL broadcast of the packed reference, plane checksum on '
+                        'every rank, per-rank walk, host gather, frames on rank 0)' if world > 1 else
+                        'pav_b200.pavlib.cigarcall.make_insdel_snv_calls per haplotype (FASTA in, DataFrames out)'),
+                'phase_seconds_last_step_rank0': phases},
+        'info': info,
+    }
+
+
+def leg_c5(args, ctl, ctx, rank, world):
+    """C5 sweep split over the ranks: device-resident Gbases/s + the public call with lazy columns + oracle spot check."""
+    from pav_b200 import _capi, device
+    from pav_b200.pavlib import density
+    n_total = args.c5_windows
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    t0 = time.perf_counter()
+    wins = c5_windows_range(1005, lo, hi)
+    t_gen = time.perf_counter() - t0
+    CHUNK = 1024
+    params = density.default_params()
+    first_cols = None
+    for rep in range(2):      # pass 0 warms the arena / pools, pass 1 is timed
+        ms_tot = ms_kmer = ms_kde = 0.0
+        rows = launches = n_eval = pairs = 0
+        status = {}
+        for a in range(0, len(wins), CHUNK):
+            sub = wins[a:a + CHUNK]
+            names = [f'w{i}' for i in range(len(sub))]
+            rs = device.SeqStore(ctx, names, [w[0] for w in sub], keep_host=False)
+            ts = device.SeqStore(ctx, names, [w[1] for w in sub], keep_host=False)
+            win = np.zeros(len(sub), dtype=_capi.DENSITY_WINDOW)
+            for i in range(len(sub)):
+                win[i] = (i, i, 0, WIN_LEN, 0, WIN_LEN, 0, 20)
+            batch = density.DensityBatch(ctx, win, params)
+            ctx.l2_flush()
+            st = batch.run(rs, ts)
+            ms_tot += st.ms_kernels
+            ms_kmer += st.ms_kmer
+            ms_kde += st.ms_kde
+            rows += int(st.rows)
+            launches += int(st.kernel_launches)
+            pairs += int(st.kde_pairs)
+            res, runs, run_off = batch.fetch_runs()
+            n_eval += int(res['n_eval'].sum())
+            for s in res['status'].tolist():
+                status[s] = status.get(s, 0) + 1
+            if rep == 1 and a == 0 and len(sub):
+                first_cols = batch.fetch_window(0, int(res['n_rows'][0])) if int(res['status'][0]) == 0 else {}
+                first_cols['_status'] = int(res['status'][0])
+            batch.close()
+            rs.close()
+            ts.close()
+    # ---- the public call: ASCII windows in host memory -> run lengths of STATE in host memory (columns on demand)
+    e2e_s, n_runs = [], 0
+    for i in range(3):
+        out = None
+        ctl.barrier()
+        t0 = time.perf_counter()
+        out = density.density_windows([(w[0], w[1], False, 20) for w in wins], lazy=True)
+        e2e_s.append(ctl.max(time.perf_counter() - t0))
+        n_runs = sum(len(d['runs']) for d in out)
+    out = None
+    e2e_t = float(np.mean(e2e_s[1:]))
+    ok = None
+    if wins and first_cols is not None:
+        try:
+            from oracle import pyoracle
+            rc, o = pyoracle.density_arrays(wins[0][0].tobytes(), wins[0][1].tobytes())
+            ok = bool(rc == first_cols['_status'] and (rc != 0 or all((first_cols[c].astype(np.int64) == o[c].astype(np.int64)).all()
+                                                                   for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE'))))
+        except Exception as ex:  # noqa: BLE001
+            log('density oracle spot check failed to run:', repr(ex))
+    per_rank = ctl.gather({'rank': rank, 'windows': len(wins), 'ms': ms_tot, 'ms_kmer': ms_kmer, 'ms_kde': ms_kde, 'rows': rows, 'oracle_spot_check': ok,
+                           'seconds_generate': t_gen})
+    ms_max = max(p['ms'] for p in per_rank)
+    total_bases = n_total * WIN_LEN
+    W, K = WIN_LEN, 31
+    kmer_bytes = len(wins) * (-(-2 * W // 4) + 8 * W + 16 * (W - K + 1) + 13 * (W - K + 1))
+    peak, peak_src = measured_peak_gbs()
+    roofs = {
+        'kmer_part': {'bound': 'hbm', 'kernels': 'ref_insert + tig_state + compact', 'algorithmic_bytes': int(kmer_bytes), 'ms': ms_kmer,
+                      'achieved': kmer_bytes / (ms_kmer * 1e-3) / 1e9 if ms_kmer > 0 else None, 'peak': peak, 'unit': 'GB/s',
+                      'frac': kmer_bytes / (ms_kmer * 1e-3) / 1e9 / peak if ms_kmer > 0 else None, 'peak_source': peak_src, 'per': f'rank {rank}'},
+        'kde_part': {'bound': 'float64 CUDA-core arithmetic (exp + FMA), not HBM',
+                     'kernels': 'runs_stats + kde_tree + kde_eval x2 + gap_classify + interp + finalize + state_rle',
+                     'ms': ms_kde, 'rows_N': rows, 'evaluated_points_E': n_eval, 'eval_fraction_E_over_N': n_eval / rows if rows else None,
+                     'logical_pairs': int(pairs), 'logical_pairs_per_sec': pairs / (ms_kde * 1e-3) if ms_kde > 0 else None},
+    }
+    checks = [p['oracle_spot_check'] for p in per_rank]
+    return {
+        'metric': METRIC_B, 'unit': UNIT_B, 'value': total_bases / (ms_max * 1e-3) / 1e9 if ms_max > 0 else None, 'ms_per_step': ms_max,
+        'scaling': 'strong', 'config': {'workload': workload_c5(args, world), 'chunk_windows': CHUNK, 'l2': 'flushed before every chunk'},
+        'e2e': {'value': total_bases / e2e_t / 1e9, 'unit': UNIT_B, 'ms_per_step': e2e_t * 1e3, 'h2d_bytes_per_step': int(2 * total_bases),
+                'd2h_bytes_per_step': int(16 * ctl.sum(n_runs) + 32 * n_total),
+                'api': 'pav_b200.pavlib.density.density_windows(lazy=True): ASCII windows in host memory -> status + run lengths of STATE in host memory; '
+                       'the 38 B/row columns stay in HBM until a window becomes a call (pavgpu_density_batch_fetch_runs / _fetch_window)'},
+        'per_rank': per_rank, 'roofline': roofs, 'rows': int(ctl.sum(rows)), 'gpu_launches': int(ctl.sum(launches)),
+        'status_counts_this_rank': {str(k): v for k, v in status.items()},
+        'oracle_spot_check': all(x is not False for x in checks) and any(x for x in checks),
+    }
+
+
+def leg_c2(args, ctx, tmp):
+    """Round-1 line (N = 1): C2 device-resident walk, C-ABI host-buffer call, public call, per-kernel roofline."""
+    from oracle import pyoracle
+    from pav_b200 import device, synth
+    from pav_b200 import fasta as fasta_mod
+    from pav_b200.pavlib import cigarcall
+    n_contigs, contig_len = args.c2_contigs, 200_000
+    chrom_len = n_contigs * contig_len // 4
+    ref, trs = synth.make_reference(1002, 4, chrom_len)
+    tigs, df = synth.make_contigs(ref, trs, 1002, n_contigs, contig_len)
+    ref_fa, tig_fa, _ = synth.write_cigar_workload(os.path.join(tmp, 'c2'), ref, tigs, df)
+    names_r, names_t = list(ref), list(tigs)
+    ref_store = device.SeqStore(ctx, names_r, [ref[n] for n in names_r])
+    tig_arrays = [tigs[n] for n in names_t]
+    tig_store = device.SeqStore(ctx, names_t, tig_arrays)
+    rid = np.array([names_r.index(c) for c in df['#CHROM']], np.int32)
+    tidx = {n: i for i, n in enumerate(names_t)}
+    qid = np.array([tidx[c] for c in df['QRY_ID']], np.int32)
+    pos, rev = df['POS'].to_numpy(np.int32), df['REV'].to_numpy(np.uint8)
+    ops, op_off, perr = device.parse_cigars(df['CIGAR'].tolist())
+    assert perr.code == 0
+    batch = device.CigarBatch(ctx, rid, qid, pos, rev, ops, op_off)
+    for _ in range(max(args.warmup, 3)):
+        ctx.l2_flush()
+        batch.run(ref_store, tig_store)
+    step_ms = []
+    for _ in range(args.steps):
+        ctx.l2_flush()
+        st = batch.run(ref_store, tig_store)
+        step_ms.append(st.ms_kernels)
+    graph = int(st.graph)
+    os.environ['PAVGPU_NO_GRAPH'] = '1'
+    parts = []
+    for _ in range(7):
+        ctx.l2_flush()
+        s2 = batch.run(ref_store, tig_store)
+        parts.append((s2.ms_count, s2.ms_scan, s2.ms_homology, s2.ms_kernels))
+    os.environ.pop('PAVGPU_NO_GRAPH', None)
+    count_ms, walk_ms, hom_ms, nograph_ms = [float(np.mean([p[i] for p in parts[2:]])) for i in range(4)]
+    n_rows = int(st.n_snv + st.n_indel)
+    my_ms = float(np.mean(step_ms))
+    snv, indel, cerr = batch.fetch()
+    parity = None
+    try:
+        n_chk = min(8, len(df))
+        o_snv, o_indel, _ = pyoracle.walk_rows(df.iloc[:n_chk], ref_fa, tig_fa)
+        g_snv, g_indel = snv[snv['rec'] < n_chk], indel[indel['rec'] < n_chk]
+        parity = bool(len(g_snv) == len(o_snv) and (g_snv['pos_ref'] == o_snv['pos_ref']).all() and (g_snv['qry_pos'] == o_snv['qry_pos']).all()
+                      and len(g_indel) == len(o_indel)
+                      and all((g_indel[c] == o_indel[c]).all() for c in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r',
+                                                                         'hom_tig_l', 'hom_tig_r')))
+    except Exception as ex:  # noqa: BLE001
+        log('C2 oracle spot check failed to run:', ex)
+    cabi_s = []
+    for i in range(1 + 3):
+        t0 = time.perf_counter()
+        ts2 = device.SeqStore(ctx, names_t, tig_arrays, keep_host=False)
+        device.cigar_call(ctx, ref_store, ts2, rid, qid, pos, rev, ops, op_off)
+        ts2.close()
+        if i >= 1:
+            cabi_s.append(time.perf_counter() - t0)
+    h2d_cabi = int(sum(len(a) for a in tig_arrays) + ops.nbytes + op_off.nbytes + rid.nbytes * 3 + rev.nbytes)
+    d2h_cabi = int(snv.nbytes + indel.nbytes)
+    snv = indel = None
+    batch.close()
+    tig_store.close()
+    e2e_s = []
+    for i in range(2 + 3):
+        fasta_mod._CACHE.clear()
+        out = None
+        t0 = time.perf_counter()
+        out = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
+        if i >= 2:
+            e2e_s.append(time.perf_counter() - t0)
+    assert len(out[0]) + len(out[1]) == n_rows
+    out = None
+    ref_store.close()
+    n_ops, n_snv, n_indel, n_chunks = int(st.n_ops), int(st.n_snv), int(st.n_indel), int(st.n_chunks)
+    peak, peak_src = measured_peak_gbs()
+    kernels = kernel_table(count_ms, walk_ms, hom_ms, int(st.homology_tiled), n_ops, n_chunks, n_snv, n_indel)
+    dom = max(kernels, key=lambda k: kernels[k][0])
+    dom_ms, dom_bytes = kernels[dom]
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel on the same input, from this round's committed ncu capture
+        tj = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic.json')))
+        if tj.get('n_ops') == n_ops and dom in tj.get('kernels', {}):
+            traffic = tj['kernels'][dom]
+    except Exception:  # noqa: BLE001
+        pass
+    step_bytes = sum(b for _, b in kernels.values())
+    span = int((df['END'] - df['POS']).sum())
+    survey_bytes = 4 * n_ops + -(-2 * span // 4) + -(-2 * span // 8) + 32 * n_snv + 64 * n_indel
+    return {
+        'config': {'workload': WORKLOAD_C2, 'ops': n_ops, 'rows': n_rows, 'snv_rows': n_snv, 'indel_rows': n_indel},
+        'metric': METRIC, 'unit': UNIT, 'value': n_rows / (my_ms * 1e-3), 'ms_per_step': my_ms, 'ms_per_step_without_graph': nograph_ms, 'graph': graph,
+        'oracle_spot_check': parity,
+        'e2e': {'value': n_rows / float(np.mean(e2e_s)), 'unit': UNIT, 'ms_per_step': float(np.mean(e2e_s)) * 1e3,
+                'h2d_bytes_per_step': int(sum(len(ref[n]) for n in names_r) + h2d_cabi), 'd2h_bytes_per_step': d2h_cabi,
+                'api': 'pav_b200.pavlib.cigarcall.make_insdel_snv_calls (FASTA in, DataFrames out)', 'phase_seconds_last_step': cigarcall.last_phase_seconds},
+        'e2e_cabi': {'value': n_rows / float(np.mean(cabi_s)), 'unit': UNIT, 'ms_per_step': float(np.mean(cabi_s)) * 1e3, 'h2d_bytes_per_step': h2d_cabi,
+                     'd2h_bytes_per_step': d2h_cabi, 'api': 'pavgpu_seqstore_create(contigs) + pavgpu_cigar_call (host buffers)'},
+        'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0, 'peak': peak, 'unit': 'GB/s',
+                     'frac': dom_bytes / (dom_ms * 1e-3) / 1e9 / peak if dom_ms else 0.0, 'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': dom_ms, 'per_kernel_ms': {k: v[0] for k, v in kernels.items()},
+                     'step': {'algorithmic_bytes': int(step_bytes), 'achieved': step_bytes / (my_ms * 1e-3) / 1e9, 'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak},
+                     'survey_8d_model': {'algorithmic_bytes': int(survey_bytes), 'achieved': survey_bytes / (my_ms * 1e-3) / 1e9,
+                                         'frac': survey_bytes / (my_ms * 1e-3) / 1e9 / peak},
+                     'bytes_model': BYTES_MODEL},
+    }
+
+
+def cpu_baseline_ours(args, tmp, info):
+    """N = 1 only: the unmodified reference on a bounded sample, both paths (the code --impl reference runs for K steps)."""
+    from oracle import refenv
+    if not refenv.available():
+        return None, None
+    cores = len(os.sched_getaffinity(0))
+    pick = cpu_sample(args, cores, info['records'])
+    tasks = []
+    for h in ('h1', 'h2'):
+        bed = os.path.join(tmp, f'{h}_align.bed')
+        tasks += [(bed, [i], os.path.join(tmp, 'ref.fa'), os.path.join(tmp, f'{h}_tig.fa'), h) for i in pick[h]]
+    rows, dt = reference_walk_step(tasks, cores)
+    a = {'value': rows / dt, 'unit': UNIT, 'cores': min(cores, len(tasks)), 'kind': 'reference',
+         'sample': f'{len(tasks)} of {sum(info["records"].values())} C3 records (seeded sample, one per worker process; {rows} variant rows, {dt:.1f}s): the unmodified '
+                   'reference\'s make_insdel_snv_calls (oracle/_ref/pavlib/cigarcall.py), FASTA read by .fai offset'}
+    b = None
+    if args.c5_windows > 0:
+        n_w = min(args.cpu_density_windows or cores, args.c5_windows)
+        gb, dt, startup, rcs = reference_density(c5_windows_range(1005, 0, n_w), tmp, cores)
+        b = {'value': gb, 'unit': UNIT_B, 'cores': cores, 'kind': 'reference',
+             'sample': f'first {n_w} of {args.c5_windows} C5 windows, one `python3 scripts/density.py ... -t 1` process per window (pavlib/inv.py:249-266), '
+                       f'{cores} at a time, {dt:.1f}s; start-up ({startup:.2f}s per process, measured separately) is inside the time',
+             'startup_seconds_per_process': startup}
+    return a, b
 
 
 def run_ours(args, rank, world, local):
@@ -363,239 +898,58 @@ def run_ours(args, rank, world, local):
         pbuild.build()
     ctl = Control(rank, world)
     ctl.barrier()
-    from pav_b200 import device, synth
-    from pav_b200 import fasta as fasta_mod
-    from pav_b200.pavlib import cigarcall
-
+    from pav_b200 import device
     os.environ['PAVGPU_DEVICE_INDEX'] = str(local)
     ctx = device.get_context(local if device._capi.lib().pavgpu_device_count() > local else 0)
+    tmp = ctl.bcast(tempfile.mkdtemp(prefix='pavbench_') if rank == 0 else None)
 
-    # ---- workload: shared reference (seed), one haplotype per rank (seed + rank)
-    t0 = time.perf_counter()
-    chrom_len = args.contigs * args.contig_len // 4
-    ref, trs = synth.make_reference(args.seed, 4, chrom_len)
-    tigs, df = synth.make_contigs(ref, trs, args.seed + rank, args.contigs, args.contig_len)
-    tmp = tempfile.mkdtemp(prefix=f'pavbench_r{rank}_')
-    ref_fa, tig_fa, _ = synth.write_cigar_workload(tmp, ref, tigs, df)
-    log(f'[rank {rank}] workload generated + written in {time.perf_counter() - t0:.1f}s ({len(df)} records)')
-
-    # ---- reference planes: rank 0 packs, everyone else receives them over NCCL
-    names_r, names_t = list(ref), list(tigs)
-    bcast_ms = 0.0
-    if rank == 0:
-        ref_store = device.SeqStore(ctx, names_r, [ref[n] for n in names_r])
-    else:
-        ref_store = device.SeqStore.from_packed(ctx, names_r, [len(ref[n]) for n in names_r], None, None)
-    if world > 1:
-        uid = device.nccl_unique_id() if rank == 0 else b''
-        uid = ctl.bcast_bytes(uid, 128)
-        ctl.barrier()
-        with stdout_to_stderr():   # NCCL prints its version banner on stdout; the driver wants one JSON line there
-            bcast_ms = ref_store.broadcast(uid, rank, world)
-        bcast_ms = ctl.max(bcast_ms)
-    tig_arrays = [tigs[n] for n in names_t]
-    tig_store = device.SeqStore(ctx, names_t, tig_arrays)
-
-    # ---- records -> HBM
-    rid = np.array([names_r.index(c) for c in df['#CHROM']], np.int32)
-    tidx = {n: i for i, n in enumerate(names_t)}
-    qid = np.array([tidx[c] for c in df['QRY_ID']], np.int32)
-    pos = df['POS'].to_numpy(np.int32)
-    rev = df['REV'].to_numpy(np.uint8)
-    ops, op_off, perr = device.parse_cigars(df['CIGAR'].tolist())
-    assert perr.code == 0
-    batch = device.CigarBatch(ctx, rid, qid, pos, rev, ops, op_off)
-
-    # ---- device-resident steps
-    clocks = ClockSampler(ctx.device)  # spans warm-up, the timed steps and ~1 s of identical untimed steps (the timed region is milliseconds)
-    t_clk = time.perf_counter()
-    for _ in range(args.warmup):
-        ctx.l2_flush()
-        batch.run(ref_store, tig_store)
-    ctl.barrier()
-    step_ms, parts = [], []
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.l2_flush()
-        st = batch.run(ref_store, tig_store)
-        step_ms.append(st.ms_kernels)
-        parts.append((st.ms_scan, st.ms_emit, st.ms_homology, st.ms_count))
-    wall_ms = (time.perf_counter() - wall0) * 1e3 / args.steps
-    while time.perf_counter() - t_clk < 1.2:   # keep the same kernels running so nvidia-smi sees the clocks under this load
-        batch.run(ref_store, tig_store)
-    clk = clocks.stop()
-    clk['window'] = 'warm-up + timed steps + identical untimed steps, 1.2 s total, nvidia-smi -lms 50'
-    ctl.barrier()
-    n_rows = int(st.n_snv + st.n_indel)
-    my_ms = float(np.mean(step_ms))
-    ms_per_step = ctl.max(my_ms)
-    total_rows = ctl.sum(n_rows)
-    value = total_rows / (ms_per_step * 1e-3)
-    scan_ms, emit_ms, hom_ms, count_ms = [float(np.mean([p[i] for p in parts])) for i in range(4)]
-
-    # ---- parity spot check of the resident run against the oracle (first records; bounded)
-    snv, indel, cerr = batch.fetch()
-    assert cerr.code == 0
-    parity = None
-    if rank == 0:
+    a = leg_c3(args, ctl, ctx, tmp, rank, world)
+    b = None
+    if args.c5_windows > 0:
         try:
-            from oracle import pyoracle
-            n_chk = min(8, len(df))
-            o_snv, o_indel, _ = pyoracle.walk_rows(df.iloc[:n_chk], ref_fa, tig_fa)
-            g_snv, g_indel = snv[snv['rec'] < n_chk], indel[indel['rec'] < n_chk]
-            parity = bool(len(g_snv) == len(o_snv) and (g_snv['pos_ref'] == o_snv['pos_ref']).all()
-                          and (g_snv['qry_pos'] == o_snv['qry_pos']).all() and len(g_indel) == len(o_indel)
-                          and all((g_indel[c] == o_indel[c]).all() for c in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift',
-                                                                             'hom_ref_l', 'hom_ref_r', 'hom_tig_l', 'hom_tig_r')))
+            b = leg_c5(args, ctl, ctx, rank, world)
         except Exception as ex:  # noqa: BLE001
-            log('oracle spot check failed to run:', ex)
-
-    # ---- e2e through the C ABI with host buffers (contig ASCII + ops in host memory -> rows in host memory)
-    cabi_s, h2d, d2h = [], 0, 0
-    for i in range((1 + args.e2e_steps) if args.e2e_steps > 0 else 0):
-        t0 = time.perf_counter()
-        ts2 = device.SeqStore(ctx, names_t, tig_arrays, keep_host=False)
-        s2, i2, e2, st2 = device.cigar_call(ctx, ref_store, ts2, rid, qid, pos, rev, ops, op_off)
-        ts2.close()
-        if i >= 1:
-            cabi_s.append(time.perf_counter() - t0)
-    h2d_cabi = int(sum(len(a) for a in tig_arrays) + ops.nbytes + op_off.nbytes + rid.nbytes * 3 + rev.nbytes)
-    d2h_cabi = int(snv.nbytes + indel.nbytes)
-    cabi_val = ctl.sum(n_rows) / ctl.max(float(np.mean(cabi_s))) if cabi_s else None
-
-    # ---- e2e through the public API (what rules/call.snakefile:810 calls)
-    batch.close()
-    tig_store.close()
-    e2e_s = []
-    df_snv = df_insdel = None
-    E2E_WARMUP = 2   # call 1 creates allocator pools, call 2 the pinned staging buffers (pinned staging starts with the second call)
-    for i in range((E2E_WARMUP + args.e2e_steps) if args.e2e_steps > 0 else 0):
-        ctl.barrier()
-        fasta_mod._CACHE.clear()   # every step re-opens and re-reads the FASTA files, like a fresh Snakemake job would
-        df_snv = df_insdel = None  # releasing the previous step's 2 M-row result is not part of this call
-        t0 = time.perf_counter()
-        df_snv, df_insdel = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
-        dt = time.perf_counter() - t0
-        if i >= E2E_WARMUP:
-            e2e_s.append(dt)
-        log(f'[rank {rank}] e2e make_insdel_snv_calls: {dt:.2f}s ({len(df_snv) + len(df_insdel)} rows) phases={cigarcall.last_phase_seconds}')
-    e2e_val = None
-    if e2e_s:
-        e2e_rows = len(df_snv) + len(df_insdel)
-        assert e2e_rows == n_rows
-        e2e_val = ctl.sum(e2e_rows) / ctl.max(float(np.mean(e2e_s)))
-    h2d_api = int(sum(len(ref[n]) for n in names_r) + h2d_cabi)
-
-    # ---- the same public call with a packed-reference sidecar next to the reference FASTA (pav_b200/sidecar.py; built once per
-    # reference, outside the timed region): reference bases are views of the mapped file, the upload is the packed planes
-    sc_s = []
-    if args.e2e_steps > 0:
-        from pav_b200 import sidecar
-        sc_path = sidecar.build(ref_fa)
-        for i in range(1 + min(args.e2e_steps, 3)):
-            ctl.barrier()
-            fasta_mod._CACHE.clear()
-            sidecar._OPEN.clear()
-            df_snv = df_insdel = None
-            t0 = time.perf_counter()
-            df_snv, df_insdel = cigarcall.make_insdel_snv_calls(df, ref_fa, tig_fa, 'h1', version_id=False)
-            dt = time.perf_counter() - t0
-            assert cigarcall.last_phase_seconds['sidecar'] and len(df_snv) + len(df_insdel) == n_rows
-            if i >= 1:
-                sc_s.append(dt)
-        os.unlink(sc_path)
-        df_snv = df_insdel = None
-    e2e_sidecar = {'value': ctl.sum(n_rows) / ctl.max(float(np.mean(sc_s))), 'unit': UNIT, 'ms_per_step': float(np.mean(sc_s)) * 1e3,
-                   'h2d_bytes_per_step': int(h2d_cabi + 0.375 * sum(len(ref[n]) for n in names_r)), 'd2h_bytes_per_step': d2h_cabi,
-                   'api': 'make_insdel_snv_calls with <ref>.pavsc present (packed planes + mapped bases; sidecar built once, untimed)'} if sc_s else None
-
-    # ---- secondary metric (Path B)
-    secondary = None
-    if args.density_windows > 0:
-        try:
-            secondary = density_secondary(ctx, args, rank)
             if world > 1:
-                secondary['value'] = ctl.sum(args.density_windows * 50_000) / ctl.max(secondary['ms_per_step'] * 1e-3) / 1e9
+                raise            # ranks must stay in step
+            log('C5 leg failed:', repr(ex))
+            b = {'error': repr(ex)}
+    c2 = None
+    if world == 1 and args.c2:
+        try:
+            c2 = leg_c2(args, ctx, tmp)
         except Exception as ex:  # noqa: BLE001
-            log('secondary (density) measurement failed:', repr(ex))
-            secondary = {'error': repr(ex)}
-
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only)
-    cpu = None
+            log('C2 leg failed:', repr(ex))
+            c2 = {'error': repr(ex)}
+    cpu_a = cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = len(os.sched_getaffinity(0))
-        n_sample = cpu_sample_contigs(args, cores, 2)
-        rps, rows, dt, used = cpu_port_rows_per_sec(df, ref_fa, tig_fa, n_sample, cores)
-        rps_fast, _, _, _ = cpu_port_rows_per_sec(df, ref_fa, tig_fa, n_sample, cores, fast=True)
-        cpu = {'value': rps, 'unit': UNIT, 'cores': used, 'kind': 'port',
-               'sample': f'first {n_sample} of {args.contigs} contigs ({rows} rows, {dt:.1f}s): FASTA read + C walk + reference-style '
-                         'DataFrame assembly (pd.Series per variant + concat, as pavlib/cigarcall.py does), one shard per process',
-               'fast_checker_value': rps_fast,
-               'note': 'value = oracle port with the reference\'s container idiom (within 7 % of the unmodified Python reference, DESIGN.md); '
-                       'fast_checker_value = same port with tuple-based assembly (what the parity tests use)'}
-
-    # ---- roofline of the dominant kernel
-    n_ops, n_snv, n_indel, n_chunks = int(st.n_ops), int(st.n_snv), int(st.n_indel), int(st.n_chunks)
-    peak, peak_src = measured_peak_gbs()
-    hom_name = ['homology_kernel', 'homology_tiled_kernel', 'homology_nbr_kernel', 'homology_bulk_kernel', 'homology_queue_kernel'][int(st.homology_tiled)]   # PAVGPU_HOMOLOGY=gather|tiled|nbr|bulk|queue
-    if int(st.walk_passes) == 1:   # single-pass walk: count + record scan, then K1+K2+K3 fused (cigar_walk_kernel)
-        kernels = {
-            'cigar_count+rec_scan': (count_ms, 4 * n_ops + 4 * n_chunks + 4 * 16 * len(df)),
-            'cigar_walk_kernel': (scan_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 64 * n_indel),
-            hom_name: (hom_ms, (64 + 64) * n_indel),
-        }
-    else:
-        kernels = {
-            'cigar_reduce+chunk_scan': (scan_ms, 4 * n_ops + 24 * n_chunks + 2 * 48 * n_chunks),
-            'cigar_emit_kernel': (emit_ms, 4 * n_ops + 24 * n_chunks + 16 * n_snv + 64 * n_indel),
-            hom_name: (hom_ms, (64 + 64) * n_indel),
-        }
-    dom = max(kernels, key=lambda k: kernels[k][0])
-    dom_ms, dom_bytes = kernels[dom]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    step_bytes = sum(b for _, b in kernels.values())
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel on the same (default C2) input, from the committed ncu capture
-        tj = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic.json')))
-        if tj.get('n_ops') == n_ops and dom in tj.get('kernels', {}):
-            traffic = tj['kernels'][dom]
-    except Exception:  # noqa: BLE001
-        pass
-    # SURVEY 8(d) byte model (assumes the north-star design that streams both aligned spans through the walk; this design does
-    # not touch sequence in the walk, so its own model above is smaller): reported beside it for comparison
-    span = int((df['END'] - df['POS']).sum())
-    survey_bytes = 4 * n_ops + -(-2 * span // 4) + -(-2 * span // 8) + 32 * n_snv + 64 * n_indel
-    roofline = {
-        'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-        'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': dom_ms,
-        'per_kernel_ms': {k: v[0] for k, v in kernels.items()},
-        'step': {'algorithmic_bytes': int(step_bytes), 'achieved': step_bytes / (my_ms * 1e-3) / 1e9, 'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak},
-        'survey_8d_model': {'algorithmic_bytes': int(survey_bytes), 'achieved': survey_bytes / (my_ms * 1e-3) / 1e9,
-                            'frac': survey_bytes / (my_ms * 1e-3) / 1e9 / peak, 'per': 'whole step (walk + homology)'},
-        'bytes_model': '4 B/op read (once in the single-pass walk) + 16 B/SNV row + 64 B indel stub (write+read) + 64 B/indel row + tile '
-                       'descriptors; sequence gathers of the homology scans not counted (DESIGN.md)',
-    }
-
+        cpu_a, cpu_b = cpu_baseline_ours(args, tmp, a['info'])
     if rank == 0:
+        info = a.pop('info')
         line = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32',
-            'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'contigs_per_gpu': args.contigs, 'contig_len': args.contig_len, 'reference_bp': 4 * chrom_len,
-                       'records_per_gpu': len(df), 'ops_per_gpu': n_ops, 'rows_per_gpu': n_rows, 'snv_rows': n_snv, 'indel_rows': n_indel,
-                       'l2': 'flushed (256 MB memset) between iterations', 'parallelism': f'records sharded over {world} GPU(s)'},
-            'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d_api, 'd2h_bytes_per_step': d2h_cabi, 'steps': args.e2e_steps, 'warmup': 2,
-                    'api': 'pav_b200.pavlib.cigarcall.make_insdel_snv_calls (FASTA in, DataFrames out)', 'ms_per_step': float(np.mean(e2e_s)) * 1e3 if e2e_s else None,
-                    'phase_seconds_last_step': cigarcall.last_phase_seconds},
-            'e2e_cabi': {'value': cabi_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d_cabi, 'd2h_bytes_per_step': d2h_cabi,
-                         'api': 'pavgpu_seqstore_create(contigs) + pavgpu_cigar_call (host buffers)', 'ms_per_step': float(np.mean(cabi_s)) * 1e3 if cabi_s else None},
-            'e2e_sidecar': e2e_sidecar,
-            'gpu_launches': int(st.kernel_launches) * args.steps, 'wall_ms_per_step_incl_flush': wall_ms,
-            'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clk, 'ref_broadcast_ms': bcast_ms, 'oracle_spot_check': parity,
-            'secondary': secondary,
+            'metric': METRIC, 'value': a['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': a['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
+            'config': {'workload': workload_c3(args, world), 'reference_bp': info['reference_bp'], 'records': info['records'], 'rows': a['rows'],
+                       'l2': 'flushed (256 MB memset) between iterations', 'parallelism': f'alignment records sharded over {world} GPU(s), LPT',
+                       'alloc_tuning': 'PAVGPU_TUNE_ALLOC=1 for the end-to-end leg (opt-in glibc / pymalloc settings of the frame builder)',
+                       'seconds_generate': info['seconds_generate'], 'seconds_write': info['seconds_write']},
+            'e2e': a['e2e'], 'gpu_launches': a['gpu_launches'], 'wall_ms_per_step_incl_flush': a['wall_ms_per_step_incl_flush'],
+            'roofline': a['roofline'], 'cpu_baseline': cpu_a, 'clocks': a['clocks'], 'per_rank': a['per_rank'],
+            'ref_broadcast_ms': a['ref_broadcast_ms'], 'ref_broadcast_bytes': a['ref_broadcast_bytes'], 'ref_pack_seconds_rank0': a['ref_pack_seconds_rank0'],
+            'planes_verified_on_every_rank': a['planes_verified_on_every_rank'], 'oracle_spot_check': a['oracle_spot_check'],
+            'secondary': b, 'c2': c2,
         }
+        if b is not None and 'error' not in b:
+            b['cpu_baseline'] = cpu_b
+        if args.metric == 'density' and b is not None and 'error' not in b:
+            top = dict(b)
+            rf = b['roofline']['kmer_part']
+            top.update({'n_gpus': world, 'steps': 1, 'warmup': 1, 'higher_is_better': True, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                        'roofline': {'bound': 'hbm', 'kernel': rf['kernels'], 'achieved': rf['achieved'], 'peak': rf['peak'], 'unit': 'GB/s', 'frac': rf['frac'],
+                                     'traffic': None, 'kde_part': b['roofline']['kde_part']},
+                        'clocks': a['clocks'], 'secondary': {k: v for k, v in line.items() if k not in ('secondary', 'c2')}})
+            line = top
         print(json.dumps(line), flush=True)
-    ref_store.close()
+    ctl.barrier()
     ctl.close()
 
 

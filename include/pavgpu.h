@@ -88,6 +88,9 @@ int pavgpu_seqstore_planes(const pavgpu_seqstore *store, void **d_pack2, size_t 
                            void **d_nmask, size_t *nmask_bytes);
 /* Copy the planes back to the host (tests, packed sidecar files). Sizes from pavgpu_seqstore_planes(). */
 int pavgpu_seqstore_export(const pavgpu_seqstore *store, uint64_t *pack2_host, uint32_t *nmask_host);
+/* Checksums of the two planes computed on the device (sums_out[0] 2-bit plane, [1] mask plane; order-independent 64-bit sums of
+ * position-salted words): every rank of a multi-GPU run compares what pavgpu_seqstore_broadcast left in its HBM with rank 0's. */
+int pavgpu_seqstore_checksum(const pavgpu_seqstore *store, uint64_t sums_out[2]);
 /* Base offset (in bases) of sequence i inside the planes. */
 int64_t pavgpu_seqstore_offset(const pavgpu_seqstore *store, int32_t seq_id);
 
@@ -221,6 +224,24 @@ int pavgpu_density_batch_fetch(pavgpu_density_batch *batch, pavgpu_density_resul
                                uint64_t **kmer_out, int32_t **index_out, int8_t **state_mer_out,
                                int8_t **state_out, double **kern_fwd_out, double **kern_fwdrev_out,
                                double **kern_rev_out, int64_t *n_rows_total);
+
+/* One run of equal STATE in row order: the tuple pavlib.density.rl_encoder yields (pavlib/density.py:330-361). */
+typedef struct {
+    int32_t state;        /* -1 for a window returned un-smoothed (scripts/density.py:193-194) */
+    int32_t count;        /* rows in the run */
+    int32_t first_index;  /* INDEX of its first row */
+    int32_t last_index;   /* INDEX of its last row */
+} pavgpu_state_run;
+
+/* Run lengths of STATE for every window of the batch: what pavlib.inv.scan_for_inv decides from after every expansion
+ * (pavlib/inv.py:294-342) -- 16 bytes per run instead of 38 bytes per row. res[n_win], run_off[n_win + 1] caller-owned;
+ * *runs_out library-allocated (pavgpu_free_host), runs of window w at [run_off[w], run_off[w + 1]). */
+int pavgpu_density_batch_fetch_runs(pavgpu_density_batch *batch, pavgpu_density_result *res, pavgpu_state_run **runs_out,
+                                    int64_t *run_off, int64_t *n_runs_total);
+/* All columns of ONE window into caller-owned arrays of res[win].n_rows entries each (NULL = skip the column): the window that
+ * becomes a call and whose table the rule writes out (pavlib/inv.py:440-454, rules/call_inv.snakefile:279-282). */
+int pavgpu_density_batch_fetch_window(pavgpu_density_batch *batch, int32_t win, uint64_t *kmer, int32_t *index,
+                                      int8_t *state_mer, int8_t *state, double *kern_fwd, double *kern_fwdrev, double *kern_rev);
 
 /* ---------------------------------------------------------------- multi-GPU ----------------- */
 /* Reference broadcast over NVLink: rank 0 owns a filled store, the other ranks an empty

@@ -3,15 +3,53 @@ reference from /root/reference when generating golden fixtures (tests/golden/mak
 
 Implements the subset the reference's hot path touches:
 pysam.FastaFile(fn) as a context manager with fetch(name, start=None, end=None)
-(pavlib/cigarcall.py:59-66, pavlib/seq.py:339-351). Plain or gzip FASTA; whole file in memory.
+(pavlib/cigarcall.py:59-66, pavlib/seq.py:339-351). A plain FASTA with a .fai next to it is read by offset like htslib's
+faidx does (one seek + one read per fetch: a worker of the CPU baseline fetching one chromosome of a 3.1 Gbp reference must not
+parse the whole file); anything else (gzip, no index) is loaded whole.
 """
 import gzip
+import os
 
 _CACHE = {}
 
 
+class _Indexed:
+    """name -> (length, offset, line_bases, line_width) from the .fai; fetch = seek + read + newline removal."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.idx = {}
+        with open(fn + '.fai') as fh:
+            for line in fh:
+                t = line.rstrip('\n').split('\t')
+                if len(t) >= 5:
+                    self.idx[t[0]] = (int(t[1]), int(t[2]), int(t[3]), int(t[4]))
+
+    def keys(self):
+        return self.idx.keys()
+
+    def length(self, name):
+        return self.idx[name][0]
+
+    def fetch(self, name, start, end):
+        length, off, lb, lw = self.idx[name]
+        start = 0 if start is None else max(0, start)
+        end = length if end is None else min(length, end)
+        if end <= start:
+            return ''
+        b0 = off + (start // lb) * lw + start % lb
+        b1 = off + ((end - 1) // lb) * lw + (end - 1) % lb + 1
+        with open(self.fn, 'rb') as fh:
+            fh.seek(b0)
+            raw = fh.read(b1 - b0)
+        return raw.replace(b'\n', b'').replace(b'\r', b'').decode('ascii')
+
+
 def _load(fn):
     if fn in _CACHE:
+        return _CACHE[fn]
+    if not str(fn).endswith('.gz') and os.path.exists(str(fn) + '.fai'):
+        _CACHE[fn] = _Indexed(str(fn))
         return _CACHE[fn]
     opener = gzip.open if str(fn).endswith('.gz') else open
     seqs, name, chunks = {}, None, []
@@ -35,7 +73,10 @@ class FastaFile:
         self.filename = filename
         self._seqs = _load(filename)
         self.references = list(self._seqs.keys())
-        self.lengths = [len(v) for v in self._seqs.values()]
+        if isinstance(self._seqs, _Indexed):
+            self.lengths = [self._seqs.length(n) for n in self.references]
+        else:
+            self.lengths = [len(v) for v in self._seqs.values()]
 
     def __enter__(self):
         return self
@@ -47,6 +88,8 @@ class FastaFile:
         pass
 
     def fetch(self, reference=None, start=None, end=None):
+        if isinstance(self._seqs, _Indexed):
+            return self._seqs.fetch(reference, start, end)
         seq = self._seqs[reference]
         if start is None and end is None:
             return seq
@@ -57,6 +100,8 @@ class FastaFile:
         return seq[start:end]
 
     def get_reference_length(self, reference):
+        if isinstance(self._seqs, _Indexed):
+            return self._seqs.length(reference)
         return len(self._seqs[reference])
 
 

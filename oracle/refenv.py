@@ -1,13 +1,14 @@
-"""Test infrastructure: put the UNMODIFIED reference (/root/reference, PAV 2.4.6.0) on sys.path
-together with the stub third-party modules in oracle/ref_stubs/. Only usable in the build
-container (the reference tree does not exist on the GPU box). Used by tests/golden/make_golden.py
-to generate golden fixtures and by container-only cross-checks."""
+"""Test / baseline infrastructure: put the UNMODIFIED reference (PAV 2.4.6.0) on sys.path together with the stub third-party
+modules in oracle/ref_stubs/. The reference is taken from /root/reference (build container) or, where that does not exist (GPU
+box), from the byte-for-byte staged copy oracle/_ref/ (oracle/stage_ref.py; git-ignored, travels with gpurun). Used by
+tests/golden/make_golden*.py to generate golden fixtures, by container-only cross-checks, and by bench.py's --impl reference and
+cpu_baseline legs. Nothing under pav_b200/ imports this."""
 import os
 import sys
 
-REF_ROOT = '/root/reference'
 _HERE = os.path.dirname(os.path.abspath(__file__))
 STUBS = os.path.join(_HERE, 'ref_stubs')
+REF_ROOT = '/root/reference' if os.path.isdir('/root/reference/pavlib') else os.path.join(_HERE, '_ref')
 
 
 def available():

@@ -22,6 +22,7 @@ assert SNV_ROW.itemsize == 16 and INDEL_ROW.itemsize == 64
 
 DENSITY_WINDOW = np.dtype([('ref_seq_id', '<i4'), ('tig_seq_id', '<i4'), ('ref_pos', '<i4'), ('ref_end', '<i4'),
                            ('tig_pos', '<i4'), ('tig_end', '<i4'), ('rev', '<i4'), ('srs', '<i4')])
+STATE_RUN = np.dtype([('state', '<i4'), ('count', '<i4'), ('first_index', '<i4'), ('last_index', '<i4')])
 DENSITY_RESULT = np.dtype([('status', '<i4'), ('smoothed', '<i4'), ('row_off', '<i8'), ('n_rows', '<i8'), ('n_eval', '<i8')])
 
 
@@ -63,10 +64,11 @@ EXPORTS = [
     'pavgpu_last_error', 'pavgpu_device_count', 'pavgpu_ctx_create', 'pavgpu_ctx_destroy', 'pavgpu_ctx_device',
     'pavgpu_free_host', 'pavgpu_host_alloc', 'pavgpu_l2_flush', 'pavgpu_seqstore_create', 'pavgpu_seqstore_create_packed', 'pavgpu_seqstore_create_empty',
     'pavgpu_seqstore_free', 'pavgpu_seqstore_n_seq', 'pavgpu_seqstore_total_bases', 'pavgpu_seqstore_planes',
-    'pavgpu_seqstore_export', 'pavgpu_seqstore_offset', 'pavgpu_cigar_parse', 'pavgpu_cigar_batch_create',
+    'pavgpu_seqstore_export', 'pavgpu_seqstore_checksum', 'pavgpu_seqstore_offset', 'pavgpu_cigar_parse', 'pavgpu_cigar_batch_create',
     'pavgpu_cigar_batch_free', 'pavgpu_cigar_batch_run', 'pavgpu_cigar_batch_fetch', 'pavgpu_cigar_call',
     'pavgpu_homology', 'pavgpu_density_default_params', 'pavgpu_density_batch_create', 'pavgpu_density_batch_free',
-    'pavgpu_density_batch_run', 'pavgpu_density_batch_fetch', 'pavgpu_nccl_unique_id', 'pavgpu_seqstore_broadcast',
+    'pavgpu_density_batch_run', 'pavgpu_density_batch_fetch', 'pavgpu_density_batch_fetch_runs', 'pavgpu_density_batch_fetch_window',
+    'pavgpu_nccl_unique_id', 'pavgpu_seqstore_broadcast',
 ]
 
 
@@ -106,6 +108,7 @@ def lib():
     L.pavgpu_seqstore_offset.restype = c_i64
     L.pavgpu_seqstore_planes.argtypes = [c_vp, P(c_vp), P(ctypes.c_size_t), P(c_vp), P(ctypes.c_size_t)]
     L.pavgpu_seqstore_export.argtypes = [c_vp, c_vp, c_vp]
+    L.pavgpu_seqstore_checksum.argtypes = [c_vp, c_vp]
     L.pavgpu_cigar_parse.argtypes = [ctypes.c_char_p, P(c_i64), c_i32, P(c_vp), P(c_i64), P(ParseErr)]
     L.pavgpu_cigar_batch_create.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp)]
     L.pavgpu_cigar_batch_free.argtypes = [c_vp]
@@ -123,6 +126,8 @@ def lib():
         L.pavgpu_density_batch_free.restype = None
         L.pavgpu_density_batch_run.argtypes = [c_vp, c_vp, c_vp, P(DensityStats)]
         L.pavgpu_density_batch_fetch.argtypes = [c_vp, c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_i64)]
+        L.pavgpu_density_batch_fetch_runs.argtypes = [c_vp, c_vp, P(c_vp), c_vp, P(c_i64)]
+        L.pavgpu_density_batch_fetch_window.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     if hasattr(L, 'pavgpu_nccl_unique_id'):
         L.pavgpu_nccl_unique_id.argtypes = [c_vp]
         L.pavgpu_seqstore_broadcast.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, P(c_f32)]

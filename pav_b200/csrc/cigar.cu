@@ -689,7 +689,7 @@ __device__ __forceinline__ void score_body(const OSeq &R, const OSeq &Q, int32_t
 }
 
 #ifndef HOM_MIN_BLOCKS
-#define HOM_MIN_BLOCKS 3
+#define HOM_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(HOM_THREADS, HOM_MIN_BLOCKS)
 homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
@@ -699,8 +699,8 @@ homology_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes 
     const int4 *sp4 = reinterpret_cast<const int4 *>(stubs + i);
     const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
     const int32_t rec = a.x, op_idx = a.y, svtype = a.z, n = a.w, pr = b.x, pq = b.y, eqb = b.z;
-    const OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0};
-    const OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w};
+    const OSeq R{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, nullptr, nullptr, 0, 0, nullptr};
+    const OSeq Q{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, nullptr, nullptr, 0, 0, nullptr};
     IndelScore o;
     score_body<false>(R, Q, svtype, n, pr, pq, eqb, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
@@ -948,8 +948,9 @@ homology_bulk_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPl
 // that matched its whole first window is not continued by its owner: it is appended to a shared-memory queue (owner, scan), and
 // after a CTA barrier the queue is worked off one item per thread, so the rest loops run with full warps of unrelated long scans.
 // Two rounds, because the left shift must be known before the four breakpoint homologies can start: round A = rests of the
-// left-shift scans (few: their threads carry on with the owner's first trips while all other owners do their own), round B =
-// rests of the homologies. An item's thread re-reads its owner's stub (L1/L2-resident).
+// left-shift scans, round B = rests of the homologies. An item's thread re-reads its owner's stub (L1/L2-resident).
+// (Measured and dropped, r02: round A overlapped with the other owners' first trips -- 3 barriers instead of 4, but 0.087 ms against
+// 0.0755 ms: the longer live ranges spill at 64 registers.)
 constexpr int HOMQ_THREADS = 256;
 
 struct StubView {
@@ -963,8 +964,8 @@ __device__ __forceinline__ StubView load_stub(const IndelStub *__restrict__ stub
     const int4 a = __ldg(sp4), b = __ldg(sp4 + 1), c = __ldg(sp4 + 2), d = __ldg(sp4 + 3);
     StubView v;
     v.rec = a.x; v.op_idx = a.y; v.svtype = a.z; v.n = a.w; v.pr = b.x; v.pq = b.y; v.eqb = b.z;
-    v.R = OSeq{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, nullptr, nullptr, 0, 0};
-    v.Q = OSeq{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, nullptr, nullptr, 0, 0};
+    v.R = OSeq{ref.pack2, ref.nmask, (int64_t)(((unsigned long long)(unsigned)c.y << 32) | (unsigned)c.x), (int64_t)d.x, 0, nullptr, nullptr, 0, 0, nullptr};
+    v.Q = OSeq{qry.pack2, qry.nmask, (int64_t)(((unsigned long long)(unsigned)c.w << 32) | (unsigned)c.z), (int64_t)d.y, b.w, nullptr, nullptr, 0, 0, nullptr};
     return v;
 }
 
@@ -981,17 +982,18 @@ __device__ __forceinline__ void queue_push(bool flag, uint16_t item, uint16_t *q
 }
 
 #ifndef HOMQ_MIN_BLOCKS
-#define HOMQ_MIN_BLOCKS 3
+#define HOMQ_MIN_BLOCKS 4
+#endif
+#ifndef HOMQ_COOP
+#define HOMQ_COOP 8      // lanes that share one pooled scan rest in round B (round A: a whole warp per item)
 #endif
 
 __global__ void __launch_bounds__(HOMQ_THREADS, HOMQ_MIN_BLOCKS)
 homology_queue_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, pavgpu_indel_row *__restrict__ rows)
 {
     __shared__ int s_cnt[2];
-    __shared__ uint16_t s_qa[HOMQ_THREADS];        // round A items: owner thread
-    __shared__ uint16_t s_qb[HOMQ_THREADS * 4];    // round B items: owner thread << 3 | scan (1..4)
-    __shared__ int32_t s_res[HOMQ_THREADS * 4];    // rest of homology k of owner t at [t * 4 + k]
-    __shared__ int32_t s_hom[HOMQ_THREADS * 4];    // first trips of owner t computed by its round-A item thread
+    __shared__ uint16_t s_q[HOMQ_THREADS * 4];     // items: owner thread << 3 | scan
+    __shared__ int32_t s_res[HOMQ_THREADS * 5];    // result of scan sc of owner t at [t * 5 + sc]
     __shared__ int32_t s_ls[HOMQ_THREADS];
     const int tid = threadIdx.x;
     const int64_t i0 = (int64_t)blockIdx.x * HOMQ_THREADS, i = i0 + tid;
@@ -999,53 +1001,51 @@ homology_queue_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
     if (tid < 2) s_cnt[tid] = 0;
     const StubView v = load_stub(stubs, live ? i : n_indel - 1, ref, qry);
     const bool ins = v.svtype == 0;
-    // ---- left shift: first trip by the owner; a scan that goes on (and can still grow the shift) becomes a round-A item
+    // ---- round A: left shift
     int h0 = indel_phase0<false>(v.R, v.Q, ins, v.n, v.pr, v.pq);
     if (v.eqb <= 0 || !live) h0 = 0;
     const bool need0 = h0 == 32 && v.eqb > 32;
     __syncthreads();                               // s_cnt is zero
-    queue_push(need0, (uint16_t)tid, s_qa, &s_cnt[0]);
+    queue_push(need0, (uint16_t)(tid << 3), s_q, &s_cnt[0]);
     __syncthreads();
-    const int n_a = s_cnt[0];
-    // ---- round A and the first trips of the four breakpoint homologies, side by side: thread t < n_a finishes the left-shift scan
-    // of item t's owner and goes straight on to that owner's first trips; every owner whose shift is already known does its own
-    if (tid < n_a) {
-        const int owner = s_qa[tid];
-        const StubView w = load_stub(stubs, i0 + owner, ref, qry);
-        const bool w_ins = w.svtype == 0;
-        const int ls_a = min(w.eqb, indel_rest<false>(w.R, w.Q, w_ins, w.n, w.pr, w.pq, 0, 0));
-        int hom_a[4];
-        indel_phase1<false>(w.R, w.Q, w_ins, w.n, w.pr, w.pq, ls_a, hom_a);
-        s_ls[owner] = ls_a;
-#pragma unroll
-        for (int k = 0; k < 4; k++) s_hom[owner * 4 + k] = hom_a[k];
+    {   // a whole warp per item: 32 windows = 1,024 bases per round
+        const int n_a = s_cnt[0], lane = tid & 31;
+        for (int t0 = 0; t0 < n_a; t0 += HOMQ_THREADS / 32) {
+            const int t = t0 + (tid >> 5);
+            const bool act = t < n_a;
+            const int owner = s_q[act ? t : 0] >> 3;
+            const StubView w = load_stub(stubs, i0 + owner, ref, qry);
+            const int h = indel_rest_coop<32>(w.R, w.Q, w.svtype == 0, w.n, w.pr, w.pq, 0, 0, act, lane);
+            if (act && lane == 0) s_res[owner * 5] = h;
+        }
     }
-    int ls = min(v.eqb, h0);
-    int hom[4] = {0, 0, 0, 0};
-    if (!need0) {
-        indel_phase1<false>(v.R, v.Q, ins, v.n, v.pr, v.pq, ls, hom);
-        s_ls[tid] = ls;
-    }
-    __syncthreads();                               // s_ls / s_hom of round-A owners are written
-    if (need0) {
-        ls = s_ls[tid];
-#pragma unroll
-        for (int k = 0; k < 4; k++) hom[k] = s_hom[tid * 4 + k];
-    }
-    // ---- round B: rests of the homologies, pooled over the CTA
-#pragma unroll
-    for (int k = 0; k < 4; k++) queue_push(live && hom[k] == 32, (uint16_t)((tid << 3) | (k + 1)), s_qb, &s_cnt[1]);
     __syncthreads();
-    for (int t = tid; t < s_cnt[1]; t += HOMQ_THREADS) {
-        const int owner = s_qb[t] >> 3, sc = s_qb[t] & 7;
-        const StubView w = load_stub(stubs, i0 + owner, ref, qry);
-        s_res[owner * 4 + sc - 1] = indel_rest<false>(w.R, w.Q, w.svtype == 0, w.n, w.pr, w.pq, s_ls[owner], sc);
+    if (need0) h0 = s_res[tid * 5];
+    const int ls = min(v.eqb, h0);
+    s_ls[tid] = ls;
+    // ---- round B: the four breakpoint homologies at the shifted position
+    int hom[4];
+    indel_phase1<false>(v.R, v.Q, ins, v.n, v.pr, v.pq, ls, hom);
+#pragma unroll
+    for (int k = 0; k < 4; k++) queue_push(live && hom[k] == 32, (uint16_t)((tid << 3) | (k + 1)), s_q, &s_cnt[1]);
+    __syncthreads();
+    {   // HOMQ_COOP lanes per item
+        const int n_b = s_cnt[1], g = tid & (HOMQ_COOP - 1);
+        for (int t0 = 0; t0 < n_b; t0 += HOMQ_THREADS / HOMQ_COOP) {
+            const int t = t0 + tid / HOMQ_COOP;
+            const bool act = t < n_b;
+            const int item = s_q[act ? t : 0];
+            const int owner = item >> 3, sc = act ? (item & 7) : 1;
+            const StubView w = load_stub(stubs, i0 + owner, ref, qry);
+            const int h = indel_rest_coop<HOMQ_COOP>(w.R, w.Q, w.svtype == 0, w.n, w.pr, w.pq, s_ls[owner], sc, act, g);
+            if (act && g == 0) s_res[owner * 5 + sc] = h;
+        }
     }
     __syncthreads();
     if (!live) return;
 #pragma unroll
     for (int k = 0; k < 4; k++)
-        if (hom[k] == 32) hom[k] = s_res[tid * 4 + k];
+        if (hom[k] == 32) hom[k] = s_res[tid * 5 + k + 1];
     IndelScore o;
     indel_finish(v.Q, ins, v.n, v.pr, v.pq, ls, hom, o);
     int4 *dst = reinterpret_cast<int4 *>(rows + i);
@@ -1053,6 +1053,96 @@ homology_queue_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
     dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
     dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
     dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
+}
+
+// K4s: the same pieces as K4q without CTA barriers, as three launches. ncu on K4q (profiles/r02_ncu_homology_queue.txt): 41 % of
+// the warp time is spent at the barriers that fence the two rest rounds -- every CTA waits for its slowest tandem-repeat scan,
+// a chain of dependent DRAM reads run by one or two of its eight warps. Here the rests leave the kernel altogether:
+//   split_first : thread per indel. First trip of the left-shift scan; if that scan must go on (eqb > 32 and all 32 bases
+//                 matched) the indel is appended to queue A and left for split_shift; otherwise the shift is known, the four
+//                 breakpoint homologies take their first trips, unfinished ones are appended to queue B as (indel, scan), and
+//                 the row is written (pending homologies as 32).
+//   split_shift : thread per queue-A item: rest of the left-shift scan, then the same first trips / queue-B appends / row.
+//   split_rest  : thread per queue-B item: rest of one homology scan, patched into its row.
+// Queues live in global memory (one warp-aggregated atomicAdd per warp and append); the second and third launch size their
+// grid-stride loops from the counters the launches before them left behind. No thread ever waits for another.
+constexpr int HOMS_THREADS = 256;
+
+__device__ __forceinline__ void gqueue_push(bool flag, uint32_t item, uint32_t *__restrict__ q, unsigned int *__restrict__ cnt)
+{
+    const unsigned m = __ballot_sync(__activemask(), flag);
+    if (!flag) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(cnt, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    q[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
+__device__ __forceinline__ void split_finish_row(const StubView &v, int64_t i, int ls, int (&hom)[4], uint32_t *__restrict__ qb, unsigned int *__restrict__ cnt_b,
+                                                 pavgpu_indel_row *__restrict__ rows)
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) gqueue_push(hom[k] == 32, (uint32_t)(i * 4 + k), qb, cnt_b);
+    IndelScore o;
+    indel_finish(v.Q, v.svtype == 0, v.n, v.pr, v.pq, ls, hom, o);
+    int4 *dst = reinterpret_cast<int4 *>(rows + i);
+    dst[0] = make_int4(v.rec, v.op_idx, v.svtype, v.n);
+    dst[1] = make_int4(o.pos, o.end, o.qry_pos, o.qry_end);
+    dst[2] = make_int4(o.ls, o.hom_rl, o.hom_rr, o.hom_tl);
+    dst[3] = make_int4(o.hom_tr, o.seq_start, 0, 0);
+}
+
+__global__ void __launch_bounds__(HOMS_THREADS, 4)
+homology_split_first_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqPlanes ref, SeqPlanes qry, uint32_t *__restrict__ qa,
+                            uint32_t *__restrict__ qb, unsigned int *__restrict__ cnt, pavgpu_indel_row *__restrict__ rows)
+{
+    const int64_t i = (int64_t)blockIdx.x * HOMS_THREADS + threadIdx.x;
+    if (i >= n_indel) return;
+    const StubView v = load_stub(stubs, i, ref, qry);
+    const bool ins = v.svtype == 0;
+    int h0 = indel_phase0<false>(v.R, v.Q, ins, v.n, v.pr, v.pq);
+    if (v.eqb <= 0) h0 = 0;
+    const bool need0 = h0 == 32 && v.eqb > 32;
+    gqueue_push(need0, (uint32_t)i, qa, cnt);
+    if (need0) return;
+    const int ls = min(v.eqb, h0);
+    int hom[4];
+    indel_phase1<false>(v.R, v.Q, ins, v.n, v.pr, v.pq, ls, hom);
+    split_finish_row(v, i, ls, hom, qb, cnt + 1, rows);
+}
+
+__global__ void __launch_bounds__(HOMS_THREADS, 4)
+homology_split_shift_kernel(const IndelStub *__restrict__ stubs, SeqPlanes ref, SeqPlanes qry, const uint32_t *__restrict__ qa, uint32_t *__restrict__ qb,
+                            unsigned int *__restrict__ cnt, pavgpu_indel_row *__restrict__ rows)
+{
+    const unsigned int n_a = cnt[0];
+    for (unsigned int t = blockIdx.x * HOMS_THREADS + threadIdx.x; t < n_a; t += gridDim.x * HOMS_THREADS) {
+        const int64_t i = (int64_t)qa[t];
+        const StubView v = load_stub(stubs, i, ref, qry);
+        const bool ins = v.svtype == 0;
+        const int ls = min(v.eqb, indel_rest<false>(v.R, v.Q, ins, v.n, v.pr, v.pq, 0, 0));
+        int hom[4];
+        indel_phase1<false>(v.R, v.Q, ins, v.n, v.pr, v.pq, ls, hom);
+        split_finish_row(v, i, ls, hom, qb, cnt + 1, rows);
+    }
+}
+
+__global__ void __launch_bounds__(HOMS_THREADS, 4)
+homology_split_rest_kernel(const IndelStub *__restrict__ stubs, SeqPlanes ref, SeqPlanes qry, const uint32_t *__restrict__ qb,
+                           const unsigned int *__restrict__ cnt, pavgpu_indel_row *__restrict__ rows)
+{
+    const unsigned int n_b = cnt[1];
+    for (unsigned int t = blockIdx.x * HOMS_THREADS + threadIdx.x; t < n_b; t += gridDim.x * HOMS_THREADS) {
+        const uint32_t item = qb[t];
+        const int64_t i = (int64_t)(item >> 2);
+        const int k = (int)(item & 3u);
+        const StubView v = load_stub(stubs, i, ref, qry);
+        const int ls = rows[i].left_shift;
+        const int h = indel_rest<false>(v.R, v.Q, v.svtype == 0, v.n, v.pr, v.pq, ls, k + 1);
+        int32_t *f = k == 0 ? &rows[i].hom_ref_l : k == 1 ? &rows[i].hom_ref_r : k == 2 ? &rows[i].hom_tig_l : &rows[i].hom_tig_r;
+        *f = h;
+    }
 }
 
 __global__ void homology_probe_kernel(SeqPlanes st, int32_t n, const int64_t *__restrict__ pos, int32_t sv_len,
@@ -1090,6 +1180,7 @@ struct pavgpu_cigar_batch {
     unsigned long long *d_first_illegal;
     int4 *d_snv; int64_t cap_snv;
     IndelStub *d_stub; pavgpu_indel_row *d_indel; int64_t cap_indel;
+    uint32_t *d_hq_a, *d_hq_b; unsigned int *d_hq_cnt;   // homology_split_*: queues of pending scans
     int64_t n_snv, n_indel;
     bool sized;                          // row buffers (single-pass) / scan scratch (multi-pass) allocated
     bool cnt_valid;                      // the device count has run: totals known
@@ -1104,7 +1195,8 @@ struct pavgpu_cigar_batch {
     std::vector<int32_t> h_ref_id, h_qry_id;
     std::vector<uint8_t> h_rev;
     bool fused;
-    int hom_kernel;                      // homology kernel of the last run: 0 gathers, 1 warp tiles, 2 / 3 per-indel neighbourhoods
+    int hom_launches;                    // kernel launches of the last homology step
+    int hom_kernel;                      // homology kernel of the last run: 0 gathers, 1 warp tiles, 2 / 3 per-indel neighbourhoods, 4 CTA queue, 5 split
     unsigned long long first_illegal;
     bool ran;
     float ms_h2d;
@@ -1112,7 +1204,7 @@ struct pavgpu_cigar_batch {
     // resident batch and replayed while the stores and the kernel choice stay the same
     cudaGraphExec_t gexec;
     uint64_t g_ref_uid, g_qry_uid;
-    int g_hom;
+    int g_hom, g_hom_launches;
     int runs;
     // host view of the ops for explaining an illegal op (error path only): borrowed from the caller in the one-shot
     // call, copied for resident batches
@@ -1298,6 +1390,7 @@ static int homology_choice(const pavgpu_cigar_batch *b)
         if (!strcmp(h, "nbr")) return 2;
         if (!strcmp(h, "bulk")) return 3;
         if (!strcmp(h, "queue")) return 4;
+        if (!strcmp(h, "split")) return 5;
     }
     if (force && force[0] == '1') return 1;
     if (force && force[0] == 'a' && dense) return 1;
@@ -1321,7 +1414,17 @@ static int launch_homology(pavgpu_cigar_batch *b, cudaStream_t st, const pavgpu_
     const int64_t rw = ref_store->total_bases / 32, qw = qry_store->total_bases / 32;
     const int dev = b->ctx->device;
     b->hom_kernel = homology_choice(b);
-    if (b->hom_kernel == 4) {
+    if (b->hom_kernel == 5 && !b->d_hq_a) b->hom_kernel = 0;   // (multi-pass walk: no queues were allocated)
+    b->hom_launches = b->hom_kernel == 5 ? 3 : 1;
+    if (b->hom_kernel == 5) {
+        // queue A: n_indel items, queue B: 4 n_indel items, two counters (behind the indel rows in the row arena)
+        CUDA_TRY(cudaMemsetAsync(b->d_hq_cnt, 0, 8, st));
+        const unsigned hb = (unsigned)((b->n_indel + HOMS_THREADS - 1) / HOMS_THREADS);
+        const unsigned gb = std::max(1u, std::min(hb, (unsigned)(b->ctx->sm_count > 0 ? b->ctx->sm_count : 148) * 4u));
+        homology_split_first_kernel<<<hb, HOMS_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_hq_a, b->d_hq_b, b->d_hq_cnt, b->d_indel);
+        homology_split_shift_kernel<<<gb, HOMS_THREADS, 0, st>>>(b->d_stub, pl_ref, pl_qry, b->d_hq_a, b->d_hq_b, b->d_hq_cnt, b->d_indel);
+        homology_split_rest_kernel<<<gb, HOMS_THREADS, 0, st>>>(b->d_stub, pl_ref, pl_qry, b->d_hq_b, b->d_hq_cnt, b->d_indel);
+    } else if (b->hom_kernel == 4) {
         const unsigned hb = (unsigned)((b->n_indel + HOMQ_THREADS - 1) / HOMQ_THREADS);
         homology_queue_kernel<<<hb, HOMQ_THREADS, 0, st>>>(b->d_stub, b->n_indel, pl_ref, pl_qry, b->d_indel);
     } else if (b->hom_kernel == 3) {
@@ -1404,12 +1507,13 @@ static int size_rows(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv, 
     }
     ArenaPlan ap;
     const size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1);
-    size_t o_agg = 0, o_cnt = 0, o_prq = 0, o_pcnt = 0, o_snv = 0, o_stub = 0, o_indel = 0;
+    size_t o_agg = 0, o_cnt = 0, o_prq = 0, o_pcnt = 0, o_snv = 0, o_stub = 0, o_indel = 0, o_hqa = 0, o_hqb = 0, o_hqc = 0;
     if (!b->fused) { o_agg = ap.add(nc * sizeof(int4)); o_cnt = ap.add(nc * sizeof(uint2)); o_prq = ap.add(nc * sizeof(int2)); o_pcnt = ap.add(nc * sizeof(longlong2)); }
     else {
         o_snv = ap.add((size_t)b->cnt_n_snv * sizeof(int4));
         o_stub = ap.add((size_t)b->cnt_n_indel * sizeof(IndelStub));
         o_indel = ap.add((size_t)b->cnt_n_indel * sizeof(pavgpu_indel_row));
+        o_hqa = ap.add((size_t)b->cnt_n_indel * 4); o_hqb = ap.add((size_t)b->cnt_n_indel * 16); o_hqc = ap.add(8);
     }
     cudaError_t e = pav_dev_alloc(ctx, ap.off, &b->d_rows_arena);
     if (e != cudaSuccess) { pav_set_error("cigar walk: cudaMalloc(%zu) for the row buffers failed: %s", ap.off, cudaGetErrorString(e)); return PAVGPU_ERR_NOMEM; }
@@ -1419,6 +1523,7 @@ static int size_rows(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv, 
     } else {
         b->d_snv = (int4 *)(base + o_snv); b->d_stub = (IndelStub *)(base + o_stub); b->d_indel = (pavgpu_indel_row *)(base + o_indel);
         b->cap_snv = b->cnt_n_snv; b->cap_indel = b->cnt_n_indel;
+        b->d_hq_a = (uint32_t *)(base + o_hqa); b->d_hq_b = (uint32_t *)(base + o_hqb); b->d_hq_cnt = (unsigned int *)(base + o_hqc);
     }
     b->sized = true;
     return PAVGPU_OK;
@@ -1466,13 +1571,14 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
     if (b->n_chunks > 0 && b->fused) {
         b->n_snv = b->cnt_n_snv; b->n_indel = b->cnt_n_indel;
         const int hom = b->n_indel > 0 ? homology_choice(b) : -1;
-        static const bool no_graph = [] { const char *g = getenv("PAVGPU_NO_GRAPH"); return g && g[0] == '1'; }();
+        const char *ng = getenv("PAVGPU_NO_GRAPH");      // read per call: bench.py repeats its timed steps without the graph for the per-kernel split
+        const bool no_graph = ng && ng[0] == '1';
         if (counted_now) {
             // first run: the count has just run eagerly (its totals sized the buffers); finish the step eagerly
             CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
             int rc = launch_walk_homology(b, st, rv, ref_store, qry_store);
             if (rc) return rc;
-            launches += 1 + (b->n_indel > 0 ? 1 : 0);
+            launches += 1 + (b->n_indel > 0 ? b->hom_launches : 0);
         } else {
             // later runs of a resident batch: the whole step -- count, record scan, walk, homology -- replayed as one graph
             if (!no_graph && (!b->gexec || b->g_ref_uid != ref_store->uid || b->g_qry_uid != qry_store->uid || b->g_hom != hom)) {
@@ -1492,10 +1598,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
                 ce = cudaGraphInstantiate(&b->gexec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (ce != cudaSuccess) { b->gexec = nullptr; pav_set_error("cigar walk: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return PAVGPU_ERR_CUDA; }
-                b->g_ref_uid = ref_store->uid; b->g_qry_uid = qry_store->uid; b->g_hom = hom;
+                b->g_ref_uid = ref_store->uid; b->g_qry_uid = qry_store->uid; b->g_hom = hom; b->g_hom_launches = b->hom_launches;
             }
             CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
-            if (b->gexec) {
+            if (b->gexec && !no_graph) {
                 CUDA_TRY(cudaGraphLaunch(b->gexec, st));
                 used_graph = 1;
             } else {
@@ -1505,7 +1611,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
                 rc = launch_walk_homology(b, st, rv, ref_store, qry_store);
                 if (rc) return rc;
             }
-            launches += 3 + (b->n_indel > 0 ? 1 : 0);
+            launches += 3 + (b->n_indel > 0 ? (b->gexec && used_graph ? b->g_hom_launches : b->hom_launches) : 0);
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         int64_t tot[2];
@@ -1550,7 +1656,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         if (b->n_indel > 0) {
             int hrc = launch_homology(b, st, ref_store, qry_store);
             if (hrc) return hrc;
-            launches++;
+            launches += b->hom_launches;
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         CUDA_TRY(cudaMemcpyAsync(&b->first_illegal, b->d_first_illegal, 8, cudaMemcpyDeviceToHost, st));

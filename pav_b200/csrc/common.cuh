@@ -146,19 +146,24 @@ struct pavgpu_seqstore {
     int64_t *d_len;
     uint64_t *d_pack2;
     uint32_t *d_nmask;
-    size_t pack2_bytes, nmask_bytes;
+    uint32_t *d_nsum;     // N summary: bit b of word j set when mask words [(32 j + b) * 8, +8) hold a set bit (seqbits.cuh nsum_any2)
+    size_t pack2_bytes, nmask_bytes, nsum_bytes;
 };
+
+// (Re)build the N summary from the mask plane on the store's stream: after packing, after an upload of packed planes, after a broadcast.
+int pav_build_nsum(pavgpu_seqstore *store);
 
 struct SeqPlanes {
     const uint64_t *pack2;
     const uint32_t *nmask;
     const int64_t *off;
     const int64_t *len;
+    const uint32_t *nsum;
 };
 
 static inline SeqPlanes planes_of(const pavgpu_seqstore *s)
 {
-    return SeqPlanes{s->d_pack2, s->d_nmask, s->d_off, s->d_len};
+    return SeqPlanes{s->d_pack2, s->d_nmask, s->d_off, s->d_len, s->d_nsum};
 }
 
 #include "seqbits.cuh"

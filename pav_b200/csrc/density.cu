@@ -90,7 +90,7 @@ ref_insert_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes 
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
     uint64_t kmer = 0;
-    if (i < n_pos) valid = kmer_at(ref.pack2, ref.nmask, P.ref_g0 + i, k, kmer);
+    if (i < n_pos) valid = kmer_at(ref.pack2, ref.nmask, P.ref_g0 + i, k, kmer, ref.nsum);
     unsigned int my_cnt = 0;
     if (valid) {
         if (P.rev) kmer = kmer_revcomp(kmer, k);  // density.py:538-539: the reference SET is reverse-complemented
@@ -149,7 +149,7 @@ tig_state_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes t
     int st = -1;
     if (i < n_pos) {
         uint64_t kmer;
-        if (kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer)) {
+        if (kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer, tig.nsum)) {
             const uint64_t *tk = keys + P.tab_off;
             bool f = table_has(tk, P.tab_log2, kmer);
             bool r = table_has(tk, P.tab_log2, kmer_revcomp(kmer, k));
@@ -207,7 +207,7 @@ compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig
     if (keep) {
         int64_t row = P.row_off + s_base + before + __popc(bal & ((1u << lane) - 1));
         uint64_t kmer = 0;
-        kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer);
+        kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer, tig.nsum);
         o_kmer[row] = kmer;
         o_index[row] = i;
         o_state_mer[row] = (int8_t)st;
@@ -511,6 +511,73 @@ finalize_kernel(const WinPlan *__restrict__ plan, int32_t win_base, double *__re
     state[r] = (int8_t)argmax3(a, b, c);
 }
 
+// D10 -----------------------------------------------------------------------------------------------
+// Run-length encoding of the final STATE column in row order: (state, count, first INDEX, last INDEX) per run -- exactly the
+// tuples pavlib.density.rl_encoder yields (pavlib/density.py:330-361) and all that scan_for_inv looks at to decide whether a
+// locus is expanded again (pavlib/inv.py:294-342). One CTA per window; at most STATE_RUN_CAP runs are stored per window (a
+// smoothed STATE column has a handful), the true number is always reported. Un-smoothed windows are one run of state -1.
+constexpr int STATE_RUN_CAP = 512;
+
+__global__ void __launch_bounds__(256)
+state_rle_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state, const int32_t *__restrict__ index,
+                 pavgpu_state_run *__restrict__ runs, int32_t *__restrict__ n_state_runs)
+{
+    const int32_t w = blockIdx.x;
+    const WinPlan P = plan[w];
+    const int32_t N = (P.status == 0) ? P.n_rows : 0;
+    pavgpu_state_run *out = runs + (int64_t)w * STATE_RUN_CAP;
+    if (N == 0) { if (threadIdx.x == 0) n_state_runs[w] = 0; return; }
+    const int32_t *ix = index + P.row_off;
+    if (!P.smoothed) {
+        if (threadIdx.x == 0) { out[0] = pavgpu_state_run{-1, N, ix[0], ix[N - 1]}; n_state_runs[w] = 1; }
+        return;
+    }
+    const int8_t *st = state + P.row_off;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {
+        const int32_t i = i0 + threadIdx.x;
+        const bool head = i < N && (i == 0 || st[i] != st[i - 1]);
+        const unsigned bal = __ballot_sync(FULL, head);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < wid) before += c; total += c; }
+        if (head) {
+            const int32_t r = s_base + before + __popc(bal & ((1u << lane) - 1u));
+            if (r < STATE_RUN_CAP) { out[r].state = (int32_t)st[i]; out[r].first_index = ix[i]; out[r].count = i; }   // count holds the first row for now
+            if (r > 0 && r - 1 < STATE_RUN_CAP) out[r - 1].last_index = ix[i - 1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    const int32_t nr = s_base;
+    const int32_t kept = min(nr, STATE_RUN_CAP);
+    if (threadIdx.x == 0 && nr <= STATE_RUN_CAP) out[nr - 1].last_index = ix[N - 1];
+    __syncthreads();
+    // first rows -> counts (run r ends where run r + 1 starts)
+    int32_t nxt[2];
+    int32_t cnt_r[2];
+    int n_mine = 0;
+    for (int32_t r = threadIdx.x; r < kept && n_mine < 2; r += blockDim.x) {
+        nxt[n_mine] = (r + 1 < kept) ? out[r + 1].count : -1;
+        cnt_r[n_mine] = out[r].count;
+        n_mine++;
+    }
+    __syncthreads();
+    n_mine = 0;
+    for (int32_t r = threadIdx.x; r < kept && n_mine < 2; r += blockDim.x) {
+        const int32_t e = nxt[n_mine] >= 0 ? nxt[n_mine] : N;       // (the last stored run of an overflowing window is not used)
+        out[r].count = e - cnt_r[n_mine];
+        n_mine++;
+    }
+    if (threadIdx.x == 0) n_state_runs[w] = nr;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -534,6 +601,7 @@ struct pavgpu_density_batch {
     int32_t *d_run_start, *d_run_len, *d_n_runs; int8_t *d_run_state;
     int64_t tree_total;
     uint8_t *d_gap_full; int32_t *d_fill_list, *d_n_fill, *d_n_eval; int64_t *d_grp_off;
+    pavgpu_state_run *d_state_runs; int32_t *d_n_state_runs;
     bool ran;
     void *d_arena;    // one allocation backs every device buffer below
     size_t arena_bytes;
@@ -655,6 +723,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         size_t o_rs = carve(4 * rcap), o_rl = carve(4 * rcap), o_rst = carve(rcap), o_nr = carve(4 * (size_t)n_win);
         size_t o_gap = carve(rcap), o_fill = carve(4 * rcap), o_nf = carve(4 * (size_t)n_win), o_ne = carve(4 * (size_t)n_win);
         size_t o_grp = carve(8 * ((size_t)n_win + 1));
+        size_t o_sruns = carve(sizeof(pavgpu_state_run) * STATE_RUN_CAP * (size_t)n_win), o_nsr = carve(4 * (size_t)n_win);
         CUDA_TRY(ctx_arena_take(ctx, off, &b->d_arena, &b->arena_bytes));
         char *base = static_cast<char *>(b->d_arena);
         b->d_plan = (WinPlan *)(base + o_plan); b->d_wc = (WinCounts *)(base + o_wc); b->d_kp = (KdeParams *)(base + o_kp);
@@ -667,6 +736,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         b->d_n_runs = (int32_t *)(base + o_nr);
         b->d_gap_full = (uint8_t *)(base + o_gap); b->d_fill_list = (int32_t *)(base + o_fill);
         b->d_n_fill = (int32_t *)(base + o_nf); b->d_n_eval = (int32_t *)(base + o_ne); b->d_grp_off = (int64_t *)(base + o_grp);
+        b->d_state_runs = (pavgpu_state_run *)(base + o_sruns); b->d_n_state_runs = (int32_t *)(base + o_nsr);
         b->allocated = true;
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
@@ -783,6 +853,9 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
+    state_rle_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state, b->d_index, b->d_state_runs, b->d_n_state_runs);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     b->stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
@@ -846,5 +919,84 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch
         pavgpu_free_host(*kern_fwd_out); pavgpu_free_host(*kern_fwdrev_out); pavgpu_free_host(*kern_rev_out);
         return PAVGPU_ERR_NOMEM;
     }
+    return PAVGPU_OK;
+}
+
+// Run lengths of STATE for every window (what scan_for_inv decides from): 16 bytes per run instead of 38 bytes per row.
+extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch_runs(pavgpu_density_batch *b, pavgpu_density_result *res,
+                                                                                        pavgpu_state_run **runs_out, int64_t *run_off, int64_t *n_runs_total)
+{
+    if (!b || !b->ran || !res || !runs_out || !run_off || !n_runs_total) { pav_set_error("density_batch_fetch_runs: bad argument or batch not run"); return PAVGPU_ERR_ARG; }
+    pavgpu_ctx *ctx = b->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int32_t n_win = b->n_win;
+    *runs_out = nullptr; *n_runs_total = 0;
+    for (int32_t w = 0; w < n_win; w++) res[w] = b->res[w];
+    run_off[0] = 0;
+    if (n_win == 0) return PAVGPU_OK;
+    PavTrace tr("density_batch_fetch_runs");
+    std::vector<int32_t> n_sr(n_win);
+    CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(n_sr.data(), b->d_n_state_runs, 4 * (size_t)n_win, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    int64_t total = 0;
+    for (int32_t w = 0; w < n_win; w++) { run_off[w] = total; total += n_sr[w]; }
+    run_off[n_win] = total;
+    *n_runs_total = total;
+    if (total == 0) return PAVGPU_OK;
+    pavgpu_state_run *h = nullptr;
+    int prc = pav_pinned_take(ctx, (size_t)total * sizeof(pavgpu_state_run), reinterpret_cast<void **>(&h));
+    if (prc) return prc;
+    int rc = [&]() -> int {
+        for (int32_t w = 0; w < n_win; w++) {
+            if (n_sr[w] > 0 && n_sr[w] <= STATE_RUN_CAP)
+                CUDA_TRY(cudaMemcpyAsync(h + run_off[w], b->d_state_runs + (int64_t)w * STATE_RUN_CAP, (size_t)n_sr[w] * sizeof(pavgpu_state_run),
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev[6], ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        // a window with more runs than the device keeps (never seen on smoothed columns): encode its STATE column here
+        for (int32_t w = 0; w < n_win; w++) {
+            if (n_sr[w] <= STATE_RUN_CAP) continue;
+            const int64_t N = b->res[w].n_rows, r0 = b->res[w].row_off;
+            std::vector<int8_t> st((size_t)N);
+            std::vector<int32_t> ix((size_t)N);
+            CUDA_TRY(cudaMemcpy(st.data(), b->d_state + r0, (size_t)N, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(ix.data(), b->d_index + r0, (size_t)N * 4, cudaMemcpyDeviceToHost));
+            pavgpu_state_run *o = h + run_off[w];
+            int64_t r = -1;
+            for (int64_t i = 0; i < N; i++) {
+                if (i == 0 || st[i] != st[i - 1]) { r++; o[r] = pavgpu_state_run{(int32_t)st[i], 0, ix[i], ix[i]}; }
+                o[r].count++; o[r].last_index = ix[i];
+            }
+        }
+        return PAVGPU_OK;
+    }();
+    tr.mark("d2h");
+    if (rc) { pavgpu_free_host(h); return rc; }
+    b->stats.ms_d2h = ev_ms(ctx->ev[5], ctx->ev[6]);
+    *runs_out = h;
+    return PAVGPU_OK;
+}
+
+// All columns of one window into caller-owned arrays of res[win].n_rows entries (any pointer may be NULL): the window that becomes a call.
+extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch_window(pavgpu_density_batch *b, int32_t win, uint64_t *kmer, int32_t *index,
+                                                                                          int8_t *state_mer, int8_t *state, double *kern_fwd,
+                                                                                          double *kern_fwdrev, double *kern_rev)
+{
+    if (!b || !b->ran || win < 0 || win >= b->n_win) { pav_set_error("density_batch_fetch_window: bad argument or batch not run"); return PAVGPU_ERR_ARG; }
+    pavgpu_ctx *ctx = b->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t n = b->res[win].n_rows, r0 = b->res[win].row_off;
+    if (n == 0) return PAVGPU_OK;
+    cudaStream_t st = ctx->stream;
+    if (kmer) CUDA_TRY(cudaMemcpyAsync(kmer, b->d_kmer + r0, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (index) CUDA_TRY(cudaMemcpyAsync(index, b->d_index + r0, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (state_mer) CUDA_TRY(cudaMemcpyAsync(state_mer, b->d_state_mer + r0, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (state) CUDA_TRY(cudaMemcpyAsync(state, b->d_state + r0, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (kern_fwd) CUDA_TRY(cudaMemcpyAsync(kern_fwd, b->d_k[0] + r0, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (kern_fwdrev) CUDA_TRY(cudaMemcpyAsync(kern_fwdrev, b->d_k[1] + r0, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (kern_rev) CUDA_TRY(cudaMemcpyAsync(kern_rev, b->d_k[2] + r0, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return PAVGPU_OK;
 }

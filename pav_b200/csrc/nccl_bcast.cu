@@ -102,6 +102,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_broadcast(
         NCCL_TRY(g_nccl.Broadcast(store->d_nmask, store->d_nmask, store->nmask_bytes, NCCL_UINT8, 0, comm, ctx->stream));
         NCCL_TRY(g_nccl.GroupEnd());
         CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (rank != 0) { int nrc = pav_build_nsum(store); if (nrc) return nrc; }   // receivers derive the N summary from the mask plane they got
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (ms_out) *ms_out = ev_ms(ctx->ev[0], ctx->ev[1]);
         return PAVGPU_OK;

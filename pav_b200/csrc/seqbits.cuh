@@ -52,7 +52,29 @@ struct OSeq {
     const uint32_t *t_nmask;
     int64_t t_w0;
     int32_t t_nw1;
+    // Optional N summary of the mask plane (one bit per 8 mask words = 256 bases, set when any of them is non-zero; nullptr: none).
+    // A window whose blocks are clear has an all-zero mask and can skip its two mask loads. Used by the k-mer kernels (-1.4 % on the
+    // C5 k-mer part); the homology kernels leave it unset: measured on C2 (B200, r02) the dependent summary load in front of the mask
+    // loads costs more than the two skipped sectors save (gather 0.122 against 0.094 ms, CTA queue 0.097 against 0.087 ms).
+    const uint32_t *nsum;
 };
+
+// Mask words w and w+1 may hold set bits (always true without a summary).
+PAV_DEV bool nsum_any2(const uint32_t *__restrict__ nsum, int64_t w)
+{
+#ifdef PAV_NO_NSUM   // A/B builds: mask loads never skipped
+    return true;
+#endif
+    if (!nsum) return true;
+    const int64_t b0 = w >> 3, b1 = (w + 1) >> 3;
+    const uint32_t s0 = __ldg(nsum + (b0 >> 5));
+    uint32_t any = (s0 >> (b0 & 31)) & 1u;
+    if (b1 != b0) {
+        const uint32_t s1 = (b1 >> 5) == (b0 >> 5) ? s0 : __ldg(nsum + (b1 >> 5));
+        any |= (s1 >> (b1 & 31)) & 1u;
+    }
+    return any != 0;
+}
 
 // Upper-cased base as 0..3 (ACGT) or 4 (anything else, or out of range).
 PAV_DEV int oseq_base(const OSeq &s, int64_t t)
@@ -95,7 +117,7 @@ PAV_DEV void fwd_window(const OSeq &s, int32_t f, uint64_t &bases, uint32_t &mas
         m0 = s.t_nmask[o]; m1 = s.t_nmask[o + 1];
     } else {
         hi = __ldg(s.pack2 + w); lo = __ldg(s.pack2 + w + 1);
-        m0 = __ldg(s.nmask + w); m1 = __ldg(s.nmask + w + 1);
+        if (nsum_any2(s.nsum, w)) { m0 = __ldg(s.nmask + w); m1 = __ldg(s.nmask + w + 1); } else { m0 = 0; m1 = 0; }
     }
     uint64_t b = sh ? ((hi << (2 * sh)) | (lo >> (64 - 2 * sh))) : hi;
     uint32_t m = __funnelshift_r(m0, m1, sh);
@@ -120,6 +142,14 @@ PAV_DEV void oseq_window(const OSeq &s, int32_t t, uint64_t &bases, uint32_t &ma
     bases = revcomp32(b);
     mask = __brev(m);
 }
+
+// HOM_BATCH_LOADS = 1 routes the first trips and the rests of score_indel2 through the prepared / loaded / finished windows below
+// (all loads of a phase in flight together). Measured on C2 (B200, r02): slower than the plain windows at every register budget
+// (queue kernel 0.092-0.104 ms against 0.0755 ms; 64 / 80 / 128 registers) -- the kernel is bound by DRAM row activations of
+// scattered sectors, not by the number of dependent round trips per thread, and the selects cost instructions. Kept for A/B builds.
+#ifndef HOM_BATCH_LOADS
+#define HOM_BATCH_LOADS 0
+#endif
 
 // The same window in three steps, so that a caller can issue the loads of several windows before it looks at any of them:
 // win_prep (all address arithmetic, no branch on data), win_load (four loads), win_finish (shifts, sequence edges, strand -- selects
@@ -155,7 +185,7 @@ PAV_DEV WinRaw win_load(const OSeq &s, const WinReq &q)
 {
     WinRaw r;
     r.hi = __ldg(s.pack2 + q.w); r.lo = __ldg(s.pack2 + q.w + 1);
-    r.m0 = __ldg(s.nmask + q.w); r.m1 = __ldg(s.nmask + q.w + 1);
+    if (nsum_any2(s.nsum, q.w)) { r.m0 = __ldg(s.nmask + q.w); r.m1 = __ldg(s.nmask + q.w + 1); } else { r.m0 = 0; r.m1 = 0; }
     return r;
 }
 
@@ -254,8 +284,8 @@ PAV_DEV int dev_homology_raw(const uint64_t *t_pack2, const uint32_t *t_nmask, i
                                                     int64_t p, const uint64_t *v_pack2, const uint32_t *v_nmask, int64_t v_base, int64_t v_len,
                                                     int v_rev, int64_t v0, int n, int left)
 {
-    const OSeq T{t_pack2, t_nmask, t_base, t_len, t_rev, nullptr, nullptr, 0, 0};
-    const OSeq V{v_pack2, v_nmask, v_base, v_len, v_rev, nullptr, nullptr, 0, 0};
+    const OSeq T{t_pack2, t_nmask, t_base, t_len, t_rev, nullptr, nullptr, 0, 0, nullptr};
+    const OSeq V{v_pack2, v_nmask, v_base, v_len, v_rev, nullptr, nullptr, 0, 0, nullptr};
     if (n <= 0 || p < 0 || p >= T.len) return 0;
     const int32_t p32 = (int32_t)p, v32 = (int32_t)v0;
     int32_t h = common_extension(T, p32, V, left ? v32 + n - 1 : v32, n, left);
@@ -412,12 +442,75 @@ PAV_DEV int scan_rest(const OSeq &T, int32_t p, const OSeq &V, int32_t v0, int n
         const int32_t a = left ? p - h : p + h;
         const int32_t b = stage == 0 ? (left ? v0 + n - 1 - 32 : v0 + 32) : (left ? a + n : a - n);
         const int32_t lim = stage == 0 ? n - 32 : 0x7fffffff - 64 - n;
-        const int32_t e = TILED ? common_extension<TILED>(T, a, B, b, lim, left) : common_extension2(T, a, B, b, lim, left);
+        const int32_t e = (TILED || !HOM_BATCH_LOADS) ? common_extension<TILED>(T, a, B, b, lim, left) : common_extension2(T, a, B, b, lim, left);
         h += e;
         if (stage == 0 && e < lim) break;
     }
     return h;
 }
+
+// ---- cooperative rests -----------------------------------------------------------------------------
+// A scan that goes on after its first 32 bases is a chain of dependent window reads when one thread follows it (tandem repeats:
+// hundreds of bases). Here G consecutive lanes share one scan: lane g compares window g, g + G, ... of it, all G windows of a
+// round are in flight together, and the first lane (in scan order) whose window stops decides. Whole warps call these functions
+// together (every lane the same number of times); a group with nothing to do passes limit 0. Device only (warp votes).
+#ifdef __CUDACC__
+template <int G>
+__device__ __forceinline__ int32_t coop_extension(const OSeq &A, int32_t a, const OSeq &B, int32_t b, int32_t limit, int left, int g)
+{
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
+    const unsigned FULLW = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane & ~(G - 1);
+    const unsigned gmask = (G == 32) ? FULLW : (((1u << G) - 1u) << gbase);
+    const int32_t a0 = left ? a - 31 : a, b0 = left ? b - 31 : b, step = left ? -32 : 32;
+    int32_t h = 0;          // bases matched so far (multiple of 32 while the group is still scanning)
+    bool done = limit <= 0;
+    int32_t result = 0;
+    while (__any_sync(FULLW, !done)) {
+        int stop = 32;
+        if (!done) {
+            const int32_t t = h / 32 + g;                 // my window of this round
+            if ((int64_t)t * 32 < (int64_t)limit) {
+                uint64_t wa, wb; uint32_t ma, mb;
+                oseq_window<false>(A, a0 + step * t, wa, ma);
+                oseq_window<false>(B, b0 + step * t, wb, mb);
+                stop = window_stop(wa, ma, wb, mb, left);
+            } else stop = 0;                              // past the cap: the scan ends here at the latest
+        }
+        const unsigned bal = __ballot_sync(FULLW, !done && stop < 32) & gmask;
+        const int f = bal ? __ffs((int)bal) - 1 : lane;   // first stopping lane of my group
+        const int sf = __shfl_sync(FULLW, stop, f);       // (every lane of the warp executes the vote and the shuffle)
+        if (!done) {
+            if (bal) {
+                result = h + 32 * (f - gbase) + sf;
+                done = true;
+            } else {
+                h += 32 * G;
+                if (h < 0 || h >= limit) { result = limit; done = true; }
+            }
+        }
+    }
+    return result < limit ? result : limit;
+}
+
+// scan_rest by a group of G lanes (all lanes of the group pass the same arguments; active == false: nothing to do, returns 32).
+template <int G>
+__device__ __forceinline__ int scan_rest_coop(const OSeq &T, int32_t p, const OSeq &V, int32_t v0, int n, int left, bool active, int g)
+{
+    const int32_t lim0 = (active && n > 32) ? n - 32 : 0;
+    const int32_t e0 = coop_extension<G>(T, left ? p - 32 : p + 32, V, left ? v0 + n - 1 - 32 : v0 + 32, lim0, left, g);
+    int32_t h = 32 + e0;
+    const bool cont = active && e0 >= lim0;              // n <= 32: straight to the self-comparison; n > 32: only after a whole copy
+    const int32_t a = left ? p - h : p + h;
+    const int32_t b = left ? a + n : a - n;
+    const int32_t e1 = coop_extension<G>(T, a, T, b, cont ? 0x7fffffff - 64 - n : 0, left, g);
+    return h + e1;
+}
+
+template <int G>
+__device__ __forceinline__ int indel_rest_coop(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, int sc, bool active, int g);
+#endif
 
 // The pieces of one indel's scoring, in the order the reference runs them (cigarcall.py:137-266). score_indel2 strings them
 // together for one thread; homology_queue_kernel runs the same pieces with the rests of a whole CTA's indels pooled in between.
@@ -447,7 +540,7 @@ PAV_DEV int first_trip_w(const OSeq &T, int32_t p, uint64_t wt, uint32_t mt, uin
 template <bool TILED>
 PAV_DEV int indel_phase0(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq)
 {
-    if (!TILED) {   // both windows requested before either is used
+    if (!TILED && HOM_BATCH_LOADS) {   // both windows requested before either is used
         const OSeq V = ins ? Q : R;
         const WinReq qv = win_prep(V, (ins ? pq : pr) + n - 32), qt = win_prep(R, pr - 32);
         const WinRaw rv = win_load(V, qv), rt = win_load(R, qt);
@@ -471,7 +564,7 @@ PAV_DEV void indel_phase1(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int
 {
     const int32_t sp = pr - ls, sq = pq - ls, v0 = ins ? sq : pr;
     uint64_t patl, patr; uint32_t patlm, patrm;
-    if (!TILED) {   // all six windows requested before any is used
+    if (!TILED && HOM_BATCH_LOADS) {   // all six windows requested before any is used
         const OSeq V = ins ? Q : R;
         const int32_t p_rl = sp - 1, p_rr = ins ? sp : sp + n, p_tl = sq - 1, p_tr = ins ? sq + n : sq;
         const WinReq qvl = win_prep(V, v0 + n - 32), qvr = win_prep(V, v0);
@@ -510,6 +603,18 @@ PAV_DEV int indel_rest(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_
     const OSeq V = ins ? Q : R;
     return scan_rest<TILED>(T, p, V, v0, n, left);
 }
+
+#ifdef __CUDACC__
+template <int G>
+__device__ __forceinline__ int indel_rest_coop(const OSeq &R, const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, int sc, bool active, int g)
+{
+    int32_t p, v0; bool on_ref; int left;
+    scan_geometry(sc, ins, n, pr, pq, ls, p, v0, on_ref, left);
+    const OSeq T = on_ref ? R : Q;
+    const OSeq V = ins ? Q : R;
+    return scan_rest_coop<G>(T, p, V, v0, n, left, active, g);
+}
+#endif
 
 PAV_DEV void indel_finish(const OSeq &Q, bool ins, int32_t n, int32_t pr, int32_t pq, int32_t ls, const int (&hom)[4], IndelScore &o)
 {
@@ -602,14 +707,16 @@ PAV_DEV uint64_t kmer_revcomp(uint64_t kmer, int k)
 // k-mer starting at global base g (first base most significant); returns false if any of its k bases
 // is not ACGT (stream() would not have emitted it, kmer.py:206-221).
 PAV_DEV bool kmer_at(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t g, int k,
-                                        uint64_t &kmer)
+                                        uint64_t &kmer, const uint32_t *__restrict__ nsum = nullptr)
 {
     int64_t w = g >> 5;
     int s = (int)(g & 31);
-    uint64_t m = (uint64_t)__ldg(nmask + w) | ((uint64_t)__ldg(nmask + w + 1) << 32);
-    m >>= s;
-    uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
-    if (m & kmask) return false;
+    if (nsum_any2(nsum, w)) {
+        uint64_t m = (uint64_t)__ldg(nmask + w) | ((uint64_t)__ldg(nmask + w + 1) << 32);
+        m >>= s;
+        uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+        if (m & kmask) return false;
+    }
     uint64_t hi = __ldg(pack2 + w), lo = __ldg(pack2 + w + 1);
     uint64_t x = s ? ((hi << (2 * s)) | (lo >> (64 - 2 * s))) : hi;
     kmer = x >> (64 - 2 * k);

@@ -11,6 +11,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -211,6 +213,29 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ a
     nmask[w] = mask;
 }
 
+// N summary of the mask plane: a warp covers 32 consecutive mask words = 4 summary bits of one summary word.
+__global__ void __launch_bounds__(256) nsum_kernel(const uint32_t *__restrict__ nmask, int64_t n_words, uint32_t *__restrict__ nsum)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned bal = __ballot_sync(0xffffffffu, w < n_words && nmask[w] != 0u);
+    if ((threadIdx.x & 31) == 0 && bal) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) bits |= ((bal >> (8 * q)) & 0xffu) ? (1u << q) : 0u;
+        atomicOr(nsum + (w >> 8), bits << ((w >> 3) & 31));
+    }
+}
+
+int pav_build_nsum(pavgpu_seqstore *s)
+{
+    pavgpu_ctx *ctx = s->ctx;
+    const int64_t n_words = s->total_bases / 32;
+    CUDA_TRY(cudaMemsetAsync(s->d_nsum, 0, s->nsum_bytes, ctx->stream));
+    nsum_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, ctx->stream>>>(s->d_nmask, n_words, s->d_nsum);
+    CUDA_TRY(cudaGetLastError());
+    return PAVGPU_OK;
+}
+
 static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, pavgpu_seqstore **out)
 {
     if (!ctx || n_seq < 0 || (n_seq > 0 && !seq_len) || !out) { pav_set_error("seqstore: bad argument"); return PAVGPU_ERR_ARG; }
@@ -236,11 +261,14 @@ static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, p
     s->total_bases = off;
     s->pack2_bytes = (size_t)(off / 32) * 8;
     s->nmask_bytes = (size_t)(off / 32) * 4;
+    s->nsum_bytes = ((size_t)(off / 32 + 1) / 256 + 2) * 4;   // windows read mask words w and w+1: one summary word of slack
     s->d_off = s->d_len = nullptr;
     s->d_pack2 = nullptr;
     s->d_nmask = nullptr;
+    s->d_nsum = nullptr;
     cudaError_t e;
     if ((e = pav_dev_alloc_t(ctx, s->pack2_bytes / 8, &s->d_pack2)) != cudaSuccess || (e = pav_dev_alloc_t(ctx, s->nmask_bytes / 4, &s->d_nmask)) != cudaSuccess ||
+        (e = pav_dev_alloc_t(ctx, s->nsum_bytes / 4, &s->d_nsum)) != cudaSuccess ||
         (e = pav_dev_alloc_t(ctx, (size_t)n_seq + 1, &s->d_off)) != cudaSuccess ||
         (e = pav_dev_alloc_t(ctx, (size_t)n_seq + 1, &s->d_len)) != cudaSuccess) {
         pav_set_error("seqstore: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -252,6 +280,7 @@ static int alloc_store(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, p
             CUDA_TRY(cudaMemcpyAsync(s->d_off, s->h_off.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(s->d_len, s->h_len.data(), sizeof(int64_t) * n_seq, cudaMemcpyHostToDevice, ctx->stream));
         }
+        CUDA_TRY(cudaMemsetAsync(s->d_nsum, 0xFF, s->nsum_bytes, ctx->stream));   // "every block may hold N" until the planes are filled
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return PAVGPU_OK;
     }();
@@ -292,6 +321,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
         int64_t blocks = (n_words + 255) / 256;
         pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_ascii, n_words, s->d_pack2, s->d_nmask);
         CUDA_TRY(cudaGetLastError());
+        { int nrc = pav_build_nsum(s); if (nrc) return nrc; }
         tr.mark("enqueue h2d + pack");
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         tr.mark("sync");
@@ -312,6 +342,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create_pac
     rc = [&]() -> int {
         CUDA_TRY(cudaMemcpyAsync(s->d_pack2, pack2_host, s->pack2_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(s->d_nmask, nmask_host, s->nmask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        { int nrc = pav_build_nsum(s); if (nrc) return nrc; }
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return PAVGPU_OK;
     }();
@@ -326,6 +357,7 @@ extern "C" __attribute__((visibility("default"))) void pavgpu_seqstore_free(pavg
     cudaSetDevice(s->ctx->device);
     pav_dev_free(s->ctx, s->d_pack2);
     pav_dev_free(s->ctx, s->d_nmask);
+    pav_dev_free(s->ctx, s->d_nsum);
     pav_dev_free(s->ctx, s->d_off);
     pav_dev_free(s->ctx, s->d_len);
     delete s;
@@ -346,6 +378,41 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_planes(con
     if (d_nmask) *d_nmask = s->d_nmask;
     if (nmask_bytes) *nmask_bytes = s->nmask_bytes;
     return PAVGPU_OK;
+}
+
+// Order-independent checksum of the two planes: sum of (word * odd constant + word index) over all words, per plane, mod 2^64.
+__global__ void __launch_bounds__(256) plane_checksum_kernel(const uint64_t *__restrict__ pack2, const uint32_t *__restrict__ nmask, int64_t n_words,
+                                                             unsigned long long *__restrict__ out)
+{
+    unsigned long long a = 0, b = 0;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+        a += (pack2[w] ^ (unsigned long long)w) * 0x9E3779B97F4A7C15ull;
+        b += ((unsigned long long)nmask[w] ^ ((unsigned long long)w << 32)) * 0xC2B2AE3D27D4EB4Full;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_checksum(const pavgpu_seqstore *s, uint64_t sums_out[2])
+{
+    if (!s || !sums_out) { pav_set_error("seqstore_checksum: bad argument"); return PAVGPU_ERR_ARG; }
+    pavgpu_ctx *ctx = s->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CUDA_TRY(pav_dev_alloc_t(ctx, 2, &d));
+    int rc = [&]() -> int {
+        CUDA_TRY(cudaMemsetAsync(d, 0, 16, ctx->stream));
+        const int64_t n_words = s->total_bases / 32;
+        const int blocks = (int)std::min<int64_t>((n_words + 255) / 256, (int64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 16);
+        plane_checksum_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(s->d_pack2, s->d_nmask, n_words, d);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(sums_out, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return PAVGPU_OK;
+    }();
+    pav_dev_free(ctx, d);
+    return rc;
 }
 
 extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_export(const pavgpu_seqstore *s, uint64_t *pack2_host, uint32_t *nmask_host)

@@ -110,6 +110,12 @@ class SeqStore:
         _capi.check(_capi.lib().pavgpu_seqstore_export(self.handle, _capi.ptr(pack2), _capi.ptr(nmask)))
         return pack2, nmask
 
+    def checksum(self):
+        """(2-bit plane, mask plane) checksums computed on the device (``pavgpu_seqstore_checksum``)."""
+        out = np.zeros(2, dtype=np.uint64)
+        _capi.check(_capi.lib().pavgpu_seqstore_checksum(self.handle, _capi.ptr(out)), 'pavgpu_seqstore_checksum')
+        return int(out[0]), int(out[1])
+
     def offset(self, i):
         return int(_capi.lib().pavgpu_seqstore_offset(self.handle, i))
 

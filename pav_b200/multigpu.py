@@ -52,19 +52,34 @@ def merge_rows(parts, shard_index):
     return snv, indel
 
 
-def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_id=True, group=None, walk_fn=None):
+last_dist_stats = None   # per-call record of the last make_insdel_snv_calls_dist on this rank (timings, checksums)
+
+
+def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_id=True, group=None, walk_fn=None, verify_planes=True):
     """Distributed ``make_insdel_snv_calls``: call on every rank with the same arguments; rank 0 returns
     ``(df_snv, df_insdel)`` identical to the single-GPU result, the other ranks return ``None``.
 
+    Records are split over the ranks by longest-processing-time-first (the reference's analogue is the file-level split
+    ``CALL_BATCH = INDEX % 10``, rules/align.snakefile:163 / pavlib/cigarcall.py:21); rank 0 packs the reference and broadcasts the
+    packed planes with one NCCL broadcast; every rank then checks the planes in its HBM against rank 0's checksum
+    (``verify_planes``), walks its shard, and the rows are gathered on the host of rank 0 and formatted there.
+
     ``walk_fn(table, ref_arr, tig_arr) -> (snv, indel)`` replaces the device walk (CPU tests of the host
-    logic inject a checker here); by default the walk runs on this rank's GPU against the reference planes
-    broadcast from rank 0.
+    logic inject a checker here).
+
+    Failures before or during the collectives (no device, out of memory while packing, NCCL) are agreed on by all ranks first, so
+    every rank raises instead of some of them waiting in a broadcast forever; only errors of a rank's own walk (CIGAR errors) are
+    captured per rank and re-raised on rank 0 in table order.
     """
+    import time
+
     import torch.distributed as dist
+    global last_dist_stats
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n_rec = df_align.shape[0]
     if n_rec == 0:
         return (cigarcall._empty(cigarcall.SNV_COLUMNS), cigarcall._empty(cigarcall.INSDEL_COLUMNS)) if rank == 0 else None
+    t0 = time.perf_counter()
     full = cigarcall.AlignTable(df_align)
     span = None
     if 'END' in df_align.columns:
@@ -73,13 +88,13 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
     mine = df_align.iloc[shards[rank]]
     ref_fa, tig_fa = fasta.open_fasta(ref_fa_name), fasta.open_fasta(tig_fa_name)
     part = (np.zeros(0, device._capi.SNV_ROW), np.zeros(0, device._capi.INDEL_ROW))
+    stats = {'rank': rank, 'world': world, 'records': int(len(mine)), 'bcast_ms': 0.0, 'checksum': None, 'planes_verified': None}
     err = None
-    try:
-        if walk_fn is not None:
-            if len(mine):
-                t = cigarcall.AlignTable(mine)
-                part = walk_fn(t, [ref_fa.fetch_array(n) for n in t.ref_names], [tig_fa.fetch_array(n) for n in t.tig_names])
-        else:
+    ref_store = ctx = None
+    if walk_fn is None:
+        # ---- the reference planes: every rank takes part in the collectives or all of them raise together
+        setup_err, uid = None, [None]
+        try:
             ctx = device.get_context()
             names = list(full.ref_names)  # every rank holds the whole reference of this table, same order
             if rank == 0:
@@ -87,21 +102,54 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
                 uid = [device.nccl_unique_id()]
             else:
                 ref_store = device.SeqStore.from_packed(ctx, names, [ref_fa.length(n) for n in names], None, None)
-                uid = [None]
-            dist.broadcast_object_list(uid, src=0, group=group)
-            ref_store.broadcast(uid[0], rank, world)
-            try:
-                if len(mine):
-                    t = cigarcall.AlignTable(mine)
-                    # ids must index the broadcast store, not the shard-local name table
-                    t.ref_id = np.array([full.ref_names[str(c)] for c in t.chrom.tolist()], dtype=np.int32)
-                    part = cigarcall.walk_rows(t, None, [tig_fa.fetch_array(n) for n in t.tig_names], ctx=ctx, ref_store=ref_store)
-            finally:
+        except Exception as ex:  # noqa: BLE001
+            setup_err = f'rank {rank}: {type(ex).__name__}: {ex}'
+        flags = [None] * world
+        dist.all_gather_object(flags, setup_err, group=group)
+        if any(flags):
+            if ref_store is not None:
                 ref_store.close()
+            raise RuntimeError('make_insdel_snv_calls_dist: reference set-up failed: ' + '; '.join(f for f in flags if f))
+        dist.broadcast_object_list(uid, src=0, group=group)
+        bc_err = None
+        try:
+            stats['bcast_ms'] = ref_store.broadcast(uid[0], rank, world)
+            stats['checksum'] = ref_store.checksum() if verify_planes else None
+        except Exception as ex:  # noqa: BLE001
+            bc_err = f'rank {rank}: {type(ex).__name__}: {ex}'
+        sums = [None] * world
+        dist.all_gather_object(sums, (bc_err, stats['checksum']), group=group)
+        bad = [e for e, _ in sums if e]
+        if not bad and verify_planes:
+            bad = [f'rank {r}: planes {c} differ from rank 0 {sums[0][1]}' for r, (_, c) in enumerate(sums) if c != sums[0][1]]
+            stats['planes_verified'] = not bad
+        if bad:
+            ref_store.close()
+            raise RuntimeError('make_insdel_snv_calls_dist: reference broadcast failed: ' + '; '.join(bad))
+    t1 = time.perf_counter()
+    # ---- this rank's shard
+    try:
+        if len(mine):
+            t = cigarcall.AlignTable(mine)
+            if walk_fn is not None:
+                part = walk_fn(t, [ref_fa.fetch_array(n) for n in t.ref_names], [tig_fa.fetch_array(n) for n in t.tig_names])
+            else:
+                # ids must index the broadcast store, not the shard-local name table
+                t.ref_id = np.array([full.ref_names[str(c)] for c in t.chrom.tolist()], dtype=np.int32)
+                part = cigarcall.walk_rows(t, None, [tig_fa.fetch_array(n) for n in t.tig_names], ctx=ctx, ref_store=ref_store)
+                stats['walk'] = dict(cigarcall.last_stats) if cigarcall.last_stats else None
     except (RuntimeError, IndexError) as ex:  # CIGAR errors: first one in table order wins on rank 0
         err = (type(ex).__name__, str(ex))
+    finally:
+        if ref_store is not None:
+            ref_store.close()
+    t2 = time.perf_counter()
+    stats['rows'] = int(len(part[0]) + len(part[1]))
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((part, err), gathered, dst=0, group=group)
+    t3 = time.perf_counter()
+    stats['seconds'] = {'shard_plan_reference_broadcast': t1 - t0, 'walk_incl_contig_read': t2 - t1, 'gather': t3 - t2}
+    last_dist_stats = stats
     if rank != 0:
         return None
     errs = [(int(shards[r][0]) if len(shards[r]) else n_rec, e) for r, (_, e) in enumerate(gathered) if e is not None]
@@ -113,5 +161,7 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
     snv, indel = merge_rows([p for p, _ in gathered], shards)
     ref_arr = [ref_fa.fetch_array(n) for n in full.ref_names]
     tig_arr = [tig_fa.fetch_array(n) for n in full.tig_names]
-    return cigarcall.build_frames(snv, indel, full.chrom, full.qry, full.rev, full.align_index, ref_arr, tig_arr, full.ref_id,
-                                  full.qry_id, hap, version_id)
+    out = cigarcall.build_frames(snv, indel, full.chrom, full.qry, full.rev, full.align_index, ref_arr, tig_arr, full.ref_id,
+                                 full.qry_id, hap, version_id)
+    stats['seconds']['frames_rank0'] = time.perf_counter() - t3
+    return out

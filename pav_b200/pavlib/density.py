@@ -61,6 +61,23 @@ class DensityBatch:
         cols = [_capi.take_host_array(p.value, n, dt) for p, dt in zip(ptrs, dts)]
         return res, dict(zip(['KMER', 'INDEX', 'STATE_MER', 'STATE', 'KERN_FWD', 'KERN_FWDREV', 'KERN_REV'], cols))
 
+    def fetch_runs(self):
+        """Run lengths of STATE per window (``pavgpu_density_batch_fetch_runs``): ``(res, runs, run_off)``."""
+        n_win = len(self.windows)
+        res = np.zeros(n_win, dtype=_capi.DENSITY_RESULT)
+        run_off = np.zeros(n_win + 1, dtype=np.int64)
+        p, n = _capi.c_vp(), _capi.c_i64()
+        _capi.check(_capi.lib().pavgpu_density_batch_fetch_runs(self.handle, _capi.ptr(res), ctypes.byref(p), _capi.ptr(run_off), ctypes.byref(n)),
+                    'pavgpu_density_batch_fetch_runs')
+        return res, _capi.take_host_array(p.value, n.value, _capi.STATE_RUN), run_off
+
+    def fetch_window(self, win, n_rows):
+        """All columns of one window (``pavgpu_density_batch_fetch_window``)."""
+        dts = [np.uint64, np.int32, np.int8, np.int8, np.float64, np.float64, np.float64]
+        cols = [np.empty(n_rows, dtype=dt) for dt in dts]
+        _capi.check(_capi.lib().pavgpu_density_batch_fetch_window(self.handle, int(win), *[_capi.ptr(c) for c in cols]), 'pavgpu_density_batch_fetch_window')
+        return dict(zip(['KMER', 'INDEX', 'STATE_MER', 'STATE', 'KERN_FWD', 'KERN_FWDREV', 'KERN_REV'], cols))
+
     def close(self):
         if getattr(self, 'handle', None):
             _capi.lib().pavgpu_density_batch_free(self.handle)
@@ -77,17 +94,52 @@ def _split(res, cols):
     out = []
     for r in res:
         a, b = int(r['row_off']), int(r['row_off'] + r['n_rows'])
-        d = {'status': int(r['status']), 'smoothed': bool(r['smoothed']), 'n_eval': int(r['n_eval'])}
+        d = {'status': int(r['status']), 'smoothed': bool(r['smoothed']), 'n_eval': int(r['n_eval']), 'n_rows': int(r['n_rows'])}
         for k, v in cols.items():
             d[k] = v[a:b]
         out.append(d)
     return out
 
 
-def density_windows(windows, k=31, ctx=None, **kw):
+class _OpenBatch:
+    """A scored batch kept on the device for as long as one of its ``LazyWindow`` results is alive."""
+
+    def __init__(self, batch, stores):
+        self.batch, self.stores = batch, stores
+
+    def __del__(self):
+        try:
+            self.batch.close()
+            for s in self.stores:
+                s.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class LazyWindow(dict):
+    """Result of one window scored with ``density_windows(..., lazy=True)``: status, row count and the run lengths of STATE come
+    back with the batch (16 bytes per run); the column arrays -- 38 bytes per row -- stay in HBM and are copied the first time one
+    of them is asked for, which the inversion scan does only for the window that becomes a call."""
+
+    _COLS = ('KMER', 'INDEX', 'STATE_MER', 'STATE', 'KERN_FWD', 'KERN_FWDREV', 'KERN_REV')
+
+    def __init__(self, base, owner, win):
+        super().__init__(base)
+        self._owner, self._win = owner, win
+
+    def __missing__(self, key):
+        if key not in self._COLS:
+            raise KeyError(key)
+        self.update(self._owner.batch.fetch_window(self._win, self['n_rows']))
+        self._owner = None
+        return dict.__getitem__(self, key)
+
+
+def density_windows(windows, k=31, ctx=None, lazy=False, **kw):
     """Score in-memory windows: ``windows`` = iterable of ``(ref uint8 array, tig uint8 array, rev, srs)``.
 
-    Returns one dict per window: ``status`` (0 / 125), ``smoothed``, ``n_eval`` and the column arrays.
+    Returns one dict per window: ``status`` (0 / 125), ``smoothed``, ``n_eval``, ``n_rows``, ``runs`` (``rl_encoder`` tuples of STATE
+    as a structured array) and the column arrays. ``lazy=True``: the columns are fetched per window on first access (``LazyWindow``).
     """
     global last_stats
     ctx = ctx or device.get_context()
@@ -95,7 +147,7 @@ def density_windows(windows, k=31, ctx=None, **kw):
     if len(windows) > MAX_WINDOWS_PER_BATCH:   # bound the device arena and the pinned result buffers (~5 MB + ~2 MB per 50 kbp window)
         out = []
         for a in range(0, len(windows), MAX_WINDOWS_PER_BATCH):
-            out.extend(density_windows(windows[a:a + MAX_WINDOWS_PER_BATCH], k=k, ctx=ctx, **kw))
+            out.extend(density_windows(windows[a:a + MAX_WINDOWS_PER_BATCH], k=k, ctx=ctx, lazy=lazy, **kw))
         return out
     refs = [np.ascontiguousarray(w[0], dtype=np.uint8) for w in windows]
     tigs = [np.ascontiguousarray(w[1], dtype=np.uint8) for w in windows]
@@ -104,6 +156,7 @@ def density_windows(windows, k=31, ctx=None, **kw):
     rs = device.SeqStore(ctx, [f'r{i}' for i in range(len(refs))], refs, keep_host=False)
     ts = device.SeqStore(ctx, [f't{i}' for i in range(len(tigs))], tigs, keep_host=False)
     t1 = time.perf_counter()
+    keep = False
     try:
         win = np.zeros(len(windows), dtype=_capi.DENSITY_WINDOW)
         win['ref_seq_id'] = win['tig_seq_id'] = np.arange(len(windows))
@@ -116,14 +169,29 @@ def density_windows(windows, k=31, ctx=None, **kw):
         try:
             st = batch.run(rs, ts)
             t3 = time.perf_counter()
-            res, cols = batch.fetch()
+            res, runs, run_off = batch.fetch_runs()
+            if lazy:
+                owner = _OpenBatch(batch, (rs, ts))
+                keep = True
+                out = []
+                for i, r in enumerate(res):
+                    base = {'status': int(r['status']), 'smoothed': bool(r['smoothed']), 'n_eval': int(r['n_eval']), 'n_rows': int(r['n_rows']),
+                            'runs': runs[run_off[i]:run_off[i + 1]], '_tig': tigs[i], '_k': int(k)}
+                    out.append(LazyWindow(base, owner, i))
+            else:
+                res, cols = batch.fetch()
+                out = _split(res, cols)
+                for i, d in enumerate(out):
+                    d['runs'] = runs[run_off[i]:run_off[i + 1]]
+                    d['_tig'], d['_k'] = tigs[i], int(k)
             t4 = time.perf_counter()
         finally:
-            batch.close()
+            if not keep:
+                batch.close()
     finally:
-        rs.close()
-        ts.close()
-    out = _split(res, cols)
+        if not keep:
+            rs.close()
+            ts.close()
     last_stats = st.as_dict()
     last_stats['seconds'] = {'stores': t1 - t0, 'batch_create': t2 - t1, 'run': t3 - t2, 'fetch': t4 - t3, 'split': time.perf_counter() - t4}
     return out
@@ -143,11 +211,30 @@ def frame_from_result(d, extra=None):
             cols[name] = pd.Series(arr, index=ix, dtype=object)
         return pd.DataFrame(cols, columns=SMOOTHED_COLUMNS + list(extra or ()), index=ix)
     assert not extra
-    # fewer than --mininf informative k-mers: frame returned before smoothing (density.py:193-194)
+    # fewer than --mininf informative k-mers: frame returned before smoothing (density.py:193-194). It is the k-mer stream's frame
+    # with rows filtered out (:161-190), so its row labels are the positions of the kept k-mers in the stream of valid k-mers
+    index = None
+    if d.get('_tig') is not None:
+        index = pd.Index(stream_ordinals(d['_tig'], d['_k'], d['INDEX']))
     return pd.DataFrame({
         'KMER': d['KMER'].astype(np.int64), 'INDEX': d['INDEX'].astype(np.int64), 'STATE': d['STATE'].astype(np.int64),
         'STATE_MER': d['STATE_MER'].astype(np.int64),
-    }, columns=RAW_COLUMNS)
+    }, columns=RAW_COLUMNS, index=index)
+
+
+_IS_ACGT = np.zeros(256, dtype=bool)
+_IS_ACGT[list(b'ACGTacgt')] = True
+
+
+def stream_ordinals(tig, k, index):
+    """Position of the k-mers starting at window offsets ``index`` in the stream of valid k-mers of ``tig`` (kanapy's ``stream``
+    emits one k-mer per offset whose k bases are all ACGTacgt, kmer.py:206-221): the row labels of the reference's raw frame."""
+    bad = np.concatenate(([0], np.cumsum(~_IS_ACGT[np.asarray(tig, dtype=np.uint8)])))
+    n_pos = len(tig) - k + 1
+    if n_pos <= 0:
+        return np.zeros(0, dtype=np.int64)
+    valid = (bad[k:k + n_pos] - bad[:n_pos]) == 0
+    return (np.cumsum(valid) - 1)[np.asarray(index, dtype=np.int64)].astype(np.int64)
 
 
 class DensityTable:
@@ -160,10 +247,16 @@ class DensityTable:
 
     @property
     def shape(self):
-        return (len(self.res['INDEX']), len(SMOOTHED_COLUMNS) if self.res['smoothed'] else len(RAW_COLUMNS))
+        n = self.res['n_rows'] if 'n_rows' in self.res else len(self.res['INDEX'])
+        return (n, len(SMOOTHED_COLUMNS) if self.res['smoothed'] else len(RAW_COLUMNS))
 
     def rl(self):
-        """``rl_encoder(frame)`` straight from the column arrays."""
+        """``rl_encoder(frame)``: from the run lengths the device computed, else straight from the column arrays."""
+        runs = self.res.get('runs')
+        if runs is not None:
+            for r in runs.tolist():
+                yield r
+            return
         ix = self.res['INDEX']
         st = self.res['STATE'] if self.res['smoothed'] else np.full(len(ix), -1, dtype=np.int8)
         n = len(st)

@@ -325,7 +325,8 @@ def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_uti
             pending.append(sc)
         if not pending:
             break
-        results = pavdensity.density_windows(windows, k=k_size, min_informative=MIN_INFORMATIVE_KMERS,
+        # lazy: run lengths of STATE for every window; full columns only for the windows that become calls
+        results = pavdensity.density_windows(windows, k=k_size, lazy=True, min_informative=MIN_INFORMATIVE_KMERS,
                                              min_state_count=MIN_KMER_STATE_COUNT, smooth=DENSITY_SMOOTH_FACTOR)
         for sc, res in zip(pending, results):
             try:

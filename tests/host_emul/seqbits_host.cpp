@@ -34,6 +34,9 @@ static inline int __clzll(long long x) { return x == 0 ? 64 : __builtin_clzll((u
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 
+#ifndef HOM_BATCH_LOADS
+#define HOM_BATCH_LOADS 1   // the host build exercises the batched-window forms too (EMU_BATCH=0 builds the plain ones)
+#endif
 #include "seqbits.cuh"
 
 extern "C" {
@@ -50,13 +53,13 @@ void emu_pack(const uint8_t *ascii, int64_t n_words, uint64_t *pack2, uint32_t *
 
 int emu_base(const uint64_t *pack2, const uint32_t *nmask, int64_t base, int64_t len, int rev, int64_t t)
 {
-    const OSeq s{pack2, nmask, base, len, rev, nullptr, nullptr, 0, 0};
+    const OSeq s{pack2, nmask, base, len, rev, nullptr, nullptr, 0, 0, nullptr};
     return oseq_base(s, t);
 }
 
 void emu_window(const uint64_t *pack2, const uint32_t *nmask, int64_t base, int64_t len, int rev, int32_t t, uint64_t *bases, uint32_t *mask)
 {
-    const OSeq s{pack2, nmask, base, len, rev, nullptr, nullptr, 0, 0};
+    const OSeq s{pack2, nmask, base, len, rev, nullptr, nullptr, 0, 0, nullptr};
     oseq_window(s, t, *bases, *mask);
 }
 
@@ -72,12 +75,13 @@ int emu_homology(const uint64_t *pack2, const uint32_t *nmask, int64_t t_base, i
 // qry_end, left_shift, hom_ref_l, hom_ref_r, hom_tig_l, hom_tig_r, seq_start.
 void emu_score_indel(const uint64_t *r_pack2, const uint32_t *r_nmask, int64_t r_base, int64_t r_len, const uint64_t *q_pack2,
                      const uint32_t *q_nmask, int64_t q_base, int64_t q_len, int q_rev, int32_t svtype, int32_t n, int32_t pr, int32_t pq,
-                     int32_t eqb, int64_t r_w0, int32_t r_tile_words, int64_t q_w0, int32_t q_tile_words, int32_t version, int32_t *out)
+                     int32_t eqb, int64_t r_w0, int32_t r_tile_words, int64_t q_w0, int32_t q_tile_words, int32_t version,
+                     const uint32_t *r_nsum, const uint32_t *q_nsum, int32_t *out)
 {
     IndelScore o;
     if (r_tile_words <= 0 && q_tile_words <= 0) {
-        const OSeq R{r_pack2, r_nmask, r_base, r_len, 0, nullptr, nullptr, 0, 0};
-        const OSeq Q{q_pack2, q_nmask, q_base, q_len, q_rev, nullptr, nullptr, 0, 0};
+        const OSeq R{r_pack2, r_nmask, r_base, r_len, 0, nullptr, nullptr, 0, 0, r_nsum};     // N summaries optional (nullptr: masks always read)
+        const OSeq Q{q_pack2, q_nmask, q_base, q_len, q_rev, nullptr, nullptr, 0, 0, q_nsum};
         if (version == 2) score_indel2<false>(R, Q, svtype, n, pr, pq, eqb, o);
         else score_indel<false>(R, Q, svtype, n, pr, pq, eqb, o);
     } else {
@@ -86,8 +90,8 @@ void emu_score_indel(const uint64_t *r_pack2, const uint32_t *r_nmask, int64_t r
         std::vector<uint32_t> tm_r(std::max(r_tile_words, 1)), tm_q(std::max(q_tile_words, 1));
         for (int k = 0; k < r_tile_words; k++) { tp_r[k] = r_pack2[r_w0 + k]; tm_r[k] = r_nmask[r_w0 + k]; }
         for (int k = 0; k < q_tile_words; k++) { tp_q[k] = q_pack2[q_w0 + k]; tm_q[k] = q_nmask[q_w0 + k]; }
-        const OSeq R{r_pack2, r_nmask, r_base, r_len, 0, tp_r.data(), tm_r.data(), r_w0, std::max(r_tile_words - 1, 0)};
-        const OSeq Q{q_pack2, q_nmask, q_base, q_len, q_rev, tp_q.data(), tm_q.data(), q_w0, std::max(q_tile_words - 1, 0)};
+        const OSeq R{r_pack2, r_nmask, r_base, r_len, 0, tp_r.data(), tm_r.data(), r_w0, std::max(r_tile_words - 1, 0), nullptr};
+        const OSeq Q{q_pack2, q_nmask, q_base, q_len, q_rev, tp_q.data(), tm_q.data(), q_w0, std::max(q_tile_words - 1, 0), nullptr};
         if (version == 2) score_indel2<true>(R, Q, svtype, n, pr, pq, eqb, o);
         else score_indel<true>(R, Q, svtype, n, pr, pq, eqb, o);
     }
@@ -95,12 +99,20 @@ void emu_score_indel(const uint64_t *r_pack2, const uint32_t *r_nmask, int64_t r
     out[5] = o.hom_rl; out[6] = o.hom_rr; out[7] = o.hom_tl; out[8] = o.hom_tr; out[9] = o.seq_start;
 }
 
+// N summary of a mask plane with nsum_kernel's layout: bit (w >> 3) & 31 of word w >> 8 set when mask word w is non-zero.
+void emu_nsum(const uint32_t *nmask, int64_t n_words, uint32_t *nsum)
+{
+    for (int64_t w = 0; w < n_words; w++)
+        if (nmask[w]) nsum[w >> 8] |= 1u << ((w >> 3) & 31);
+}
+
 // k-mers of a window the way ref_insert_kernel / tig_state_kernel read them: valid[i] = kmer_at(g0 + i), kmer[i], rc[i].
-void emu_kmers(const uint64_t *pack2, const uint32_t *nmask, int64_t g0, int32_t n_pos, int k, uint64_t *kmer, uint64_t *rc, uint8_t *valid)
+void emu_kmers(const uint64_t *pack2, const uint32_t *nmask, int64_t g0, int32_t n_pos, int k, uint64_t *kmer, uint64_t *rc, uint8_t *valid,
+               const uint32_t *nsum)
 {
     for (int32_t i = 0; i < n_pos; i++) {
         uint64_t x = 0;
-        valid[i] = kmer_at(pack2, nmask, g0 + i, k, x) ? 1 : 0;
+        valid[i] = kmer_at(pack2, nmask, g0 + i, k, x, nsum) ? 1 : 0;
         kmer[i] = valid[i] ? x : 0;
         rc[i] = valid[i] ? kmer_revcomp(x, k) : 0;
     }

@@ -8,9 +8,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    out = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--contigs', '8', '--contig-len', '20000',
-                          '--steps', '1', '--warmup', '0', '--cpu-sample-contigs', '8'], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                         timeout=300, cwd=REPO)
+    out = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--scale', '0.004', '--steps', '1', '--warmup', '0',
+                          '--cpu-sample-records', '2', '--cpu-density-windows', '1'], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         timeout=600, cwd=REPO)
     assert out.returncode == 0, out.stderr.decode()[-2000:]
     lines = [ln for ln in out.stdout.decode().splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -19,6 +19,10 @@ def test_reference_arm_json_line():
               'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
         assert k in d, k
     assert d['impl'] == 'reference' and d['value'] > 0 and d['higher_is_better'] is True
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['kind'] == 'reference' and d['cpu_baseline']['cores'] >= 1      # the unmodified reference (oracle/_ref or /root/reference)
+    assert d['config']['workload'].startswith('C3') and d['scaling'] == 'strong'
+    sec = d['secondary']                                                                       # Path B: scripts/density.py per window
+    assert sec['metric'] == 'inv_kmer_density_gbases_per_sec' and sec['value'] > 0 and sec['cpu_baseline']['kind'] == 'reference'
+    assert sec['cpu_baseline']['startup_seconds_per_process'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']

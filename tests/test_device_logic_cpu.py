@@ -35,8 +35,9 @@ def emu():
     L.emu_base.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i64]
     L.emu_window.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i32, c_vp, c_vp]
     L.emu_homology.argtypes = [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_i64, c_i64, c_i64, ctypes.c_int, c_i64, ctypes.c_int, ctypes.c_int]
-    L.emu_score_indel.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, ctypes.c_int] + [c_i32] * 5 + [c_i64, c_i32, c_i64, c_i32, c_i32, c_vp]
-    L.emu_kmers.argtypes = [c_vp, c_vp, c_i64, c_i32, ctypes.c_int, c_vp, c_vp, c_vp]
+    L.emu_score_indel.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, ctypes.c_int] + [c_i32] * 5 + [c_i64, c_i32, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]
+    L.emu_kmers.argtypes = [c_vp, c_vp, c_i64, c_i32, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]
+    L.emu_nsum.argtypes = [c_vp, c_i64, c_vp]
     L.emu_nbr_first_word.argtypes = [c_i64, c_i64]
     L.emu_nbr_first_word.restype = c_i64
     L.emu_tile_range.argtypes = [c_i64, c_i64, c_i64, c_vp, c_vp]
@@ -61,6 +62,8 @@ class Planes:
         self.pack2 = np.zeros(self.words, np.uint64)
         self.nmask = np.zeros(self.words, np.uint32)
         emu.emu_pack(self.ascii.ctypes.data, self.words, self.pack2.ctypes.data, self.nmask.ctypes.data)
+        self.nsum = np.zeros((self.words + 1) // 256 + 2, np.uint32)     # N summary as pavgpu_seqstore sizes it
+        emu.emu_nsum(self.nmask.ctypes.data, self.words, self.nsum.ctypes.data)
 
     def p(self):
         return self.pack2.ctypes.data, self.nmask.ctypes.data
@@ -209,8 +212,10 @@ def test_score_indel_matches_oracle(emu, tmp_path, seed, kw):
         tiles.append((max((cr >> 5) - 3, 0), min(7, R.words - max((cr >> 5) - 3, 0)), 0, 0))      # reference staged, contig not
         for w0r, nr, w0q, nq in tiles:
             for version in (1, 2):
-                emu.emu_score_indel(rp, rm, R.off[ri], rl, qp, qm, Q.off[qi], ql, rev, svtype, n, pr, pq, eqb, w0r, nr, w0q, nq, version, out)
-                assert list(out)[:9] == want, (version, k, rec, svtype, n, pr, pq, eqb, (w0r, nr, w0q, nq))
+                for sums in ((None, None), (R.nsum.ctypes.data, Q.nsum.ctypes.data)) if nr == 0 and nq == 0 else ((None, None),):   # with / without N summaries
+                    emu.emu_score_indel(rp, rm, R.off[ri], rl, qp, qm, Q.off[qi], ql, rev, svtype, n, pr, pq, eqb, w0r, nr, w0q, nq, version,
+                                        sums[0], sums[1], out)
+                    assert list(out)[:9] == want, (version, sums[0] is not None, k, rec, svtype, n, pr, pq, eqb, (w0r, nr, w0q, nq))
 
 
 def test_kmers_from_planes(emu):
@@ -226,7 +231,10 @@ def test_kmers_from_planes(emu):
     for k in (31, 21, 5):
         n_pos = len(s) - k + 1
         km = np.zeros(n_pos, np.uint64); rc = np.zeros(n_pos, np.uint64); ok = np.zeros(n_pos, np.uint8)
-        emu.emu_kmers(pp, pm, pl.off[1], n_pos, k, km.ctypes.data, rc.ctypes.data, ok.ctypes.data)
+        emu.emu_kmers(pp, pm, pl.off[1], n_pos, k, km.ctypes.data, rc.ctypes.data, ok.ctypes.data, None)
+        km2 = np.zeros(n_pos, np.uint64); rc2 = np.zeros(n_pos, np.uint64); ok2 = np.zeros(n_pos, np.uint8)
+        emu.emu_kmers(pp, pm, pl.off[1], n_pos, k, km2.ctypes.data, rc2.ctypes.data, ok2.ctypes.data, pl.nsum.ctypes.data)   # mask loads skipped where the summary is clear
+        assert (km2 == km).all() and (rc2 == rc).all() and (ok2 == ok).all()
         want_km, want_ix = pyoracle.kmer_stream(s.tobytes(), k)
         assert (np.flatnonzero(ok) == want_ix).all()
         assert (km[ok == 1] == want_km).all()

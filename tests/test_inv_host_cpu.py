@@ -25,7 +25,7 @@ def oracle_density(monkeypatch):
     from oracle import pyoracle
     from pav_b200.pavlib import density
 
-    def density_windows(windows, k=31, ctx=None, min_informative=2000, min_state_count=20, smooth=1.0, delta=0.005, max_ref_kmer_count=100):
+    def density_windows(windows, k=31, ctx=None, lazy=False, min_informative=2000, min_state_count=20, smooth=1.0, delta=0.005, max_ref_kmer_count=100):
         assert max_ref_kmer_count == 100
         out = []
         for ref, tig, rev, srs in windows:
