@@ -73,9 +73,11 @@ int pavgpu_l2_flush(pavgpu_ctx *ctx, size_t bytes);
  */
 int pavgpu_seqstore_create(pavgpu_ctx *ctx, int32_t n_seq, const uint8_t *const *seq_ascii,
                            const int64_t *seq_len, pavgpu_seqstore **store_out);
-/* Build from already packed planes (the payload of the multi-GPU reference broadcast). */
+/* Build from already packed planes (a packed-reference sidecar, pav_b200/sidecar.py). The byte sizes of the caller's buffers are
+ * checked against the layout this library derives from seq_len (PAVGPU_ERR_ARG on a mismatch: planes written under another
+ * alignment / guard layout, or a truncated file). */
 int pavgpu_seqstore_create_packed(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len,
-                                  const uint64_t *pack2_host, const uint32_t *nmask_host,
+                                  const uint64_t *pack2_host, size_t pack2_bytes, const uint32_t *nmask_host, size_t nmask_bytes,
                                   pavgpu_seqstore **store_out);
 /* Allocate planes for n_seq sequences without filling them (receiver side of a device broadcast). */
 int pavgpu_seqstore_create_empty(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len,
@@ -188,7 +190,7 @@ typedef struct {
 } pavgpu_density_window;
 
 typedef struct {
-    int32_t k;                  /* -k (<= 32 on the GPU path; larger raises) */
+    int32_t k;                  /* -k: 1 <= k <= 31 on the GPU path (exact 62-bit keys, all-ones is the empty-slot sentinel); larger k fails with PAVGPU_ERR_ARG */
     int32_t min_informative;    /* --mininf 2000 */
     int32_t min_state_count;    /* --minstatecount 20 */
     int32_t max_ref_kmer_count; /* MAX_REF_KMER_COUNT 100 (density.py:47) */
@@ -209,6 +211,7 @@ typedef struct {
     float ms_kmer, ms_kde, ms_fill;
     int64_t bases, rows, kde_pairs;
     int32_t kernel_launches;
+    int32_t kmer_tables_on_chip;   /* 1: reference k-mer tables lived in the distributed shared memory of one cluster per window */
 } pavgpu_density_stats;
 
 void pavgpu_density_default_params(pavgpu_density_params *p);

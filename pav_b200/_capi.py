@@ -52,7 +52,8 @@ class DensityParams(ctypes.Structure):
 
 class DensityStats(ctypes.Structure):
     _fields_ = [('ms_h2d', c_f32), ('ms_kernels', c_f32), ('ms_d2h', c_f32), ('ms_kmer', c_f32), ('ms_kde', c_f32),
-                ('ms_fill', c_f32), ('bases', c_i64), ('rows', c_i64), ('kde_pairs', c_i64), ('kernel_launches', c_i32)]
+                ('ms_fill', c_f32), ('bases', c_i64), ('rows', c_i64), ('kde_pairs', c_i64), ('kernel_launches', c_i32),
+                ('kmer_tables_on_chip', c_i32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -96,7 +97,7 @@ def lib():
     L.pavgpu_free_host.restype = None
     L.pavgpu_l2_flush.argtypes = [c_vp, ctypes.c_size_t]
     L.pavgpu_seqstore_create.argtypes = [c_vp, c_i32, P(c_vp), P(c_i64), P(c_vp)]
-    L.pavgpu_seqstore_create_packed.argtypes = [c_vp, c_i32, P(c_i64), c_vp, c_vp, P(c_vp)]
+    L.pavgpu_seqstore_create_packed.argtypes = [c_vp, c_i32, P(c_i64), c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, P(c_vp)]
     L.pavgpu_seqstore_create_empty.argtypes = [c_vp, c_i32, P(c_i64), P(c_vp)]
     L.pavgpu_seqstore_free.argtypes = [c_vp]
     L.pavgpu_seqstore_free.restype = None

@@ -984,6 +984,9 @@ __device__ __forceinline__ void queue_push(bool flag, uint16_t item, uint16_t *q
 #ifndef HOMQ_MIN_BLOCKS
 #define HOMQ_MIN_BLOCKS 4
 #endif
+#ifndef HOMQ_PREFETCH
+#define HOMQ_PREFETCH 0
+#endif
 #ifndef HOMQ_COOP
 #define HOMQ_COOP 8      // lanes that share one pooled scan rest in round B (round A: a whole warp per item)
 #endif
@@ -1001,6 +1004,15 @@ homology_queue_kernel(const IndelStub *__restrict__ stubs, int64_t n_indel, SeqP
     if (tid < 2) s_cnt[tid] = 0;
     const StubView v = load_stub(stubs, live ? i : n_indel - 1, ref, qry);
     const bool ins = v.svtype == 0;
+#if HOMQ_PREFETCH
+    {   // the sectors around both breakpoints are asked for (into L2) before the first scan waits for any of them
+        const int64_t gr = v.R.base + v.pr, gq = v.Q.base + (v.Q.rev ? v.Q.len - 1 - v.pq : v.pq);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ref.pack2 + (gr >> 5)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ref.nmask + (gr >> 5)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qry.pack2 + (gq >> 5)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qry.nmask + (gq >> 5)));
+    }
+#endif
     // ---- round A: left shift
     int h0 = indel_phase0<false>(v.R, v.Q, ins, v.n, v.pr, v.pq);
     if (v.eqb <= 0 || !live) h0 = 0;
@@ -1374,7 +1386,7 @@ constexpr int64_t HOM_TILED_MIN_INDELS = 4096;
 // PAVGPU_HOMOLOGY_NBR=1 still work). 0 gathers, 1 warp tiles, 2 per-indel neighbourhoods (cp.async), 3 per-indel neighbourhoods
 // (bulk copies + mbarrier), 4 gathers with CTA-pooled scan rests (queue).
 #ifndef HOM_DEFAULT_KERNEL
-#define HOM_DEFAULT_KERNEL 0
+#define HOM_DEFAULT_KERNEL 4     // CTA-pooled rests: 0.073 ms on C2 against 0.094 (gathers), 0.087 (split), 0.112-0.130 (bulk) -- DESIGN.md 6.1
 #endif
 
 static int homology_choice(const pavgpu_cigar_batch *b)

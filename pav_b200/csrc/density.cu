@@ -32,7 +32,11 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -70,6 +74,8 @@ struct WinCounts {  // written by D1 / D2
     unsigned long long ref_valid;
     unsigned int ref_max;
     unsigned int cnt[3];
+    unsigned int overflow;        // kmer_cluster_kernel: a table partition filled up (the batch is redone with the global tables)
+    unsigned int pad;
 };
 
 struct KdeParams {  // per window, written by D4
@@ -167,6 +173,125 @@ tig_state_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes t
         if (c1) atomicAdd(&wc[w].cnt[1], c1);
         if (c2) atomicAdd(&wc[w].cnt[2], c2);
     }
+}
+
+// D1 + D2 on chip --------------------------------------------------------------------------------------
+// One thread-block cluster of 8 CTAs per window; the window's reference k-mer table lives in the DISTRIBUTED SHARED MEMORY of
+// the cluster -- 8 x 16,384 slots of 8-byte keys + 16-bit counts = 160 KB per CTA -- and never touches L2 or HBM. The hash of a
+// k-mer picks the owning CTA (top 3 bits) and the slot inside it (next 14 bits; linear probing stays inside the owner's part);
+// inserts are remote shared-memory atomics (CAS on the key, add on the packed count), probes remote shared-memory loads. Every
+// position of the window is k-merised once (CTA r takes positions r * 1024 + t, stride 8,192 -- no redundant arithmetic), and
+// the contig pass keeps tig_state_kernel's tile structure so its outputs (state per position, counts per 1,024-position tile)
+// feed the same compaction. ncu on the global-table kernels (profiles/r02_ncu_density_296win.txt): ref_insert 0.52 ms moving
+// 810 MB of DRAM sectors for 14.8 M inserts into 444 MB of tables (plus their memsets), tig_state 0.31 ms.
+// Opt-in (PAVGPU_DENSITY_CLUSTER_TABLES=1) for batches whose windows all have at most KC_MAX_REF reference k-mers (load factor
+// <= 0.5); larger windows, or a partition that fills up (flagged in WinCounts.overflow), take the global-table kernels. Measured
+// slower than them on B200 (1.42 ms against 0.81 ms for 296 windows x 50 kbp): see the note at the launch site.
+constexpr int KC_CLUSTER = 8;
+constexpr int KC_THREADS = 1024;
+constexpr int KC_LOG2_SLOTS = 14;
+constexpr int KC_SLOTS = 1 << KC_LOG2_SLOTS;                 // per CTA
+constexpr int KC_MAX_REF = KC_CLUSTER * KC_SLOTS / 2;        // 65,536 reference k-mers per window
+constexpr size_t KC_SMEM = (size_t)KC_SLOTS * 8 + (size_t)KC_SLOTS * 2;
+static_assert(KC_CLUSTER == 8, "the owner is the top three hash bits");
+
+__device__ __forceinline__ void kc_locate(uint64_t kmer, unsigned &owner, unsigned &slot)
+{
+    const uint64_t h = kmer * 0x9E3779B97F4A7C15ull;
+    owner = (unsigned)(h >> 61);
+    slot = (unsigned)(h >> (61 - KC_LOG2_SLOTS)) & (KC_SLOTS - 1);
+}
+
+__device__ __forceinline__ bool kc_has(cg::cluster_group &cluster, uint64_t *keys, uint64_t key)
+{
+    unsigned owner, slot;
+    kc_locate(key, owner, slot);
+    const uint64_t *rk = cluster.map_shared_rank(keys, owner);
+    for (int probe = 0; probe < KC_SLOTS; probe++) {
+        const uint64_t v = rk[slot];
+        if (v == key) return true;
+        if (v == EMPTY_KEY) return false;
+        slot = (slot + 1) & (KC_SLOTS - 1);
+    }
+    return false;
+}
+
+__global__ void __cluster_dims__(KC_CLUSTER, 1, 1) __launch_bounds__(KC_THREADS, 1)
+kmer_cluster_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes ref, SeqPlanes tig, int k, int8_t *__restrict__ st_pos,
+                    uint32_t *__restrict__ tile_cnt, WinCounts *__restrict__ wc)
+{
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(kc_smem);
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(kc_smem + (size_t)KC_SLOTS * 8);   // two 16-bit counts per word
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank();
+    const int32_t w = win_base + (int32_t)(blockIdx.x / KC_CLUSTER);
+    const WinPlan P = plan[w];
+    for (int i = threadIdx.x; i < KC_SLOTS; i += KC_THREADS) keys[i] = EMPTY_KEY;
+    for (int i = threadIdx.x; i < KC_SLOTS / 2; i += KC_THREADS) cnt32[i] = 0u;
+    cluster.sync();
+    // ---- reference k-mers -> the cluster's table
+    const int32_t n_ref = P.ref_len - k + 1;
+    unsigned n_valid = 0, my_max = 0, over = 0;
+    for (int32_t i = (int32_t)crank * KC_THREADS + threadIdx.x; i < n_ref; i += KC_CLUSTER * KC_THREADS) {
+        uint64_t kmer;
+        if (!kmer_at(ref.pack2, ref.nmask, P.ref_g0 + i, k, kmer, ref.nsum)) continue;
+        n_valid++;
+        if (P.rev) kmer = kmer_revcomp(kmer, k);  // density.py:538-539: the reference SET is reverse-complemented
+        unsigned owner, slot;
+        kc_locate(kmer, owner, slot);
+        uint64_t *rk = cluster.map_shared_rank(keys, owner);
+        uint32_t *rc = cluster.map_shared_rank(cnt32, owner);
+        bool placed = false;
+        for (int probe = 0; probe < KC_SLOTS; probe++) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(rk + slot), (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
+            if (old == EMPTY_KEY || old == kmer) {
+                const unsigned sh = 16u * (slot & 1u);
+                const unsigned c = ((atomicAdd(rc + (slot >> 1), 1u << sh) >> sh) & 0xffffu) + 1u;   // (a window has <= 65,536 reference k-mers: no carry)
+                my_max = max(my_max, c);
+                placed = true;
+                break;
+            }
+            slot = (slot + 1) & (KC_SLOTS - 1);
+        }
+        if (!placed) over = 1;
+    }
+    {
+        const unsigned nv = __reduce_add_sync(FULL, n_valid), mx = __reduce_max_sync(FULL, my_max), ov = __reduce_or_sync(FULL, over);
+        if ((threadIdx.x & 31) == 0) {
+            if (nv) atomicAdd(&wc[w].ref_valid, (unsigned long long)nv);
+            if (mx) atomicMax(&wc[w].ref_max, mx);
+            if (ov) atomicOr(&wc[w].overflow, 1u);
+        }
+    }
+    cluster.sync();   // every insert of the cluster has landed
+    // ---- contig k-mers: state per position, counts per 1,024-position tile (tile t is CTA t % 8's)
+    const int32_t n_pos = P.tig_len - k + 1;
+    const int32_t n_tiles = (max(n_pos, 0) + TILE - 1) / TILE;
+    for (int32_t t = (int32_t)crank; t < n_tiles; t += KC_CLUSTER) {
+        const int32_t i = t * TILE + threadIdx.x;
+        int st = -1;
+        if (i < n_pos) {
+            uint64_t kmer;
+            if (kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer, tig.nsum)) {
+                const bool f = kc_has(cluster, keys, kmer);
+                const bool r = kc_has(cluster, keys, kmer_revcomp(kmer, k));
+                st = f ? (r ? 1 : 0) : (r ? 2 : -1);  // KMER_ORIENTATION_STATE, density.py:38-43
+            }
+            st_pos[P.pos_off + i] = (int8_t)st;
+        }
+        const unsigned c0 = __syncthreads_count(st == 0);
+        const unsigned c1 = __syncthreads_count(st == 1);
+        const unsigned c2 = __syncthreads_count(st == 2);
+        if (threadIdx.x == 0) {
+            uint32_t *tc = tile_cnt + (P.tile_off + t) * 3;
+            tc[0] = c0; tc[1] = c1; tc[2] = c2;
+            if (c0) atomicAdd(&wc[w].cnt[0], c0);
+            if (c1) atomicAdd(&wc[w].cnt[1], c1);
+            if (c2) atomicAdd(&wc[w].cnt[2], c2);
+        }
+    }
+    cluster.sync();   // nobody leaves while its part of the table may still be read
 }
 
 // D3 ---------------------------------------------------------------------------------------------
@@ -298,46 +423,79 @@ runs_stats_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ s
 }
 
 // D5b ---------------------------------------------------------------------------------------------
-// One block per (window, state): leaves tree[npad + d] = exp(-(d / L)^2 / 2) for d < N (0 beyond), then the
-// internal nodes level by level (node i = node 2i + node 2i+1).
+// One block per (window, state): the Gaussian table T[d] = exp(-(d / L)^2 / 2), d in [0, N), and its suffix sums
+// S[d] = T[d] + T[d + 1] + ... + T[N - 1] (S[N] = 0), accumulated from the far tail towards d = 0, i.e. from the smallest terms to
+// the largest. Layout inside the window's slot of the per-state slab: T at [0, N), S at [N, 2 N + 1).
+// (Round 1 kept a binary sum tree here -- 2 log2 N reads per range sum, 1.06 GB written for 296 windows; a range sum over distances
+// lo..hi is S[lo] - S[hi + 1]: two reads. The subtraction loses about log10(S[lo] / result) digits, which for runs of 8 or more
+// k-mers is one to two digits of sixteen; shorter runs are summed term by term from T.)
+constexpr int SCAN_ITEMS = 4;
+
 __global__ void __launch_bounds__(TREE_THREADS)
-kde_tree_kernel(const WinPlan *__restrict__ plan, const KdeParams *__restrict__ kp, double *__restrict__ tree0, double *__restrict__ tree1,
-                double *__restrict__ tree2)
+kde_table_kernel(const WinPlan *__restrict__ plan, const KdeParams *__restrict__ kp, double *__restrict__ tab0, double *__restrict__ tab1,
+                 double *__restrict__ tab2)
 {
-    int32_t w = blockIdx.x / 3, s = blockIdx.x % 3;
+    const int32_t w = blockIdx.x / 3, s = blockIdx.x % 3;
     const WinPlan P = plan[w];
     if (!P.smoothed) return;
     if (kp[w].n[s] == 0) return;   // state absent: never read
-    double *t = (s == 0 ? tree0 : (s == 1 ? tree1 : tree2)) + P.tree_off;
-    const int32_t N = P.n_rows, npad = P.npad;
+    double *T = (s == 0 ? tab0 : (s == 1 ? tab1 : tab2)) + P.tree_off;
+    const int32_t N = P.n_rows;
+    double *S = T + N;
     const double L = kp[w].L[s];
-    for (int32_t d = threadIdx.x; d < npad; d += blockDim.x) {
-        double v = 0.0;
-        if (d < N) { double x = (double)d / L; v = exp(-(x * x) / 2.0); }
-        t[npad + d] = v;
+    for (int32_t d = threadIdx.x; d < N; d += blockDim.x) {
+        const double x = (double)d / L;
+        T[d] = exp(-(x * x) / 2.0);
     }
+    __shared__ double s_warp[TREE_THREADS / 32];
+    __shared__ double s_carry;
+    if (threadIdx.x == 0) { s_carry = 0.0; S[N] = 0.0; }
     __syncthreads();
-    for (int32_t len = npad >> 1; len >= 1; len >>= 1) {
-        for (int32_t i = len + threadIdx.x; i < 2 * len; i += blockDim.x) t[i] = t[2 * i] + t[2 * i + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int CH = TREE_THREADS * SCAN_ITEMS;
+    // chunks from the tail; inside a chunk thread t owns elements [base + t * ITEMS, +ITEMS), later threads hold the farther distances
+    for (int32_t base = ((N - 1) / CH) * CH; base >= 0; base -= CH) {
+        const int32_t d0 = base + threadIdx.x * SCAN_ITEMS;
+        double v[SCAN_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) v[i] = (d0 + i < N) ? T[d0 + i] : 0.0;
+        // suffix sums inside the thread, far element first
+#pragma unroll
+        for (int i = SCAN_ITEMS - 2; i >= 0; i--) v[i] += v[i + 1];
+        // exclusive suffix over threads: sum of the totals of all threads with a larger index
+        double tot = v[0], inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_down_sync(FULL, inc, o);
+            if (lane + o < 32) inc += u;
+        }
+        if (lane == 0) s_warp[wid] = inc;           // warp total
+        // what lies behind me inside the warp = the inclusive suffix of the next lane. (Not inc - tot: with a narrow bandwidth the
+        // table falls by many orders of magnitude per element and the difference of two nearly equal sums is all rounding error.)
+        const double nxt = __shfl_down_sync(FULL, inc, 1);
+        const double behind = lane < 31 ? nxt : 0.0;
+        __syncthreads();
+        double after = 0.0;                          // totals of the warps behind mine, farthest first
+        for (int q = TREE_THREADS / 32 - 1; q > wid; q--) after += s_warp[q];
+        const double excl = behind + (after + s_carry);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++)
+            if (d0 + i < N) S[d0 + i] = v[i] + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = v[0] + excl;  // S[base]
         __syncthreads();
     }
 }
 
-// Sum of leaves lo..hi (inclusive) of a sum tree with npad leaves; all terms are >= 0.
-__device__ __forceinline__ double tree_range_sum(const double *__restrict__ t, int32_t npad, int32_t lo, int32_t hi)
+// Sum of T over distances lo..hi (inclusive, 0 <= lo <= hi < N); all terms are >= 0.
+__device__ __forceinline__ double table_range_sum(const double *__restrict__ T, const double *__restrict__ S, int32_t lo, int32_t hi)
 {
-    double acc = 0.0;
     if (hi - lo < 8) {
-        for (int32_t d = lo; d <= hi; d++) acc += __ldg(t + npad + d);
+        double acc = 0.0;
+        for (int32_t d = hi; d >= lo; d--) acc += __ldg(T + d);
         return acc;
     }
-    int32_t l = lo + npad, r = hi + npad + 1;
-    while (l < r) {
-        if (l & 1) acc += __ldg(t + l++);
-        if (r & 1) acc += __ldg(t + --r);
-        l >>= 1; r >>= 1;
-    }
-    return acc;
+    return __ldg(S + lo) - __ldg(S + hi + 1);
 }
 
 // D6 ---------------------------------------------------------------------------------------------
@@ -358,7 +516,7 @@ kde_eval_kernel(const WinPlan *__restrict__ plan, int32_t n_win, const int64_t *
     }
     const int32_t w = lo;
     const WinPlan P = plan[w];
-    const int32_t N = P.n_rows, npad = P.npad;
+    const int32_t N = P.n_rows;
     const int sub = threadIdx.x % EVAL_LANES;
     int32_t e = (int32_t)(blk - grp_off[w]) * EVAL_GROUP + threadIdx.x / EVAL_LANES;
     int32_t j = -1;
@@ -366,7 +524,7 @@ kde_eval_kernel(const WinPlan *__restrict__ plan, int32_t n_win, const int64_t *
         if (mode == 0) { int64_t jj = (int64_t)e * P.srs; j = jj > N - 1 ? N - 1 : (int32_t)jj; }
         else j = fill_list[P.row_off + e];
     }
-    const double *t0 = tree0 + P.tree_off, *t1 = tree1 + P.tree_off, *t2 = tree2 + P.tree_off;
+    const double *t0 = tree0 + P.tree_off, *t1 = tree1 + P.tree_off, *t2 = tree2 + P.tree_off;   // per state: T at [0, N), S at [N, 2 N + 1)
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     if (j >= 0) {
         const int32_t nr = n_runs[w];
@@ -376,12 +534,13 @@ kde_eval_kernel(const WinPlan *__restrict__ plan, int32_t n_win, const int64_t *
             int32_t a = __ldg(rs + r), b = a + __ldg(rl + r) - 1;
             int s = __ldg(rst + r);
             const double *t = s == 0 ? t0 : (s == 1 ? t1 : t2);
+            const double *sfx = t + N;
             double v;
-            if (j < a) v = tree_range_sum(t, npad, a - j, b - j);
-            else if (j > b) v = tree_range_sum(t, npad, j - b, j - a);
+            if (j < a) v = table_range_sum(t, sfx, a - j, b - j);
+            else if (j > b) v = table_range_sum(t, sfx, j - b, j - a);
             else {
-                v = tree_range_sum(t, npad, 0, j - a);
-                if (b > j) v += tree_range_sum(t, npad, 1, b - j);
+                v = table_range_sum(t, sfx, 0, j - a);
+                if (b > j) v += table_range_sum(t, sfx, 1, b - j);
             }
             a0 += (s == 0) ? v : 0.0;
             a1 += (s == 1) ? v : 0.0;
@@ -516,9 +675,9 @@ finalize_kernel(const WinPlan *__restrict__ plan, int32_t win_base, double *__re
 // tuples pavlib.density.rl_encoder yields (pavlib/density.py:330-361) and all that scan_for_inv looks at to decide whether a
 // locus is expanded again (pavlib/inv.py:294-342). One CTA per window; at most STATE_RUN_CAP runs are stored per window (a
 // smoothed STATE column has a handful), the true number is always reported. Un-smoothed windows are one run of state -1.
-constexpr int STATE_RUN_CAP = 512;
+constexpr int STATE_RUN_CAP = 512;    // <= the block size of state_rle_kernel
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 state_rle_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ state, const int32_t *__restrict__ index,
                  pavgpu_state_run *__restrict__ runs, int32_t *__restrict__ n_state_runs)
 {
@@ -533,48 +692,42 @@ state_rle_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ st
         return;
     }
     const int8_t *st = state + P.row_off;
+    // every thread owns a contiguous slice of the rows: count the run heads in it, scan the counts over the block, write them
+    const int32_t per = (N + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
+    const int32_t lo = min((int32_t)threadIdx.x * per, N), hi = min(lo + per, N);
+    int cnt = 0;
+    for (int32_t i = lo; i < hi; i++) cnt += (i == 0 || st[i] != st[i - 1]) ? 1 : 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {
-        const int32_t i = i0 + threadIdx.x;
-        const bool head = i < N && (i == 0 || st[i] != st[i - 1]);
-        const unsigned bal = __ballot_sync(FULL, head);
-        if (lane == 0) s_warp[wid] = __popc(bal);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < wid) before += c; total += c; }
-        if (head) {
-            const int32_t r = s_base + before + __popc(bal & ((1u << lane) - 1u));
+    int before = 0;
+    for (int q = 0; q < wid; q++) before += s_warp[q];
+    if (threadIdx.x == blockDim.x - 1) s_total = before + inc;
+    int32_t r = before + inc - cnt;                        // rank of my first head
+    for (int32_t i = lo; i < hi; i++) {
+        if (i == 0 || st[i] != st[i - 1]) {
             if (r < STATE_RUN_CAP) { out[r].state = (int32_t)st[i]; out[r].first_index = ix[i]; out[r].count = i; }   // count holds the first row for now
             if (r > 0 && r - 1 < STATE_RUN_CAP) out[r - 1].last_index = ix[i - 1];
+            r++;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += total;
-        __syncthreads();
     }
-    const int32_t nr = s_base;
+    __syncthreads();
+    const int32_t nr = s_total;
     const int32_t kept = min(nr, STATE_RUN_CAP);
     if (threadIdx.x == 0 && nr <= STATE_RUN_CAP) out[nr - 1].last_index = ix[N - 1];
-    __syncthreads();
     // first rows -> counts (run r ends where run r + 1 starts)
-    int32_t nxt[2];
-    int32_t cnt_r[2];
-    int n_mine = 0;
-    for (int32_t r = threadIdx.x; r < kept && n_mine < 2; r += blockDim.x) {
-        nxt[n_mine] = (r + 1 < kept) ? out[r + 1].count : -1;
-        cnt_r[n_mine] = out[r].count;
-        n_mine++;
+    int32_t first = 0, next = -1;
+    if ((int32_t)threadIdx.x < kept) {
+        first = out[threadIdx.x].count;
+        next = ((int32_t)threadIdx.x + 1 < kept) ? out[threadIdx.x + 1].count : -1;
     }
     __syncthreads();
-    n_mine = 0;
-    for (int32_t r = threadIdx.x; r < kept && n_mine < 2; r += blockDim.x) {
-        const int32_t e = nxt[n_mine] >= 0 ? nxt[n_mine] : N;       // (the last stored run of an overflowing window is not used)
-        out[r].count = e - cnt_r[n_mine];
-        n_mine++;
-    }
+    if ((int32_t)threadIdx.x < kept) out[threadIdx.x].count = (next >= 0 ? next : N) - first;   // (the last stored run of an overflowing window is not used)
     if (threadIdx.x == 0) n_state_runs[w] = nr;
 }
 
@@ -680,7 +833,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
 
     // ---- plan, part 1 (host)
     int64_t tab = 0, pos = 0, tiles = 0, bases = 0, tree_cap = 0;
-    int32_t max_ref_blocks = 1, max_tig_tiles = 1;
+    int32_t max_ref_blocks = 1, max_tig_tiles = 1, max_ref_kmers = 0;
     for (int32_t w = 0; w < n_win; w++) {
         const pavgpu_density_window &W = b->win[w];
         if (W.ref_seq_id < 0 || W.ref_seq_id >= ref_store->n_seq || W.tig_seq_id < 0 || W.tig_seq_id >= tig_store->n_seq ||
@@ -701,10 +854,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         P.pos_off = pos; pos += n_tig;
         P.tile_off = tiles; tiles += (n_tig + TILE - 1) / TILE;
         max_ref_blocks = std::max(max_ref_blocks, (n_ref + 255) / 256);
+        max_ref_kmers = std::max(max_ref_kmers, n_ref);
         max_tig_tiles = std::max(max_tig_tiles, (n_tig + TILE - 1) / TILE);
         bases += P.tig_len;
         P.tree_off = tree_cap;                                   // upper bound: N <= n_tig
-        tree_cap += 2 * ((int64_t)1 << log2_ceil(std::max(n_tig, 1)));
+        tree_cap += 2 * (int64_t)std::max(n_tig, 1) + 2;         // T[N] + S[N + 1], N <= n_tig
     }
     b->tab_slots = tab; b->pos_total = pos; b->tile_total = tiles; b->tree_total = tree_cap;
     b->stats.bases = bases;
@@ -743,25 +897,54 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaEventRecord(ctx->ev[1], st));   // the table initialisation below is part of the step
     CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_wc, 0, sizeof(WinCounts) * n_win, st));
-    CUDA_TRY(cudaMemsetAsync(b->d_keys, 0xFF, sizeof(uint64_t) * std::max<int64_t>(tab, 1), st));
-    CUDA_TRY(cudaMemsetAsync(b->d_counts, 0, sizeof(uint32_t) * std::max<int64_t>(tab, 1), st));
-
     const int32_t YMAX = 32768;
-    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
-        int32_t ny = std::min(YMAX, n_win - w0);
-        ref_insert_kernel<<<dim3(max_ref_blocks, ny), 256, 0, st>>>(b->d_plan, w0, planes_of(ref_store), k, b->d_keys, b->d_counts, b->d_wc);
-        launches++;
-    }
-    CUDA_TRY(cudaGetLastError());
-    for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
-        int32_t ny = std::min(YMAX, n_win - w0);
-        tig_state_kernel<<<dim3(max_tig_tiles, ny), TILE, 0, st>>>(b->d_plan, w0, planes_of(tig_store), k, b->d_keys, b->d_st_pos, b->d_tile_cnt, b->d_wc);
-        launches++;
-    }
-    CUDA_TRY(cudaGetLastError());
+    // k-mer tables: in the distributed shared memory of one cluster per window when every window is small enough, else in HBM
+    // (opt-in: measured on B200, r02, 296 windows x 50 kbp: 1.42 ms for the cluster kernel against 0.51 + 0.30 ms for ref_insert + tig_state --
+    // remote shared-memory atomics and loads at one 1,024-thread CTA per SM and 16 resident clusters are latency-bound)
+    static const bool kc_on = [] { const char *e = getenv("PAVGPU_DENSITY_CLUSTER_TABLES"); return e && e[0] == '1'; }();
+    bool use_cluster = kc_on && max_ref_kmers <= KC_MAX_REF;
     std::vector<WinCounts> wc(n_win);
-    CUDA_TRY(cudaMemcpyAsync(wc.data(), b->d_wc, sizeof(WinCounts) * n_win, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (use_cluster) {
+            static bool attr_done[64] = {};
+            const int dev = ctx->device;
+            if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+                CUDA_TRY(cudaFuncSetAttribute(kmer_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC_SMEM));
+                if (dev >= 0 && dev < 64) attr_done[dev] = true;
+            }
+            const int32_t XMAX = 65535 * 8 / KC_CLUSTER;   // windows per launch
+            for (int32_t w0 = 0; w0 < n_win; w0 += XMAX) {
+                const int32_t nx = std::min(XMAX, n_win - w0);
+                kmer_cluster_kernel<<<(unsigned)nx * KC_CLUSTER, KC_THREADS, KC_SMEM, st>>>(b->d_plan, w0, planes_of(ref_store), planes_of(tig_store), k,
+                                                                                             b->d_st_pos, b->d_tile_cnt, b->d_wc);
+                launches++;
+            }
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            CUDA_TRY(cudaMemsetAsync(b->d_keys, 0xFF, sizeof(uint64_t) * std::max<int64_t>(tab, 1), st));
+            CUDA_TRY(cudaMemsetAsync(b->d_counts, 0, sizeof(uint32_t) * std::max<int64_t>(tab, 1), st));
+            for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+                int32_t ny = std::min(YMAX, n_win - w0);
+                ref_insert_kernel<<<dim3(max_ref_blocks, ny), 256, 0, st>>>(b->d_plan, w0, planes_of(ref_store), k, b->d_keys, b->d_counts, b->d_wc);
+                launches++;
+            }
+            CUDA_TRY(cudaGetLastError());
+            for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+                int32_t ny = std::min(YMAX, n_win - w0);
+                tig_state_kernel<<<dim3(max_tig_tiles, ny), TILE, 0, st>>>(b->d_plan, w0, planes_of(tig_store), k, b->d_keys, b->d_st_pos, b->d_tile_cnt, b->d_wc);
+                launches++;
+            }
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpyAsync(wc.data(), b->d_wc, sizeof(WinCounts) * n_win, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        bool overflow = false;
+        for (int32_t w = 0; w < n_win && use_cluster; w++) overflow |= wc[w].overflow != 0;
+        if (!overflow) break;
+        use_cluster = false;      // a partition of some window filled up: redo the k-mer part with the global tables
+        CUDA_TRY(cudaMemsetAsync(b->d_wc, 0, sizeof(WinCounts) * n_win, st));
+    }
+    b->stats.kmer_tables_on_chip = use_cluster ? 1 : 0;
     tr.mark("plan + k-mer kernels");
 
     // ---- plan, part 2 (host): status, keep mask, N, dense row offsets, sample counts
@@ -813,7 +996,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     runs_stats_kernel<<<n_win, 1024, 0, st>>>(b->d_plan, b->d_state_mer, b->prm.smooth, b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs,
                                               b->d_kp);
-    kde_tree_kernel<<<n_win * 3, TREE_THREADS, 0, st>>>(b->d_plan, b->d_kp, b->d_tree[0], b->d_tree[1], b->d_tree[2]);
+    kde_table_kernel<<<n_win * 3, TREE_THREADS, 0, st>>>(b->d_plan, b->d_kp, b->d_tree[0], b->d_tree[1], b->d_tree[2]);
     launches += 2;
     CUDA_TRY(cudaGetLastError());
     int64_t pairs = 0;
@@ -853,7 +1036,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
-    state_rle_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->d_state, b->d_index, b->d_state_runs, b->d_n_state_runs);
+    state_rle_kernel<<<n_win, 1024, 0, st>>>(b->d_plan, b->d_state, b->d_index, b->d_state_runs, b->d_n_state_runs);
     launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
@@ -944,17 +1127,19 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch
     run_off[n_win] = total;
     *n_runs_total = total;
     if (total == 0) return PAVGPU_OK;
-    pavgpu_state_run *h = nullptr;
+    pavgpu_state_run *h = nullptr, *blk = nullptr;
     int prc = pav_pinned_take(ctx, (size_t)total * sizeof(pavgpu_state_run), reinterpret_cast<void **>(&h));
     if (prc) return prc;
+    // one copy of the whole per-window run block (n_win x STATE_RUN_CAP x 16 B: a few MB) instead of one small copy per window
+    prc = pav_pinned_take(ctx, (size_t)n_win * STATE_RUN_CAP * sizeof(pavgpu_state_run), reinterpret_cast<void **>(&blk));
+    if (prc) { pavgpu_free_host(h); return prc; }
     int rc = [&]() -> int {
-        for (int32_t w = 0; w < n_win; w++) {
-            if (n_sr[w] > 0 && n_sr[w] <= STATE_RUN_CAP)
-                CUDA_TRY(cudaMemcpyAsync(h + run_off[w], b->d_state_runs + (int64_t)w * STATE_RUN_CAP, (size_t)n_sr[w] * sizeof(pavgpu_state_run),
-                                         cudaMemcpyDeviceToHost, ctx->stream));
-        }
+        CUDA_TRY(cudaMemcpyAsync(blk, b->d_state_runs, (size_t)n_win * STATE_RUN_CAP * sizeof(pavgpu_state_run), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev[6], ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (int32_t w = 0; w < n_win; w++)
+            if (n_sr[w] > 0 && n_sr[w] <= STATE_RUN_CAP)
+                memcpy(h + run_off[w], blk + (size_t)w * STATE_RUN_CAP, (size_t)n_sr[w] * sizeof(pavgpu_state_run));
         // a window with more runs than the device keeps (never seen on smoothed columns): encode its STATE column here
         for (int32_t w = 0; w < n_win; w++) {
             if (n_sr[w] <= STATE_RUN_CAP) continue;
@@ -973,6 +1158,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_fetch
         return PAVGPU_OK;
     }();
     tr.mark("d2h");
+    pavgpu_free_host(blk);
     if (rc) { pavgpu_free_host(h); return rc; }
     b->stats.ms_d2h = ev_ms(ctx->ev[5], ctx->ev[6]);
     *runs_out = h;

@@ -12,6 +12,7 @@
 #include <unordered_map>
 
 #include <algorithm>
+#include <thread>
 
 #include "common.cuh"
 
@@ -313,10 +314,36 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
         return PAVGPU_ERR_NOMEM;
     }
     rc = [&]() -> int {
-        CUDA_TRY(cudaMemsetAsync(d_ascii, 'N', (size_t)s->total_bases, ctx->stream));
-        for (int32_t i = 0; i < n_seq; i++)
-            if (seq_len[i] > 0)
-                CUDA_TRY(cudaMemcpyAsync(d_ascii + s->h_off[i], seq_ascii[i], (size_t)seq_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        // Many small sequences (a batch of density windows): one pageable cudaMemcpyAsync each costs ~10 us of driver staging per
+        // call. They are laid out -- padding included -- in one pinned buffer by a few host threads instead and go up in one copy.
+        const bool many_small = n_seq >= 16 && s->total_bases <= ((int64_t)256 << 20) && s->total_bases / n_seq <= ((int64_t)1 << 20);
+        uint8_t *stage = nullptr;
+        if (many_small && pav_pinned_take(ctx, (size_t)s->total_bases, reinterpret_cast<void **>(&stage)) != PAVGPU_OK) stage = nullptr;
+        struct StageGuard {   // back to the pool once the stream is done with it, on every way out
+            uint8_t *p; cudaStream_t st;
+            ~StageGuard() { if (p) { cudaStreamSynchronize(st); pavgpu_free_host(p); } }
+        } guard{stage, ctx->stream};
+        if (stage) {
+            const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, (int64_t)std::thread::hardware_concurrency(), s->total_bases >> 20}));
+            auto fill = [&](int32_t lo, int32_t hi) {
+                for (int32_t i = lo; i < hi; i++) {
+                    const int64_t end = (i + 1 < n_seq) ? s->h_off[i + 1] : s->total_bases;
+                    if (seq_len[i] > 0) memcpy(stage + s->h_off[i], seq_ascii[i], (size_t)seq_len[i]);
+                    memset(stage + s->h_off[i] + seq_len[i], 'N', (size_t)(end - s->h_off[i] - seq_len[i]));
+                }
+            };
+            if (n_seq == 0) memset(stage, 'N', (size_t)s->total_bases);
+            std::vector<std::thread> pool;
+            for (int t = 1; t < n_thr; t++) pool.emplace_back(fill, (int32_t)((int64_t)n_seq * t / n_thr), (int32_t)((int64_t)n_seq * (t + 1) / n_thr));
+            fill(0, (int32_t)((int64_t)n_seq / n_thr));
+            for (auto &th : pool) th.join();
+            CUDA_TRY(cudaMemcpyAsync(d_ascii, stage, (size_t)s->total_bases, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CUDA_TRY(cudaMemsetAsync(d_ascii, 'N', (size_t)s->total_bases, ctx->stream));
+            for (int32_t i = 0; i < n_seq; i++)
+                if (seq_len[i] > 0)
+                    CUDA_TRY(cudaMemcpyAsync(d_ascii + s->h_off[i], seq_ascii[i], (size_t)seq_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        }
         int64_t n_words = s->total_bases / 32;
         int64_t blocks = (n_words + 255) / 256;
         pack_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_ascii, n_words, s->d_pack2, s->d_nmask);
@@ -334,11 +361,18 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create(pav
 }
 
 extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_create_packed(pavgpu_ctx *ctx, int32_t n_seq, const int64_t *seq_len, const uint64_t *pack2_host,
-                                             const uint32_t *nmask_host, pavgpu_seqstore **out)
+                                             size_t pack2_bytes, const uint32_t *nmask_host, size_t nmask_bytes, pavgpu_seqstore **out)
 {
+    if (!pack2_host || !nmask_host) { pav_set_error("seqstore_create_packed: planes are NULL"); return PAVGPU_ERR_ARG; }
     pavgpu_seqstore *s = nullptr;
     int rc = alloc_store(ctx, n_seq, seq_len, &s);
     if (rc) return rc;
+    if (pack2_bytes != s->pack2_bytes || nmask_bytes != s->nmask_bytes) {   // planes packed under another layout (alignment, tail guard) or truncated
+        pav_set_error("seqstore_create_packed: plane sizes (%zu, %zu) do not match this library's layout for these lengths (%zu, %zu)", pack2_bytes,
+                      nmask_bytes, s->pack2_bytes, s->nmask_bytes);
+        pavgpu_seqstore_free(s);
+        return PAVGPU_ERR_ARG;
+    }
     rc = [&]() -> int {
         CUDA_TRY(cudaMemcpyAsync(s->d_pack2, pack2_host, s->pack2_bytes, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(s->d_nmask, nmask_host, s->nmask_bytes, cudaMemcpyHostToDevice, ctx->stream));

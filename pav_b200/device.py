@@ -89,8 +89,9 @@ class SeqStore:
             _capi.check(L.pavgpu_seqstore_create_empty(ctx.handle, len(self.names), self.lengths.ctypes.data_as(ctypes.POINTER(c_i64)),
                                                        ctypes.byref(h)), 'pavgpu_seqstore_create_empty')
         else:
+            pack2, nmask = np.ascontiguousarray(pack2), np.ascontiguousarray(nmask)
             _capi.check(L.pavgpu_seqstore_create_packed(ctx.handle, len(self.names), self.lengths.ctypes.data_as(ctypes.POINTER(c_i64)),
-                                                        _capi.ptr(pack2), _capi.ptr(nmask), ctypes.byref(h)),
+                                                        _capi.ptr(pack2), pack2.nbytes, _capi.ptr(nmask), nmask.nbytes, ctypes.byref(h)),
                         'pavgpu_seqstore_create_packed')
         self.handle = h
         self.host = None

@@ -7,6 +7,14 @@ strings into HBM and runs the same device routine -- there is no CPU implementat
 from .. import device
 
 
+def _empty_sv(base_getter):
+    """The reference with an empty SV sequence: the first ACGT base it looks at ends in ``x % 0`` (pavlib/call.py:582,637)."""
+    base = base_getter()
+    if base not in {'A', 'C', 'G', 'T'}:
+        return 0
+    raise ZeroDivisionError('integer modulo by zero')
+
+
 def left_homology(pos_tig, seq_tig, seq_sv):
     """Perfect-homology bases upstream of ``pos_tig`` (0-based, inclusive start of the leftward scan)."""
     if seq_sv is None or seq_tig is None:
@@ -15,6 +23,8 @@ def left_homology(pos_tig, seq_tig, seq_sv):
         return 0
     if pos_tig >= len(seq_tig):
         raise IndexError('string index out of range')
+    if len(seq_sv) == 0:
+        return _empty_sv(lambda: seq_tig[pos_tig])
     left, _ = device.homology(seq_tig, seq_sv, [pos_tig])
     return int(left[0])
 
@@ -26,10 +36,16 @@ def right_homology(pos_tig, seq_tig, seq_sv):
     if pos_tig >= len(seq_tig):
         return 0
     if pos_tig < 0:
-        pos_tig_py = len(seq_tig) + pos_tig
-        if pos_tig_py < 0:
+        # The reference's loop indexes seq_tig[pos_tig + hom_len] with hom_len < len(seq_tig) - pos_tig (pavlib/call.py:627-634):
+        # a negative position reads the last |pos_tig| bases through Python's negative indexing and then carries on from the start
+        # of the sequence, i.e. it scans seq_tig[pos_tig:] + seq_tig from its first base. Same scan on the device over that string.
+        if len(seq_tig) + pos_tig < 0:
             raise IndexError('string index out of range')
-        # Python negative indexing semantics of the reference loop: position wraps, limit does not.
-        raise NotImplementedError('right_homology with a negative position is not supported on the GPU path')
+        if len(seq_sv) == 0:
+            return _empty_sv(lambda: seq_tig[pos_tig])
+        _, right = device.homology(seq_tig[pos_tig:] + seq_tig, seq_sv, [0])
+        return int(right[0])
+    if len(seq_sv) == 0:
+        return _empty_sv(lambda: seq_tig[pos_tig])
     _, right = device.homology(seq_tig, seq_sv, [pos_tig])
     return int(right[0])

@@ -289,8 +289,10 @@ def call_rows(df_align, ref_fa_name, tig_fa_name):
 
 _MALLOC_TUNED = False
 _CALLS = 0        # make_insdel_snv_calls calls in this process (pinned staging starts with the second one)
-_READERS = 3      # reader threads per FASTA
-_PINNED_STAGING_MAX = int(os.environ.get('PAVGPU_PINNED_STAGING_MAX_MB', '1024')) << 20   # larger inputs stay in ordinary memory
+_READERS = int(os.environ.get('PAVGPU_FASTA_READERS', str(min(12, max(3, len(os.sched_getaffinity(0)) // 2)))))   # reader threads per FASTA
+#   (C3, one haplotype, B200 box with 16 cores: 3 readers + 1 GB pinned cap 1.63 s per call, 12 readers 1.52 s, 12 readers + pinned staging
+#   for the whole 3.1 GB of each side 1.05 s -- profiles/r02_c3_e2e_sweep.log)
+_PINNED_STAGING_MAX = int(os.environ.get('PAVGPU_PINNED_STAGING_MAX_MB', '4096')) << 20   # per FASTA side; larger inputs stay in ordinary memory
 
 
 def _tune_malloc():

@@ -41,9 +41,21 @@ class InvCall:
         self.region_ref_discovery = region_ref_discovery
         self.region_tig_discovery = region_tig_discovery
         self.region_flag = region_flag
-        self.df = df
+        self._df = df           # the density table, or a zero-argument callable that builds it when somebody asks (batch driver)
         self.svlen = len(region_ref_outer)
         self.id = '{}-{}-INV-{}'.format(region_ref_outer.chrom, region_ref_outer.pos + 1, self.svlen)
+
+    @property
+    def df(self):
+        """Density table with the FLANK / MATCH columns (pavlib/inv.py:440-454). The batch driver hands over the column arrays
+        and builds the frame on first access: a caller that only wants the regions never pays for it (1.2 ms of pandas per call)."""
+        if callable(self._df):
+            self._df = self._df()
+        return self._df
+
+    @df.setter
+    def df(self, value):
+        self._df = value
 
     def __repr__(self):
         return self.id
@@ -228,11 +240,15 @@ class _InvScan:
             return None
         # NOTE: the reference passes region_ref where annotate_inv_dup_mers expects the contig discovery region
         # (pavlib/inv.py:440-442); reproduced as is.
-        if isinstance(df, pavdensity.DensityTable):   # batch driver: the frame is built once, with the two flank columns already in it
-            res = df.res
-            flank, match = _dup_mer_columns(res['INDEX'], res['KMER'].astype(np.int64), region_ref_outer, region_ref_inner, region_tig_outer,
-                                            region_tig_inner, region_ref, self.ref_fa_name, self.k_util)
-            df = df.frame(extra={'FLANK': flank, 'MATCH': match})
+        if isinstance(df, pavdensity.DensityTable):   # batch driver: the frame is built once, with the two flank columns already in it,
+            table, res = df, df.res                   # and only when the call's table is asked for (InvCall.df)
+            res['INDEX']                              # a lazy window copies its columns off the device now: the batch does not outlive the round
+            ref_fa_name, k_util = self.ref_fa_name, self.k_util
+
+            def df():
+                flank, match = _dup_mer_columns(res['INDEX'], res['KMER'].astype(np.int64), region_ref_outer, region_ref_inner, region_tig_outer,
+                                                region_tig_inner, region_ref, ref_fa_name, k_util)
+                return table.frame(extra={'FLANK': flank, 'MATCH': match})
         else:
             df = annotate_inv_dup_mers(df, region_ref_outer, region_ref_inner, region_tig_outer, region_tig_inner, region_ref,
                                        self.ref_fa_name, self.k_util)

@@ -44,17 +44,21 @@ class AlignLift:
             self._by_qid.setdefault(q, []).append(i)
         self._by_chrom = {c: np.array(v, dtype=np.int64) for c, v in self._by_chrom.items()}
         self._by_qid = {q: np.array(v, dtype=np.int64) for q, v in self._by_qid.items()}
-        self._cache = {}
-        self._order = []
+        # Block tables of the records looked at so far. The reference keeps the interval trees of the last ``cache_align`` (10)
+        # records; a batch of hundreds of loci on as many records rebuilt its tables on most lookups that way (a fifth of the host
+        # time of call_inv_batch). The tables are a cache either way, so they are kept until they add up to PAVGPU_LIFT_CACHE_MB
+        # (default 256), oldest out first, and never fewer than ``cache_align`` of them.
+        import collections
+        import os
+        self._cache = collections.OrderedDict()
+        self._cache_bytes = 0
+        self._cache_cap = int(os.environ.get('PAVGPU_LIFT_CACHE_MB', '256')) << 20
 
     # ------------------------------------------------------------------ per-record block tables
     def _record_map(self, i):
         if i in self._cache:
-            self._order.remove(i)
-            self._order.insert(0, i)
+            self._cache.move_to_end(i)
             return self._cache[i]
-        while len(self._order) >= self.cache_align:
-            del self._cache[self._order.pop()]
         row = {'#CHROM': self._chrom[i], 'POS': self._pos[i], 'QRY_ID': self._qid[i]}
         ops, _, perr = device.parse_cigars([self._cigar[i]])
         if perr.code != 0:
@@ -79,8 +83,12 @@ class AlignLift:
         m.q_begin, m.q_end = qry[qsel], qry[qsel] + ln[qsel]
         m.q_d0 = sub[qsel]
         m.q_d1 = np.where(is_m[qsel], sub[qsel] + ln[qsel], sub[qsel] + 1)
+        m_bytes = sum(getattr(m, f).nbytes for f in _RecordMap.__slots__)
+        while len(self._cache) >= max(int(self.cache_align), 1) and self._cache_bytes + m_bytes > self._cache_cap:
+            _, old = self._cache.popitem(last=False)
+            self._cache_bytes -= sum(getattr(old, f).nbytes for f in _RecordMap.__slots__)
         self._cache[i] = m
-        self._order.insert(0, i)
+        self._cache_bytes += m_bytes
         return m
 
     @staticmethod

@@ -42,7 +42,7 @@ def write(path, names, arrays, pack2, nmask, source=None):
         ascii_off.append(off)
         off += _pad(ln, 64)
     meta = {'names': [str(n) for n in names], 'lengths': lengths, 'ascii_off': ascii_off, 'ascii_bytes': off,
-            'pack2_bytes': int(pack2.nbytes), 'nmask_bytes': int(nmask.nbytes)}
+            'pack2_bytes': int(pack2.nbytes), 'nmask_bytes': int(nmask.nbytes), 'layout': PLANE_LAYOUT}
     if source:
         st = os.stat(source)
         meta['source'] = {'path': os.path.abspath(source), 'size': st.st_size, 'mtime_ns': st.st_mtime_ns}
@@ -78,6 +78,12 @@ def build(fasta_path, out_path=None, ctx=None):
     return write(out_path or fasta_path + SUFFIX, names, arrays, pack2, nmask, source=fasta_path)
 
 
+# Layout of the packed planes a sidecar holds: sequence starts aligned to 128 bases, one 128-base tail guard, 32 bases per 64-bit word
+# (first base most significant), one mask bit per base. A file written under another layout is refused (the C call checks the byte
+# sizes against the layout the loaded library derives from the sequence lengths as well).
+PLANE_LAYOUT = {'seq_align': 128, 'tail_guard': 128, 'version': 1}
+
+
 class Sidecar:
     def __init__(self, path):
         self.path = path
@@ -95,6 +101,11 @@ class Sidecar:
         self._nmask = self._pack2 + _pad(self.meta['pack2_bytes'])
         if len(self._map) < self._nmask + self.meta['nmask_bytes']:
             raise RuntimeError(f'{path}: truncated sidecar')
+        if self.meta.get('layout', PLANE_LAYOUT) != PLANE_LAYOUT:
+            raise RuntimeError(f'{path}: packed under plane layout {self.meta.get("layout")}, this build uses {PLANE_LAYOUT}; rebuild the sidecar')
+        words = int(sum((int(n) + 127) // 128 * 128 for n in self.lengths) + 128) // 32
+        if self.meta['pack2_bytes'] != 8 * words or self.meta['nmask_bytes'] != 4 * words:
+            raise RuntimeError(f'{path}: plane sizes do not match the sequence lengths (corrupt or foreign sidecar)')
 
     def fresh_for(self, fasta_path):
         src = self.meta.get('source')

@@ -22,3 +22,12 @@ for i in range(2 * n_calls):
     dt = time.perf_counter() - t0
     print(f'call {i} lazy={lazy}: {dt * 1e3:.1f} ms = {n_win * 50_000 / dt / 1e9:.3f} Gbases/s; seconds={ {k: round(v, 4) for k, v in density.last_stats["seconds"].items()} } '
           f'kernels={density.last_stats["ms_kernels"]:.2f} ms d2h={density.last_stats["ms_d2h"]:.2f} ms', flush=True)
+
+if os.environ.get('PROFILE'):
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    out = density.density_windows(wins, lazy=True)
+    pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(25)

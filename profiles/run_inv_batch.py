@@ -37,6 +37,15 @@ df_flag = pd.DataFrame(flags, columns=['#CHROM', 'POS', 'END', 'ID', 'SVTYPE', '
 df_aln = pd.DataFrame(aln, columns=['#CHROM', 'POS', 'END', 'INDEX', 'QRY_ID', 'QRY_POS', 'QRY_END', 'QRY_LEN', 'REV', 'CIGAR'])
 df_fai = seq.get_df_fai(tig_fa + '.fai')
 
+if os.environ.get('PROFILE'):     # where the host time of the rule goes (one warm-up call first)
+    import cProfile
+    import pstats
+    flag.call_inv_batch(df_flag, 0, ref_fa, tig_fa, df_aln, df_fai, 'h1', log=io.StringIO())
+    pr = cProfile.Profile()
+    pr.enable()
+    flag.call_inv_batch(df_flag, 0, ref_fa, tig_fa, df_aln, df_fai, 'h1', log=io.StringIO())
+    pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
 times = []
 for rep in range(3):
     log = io.StringIO()

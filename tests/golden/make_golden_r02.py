@@ -147,5 +147,65 @@ def main_ties(rng, out):
     print(json.dumps(out, indent=1))
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and 'homology-wrap' not in sys.argv and 'kern-exact' not in sys.argv:
     main()
+
+
+def homology_wrap_cases():
+    """pavlib.call.right_homology with a negative position (Python's negative indexing wraps the first |pos| reads to the end of the
+    sequence, the limit len - pos lets the scan run on from its start; pavlib/call.py:623-647) and both functions with an empty SV
+    sequence (`x % 0`), as the reference itself answers them."""
+    import pavlib.call
+    rng = np.random.default_rng(77)
+    out = []
+    seqs = ['ACGTACGTACGTACGT', 'AAAAAAAAAA', 'CAGCAGCAGCAGTT', 'GATTACANGATTACA']
+    for _ in range(12):
+        unit = synth.random_seq(rng, int(rng.integers(1, 5))).tobytes().decode()
+        seqs.append(unit * int(rng.integers(3, 40)) + synth.random_seq(rng, int(rng.integers(0, 30))).tobytes().decode())
+    for seq in seqs:
+        for sv in (seq[:1], seq[:3], seq[-2:], seq[-4:] + seq[:2], 'ACGT', ''):
+            for pos in sorted({-1, -2, -3, -len(seq), -len(seq) - 1, -len(seq) // 2, 0, len(seq) - 1, len(seq)}):
+                rec = {'seq': seq, 'sv': sv, 'pos': pos}
+                for name, fn in (('left', pavlib.call.left_homology), ('right', pavlib.call.right_homology)):
+                    try:
+                        rec[name] = int(fn(pos, seq, sv))
+                    except Exception as ex:  # noqa: BLE001
+                        rec[name] = {'error': type(ex).__name__}
+                out.append(rec)
+    with open(os.path.join(HERE, 'homology_wrap.json'), 'w') as fh:
+        json.dump(out, fh)
+    print('homology_wrap', len(out), 'cases,', sum(isinstance(r['right'], dict) or isinstance(r['left'], dict) for r in out), 'with an exception')
+
+
+if __name__ == '__main__' and 'homology-wrap' in sys.argv:
+    homology_wrap_cases()
+
+
+def density_kern_exact():
+    """density.tsv.gz stores KERN_* as decimal text, and pandas' to_csv keeps 16 decimal places: values around 1e-4 carry 12-13
+    significant digits there, which caps any comparison at ~1e-12 relative (found in r02: the scalar C oracle and the GPU both sat at
+    ~1e-12 against the TSV while scipy itself is within 1e-14 of the exact sum). The reference is run again on every smoothed case
+    and its three float64 columns are stored bit for bit (kern.npy, 3 x N); the discrete columns must equal the stored table."""
+    import pandas as pd
+    from concurrent.futures import ThreadPoolExecutor
+    base = os.path.join(HERE, 'density')
+
+    def one(case):
+        d = os.path.join(base, case)
+        meta = json.load(open(os.path.join(d, 'meta.json')))
+        if meta['returncode'] != 0 or 'KERN_FWD' not in (meta.get('columns') or []):
+            return case, None
+        rc, df, _ = mg._run_density(os.path.join(d, 'ref.fa'), os.path.join(d, 'tig.fa'), meta['refregion'], meta['tigregion'], meta['k'], meta['rev'],
+                                    meta['srs'], meta.get('extra', ()))
+        gold = pd.read_csv(os.path.join(d, 'density.tsv.gz'), sep='\t')
+        assert rc == 0 and all((df[c].to_numpy() == gold[c].to_numpy()).all() for c in ('INDEX', 'STATE_MER', 'STATE', 'KMER')), case
+        k = np.stack([df[c].to_numpy(dtype=np.float64) for c in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV')])
+        np.save(os.path.join(d, 'kern.npy'), k)
+        return case, float(np.max(np.abs(k - np.stack([gold[c].to_numpy() for c in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV')]))))
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        for case, err in ex.map(one, sorted(os.listdir(base))):
+            print('kern.npy', case, 'max |text - binary| =', err)
+
+
+if __name__ == '__main__' and 'kern-exact' in sys.argv:
+    density_kern_exact()

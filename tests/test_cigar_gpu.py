@@ -124,6 +124,23 @@ def test_homology_golden_gpu():
                 assert r == c['right'], c
 
 
+def test_homology_wraparound_and_empty_sv():
+    """pavlib.call.left_homology / right_homology at the edges the reference answers in its own way: a negative position for the
+    rightward scan (Python's negative indexing: the scan reads the sequence's tail, then carries on from its start), positions
+    outside the sequence, an empty SV sequence -- values and exception types stored from the reference (homology_wrap.json)."""
+    from pav_b200.pavlib import call
+    cases = json.load(open(os.path.join(GOLDEN, 'homology_wrap.json')))
+    assert len(cases) > 500
+    for c in cases:
+        for name, fn in (('left', call.left_homology), ('right', call.right_homology)):
+            want = c[name]
+            if isinstance(want, dict):
+                with pytest.raises({'IndexError': IndexError, 'ZeroDivisionError': ZeroDivisionError}[want['error']]):
+                    fn(c['pos'], c['seq'], c['sv'])
+            else:
+                assert fn(c['pos'], c['seq'], c['sv']) == want, (name, c)
+
+
 def test_pavlib_call_signatures():
     from pav_b200.pavlib import call
     assert call.left_homology(5, None, 'A') == 0 and call.right_homology(5, 'ACGT', None) == 0
@@ -222,7 +239,7 @@ def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
     qid = np.array([names_t.index(c) for c in df['QRY_ID']], np.int32)
     out = {}
     monkeypatch.delenv('PAVGPU_HOMOLOGY_NBR', raising=False)
-    for mode in ('gather', 'auto', '1', 'nbr', 'bulk', 'tiled-auto', 'queue', 'split'):
+    for mode in ('gather', 'auto', '1', 'nbr', 'bulk', 'tiled-auto', 'queue', 'split', 'default'):
         monkeypatch.delenv('PAVGPU_HOMOLOGY', raising=False)
         if mode == 'nbr':
             monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', '0')
@@ -230,12 +247,15 @@ def test_homology_kernel_choice_c2_slice(tmp_path, monkeypatch):
         elif mode in ('auto', '1'):
             monkeypatch.setenv('PAVGPU_HOMOLOGY_TILED', mode)
             monkeypatch.setenv('PAVGPU_HOMOLOGY_NBR', '0')
+        elif mode == 'default':
+            monkeypatch.delenv('PAVGPU_HOMOLOGY_TILED', raising=False)
+            monkeypatch.delenv('PAVGPU_HOMOLOGY_NBR', raising=False)
         else:
             monkeypatch.setenv('PAVGPU_HOMOLOGY', mode)
         _, indel, err, st = device.cigar_call(ctx, rs, ts, rid, qid, df['POS'].to_numpy(np.int32), df['REV'].to_numpy(np.uint8), ops, op_off)
         assert err.code == 0
         out[mode] = (indel.copy(), st.homology_tiled)
-    assert [out[m][1] for m in ('gather', 'auto', '1', 'nbr', 'bulk', 'tiled-auto', 'queue', 'split')] == [0, 1, 1, 2, 3, 1, 4, 5]
+    assert [out[m][1] for m in ('gather', 'auto', '1', 'nbr', 'bulk', 'tiled-auto', 'queue', 'split', 'default')] == [0, 1, 1, 2, 3, 1, 4, 5, 4]
     assert all(out[m][0].tobytes() == out['gather'][0].tobytes() for m in out)
     for f in ('pos', 'end', 'svlen', 'qry_pos', 'qry_end', 'left_shift', 'hom_ref_l', 'hom_ref_r', 'hom_tig_l', 'hom_tig_r', 'rec', 'svtype'):
         assert (out['gather'][0][f] == o_indel[f]).all(), f

@@ -19,8 +19,12 @@ def _worker(rank, world, port, tmp, out_q):
     from pav_b200 import multigpu
     df = pd.read_csv(os.path.join(tmp, 'wl_align.bed'), sep='\t', dtype={'#CHROM': str, 'QRY_ID': str}, keep_default_na=False)
     res = multigpu.make_insdel_snv_calls_dist(df, os.path.join(tmp, 'wl_ref.fa'), os.path.join(tmp, 'wl_tig.fa'), 'h1', version_id=True)
+    st = multigpu.last_dist_stats
+    # what every rank holds after the broadcast, read back from ITS device: full export of the planes (not only the checksum)
+    from pav_b200 import device, fasta
+    out_q.put(('stats', rank, st['planes_verified'], st['checksum'], st['records'], st['rows']))
     if rank == 0:
-        out_q.put((res[0].to_csv(sep='\t', index=False), res[1].to_csv(sep='\t', index=False)))
+        out_q.put(('tables', res[0].to_csv(sep='\t', index=False), res[1].to_csv(sep='\t', index=False)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -40,8 +44,13 @@ def test_two_gpus_equal_oracle(tmp_path):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    msgs = [q.get(timeout=300) for _ in range(3)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert got[0] == exp[0].to_csv(sep='\t', index=False) and got[1] == exp[1].to_csv(sep='\t', index=False)
+    got = [m for m in msgs if m[0] == 'tables'][0]
+    stats = sorted(m for m in msgs if m[0] == 'stats')
+    assert got[1] == exp[0].to_csv(sep='\t', index=False) and got[2] == exp[1].to_csv(sep='\t', index=False)
+    # both ranks verified the planes they hold against rank 0's checksum, hold the same checksum, and both walked records
+    assert [m[2] for m in stats] == [True, True] and stats[0][3] == stats[1][3] and stats[0][3] != (0, 0)
+    assert all(m[4] > 0 and m[5] > 0 for m in stats) and sum(m[4] for m in stats) == len(df)

@@ -73,3 +73,31 @@ def test_forced_sidecar_must_exist(tmp_path, monkeypatch):
     monkeypatch.setenv('PAVGPU_SIDECAR', str(tmp_path / 'missing.pavsc'))
     with pytest.raises(RuntimeError, match='no such file'):
         sidecar.find(str(tmp_path / 'ref.fa'))
+
+
+def test_rejects_planes_of_another_layout(tmp_path):
+    """A sidecar whose plane sizes do not follow from its sequence lengths under this build's layout (written by another layout, or
+    with a doctored header) is refused when it is opened -- before any byte of it could be handed to the device."""
+    import json
+    import struct
+    from pav_b200 import sidecar
+    names, arrays = ['a', 'b'], [np.frombuffer(b'ACGT' * 100, np.uint8), np.frombuffer(b'GGCC' * 10, np.uint8)]
+    words = sum((len(a) + 127) // 128 * 128 for a in arrays) // 32 + 4
+    good = sidecar.write(str(tmp_path / 'ok.pavsc'), names, arrays, np.zeros(words, np.uint64), np.zeros(words, np.uint32))
+    sidecar.Sidecar(good)
+    short = sidecar.write(str(tmp_path / 'short.pavsc'), names, arrays, np.zeros(words - 4, np.uint64), np.zeros(words - 4, np.uint32))   # no tail guard
+    with pytest.raises(RuntimeError, match='plane sizes'):
+        sidecar.Sidecar(short)
+    raw = bytearray(open(good, 'rb').read())
+    n = struct.unpack('<Q', raw[8:16])[0]
+    meta = json.loads(raw[16:16 + n].decode())
+    meta['layout'] = {'seq_align': 64, 'tail_guard': 128, 'version': 1}
+    blob = json.dumps(meta).encode()
+    assert len(blob) <= n + 64
+    blob = blob.ljust(n)[:n] if len(blob) <= n else blob
+    if len(blob) == n:
+        raw[16:16 + n] = blob
+        other = tmp_path / 'other.pavsc'
+        other.write_bytes(bytes(raw))
+        with pytest.raises(RuntimeError, match='plane layout'):
+            sidecar.Sidecar(str(other))
