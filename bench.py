@@ -11,8 +11,8 @@ Workloads (BASELINE.json configs, SURVEY 8(d) generators, all synthetic and seed
       reference and broadcasts the packed planes with one NCCL broadcast, every rank checks the planes it received against rank
       0's checksum -- BASELINE configs[2] at N = 1, configs[3] at N > 1: STRONG scaling (total work fixed).
         value  device-resident: packed planes, packed CIGAR ops and record descriptors already in HBM; one step = per-record
-               row counts + record scan + CIGAR walk + homology for this rank's records of both haplotypes, replayed as CUDA
-               graphs, timed with CUDA events on the library stream, L2 flushed (256 MB memset) between steps; rows stay in HBM.
+               row counts + record scan + CIGAR walk + homology for this rank's records of both haplotypes (one batch), replayed as one
+               CUDA graph, timed with CUDA events on the library stream, L2 flushed (256 MB memset) between steps; rows stay in HBM.
                value = rows of all ranks / max over ranks of the mean step time.
         e2e    the call PAV makes, FASTA in -> DataFrames out: pavlib.cigarcall.make_insdel_snv_calls per haplotype at N = 1,
                pav_b200.multigpu.make_insdel_snv_calls_dist at N > 1 (LPT shards -> NCCL broadcast -> per-rank walk -> host
@@ -432,17 +432,29 @@ def shard_plan(dfs, world):
     return {h: [np.array(sorted(v), dtype=np.int64) for v in plan[h]] for h in plan}
 
 
-class ResidentHap:
-    """This rank's records of one haplotype resident in HBM (contig planes + packed ops)."""
+class ResidentShard:
+    """This rank's records of BOTH haplotypes resident in HBM as one batch (contig planes of both haplotypes in one store + packed
+    ops): one step of the rank is one replay of one CUDA graph."""
 
-    def __init__(self, ctx, hap, df, rows, tig_fa, ref_names):
+    def __init__(self, ctx, dfs, plan_rank, tig_fa, ref_names):
+        import pandas as pd
+
         from pav_b200 import device
         from pav_b200 import fasta as fasta_mod
-        self.hap, self.tig_fa_path = hap, tig_fa
-        self.df = df.iloc[rows].reset_index(drop=True)
-        fa = fasta_mod.open_fasta(tig_fa)
-        names_t = list(dict.fromkeys(self.df['QRY_ID']))
-        self.tig_store = device.SeqStore(ctx, names_t, [fa.fetch_array(n) for n in names_t], keep_host=False)
+        parts = []
+        for h in ('h1', 'h2'):
+            d = dfs[h].iloc[plan_rank[h]].copy()
+            d['_HAP'] = h
+            parts.append(d)
+        self.df = pd.concat(parts, ignore_index=True)
+        self.tig_fa = tig_fa
+        names_t, arrays = [], []
+        for h in ('h1', 'h2'):
+            fa = fasta_mod.open_fasta(tig_fa[h])
+            for n in dict.fromkeys(self.df.loc[self.df['_HAP'] == h, 'QRY_ID']):
+                names_t.append(n)
+                arrays.append(fa.fetch_array(n))
+        self.tig_store = device.SeqStore(ctx, names_t, arrays, keep_host=False)
         tidx = {n: i for i, n in enumerate(names_t)}
         ridx = {n: i for i, n in enumerate(ref_names)}
         rid = np.array([ridx[c] for c in self.df['#CHROM']], np.int32)
@@ -474,9 +486,8 @@ def oracle_check_records(rh, tmp, ref_fa, tag, n_chk=2):
         small = min(set(rh.df['#CHROM']), key=fa_r.length)
         pick = np.flatnonzero((rh.df['#CHROM'] == small).to_numpy())[:n_chk]
         sub = rh.df.iloc[pick]
-        fa_t = fasta_mod.open_fasta(rh.tig_fa_path)
-        ref_p, tig_p, _ = synth.write_cigar_workload(os.path.join(tmp, f'chk_{tag}'), {small: fa_r.fetch_array(small)},
-                                                     {q: fa_t.fetch_array(q) for q in sub['QRY_ID']}, sub)
+        tig_seqs = {q: fasta_mod.open_fasta(rh.tig_fa[h]).fetch_array(q) for q, h in zip(sub['QRY_ID'], sub['_HAP'])}
+        ref_p, tig_p, _ = synth.write_cigar_workload(os.path.join(tmp, f'chk_{tag}'), {small: fa_r.fetch_array(small)}, tig_seqs, sub)
         o_snv, o_indel, _ = pyoracle.walk_rows(sub, ref_p, tig_p)
         snv, indel, cerr = rh.batch.fetch()
         assert cerr.code == 0
@@ -539,7 +550,7 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
     _, b2, _, bm = ref_store.plane_sizes()
 
     # ---- this rank's records -> HBM
-    haps = [ResidentHap(ctx, h, dfs[h], plan[h][rank], tig_fa[h], ref_names) for h in ('h1', 'h2')]
+    haps = [ResidentShard(ctx, dfs, {h: plan[h][rank] for h in ('h1', 'h2')}, tig_fa, ref_names)]
     ctl.barrier()
 
     def step():
@@ -578,7 +589,7 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
     hom_kernel = max((int(s.homology_tiled) for s in sts), default=0)
     my_rows = n_snv + n_indel
     my_ms = float(np.mean(step_ms)) if step_ms else 0.0
-    parity = [oracle_check_records(rh, tmp, ref_fa, f'r{rank}_{rh.hap}') for rh in haps]
+    parity = [oracle_check_records(rh, tmp, ref_fa, f'r{rank}', n_chk=3) for rh in haps]
     per_rank = ctl.gather({'rank': rank, 'records': int(sum(len(rh.df) for rh in haps)), 'ops': n_ops, 'rows': my_rows, 'ms_per_step': my_ms,
                            'ms_count_scan': count_ms, 'ms_walk': walk_ms, 'ms_homology': hom_ms, 'ms_per_step_without_graph': nograph_ms,
                            'planes_checksum_equal_rank0': planes_ok[rank], 'oracle_spot_check': parity, 'graph': graph_used,
@@ -620,6 +631,26 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
     e2e_rows = int(ctl.max(e2e_rows))
     if e2e_s:
         assert e2e_rows == total_rows, (e2e_rows, total_rows)
+    # ---- the reference's own way of spreading this work: one job per batch of records (CALL_BATCH = INDEX % 10, rules/align.snakefile:163),
+    # every job formatting ITS rows into its own pair of tables (merged later by file concatenation, rule call_cigar_merge). Here: one
+    # batch per rank = its LPT shard, the public single-GPU call on it, no gather.
+    batch_s = []
+    if world > 1 and args.e2e_steps > 0:
+        for i in range(E2E_WARMUP + args.e2e_steps):
+            fasta_mod._CACHE.clear()
+            out = None
+            ctl.barrier()
+            t0 = time.perf_counter()
+            rows_b = 0
+            for h in ('h1', 'h2'):
+                out = cigarcall.make_insdel_snv_calls(dfs[h].iloc[plan[h][rank]], ref_fa, tig_fa[h], h, version_id=False)
+                rows_b += len(out[0]) + len(out[1])
+                out = None
+            dt = ctl.max(time.perf_counter() - t0)
+            assert rows_b == my_rows, (rows_b, my_rows)
+            if i >= E2E_WARMUP:
+                batch_s.append(dt)
+            log(f'[rank {rank}] e2e (one batch per rank) step {i}: {dt:.2f}s ({rows_b} rows on this rank)')
     contig_bytes = int(sum(fasta_mod.open_fasta(tig_fa[h]).length(n) for h in ('h1', 'h2') for n in set(dfs[h]['QRY_ID'])))
     # per e2e step: each of the two haplotype calls uploads the reference (ASCII, packing rank) and every rank its contigs and ops
     h2d = int(2 * info['reference_bp'] + contig_bytes + 4 * ctl.sum(n_ops))
@@ -637,8 +668,8 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
         'bound': 'hbm', 'kernel': dom, 'achieved': dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0, 'peak': peak, 'unit': 'GB/s',
         'frac': dom_bytes / (dom_ms * 1e-3) / 1e9 / peak if dom_ms > 0 else 0.0, 'traffic': None, 'peak_source': peak_src,
         'algorithmic_bytes_per_launch': int(dom_bytes), 'kernel_ms': dom_ms, 'per_kernel_ms': {k: v[0] for k, v in kernels.items()},
-        'per_kernel_ms_source': 'rank 0, both haplotype batches, the timed steps repeated without the CUDA graph (events between the launches); '
-                                'the timed steps themselves replay one graph per haplotype batch',
+        'per_kernel_ms_source': 'rank 0, the timed steps repeated without the CUDA graph (events between the launches); the timed steps themselves '
+                                'replay one graph (this rank\'s records of both haplotypes are one batch)',
         'step': {'algorithmic_bytes': int(step_bytes), 'achieved': step_bytes / (my_ms * 1e-3) / 1e9 if my_ms else None,
                  'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak if my_ms else None},
         'survey_8d_model': {'algorithmic_bytes': int(survey_bytes), 'achieved': survey_bytes / (my_ms * 1e-3) / 1e9 if my_ms else None,
@@ -658,6 +689,10 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
                         'every rank, per-rank walk, host gather, frames on rank 0)' if world > 1 else
                         'pav_b200.pavlib.cigarcall.make_insdel_snv_calls per haplotype (FASTA in, DataFrames out)'),
                 'phase_seconds_last_step_rank0': phases},
+        'e2e_batches': ({'value': total_rows / float(np.mean(batch_s)), 'unit': UNIT, 'ms_per_step': float(np.mean(batch_s)) * 1e3,
+                         'api': 'pavlib.cigarcall.make_insdel_snv_calls on one batch of records per rank (its LPT shard), every rank reading the FASTA files, '
+                                'uploading the reference itself and formatting its own tables -- the reference\'s CALL_BATCH model (rules/align.snakefile:163), no gather'}
+                        if batch_s else None),
         'info': info,
     }
 
@@ -932,7 +967,7 @@ def run_ours(args, rank, world, local):
                        'l2': 'flushed (256 MB memset) between iterations', 'parallelism': f'alignment records sharded over {world} GPU(s), LPT',
                        'alloc_tuning': 'PAVGPU_TUNE_ALLOC=1 for the end-to-end leg (opt-in glibc / pymalloc settings of the frame builder)',
                        'seconds_generate': info['seconds_generate'], 'seconds_write': info['seconds_write']},
-            'e2e': a['e2e'], 'gpu_launches': a['gpu_launches'], 'wall_ms_per_step_incl_flush': a['wall_ms_per_step_incl_flush'],
+            'e2e': a['e2e'], 'e2e_batches': a['e2e_batches'], 'gpu_launches': a['gpu_launches'], 'wall_ms_per_step_incl_flush': a['wall_ms_per_step_incl_flush'],
             'roofline': a['roofline'], 'cpu_baseline': cpu_a, 'clocks': a['clocks'], 'per_rank': a['per_rank'],
             'ref_broadcast_ms': a['ref_broadcast_ms'], 'ref_broadcast_bytes': a['ref_broadcast_bytes'], 'ref_pack_seconds_rank0': a['ref_pack_seconds_rank0'],
             'planes_verified_on_every_rank': a['planes_verified_on_every_rank'], 'oracle_spot_check': a['oracle_spot_check'],

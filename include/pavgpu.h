@@ -211,7 +211,7 @@ typedef struct {
     float ms_kmer, ms_kde, ms_fill;
     int64_t bases, rows, kde_pairs;
     int32_t kernel_launches;
-    int32_t kmer_tables_on_chip;   /* 1: reference k-mer tables lived in the distributed shared memory of one cluster per window */
+    int32_t kmer_tables_on_chip;   /* windows whose reference k-mer table was built and probed in shared memory (kmer_window_kernel); the rest used tables in HBM */
 } pavgpu_density_stats;
 
 void pavgpu_density_default_params(pavgpu_density_params *p);

@@ -5,24 +5,27 @@
 // (reference k-mer Counter), scipy.stats.gaussian_kde (float64 Gaussian KDE). SURVEY appendix A.2.
 //
 // One *batch* of windows is processed per call (one window = one run of scripts/density.py):
-//   D1 ref_insert_kernel   exact k-mers of the reference window -> per-window open-addressing table
-//                          (62-bit keys, counts; count > 100 or no k-mers => status 125)
+//   D1+D2 kmer_window_kernel  windows of up to 53,248 reference k-mers: one CTA per window, the reference k-mer table in shared memory
+//                          (16-bit positions into the staged planes instead of keys, canonical k-mers, one probe sequence per contig k-mer)
+//   D1 ref_insert_kernel   larger windows: exact k-mers of the reference window -> per-window open-addressing table in HBM
+//                          (62-bit keys + count of FURTHER copies: one atomic per distinct k-mer, two per repeat; more than 100
+//                          copies or no k-mers => status 125)
 //   D2 tig_state_kernel    contig k-mer + reverse complement, two probes -> STATE_MER per position
 //   -- host: keep-mask (state count >= 20), N, dense row offsets --
 //   D3 compact_kernel      order-preserving compaction of informative k-mers -> KMER / INDEX / STATE_MER
 //   D4 runs_stats_kernel   one pass: maximal runs of equal STATE_MER in INDEX_DEN space (start, length, state) and, per
 //                          state, n / mean / var(ddof=1) of INDEX_DEN (exact integer sums) -> bandwidth L_s and norm_s
-//   D5 kde_tree_kernel     T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both live
-//                          on the integer lattice, so N exps replace N * E exps; the table is the leaf level
-//                          of a binary sum tree (node i = node 2i + node 2i+1, all terms positive)
+//   D5 kde_table_kernel    T_s[d] = exp(-(d / L_s)^2 / 2), d in [0, N): data and evaluation points both live
+//                          on the integer lattice, so N exps replace N * E exps; beside it the suffix sums S_s[d] = T_s[d] + ... + T_s[N-1]
 //   D6 kde_eval_kernel     K_s(j) = norm_s * sum over runs [a,b] of state s of sum_{i=a..b} T_s[|i - j|]; the
-//                          inner sum is one or two range sums of the tree (<= 2 log2 N reads, no cancellation),
-//                          so a point costs O(#runs * log N) instead of O(N); 8 lanes share one point
+//                          inner sum is one or two range sums: S_s[lo] - S_s[hi + 1] (runs shorter than 8 are summed from T_s),
+//                          so a point costs O(#runs) instead of O(N); 8 lanes share one point
 //   D7 gap_classify_kernel per gap: state change / argmax change / |delta| > 0.005 => list of points that
 //                          need a full evaluation
 //   D6' kde_eval_kernel    on that list
-//   D8 interp_kernel       numpy.interp for the remaining gaps
-//   D9 finalize_kernel     spikes (> 1 -> reciprocal) and STATE = argmax (first max wins)
+//   D8/D9 finish_rows_kernel  one pass that writes every row: sampled values (kept in dense arrays of their own), numpy.interp for the
+//                          gaps not evaluated in full, spikes (> 1 -> reciprocal), STATE = argmax (first max wins)
+//   D10 state_rle_kernel   run lengths of STATE (the rl_encoder tuples)
 //
 // The k-mer of position g is read straight out of the 2-bit plane with a funnel shift (no rolling
 // state, so every position is independent); validity is k zero bits of the N-mask plane, which is
@@ -32,11 +35,8 @@
 #include <cstdlib>
 #include <cstring>
 
-#include <cooperative_groups.h>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -56,7 +56,7 @@ struct WinPlan {  // per window, device-visible
     // tables
     int64_t tab_off;              // slot offset of this window's hash table
     int32_t tab_log2;             // log2(capacity)
-    int32_t pad0;
+    int32_t mode;                 // k-mer part: 0 = global tables (ref_insert + tig_state), 1 = kmer_window_kernel, 2 = already done
     int64_t pos_off;              // offset of this window in the per-position scratch (tig positions)
     int64_t tile_off;             // offset of this window's tiles in the per-tile count array
     // after the first host sync
@@ -74,7 +74,7 @@ struct WinCounts {  // written by D1 / D2
     unsigned long long ref_valid;
     unsigned int ref_max;
     unsigned int cnt[3];
-    unsigned int overflow;        // kmer_cluster_kernel: a table partition filled up (the batch is redone with the global tables)
+    unsigned int overflow;        // kmer_window_kernel: a k-mer count went above what its 6 bits decide (the window is redone with the global tables)
     unsigned int pad;
 };
 
@@ -92,6 +92,7 @@ ref_insert_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes 
 {
     int32_t w = win_base + blockIdx.y;
     const WinPlan P = plan[w];
+    if (P.mode != 0) return;
     int32_t n_pos = P.ref_len - k + 1;
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
@@ -106,10 +107,8 @@ ref_insert_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes 
         uint64_t slot = hash_kmer(kmer, P.tab_log2);
         while (true) {
             unsigned long long old = atomicCAS((unsigned long long *)(tk + slot), (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
-            if (old == EMPTY_KEY || old == kmer) {
-                my_cnt = atomicAdd(tc + slot, 1u) + 1u;
-                break;
-            }
+            if (old == EMPTY_KEY) { my_cnt = 1u; break; }            // first copy of this k-mer: the slot's count stays 0 = "no further copies"
+            if (old == kmer) { my_cnt = atomicAdd(tc + slot, 1u) + 2u; break; }   // a further copy: only these pay a second atomic (rare outside repeats)
             slot = (slot + 1) & mask;
         }
     }
@@ -148,6 +147,7 @@ tig_state_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes t
 {
     int32_t w = win_base + blockIdx.y;
     const WinPlan P = plan[w];
+    if (P.mode != 0) return;
     int32_t n_pos = P.tig_len - k + 1;
     int32_t n_tiles = (max(n_pos, 0) + TILE - 1) / TILE;
     if ((int)blockIdx.x >= n_tiles) return;
@@ -176,122 +176,189 @@ tig_state_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes t
 }
 
 // D1 + D2 on chip --------------------------------------------------------------------------------------
-// One thread-block cluster of 8 CTAs per window; the window's reference k-mer table lives in the DISTRIBUTED SHARED MEMORY of
-// the cluster -- 8 x 16,384 slots of 8-byte keys + 16-bit counts = 160 KB per CTA -- and never touches L2 or HBM. The hash of a
-// k-mer picks the owning CTA (top 3 bits) and the slot inside it (next 14 bits; linear probing stays inside the owner's part);
-// inserts are remote shared-memory atomics (CAS on the key, add on the packed count), probes remote shared-memory loads. Every
-// position of the window is k-merised once (CTA r takes positions r * 1024 + t, stride 8,192 -- no redundant arithmetic), and
-// the contig pass keeps tig_state_kernel's tile structure so its outputs (state per position, counts per 1,024-position tile)
-// feed the same compaction. ncu on the global-table kernels (profiles/r02_ncu_density_296win.txt): ref_insert 0.52 ms moving
-// 810 MB of DRAM sectors for 14.8 M inserts into 444 MB of tables (plus their memsets), tig_state 0.31 ms.
-// Opt-in (PAVGPU_DENSITY_CLUSTER_TABLES=1) for batches whose windows all have at most KC_MAX_REF reference k-mers (load factor
-// <= 0.5); larger windows, or a partition that fills up (flagged in WinCounts.overflow), take the global-table kernels. Measured
-// slower than them on B200 (1.42 ms against 0.81 ms for 296 windows x 50 kbp): see the note at the launch site.
-constexpr int KC_CLUSTER = 8;
-constexpr int KC_THREADS = 1024;
-constexpr int KC_LOG2_SLOTS = 14;
-constexpr int KC_SLOTS = 1 << KC_LOG2_SLOTS;                 // per CTA
-constexpr int KC_MAX_REF = KC_CLUSTER * KC_SLOTS / 2;        // 65,536 reference k-mers per window
-constexpr size_t KC_SMEM = (size_t)KC_SLOTS * 8 + (size_t)KC_SLOTS * 2;
-static_assert(KC_CLUSTER == 8, "the owner is the top three hash bits");
+// One 1,024-thread CTA per window; the window's reference k-mer table lives in the shared memory of its SM and never touches L2
+// or HBM. What makes it fit: the table does not hold keys. The CTA first stages the window's slice of the packed reference planes
+// (12 bytes per 32 bases: 20 KB for 50 kbp); a slot then holds the 16-bit POSITION of the first copy of its k-mer, and a probe
+// re-derives that k-mer from the staged planes to compare. k-mers are stored canonically (the smaller of the k-mer and its reverse
+// complement), with one byte per slot beside the position: bit 0 / bit 1 = "seen in this / the other orientation", bits 2-7 = copies
+// seen in either. A contig k-mer therefore costs ONE probe sequence, not one per orientation, and contig k-mers that are in the
+// reference in either orientation -- nearly all of them -- end on a hit. 65,536 slots x 3 bytes = 192 KB + 20 KB of planes.
+//   * windows with at most KS_MAX_REF reference k-mers take this kernel (WinPlan.mode 1), larger ones the global tables (mode 0);
+//   * MAX_REF_KMER_COUNT (density.py:47, :510-527) asks whether some ORIENTED k-mer has more than that many copies. The 6-bit
+//     count is of both orientations together, so "no count above min(limit, 60)" proves the answer is no; a window where some count
+//     goes above that is flagged (WinCounts.overflow) and redone with the global tables, which count exactly.
+// Measured on B200 (r02, 296 windows x 50 kbp): see DESIGN.md section 6.1; the r02 attempt with the table spread over the distributed shared
+// memory of an 8-CTA cluster (8-byte keys, remote atomics) took 1.42 ms against 0.81 ms for the global tables and was removed.
+constexpr int KS_THREADS = 1024;
+constexpr int KS_MAX_LOG2 = 16;
+constexpr int KS_MAX_REF = 53248;                                   // reference k-mers per window: load <= 0.8125
+constexpr int KS_SEQ_WORDS = 1672;                                  // plane words staged: (31 + KS_MAX_REF + 30 + 31) / 32 + 1, rounded up
+constexpr int KS_CNT_LIMIT = 60;
+constexpr int KS_MAX_TILES = 256;                                   // contig tiles (of 1,024 positions) whose counters fit beside the table
+constexpr unsigned KS_EMPTY = 0xFFFFu;
+constexpr size_t KS_SMEM = ((size_t)3 << KS_MAX_LOG2) + (size_t)KS_SEQ_WORDS * 12;
+static_assert((31 + KS_MAX_REF + 30 + 31) / 32 + 1 <= KS_SEQ_WORDS, "staging area too small");
+static_assert(KS_SMEM + KS_MAX_TILES * 12 + 1024 <= 227 * 1024, "does not fit the shared memory of an SM");
 
-__device__ __forceinline__ void kc_locate(uint64_t kmer, unsigned &owner, unsigned &slot)
+// k-mer at base `g` of the staged slice (plain shared-memory loads; kmer_at is the same arithmetic on the planes in HBM)
+__device__ __forceinline__ uint64_t kmer_staged(const uint64_t *sp, int32_t g, int k)
 {
-    const uint64_t h = kmer * 0x9E3779B97F4A7C15ull;
-    owner = (unsigned)(h >> 61);
-    slot = (unsigned)(h >> (61 - KC_LOG2_SLOTS)) & (KC_SLOTS - 1);
+    const int32_t w = g >> 5;
+    const int s = g & 31;
+    const uint64_t hi = sp[w], lo = sp[w + 1];
+    const uint64_t x = s ? ((hi << (2 * s)) | (lo >> (64 - 2 * s))) : hi;
+    return x >> (64 - 2 * k);
 }
 
-__device__ __forceinline__ bool kc_has(cg::cluster_group &cluster, uint64_t *keys, uint64_t key)
+__device__ __forceinline__ bool kmer_staged_valid(const uint32_t *sm, int32_t g, int k)
 {
-    unsigned owner, slot;
-    kc_locate(key, owner, slot);
-    const uint64_t *rk = cluster.map_shared_rank(keys, owner);
-    for (int probe = 0; probe < KC_SLOTS; probe++) {
-        const uint64_t v = rk[slot];
-        if (v == key) return true;
-        if (v == EMPTY_KEY) return false;
-        slot = (slot + 1) & (KC_SLOTS - 1);
-    }
-    return false;
+    const int32_t w = g >> 5;
+    const uint64_t m = ((uint64_t)sm[w] | ((uint64_t)sm[w + 1] << 32)) >> (g & 31);
+    return (m & ((1ull << k) - 1)) == 0;
 }
 
-__global__ void __cluster_dims__(KC_CLUSTER, 1, 1) __launch_bounds__(KC_THREADS, 1)
-kmer_cluster_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes ref, SeqPlanes tig, int k, int8_t *__restrict__ st_pos,
-                    uint32_t *__restrict__ tile_cnt, WinCounts *__restrict__ wc)
+__global__ void __launch_bounds__(KS_THREADS, 1)
+kmer_window_kernel(const WinPlan *__restrict__ plan, SeqPlanes ref, SeqPlanes tig, int k, unsigned cnt_limit, int8_t *__restrict__ st_pos,
+                   uint32_t *__restrict__ tile_cnt, WinCounts *__restrict__ wc)
 {
-    extern __shared__ __align__(16) unsigned char kc_smem[];
-    uint64_t *keys = reinterpret_cast<uint64_t *>(kc_smem);
-    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(kc_smem + (size_t)KC_SLOTS * 8);   // two 16-bit counts per word
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned crank = cluster.block_rank();
-    const int32_t w = win_base + (int32_t)(blockIdx.x / KC_CLUSTER);
+    extern __shared__ __align__(16) unsigned char ks_smem[];
+    unsigned short *pos16 = reinterpret_cast<unsigned short *>(ks_smem);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(ks_smem + ((size_t)2 << KS_MAX_LOG2));          // one byte per slot
+    uint64_t *sp = reinterpret_cast<uint64_t *>(ks_smem + ((size_t)3 << KS_MAX_LOG2));
+    uint32_t *sm = reinterpret_cast<uint32_t *>(ks_smem + ((size_t)3 << KS_MAX_LOG2) + (size_t)KS_SEQ_WORDS * 8);
+    __shared__ unsigned s_tile[KS_MAX_TILES * 3];
+    const int32_t w = blockIdx.x;
     const WinPlan P = plan[w];
-    for (int i = threadIdx.x; i < KC_SLOTS; i += KC_THREADS) keys[i] = EMPTY_KEY;
-    for (int i = threadIdx.x; i < KC_SLOTS / 2; i += KC_THREADS) cnt32[i] = 0u;
-    cluster.sync();
-    // ---- reference k-mers -> the cluster's table
+    if (P.mode != 1) return;
+    const int lg = max(min(P.tab_log2, KS_MAX_LOG2), 8);
+    const unsigned slots = 1u << lg, mask = slots - 1;
+    {
+        const uint4 ff = make_uint4(~0u, ~0u, ~0u, ~0u), zz = make_uint4(0u, 0u, 0u, 0u);
+        for (unsigned i = threadIdx.x; i < slots / 8; i += KS_THREADS) reinterpret_cast<uint4 *>(pos16)[i] = ff;
+        for (unsigned i = threadIdx.x; i < slots / 16; i += KS_THREADS) reinterpret_cast<uint4 *>(meta)[i] = zz;
+    }
+    const int64_t w0 = P.ref_g0 >> 5;
+    const int32_t off = (int32_t)(P.ref_g0 & 31);
     const int32_t n_ref = P.ref_len - k + 1;
+    const int32_t nw = (off + P.ref_len + 31) / 32 + 1;
+    for (int32_t i = threadIdx.x; i < nw; i += KS_THREADS) { sp[i] = __ldg(ref.pack2 + w0 + i); sm[i] = __ldg(ref.nmask + w0 + i); }
+    __syncthreads();
+    // Probing: double hashing (the step is an odd number from other bits of the hash, so a sequence visits every slot). Shared memory
+    // has no lines to stay inside, and at the load this table runs at (up to 0.81) linear probing's clusters cost 9 probes per miss
+    // and tails of 40 and more in a warp; double hashing 4 and ~15.
+    // Lanes STREAM: a lane whose k-mer is settled takes its next position in the same trip of the loop instead of waiting for the
+    // slowest probe sequence of the warp (ncu, r02, with every lane waiting: 10.8 of 32 lanes active per instruction, issue-bound).
+    // ---- reference k-mers -> table
     unsigned n_valid = 0, my_max = 0, over = 0;
-    for (int32_t i = (int32_t)crank * KC_THREADS + threadIdx.x; i < n_ref; i += KC_CLUSTER * KC_THREADS) {
-        uint64_t kmer;
-        if (!kmer_at(ref.pack2, ref.nmask, P.ref_g0 + i, k, kmer, ref.nsum)) continue;
-        n_valid++;
-        if (P.rev) kmer = kmer_revcomp(kmer, k);  // density.py:538-539: the reference SET is reverse-complemented
-        unsigned owner, slot;
-        kc_locate(kmer, owner, slot);
-        uint64_t *rk = cluster.map_shared_rank(keys, owner);
-        uint32_t *rc = cluster.map_shared_rank(cnt32, owner);
-        bool placed = false;
-        for (int probe = 0; probe < KC_SLOTS; probe++) {
-            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(rk + slot), (unsigned long long)EMPTY_KEY, (unsigned long long)kmer);
-            if (old == EMPTY_KEY || old == kmer) {
-                const unsigned sh = 16u * (slot & 1u);
-                const unsigned c = ((atomicAdd(rc + (slot >> 1), 1u << sh) >> sh) & 0xffffu) + 1u;   // (a window has <= 65,536 reference k-mers: no carry)
-                my_max = max(my_max, c);
-                placed = true;
-                break;
+    {
+        int32_t next = threadIdx.x, i = 0;
+        bool act = false;
+        uint64_t raw = 0, rcr = 0;
+        unsigned slot = 0, step = 0, o = 0;
+        while (true) {
+            if (!act && next < n_ref) {
+                i = next; next += KS_THREADS;
+                if (kmer_staged_valid(sm, off + i, k)) {
+                    n_valid++;
+                    raw = kmer_staged(sp, off + i, k); rcr = kmer_revcomp(raw, k);
+                    const uint64_t kmer = P.rev ? rcr : raw;          // density.py:538-539: the reference SET is reverse-complemented
+                    const uint64_t other = P.rev ? raw : rcr;
+                    o = kmer > other ? 1u : 0u;                       // orientation of `kmer` relative to the canonical form
+                    const uint64_t h = (o ? other : kmer) * 0x9E3779B97F4A7C15ull;
+                    slot = (unsigned)(h >> (64 - lg)); step = ((unsigned)(h >> 7) | 1u) & mask;
+                    act = true;
+                }
             }
-            slot = (slot + 1) & (KC_SLOTS - 1);
+            if (!__any_sync(FULL, act || next < n_ref)) break;
+            if (act) {
+                unsigned cur = *reinterpret_cast<volatile unsigned short *>(pos16 + slot);
+                if (cur == KS_EMPTY) {
+                    cur = atomicCAS(pos16 + slot, (unsigned short)KS_EMPTY, (unsigned short)i);
+                    if (cur == KS_EMPTY) cur = (unsigned)i;
+                }
+                bool same = cur == (unsigned)i;
+                if (!same) { const uint64_t k2 = kmer_staged(sp, off + (int32_t)cur, k); same = (k2 == raw) || (k2 == rcr); }
+                if (same) {
+                    const unsigned sh = 8u * (slot & 3u);
+                    const unsigned old = atomicAdd(meta + (slot >> 2), 4u << sh) >> sh;
+                    if (!((old >> o) & 1u)) atomicOr(meta + (slot >> 2), (1u << o) << sh);
+                    const unsigned c = ((old >> 2) & 63u) + 1u;
+                    my_max = max(my_max, c);
+                    if (c > cnt_limit) over = 1u;             // flagged before the 6-bit field can carry into its neighbour
+                    act = false;
+                } else slot = (slot + step) & mask;
+            }
         }
-        if (!placed) over = 1;
+    }
+    if (__syncthreads_or((int)over)) {                        // redone with the global tables; nothing of this window is used
+        if (threadIdx.x == 0) atomicOr(&wc[w].overflow, 1u);
+        return;
     }
     {
-        const unsigned nv = __reduce_add_sync(FULL, n_valid), mx = __reduce_max_sync(FULL, my_max), ov = __reduce_or_sync(FULL, over);
+        const unsigned nv = __reduce_add_sync(FULL, n_valid), mx = __reduce_max_sync(FULL, my_max);
         if ((threadIdx.x & 31) == 0) {
             if (nv) atomicAdd(&wc[w].ref_valid, (unsigned long long)nv);
-            if (mx) atomicMax(&wc[w].ref_max, mx);
-            if (ov) atomicOr(&wc[w].overflow, 1u);
+            if (mx) atomicMax(&wc[w].ref_max, mx);            // an upper bound of the oriented maximum, <= the limit here
         }
     }
-    cluster.sync();   // every insert of the cluster has landed
-    // ---- contig k-mers: state per position, counts per 1,024-position tile (tile t is CTA t % 8's)
+    // ---- contig k-mers: state per position, counts per 1,024-position tile (tig_state_kernel's outputs)
     const int32_t n_pos = P.tig_len - k + 1;
     const int32_t n_tiles = (max(n_pos, 0) + TILE - 1) / TILE;
-    for (int32_t t = (int32_t)crank; t < n_tiles; t += KC_CLUSTER) {
-        const int32_t i = t * TILE + threadIdx.x;
-        int st = -1;
-        if (i < n_pos) {
-            uint64_t kmer;
-            if (kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer, tig.nsum)) {
-                const bool f = kc_has(cluster, keys, kmer);
-                const bool r = kc_has(cluster, keys, kmer_revcomp(kmer, k));
-                st = f ? (r ? 1 : 0) : (r ? 2 : -1);  // KMER_ORIENTATION_STATE, density.py:38-43
+    for (int32_t t = threadIdx.x; t < n_tiles * 3; t += KS_THREADS) s_tile[t] = 0u;
+    __syncthreads();
+    {
+        int32_t next = threadIdx.x, i = 0;
+        bool act = false;
+        uint64_t km = 0, rc = 0;
+        unsigned slot = 0, step = 0;
+        while (true) {
+            if (!act && next < n_pos) {
+                i = next; next += KS_THREADS;
+                if (kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, km, tig.nsum)) {
+                    rc = kmer_revcomp(km, k);
+                    const uint64_t h = (km > rc ? rc : km) * 0x9E3779B97F4A7C15ull;
+                    slot = (unsigned)(h >> (64 - lg)); step = ((unsigned)(h >> 7) | 1u) & mask;
+                    act = true;
+                } else st_pos[P.pos_off + i] = (int8_t)-1;
             }
-            st_pos[P.pos_off + i] = (int8_t)st;
-        }
-        const unsigned c0 = __syncthreads_count(st == 0);
-        const unsigned c1 = __syncthreads_count(st == 1);
-        const unsigned c2 = __syncthreads_count(st == 2);
-        if (threadIdx.x == 0) {
-            uint32_t *tc = tile_cnt + (P.tile_off + t) * 3;
-            tc[0] = c0; tc[1] = c1; tc[2] = c2;
-            if (c0) atomicAdd(&wc[w].cnt[0], c0);
-            if (c1) atomicAdd(&wc[w].cnt[1], c1);
-            if (c2) atomicAdd(&wc[w].cnt[2], c2);
+            if (!__any_sync(FULL, act || next < n_pos)) break;
+            if (act) {
+                const unsigned cur = pos16[slot];
+                int st = -2;                                   // -2: keep probing
+                if (cur == KS_EMPTY) st = -1;                  // in neither orientation
+                else {
+                    const uint64_t k2 = kmer_staged(sp, off + (int32_t)cur, k);
+                    if (k2 == km || k2 == rc) {
+                        const unsigned bits = (meta[slot >> 2] >> (8u * (slot & 3u))) & 3u;
+                        const unsigned o = km > rc ? 1u : 0u;
+                        const bool f = (bits >> o) & 1u;
+                        const bool r = (km == rc) ? f : ((bits >> (o ^ 1u)) & 1u);
+                        st = f ? (r ? 1 : 0) : (r ? 2 : -1);  // KMER_ORIENTATION_STATE, density.py:38-43
+                    }
+                }
+                if (st == -2) slot = (slot + step) & mask;
+                else {
+                    st_pos[P.pos_off + i] = (int8_t)st;
+                    if (st >= 0) atomicAdd(&s_tile[(i / TILE) * 3 + st], 1u);
+                    act = false;
+                }
+            }
         }
     }
-    cluster.sync();   // nobody leaves while its part of the table may still be read
+    __syncthreads();
+    unsigned t0 = 0, t1 = 0, t2 = 0;
+    for (int32_t t = threadIdx.x; t < n_tiles; t += KS_THREADS) {
+        uint32_t *tc = tile_cnt + (P.tile_off + t) * 3;
+        const unsigned c0 = s_tile[t * 3], c1 = s_tile[t * 3 + 1], c2 = s_tile[t * 3 + 2];
+        tc[0] = c0; tc[1] = c1; tc[2] = c2;
+        t0 += c0; t1 += c1; t2 += c2;
+    }
+    t0 = __reduce_add_sync(FULL, t0); t1 = __reduce_add_sync(FULL, t1); t2 = __reduce_add_sync(FULL, t2);
+    if ((threadIdx.x & 31) == 0 && (t0 | t1 | t2)) {
+        if (t0) atomicAdd(&wc[w].cnt[0], t0);
+        if (t1) atomicAdd(&wc[w].cnt[1], t1);
+        if (t2) atomicAdd(&wc[w].cnt[2], t2);
+    }
 }
 
 // D3 ---------------------------------------------------------------------------------------------
@@ -327,8 +394,14 @@ compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) s_warp[wid] = __popc(bal);
     __syncthreads();
-    unsigned before = 0;
-    for (int q = 0; q < wid; q++) before += s_warp[q];
+    if (wid == 0) {   // exclusive scan of the 32 warp counts by one warp (was: every thread summing up to 31 counts)
+        unsigned c = s_warp[lane], inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+        s_warp[lane] = inc - c;
+    }
+    __syncthreads();
+    const unsigned before = s_warp[wid];
     if (keep) {
         int64_t row = P.row_off + s_base + before + __popc(bal & ((1u << lane) - 1));
         uint64_t kmer = 0;
@@ -368,35 +441,44 @@ runs_stats_kernel(const WinPlan *__restrict__ plan, const int8_t *__restrict__ s
     const int32_t N = P.n_rows;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __shared__ int s_warp[32];
-    __shared__ int s_base;
+    __shared__ int s_total;
     __shared__ unsigned long long s_buf[32];
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
+    // every thread owns a contiguous slice of the rows: its run heads are counted, ranked by a block scan and written; the sums
+    // for the bandwidths come from the same pass (r01 walked the column 1,024 rows at a time with three barriers per step)
+    const int32_t per = (N + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
+    const int32_t lo = min((int32_t)threadIdx.x * per, N), hi = min(lo + per, N);
     unsigned long long cn[3] = {0, 0, 0}, c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
-    for (int32_t i0 = 0; i0 < N; i0 += blockDim.x) {   // order-preserving compaction of run heads, 1024 rows per step
-        int32_t i = i0 + threadIdx.x;
-        int st = (i < N) ? (int)sm[i] : -1;
-        bool head = (i < N) && (i == 0 || st != (int)sm[i - 1]);
-        if (st >= 0) {
+    int cnt = 0;
+    {
+        int prev = lo > 0 ? (int)sm[lo - 1] : -2;
+        for (int32_t i = lo; i < hi; i++) {
+            const int st = (int)sm[i];
+            cnt += (st != prev) ? 1 : 0;
+            prev = st;
 #pragma unroll
             for (int s = 0; s < 3; s++)
                 if (st == s) { cn[s] += 1; c1[s] += (unsigned long long)i; c2[s] += (unsigned long long)i * (unsigned long long)i; }
         }
-        unsigned bal = __ballot_sync(FULL, head);
-        if (lane == 0) s_warp[wid] = __popc(bal);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int q = 0; q < 32; q++) { int c = s_warp[q]; if (q < wid) before += c; total += c; }
-        if (head) {
-            int32_t r = s_base + before + __popc(bal & ((1u << lane) - 1));
-            run_start[P.row_off + r] = i;
-            run_state[P.row_off + r] = (int8_t)st;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += total;
-        __syncthreads();
     }
-    int32_t nr = s_base;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int before = 0;
+    for (int q = 0; q < wid; q++) before += s_warp[q];
+    if (threadIdx.x == blockDim.x - 1) s_total = before + inc;
+    {
+        int32_t r = before + inc - cnt;
+        int prev = lo > 0 ? (int)sm[lo - 1] : -2;
+        for (int32_t i = lo; i < hi; i++) {
+            const int st = (int)sm[i];
+            if (st != prev) { run_start[P.row_off + r] = i; run_state[P.row_off + r] = (int8_t)st; r++; }
+            prev = st;
+        }
+    }
+    __syncthreads();
+    int32_t nr = s_total;
     for (int32_t r = threadIdx.x; r < nr; r += blockDim.x) {
         int32_t a = run_start[P.row_off + r];
         int32_t e = (r + 1 < nr) ? run_start[P.row_off + r + 1] : N;
@@ -442,11 +524,12 @@ kde_table_kernel(const WinPlan *__restrict__ plan, const KdeParams *__restrict__
     double *T = (s == 0 ? tab0 : (s == 1 ? tab1 : tab2)) + P.tree_off;
     const int32_t N = P.n_rows;
     double *S = T + N;
+    // exp(-(d / L)^2 / 2) as exp(-(d * d) * c), c = 1 / (2 L^2): d * d is an exact integer, so the argument carries the rounding of c and of
+    // one product -- as many roundings as (d / L) squared, without a float64 division per element (this kernel is bound by float64
+    // arithmetic: ~38 M exp for 296 windows)
     const double L = kp[w].L[s];
-    for (int32_t d = threadIdx.x; d < N; d += blockDim.x) {
-        const double x = (double)d / L;
-        T[d] = exp(-(x * x) / 2.0);
-    }
+    const double c = 1.0 / (2.0 * (L * L));
+    for (int32_t d = threadIdx.x; d < N; d += blockDim.x) T[d] = exp(-((double)((int64_t)d * d) * c));
     __shared__ double s_warp[TREE_THREADS / 32];
     __shared__ double s_carry;
     if (threadIdx.x == 0) { s_carry = 0.0; S[N] = 0.0; }
@@ -553,10 +636,11 @@ kde_eval_kernel(const WinPlan *__restrict__ plan, int32_t n_win, const int64_t *
         a1 += __shfl_xor_sync(FULL, a1, d);
         a2 += __shfl_xor_sync(FULL, a2, d);
     }
-    if (j >= 0 && sub == 0) {
-        k0[P.row_off + j] = a0 * kp[w].norm[0];
-        k1[P.row_off + j] = a1 * kp[w].norm[1];
-        k2[P.row_off + j] = a2 * kp[w].norm[2];
+    if (j >= 0 && sub == 0) {   // mode 0: the e-th sample, kept densely (row_off + e); mode 1: the row itself
+        const int64_t o = P.row_off + (mode == 0 ? e : j);
+        k0[o] = a0 * kp[w].norm[0];
+        k1[o] = a1 * kp[w].norm[1];
+        k2[o] = a2 * kp[w].norm[2];
     }
 }
 
@@ -582,7 +666,7 @@ gap_classify_kernel(const WinPlan *__restrict__ plan, double delta, const int8_t
     int32_t N = P.n_rows, srs = P.srs;
     int32_t n_gap = P.n_samp - 1;
     const int8_t *sm = state_mer + P.row_off;
-    const double *a0 = k0 + P.row_off, *a1 = k1 + P.row_off, *a2 = k2 + P.row_off;
+    const double *a0 = k0 + P.row_off, *a1 = k1 + P.row_off, *a2 = k2 + P.row_off;   // the SAMPLED values: entry g = row g * srs, the last = row N - 1
     __shared__ int s_scan[256];
     __shared__ int s_base;
     if (threadIdx.x == 0) s_base = 0;
@@ -595,10 +679,10 @@ gap_classify_kernel(const WinPlan *__restrict__ plan, double delta, const int8_t
             a = g * srs;
             b = min(a + srs, N - 1);
             if (b > a + 1) {
-                bool change = argmax3(a0[a], a1[a], a2[a]) != argmax3(a0[b], a1[b], a2[b]);
+                bool change = argmax3(a0[g], a1[g], a2[g]) != argmax3(a0[g + 1], a1[g + 1], a2[g + 1]);
                 int8_t s0 = sm[a];
                 for (int32_t i = a + 1; i <= b && !change; i++) change = sm[i] != s0;
-                double dm = fmax(fabs(a0[a] - a0[b]), fmax(fabs(a1[a] - a1[b]), fabs(a2[a] - a2[b])));
+                double dm = fmax(fabs(a0[g] - a0[g + 1]), fmax(fabs(a1[g] - a1[g + 1]), fabs(a2[g] - a2[g + 1])));
                 bool full = change || dm > delta;
                 gap_full[P.row_off + g] = full ? 1 : 0;
                 cnt = full ? (b - a - 1) : 0;
@@ -625,49 +709,97 @@ gap_classify_kernel(const WinPlan *__restrict__ plan, double delta, const int8_t
 }
 
 // D8 / D9 ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-interp_kernel(const WinPlan *__restrict__ plan, int32_t win_base, const uint8_t *__restrict__ gap_full, double *__restrict__ k0,
-              double *__restrict__ k1, double *__restrict__ k2)
+// One pass that WRITES every row of the three KERN columns and STATE: a sampled row takes its value from the dense sample arrays
+// kde_eval_kernel (mode 0) filled, a row of a gap evaluated in full keeps the value kde_eval_kernel (mode 1) wrote, every other row is
+// numpy.interp between the two samples around it (`slope * (x - x0) + y0`, from the RAW sampled values); then the spike rule
+// (`> 1 -> 1 / x`, density.py:330-332; pandas aligns the right-hand frame on the column, so it is an element-wise reciprocal) and
+// STATE = argmax, first maximum wins (:335-338).
+// (Why the samples live in their own arrays: with the samples inside the columns, reading one row in `srs` = 20 pulled nearly every
+// 128-byte line of the columns through L2 -- ncu, 296 windows: 248 MB read by this kernel, 243 MB by the separate spike pass over the
+// sampled rows and 256 MB by gap_classify_kernel, for 15 MB of samples.)
+// y / x for an integer-valued x with r = 1 / x already at hand: q = y * r, then one correction with the exact remainder (Markstein: with r the
+// correctly rounded reciprocal, fma(fma(-q, x, y), r, q) is y / x correctly rounded -- bit for bit what the division returns). The remainder
+// must not underflow for that, so differences below 2^-900 (densities thousands of bandwidths from their data) take the division itself.
+__device__ __forceinline__ double div_by_int(double y, double x, double r)
 {
-    int32_t w = win_base + blockIdx.y;
-    const WinPlan P = plan[w];
-    if (!P.smoothed) return;
-    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    int32_t N = P.n_rows;
-    if (j >= N) return;
-    int32_t g = j / P.srs;
-    int32_t a = g * P.srs, b = min(a + P.srs, N - 1);
-    if (j == a || j == b || gap_full[P.row_off + g]) return;
-    double *ks[3] = {k0 + P.row_off, k1 + P.row_off, k2 + P.row_off};
-#pragma unroll
-    for (int s = 0; s < 3; s++) {  // numpy.interp: slope * (x - x0) + y0
-        double ya = ks[s][a], yb = ks[s][b];
-        double slope = (yb - ya) / ((double)b - (double)a);
-        ks[s][j] = slope * ((double)j - (double)a) + ya;
-    }
+    if (fabs(y) < 0x1p-900 && y != 0.0) return y / x;
+    const double q = y * r;
+    return fma(fma(-q, x, y), r, q);
 }
 
+constexpr int FIN_ROWS = 4;      // rows per thread: the dependent loads (plan, gap flag, values) of FIN_ROWS rows overlap
+
 __global__ void __launch_bounds__(256)
-finalize_kernel(const WinPlan *__restrict__ plan, int32_t win_base, double *__restrict__ k0, double *__restrict__ k1, double *__restrict__ k2,
-                int8_t *__restrict__ state)
+finish_rows_kernel(const WinPlan *__restrict__ plan, int32_t win_base, const uint8_t *__restrict__ gap_full, const double *__restrict__ s0,
+                   const double *__restrict__ s1, const double *__restrict__ s2, double *__restrict__ k0, double *__restrict__ k1,
+                   double *__restrict__ k2, int8_t *__restrict__ state)
 {
-    int32_t w = win_base + blockIdx.y;
+    const int32_t w = win_base + blockIdx.y;
     const WinPlan P = plan[w];
     if (P.status != 0) return;
-    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n_rows) return;
-    int64_t r = P.row_off + j;
+    const int32_t N = P.n_rows;
+    const int32_t j0 = blockIdx.x * (256 * FIN_ROWS) + threadIdx.x;
+    if (j0 >= N) return;
     if (!P.smoothed) {
-        state[r] = -1;
-        double nan = __longlong_as_double(0x7ff8000000000000ll);
-        k0[r] = nan; k1[r] = nan; k2[r] = nan;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+        for (int q = 0; q < FIN_ROWS; q++) {
+            const int32_t j = j0 + q * 256;
+            if (j < N) { const int64_t r = P.row_off + j; state[r] = -1; k0[r] = nan; k1[r] = nan; k2[r] = nan; }
+        }
         return;
     }
-    double a = k0[r], b = k1[r], c = k2[r];
-    if (a > 1.0) { a = 1.0 / a; k0[r] = a; }   // density.py:330-332
-    if (b > 1.0) { b = 1.0 / b; k1[r] = b; }
-    if (c > 1.0) { c = 1.0 / c; k2[r] = c; }
-    state[r] = (int8_t)argmax3(a, b, c);
+    double *ks[3] = {k0 + P.row_off, k1 + P.row_off, k2 + P.row_off};
+    const double *ss[3] = {s0 + P.row_off, s1 + P.row_off, s2 + P.row_off};
+    int32_t g[FIN_ROWS], a[FIN_ROWS], b[FIN_ROWS];
+    bool in[FIN_ROWS], sampled[FIN_ROWS], interp[FIN_ROWS];
+#pragma unroll
+    for (int q = 0; q < FIN_ROWS; q++) {
+        const int32_t j = j0 + q * 256;
+        in[q] = j < N;
+        g[q] = j / P.srs;
+        a[q] = g[q] * P.srs; b[q] = min(a[q] + P.srs, N - 1);
+        sampled[q] = (j == a[q]) || (j == N - 1);
+        interp[q] = in[q] && !sampled[q] && !gap_full[P.row_off + g[q]];
+    }
+    double ya[FIN_ROWS][3], yb[FIN_ROWS][3];
+#pragma unroll
+    for (int q = 0; q < FIN_ROWS; q++) {
+        const int32_t j = j0 + q * 256;
+        const int32_t e = (j == a[q]) ? g[q] : g[q] + 1;          // a sampled row's entry: its lattice point, or the last sample for row N - 1
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            ya[q][s] = !in[q] ? 0.0 : (sampled[q] ? ss[s][e] : (interp[q] ? ss[s][g[q]] : ks[s][j]));
+            yb[q][s] = interp[q] ? ss[s][g[q] + 1] : 0.0;
+        }
+    }
+    // x1 - x0 is `srs` for every gap but the last one of a window: one reciprocal per thread instead of three divisions per row
+    // (ncu, r02: this kernel was issuing 350 instructions per row, most of them float64 division sequences)
+    const double r_srs = 1.0 / (double)P.srs;
+    double dx[FIN_ROWS], rdx[FIN_ROWS];
+#pragma unroll
+    for (int q = 0; q < FIN_ROWS; q++) {
+        dx[q] = (double)(b[q] - a[q]);
+        rdx[q] = r_srs;
+        if (interp[q] && b[q] - a[q] != P.srs) rdx[q] = 1.0 / dx[q];
+    }
+#pragma unroll
+    for (int q = 0; q < FIN_ROWS; q++) {
+        const int32_t j = j0 + q * 256;
+        if (!in[q]) continue;
+        double v[3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            v[s] = ya[q][s];
+            if (interp[q]) {   // numpy.interp: slope = (y1 - y0) / (x1 - x0); slope * (x - x0) + y0, a product and a sum (no FMA)
+                const double dy = yb[q][s] - ya[q][s];
+                v[s] = __dadd_rn(__dmul_rn(div_by_int(dy, dx[q], rdx[q]), (double)(j - a[q])), ya[q][s]);
+            }
+            if (v[s] > 1.0) v[s] = 1.0 / v[s];   // density.py:330-332
+            ks[s][j] = v[s];
+        }
+        state[P.row_off + j] = (int8_t)argmax3(v[0], v[1], v[2]);
+    }
 }
 
 // D10 -----------------------------------------------------------------------------------------------
@@ -750,7 +882,7 @@ struct pavgpu_density_batch {
     uint64_t *d_keys; uint32_t *d_counts;
     int8_t *d_st_pos; uint32_t *d_tile_cnt;
     uint64_t *d_kmer; int32_t *d_index; int8_t *d_state_mer, *d_state;
-    double *d_k[3], *d_tree[3];
+    double *d_k[3], *d_samp[3], *d_tree[3];   // d_samp: the sampled values of a window, densely at [row_off, row_off + n_samp)
     int32_t *d_run_start, *d_run_len, *d_n_runs; int8_t *d_run_state;
     int64_t tree_total;
     uint8_t *d_gap_full; int32_t *d_fill_list, *d_n_fill, *d_n_eval; int64_t *d_grp_off;
@@ -833,7 +965,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
 
     // ---- plan, part 1 (host)
     int64_t tab = 0, pos = 0, tiles = 0, bases = 0, tree_cap = 0;
-    int32_t max_ref_blocks = 1, max_tig_tiles = 1, max_ref_kmers = 0;
+    // PAVGPU_DENSITY_ONCHIP=0 sends every window to the global tables (A/B runs and the tests of that path)
+    const char *oc_env = getenv("PAVGPU_DENSITY_ONCHIP");
+    const bool onchip_on = !(oc_env && oc_env[0] == '0');
+    int32_t n_onchip = 0;
+    int32_t max_ref_blocks = 1, max_tig_tiles = 1;
     for (int32_t w = 0; w < n_win; w++) {
         const pavgpu_density_window &W = b->win[w];
         if (W.ref_seq_id < 0 || W.ref_seq_id >= ref_store->n_seq || W.tig_seq_id < 0 || W.tig_seq_id >= tig_store->n_seq ||
@@ -851,10 +987,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         int32_t n_ref = std::max(P.ref_len - k + 1, 0), n_tig = std::max(P.tig_len - k + 1, 0);
         P.tab_log2 = std::max(log2_ceil(2 * (int64_t)std::max(n_ref, 1)), 4);
         P.tab_off = tab; tab += (int64_t)1 << P.tab_log2;
+        P.mode = (onchip_on && n_ref >= 1 && n_ref <= KS_MAX_REF && (n_tig + TILE - 1) / TILE <= KS_MAX_TILES) ? 1 : 0;
+        n_onchip += P.mode;
         P.pos_off = pos; pos += n_tig;
         P.tile_off = tiles; tiles += (n_tig + TILE - 1) / TILE;
         max_ref_blocks = std::max(max_ref_blocks, (n_ref + 255) / 256);
-        max_ref_kmers = std::max(max_ref_kmers, n_ref);
         max_tig_tiles = std::max(max_tig_tiles, (n_tig + TILE - 1) / TILE);
         bases += P.tig_len;
         P.tree_off = tree_cap;                                   // upper bound: N <= n_tig
@@ -872,8 +1009,8 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         size_t o_plan = carve(sizeof(WinPlan) * n_win), o_wc = carve(sizeof(WinCounts) * n_win), o_kp = carve(sizeof(KdeParams) * n_win);
         size_t o_keys = carve(8 * tcap), o_counts = carve(4 * tcap), o_st = carve(rcap), o_tile = carve(12 * (size_t)std::max<int64_t>(tiles, 1));
         size_t o_kmer = carve(8 * rcap), o_index = carve(4 * rcap), o_sm = carve(rcap), o_state = carve(rcap);
-        size_t o_k[3], o_tree[3];
-        for (int s = 0; s < 3; s++) { o_k[s] = carve(8 * rcap); o_tree[s] = carve(8 * (size_t)std::max<int64_t>(tree_cap, 1)); }
+        size_t o_k[3], o_samp[3], o_tree[3];
+        for (int s = 0; s < 3; s++) { o_k[s] = carve(8 * rcap); o_samp[s] = carve(8 * rcap); o_tree[s] = carve(8 * (size_t)std::max<int64_t>(tree_cap, 1)); }
         size_t o_rs = carve(4 * rcap), o_rl = carve(4 * rcap), o_rst = carve(rcap), o_nr = carve(4 * (size_t)n_win);
         size_t o_gap = carve(rcap), o_fill = carve(4 * rcap), o_nf = carve(4 * (size_t)n_win), o_ne = carve(4 * (size_t)n_win);
         size_t o_grp = carve(8 * ((size_t)n_win + 1));
@@ -885,7 +1022,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
         b->d_tile_cnt = (uint32_t *)(base + o_tile);
         b->d_kmer = (uint64_t *)(base + o_kmer); b->d_index = (int32_t *)(base + o_index);
         b->d_state_mer = (int8_t *)(base + o_sm); b->d_state = (int8_t *)(base + o_state);
-        for (int s = 0; s < 3; s++) { b->d_k[s] = (double *)(base + o_k[s]); b->d_tree[s] = (double *)(base + o_tree[s]); }
+        for (int s = 0; s < 3; s++) { b->d_k[s] = (double *)(base + o_k[s]); b->d_samp[s] = (double *)(base + o_samp[s]); b->d_tree[s] = (double *)(base + o_tree[s]); }
         b->d_run_start = (int32_t *)(base + o_rs); b->d_run_len = (int32_t *)(base + o_rl); b->d_run_state = (int8_t *)(base + o_rst);
         b->d_n_runs = (int32_t *)(base + o_nr);
         b->d_gap_full = (uint8_t *)(base + o_gap); b->d_fill_list = (int32_t *)(base + o_fill);
@@ -898,53 +1035,65 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(b->d_wc, 0, sizeof(WinCounts) * n_win, st));
     const int32_t YMAX = 32768;
-    // k-mer tables: in the distributed shared memory of one cluster per window when every window is small enough, else in HBM
-    // (opt-in: measured on B200, r02, 296 windows x 50 kbp: 1.42 ms for the cluster kernel against 0.51 + 0.30 ms for ref_insert + tig_state --
-    // remote shared-memory atomics and loads at one 1,024-thread CTA per SM and 16 resident clusters are latency-bound)
-    static const bool kc_on = [] { const char *e = getenv("PAVGPU_DENSITY_CLUSTER_TABLES"); return e && e[0] == '1'; }();
-    bool use_cluster = kc_on && max_ref_kmers <= KC_MAX_REF;
+    // k-mer part: windows small enough for kmer_window_kernel build and probe their table in shared memory (mode 1); the others, and
+    // the windows that kernel hands back (a k-mer count its 6 bits cannot decide), go through the tables in HBM (mode 0).
     std::vector<WinCounts> wc(n_win);
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if (use_cluster) {
-            static bool attr_done[64] = {};
-            const int dev = ctx->device;
-            if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-                CUDA_TRY(cudaFuncSetAttribute(kmer_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KC_SMEM));
-                if (dev >= 0 && dev < 64) attr_done[dev] = true;
-            }
-            const int32_t XMAX = 65535 * 8 / KC_CLUSTER;   // windows per launch
-            for (int32_t w0 = 0; w0 < n_win; w0 += XMAX) {
-                const int32_t nx = std::min(XMAX, n_win - w0);
-                kmer_cluster_kernel<<<(unsigned)nx * KC_CLUSTER, KC_THREADS, KC_SMEM, st>>>(b->d_plan, w0, planes_of(ref_store), planes_of(tig_store), k,
-                                                                                             b->d_st_pos, b->d_tile_cnt, b->d_wc);
-                launches++;
-            }
-            CUDA_TRY(cudaGetLastError());
-        } else {
+    auto run_global = [&](bool whole_slab) -> int {
+        if (whole_slab) {
             CUDA_TRY(cudaMemsetAsync(b->d_keys, 0xFF, sizeof(uint64_t) * std::max<int64_t>(tab, 1), st));
             CUDA_TRY(cudaMemsetAsync(b->d_counts, 0, sizeof(uint32_t) * std::max<int64_t>(tab, 1), st));
-            for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
-                int32_t ny = std::min(YMAX, n_win - w0);
-                ref_insert_kernel<<<dim3(max_ref_blocks, ny), 256, 0, st>>>(b->d_plan, w0, planes_of(ref_store), k, b->d_keys, b->d_counts, b->d_wc);
-                launches++;
+        } else {
+            for (int32_t w = 0; w < n_win; w++) {
+                const WinPlan &P = b->plan[w];
+                if (P.mode != 0) continue;
+                CUDA_TRY(cudaMemsetAsync(b->d_keys + P.tab_off, 0xFF, sizeof(uint64_t) << P.tab_log2, st));
+                CUDA_TRY(cudaMemsetAsync(b->d_counts + P.tab_off, 0, sizeof(uint32_t) << P.tab_log2, st));
             }
-            CUDA_TRY(cudaGetLastError());
-            for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
-                int32_t ny = std::min(YMAX, n_win - w0);
-                tig_state_kernel<<<dim3(max_tig_tiles, ny), TILE, 0, st>>>(b->d_plan, w0, planes_of(tig_store), k, b->d_keys, b->d_st_pos, b->d_tile_cnt, b->d_wc);
-                launches++;
-            }
-            CUDA_TRY(cudaGetLastError());
         }
+        for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+            int32_t ny = std::min(YMAX, n_win - w0);
+            ref_insert_kernel<<<dim3(max_ref_blocks, ny), 256, 0, st>>>(b->d_plan, w0, planes_of(ref_store), k, b->d_keys, b->d_counts, b->d_wc);
+            launches++;
+        }
+        for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
+            int32_t ny = std::min(YMAX, n_win - w0);
+            tig_state_kernel<<<dim3(max_tig_tiles, ny), TILE, 0, st>>>(b->d_plan, w0, planes_of(tig_store), k, b->d_keys, b->d_st_pos, b->d_tile_cnt, b->d_wc);
+            launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return PAVGPU_OK;
+    };
+    if (n_onchip > 0) {
+        static bool attr_done[64] = {};
+        const int dev = ctx->device;
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(kmer_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
+        const unsigned cnt_limit = (unsigned)std::max<int64_t>(std::min<int64_t>(b->prm.max_ref_kmer_count, KS_CNT_LIMIT), 0);
+        kmer_window_kernel<<<(unsigned)n_win, KS_THREADS, KS_SMEM, st>>>(b->d_plan, planes_of(ref_store), planes_of(tig_store), k, cnt_limit,
+                                                                         b->d_st_pos, b->d_tile_cnt, b->d_wc);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (n_onchip < n_win) { int rc = run_global(n_onchip == 0 || (n_win - n_onchip) > 64); if (rc != PAVGPU_OK) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(wc.data(), b->d_wc, sizeof(WinCounts) * n_win, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int32_t n_redo = 0;
+    for (int32_t w = 0; w < n_win; w++) n_redo += (b->plan[w].mode == 1 && wc[w].overflow) ? 1 : 0;
+    if (n_redo > 0) {
+        for (int32_t w = 0; w < n_win; w++) {
+            WinPlan &P = b->plan[w];
+            if (P.mode == 1 && wc[w].overflow) { P.mode = 0; memset(&wc[w], 0, sizeof(WinCounts)); }
+            else P.mode = 2;
+        }
+        CUDA_TRY(cudaMemcpyAsync(b->d_plan, b->plan.data(), sizeof(WinPlan) * n_win, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_wc, wc.data(), sizeof(WinCounts) * n_win, cudaMemcpyHostToDevice, st));
+        { int rc = run_global(n_redo > 64); if (rc != PAVGPU_OK) return rc; }
         CUDA_TRY(cudaMemcpyAsync(wc.data(), b->d_wc, sizeof(WinCounts) * n_win, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        bool overflow = false;
-        for (int32_t w = 0; w < n_win && use_cluster; w++) overflow |= wc[w].overflow != 0;
-        if (!overflow) break;
-        use_cluster = false;      // a partition of some window filled up: redo the k-mer part with the global tables
-        CUDA_TRY(cudaMemsetAsync(b->d_wc, 0, sizeof(WinCounts) * n_win, st));
     }
-    b->stats.kmer_tables_on_chip = use_cluster ? 1 : 0;
+    b->stats.kmer_tables_on_chip = n_onchip - n_redo;
     tr.mark("plan + k-mer kernels");
 
     // ---- plan, part 2 (host): status, keep mask, N, dense row offsets, sample counts
@@ -1003,11 +1152,11 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     if (grp_off[n_win] > 0) {
         kde_eval_kernel<<<(unsigned)grp_off[n_win], EVAL_THREADS, 0, st>>>(b->d_plan, n_win, b->d_grp_off, b->d_n_eval, 0, nullptr, b->d_kp,
                                                                            b->d_run_start, b->d_run_len, b->d_run_state, b->d_n_runs, b->d_tree[0],
-                                                                           b->d_tree[1], b->d_tree[2], b->d_k[0], b->d_k[1], b->d_k[2]);
+                                                                           b->d_tree[1], b->d_tree[2], b->d_samp[0], b->d_samp[1], b->d_samp[2]);
         launches++;
         CUDA_TRY(cudaGetLastError());
     }
-    gap_classify_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->prm.delta, b->d_state_mer, b->d_k[0], b->d_k[1], b->d_k[2], b->d_gap_full,
+    gap_classify_kernel<<<n_win, 256, 0, st>>>(b->d_plan, b->prm.delta, b->d_state_mer, b->d_samp[0], b->d_samp[1], b->d_samp[2], b->d_gap_full,
                                                b->d_fill_list, b->d_n_fill);
     launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1031,9 +1180,9 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_density_batch_run(p
     }
     for (int32_t w0 = 0; w0 < n_win; w0 += YMAX) {
         int32_t ny = std::min(YMAX, n_win - w0);
-        interp_kernel<<<dim3(row_blocks, ny), 256, 0, st>>>(b->d_plan, w0, b->d_gap_full, b->d_k[0], b->d_k[1], b->d_k[2]);
-        finalize_kernel<<<dim3(row_blocks, ny), 256, 0, st>>>(b->d_plan, w0, b->d_k[0], b->d_k[1], b->d_k[2], b->d_state);
-        launches += 2;
+        finish_rows_kernel<<<dim3((row_blocks + FIN_ROWS - 1) / FIN_ROWS, ny), 256, 0, st>>>(b->d_plan, w0, b->d_gap_full, b->d_samp[0], b->d_samp[1],
+                                                                                              b->d_samp[2], b->d_k[0], b->d_k[1], b->d_k[2], b->d_state);
+        launches++;
     }
     CUDA_TRY(cudaGetLastError());
     state_rle_kernel<<<n_win, 1024, 0, st>>>(b->d_plan, b->d_state, b->d_index, b->d_state_runs, b->d_n_state_runs);

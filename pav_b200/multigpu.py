@@ -47,8 +47,10 @@ def merge_rows(parts, shard_index):
         indels.append(indel)
     snv = np.concatenate(snvs) if snvs else np.zeros(0, cigarcall.device._capi.SNV_ROW)
     indel = np.concatenate(indels) if indels else np.zeros(0, cigarcall.device._capi.INDEL_ROW)
-    snv = snv[np.lexsort((snv['pos_ref'], snv['op_idx'], snv['rec']))]
-    indel = indel[np.lexsort((indel['op_idx'], indel['rec']))]
+    # inside a shard the rows of a record are contiguous and already in (op, base) order, and the shards' records are ascending:
+    # a stable sort on the record number alone restores the global emission order (a few sorted runs: cheap for the merge sort)
+    snv = snv[np.argsort(snv['rec'], kind='stable')]
+    indel = indel[np.argsort(indel['rec'], kind='stable')]
     return snv, indel
 
 
@@ -79,6 +81,7 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
     n_rec = df_align.shape[0]
     if n_rec == 0:
         return (cigarcall._empty(cigarcall.SNV_COLUMNS), cigarcall._empty(cigarcall.INSDEL_COLUMNS)) if rank == 0 else None
+    from concurrent.futures import ThreadPoolExecutor
     t0 = time.perf_counter()
     full = cigarcall.AlignTable(df_align)
     span = None
@@ -91,58 +94,78 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
     stats = {'rank': rank, 'world': world, 'records': int(len(mine)), 'bcast_ms': 0.0, 'checksum': None, 'planes_verified': None}
     err = None
     ref_store = ctx = None
-    if walk_fn is None:
-        # ---- the reference planes: every rank takes part in the collectives or all of them raise together
-        setup_err, uid = None, [None]
+    ref_arr = tig_all = None
+    pool = ThreadPoolExecutor(max_workers=2 * cigarcall._READERS + 1)
+    try:
+        t_mine = cigarcall.AlignTable(mine) if len(mine) else None
+        if walk_fn is None:
+            # ---- the reference planes: every rank takes part in the collectives or all of them raise together
+            setup_err, uid = None, [None]
+            tig_futs = []
+            try:
+                ctx = device.get_context()
+                names = list(full.ref_names)  # every rank holds the whole reference of this table, same order
+                # sequences are read by a few threads each (cigarcall.read_sequences): rank 0 the reference and, for the frames it
+                # builds at the end, every contig of the table; the other ranks the contigs of their records
+                pinned = cigarcall._CALLS >= 1
+                cigarcall._CALLS += 1
+                if rank == 0:
+                    ref_arr, ref_futs = cigarcall.read_sequences(ref_fa, names, pool, ctx, pinned)
+                    tig_all, tig_futs = cigarcall.read_sequences(tig_fa, list(full.tig_names), pool, ctx, pinned)
+                    for f in ref_futs:
+                        f.result()
+                    ref_store = device.SeqStore(ctx, names, ref_arr, keep_host=False)
+                    uid = [device.nccl_unique_id()]
+                else:
+                    if t_mine is not None:
+                        tig_all, tig_futs = cigarcall.read_sequences(tig_fa, list(t_mine.tig_names), pool, ctx, pinned)
+                    ref_store = device.SeqStore.from_packed(ctx, names, [ref_fa.length(n) for n in names], None, None)
+            except Exception as ex:  # noqa: BLE001
+                setup_err = f'rank {rank}: {type(ex).__name__}: {ex}'
+            flags = [None] * world
+            dist.all_gather_object(flags, setup_err, group=group)
+            if any(flags):
+                if ref_store is not None:
+                    ref_store.close()
+                raise RuntimeError('make_insdel_snv_calls_dist: reference set-up failed: ' + '; '.join(f for f in flags if f))
+            dist.broadcast_object_list(uid, src=0, group=group)
+            bc_err = None
+            try:
+                stats['bcast_ms'] = ref_store.broadcast(uid[0], rank, world)
+                stats['checksum'] = ref_store.checksum() if verify_planes else None
+            except Exception as ex:  # noqa: BLE001
+                bc_err = f'rank {rank}: {type(ex).__name__}: {ex}'
+            sums = [None] * world
+            dist.all_gather_object(sums, (bc_err, stats['checksum']), group=group)
+            bad = [e for e, _ in sums if e]
+            if not bad and verify_planes:
+                bad = [f'rank {r}: planes {c} differ from rank 0 {sums[0][1]}' for r, (_, c) in enumerate(sums) if c != sums[0][1]]
+                stats['planes_verified'] = not bad
+            if bad:
+                ref_store.close()
+                raise RuntimeError('make_insdel_snv_calls_dist: reference broadcast failed: ' + '; '.join(bad))
+        t1 = time.perf_counter()
+        # ---- this rank's shard
         try:
-            ctx = device.get_context()
-            names = list(full.ref_names)  # every rank holds the whole reference of this table, same order
-            if rank == 0:
-                ref_store = device.SeqStore(ctx, names, [ref_fa.fetch_array(n) for n in names], keep_host=False)
-                uid = [device.nccl_unique_id()]
-            else:
-                ref_store = device.SeqStore.from_packed(ctx, names, [ref_fa.length(n) for n in names], None, None)
-        except Exception as ex:  # noqa: BLE001
-            setup_err = f'rank {rank}: {type(ex).__name__}: {ex}'
-        flags = [None] * world
-        dist.all_gather_object(flags, setup_err, group=group)
-        if any(flags):
+            if t_mine is not None:
+                t = t_mine
+                if walk_fn is not None:
+                    part = walk_fn(t, [ref_fa.fetch_array(n) for n in t.ref_names], [tig_fa.fetch_array(n) for n in t.tig_names])
+                else:
+                    for f in tig_futs:
+                        f.result()
+                    # ids must index the broadcast store, not the shard-local name table
+                    t.ref_id = np.array([full.ref_names[str(c)] for c in t.chrom.tolist()], dtype=np.int32)
+                    tig_arr_mine = [tig_all[full.tig_names[n]] for n in t.tig_names] if rank == 0 else tig_all
+                    part = cigarcall.walk_rows(t, None, tig_arr_mine, ctx=ctx, ref_store=ref_store)
+                    stats['walk'] = dict(cigarcall.last_stats) if cigarcall.last_stats else None
+        except (RuntimeError, IndexError) as ex:  # CIGAR errors: first one in table order wins on rank 0
+            err = (type(ex).__name__, str(ex))
+        finally:
             if ref_store is not None:
                 ref_store.close()
-            raise RuntimeError('make_insdel_snv_calls_dist: reference set-up failed: ' + '; '.join(f for f in flags if f))
-        dist.broadcast_object_list(uid, src=0, group=group)
-        bc_err = None
-        try:
-            stats['bcast_ms'] = ref_store.broadcast(uid[0], rank, world)
-            stats['checksum'] = ref_store.checksum() if verify_planes else None
-        except Exception as ex:  # noqa: BLE001
-            bc_err = f'rank {rank}: {type(ex).__name__}: {ex}'
-        sums = [None] * world
-        dist.all_gather_object(sums, (bc_err, stats['checksum']), group=group)
-        bad = [e for e, _ in sums if e]
-        if not bad and verify_planes:
-            bad = [f'rank {r}: planes {c} differ from rank 0 {sums[0][1]}' for r, (_, c) in enumerate(sums) if c != sums[0][1]]
-            stats['planes_verified'] = not bad
-        if bad:
-            ref_store.close()
-            raise RuntimeError('make_insdel_snv_calls_dist: reference broadcast failed: ' + '; '.join(bad))
-    t1 = time.perf_counter()
-    # ---- this rank's shard
-    try:
-        if len(mine):
-            t = cigarcall.AlignTable(mine)
-            if walk_fn is not None:
-                part = walk_fn(t, [ref_fa.fetch_array(n) for n in t.ref_names], [tig_fa.fetch_array(n) for n in t.tig_names])
-            else:
-                # ids must index the broadcast store, not the shard-local name table
-                t.ref_id = np.array([full.ref_names[str(c)] for c in t.chrom.tolist()], dtype=np.int32)
-                part = cigarcall.walk_rows(t, None, [tig_fa.fetch_array(n) for n in t.tig_names], ctx=ctx, ref_store=ref_store)
-                stats['walk'] = dict(cigarcall.last_stats) if cigarcall.last_stats else None
-    except (RuntimeError, IndexError) as ex:  # CIGAR errors: first one in table order wins on rank 0
-        err = (type(ex).__name__, str(ex))
     finally:
-        if ref_store is not None:
-            ref_store.close()
+        pool.shutdown(wait=True)
     t2 = time.perf_counter()
     stats['rows'] = int(len(part[0]) + len(part[1]))
     gathered = [None] * world if rank == 0 else None
@@ -159,8 +182,12 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
         _, (kind, msg) = min(errs, key=lambda x: x[0])
         raise (IndexError if kind == 'IndexError' else RuntimeError)(msg)
     snv, indel = merge_rows([p for p, _ in gathered], shards)
-    ref_arr = [ref_fa.fetch_array(n) for n in full.ref_names]
-    tig_arr = [tig_fa.fetch_array(n) for n in full.tig_names]
+    if ref_arr is None:        # (walk_fn runs: nothing was read up front)
+        ref_arr = [ref_fa.fetch_array(n) for n in full.ref_names]
+        tig_all = [tig_fa.fetch_array(n) for n in full.tig_names]
+    tig_arr = tig_all
+    stats['seconds']['merge_rank0'] = time.perf_counter() - t3
+    t3 = time.perf_counter()
     out = cigarcall.build_frames(snv, indel, full.chrom, full.qry, full.rev, full.align_index, ref_arr, tig_arr, full.ref_id,
                                  full.qry_id, hap, version_id)
     stats['seconds']['frames_rank0'] = time.perf_counter() - t3

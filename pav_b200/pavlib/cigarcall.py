@@ -200,6 +200,41 @@ def make_insdel_snv_calls(df_align, ref_fa_name, tig_fa_name, hap, version_id=Tr
     return frames
 
 
+def read_sequences(fa, names, pool, ctx=None, pinned=False):
+    """-> (list of uint8 arrays in the order of ``names``, futures): the records are read by up to ``_READERS`` jobs of about equal
+    size submitted to ``pool`` (file reads, numpy copies and the C calls release the GIL); with ``pinned`` the bases land in one
+    pinned staging buffer of the context's pool (H2D at PCIe speed) when they fit ``PAVGPU_PINNED_STAGING_MAX_MB``."""
+    names = list(names)
+    for nm in names:
+        if str(nm) not in fa.index:
+            raise KeyError(f'sequence {str(nm)!r} not found in {fa.path}')
+    lens = [fa.length(nm) for nm in names]
+    offs = np.concatenate(([0], np.cumsum([(ln + 63) // 64 * 64 for ln in lens]))).astype(np.int64)
+    buf = None
+    if pinned and ctx is not None and int(offs[-1]) <= _PINNED_STAGING_MAX:
+        try:
+            buf = device.pinned_empty(ctx, int(offs[-1]))
+        except RuntimeError:   # no pinned memory to be had: ordinary memory works, only slower
+            buf = None
+    if buf is None:
+        buf = np.empty(int(offs[-1]), dtype=np.uint8)
+    out = [buf[offs[i]:offs[i] + lens[i]] for i in range(len(names))]
+    target, parts, cur, acc = max(int(offs[-1]) // _READERS, 1), [], [], 0
+    for i in range(len(names)):
+        cur.append(i)
+        acc += lens[i]
+        if acc >= target and len(parts) < _READERS - 1:
+            parts.append(cur)
+            cur, acc = [], 0
+    if cur:
+        parts.append(cur)
+
+    def job(idx):
+        for i in idx:
+            fa.fetch_into(names[i], out[i])
+    return out, [pool.submit(job, idx) for idx in parts]
+
+
 def call_rows(df_align, ref_fa_name, tig_fa_name):
     """First half of ``make_insdel_snv_calls`` (``df_align`` not empty): read the sequences, run the walk on the GPU.
 
@@ -221,36 +256,7 @@ def call_rows(df_align, ref_fa_name, tig_fa_name):
     _CALLS += 1
 
     def read_all(fa, names):
-        """-> list of uint8 arrays in the order of ``names``, read in up to ``_READERS`` slices of about equal size."""
-        names = list(names)
-        for nm in names:
-            if str(nm) not in fa.index:
-                raise KeyError(f'sequence {str(nm)!r} not found in {fa.path}')
-        lens = [fa.length(nm) for nm in names]
-        offs = np.concatenate(([0], np.cumsum([(ln + 63) // 64 * 64 for ln in lens]))).astype(np.int64)
-        buf = None
-        if pinned and int(offs[-1]) <= _PINNED_STAGING_MAX:
-            try:
-                buf = device.pinned_empty(ctx, int(offs[-1]))
-            except RuntimeError:   # no pinned memory to be had: ordinary memory works, only slower
-                buf = None
-        if buf is None:
-            buf = np.empty(int(offs[-1]), dtype=np.uint8)
-        out = [buf[offs[i]:offs[i] + lens[i]] for i in range(len(names))]
-        target, parts, cur, acc = max(int(offs[-1]) // _READERS, 1), [], [], 0
-        for i in range(len(names)):
-            cur.append(i)
-            acc += lens[i]
-            if acc >= target and len(parts) < _READERS - 1:
-                parts.append(cur)
-                cur, acc = [], 0
-        if cur:
-            parts.append(cur)
-
-        def job(idx):
-            for i in idx:
-                fa.fetch_into(names[i], out[i])
-        return out, [pool.submit(job, idx) for idx in parts]
+        return read_sequences(fa, names, pool, ctx, pinned)
 
     with ThreadPoolExecutor(max_workers=2 * _READERS + 1) as pool:
         futs = []

