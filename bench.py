@@ -14,9 +14,12 @@ Workloads (BASELINE.json configs, SURVEY 8(d) generators, all synthetic and seed
                row counts + record scan + CIGAR walk + homology for this rank's records of both haplotypes (one batch), replayed as one
                CUDA graph, timed with CUDA events on the library stream, L2 flushed (256 MB memset) between steps; rows stay in HBM.
                value = rows of all ranks / max over ranks of the mean step time.
-        e2e    the call PAV makes, FASTA in -> DataFrames out: pavlib.cigarcall.make_insdel_snv_calls per haplotype at N = 1,
-               pav_b200.multigpu.make_insdel_snv_calls_dist at N > 1 (LPT shards -> NCCL broadcast -> per-rank walk -> host
-               gather -> frames on rank 0); wall clock, max over ranks.
+        e2e    the call PAV makes, FASTA in -> DataFrames out, wall clock, max over ranks: pavlib.cigarcall.make_insdel_snv_calls per
+               haplotype at N = 1; at N > 1 every rank makes that call on the chromosomes it owns
+               (pav_b200.multigpu.make_insdel_snv_calls_shard: LPT over chromosomes, 1 / N of the reference read, uploaded and packed per
+               rank, no communication, tables concatenate).
+        e2e_dist (N > 1)  pav_b200.multigpu.make_insdel_snv_calls_dist: records LPT-sharded over ranks -> NCCL broadcast of the packed
+               reference -> per-rank walk -> host gather -> ONE merged table formatted on rank 0.
   C5  (`secondary`, every N; top level with --metric density)  10,000 flagged 50 kbp windows, k = 31 (BASELINE configs[4]),
       split evenly over the ranks: inv k-mer Gbases/s device-resident and through pavlib.density.density_windows(lazy=True)
       (ASCII windows in host memory -> run lengths of STATE in host memory, the columns stay in HBM until a window becomes a call).
@@ -55,7 +58,7 @@ def workload_c3(args, world):
     sc = '' if args.scale == 1.0 else f' [scale {args.scale}]'
     return (f'C3{sc}: 2 phased haplotypes (h1/h2) of 10 Mbp contigs vs 3.1 Gbp hg38-shaped reference (24 chromosomes, 50% soft-masked, 5% N), '
             f'{args.regime} edit regime, records sharded by alignment record (LPT) over {world} GPU(s)'
-            + (', one NCCL broadcast of the packed reference, host gather of the rows' if world > 1 else ''))
+            + (', one NCCL broadcast of the packed reference' if world > 1 else ''))
 
 
 def workload_c5(args, world):
@@ -602,7 +605,12 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
         rh.close()
     checks = [x for p in per_rank for x in p['oracle_spot_check']]
 
-    # ---- end to end: FASTA in -> DataFrames out (on rank 0 when sharded)
+    # ---- end to end: FASTA in -> DataFrames out.
+    # N = 1: the public call per haplotype. N > 1: every rank makes the public call on the chromosomes it owns
+    # (multigpu.make_insdel_snv_calls_shard: LPT over chromosomes, no communication -- each rank reads, uploads and packs 1 / N of the
+    # reference and formats its own tables; the reference's own model of one job per batch of records, rules/align.snakefile:163, with
+    # the chromosome as batch key so that the tables concatenate). The other multi-GPU call, make_insdel_snv_calls_dist (records over
+    # ranks, NCCL broadcast of the packed reference, ONE merged table formatted on rank 0), is timed beside it as `e2e_dist`.
     e2e_s, e2e_rows, phases = [], 0, None
     E2E_WARMUP = 1
     os.environ.setdefault('PAVGPU_TUNE_ALLOC', '1')    # opt-in allocator tuning of the frame builder, declared in `config`
@@ -614,43 +622,42 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
         rows_step, ph = 0, {}
         for h in ('h1', 'h2'):
             if world > 1:
-                with stdout_to_stderr():
-                    out = multigpu.make_insdel_snv_calls_dist(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
-                ph[h] = multigpu.last_dist_stats['seconds']
+                out = multigpu.make_insdel_snv_calls_shard(dfs[h], ref_fa, tig_fa[h], h, rank, world, version_id=False)
             else:
                 out = cigarcall.make_insdel_snv_calls(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
-                ph[h] = cigarcall.last_phase_seconds
-            if out is not None:
-                rows_step += len(out[0]) + len(out[1])
+            ph[h] = cigarcall.last_phase_seconds
+            rows_step += len(out[0]) + len(out[1])
             out = None
         dt = ctl.max(time.perf_counter() - t0)
+        rows_all = int(ctl.sum(rows_step))
         if i >= E2E_WARMUP:
             e2e_s.append(dt)
-            e2e_rows, phases = rows_step, ph
+            e2e_rows, phases = rows_all, ph
         log(f'[rank {rank}] e2e step {i}: {dt:.2f}s ({rows_step} rows formatted on this rank) {ph}')
-    e2e_rows = int(ctl.max(e2e_rows))
     if e2e_s:
         assert e2e_rows == total_rows, (e2e_rows, total_rows)
-    # ---- the reference's own way of spreading this work: one job per batch of records (CALL_BATCH = INDEX % 10, rules/align.snakefile:163),
-    # every job formatting ITS rows into its own pair of tables (merged later by file concatenation, rule call_cigar_merge). Here: one
-    # batch per rank = its LPT shard, the public single-GPU call on it, no gather.
-    batch_s = []
+    dist_s, dist_ph = [], None
     if world > 1 and args.e2e_steps > 0:
         for i in range(E2E_WARMUP + args.e2e_steps):
             fasta_mod._CACHE.clear()
             out = None
             ctl.barrier()
             t0 = time.perf_counter()
-            rows_b = 0
+            rows_d, ph = 0, {}
             for h in ('h1', 'h2'):
-                out = cigarcall.make_insdel_snv_calls(dfs[h].iloc[plan[h][rank]], ref_fa, tig_fa[h], h, version_id=False)
-                rows_b += len(out[0]) + len(out[1])
+                with stdout_to_stderr():
+                    out = multigpu.make_insdel_snv_calls_dist(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
+                ph[h] = dict(multigpu.last_dist_stats['seconds'], nccl_comm_reused=multigpu.last_dist_stats.get('nccl_comm_reused'))
+                if out is not None:
+                    rows_d += len(out[0]) + len(out[1])
                 out = None
             dt = ctl.max(time.perf_counter() - t0)
-            assert rows_b == my_rows, (rows_b, my_rows)
+            if rank == 0:
+                assert rows_d == total_rows, (rows_d, total_rows)
             if i >= E2E_WARMUP:
-                batch_s.append(dt)
-            log(f'[rank {rank}] e2e (one batch per rank) step {i}: {dt:.2f}s ({rows_b} rows on this rank)')
+                dist_s.append(dt)
+                dist_ph = ph
+            log(f'[rank {rank}] e2e_dist step {i}: {dt:.2f}s ({rows_d} rows formatted on this rank) {ph}')
     contig_bytes = int(sum(fasta_mod.open_fasta(tig_fa[h]).length(n) for h in ('h1', 'h2') for n in set(dfs[h]['QRY_ID'])))
     # per e2e step: each of the two haplotype calls uploads the reference (ASCII, packing rank) and every rank its contigs and ops
     h2d = int(2 * info['reference_bp'] + contig_bytes + 4 * ctl.sum(n_ops))
@@ -685,14 +692,15 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
         'planes_verified_on_every_rank': all(planes_ok), 'oracle_spot_check': bool(checks) and all(x is not False for x in checks) and any(x for x in checks),
         'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': args.e2e_steps, 'warmup': E2E_WARMUP,
                 'ms_per_step': float(np.mean(e2e_s)) * 1e3 if e2e_s else None,
-                'api': ('pav_b200.multigpu.make_insdel_snv_calls_dist per haplotype (LPT shards, NCCL broadcast of the packed reference, plane checksum on '
-                        'every rank, per-rank walk, host gather, frames on rank 0)' if world > 1 else
+                'api': ('pav_b200.multigpu.make_insdel_snv_calls_shard per haplotype on every rank: the public call on the chromosomes the rank owns '
+                        '(LPT over chromosomes; FASTA in, DataFrames out, no communication; tables concatenate with merge_shard_frames)' if world > 1 else
                         'pav_b200.pavlib.cigarcall.make_insdel_snv_calls per haplotype (FASTA in, DataFrames out)'),
                 'phase_seconds_last_step_rank0': phases},
-        'e2e_batches': ({'value': total_rows / float(np.mean(batch_s)), 'unit': UNIT, 'ms_per_step': float(np.mean(batch_s)) * 1e3,
-                         'api': 'pavlib.cigarcall.make_insdel_snv_calls on one batch of records per rank (its LPT shard), every rank reading the FASTA files, '
-                                'uploading the reference itself and formatting its own tables -- the reference\'s CALL_BATCH model (rules/align.snakefile:163), no gather'}
-                        if batch_s else None),
+        'e2e_dist': ({'value': total_rows / float(np.mean(dist_s)), 'unit': UNIT, 'ms_per_step': float(np.mean(dist_s)) * 1e3,
+                      'api': 'pav_b200.multigpu.make_insdel_snv_calls_dist per haplotype (records LPT-sharded over ranks, NCCL broadcast of the packed '
+                             'reference, plane checksum on every rank, per-rank walk, host gather, ONE merged table formatted on rank 0)',
+                      'phase_seconds_last_step_rank0': dist_ph}
+                     if dist_s else None),
         'info': info,
     }
 
@@ -967,7 +975,7 @@ def run_ours(args, rank, world, local):
                        'l2': 'flushed (256 MB memset) between iterations', 'parallelism': f'alignment records sharded over {world} GPU(s), LPT',
                        'alloc_tuning': 'PAVGPU_TUNE_ALLOC=1 for the end-to-end leg (opt-in glibc / pymalloc settings of the frame builder)',
                        'seconds_generate': info['seconds_generate'], 'seconds_write': info['seconds_write']},
-            'e2e': a['e2e'], 'e2e_batches': a['e2e_batches'], 'gpu_launches': a['gpu_launches'], 'wall_ms_per_step_incl_flush': a['wall_ms_per_step_incl_flush'],
+            'e2e': a['e2e'], 'e2e_dist': a['e2e_dist'], 'gpu_launches': a['gpu_launches'], 'wall_ms_per_step_incl_flush': a['wall_ms_per_step_incl_flush'],
             'roofline': a['roofline'], 'cpu_baseline': cpu_a, 'clocks': a['clocks'], 'per_rank': a['per_rank'],
             'ref_broadcast_ms': a['ref_broadcast_ms'], 'ref_broadcast_bytes': a['ref_broadcast_bytes'], 'ref_pack_seconds_rank0': a['ref_pack_seconds_rank0'],
             'planes_verified_on_every_rank': a['planes_verified_on_every_rank'], 'oracle_spot_check': a['oracle_spot_check'],

@@ -251,8 +251,13 @@ int pavgpu_density_batch_fetch_window(pavgpu_density_batch *batch, int32_t win, 
  * one of the same shape. The caller moves the 128-byte id from rank 0 to all ranks (any side
  * channel); the library dlopen()s libnccl.so.2 on first use. */
 int pavgpu_nccl_unique_id(uint8_t id_out[128]);
+/* The communicator made from `id` is kept for the life of the process, one per (device, rank, n_ranks): with id == NULL the
+ * broadcast reuses it (ncclCommInitRank costs seconds, the broadcast milliseconds). Every rank must make the same choice;
+ * pavgpu_nccl_comm_cached() tells whether this rank has one, pavgpu_nccl_comm_release_all() destroys them. */
 int pavgpu_seqstore_broadcast(pavgpu_ctx *ctx, pavgpu_seqstore *store, const uint8_t id[128],
                               int32_t rank, int32_t n_ranks, float *ms_out);
+int pavgpu_nccl_comm_cached(pavgpu_ctx *ctx, int32_t rank, int32_t n_ranks);
+void pavgpu_nccl_comm_release_all(void);
 
 #ifdef __cplusplus
 }

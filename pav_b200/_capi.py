@@ -69,7 +69,7 @@ EXPORTS = [
     'pavgpu_cigar_batch_free', 'pavgpu_cigar_batch_run', 'pavgpu_cigar_batch_fetch', 'pavgpu_cigar_call',
     'pavgpu_homology', 'pavgpu_density_default_params', 'pavgpu_density_batch_create', 'pavgpu_density_batch_free',
     'pavgpu_density_batch_run', 'pavgpu_density_batch_fetch', 'pavgpu_density_batch_fetch_runs', 'pavgpu_density_batch_fetch_window',
-    'pavgpu_nccl_unique_id', 'pavgpu_seqstore_broadcast',
+    'pavgpu_nccl_unique_id', 'pavgpu_seqstore_broadcast', 'pavgpu_nccl_comm_cached', 'pavgpu_nccl_comm_release_all',
 ]
 
 
@@ -132,6 +132,9 @@ def lib():
     if hasattr(L, 'pavgpu_nccl_unique_id'):
         L.pavgpu_nccl_unique_id.argtypes = [c_vp]
         L.pavgpu_seqstore_broadcast.argtypes = [c_vp, c_vp, c_vp, c_i32, c_i32, P(c_f32)]
+        L.pavgpu_nccl_comm_cached.argtypes = [c_vp, c_i32, c_i32]
+        L.pavgpu_nccl_comm_release_all.argtypes = []
+        L.pavgpu_nccl_comm_release_all.restype = None
     _lib = L
     return L
 

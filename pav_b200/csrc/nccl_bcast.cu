@@ -8,6 +8,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -66,7 +69,27 @@ int load_nccl()
         }                                                                                    \
     } while (0)
 
+// Communicators are kept for the life of the process, one per (device, rank, n_ranks): ncclCommInitRank costs seconds, the
+// broadcast it serves milliseconds (r02, 2 x B200: 2.3-5 s of a 4.6 s distributed call were communicator set-up).
+std::mutex g_comm_mu;
+std::map<std::tuple<int, int, int>, NcclComm> g_comms;
+
 }  // namespace
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_nccl_comm_cached(pavgpu_ctx *ctx, int32_t rank, int32_t n_ranks)
+{
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    return g_comms.count(std::make_tuple(ctx->device, (int)rank, (int)n_ranks)) ? 1 : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) void pavgpu_nccl_comm_release_all(void)
+{
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    for (auto &kv : g_comms)
+        if (kv.second && g_nccl.CommDestroy) g_nccl.CommDestroy(kv.second);
+    g_comms.clear();
+}
 
 extern "C" __attribute__((visibility("default"))) int pavgpu_nccl_unique_id(uint8_t id_out[128])
 {
@@ -82,20 +105,36 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_nccl_unique_id(uint
 extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_broadcast(pavgpu_ctx *ctx, pavgpu_seqstore *store, const uint8_t id_in[128],
                                                                                   int32_t rank, int32_t n_ranks, float *ms_out)
 {
-    if (!ctx || !store || !id_in || rank < 0 || rank >= n_ranks) { pav_set_error("seqstore_broadcast: bad argument"); return PAVGPU_ERR_ARG; }
+    if (!ctx || !store || rank < 0 || rank >= n_ranks) { pav_set_error("seqstore_broadcast: bad argument"); return PAVGPU_ERR_ARG; }
     if (ms_out) *ms_out = 0.f;
     if (n_ranks == 1) return PAVGPU_OK;
     int rc = load_nccl();
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    NcclUniqueId id;
-    memcpy(id.internal, id_in, 128);
+    // id_in == NULL: the communicator of an earlier call of this process with the same (device, rank, n_ranks); else a new one from id_in
+    // (it replaces a cached one) -- every rank must make the same choice, pavgpu_nccl_comm_cached() tells which one is possible
+    const auto key = std::make_tuple(ctx->device, (int)rank, (int)n_ranks);
     NcclComm comm = nullptr;
-    NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+    {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        auto it = g_comms.find(key);
+        if (!id_in) {
+            if (it == g_comms.end()) { pav_set_error("seqstore_broadcast: no communicator cached for rank %d of %d and no unique id given", rank, n_ranks); return PAVGPU_ERR_ARG; }
+            comm = it->second;
+        } else {
+            if (it != g_comms.end()) { g_nccl.CommDestroy(it->second); g_comms.erase(it); }
+            NcclUniqueId id;
+            memcpy(id.internal, id_in, 128);
+            NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+            g_comms[key] = comm;
+        }
+    }
+    const bool fresh = id_in != nullptr;
     rc = [&]() -> int {
-        // warm the communicator (channel setup) on a few bytes so the timed transfer is the transfer
-        NCCL_TRY(g_nccl.Broadcast(store->d_nmask, store->d_nmask, 4, NCCL_UINT8, 0, comm, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (fresh) {   // warm the communicator (channel setup) on a few bytes so the timed transfer is the transfer
+            NCCL_TRY(g_nccl.Broadcast(store->d_nmask, store->d_nmask, 4, NCCL_UINT8, 0, comm, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
         CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
         NCCL_TRY(g_nccl.GroupStart());
         NCCL_TRY(g_nccl.Broadcast(store->d_pack2, store->d_pack2, store->pack2_bytes, NCCL_UINT8, 0, comm, ctx->stream));
@@ -107,6 +146,10 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_seqstore_broadcast(
         if (ms_out) *ms_out = ev_ms(ctx->ev[0], ctx->ev[1]);
         return PAVGPU_OK;
     }();
-    g_nccl.CommDestroy(comm);
+    if (rc != PAVGPU_OK) {   // a communicator that failed is not reused
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        g_nccl.CommDestroy(comm);
+        g_comms.erase(key);
+    }
     return rc;
 }

@@ -121,10 +121,11 @@ class SeqStore:
         return int(_capi.lib().pavgpu_seqstore_offset(self.handle, i))
 
     def broadcast(self, unique_id, rank, n_ranks):
-        """NCCL broadcast of both planes from rank 0. Returns device milliseconds."""
+        """NCCL broadcast of both planes from rank 0. Returns device milliseconds. ``unique_id`` None: reuse the
+        communicator an earlier call of this process made for (device, rank, n_ranks) -- see ``nccl_comm_cached``."""
         ms = ctypes.c_float()
-        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
-        _capi.check(_capi.lib().pavgpu_seqstore_broadcast(self.ctx.handle, self.handle, _capi.ptr(buf), rank, n_ranks,
+        buf = None if unique_id is None else np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        _capi.check(_capi.lib().pavgpu_seqstore_broadcast(self.ctx.handle, self.handle, None if buf is None else _capi.ptr(buf), rank, n_ranks,
                                                           ctypes.byref(ms)), 'pavgpu_seqstore_broadcast')
         return ms.value
 
@@ -145,6 +146,11 @@ def pinned_empty(ctx, nbytes):
     p = c_vp()
     _capi.check(_capi.lib().pavgpu_host_alloc(ctx.handle, int(max(nbytes, 1)), ctypes.byref(p)), 'pavgpu_host_alloc')
     return _capi.take_host_array(p.value, int(max(nbytes, 1)), np.uint8)[:nbytes]
+
+
+def nccl_comm_cached(ctx, rank, n_ranks):
+    """True when this process already holds an NCCL communicator for (ctx's device, rank, n_ranks)."""
+    return bool(_capi.lib().pavgpu_nccl_comm_cached(ctx.handle, rank, n_ranks))
 
 
 def nccl_unique_id():

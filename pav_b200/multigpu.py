@@ -54,6 +54,52 @@ def merge_rows(parts, shard_index):
     return snv, indel
 
 
+def chrom_shards(df_align, n_shards):
+    """Partition the records by REFERENCE SEQUENCE: longest-processing-time-first over the chromosomes (cost = the summed
+    ``record_costs`` of a chromosome's records). Returns ``n_shards`` sorted index arrays into ``df_align``.
+
+    A chromosome lives in exactly one shard, so a shard is a self-contained ``make_insdel_snv_calls`` input: it reads, uploads and
+    packs only its own chromosomes (1 / n of the reference per rank, no broadcast, no gather), variant IDs and their ``version_id``
+    suffixes never cross shards, and the per-shard tables concatenate into the whole table (``merge_shard_frames``). This is the
+    split to use when every rank formats its own rows -- the reference's model of one job per batch of records
+    (CALL_BATCH, rules/align.snakefile:163; tables merged by rule call_cigar_merge) with the batch key changed from INDEX % 10 to
+    the chromosome. ``make_insdel_snv_calls_dist`` (records over ranks, one merged table on rank 0) is the other one."""
+    chrom = df_align['#CHROM'].to_numpy(dtype=object)
+    span = (df_align['END'].to_numpy(dtype=np.int64) - df_align['POS'].to_numpy(dtype=np.int64)) if 'END' in df_align.columns else None
+    cost = record_costs(df_align['CIGAR'].tolist(), span)
+    names, inv = np.unique(chrom.astype(str), return_inverse=True)
+    per_chrom = np.bincount(inv, weights=cost, minlength=len(names))
+    bins = lpt_shards(per_chrom, n_shards)
+    owner = np.empty(len(names), dtype=np.int64)
+    for r, b in enumerate(bins):
+        owner[b] = r
+    rec_owner = owner[inv]
+    return [np.flatnonzero(rec_owner == r) for r in range(n_shards)]
+
+
+def make_insdel_snv_calls_shard(df_align, ref_fa_name, tig_fa_name, hap, rank, world, version_id=True):
+    """This rank's part of ``make_insdel_snv_calls`` under ``chrom_shards``: the two tables of the chromosomes it owns (columns and
+    row order as in the whole table restricted to those chromosomes; row labels count the shard's own rows). No communication."""
+    idx = chrom_shards(df_align, world)[rank]
+    return cigarcall.make_insdel_snv_calls(df_align.iloc[idx], ref_fa_name, tig_fa_name, hap, version_id=version_id)
+
+
+def merge_shard_frames(frames):
+    """``[(df_snv, df_insdel), ...]`` of all shards -> the whole pair of tables: the shards' rows in chromosome order (each shard is
+    already sorted inside its chromosomes, and no chromosome is in two shards), row labels renumbered."""
+    import pandas as pd
+    out = []
+    for k in (0, 1):
+        parts = [f[k] for f in frames if f is not None and len(f[k])]
+        if not parts:
+            out.append(frames[0][k])
+            continue
+        df = pd.concat(parts, axis=0)
+        order = np.argsort(df['#CHROM'].to_numpy(dtype=object).astype(str), kind='stable')
+        out.append(df.iloc[order].reset_index(drop=True))
+    return tuple(out)
+
+
 last_dist_stats = None   # per-call record of the last make_insdel_snv_calls_dist on this rank (timings, checksums)
 
 
@@ -100,7 +146,7 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
         t_mine = cigarcall.AlignTable(mine) if len(mine) else None
         if walk_fn is None:
             # ---- the reference planes: every rank takes part in the collectives or all of them raise together
-            setup_err, uid = None, [None]
+            setup_err, uid, have_comm = None, [None], False
             tig_futs = []
             try:
                 ctx = device.get_context()
@@ -115,20 +161,29 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
                     for f in ref_futs:
                         f.result()
                     ref_store = device.SeqStore(ctx, names, ref_arr, keep_host=False)
-                    uid = [device.nccl_unique_id()]
                 else:
                     if t_mine is not None:
                         tig_all, tig_futs = cigarcall.read_sequences(tig_fa, list(t_mine.tig_names), pool, ctx, pinned)
                     ref_store = device.SeqStore.from_packed(ctx, names, [ref_fa.length(n) for n in names], None, None)
+                have_comm = device.nccl_comm_cached(ctx, rank, world)
             except Exception as ex:  # noqa: BLE001
                 setup_err = f'rank {rank}: {type(ex).__name__}: {ex}'
+                have_comm = False
             flags = [None] * world
-            dist.all_gather_object(flags, setup_err, group=group)
-            if any(flags):
+            dist.all_gather_object(flags, (setup_err, have_comm), group=group)
+            if any(e for e, _ in flags):
                 if ref_store is not None:
                     ref_store.close()
-                raise RuntimeError('make_insdel_snv_calls_dist: reference set-up failed: ' + '; '.join(f for f in flags if f))
-            dist.broadcast_object_list(uid, src=0, group=group)
+                raise RuntimeError('make_insdel_snv_calls_dist: reference set-up failed: ' + '; '.join(e for e, _ in flags if e))
+            # the NCCL communicator of an earlier call is reused when every rank still has it (setting one up costs seconds);
+            # otherwise rank 0 draws a new id and all ranks join it
+            if all(h for _, h in flags):
+                uid = [None]
+            else:
+                if rank == 0:
+                    uid = [device.nccl_unique_id()]
+                dist.broadcast_object_list(uid, src=0, group=group)
+            stats['nccl_comm_reused'] = uid[0] is None
             bc_err = None
             try:
                 stats['bcast_ms'] = ref_store.broadcast(uid[0], rank, world)

@@ -101,3 +101,27 @@ def test_dist_two_ranks_equal_single_process(tmp_path):
     assert got[0] == exp_snv.to_csv(sep='\t', index=False)
     assert got[1] == exp_indel.to_csv(sep='\t', index=False)
     assert got[2] == [int(i) for i in exp_snv.index] and got[3] == [int(i) for i in exp_indel.index]
+
+
+def test_chrom_shards_partition_by_reference_sequence():
+    """multigpu.chrom_shards: every record in exactly one shard, a chromosome never in two, loads balanced by LPT over chromosomes."""
+    import pandas as pd
+    from pav_b200 import multigpu
+    rng = np.random.default_rng(5)
+    chroms = [f'chr{i}' for i in range(1, 25)]
+    weight = np.linspace(8.0, 1.5, 24)
+    rows = []
+    for c, wgt in zip(chroms, weight):
+        for _ in range(int(wgt * 4)):
+            n_ops = int(rng.integers(200, 400))
+            rows.append((c, 0, 1000 * n_ops, '10=' * n_ops))
+    order = rng.permutation(len(rows))
+    df = pd.DataFrame([rows[i] for i in order], columns=['#CHROM', 'POS', 'END', 'CIGAR'])
+    for world in (1, 2, 4, 8):
+        shards = multigpu.chrom_shards(df, world)
+        assert len(shards) == world and sorted(np.concatenate(shards).tolist()) == list(range(len(df)))
+        owners = [set(df['#CHROM'].iloc[s]) for s in shards]
+        assert sum(len(o) for o in owners) == 24
+        cost = multigpu.record_costs(df['CIGAR'].tolist(), (df['END'] - df['POS']).to_numpy())
+        load = np.array([cost[s].sum() for s in shards])
+        assert load.max() <= 1.15 * load.mean(), (world, load)
