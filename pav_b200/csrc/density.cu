@@ -375,6 +375,12 @@ compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig
     if ((int)blockIdx.x >= n_tiles) return;
     __shared__ unsigned s_base;
     __shared__ unsigned s_warp[TILE / 32];
+    // this position's state and k-mer first: their loads do not depend on the prefix below and overlap with it (the CTA is one chain of
+    // dependent loads -- plan, tile counts, state, planes -- and two of them are resident per SM)
+    const int32_t i = blockIdx.x * TILE + threadIdx.x;
+    const int st = (i < n_pos) ? (int)st_pos[P.pos_off + i] : -1;
+    uint64_t kmer = 0;
+    if (i < n_pos) kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer, tig.nsum);
     // rows written by earlier tiles of this window
     unsigned part = 0;
     for (int t = threadIdx.x; t < (int)blockIdx.x; t += blockDim.x) {
@@ -387,8 +393,6 @@ compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig
     __syncthreads();
     if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_base, part);
     __syncthreads();
-    int32_t i = blockIdx.x * TILE + threadIdx.x;
-    int st = (i < n_pos) ? (int)st_pos[P.pos_off + i] : -1;
     bool keep = st >= 0 && ((P.keep_mask >> st) & 1);
     unsigned bal = __ballot_sync(FULL, keep);
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -404,8 +408,6 @@ compact_kernel(const WinPlan *__restrict__ plan, int32_t win_base, SeqPlanes tig
     const unsigned before = s_warp[wid];
     if (keep) {
         int64_t row = P.row_off + s_base + before + __popc(bal & ((1u << lane) - 1));
-        uint64_t kmer = 0;
-        kmer_at(tig.pack2, tig.nmask, P.tig_g0 + i, k, kmer, tig.nsum);
         o_kmer[row] = kmer;
         o_index[row] = i;
         o_state_mer[row] = (int8_t)st;
@@ -727,7 +729,10 @@ __device__ __forceinline__ double div_by_int(double y, double x, double r)
     return fma(fma(-q, x, y), r, q);
 }
 
-constexpr int FIN_ROWS = 4;      // rows per thread: the dependent loads (plan, gap flag, values) of FIN_ROWS rows overlap
+#ifndef FIN_ROWS_N
+#define FIN_ROWS_N 2
+#endif
+constexpr int FIN_ROWS = FIN_ROWS_N;      // rows per thread: the dependent loads (plan, gap flag, values) of FIN_ROWS rows overlap (r02, 296 windows: 1 row 0.205 ms, 2 rows 0.16, 4 rows 0.215, 8 rows 0.38 -- registers)
 
 __global__ void __launch_bounds__(256)
 finish_rows_kernel(const WinPlan *__restrict__ plan, int32_t win_base, const uint8_t *__restrict__ gap_full, const double *__restrict__ s0,

@@ -135,6 +135,7 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
         span = df_align['END'].to_numpy(dtype=np.int64) - full.pos
     shards = lpt_shards(record_costs(full.cigars, span), world)
     mine = df_align.iloc[shards[rank]]
+    marks = [('plan', time.perf_counter())]
     ref_fa, tig_fa = fasta.open_fasta(ref_fa_name), fasta.open_fasta(tig_fa_name)
     part = (np.zeros(0, device._capi.SNV_ROW), np.zeros(0, device._capi.INDEL_ROW))
     stats = {'rank': rank, 'world': world, 'records': int(len(mine)), 'bcast_ms': 0.0, 'checksum': None, 'planes_verified': None}
@@ -160,12 +161,14 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
                     tig_all, tig_futs = cigarcall.read_sequences(tig_fa, list(full.tig_names), pool, ctx, pinned)
                     for f in ref_futs:
                         f.result()
+                    marks.append(('read_reference', time.perf_counter()))
                     ref_store = device.SeqStore(ctx, names, ref_arr, keep_host=False)
                 else:
                     if t_mine is not None:
                         tig_all, tig_futs = cigarcall.read_sequences(tig_fa, list(t_mine.tig_names), pool, ctx, pinned)
                     ref_store = device.SeqStore.from_packed(ctx, names, [ref_fa.length(n) for n in names], None, None)
                 have_comm = device.nccl_comm_cached(ctx, rank, world)
+                marks.append(('store', time.perf_counter()))
             except Exception as ex:  # noqa: BLE001
                 setup_err = f'rank {rank}: {type(ex).__name__}: {ex}'
                 have_comm = False
@@ -184,10 +187,13 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
                     uid = [device.nccl_unique_id()]
                 dist.broadcast_object_list(uid, src=0, group=group)
             stats['nccl_comm_reused'] = uid[0] is None
+            marks.append(('agree', time.perf_counter()))
             bc_err = None
             try:
                 stats['bcast_ms'] = ref_store.broadcast(uid[0], rank, world)
+                marks.append(('broadcast', time.perf_counter()))
                 stats['checksum'] = ref_store.checksum() if verify_planes else None
+                marks.append(('checksum', time.perf_counter()))
             except Exception as ex:  # noqa: BLE001
                 bc_err = f'rank {rank}: {type(ex).__name__}: {ex}'
             sums = [None] * world
@@ -227,6 +233,10 @@ def make_insdel_snv_calls_dist(df_align, ref_fa_name, tig_fa_name, hap, version_
     dist.gather_object((part, err), gathered, dst=0, group=group)
     t3 = time.perf_counter()
     stats['seconds'] = {'shard_plan_reference_broadcast': t1 - t0, 'walk_incl_contig_read': t2 - t1, 'gather': t3 - t2}
+    prev = t0
+    for name, t in marks:      # where the first phase goes (each mark: seconds since the previous one)
+        stats['seconds']['setup_' + name] = t - prev
+        prev = t
     last_dist_stats = stats
     if rank != 0:
         return None
