@@ -513,6 +513,23 @@ def kernel_table(count_ms, walk_ms, hom_ms, hom_kernel, n_ops, n_chunks, n_snv, 
     }
 
 
+def gather_bound(n_indel, hom_ms):
+    """Second, tighter bound of the homology kernel: its sequence reads are SCATTERED 32-byte sectors, and the memory system delivers
+    those at a fraction of the streaming rate. The ceiling is measured by profiles/microbench/gather_rate.cu on a B200 of this pool
+    (independent random 8-byte loads over 4 GiB, saturated: profiles/r02_gather_rate.jsonl); the floor of the kernel is four such
+    accesses per indel (one per plane) plus its 128 B of streamed stub + row at the copy rate."""
+    try:
+        rows = [json.loads(ln) for ln in open(os.path.join(REPO, 'profiles', 'r02_gather_rate.jsonl')) if ln.strip()]
+        peak = max(r['gsectors_per_s'] for r in rows if r.get('pattern') == 'random')
+    except Exception:  # noqa: BLE001
+        return None
+    hbm, _ = measured_peak_gbs()
+    floor_ms = 4 * n_indel / (peak * 1e9) * 1e3 + 128 * n_indel / (hbm * 1e9) * 1e3
+    return {'peak_gaccesses_per_s': peak, 'source': 'profiles/r02_gather_rate.jsonl (profiles/microbench/gather_rate.cu)', 'accesses_per_launch': 4 * n_indel,
+            'floor_ms': floor_ms, 'frac': floor_ms / hom_ms if hom_ms > 0 else None,
+            'note': 'homology kernel against the measured rate of scattered sector reads (48.9 G/s = 1.57 TB/s as 32-byte sectors, a quarter of the copy rate)'}
+
+
 BYTES_MODEL = ('4 B/op + 4 B/chunk (count); 4 B/op + 32 B/chunk descriptors + 16 B/SNV row + 64 B/indel stub (walk); 64 B stub + 64 B row + 128 B of '
                'sequence = one 32-byte DRAM sector from each of the four planes an indel touches (homology); DESIGN.md section 3')
 
@@ -616,7 +633,7 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
     os.environ.setdefault('PAVGPU_TUNE_ALLOC', '1')    # opt-in allocator tuning of the frame builder, declared in `config`
     for i in range((E2E_WARMUP + args.e2e_steps) if args.e2e_steps > 0 else 0):
         fasta_mod._CACHE.clear()   # every step re-opens and re-reads the FASTA files, like a fresh Snakemake job would
-        out = None                 # the previous step's frames are released before the clock starts (the CPU arm's workers exit with theirs)
+        outs = []                  # a step's frames (both haplotypes) are released after its clock stops (the CPU arm's workers exit with theirs)
         ctl.barrier()
         t0 = time.perf_counter()
         rows_step, ph = 0, {}
@@ -627,8 +644,10 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
                 out = cigarcall.make_insdel_snv_calls(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
             ph[h] = cigarcall.last_phase_seconds
             rows_step += len(out[0]) + len(out[1])
+            outs.append(out)
             out = None
         dt = ctl.max(time.perf_counter() - t0)
+        outs = None
         rows_all = int(ctl.sum(rows_step))
         if i >= E2E_WARMUP:
             e2e_s.append(dt)
@@ -681,7 +700,7 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
                  'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak if my_ms else None},
         'survey_8d_model': {'algorithmic_bytes': int(survey_bytes), 'achieved': survey_bytes / (my_ms * 1e-3) / 1e9 if my_ms else None,
                             'frac': survey_bytes / (my_ms * 1e-3) / 1e9 / peak if my_ms else None, 'per': 'whole step of rank 0 (count + walk + homology)'},
-        'bytes_model': BYTES_MODEL,
+        'bytes_model': BYTES_MODEL, 'gather': gather_bound(n_indel, hom_ms),
         'note': 'traffic (DRAM bytes from ncu) is reported for the C2 leg (`c2.roofline`), the input the ncu captures under profiles/ are taken on',
     }
     ref_store.close()
@@ -749,7 +768,7 @@ def leg_c5(args, ctl, ctx, rank, world):
             rs.close()
             ts.close()
     # ---- the public call: ASCII windows in host memory -> run lengths of STATE in host memory (columns on demand)
-    e2e_s, n_runs = [], 0
+    e2e_s, n_runs, e2e_phases = [], 0, {}
     for i in range(3):
         out = None
         ctl.barrier()
@@ -757,6 +776,7 @@ def leg_c5(args, ctl, ctx, rank, world):
         out = density.density_windows([(w[0], w[1], False, 20) for w in wins], lazy=True)
         e2e_s.append(ctl.max(time.perf_counter() - t0))
         n_runs = sum(len(d['runs']) for d in out)
+        e2e_phases = dict(density.last_stats.get('seconds_all_batches') or density.last_stats.get('seconds') or {})
     out = None
     e2e_t = float(np.mean(e2e_s[1:]))
     ok = None
@@ -776,11 +796,15 @@ def leg_c5(args, ctl, ctx, rank, world):
     kmer_bytes = len(wins) * (-(-2 * W // 4) + 8 * W + 16 * (W - K + 1) + 13 * (W - K + 1))
     peak, peak_src = measured_peak_gbs()
     roofs = {
-        'kmer_part': {'bound': 'hbm', 'kernels': 'ref_insert + tig_state + compact', 'algorithmic_bytes': int(kmer_bytes), 'ms': ms_kmer,
+        'kmer_part': {'bound': 'hbm', 'kernels': 'kmer_window (reference k-mer table in shared memory; ref_insert + tig_state for windows it does not take) + compact',
+                      'bytes_model': 'per window: packed planes of both windows + 8 B per reference k-mer inserted + 2 x 8 B probed per contig k-mer + 13 B per row '
+                                     'compacted -- the bytes of a table in HBM (r01 model, kept so that fractions compare across rounds); with the table in shared '
+                                     'memory the 24 B per position never leave the SM (ncu: 9 MB of DRAM reads per 296 windows for the k-mer kernel)',
+                      'algorithmic_bytes': int(kmer_bytes), 'ms': ms_kmer,
                       'achieved': kmer_bytes / (ms_kmer * 1e-3) / 1e9 if ms_kmer > 0 else None, 'peak': peak, 'unit': 'GB/s',
                       'frac': kmer_bytes / (ms_kmer * 1e-3) / 1e9 / peak if ms_kmer > 0 else None, 'peak_source': peak_src, 'per': f'rank {rank}'},
         'kde_part': {'bound': 'float64 CUDA-core arithmetic (exp + FMA), not HBM',
-                     'kernels': 'runs_stats + kde_tree + kde_eval x2 + gap_classify + interp + finalize + state_rle',
+                     'kernels': 'runs_stats + kde_table + kde_eval x2 + gap_classify + finish_rows + state_rle',
                      'ms': ms_kde, 'rows_N': rows, 'evaluated_points_E': n_eval, 'eval_fraction_E_over_N': n_eval / rows if rows else None,
                      'logical_pairs': int(pairs), 'logical_pairs_per_sec': pairs / (ms_kde * 1e-3) if ms_kde > 0 else None},
     }
@@ -788,7 +812,7 @@ def leg_c5(args, ctl, ctx, rank, world):
     return {
         'metric': METRIC_B, 'unit': UNIT_B, 'value': total_bases / (ms_max * 1e-3) / 1e9 if ms_max > 0 else None, 'ms_per_step': ms_max,
         'scaling': 'strong', 'config': {'workload': workload_c5(args, world), 'chunk_windows': CHUNK, 'l2': 'flushed before every chunk'},
-        'e2e': {'value': total_bases / e2e_t / 1e9, 'unit': UNIT_B, 'ms_per_step': e2e_t * 1e3, 'h2d_bytes_per_step': int(2 * total_bases),
+        'e2e': {'value': total_bases / e2e_t / 1e9, 'unit': UNIT_B, 'ms_per_step': e2e_t * 1e3, 'phase_seconds_last_step_rank0': e2e_phases, 'h2d_bytes_per_step': int(2 * total_bases),
                 'd2h_bytes_per_step': int(16 * ctl.sum(n_runs) + 32 * n_total),
                 'api': 'pav_b200.pavlib.density.density_windows(lazy=True): ASCII windows in host memory -> status + run lengths of STATE in host memory; '
                        'the 38 B/row columns stay in HBM until a window becomes a call (pavgpu_density_batch_fetch_runs / _fetch_window)'},
@@ -905,7 +929,7 @@ def leg_c2(args, ctx, tmp):
                      'step': {'algorithmic_bytes': int(step_bytes), 'achieved': step_bytes / (my_ms * 1e-3) / 1e9, 'frac': step_bytes / (my_ms * 1e-3) / 1e9 / peak},
                      'survey_8d_model': {'algorithmic_bytes': int(survey_bytes), 'achieved': survey_bytes / (my_ms * 1e-3) / 1e9,
                                          'frac': survey_bytes / (my_ms * 1e-3) / 1e9 / peak},
-                     'bytes_model': BYTES_MODEL},
+                     'bytes_model': BYTES_MODEL, 'gather': gather_bound(n_indel, hom_ms)},
     }
 
 

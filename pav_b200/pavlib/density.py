@@ -145,9 +145,12 @@ def density_windows(windows, k=31, ctx=None, lazy=False, **kw):
     ctx = ctx or device.get_context()
     windows = list(windows)
     if len(windows) > MAX_WINDOWS_PER_BATCH:   # bound the device arena and the pinned result buffers (~5 MB + ~2 MB per 50 kbp window)
-        out = []
+        out, total = [], {}
         for a in range(0, len(windows), MAX_WINDOWS_PER_BATCH):
             out.extend(density_windows(windows[a:a + MAX_WINDOWS_PER_BATCH], k=k, ctx=ctx, lazy=lazy, **kw))
+            for name, sec in last_stats['seconds'].items():
+                total[name] = total.get(name, 0.0) + sec
+        last_stats['seconds_all_batches'] = total      # (the other entries describe the last batch)
         return out
     refs = [np.ascontiguousarray(w[0], dtype=np.uint8) for w in windows]
     tigs = [np.ascontiguousarray(w[1], dtype=np.uint8) for w in windows]

@@ -44,6 +44,9 @@ class AlignLift:
             self._by_qid.setdefault(q, []).append(i)
         self._by_chrom = {c: np.array(v, dtype=np.int64) for c, v in self._by_chrom.items()}
         self._by_qid = {q: np.array(v, dtype=np.int64) for q, v in self._by_qid.items()}
+        # scalar copies for the common case of one candidate record (a numpy mask over a 1-element array costs ~10 us per lookup)
+        self._pos_l, self._end_l = self._pos.tolist(), self._end.tolist()
+        self._qpos_l, self._qend_l = self._qpos.tolist(), self._qend.tolist()
         # Block tables of the records looked at so far. The reference keeps the interval trees of the last ``cache_align`` (10)
         # records; a batch of hundreds of loci on as many records rebuilt its tables on most lookups that way (a fifth of the host
         # time of call_inv_batch). The tables are a cache either way, so they are kept until they add up to PAVGPU_LIFT_CACHE_MB
@@ -65,11 +68,11 @@ class AlignLift:
             raise RuntimeError('Malformed CIGAR for alignment {}:{} ({})'.format(row['#CHROM'], row['POS'], row['QRY_ID']))
         code = (ops & 15).astype(np.int64)
         ln = (ops >> 4).astype(np.int64)
-        bad = ~np.isin(code, (0, 1, 2, 4, 5, 7, 8))
+        is_m = (code == 0) | (code == 7) | (code == 8)
+        bad = ~(is_m | (code == 1) | (code == 2) | (code == 4) | (code == 5))
         if bad.any():
             raise RuntimeError('Unhandled CIGAR operation: {}: Alignment {}:{} ({})'.format(
                 'MIDNSHP=X'[int(code[bad][0])], row['#CHROM'], row['POS'], row['QRY_ID']))
-        is_m = np.isin(code, _MATCH_CODES)
         ref_adv = np.where(is_m | (code == 2), ln, 0)
         qry_adv = np.where(is_m | (code == 1) | (code == 4) | (code == 5), ln, 0)
         sub = int(row['POS']) + np.cumsum(ref_adv) - ref_adv
@@ -111,7 +114,13 @@ class AlignLift:
         out = []
         for pos in coord:
             cand = self._by_chrom.get(subject_id)
-            hit = cand[(self._pos[cand] <= pos) & (self._end[cand] > pos)] if cand is not None else ()
+            if cand is None:
+                hit = ()
+            elif len(cand) == 1:
+                i0 = int(cand[0])
+                hit = (i0,) if self._pos_l[i0] <= pos < self._end_l[i0] else ()
+            else:
+                hit = cand[(self._pos[cand] <= pos) & (self._end[cand] > pos)]
             if len(hit) != 1:
                 out.append(None)
                 continue
@@ -140,7 +149,13 @@ class AlignLift:
         for pos in coord:
             pos_org = pos
             cand = self._by_qid.get(query_id)
-            hit = cand[(self._qpos[cand] <= pos) & (self._qend[cand] > pos)] if cand is not None else ()
+            if cand is None:
+                hit = ()
+            elif len(cand) == 1:
+                i0 = int(cand[0])
+                hit = (i0,) if self._qpos_l[i0] <= pos < self._qend_l[i0] else ()
+            else:
+                hit = cand[(self._qpos[cand] <= pos) & (self._qend[cand] > pos)]
             if len(hit) == 0 and gap:
                 out.append(self._get_subject_gap(query_id, pos))
                 continue
