@@ -215,6 +215,40 @@ class Fasta:
             dst[full * linebases:] = self._buf[b0:b0 + rem]
         return dst
 
+    def line_chunks(self, name, chunk_bases):
+        """Split record ``name`` for ``fetch_lines_into``: ``[(line0, line1), ...]`` over its FULL lines, about ``chunk_bases`` each
+        (the last chunk also carries the partial last line); ``None`` when the record cannot be copied by lines (compressed file)."""
+        name = str(name)
+        length, offset, linebases, linewidth = self.index[name]
+        if self._bgzf is not None or self._buf is None or len(self._buf) < offset or length == 0 or linebases <= 0:
+            return None
+        full = length // linebases
+        if full and offset + full * linewidth > len(self._buf):
+            full -= 1       # (the file ends right after the last full line, without its newline: fetch_into handles that record whole)
+            return None
+        per = max(int(chunk_bases) // linebases, 1)
+        cuts = list(range(0, full, per)) + [full]
+        if len(cuts) == 1:
+            cuts = [0, 0]
+        return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+
+    def fetch_lines_into(self, name, out, line0, line1):
+        """Full lines ``[line0, line1)`` of record ``name`` into their place in ``out`` (laid out like ``fetch_into``'s result); the
+        chunk that ends at the record's last full line also copies the partial line behind it. Chunks of one record can be copied
+        by different threads."""
+        name = str(name)
+        length, offset, linebases, linewidth = self.index[name]
+        full = length // linebases
+        n = line1 - line0
+        if n > 0:
+            src = self._buf[offset + line0 * linewidth:offset + line1 * linewidth].reshape(n, linewidth)[:, :linebases]
+            np.copyto(out[line0 * linebases:line1 * linebases].reshape(n, linebases), src)
+        if line1 == full:
+            rem = length - full * linebases
+            if rem:
+                b0 = offset + full * linewidth
+                out[full * linebases:length] = self._buf[b0:b0 + rem]
+
     def fetch(self, name, start=None, end=None):
         """``pysam.FastaFile.fetch`` look-alike returning ``str``."""
         return self.fetch_array(name, start, end).tobytes().decode('ascii')

@@ -459,3 +459,31 @@ def test_binding_arity_matches_header():
             assert len(fn.argtypes) == n, (name, n, len(fn.argtypes))
         else:
             assert n == 0 or name in ('pavgpu_device_count', 'pavgpu_last_error'), name
+
+
+def test_read_sequences_splits_large_records_across_jobs(tmp_path):
+    """cigarcall.read_sequences: large records are copied as runs of lines by several jobs, small ones grouped; every layout of the
+    last line (full, partial, no trailing newline) gives the bases of the plain reader."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from pav_b200 import fasta, synth
+    from pav_b200.pavlib import cigarcall
+    rng = np.random.default_rng(17)
+    seqs = {f'c{i}': synth.random_seq(rng, n) for i, n in enumerate([9_000_123, 2_400_000, 61, 60, 59, 1, 4_345_678, 7, 3_000_060])}
+    p = synth.write_fasta(str(tmp_path / 'x.fa'), seqs)
+    for strip_newline in (False, True):
+        if strip_newline:
+            raw = open(p, 'rb').read().rstrip(b'\n')
+            p = str(tmp_path / 'y.fa')
+            open(p, 'wb').write(raw)
+            import subprocess
+            idx = fasta.Fasta(p)     # builds y.fa.fai
+            assert idx.length('c8') == 3_000_060
+        fa = fasta.open_fasta(p)
+        with ThreadPoolExecutor(6) as pool:
+            out, futs = cigarcall.read_sequences(fa, list(seqs), pool)
+            for f in futs:
+                f.result()
+        assert len(futs) > len(seqs) // 2
+        for nm, a in zip(seqs, out):
+            assert np.array_equal(a, seqs[nm]), (nm, strip_newline)
