@@ -11,6 +11,8 @@ directory travels to the GPU box with the tree). Only the package trees the hot 
     dep/svpop/svpoplib/          svpoplib.variant.version_id, svpoplib.ref.get_df_fai (imported by pavlib/__init__)
     dep/svpop/dep/kanapy/        kanapy.util.kmer (k-mer arithmetic / stream)
     dep/svpop/dep/ply/ply/       PLY (imported by svpoplib.svmergeconfig at import time)
+    rules/call.snakefile,        the rule bodies `call_cigar` and `call_inv_batch`, executed UNMODIFIED against the overlay by
+    rules/call_inv.snakefile     tests/test_dropin_gpu.py (the drop-in check at the rule level)
 
 oracle/_ref/MANIFEST.json records the sha256 of every staged file next to the sha256 of its source, so "unmodified" can be checked.
 Used by: bench.py --impl reference and bench.py's cpu_baseline leg (oracle/refenv.py resolves /root/reference first, then
@@ -28,7 +30,7 @@ SRC = '/root/reference'
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, '_ref')
 TREES = ['pavlib', 'dep/svpop/svpoplib', 'dep/svpop/dep/kanapy', 'dep/svpop/dep/ply/ply']
-FILES = ['scripts/density.py', 'LICENSE', 'dep/svpop/LICENSE']
+FILES = ['scripts/density.py', 'LICENSE', 'dep/svpop/LICENSE', 'rules/call.snakefile', 'rules/call_inv.snakefile']
 
 
 def _sha(path):
