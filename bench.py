@@ -633,7 +633,7 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
     os.environ.setdefault('PAVGPU_TUNE_ALLOC', '1')    # opt-in allocator tuning of the frame builder, declared in `config`
     for i in range((E2E_WARMUP + args.e2e_steps) if args.e2e_steps > 0 else 0):
         fasta_mod._CACHE.clear()   # every step re-opens and re-reads the FASTA files, like a fresh Snakemake job would
-        outs = []                  # a step's frames (both haplotypes) are released after its clock stops (the CPU arm's workers exit with theirs)
+        out = None                 # the previous step's frames are released before the clock starts (the CPU arm's workers exit with theirs)
         ctl.barrier()
         t0 = time.perf_counter()
         rows_step, ph = 0, {}
@@ -644,10 +644,8 @@ def leg_c3(args, ctl, ctx, tmp, rank, world):
                 out = cigarcall.make_insdel_snv_calls(dfs[h], ref_fa, tig_fa[h], h, version_id=False)
             ph[h] = cigarcall.last_phase_seconds
             rows_step += len(out[0]) + len(out[1])
-            outs.append(out)
-            out = None
+            out = None             # (holding h1's frames while h2's are built was measured: no faster -- the allocator cannot reuse their memory)
         dt = ctl.max(time.perf_counter() - t0)
-        outs = None
         rows_all = int(ctl.sum(rows_step))
         if i >= E2E_WARMUP:
             e2e_s.append(dt)

@@ -130,6 +130,10 @@ class _InvScan:
     def __init__(self, region_flag, ref_fa_name, tig_fa_name, align_lift, k_util, n_tree, max_region_size, log, srs_tree, min_exp_count,
                  df_fai=None):
         self.region_flag = region_flag
+        # Regions handed back inside the InvCall are built from the CALLER's Region class: a rule that passes the reference's
+        # pavlib.seq.Region goes on to hand them to the reference's own functions, which test `region.__class__ == Region`
+        # (pavlib/seq.py:341-346, region_seq_fasta in rule call_inv_batch)
+        self.region_cls = type(region_flag) if hasattr(region_flag, 'to_base1_string') else pavseq.Region
         self.ref_fa_name, self.tig_fa_name = ref_fa_name, tig_fa_name
         self.align_lift, self.k_util, self.log = align_lift, k_util, log
         self.k_size = int(k_util.k_size)
@@ -217,9 +221,9 @@ class _InvScan:
         if state_rl[0][0] != 0 or state_rl[-1][0] != 0:
             raise RuntimeError('Found INV region not flanked by reference sequence (program bug): {}'.format(region_ref))
         state_rl_inv = [record for record in state_rl if record[0] == 2]
-        region_tig_outer = pavseq.Region(region_tig.chrom, state_rl[1][2] + region_tig.pos,
+        region_tig_outer = self.region_cls(region_tig.chrom, state_rl[1][2] + region_tig.pos,
                                          state_rl[-2][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
-        region_tig_inner = pavseq.Region(region_tig.chrom, state_rl_inv[0][2] + region_tig.pos,
+        region_tig_inner = self.region_cls(region_tig.chrom, state_rl_inv[0][2] + region_tig.pos,
                                          state_rl_inv[-1][3] + region_tig.pos + k_size, is_rev=region_tig.is_rev)
         region_ref_outer = align_lift.lift_region_to_sub(region_tig_outer)
         if region_ref_outer is None:
