@@ -113,6 +113,23 @@ typedef struct {
 int pavgpu_cigar_parse(const char *cigar_text, const int64_t *text_off, int32_t n_rec,
                        uint32_t **ops_out, int64_t *op_off_out, pavgpu_parse_err *err);
 
+/* Per-record CIGAR summary for the SAM -> alignment-table step (pavlib/align/align.py:666-794, what get_align_bed derives from
+ * pysam's cigartuples record by record): computed on the device, one warp per record, from the packed ops of pavgpu_cigar_parse. */
+typedef struct { /* 48 B */
+    int64_t ref_bp;       /* bases of the reference covered by the core: sum of = X D N lengths (:735-741) */
+    int64_t qry_bp;       /* bases of the query covered by the core: sum of = X I lengths */
+    int64_t lead;         /* summed lengths of the clip ops (S / H) before the first non-clip op (:706-716) */
+    int64_t trail;        /* ... after the last non-clip op */
+    int32_t first_body;   /* op number of the first / last non-clip op inside the record; -1: the record has only clips */
+    int32_t last_body;
+    int32_t clip_h_first; /* length of op 0 when it is H, else 0 */
+    int32_t lead_s;       /* length of the first op that is not H when that op is S, else 0 (pysam's query_alignment_start) */
+    int32_t flags;        /* bit 0: an M op is present (rejected, :700-704); bit 1: a clip op lies between first_body and last_body */
+    int32_t n_ops;
+} pavgpu_cigar_rec_stats;
+int pavgpu_cigar_record_stats(pavgpu_ctx *ctx, const uint32_t *ops, const int64_t *op_off, int32_t n_rec,
+                              pavgpu_cigar_rec_stats *stats_out);
+
 typedef struct { /* 16 B: one row per mismatched base (pavlib/cigarcall.py:98-135) */
     int32_t pos_ref;  /* POS (END = POS + 1) */
     int32_t qry_pos;  /* 0-based position on the forward contig; QRY_REGION = qry_pos+1 .. qry_pos+1 */

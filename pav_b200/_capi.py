@@ -22,6 +22,8 @@ assert SNV_ROW.itemsize == 16 and INDEL_ROW.itemsize == 64
 
 DENSITY_WINDOW = np.dtype([('ref_seq_id', '<i4'), ('tig_seq_id', '<i4'), ('ref_pos', '<i4'), ('ref_end', '<i4'),
                            ('tig_pos', '<i4'), ('tig_end', '<i4'), ('rev', '<i4'), ('srs', '<i4')])
+CIGAR_REC_STATS = np.dtype([('ref_bp', '<i8'), ('qry_bp', '<i8'), ('lead', '<i8'), ('trail', '<i8'), ('first_body', '<i4'), ('last_body', '<i4'),
+                            ('clip_h_first', '<i4'), ('lead_s', '<i4'), ('flags', '<i4'), ('n_ops', '<i4')])
 STATE_RUN = np.dtype([('state', '<i4'), ('count', '<i4'), ('first_index', '<i4'), ('last_index', '<i4')])
 DENSITY_RESULT = np.dtype([('status', '<i4'), ('smoothed', '<i4'), ('row_off', '<i8'), ('n_rows', '<i8'), ('n_eval', '<i8')])
 
@@ -70,6 +72,7 @@ EXPORTS = [
     'pavgpu_homology', 'pavgpu_density_default_params', 'pavgpu_density_batch_create', 'pavgpu_density_batch_free',
     'pavgpu_density_batch_run', 'pavgpu_density_batch_fetch', 'pavgpu_density_batch_fetch_runs', 'pavgpu_density_batch_fetch_window',
     'pavgpu_nccl_unique_id', 'pavgpu_seqstore_broadcast', 'pavgpu_nccl_comm_cached', 'pavgpu_nccl_comm_release_all',
+    'pavgpu_cigar_record_stats',
 ]
 
 
@@ -111,6 +114,7 @@ def lib():
     L.pavgpu_seqstore_export.argtypes = [c_vp, c_vp, c_vp]
     L.pavgpu_seqstore_checksum.argtypes = [c_vp, c_vp]
     L.pavgpu_cigar_parse.argtypes = [ctypes.c_char_p, P(c_i64), c_i32, P(c_vp), P(c_i64), P(ParseErr)]
+    L.pavgpu_cigar_record_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
     L.pavgpu_cigar_batch_create.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp)]
     L.pavgpu_cigar_batch_free.argtypes = [c_vp]
     L.pavgpu_cigar_batch_free.restype = None

@@ -1226,6 +1226,106 @@ struct pavgpu_cigar_batch {
     std::vector<int32_t> h_pos;
 };
 
+// ------------------------------------------------------------------------------------------------
+// SAM -> alignment table: the per-record sums get_align_bed needs, one warp per record.
+// Pass 1 finds the first / last non-clip op and the first op that is not H; pass 2 (the record's ops are in L1 / L2 by then) sums
+// the lengths by op class on either side of them.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(128)
+cigar_record_stats_kernel(const uint32_t *__restrict__ ops, const int64_t *__restrict__ op_off, int32_t n_rec, pavgpu_cigar_rec_stats *__restrict__ out)
+{
+    const int32_t r = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_rec) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t o0 = op_off[r], n = op_off[r + 1] - o0;
+    const uint32_t *p = ops + o0;
+    int64_t first = n, last = -1, first_noth = n;
+    for (int64_t i = lane; i < n; i += 32) {
+        const uint32_t code = p[i] & 15u;
+        const bool clip = code == PAVGPU_OP_S || code == PAVGPU_OP_H;
+        if (!clip) { first = min(first, i); last = max(last, i); }
+        if (code != PAVGPU_OP_H) first_noth = min(first_noth, i);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+        first_noth = min(first_noth, __shfl_xor_sync(0xffffffffu, first_noth, d));
+    }
+    unsigned long long ref_bp = 0, qry_bp = 0, lead = 0, trail = 0;
+    unsigned flags = 0;
+    for (int64_t i = lane; i < n; i += 32) {
+        const uint32_t op = p[i], code = op & 15u;
+        const unsigned long long len = op >> 4;
+        const bool clip = code == PAVGPU_OP_S || code == PAVGPU_OP_H;
+        if (code == PAVGPU_OP_M) flags |= 1u;
+        if (clip) {
+            if (last < 0 || i < first) lead += len;          // (a record of clips only: everything is leading, as in the reference)
+            else if (i > last) trail += len;
+            else flags |= 2u;
+        } else {
+            const bool eqx = code == PAVGPU_OP_EQ || code == PAVGPU_OP_X;
+            if (eqx || code == PAVGPU_OP_D || code == PAVGPU_OP_N) ref_bp += len;
+            if (eqx || code == PAVGPU_OP_I) qry_bp += len;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ref_bp += __shfl_xor_sync(0xffffffffu, ref_bp, d);
+        qry_bp += __shfl_xor_sync(0xffffffffu, qry_bp, d);
+        lead += __shfl_xor_sync(0xffffffffu, lead, d);
+        trail += __shfl_xor_sync(0xffffffffu, trail, d);
+        flags |= __shfl_xor_sync(0xffffffffu, flags, d);
+    }
+    if (lane == 0) {
+        pavgpu_cigar_rec_stats s;
+        s.ref_bp = (int64_t)ref_bp; s.qry_bp = (int64_t)qry_bp; s.lead = (int64_t)lead; s.trail = (int64_t)trail;
+        s.first_body = last < 0 ? -1 : (int32_t)first;
+        s.last_body = (int32_t)last;
+        s.clip_h_first = (n > 0 && (p[0] & 15u) == PAVGPU_OP_H) ? (int32_t)(p[0] >> 4) : 0;
+        s.lead_s = (first_noth < n && (p[first_noth] & 15u) == PAVGPU_OP_S) ? (int32_t)(p[first_noth] >> 4) : 0;
+        s.flags = (int32_t)flags;
+        s.n_ops = (int32_t)n;
+        out[r] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_record_stats(pavgpu_ctx *ctx, const uint32_t *ops, const int64_t *op_off, int32_t n_rec,
+                                                                                  pavgpu_cigar_rec_stats *stats_out)
+{
+    if (!ctx || n_rec < 0 || (n_rec > 0 && (!op_off || !stats_out))) { pav_set_error("cigar_record_stats: bad argument"); return PAVGPU_ERR_ARG; }
+    if (n_rec == 0) return PAVGPU_OK;
+    const int64_t n_ops = op_off[n_rec] - op_off[0];
+    if (n_ops < 0 || op_off[0] != 0 || (n_ops > 0 && !ops)) { pav_set_error("cigar_record_stats: op_off must start at 0 and ascend"); return PAVGPU_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t b_ops = sizeof(uint32_t) * (size_t)std::max<int64_t>(n_ops, 1), b_off = sizeof(int64_t) * ((size_t)n_rec + 1),
+                 b_out = sizeof(pavgpu_cigar_rec_stats) * (size_t)n_rec;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    void *arena = nullptr;
+    CUDA_TRY(pav_dev_alloc(ctx, up(b_ops) + up(b_off) + up(b_out), &arena));
+    char *base = static_cast<char *>(arena);
+    uint32_t *d_ops = reinterpret_cast<uint32_t *>(base);
+    int64_t *d_off = reinterpret_cast<int64_t *>(base + up(b_ops));
+    pavgpu_cigar_rec_stats *d_out = reinterpret_cast<pavgpu_cigar_rec_stats *>(base + up(b_ops) + up(b_off));
+    int rc = [&]() -> int {
+        if (n_ops > 0) CUDA_TRY(cudaMemcpyAsync(d_ops, ops, sizeof(uint32_t) * (size_t)n_ops, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_off, op_off, b_off, cudaMemcpyHostToDevice, st));
+        const unsigned blocks = (unsigned)(((int64_t)n_rec * 32 + 127) / 128);
+        cigar_record_stats_kernel<<<blocks, 128, 0, st>>>(d_ops, d_off, n_rec, d_out);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(stats_out, d_out, b_out, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return PAVGPU_OK;
+    }();
+    pav_dev_free(ctx, arena);
+    return rc;
+}
+
 extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_parse(const char *text, const int64_t *text_off, int32_t n_rec, uint32_t **ops_out,
                                   int64_t *op_off_out, pavgpu_parse_err *err)
 {

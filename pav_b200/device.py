@@ -159,6 +159,19 @@ def nccl_unique_id():
     return buf.tobytes()
 
 
+def cigar_record_stats(ops, op_off, ctx=None):
+    """Per-record CIGAR summary on the device (``pavgpu_cigar_record_stats``): structured array ``_capi.CIGAR_REC_STATS``, one
+    entry per record of ``parse_cigars``' output."""
+    ctx = ctx or get_context()
+    n_rec = len(op_off) - 1
+    out = np.zeros(n_rec, dtype=_capi.CIGAR_REC_STATS)
+    ops = np.ascontiguousarray(ops, dtype=np.uint32)
+    op_off = np.ascontiguousarray(op_off, dtype=np.int64)
+    _capi.check(_capi.lib().pavgpu_cigar_record_stats(ctx.handle, _capi.ptr(ops) if len(ops) else None, _capi.ptr(op_off), n_rec, _capi.ptr(out)),
+                'pavgpu_cigar_record_stats')
+    return out
+
+
 def parse_cigars(cigars):
     """Tokenise CIGAR strings on the host (C): -> (ops uint32, op_off int64[n+1], ParseErr)."""
     L = _capi.lib()

@@ -205,12 +205,45 @@ def _core_text(cigar, core_c, core_n, all_n):
     return ''.join(f'{a}{CIGAR_CODE_TO_CHAR[b]}' for b, a in zip(core_c.tolist(), core_n.tolist()))
 
 
-def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
+def _record_stats_host(code, ln, op_off):
+    """The per-record sums of ``pavgpu_cigar_record_stats`` with numpy on the host (same fields)."""
+    from .. import _capi
+    out = np.zeros(len(op_off) - 1, dtype=_capi.CIGAR_REC_STATS)
+    for i in range(len(op_off) - 1):
+        c, n = code[op_off[i]:op_off[i + 1]], ln[op_off[i]:op_off[i + 1]]
+        is_clip = (c == CIGAR_S) | (c == CIGAR_H)
+        body = np.flatnonzero(~is_clip)
+        s = out[i]
+        s['n_ops'] = len(c)
+        s['flags'] = int((c == CIGAR_M).any())
+        if len(body) == 0:
+            s['lead'], s['first_body'], s['last_body'] = int(n.sum()), -1, -1
+        else:
+            a, b = int(body[0]), int(body[-1])
+            s['lead'], s['trail'], s['first_body'], s['last_body'] = int(n[:a].sum()), int(n[b + 1:].sum()), a, b
+            cc, cn = c[a:b + 1], n[a:b + 1]
+            eqx = (cc == CIGAR_EQ) | (cc == CIGAR_X)
+            s['ref_bp'] = int(cn[eqx | (cc == CIGAR_D) | (cc == CIGAR_N)].sum())
+            s['qry_bp'] = int(cn[eqx | (cc == CIGAR_I)].sum())
+            if is_clip[a:b + 1].any():
+                s['flags'] |= 2
+        if len(c):
+            s['clip_h_first'] = int(n[0]) if c[0] == CIGAR_H else 0
+            noth = np.flatnonzero(c != CIGAR_H)
+            if len(noth) and c[noth[0]] == CIGAR_S:
+                s['lead_s'] = int(n[noth[0]])
+    return out
+
+
+def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0, device_stats=False):
     """
     Read a SAM text file (plain or gzip) as the alignment table PAV processes (reference: pavlib/align/align.py:666-794,
     which reads SAM/BAM/CRAM through pysam). Unmapped records, records below ``min_mapq`` and records without a CIGAR are
     dropped; soft clips become hard clips; ``M`` operations are rejected; the table is sorted by
     ``#CHROM, POS, END (descending), QRY_ID`` and every record is sanity-checked.
+
+    ``device_stats=True``: the per-record CIGAR sums (aligned spans, clips, M test) come from ``pavgpu_cigar_record_stats``
+    (one warp per record on the GPU) instead of the numpy pass on the host; same table.
     """
     from .. import device
     recs = []
@@ -240,34 +273,21 @@ def get_align_bed(align_file, df_tig_fai, hap, min_mapq=0):
         raise RuntimeError('Malformed CIGAR in SAM record {} ({})'.format(recs[perr.rec][0], recs[perr.rec][1]))
     code = (ops & 15).astype(np.int64)
     ln = (ops >> 4).astype(np.int64)
+    stats = device.cigar_record_stats(ops, op_off) if device_stats else _record_stats_host(code, ln, op_off)
     rows = []
     for i, (idx, qname, flag, rname, pos, mapq, _, tags) in enumerate(recs):
         c, n = code[op_off[i]:op_off[i + 1]], ln[op_off[i]:op_off[i + 1]]
-        if (c == CIGAR_M).any():
+        st = stats[i]
+        if st['flags'] & 1:
             raise RuntimeError(('Found alignment match CIGAR operation (M) for record {} (Start = {}:{}): '
                                 'Alignment requires CIGAR base-level match/mismatch (=X)').format(qname, rname, pos))
-        is_clip = (c == CIGAR_S) | (c == CIGAR_H)
-        body = np.flatnonzero(~is_clip)
-        if len(body) == 0:
-            lead = int(n.sum())
-            trail = 0
+        lead, trail, ref_bp, qry_bp = int(st['lead']), int(st['trail']), int(st['ref_bp']), int(st['qry_bp'])
+        if st['first_body'] < 0:
             core_c, core_n = c[:0], n[:0]
         else:
-            lead = int(n[:body[0]].sum())
-            trail = int(n[body[-1] + 1:].sum())
-            core_c, core_n = c[body[0]:body[-1] + 1], n[body[0]:body[-1] + 1]
-        eqx = (core_c == CIGAR_EQ) | (core_c == CIGAR_X)
-        ref_bp = int(core_n[eqx | (core_c == CIGAR_D) | (core_c == CIGAR_N)].sum())
-        qry_bp = int(core_n[eqx | (core_c == CIGAR_I)].sum())
+            core_c, core_n = c[st['first_body']:st['last_body'] + 1], n[st['first_body']:st['last_body'] + 1]
         # pysam: query_alignment_start counts leading soft clips only; hard clips are added back by the reference
-        clip_h = int(n[0]) if c[0] == CIGAR_H else 0
-        lead_s = 0
-        for cc, nn in zip(c.tolist(), n.tolist()):
-            if cc == CIGAR_H:
-                continue
-            if cc == CIGAR_S:
-                lead_s = nn
-            break
+        clip_h, lead_s = int(st['clip_h_first']), int(st['lead_s'])
         tig_map_pos = lead if lead > 0 else 0
         if lead_s + clip_h != tig_map_pos:
             raise RuntimeError(f'First aligned based from pysam ({lead_s}) does not match clipping ({tig_map_pos}) at alignment record {idx}')

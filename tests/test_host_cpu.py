@@ -410,7 +410,7 @@ def test_binding_layouts_match_header(tmp_path):
         'pavgpu_parse_err': _capi.ParseErr, 'pavgpu_cigar_err': _capi.CigarErr, 'pavgpu_cigar_stats': _capi.CigarStats,
         'pavgpu_density_params': _capi.DensityParams, 'pavgpu_density_stats': _capi.DensityStats,
         'pavgpu_snv_row': _capi.SNV_ROW, 'pavgpu_indel_row': _capi.INDEL_ROW, 'pavgpu_density_window': _capi.DENSITY_WINDOW,
-        'pavgpu_density_result': _capi.DENSITY_RESULT, 'pavgpu_state_run': _capi.STATE_RUN,
+        'pavgpu_density_result': _capi.DENSITY_RESULT, 'pavgpu_state_run': _capi.STATE_RUN, 'pavgpu_cigar_rec_stats': _capi.CIGAR_REC_STATS,
     }
 
     def fields(b):
