@@ -263,6 +263,20 @@ int pavgpu_density_batch_fetch_runs(pavgpu_density_batch *batch, pavgpu_density_
 int pavgpu_density_batch_fetch_window(pavgpu_density_batch *batch, int32_t win, uint64_t *kmer, int32_t *index,
                                       int8_t *state_mer, int8_t *state, double *kern_fwd, double *kern_fwdrev, double *kern_rev);
 
+/* ---------------------------------------------------------------- coordinate lifts ---------- */
+/* Reference <-> contig lifts through alignment records (pavlib/align/lift.py:177-331 lift_to_sub, :380-476 lift_to_qry), batched:
+ * the index holds, for every packed CIGAR op of every record, its first reference and first contig coordinate (segmented prefix
+ * sums on the device, one CTA per record); a lift is a binary search inside the record plus the reference's block rules (one-base
+ * blocks map to the end of their image, reverse records flip the contig coordinate, contig -> reference accepts the exact end of a
+ * block). pos / rev / qry_len: POS, REV and contig length of each record. *bad_rec_out: first record with an op the lift does not
+ * handle (anything but M I D S H = X), or -1. status[i]: 0 = lifted, 1 = no block (the reference raises RuntimeError). */
+typedef struct pavgpu_lift_index pavgpu_lift_index;
+int pavgpu_lift_index_create(pavgpu_ctx *ctx, const uint32_t *ops, const int64_t *op_off, int32_t n_rec, const int64_t *pos,
+                             const uint8_t *rev, const int64_t *qry_len, pavgpu_lift_index **index_out, int32_t *bad_rec_out);
+void pavgpu_lift_index_free(pavgpu_lift_index *index);
+int pavgpu_lift_points(pavgpu_lift_index *index, int32_t n, const int32_t *rec, const int64_t *coord, int32_t to_qry,
+                       int64_t *out, int32_t *status);
+
 /* ---------------------------------------------------------------- multi-GPU ----------------- */
 /* Reference broadcast over NVLink: rank 0 owns a filled store, the other ranks an empty
  * one of the same shape. The caller moves the 128-byte id from rank 0 to all ranks (any side

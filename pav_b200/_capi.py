@@ -72,7 +72,7 @@ EXPORTS = [
     'pavgpu_homology', 'pavgpu_density_default_params', 'pavgpu_density_batch_create', 'pavgpu_density_batch_free',
     'pavgpu_density_batch_run', 'pavgpu_density_batch_fetch', 'pavgpu_density_batch_fetch_runs', 'pavgpu_density_batch_fetch_window',
     'pavgpu_nccl_unique_id', 'pavgpu_seqstore_broadcast', 'pavgpu_nccl_comm_cached', 'pavgpu_nccl_comm_release_all',
-    'pavgpu_cigar_record_stats',
+    'pavgpu_cigar_record_stats', 'pavgpu_lift_index_create', 'pavgpu_lift_index_free', 'pavgpu_lift_points',
 ]
 
 
@@ -115,6 +115,10 @@ def lib():
     L.pavgpu_seqstore_checksum.argtypes = [c_vp, c_vp]
     L.pavgpu_cigar_parse.argtypes = [ctypes.c_char_p, P(c_i64), c_i32, P(c_vp), P(c_i64), P(ParseErr)]
     L.pavgpu_cigar_record_stats.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp]
+    L.pavgpu_lift_index_create.argtypes = [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, P(c_vp), P(c_i32)]
+    L.pavgpu_lift_index_free.argtypes = [c_vp]
+    L.pavgpu_lift_index_free.restype = None
+    L.pavgpu_lift_points.argtypes = [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]
     L.pavgpu_cigar_batch_create.argtypes = [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, P(c_vp)]
     L.pavgpu_cigar_batch_free.argtypes = [c_vp]
     L.pavgpu_cigar_batch_free.restype = None

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libpavgpu.so')
-SOURCES = ['seqstore.cu', 'cigar.cu', 'density.cu', 'nccl_bcast.cu']
+SOURCES = ['seqstore.cu', 'cigar.cu', 'density.cu', 'nccl_bcast.cu', 'lift.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
          '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr'] + os.environ.get('PAVGPU_NVCC_DEFS', '').split()   # e.g. -DHOM_MIN_BLOCKS=5 for tuning runs

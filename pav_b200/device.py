@@ -159,6 +159,45 @@ def nccl_unique_id():
     return buf.tobytes()
 
 
+class LiftIndex:
+    """Device index for batched coordinate lifts (``pavgpu_lift_index_*``): per-op first reference / contig coordinates of every
+    record. ``bad_rec``: first record with an op the lift does not handle, or -1."""
+
+    def __init__(self, ctx, ops, op_off, pos, rev, qry_len):
+        self.ctx = ctx
+        ops = np.ascontiguousarray(ops, dtype=np.uint32)
+        op_off = np.ascontiguousarray(op_off, dtype=np.int64)
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        rev = np.ascontiguousarray(rev, dtype=np.uint8)
+        qry_len = np.ascontiguousarray(qry_len, dtype=np.int64)
+        self.n_rec = len(pos)
+        h, bad = c_vp(), _capi.c_i32(-1)
+        _capi.check(_capi.lib().pavgpu_lift_index_create(ctx.handle, _capi.ptr(ops) if len(ops) else None, _capi.ptr(op_off), self.n_rec, _capi.ptr(pos),
+                                                         _capi.ptr(rev), _capi.ptr(qry_len), ctypes.byref(h), ctypes.byref(bad)), 'pavgpu_lift_index_create')
+        self.handle, self.bad_rec = h, int(bad.value)
+
+    def lift(self, rec, coord, to_qry):
+        """-> (lifted int64 array, status int32 array: 0 lifted, 1 no block)."""
+        rec = np.ascontiguousarray(rec, dtype=np.int32)
+        coord = np.ascontiguousarray(coord, dtype=np.int64)
+        out, status = np.zeros(len(rec), dtype=np.int64), np.zeros(len(rec), dtype=np.int32)
+        if len(rec):
+            _capi.check(_capi.lib().pavgpu_lift_points(self.handle, len(rec), _capi.ptr(rec), _capi.ptr(coord), int(bool(to_qry)), _capi.ptr(out), _capi.ptr(status)),
+                        'pavgpu_lift_points')
+        return out, status
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _capi.lib().pavgpu_lift_index_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def cigar_record_stats(ops, op_off, ctx=None):
     """Per-record CIGAR summary on the device (``pavgpu_cigar_record_stats``): structured array ``_capi.CIGAR_REC_STATS``, one
     entry per record of ``parse_cigars``' output."""

@@ -152,6 +152,7 @@ class _InvScan:
             raise NotImplementedError('Custom state-run-smooth parameters are not currently implemented')
         self.srs_tree = srs_tree
         self.region_tig = None
+        self._prelift = None
         self.done = False
         self.result = None
 
@@ -167,7 +168,10 @@ class _InvScan:
             return self._finish(None)
         if self.n_tree_chrom is not None and len(self.n_tree_chrom[region_ref.pos:region_ref.end]) > 0:
             _write_log('Region overlaps N bases: {}'.format(region_ref), log)  # logged only, as in the reference
-        self.region_tig = self.align_lift.lift_region_to_qry(region_ref)
+        if self._prelift is not None:      # the batch driver lifted the regions of all open loci in one device call
+            self.region_tig, self._prelift = self._prelift[0], None
+        else:
+            self.region_tig = self.align_lift.lift_region_to_qry(region_ref)
         if self.region_tig is None:
             _write_log('Could not lift reference region onto contigs: {}'.format(region_ref), log)
             return self._finish(None)
@@ -326,8 +330,17 @@ def scan_for_inv_batch(region_flags, ref_fa_name, tig_fa_name, align_lift, k_uti
             scans.append(_Failed(ex))
     ref_fa, tig_fa = _fasta.open_fasta(ref_fa_name), _fasta.open_fasta(tig_fa_name)
     k_size = int(k_util.k_size)
+    batched_lift = getattr(align_lift, 'lift_regions_to_qry', None)
     while True:
         pending, windows = [], []
+        open_scans = [sc for sc in scans if not sc.done]
+        if batched_lift is not None and len(open_scans) > 1:
+            try:     # both ends of every open locus' region in one device call (pavgpu_lift_points)
+                for sc, r in zip(open_scans, batched_lift([sc.region_ref for sc in open_scans])):
+                    sc._prelift = [r]
+            except RuntimeError:   # some locus cannot be lifted: every locus meets its own error in its own turn below
+                for sc in open_scans:
+                    sc._prelift = None
         for sc in scans:
             if sc.done:
                 continue

@@ -56,6 +56,7 @@ class AlignLift:
         self._cache = collections.OrderedDict()
         self._cache_bytes = 0
         self._cache_cap = int(os.environ.get('PAVGPU_LIFT_CACHE_MB', '256')) << 20
+        self._dev_index = None      # device.LiftIndex, built by the first batched lift
 
     # ------------------------------------------------------------------ per-record block tables
     def _record_map(self, i):
@@ -104,6 +105,64 @@ class AlignLift:
                 return -1
             k -= 1
         return k
+
+    # ------------------------------------------------------------------ batched point lifts on the device
+    def _device_index(self):
+        """``device.LiftIndex`` over every record of the table, built on first use; ``None`` when a record has an op the lift does not
+        handle (the per-point path then raises for that record when -- and only when -- it is looked at, like the reference)."""
+        if self._dev_index is None:
+            ops, op_off, perr = device.parse_cigars(self._cigar.tolist())
+            if perr.code != 0:
+                self._dev_index = False
+            else:
+                qlen = np.array([int(self.df_fai[q]) for q in self._qid.tolist()], dtype=np.int64)
+                idx = device.LiftIndex(device.get_context(), ops, op_off, self._pos, np.asarray(self._rev, dtype=bool).astype(np.uint8), qlen)
+                self._dev_index = idx if idx.bad_rec < 0 else False
+        return self._dev_index or None
+
+    def lift_points(self, ids, coords, to_qry, gap=False):
+        """Many point lifts at once: ``ids[i]`` = chromosome (``to_qry``) or contig name, ``coords[i]`` = position. Same results, in
+        order, as ``lift_to_qry(id, coord)`` / ``lift_to_sub(id, coord, gap)`` one at a time -- the tuples, ``None`` where no single
+        record covers the position, ``RuntimeError`` for the first position inside a record that no block covers -- with the block
+        search of all positions in one launch (``pavgpu_lift_points``)."""
+        idx = self._device_index()
+        one = self.lift_to_qry if to_qry else (lambda i, c: self.lift_to_sub(i, c, gap))
+        if idx is None:
+            return [one(i, c) for i, c in zip(ids, coords)]
+        by = self._by_chrom if to_qry else self._by_qid
+        lo_l, hi_l = (self._pos_l, self._end_l) if to_qry else (self._qpos_l, self._qend_l)
+        recs, sel = [], []
+        out = [None] * len(ids)
+        for n, (name, pos) in enumerate(zip(ids, coords)):
+            cand = by.get(name)
+            hit = [] if cand is None else [i for i in cand.tolist() if lo_l[i] <= pos < hi_l[i]]
+            if len(hit) == 1:
+                recs.append(hit[0])
+                sel.append(n)
+            elif len(hit) == 0 and gap and not to_qry:
+                out[n] = self._get_subject_gap(name, pos)
+        lifted, status = idx.lift(recs, [coords[n] for n in sel], to_qry)
+        for n, i, v, st in zip(sel, recs, lifted.tolist(), status.tolist()):
+            if st != 0:
+                one(ids[n], coords[n])      # raises the reference's RuntimeError with its text
+                raise RuntimeError('lift: device and host disagree on {}:{}'.format(ids[n], coords[n]))
+            out[n] = ((self._qid[i] if to_qry else self._chrom[i]), v, self._rev[i], v, v, (self._aln_index[i],))
+        return out
+
+    def lift_regions_to_qry(self, regions):
+        """``lift_region_to_qry`` for a list of regions (both ends of all of them in one device call)."""
+        ids = [r.chrom for r in regions for _ in (0, 1)]
+        coords = [c for r in regions for c in (r.pos, r.end)]
+        pts = self.lift_points(ids, coords, True)
+        out = []
+        for k, _ in enumerate(regions):
+            q_pos, q_end = pts[2 * k], pts[2 * k + 1]
+            if q_pos is None or q_end is None or q_pos[0] != q_end[0] or q_pos[2] != q_end[2]:
+                out.append(None)
+                continue
+            out.append(pavseq.Region(q_pos[0], q_pos[1], q_end[1], is_rev=q_pos[2], pos_min=q_pos[3], pos_max=q_pos[4],
+                                     end_min=q_end[3], end_max=q_end[4], pos_aln_index=(q_pos[5],), end_aln_index=(q_end[5],)))
+        return out
 
     # ------------------------------------------------------------------ point lifts
     def lift_to_qry(self, subject_id, coord):
