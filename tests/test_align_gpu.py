@@ -33,12 +33,12 @@ def test_cigar_record_stats_equal_host_sums():
     cigars = []
     for r in range(3000):
         n = int(rng.choice([1, 2, 3, 5, 17, 33, 64, 400]))
-        body = ''.join('%d%s' % (int(rng.integers(1, 5000)), 'MIDN=XP'[int(rng.choice([1, 2, 3, 4, 5, 4, 4, 5, 6, 0] if r % 50 == 0 else [1, 2, 4, 5, 4, 4]))])
-                       for _ in range(n))
+        body = ['%d%s' % (int(rng.integers(1, 5000)), 'MIDN=XP'[int(rng.choice([1, 2, 3, 4, 5, 4, 4, 5, 6, 0] if r % 50 == 0 else [1, 2, 4, 5, 4, 4]))])
+                for _ in range(n)]
         lead = ['', '5H', '7S', '3H9S', '9S3H', '2S2S'][int(rng.integers(0, 6))]
         tail = ['', '4S', '6H', '8S1H', '1H8S'][int(rng.integers(0, 5))]
         mid = '11S' if r % 97 == 0 else ''
-        cigars.append(lead + body[:len(body) // 2] + mid + body[len(body) // 2:] + tail)
+        cigars.append(lead + ''.join(body[:len(body) // 2]) + mid + ''.join(body[len(body) // 2:]) + tail)
     cigars += ['10H', '3S4H', '12=', '1X']
     cigars.append(''.join('%d%s' % (1 + i % 7, '=XID'[i % 4]) for i in range(200_000)))
     ops, op_off, perr = device.parse_cigars(cigars)
