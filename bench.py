@@ -507,7 +507,7 @@ def oracle_check_records(rh, tmp, ref_fa, tag, n_chk=2):
 def kernel_table(count_ms, walk_ms, hom_ms, hom_kernel, n_ops, n_chunks, n_snv, n_indel):
     """kernel -> (ms, algorithmic bytes per launch): DESIGN.md section 3."""
     return {
-        'cigar_count+rec_scan': (count_ms, 4 * n_ops + 4 * n_chunks),
+        'cigar_count_kernel': (count_ms, 4 * n_ops + 4 * n_chunks),     # per-record row counts + (its last CTA) the record scan
         'cigar_walk_kernel': (walk_ms, 4 * n_ops + 2 * 16 * n_chunks + 16 * n_snv + 64 * n_indel),
         HOM_NAMES[hom_kernel]: (hom_ms, (64 + 64 + 128) * n_indel),
     }

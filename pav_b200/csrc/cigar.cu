@@ -565,19 +565,48 @@ cigar_walk_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, i
     }
 }
 
+// In-place exclusive scan of the two per-record count arrays (n_rec entries each, totals written to [n_rec]) by ONE CTA of
+// WARPS_PER_BLOCK warps: the last CTA of cigar_count_kernel. The counts were produced by atomics of other CTAs: read through L2.
+__device__ __forceinline__ void rec_scan_block(unsigned long long *a, unsigned long long *b, int32_t n_rec)
+{
+    constexpr int T = WARPS_PER_BLOCK * 32;
+    __shared__ unsigned long long s_a[T], s_b[T];
+    const int t = threadIdx.x;
+    const int32_t per = (n_rec + T - 1) / T;
+    const int32_t lo = min(t * per, n_rec), hi = min(lo + per, n_rec);
+    unsigned long long sa = 0, sb = 0;
+    for (int32_t r = lo; r < hi; r++) { sa += __ldcg(a + r); sb += __ldcg(b + r); }
+    s_a[t] = sa; s_b[t] = sb;
+    __syncthreads();
+    for (int d = 1; d < T; d <<= 1) {
+        const unsigned long long va = t >= d ? s_a[t - d] : 0ull, vb = t >= d ? s_b[t - d] : 0ull;
+        __syncthreads();
+        s_a[t] += va; s_b[t] += vb;
+        __syncthreads();
+    }
+    unsigned long long ea = t > 0 ? s_a[t - 1] : 0ull, eb = t > 0 ? s_b[t - 1] : 0ull;
+    for (int32_t r = lo; r < hi; r++) {
+        const unsigned long long ca = __ldcg(a + r), cb = __ldcg(b + r);
+        a[r] = ea; b[r] = eb;
+        ea += ca; eb += cb;
+    }
+    if (t == T - 1) { a[n_rec] = s_a[t]; b[n_rec] = s_b[t]; }
+}
+
 // K0a / K0b ---------------------------------------------------------------------------------------
 // What the walk needs before it can place rows without atomics: the first SNV / indel row slot of every record and the record of
-// every chunk's first op. Round 1 built them in a host pass over every op (1.9 ms for C2, outside the timed step); here they come
-// from the ops already in HBM: one warp per 256-op chunk sums its rows (a chunk inside one record, the common case, ends in one
-// atomicAdd per counter; chunks spanning records add per lane at every record change), then one CTA turns the per-record counts
-// into exclusive offsets in place (totals at [n_rec]).
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-cigar_count_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks, int32_t *__restrict__ chunk_rec,
-                   unsigned long long *__restrict__ rec_ns, unsigned long long *__restrict__ rec_ni, unsigned long long *__restrict__ span_total)
+// every chunk's first op. Round 1 built them in a host pass over every op (1.9 ms for C2, outside the timed step). Now the row
+// counts come from the ops already in HBM: one warp per 256-op chunk sums its rows (a chunk inside one record, the common case, ends
+// in one atomicAdd per counter; chunks spanning records add per lane at every record change), and the last CTA to finish turns the
+// per-record counts into exclusive offsets in place (totals at [n_rec]). The chunk -> record index is a merge of the chunk grid with
+// op_off (no op involved) and is uploaded with the batch.
+// The kernel also prepares the walk that follows it in the stream: every warp clears its chunk's look-back descriptor and chunk 0
+// resets the first-illegal-op cell (two memset nodes less per step). SPAN: also sum the reference span of the batch (a statistic;
+// only the first, eager run of a batch asks for it -- one atomic per chunk on a single address is not free).
+// Row counts of ONE chunk (the warp's lanes hold its ops), added to the per-record counters; returns the lane's reference advance.
+__device__ __forceinline__ unsigned long long count_one_chunk(const uint32_t *__restrict__ ops, int64_t n_ops, const RecView &rv, int64_t chunk, int32_t rec_lo,
+                                                              int lane, unsigned long long *__restrict__ rec_ns, unsigned long long *__restrict__ rec_ni)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t chunk = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (chunk >= n_chunks) return;
     const int64_t c0 = chunk * CHUNK, c1 = min(c0 + (int64_t)CHUNK, n_ops);
     const int64_t g0 = c0 + (int64_t)lane * OPS_PER_LANE;
     const int64_t rem = n_ops - g0;
@@ -586,9 +615,6 @@ cigar_count_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, 
 #pragma unroll
     for (int j = 0; j < OPS_PER_LANE; j++) op[j] = 0;
     if (nvalid > 0) load_lane_ops(ops, g0, op);
-    int32_t rec_lo = 0;
-    if (lane == 0) { rec_lo = find_rec(rv.op_off, rv.n_rec, c0); chunk_rec[chunk] = rec_lo; }
-    rec_lo = __shfl_sync(FULL, rec_lo, 0);
     const int64_t rec_end = __ldg(rv.op_off + rec_lo + 1);
     unsigned long long ns = 0, ni = 0, ra = 0;
     if (rec_end >= c1) {   // the whole chunk lies in one record (warp-uniform): padding ops are zero and count nothing
@@ -600,67 +626,104 @@ cigar_count_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, 
             ra += ((REF_ADV_MASK >> code) & 1u) ? len : 0u;
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            ns += __shfl_xor_sync(FULL, ns, d); ni += __shfl_xor_sync(FULL, ni, d); ra += __shfl_xor_sync(FULL, ra, d);
-        }
-        if (lane == 0) {
+        for (int d = 16; d > 0; d >>= 1) { ns += __shfl_xor_sync(FULL, ns, d); ni += __shfl_xor_sync(FULL, ni, d); }
+        if (lane == 0) {    // (merging the sums of a CTA's chunks in shared memory before the atomics was measured: 0.084 ms against 0.043)
             if (ns) atomicAdd(rec_ns + rec_lo, ns);
             if (ni) atomicAdd(rec_ni + rec_lo, ni);
         }
-    } else {
-        if (nvalid > 0) {
-            int32_t rec = g0 >= rec_end ? find_rec(rv.op_off, rv.n_rec, g0) : rec_lo;
-            int64_t next_off = __ldg(rv.op_off + rec + 1);
+    } else if (nvalid > 0) {
+        int32_t rec = g0 >= rec_end ? find_rec(rv.op_off, rv.n_rec, g0) : rec_lo;
+        int64_t next_off = __ldg(rv.op_off + rec + 1);
 #pragma unroll
-            for (int j = 0; j < OPS_PER_LANE; j++) {
-                if (j < nvalid) {
-                    const int64_t g = g0 + j;
-                    if (g >= next_off) {
-                        if (ns) atomicAdd(rec_ns + rec, ns);
-                        if (ni) atomicAdd(rec_ni + rec, ni);
-                        ns = 0; ni = 0;
-                        while (g >= next_off) { ++rec; next_off = __ldg(rv.op_off + rec + 1); }
-                    }
-                    const uint32_t code = op[j] & 15u, len = op[j] >> 4;
-                    ns += (code == PAVGPU_OP_X) ? len : 0u;
-                    ni += (code == PAVGPU_OP_I || code == PAVGPU_OP_D) ? 1u : 0u;
-                    ra += ((REF_ADV_MASK >> code) & 1u) ? len : 0u;
+        for (int j = 0; j < OPS_PER_LANE; j++) {
+            if (j < nvalid) {
+                const int64_t g = g0 + j;
+                if (g >= next_off) {
+                    if (ns) atomicAdd(rec_ns + rec, ns);
+                    if (ni) atomicAdd(rec_ni + rec, ni);
+                    ns = 0; ni = 0;
+                    while (g >= next_off) { ++rec; next_off = __ldg(rv.op_off + rec + 1); }
                 }
+                const uint32_t code = op[j] & 15u, len = op[j] >> 4;
+                ns += (code == PAVGPU_OP_X) ? len : 0u;
+                ni += (code == PAVGPU_OP_I || code == PAVGPU_OP_D) ? 1u : 0u;
+                ra += ((REF_ADV_MASK >> code) & 1u) ? len : 0u;
             }
-            if (ns) atomicAdd(rec_ns + rec, ns);
-            if (ni) atomicAdd(rec_ni + rec, ni);
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) ra += __shfl_xor_sync(FULL, ra, d);
+        if (ns) atomicAdd(rec_ns + rec, ns);
+        if (ni) atomicAdd(rec_ni + rec, ni);
     }
-    if (lane == 0 && ra) atomicAdd(span_total, ra);
+    return ra;
 }
 
-// In-place exclusive scan of the two per-record count arrays (n_rec entries each, totals written to [n_rec]); one CTA.
-__global__ void __launch_bounds__(SCAN_THREADS)
-rec_scan_kernel(unsigned long long *__restrict__ a, unsigned long long *__restrict__ b, int32_t n_rec)
+#ifndef COUNT_CPW_N
+#define COUNT_CPW_N 4
+#endif
+constexpr int COUNT_CPW = COUNT_CPW_N;    // consecutive chunks per warp: a warp's chain of dependent loads (chunk -> record -> record end) and
+                                          // its atomics are paid once per COUNT_CPW chunks when they all lie in one record (the common case)
+template <bool SPAN>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+cigar_count_kernel(const uint32_t *__restrict__ ops, int64_t n_ops, RecView rv, int64_t n_chunks, const int32_t *__restrict__ chunk_rec,
+                   unsigned long long *__restrict__ rec_ns, unsigned long long *__restrict__ rec_ni, unsigned long long *__restrict__ span_total,
+                   ulonglong2 *__restrict__ desc, unsigned long long *__restrict__ first_illegal, unsigned int *__restrict__ done)
 {
-    __shared__ unsigned long long s_a[SCAN_THREADS], s_b[SCAN_THREADS];
-    const int t = threadIdx.x;
-    const int32_t per = (n_rec + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int32_t lo = min(t * per, n_rec), hi = min(lo + per, n_rec);
-    unsigned long long sa = 0, sb = 0;
-    for (int32_t r = lo; r < hi; r++) { sa += a[r]; sb += b[r]; }
-    s_a[t] = sa; s_b[t] = sb;
+    const int lane = threadIdx.x & 31;
+    const int64_t first = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * COUNT_CPW;
+    if (first < n_chunks) {
+        const int nck = (int)min((int64_t)COUNT_CPW, n_chunks - first);
+        if (lane < nck) desc[first + lane] = make_ulonglong2(0ull, 0ull);
+        if (first == 0 && lane == 0) *first_illegal = ~0ull;
+        const int32_t rec_lo = __ldg(chunk_rec + first);
+        const int64_t rec_end = __ldg(rv.op_off + rec_lo + 1);
+        const int64_t grp_end = min((first + nck) * (int64_t)CHUNK, n_ops);
+        unsigned long long ra = 0;
+        if (rec_end >= grp_end) {     // all chunks of the group in one record: every load in flight at once, one reduction, one pair of atomics
+            uint32_t op[COUNT_CPW][OPS_PER_LANE];
+#pragma unroll
+            for (int k = 0; k < COUNT_CPW; k++) {
+#pragma unroll
+                for (int j = 0; j < OPS_PER_LANE; j++) op[k][j] = 0;
+                const int64_t g0 = (first + k) * (int64_t)CHUNK + (int64_t)lane * OPS_PER_LANE;
+                if (k < nck && g0 < n_ops) load_lane_ops(ops, g0, op[k]);      // (the ops array is padded to whole chunks with zeros)
+            }
+            unsigned long long ns = 0, ni = 0;
+#pragma unroll
+            for (int k = 0; k < COUNT_CPW; k++) {
+#pragma unroll
+                for (int j = 0; j < OPS_PER_LANE; j++) {
+                    const uint32_t code = op[k][j] & 15u, len = op[k][j] >> 4;
+                    ns += (code == PAVGPU_OP_X) ? len : 0u;
+                    ni += (code == PAVGPU_OP_I || code == PAVGPU_OP_D) ? 1u : 0u;
+                    if (SPAN) ra += ((REF_ADV_MASK >> code) & 1u) ? len : 0u;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { ns += __shfl_xor_sync(FULL, ns, d); ni += __shfl_xor_sync(FULL, ni, d); }
+            if (lane == 0) {
+                if (ns) atomicAdd(rec_ns + rec_lo, ns);
+                if (ni) atomicAdd(rec_ni + rec_lo, ni);
+            }
+        } else {
+            for (int k = 0; k < nck; k++) ra += count_one_chunk(ops, n_ops, rv, first + k, __ldg(chunk_rec + first + k), lane, rec_ns, rec_ni);
+        }
+        if (SPAN) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) ra += __shfl_xor_sync(FULL, ra, d);
+            if (lane == 0 && ra) atomicAdd(span_total, ra);
+        }
+    }
+    // the last CTA to finish turns the per-record counts into exclusive offsets (was a second, single-CTA launch)
+    __shared__ bool s_last;
     __syncthreads();
-    for (int d = 1; d < SCAN_THREADS; d <<= 1) {
-        const unsigned long long va = t >= d ? s_a[t - d] : 0ull, vb = t >= d ? s_b[t - d] : 0ull;
-        __syncthreads();
-        s_a[t] += va; s_b[t] += vb;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
     }
-    unsigned long long ea = t > 0 ? s_a[t - 1] : 0ull, eb = t > 0 ? s_b[t - 1] : 0ull;
-    for (int32_t r = lo; r < hi; r++) {
-        const unsigned long long ca = a[r], cb = b[r];
-        a[r] = ea; b[r] = eb;
-        ea += ca; eb += cb;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        rec_scan_block(rec_ns, rec_ni, rv.n_rec);
     }
-    if (t == SCAN_THREADS - 1) { a[n_rec] = s_a[t]; b[n_rec] = s_b[t]; }
 }
 
 // K4 ---------------------------------------------------------------------------------------------
@@ -1196,11 +1259,11 @@ struct pavgpu_cigar_batch {
     int64_t n_snv, n_indel;
     bool sized;                          // row buffers (single-pass) / scan scratch (multi-pass) allocated
     bool cnt_valid;                      // the device count has run: totals known
-    int64_t cnt_n_snv, cnt_n_indel;      // row totals from the device count (cigar_count_kernel + rec_scan_kernel)
+    int64_t cnt_n_snv, cnt_n_indel;      // row totals from the device count (cigar_count_kernel)
     int64_t ref_span;                    // reference bases the records advance over (same pass): indel density picks the homology kernel
     ulonglong2 *d_desc;
     int64_t *d_rec_snv_off, *d_rec_indel_off;   // per-record row counts -> first row slot of every record (device-built, n_rec + 1 entries)
-    int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (device-built)
+    int32_t *d_chunk_rec;                        // record of the first op of every 256-op chunk (from op_off, uploaded with the batch)
     RecDesc *d_recdesc;                          // per-record constants of the current (ref_store, qry_store) pair
     uint64_t recdesc_ref_uid, recdesc_qry_uid;   // stores the table was built for (0 = none yet)
     std::vector<RecDesc> h_recdesc;
@@ -1430,8 +1493,9 @@ static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_i
     const size_t nc = (size_t)std::max<int64_t>(b->n_chunks, 1), nr = (size_t)std::max(n_rec, 1);
     ArenaPlan ap;
     const size_t o_ref_id = ap.add(nr * 4), o_qry_id = ap.add(nr * 4), o_pos = ap.add(nr * 4), o_rev = ap.add(nr), o_op_off = ap.add((nr + 1) * 8);
-    const size_t o_ops = ap.add(ops_padded * 4), o_totals = ap.add(32), o_illegal = ap.add(8), o_desc = ap.add(nc * sizeof(ulonglong2));
-    const size_t o_rso = ap.add((nr + 1) * 8), o_rio = ap.add((nr + 1) * 8), o_crec = ap.add(nc * 4), o_rdesc = ap.add(nr * sizeof(RecDesc));
+    const size_t o_ops = ap.add(ops_padded * 4), o_illegal = ap.add(8), o_desc = ap.add(nc * sizeof(ulonglong2));
+    const size_t o_rso = ap.add((nr + 1) * 8), o_rio = ap.add((nr + 1) * 8), o_totals = ap.add(32);   // (cleared together: launch_count)
+    const size_t o_crec = ap.add(nc * 4), o_rdesc = ap.add(nr * sizeof(RecDesc));
     int rc = [&]() -> int {
         cudaStream_t st = ctx->stream;
         cudaError_t e = pav_dev_alloc(ctx, ap.off, &b->d_arena);
@@ -1451,6 +1515,18 @@ static int batch_create(pavgpu_ctx *ctx, int32_t n_rec, const int32_t *ref_seq_i
             CUDA_TRY(cudaMemcpyAsync(b->d_rev, rev, (size_t)n_rec, cudaMemcpyHostToDevice, st));
         }
         CUDA_TRY(cudaMemcpyAsync(b->d_op_off, op_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+        // record of every chunk's first op: a merge of the chunk grid with the record offsets, O(records + chunks) on the host -- no op
+        // is looked at (the count kernel found it by binary search per chunk: ten dependent loads at the head of every warp)
+        std::vector<int32_t> h_chunk_rec((size_t)b->n_chunks);
+        {
+            int32_t r = 0;
+            for (int64_t c = 0; c < b->n_chunks; c++) {
+                const int64_t g = c * CHUNK;
+                while (r + 1 < n_rec && op_off[r + 1] <= g) r++;
+                h_chunk_rec[(size_t)c] = r;
+            }
+        }
+        if (b->n_chunks) CUDA_TRY(cudaMemcpyAsync(b->d_chunk_rec, h_chunk_rec.data(), (size_t)b->n_chunks * 4, cudaMemcpyHostToDevice, st));
         if (n_ops) CUDA_TRY(cudaMemcpyAsync(b->d_ops, ops, (size_t)n_ops * 4, cudaMemcpyHostToDevice, st));
         if (ops_padded > (size_t)n_ops)   // lanes always load whole vectors: zero the tail of the last chunk
             CUDA_TRY(cudaMemsetAsync(b->d_ops + n_ops, 0, (ops_padded - (size_t)n_ops) * 4, st));
@@ -1566,18 +1642,16 @@ static int launch_homology(pavgpu_cigar_batch *b, cudaStream_t st, const pavgpu_
 }
 
 // Row counts on the device (K0a + K0b): per-record counts -> exclusive offsets in place, chunk -> record index, reference span.
-static int launch_count(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv)
+static int launch_count(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv, bool span = false)
 {
-    CUDA_TRY(cudaMemsetAsync(b->d_rec_snv_off, 0, (size_t)(b->n_rec + 1) * 8, st));
-    CUDA_TRY(cudaMemsetAsync(b->d_rec_indel_off, 0, (size_t)(b->n_rec + 1) * 8, st));
-    CUDA_TRY(cudaMemsetAsync(b->d_totals, 0, 32, st));
-    const unsigned blocks = (unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    cigar_count_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec,
-                                                                 reinterpret_cast<unsigned long long *>(b->d_rec_snv_off),
-                                                                 reinterpret_cast<unsigned long long *>(b->d_rec_indel_off),
-                                                                 reinterpret_cast<unsigned long long *>(b->d_totals + 2));
-    rec_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(reinterpret_cast<unsigned long long *>(b->d_rec_snv_off),
-                                                 reinterpret_cast<unsigned long long *>(b->d_rec_indel_off), b->n_rec);
+    // the two per-record count arrays and the totals are neighbours in the arena: one memset
+    CUDA_TRY(cudaMemsetAsync(b->d_rec_snv_off, 0, (size_t)(reinterpret_cast<char *>(b->d_totals) + 32 - reinterpret_cast<char *>(b->d_rec_snv_off)), st));
+    const unsigned blocks = (unsigned)((b->n_chunks + WARPS_PER_BLOCK * COUNT_CPW - 1) / (WARPS_PER_BLOCK * COUNT_CPW));
+    auto kern = span ? cigar_count_kernel<true> : cigar_count_kernel<false>;
+    kern<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, reinterpret_cast<unsigned long long *>(b->d_rec_snv_off),
+                                                  reinterpret_cast<unsigned long long *>(b->d_rec_indel_off),
+                                                  reinterpret_cast<unsigned long long *>(b->d_totals + 2), b->d_desc, b->d_first_illegal,
+                                                  reinterpret_cast<unsigned int *>(b->d_totals + 3));   // ([3]: CTAs done, cleared with the totals)
     CUDA_TRY(cudaGetLastError());
     return PAVGPU_OK;
 }
@@ -1587,8 +1661,7 @@ static int launch_walk_homology(pavgpu_cigar_batch *b, cudaStream_t st, const Re
                                 const pavgpu_seqstore *qry_store)
 {
     pavgpu_ctx *ctx = b->ctx;
-    CUDA_TRY(cudaMemsetAsync(b->d_first_illegal, 0xFF, 8, st));
-    CUDA_TRY(cudaMemsetAsync(b->d_desc, 0, sizeof(ulonglong2) * (size_t)b->n_chunks, st));
+    // (the look-back descriptors and the first-illegal-op cell were reset by cigar_count_kernel, which always runs before this)
     cigar_walk_kernel<<<(unsigned)((b->n_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(
         b->d_ops, b->n_ops, rv, b->n_chunks, b->d_chunk_rec, b->d_desc, b->d_recdesc, b->d_rec_snv_off, b->d_rec_indel_off, b->d_snv, b->d_stub,
         b->d_first_illegal, reinterpret_cast<unsigned long long *>(b->d_totals));
@@ -1606,7 +1679,7 @@ static int size_rows(pavgpu_cigar_batch *b, cudaStream_t st, const RecView &rv, 
 {
     pavgpu_ctx *ctx = b->ctx;
     if (count) {   // (the multi-pass walk sizes its row buffers from its own scan)
-        int rc = launch_count(b, st, rv);
+        int rc = launch_count(b, st, rv, true);
         if (rc) return rc;
         int64_t tot[3] = {0, 0, 0};
         CUDA_TRY(cudaMemcpyAsync(&tot[0], b->d_rec_snv_off + b->n_rec, 8, cudaMemcpyDeviceToHost, st));
@@ -1678,7 +1751,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
         int rc = size_rows(b, st, rv, b->fused);   // single-pass walk: count + record scan + a 24-byte read-back, once per batch
         if (rc) return rc;
         counted_now = b->cnt_valid;
-        launches += counted_now ? 2 : 0;
+        launches += counted_now ? 1 : 0;
     }
     if (b->n_chunks > 0 && b->fused) {
         b->n_snv = b->cnt_n_snv; b->n_indel = b->cnt_n_indel;
@@ -1723,7 +1796,7 @@ extern "C" __attribute__((visibility("default"))) int pavgpu_cigar_batch_run(pav
                 rc = launch_walk_homology(b, st, rv, ref_store, qry_store);
                 if (rc) return rc;
             }
-            launches += 3 + (b->n_indel > 0 ? (b->gexec && used_graph ? b->g_hom_launches : b->hom_launches) : 0);
+            launches += 2 + (b->n_indel > 0 ? (b->gexec && used_graph ? b->g_hom_launches : b->hom_launches) : 0);
         }
         CUDA_TRY(cudaEventRecord(ctx->ev[4], st));
         int64_t tot[2];
