@@ -306,6 +306,39 @@ def reference_walk_step(tasks, cores):
     return int(sum(counts)), dt
 
 
+def _port_shard(task):
+    """The oracle's C restatement of the walk + the reference's own container idiom for the frames (pd.Series per variant, concat):
+    the `port` figure kept beside the reference's (round 1's CPU arm)."""
+    bed, rows, ref_fa, tig_fa, hap = task
+    from oracle import pyoracle
+    df = read_align(bed).iloc[rows]
+    a, b = pyoracle.make_insdel_snv_calls(df, ref_fa, tig_fa, hap, version_id=False, reference_containers=True)
+    return len(a) + len(b)
+
+
+def port_walk_step(tasks, cores):
+    pool = _pool(cores)
+    t0 = time.perf_counter()
+    counts = pool.map(_port_shard, tasks, chunksize=1)
+    dt = time.perf_counter() - t0
+    return int(sum(counts)), dt
+
+
+def _port_density(w):
+    from oracle import pyoracle
+    rc, _ = pyoracle.density_arrays(w[0].tobytes(), w[1].tobytes())
+    return rc
+
+
+def port_density(windows, cores):
+    """The oracle's C restatement of scripts/density.py, one window per worker. Returns (Gbases/s, seconds)."""
+    pool = _pool(cores)
+    t0 = time.perf_counter()
+    pool.map(_port_density, windows, chunksize=1)
+    dt = time.perf_counter() - t0
+    return sum(len(w[1]) for w in windows) / dt / 1e9, dt
+
+
 def reference_density(windows, tmp, cores):
     """scripts/density.py per window, spawned like pavlib/inv.py:249-266 (-t 1), ``cores`` processes at a time. Returns
     (Gbases/s, seconds, start-up seconds per process, return codes)."""
@@ -384,24 +417,34 @@ def run_reference(args, rank, world):
     sample = (f'{len(tasks)} of {sum(info["records"].values())} C3 records (seeded sample, one per worker process; {rows} variant rows per step): FASTA read '
               f'by .fai offset + the reference\'s own make_insdel_snv_calls (pavlib/cigarcall.py:24-362, unmodified, oracle/_ref) per step; '
               f'{len(vals)} timed steps')
+    # the port figure beside it: the oracle's C walk + reference-style frame assembly on the same sample, same pool
+    from oracle import pyoracle
+    pyoracle.build()
+    p_rows, p_dt = port_walk_step(tasks, cores)
+    port = {'value': p_rows / p_dt, 'unit': UNIT, 'kind': 'port', 'seconds': p_dt,
+            'what': 'oracle/pav_oracle.c walk + the reference\'s container idiom for the frames (pd.Series per variant + concat), same records, same pool'}
+    log(f'[reference] port on the same sample: {p_rows} rows in {p_dt:.2f}s -> {p_rows / p_dt:.0f} rows/s')
     sec = None
     if args.c5_windows > 0:
         n_w = min(args.cpu_density_windows or max(64, cores), args.c5_windows)
         wins = c5_windows_range(1005, 0, n_w)
         gb, dt, startup, rcs = reference_density(wins, tmp, cores)
+        pgb, pdt = port_density(wins, cores)
         sec = {'impl': 'reference', 'metric': METRIC_B, 'value': gb, 'unit': UNIT_B, 'seconds': dt, 'cores': cores,
                'config': {'workload': workload_c5(args, args.gpus)},
                'cpu_baseline': {'value': gb, 'unit': UNIT_B, 'cores': cores, 'kind': 'reference',
                                 'sample': f'first {n_w} of {args.c5_windows} C5 windows, one `python3 scripts/density.py ... -t 1` process per window '
                                           f'(spawned like pavlib/inv.py:249-266), {cores} at a time; interpreter + import start-up ({startup:.2f}s per '
                                           f'process, measured separately) is inside the time',
-                                'startup_seconds_per_process': startup, 'return_codes': {str(c): rcs.count(c) for c in set(rcs)}}}
+                                'startup_seconds_per_process': startup, 'return_codes': {str(c): rcs.count(c) for c in set(rcs)},
+                                'port': {'value': pgb, 'unit': UNIT_B, 'kind': 'port', 'seconds': pdt,
+                                         'what': 'oracle/pav_oracle.c restatement of scripts/density.py, same windows, one per worker, in-process'}}}
         log(f'[reference] density: {n_w} windows in {dt:.1f}s = {gb:.3e} Gbases/s on {cores} cores (start-up {startup:.2f}s per process)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
         'config': {'workload': workload_c3(args, args.gpus), 'reference_bp': info['reference_bp'], 'records': info['records']},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': min(cores, len(tasks)), 'kind': 'reference', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': min(cores, len(tasks)), 'kind': 'reference', 'sample': sample, 'port': port},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'secondary': sec,
     }
@@ -946,6 +989,11 @@ def cpu_baseline_ours(args, tmp, info):
     a = {'value': rows / dt, 'unit': UNIT, 'cores': min(cores, len(tasks)), 'kind': 'reference',
          'sample': f'{len(tasks)} of {sum(info["records"].values())} C3 records (seeded sample, one per worker process; {rows} variant rows, {dt:.1f}s): the unmodified '
                    'reference\'s make_insdel_snv_calls (oracle/_ref/pavlib/cigarcall.py), FASTA read by .fai offset'}
+    try:      # the port figure beside it (oracle C walk + reference-style frame assembly, same records, same pool)
+        p_rows, p_dt = port_walk_step(tasks, cores)
+        a['port'] = {'value': p_rows / p_dt, 'unit': UNIT, 'kind': 'port', 'seconds': p_dt}
+    except Exception as ex:  # noqa: BLE001
+        log('port walk leg failed:', repr(ex))
     b = None
     if args.c5_windows > 0:
         n_w = min(args.cpu_density_windows or cores, args.c5_windows)
@@ -954,6 +1002,11 @@ def cpu_baseline_ours(args, tmp, info):
              'sample': f'first {n_w} of {args.c5_windows} C5 windows, one `python3 scripts/density.py ... -t 1` process per window (pavlib/inv.py:249-266), '
                        f'{cores} at a time, {dt:.1f}s; start-up ({startup:.2f}s per process, measured separately) is inside the time',
              'startup_seconds_per_process': startup}
+        try:
+            pgb, pdt = port_density(c5_windows_range(1005, 0, n_w), cores)
+            b['port'] = {'value': pgb, 'unit': UNIT_B, 'kind': 'port', 'seconds': pdt}
+        except Exception as ex:  # noqa: BLE001
+            log('port density leg failed:', repr(ex))
     return a, b
 
 

@@ -24,5 +24,7 @@ def test_reference_arm_json_line():
     sec = d['secondary']                                                                       # Path B: scripts/density.py per window
     assert sec['metric'] == 'inv_kmer_density_gbases_per_sec' and sec['value'] > 0 and sec['cpu_baseline']['kind'] == 'reference'
     assert sec['cpu_baseline']['startup_seconds_per_process'] > 0
+    assert d['cpu_baseline']['port']['kind'] == 'port' and d['cpu_baseline']['port']['value'] > 0      # the oracle port beside the reference
+    assert sec['cpu_baseline']['port']['value'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']
