@@ -63,7 +63,9 @@ def chrom_shards(df_align, n_shards):
     suffixes never cross shards, and the per-shard tables concatenate into the whole table (``merge_shard_frames``). This is the
     split to use when every rank formats its own rows -- the reference's model of one job per batch of records
     (CALL_BATCH, rules/align.snakefile:163; tables merged by rule call_cigar_merge) with the batch key changed from INDEX % 10 to
-    the chromosome. ``make_insdel_snv_calls_dist`` (records over ranks, one merged table on rank 0) is the other one."""
+    the chromosome. ``make_insdel_snv_calls_dist`` (records over ranks, one merged table on rank 0) is the other one.
+    With fewer chromosomes than ranks the surplus ranks get empty shards (and return empty tables): a human reference keeps 8 GPUs
+    busy (24 chromosomes, chr1 is 8 % of the genome), a 4-chromosome input does not -- shard that one by record."""
     chrom = df_align['#CHROM'].to_numpy(dtype=object)
     span = (df_align['END'].to_numpy(dtype=np.int64) - df_align['POS'].to_numpy(dtype=np.int64)) if 'END' in df_align.columns else None
     cost = record_costs(df_align['CIGAR'].tolist(), span)

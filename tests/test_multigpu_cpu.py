@@ -125,3 +125,13 @@ def test_chrom_shards_partition_by_reference_sequence():
         cost = multigpu.record_costs(df['CIGAR'].tolist(), (df['END'] - df['POS']).to_numpy())
         load = np.array([cost[s].sum() for s in shards])
         assert load.max() <= 1.15 * load.mean(), (world, load)
+    # more ranks than chromosomes: the surplus ranks get empty shards, nothing is lost
+    small = df.loc[df['#CHROM'].isin(['chr1', 'chr2', 'chr3'])].reset_index(drop=True)
+    shards = multigpu.chrom_shards(small, 8)
+    assert sum(1 for s_ in shards if len(s_)) == 3 and sorted(np.concatenate(shards).tolist()) == list(range(len(small)))
+    import pandas as pd
+    empty = (pd.DataFrame({'#CHROM': []}), pd.DataFrame({'#CHROM': []}))
+    part = (pd.DataFrame({'#CHROM': ['b', 'a', 'a'], 'POS': [5, 1, 9]}), pd.DataFrame({'#CHROM': ['a'], 'POS': [3]}))
+    snv, ins = multigpu.merge_shard_frames([empty, part, empty])
+    assert snv['#CHROM'].tolist() == ['a', 'a', 'b'] and snv['POS'].tolist() == [1, 9, 5] and ins['POS'].tolist() == [3]
+    assert multigpu.merge_shard_frames([empty, empty])[0].shape[0] == 0
