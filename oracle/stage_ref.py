@@ -48,7 +48,8 @@ def stage(force=False):
     if not force and os.path.exists(man_path):
         try:
             man = json.load(open(man_path))
-            if all(os.path.exists(os.path.join(DST, f)) for f in man['files']):
+            wanted = [f for f in FILES if os.path.exists(os.path.join(SRC, f))]
+            if all(os.path.exists(os.path.join(DST, f)) for f in man['files']) and all(f in man['files'] for f in wanted):
                 return man
         except Exception:  # noqa: BLE001
             pass
