@@ -28,3 +28,23 @@ def test_reference_arm_json_line():
     assert sec['cpu_baseline']['port']['value'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']
+
+
+def test_bench_helpers():
+    """Pure helpers of bench.py: the byte model per kernel, the gather floor from the committed microbenchmark, the LPT plan."""
+    import importlib.util
+
+    import numpy as np
+    import pandas as pd
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(REPO, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    k = bench.kernel_table(0.02, 0.04, 0.07, 4, 1000, 4, 300, 50)
+    assert k['homology_queue_kernel'] == (0.07, 256 * 50) and k['cigar_walk_kernel'][1] == 4 * 1000 + 32 * 4 + 16 * 300 + 64 * 50
+    g = bench.gather_bound(370_433, 0.0727)
+    assert g is not None and 40 < g['peak_gaccesses_per_s'] < 60 and 0.03 < g['floor_ms'] < 0.045 and 0.4 < g['frac'] < 0.7
+    rng = np.random.default_rng(3)
+    dfs = {h: pd.DataFrame({'POS': 0, 'END': rng.integers(10_000, 5_000_000, 40), 'CIGAR': ['10=' * int(n) for n in rng.integers(1, 400, 40)]}) for h in ('h1', 'h2')}
+    plan = bench.shard_plan(dfs, 4)
+    for h in dfs:
+        assert sorted(np.concatenate(plan[h]).tolist()) == list(range(40))
