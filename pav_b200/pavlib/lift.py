@@ -111,13 +111,16 @@ class AlignLift:
         """``device.LiftIndex`` over every record of the table, built on first use; ``None`` when a record has an op the lift does not
         handle (the per-point path then raises for that record when -- and only when -- it is looked at, like the reference)."""
         if self._dev_index is None:
-            ops, op_off, perr = device.parse_cigars(self._cigar.tolist())
-            if perr.code != 0:
-                self._dev_index = False
-            else:
-                qlen = np.array([int(self.df_fai[q]) for q in self._qid.tolist()], dtype=np.int64)
-                idx = device.LiftIndex(device.get_context(), ops, op_off, self._pos, np.asarray(self._rev, dtype=bool).astype(np.uint8), qlen)
-                self._dev_index = idx if idx.bad_rec < 0 else False
+            self._dev_index = False
+            try:
+                ops, op_off, perr = device.parse_cigars(self._cigar.tolist())
+                if perr.code == 0:
+                    qlen = np.array([int(self.df_fai[q]) for q in self._qid.tolist()], dtype=np.int64)
+                    idx = device.LiftIndex(device.get_context(), ops, op_off, self._pos, np.asarray(self._rev, dtype=bool).astype(np.uint8), qlen)
+                    if idx.bad_rec < 0:
+                        self._dev_index = idx
+            except Exception:  # noqa: BLE001  (a contig missing from the .fai, a malformed CIGAR, no device: the per-point path reports what is
+                pass           #  wrong for the record that is actually looked at, like the reference; the lift is host logic either way)
         return self._dev_index or None
 
     def lift_points(self, ids, coords, to_qry, gap=False):
