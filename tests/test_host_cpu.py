@@ -487,3 +487,26 @@ def test_read_sequences_splits_large_records_across_jobs(tmp_path):
         assert len(futs) > len(seqs) // 2
         for nm, a in zip(seqs, out):
             assert np.array_equal(a, seqs[nm]), (nm, strip_newline)
+
+
+def test_record_stats_host_agree_with_count_cigar():
+    """The per-record sums get_align_bed uses (align._record_stats_host, the host twin of pavgpu_cigar_record_stats) against
+    count_cigar on well-formed records: aligned spans and clips must tell the same story."""
+    from pav_b200 import device
+    from pav_b200.pavlib import align
+    rng = np.random.default_rng(8)
+    cigars = []
+    for _ in range(400):
+        body = ''.join('%d%s' % (int(rng.integers(1, 3000)), '=XID'[int(rng.integers(0, 4))]) for _ in range(int(rng.integers(1, 60))))
+        body = '7=' + body + '3='          # (aligned ends, so that clips sit next to aligned bases)
+        lead = ['', '5H', '7S', '3H9S'][int(rng.integers(0, 4))]
+        tail = ['', '4S', '6H', '8S1H'][int(rng.integers(0, 4))]
+        cigars.append(lead + body + tail)
+    ops, op_off, perr = device.parse_cigars(cigars)
+    assert perr.code == 0
+    st = align._record_stats_host((ops & 15).astype(np.int64), (ops >> 4).astype(np.int64), op_off)
+    for c, s_ in zip(cigars, st):
+        ref_bp, tig_bp, h_l, s_l, h_r, s_r = align.count_cigar(c)
+        assert (int(s_['ref_bp']), int(s_['qry_bp'])) == (ref_bp, tig_bp), c
+        assert int(s_['lead']) == h_l + s_l and int(s_['trail']) == h_r + s_r and int(s_['clip_h_first']) == h_l and int(s_['lead_s']) == s_l, c
+        assert int(s_['flags']) == 0 and s_['first_body'] >= 0
