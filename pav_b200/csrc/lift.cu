@@ -14,21 +14,12 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "liftcore.cuh"
 
 namespace {
 
 constexpr int LP_THREADS = 256;
 constexpr int LP_ITEMS = 4;
-
-__device__ __forceinline__ void op_advance(uint32_t op, long long &ra, long long &qa, unsigned &bad)
-{
-    const uint32_t code = op & 15u;
-    const long long len = op >> 4;
-    const bool m = code == PAVGPU_OP_M || code == PAVGPU_OP_EQ || code == PAVGPU_OP_X;
-    ra = (m || code == PAVGPU_OP_D) ? len : 0;
-    qa = (m || code == PAVGPU_OP_I || code == PAVGPU_OP_S || code == PAVGPU_OP_H) ? len : 0;
-    if (!(m || code == PAVGPU_OP_I || code == PAVGPU_OP_D || code == PAVGPU_OP_S || code == PAVGPU_OP_H)) bad = 1u;
-}
 
 // One CTA per record: exclusive prefix sums of the reference / contig advances of its ops, POS added to the reference one.
 __global__ void __launch_bounds__(LP_THREADS)
@@ -49,7 +40,7 @@ lift_prefix_kernel(const uint32_t *__restrict__ ops, const int64_t *__restrict__
 #pragma unroll
         for (int k = 0; k < LP_ITEMS; k++) {
             ra[k] = qa[k] = 0;
-            if (i0 + k < n) op_advance(ops[o0 + i0 + k], ra[k], qa[k], bad);
+            if (i0 + k < n) lift_op_advance(ops[o0 + i0 + k], ra[k], qa[k], bad);
             tr += ra[k]; tq += qa[k];
         }
         long long ir = tr, iq = tq;
@@ -75,17 +66,6 @@ lift_prefix_kernel(const uint32_t *__restrict__ ops, const int64_t *__restrict__
     if (__syncthreads_or((int)bad) && threadIdx.x == 0) atomicMin(bad_rec, r);
 }
 
-// Last op k of [lo, hi) with start[k] <= p, or lo - 1.
-__device__ __forceinline__ int64_t last_le(const int64_t *__restrict__ start, int64_t lo, int64_t hi, int64_t p)
-{
-    int64_t a = lo, b = hi;
-    while (a < b) {
-        const int64_t m = (a + b) >> 1;
-        if (start[m] <= p) a = m + 1; else b = m;
-    }
-    return a - 1;
-}
-
 __global__ void __launch_bounds__(128)
 lift_points_kernel(const uint32_t *__restrict__ ops, const int64_t *__restrict__ op_off, const int64_t *__restrict__ ref_start,
                    const int64_t *__restrict__ qry_start, const uint8_t *__restrict__ rev, const int64_t *__restrict__ qry_len, int32_t n,
@@ -94,39 +74,9 @@ lift_points_kernel(const uint32_t *__restrict__ ops, const int64_t *__restrict__
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int32_t r = rec[t];
-    const int64_t lo = op_off[r], hi = op_off[r + 1];
-    int64_t p = coord[t];
-    const int64_t *start = to_qry ? ref_start : qry_start;
-    const int64_t *image = to_qry ? qry_start : ref_start;
-    if (!to_qry && rev[r]) p = qry_len[r] - p;
-    // the block containing p: the last op starting at or before p that advances in the source coordinate, if p is inside it and it is
-    // a block of the lift (reference -> contig: M = X D; contig -> reference: M = X I -- clips advance the contig but lift nothing)
-    auto find = [&](int64_t q, int64_t &k, int64_t &len, bool &aligned) -> bool {
-        k = last_le(start, lo, hi, q);
-        while (k >= lo) {
-            const uint32_t op = ops[k], code = op & 15u;
-            len = op >> 4;
-            aligned = code == PAVGPU_OP_M || code == PAVGPU_OP_EQ || code == PAVGPU_OP_X;
-            const bool adv = to_qry ? (aligned || code == PAVGPU_OP_D) : (aligned || code == PAVGPU_OP_I || code == PAVGPU_OP_S || code == PAVGPU_OP_H);
-            if (adv && len > 0) {
-                const bool in_lift = to_qry ? true : (aligned || code == PAVGPU_OP_I);
-                return in_lift && q < start[k] + len;
-            }
-            k--;     // ops that do not advance here share their start with the next one: step over them
-        }
-        return false;
-    };
-    int64_t k, len; bool aligned;
-    bool ok = find(p, k, len, aligned);
-    if (!ok && !to_qry) {      // exactly the end of a block (lift.py:226-238)
-        ok = find(p - 1, k, len, aligned) && start[k] + len == p;
-    }
-    if (!ok) { out[t] = 0; status[t] = 1; return; }
-    // image interval of the block: aligned -> [image, image + len), else one base [image, image + 1)
-    const int64_t d0 = image[k], d1 = aligned ? d0 + len : d0 + 1;
-    int64_t v = (d1 - d0 > 1) ? d0 + (p - start[k]) : d1;
-    if (to_qry && rev[r]) v = qry_len[r] - v;
-    out[t] = v; status[t] = 0;
+    int64_t v = 0;
+    status[t] = lift_point(ops, ref_start, qry_start, op_off[r], op_off[r + 1], rev[r], qry_len[r], to_qry, coord[t], v);
+    out[t] = v;
 }
 
 }  // namespace

@@ -274,3 +274,122 @@ def test_staging_ranges(emu):
             assert a * 32 <= max(lo_g - M, 0) and (b * 32 >= min(hi_g + M + 33, total))    # every window within the margin has both its words staged
         else:
             assert nw.value == 0
+
+
+# ---- coordinate lifts: pav_b200/csrc/liftcore.cuh on the host -------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def lift_emu():
+    src = os.path.join(HERE, 'host_emul', 'lift_host.cpp')
+    out_dir = os.path.join(HERE, 'host_emul', '_build')
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, 'lift_host.so')
+    hdr = os.path.join(REPO, 'pav_b200', 'csrc', 'liftcore.cuh')
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(['g++', '-O1', '-std=c++17', '-shared', '-fPIC', '-Wno-unknown-pragmas', '-I', os.path.dirname(hdr), '-I', os.path.join(REPO, 'include'),
+                               '-o', so + '.tmp', src])
+        os.replace(so + '.tmp', so)
+    L = ctypes.CDLL(so)
+    L.emu_lift_prefix.argtypes = [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]
+    L.emu_lift_prefix.restype = c_i32
+    L.emu_lift_points.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]
+    return L
+
+
+class _HostLiftIndex:
+    """Stand-in for device.LiftIndex (same ``lift`` interface) running liftcore.cuh on the host."""
+
+    def __init__(self, emu, ops, op_off, pos, rev, qry_len):
+        p = lambda a: a.ctypes.data_as(c_vp)  # noqa: E731
+        self.emu, self.p = emu, p
+        self.ops, self.op_off = np.ascontiguousarray(ops, np.uint32), np.ascontiguousarray(op_off, np.int64)
+        self.rev, self.qry_len = np.ascontiguousarray(rev, np.uint8), np.ascontiguousarray(qry_len, np.int64)
+        pos = np.ascontiguousarray(pos, np.int64)
+        self.ref_start, self.qry_start = np.zeros(len(self.ops), np.int64), np.zeros(len(self.ops), np.int64)
+        self.bad_rec = emu.emu_lift_prefix(p(self.ops), p(self.op_off), len(pos), p(pos), p(self.ref_start), p(self.qry_start))
+
+    def lift(self, rec, coord, to_qry):
+        rec, coord = np.ascontiguousarray(rec, np.int32), np.ascontiguousarray(coord, np.int64)
+        out, status = np.zeros(len(rec), np.int64), np.zeros(len(rec), np.int32)
+        p = self.p
+        self.emu.emu_lift_points(p(self.ops), p(self.op_off), p(self.ref_start), p(self.qry_start), p(self.rev), p(self.qry_len), len(rec), p(rec), p(coord),
+                                 int(bool(to_qry)), p(out), p(status))
+        return out, status
+
+
+def _host_indexed(lift_emu, df, fai):
+    from pav_b200 import device
+    from pav_b200.pavlib import lift
+    al = lift.AlignLift(df, fai)
+    ops, op_off, perr = device.parse_cigars(al._cigar.tolist())
+    assert perr.code == 0
+    qlen = np.array([int(fai[q]) for q in al._qid.tolist()], np.int64)
+    idx = _HostLiftIndex(lift_emu, ops, op_off, al._pos, np.asarray(al._rev, bool).astype(np.uint8), qlen)
+    assert idx.bad_rec == -1
+    al._dev_index = idx
+    return al
+
+
+def test_liftcore_matches_reference_golden(lift_emu):
+    """The device lift arithmetic (liftcore.cuh, host build) behind AlignLift.lift_points / lift_regions_to_qry against the answers
+    of the reference's own pavlib.align.AlignLift (tests/golden/lift: 3,000 point lifts incl. gap=True and the positions it raises on,
+    400 region lifts) -- the CPU twin of tests/test_lift_gpu.py."""
+    import json
+
+    import pandas as pd
+    from pav_b200.pavlib import seq
+    d = os.path.join(REPO, 'tests', 'golden', 'lift')
+    df = pd.read_csv(os.path.join(d, 'align.bed'), sep='\t')
+    fai = pd.read_csv(os.path.join(d, 'tig.fai.tsv'), sep='\t', header=None, index_col=0)[1]
+    al = _host_indexed(lift_emu, df, fai)
+    queries = json.load(open(os.path.join(d, 'queries.json')))
+
+    def plain(x):
+        return None if x is None else [x[0], int(x[1]), bool(x[2]), int(x[3]), int(x[4]), [int(i) for i in x[5]]]
+    n = 0
+    for kind, to_qry, gap in (('to_qry', True, False), ('to_sub', False, False), ('to_sub', False, True)):
+        qs = [q for q in queries if q['f'] == kind and (kind == 'to_qry' or q['gap'] == gap)]
+        good = [q for q in qs if 'error' not in q]
+        got = al.lift_points([q['id'] for q in good], [q['pos'] for q in good], to_qry, gap=gap)
+        assert [plain(g) for g in got] == [q['result'] for q in good]
+        for q in qs:
+            if 'error' in q:
+                with pytest.raises(RuntimeError):
+                    al.lift_points([q['id']], [q['pos']], to_qry, gap=gap)
+        n += len(qs)
+    regions = [q for q in queries if q['f'] == 'region']
+    got = al.lift_regions_to_qry([seq.Region(q['chrom'], q['pos'], q['end']) for q in regions])
+    assert [None if r is None else [r.chrom, r.pos, r.end, bool(r.is_rev)] for r in got] == [q['qry'] for q in regions]
+    assert n + len(regions) == 3400
+
+
+def test_liftcore_equals_host_lifts_on_random_tables(lift_emu):
+    import pandas as pd
+    from pav_b200.pavlib import lift
+    for seed, clip in ((5, (0, 0)), (6, (40, 25)), (7, (3, 0))):
+        ref, tigs, df = synth.make_cigar_workload(seed, 2, 150_000, 9, 40_000, edit_rate=0.02, rev_frac=0.5, clip=clip)
+        df = df.reset_index(drop=True)
+        fai = pd.Series({k: len(v) for k, v in tigs.items()})
+        host = lift.AlignLift(df, fai)
+        host._dev_index = False
+        dev = _host_indexed(lift_emu, df, fai)
+        rng = np.random.default_rng(seed)
+        for to_qry in (True, False):
+            ids, coords = [], []
+            for _ in range(1500):
+                row = df.iloc[int(rng.integers(0, df.shape[0]))]
+                if to_qry:
+                    ids.append(row['#CHROM']); coords.append(int(rng.integers(row['POS'] - 20, row['END'] + 20)))
+                else:
+                    ids.append(row['QRY_ID']); coords.append(int(rng.integers(max(row['QRY_POS'] - 60, 0), row['QRY_END'] + 60)))
+            exp, bad = [], set()
+            for k, (i, c) in enumerate(zip(ids, coords)):
+                try:
+                    exp.append(host.lift_to_qry(i, c) if to_qry else host.lift_to_sub(i, c))
+                except RuntimeError:
+                    exp.append('error'); bad.add(k)
+            keep = [k for k in range(len(ids)) if k not in bad]
+            got = dev.lift_points([ids[k] for k in keep], [coords[k] for k in keep], to_qry)
+            assert got == [exp[k] for k in keep]
+            for k in sorted(bad)[:10]:
+                with pytest.raises(RuntimeError):
+                    dev.lift_points([ids[k]], [coords[k]], to_qry)
